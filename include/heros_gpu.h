@@ -1,0 +1,189 @@
+/*
+ * heros_gpu.h -- C ABI of libheros_gpu.so, the B200 (sm_100a) engine for the data-parallel hot path of the
+ * MedLabs/HEROS Covid-19 model: per-movement disease transmission over sub-location occupancy and the
+ * disease-phase progression of all agents.
+ *
+ * This is the drop-in boundary.  The reference exposes this path as Java abstract-method plug-ins of
+ * nl.tudelft.simulation:medlabs:2.1.3; a Java host binds the functions below through the Panama Foreign Function &
+ * Memory API (java.lang.foreign.Linker.downcallHandle) -- see INTEGRATION.md for the binding class.  Each entry
+ * point names the reference interface it replaces (paths relative to /root/reference/src/main/java/eu/heros/).
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = HEROS_OK, < 0 = error; heros_last_error() returns a description.
+ *     No C++ exception and no exit() crosses the ABI.
+ *   - all times are fp64 simulation hours (the DSOL simulator time unit, model/HerosApplication.java:170);
+ *     person / location ids are int32 indices 0..n-1 in the order of heros_set_persons / heros_set_locations.
+ *   - host buffers are caller-owned and only read (or written, for outputs) during the call; the engine owns all
+ *     device memory.  Output buffers are caller-allocated with a capacity; the element count is returned.
+ *   - a handle is not thread-safe (matches the single DSOL simulator thread); distinct handles are independent
+ *     (one per replication / seed / GPU).
+ *   - there is no CPU fallback: heros_create fails with HEROS_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef HEROS_GPU_H
+#define HEROS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEROS_ABI_VERSION 1
+
+typedef struct heros_engine* heros_handle;
+
+enum heros_status {
+    HEROS_OK = 0,
+    HEROS_ERR_INVALID = -1,      /* bad argument / call order */
+    HEROS_ERR_CUDA = -2,         /* CUDA runtime error, or no device */
+    HEROS_ERR_UNSUPPORTED = -3,  /* configuration outside what the engine reproduces exactly */
+    HEROS_ERR_CAPACITY = -4,     /* caller buffer too small */
+    HEROS_ERR_UNKNOWN_PARAMETER = -5
+};
+
+/* generic.diseasePropertiesModel (factory/ConstructHerosModel.java:137-139) */
+enum heros_model { HEROS_MODEL_AREA = 0, HEROS_MODEL_DISTANCE = 1 };
+
+/* which movements make the medlabs engine call infectPeople (driver contract C8) */
+enum heros_trigger { HEROS_TRIGGER_EXIT_ONLY = 0, HEROS_TRIGGER_ENTER_AND_EXIT = 1 };
+
+/* disease phases, registration order of disease/Covid19Progression.java:130-137 */
+enum heros_phase {
+    HEROS_SUSCEPTIBLE = 0, HEROS_EXPOSED = 1, HEROS_INFECTED_ASYMPTOMATIC = 2, HEROS_INFECTED_SYMPTOMATIC = 3,
+    HEROS_HOSPITALIZED = 4, HEROS_ICU = 5, HEROS_DEAD = 6, HEROS_RECOVERED = 7, HEROS_N_PHASES = 8
+};
+
+typedef struct heros_config {
+    uint32_t abi_version;  /* HEROS_ABI_VERSION */
+    int32_t model;         /* heros_model */
+    int32_t trigger;       /* heros_trigger */
+    int32_t device;        /* CUDA device ordinal */
+    uint64_t seed;         /* generic.Seed; key of every Philox draw */
+    double window_hours;   /* batch window; must be <= the latent period (t_e_min / L) of the transmission model */
+} heros_config;
+
+/* covidT_area.* exactly as in the .properties file (days / seconds); converted as disease/Covid19TransmissionArea.java:63-68 */
+typedef struct heros_area_params {
+    double contagiousness, beta, t_e_min, t_e_mode, t_e_max, calculation_threshold;
+} heros_area_params;
+
+/* covidT_dist.*; converted as disease/Covid19TransmissionDistance.java:59-68 */
+typedef struct heros_dist_params {
+    double L, I, C, v_max, v_0, r, psi, alpha, mu, calculation_threshold;
+} heros_dist_params;
+
+enum heros_distribution { HEROS_DIST_CONSTANT = 0, HEROS_DIST_UNIFORM = 1, HEROS_DIST_TRIANGULAR = 2 };
+typedef struct heros_duration { int32_t kind; int32_t reserved; double a, b, c; } heros_duration; /* days */
+
+/* covidP.* (disease/Covid19Progression.java:143-173).  ConditionalProbability values are tabulated by the host as
+ * fraction[which][female][age 0..127]; which / period indices below. */
+enum { HEROS_F_ASYMPTOMATIC = 0, HEROS_F_SYMPTOMATIC_TO_HOSPITALIZED = 1, HEROS_F_HOSPITALIZED_TO_ICU = 2,
+       HEROS_F_HOSPITALIZED_TO_DEAD = 3, HEROS_F_ICU_TO_DEAD = 4, HEROS_N_FRACTIONS = 5 };
+enum { HEROS_P_INCUBATION_ASYMPTOMATIC = 0, HEROS_P_INCUBATION_SYMPTOMATIC = 1, HEROS_P_ASYMPTOMATIC_TO_RECOVERED = 2,
+       HEROS_P_SYMPTOMATIC_TO_HOSPITALIZED = 3, HEROS_P_SYMPTOMATIC_TO_RECOVERED = 4, HEROS_P_HOSPITALIZED_TO_ICU = 5,
+       HEROS_P_HOSPITALIZED_TO_DEAD = 6, HEROS_P_HOSPITALIZED_TO_RECOVERED = 7, HEROS_P_ICU_TO_DEAD = 8,
+       HEROS_P_ICU_TO_RECOVERED = 9, HEROS_N_PERIODS = 10 };
+typedef struct heros_prog_params {
+    double fraction[HEROS_N_FRACTIONS][2][128];
+    heros_duration period[HEROS_N_PERIODS];
+} heros_prog_params;
+
+typedef struct heros_step_stats {
+    int64_t windows;          /* windows processed by this call */
+    int64_t visits;           /* stays bucketed (sum over windows) */
+    int64_t sublocations;     /* occupied sub-location segments (sum over windows) */
+    int64_t evaluations;      /* infectPeople evaluations with calculated == true */
+    int64_t draws;            /* Philox infection draws */
+    int64_t infections;       /* new infections applied */
+    int64_t transitions;      /* disease-phase transitions applied (incl. exposures) */
+    int64_t gpu_launches;     /* kernels launched by this call */
+    double gpu_ms;            /* device time of this call (CUDA events on the engine stream) */
+    double transmit_ms;       /* of which: transmission kernels */
+    int64_t near_ties;        /* draws with |u - p| < 1e-13 (a flip could differ from the fp64 CPU result) */
+} heros_step_stats;
+
+/* ---- lifecycle ---- */
+int32_t heros_abi_version(void);
+int32_t heros_create(const heros_config* cfg, heros_handle* out);
+int32_t heros_destroy(heros_handle h);
+const char* heros_last_error(heros_handle h); /* h may be NULL: error of the last failed heros_create */
+
+/* ---- static inputs (factory/ConstructHerosModel.java: readLocationTypeTable :230-269, readLocationTable :300-395,
+ *      readPersonTable :450-758).  Column meaning as in the CSV files; total_area = area * nb_sublocations as float
+ *      (:381).  Optional arrays may be NULL. ---- */
+int32_t heros_set_location_types(heros_handle h, int32_t n, const uint8_t* infect_in_sublocation,
+                                 const double* correction_factor_area, const uint8_t* cap_constrained,
+                                 const double* cap_persons_per_m2, const double* size_factor);
+int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, const int16_t* n_sublocations,
+                            const float* total_area_m2, const float* lat, const float* lon);
+int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const uint8_t* female, const uint8_t* role,
+                          const int32_t* home_location, const int16_t* home_sublocation,
+                          const int32_t* work_location);
+
+/* ---- model parameters ---- */
+int32_t heros_set_transmission_area(heros_handle h, const heros_area_params* p);     /* Covid19TransmissionArea(model) */
+int32_t heros_set_transmission_distance(heros_handle h, const heros_dist_params* p); /* Covid19TransmissionDistance(model) */
+int32_t heros_set_progression(heros_handle h, const heros_prog_params* p);           /* Covid19Progression(model) */
+/* DiseaseTransmission.setParameter(name, value) as fired by policy/DiseasePolicy.java:29-43 at simulator time
+ * at_time.  Names "psi", "mu" (distance model only); anything else returns HEROS_ERR_UNKNOWN_PARAMETER, like the
+ * reference's "Unrecognized variable name" message (Covid19TransmissionDistance.java:263, ...Area.java:254). */
+int32_t heros_set_parameter(heros_handle h, const char* name, double value, double at_time);
+
+/* ---- dynamic inputs ---- */
+/* DiseaseProgression.expose(person, exposed) (Covid19Progression.java:182-201) for persons that are Susceptible:
+ * initial seeding (ConstructHerosModel.java:1109-1128) and probability-based locations.  exposure time = (float) at_time. */
+int32_t heros_expose(heros_handle h, int32_t n, const int32_t* person, const double* at_time);
+/* Deterministic replacement of infectPersons (ConstructHerosModel.java:1109-1128): exposes at t = 0 the n_infected
+ * eligible persons (Susceptible, min_age <= age <= max_age) with the smallest Philox hash of (seed, person).
+ * selected_out (may be NULL) receives the chosen ids in ascending order. */
+int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_age, int32_t max_age,
+                              int32_t* selected_out);
+/* Stays of persons in sub-locations: what Location.addPerson / removePerson of the medlabs engine record.  A stay
+ * still open at submission time has t_out = +inf and is re-submitted, with the same t_in, once it is closed.  A stay
+ * must be submitted before heros_step passes its t_in.  t_out <= t_in stays are ignored. */
+int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
+                            const int16_t* sublocation, const double* t_in, const double* t_out);
+/* same, from device memory of the engine's GPU (multi-GPU exchange buffers, device-side schedule generators) */
+int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
+                                   const int16_t* sublocation, const double* t_in, const double* t_out);
+
+/* ---- the hot path: advance simulated time to t_until in windows of cfg.window_hours: bucket stays by
+ *      sub-location, evaluate infectPeople for every movement event of the window, draw, resolve (earliest successful
+ *      draw wins), run the disease-phase state machine.  stats may be NULL. ---- */
+int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats);
+
+/* ---- outputs ---- */
+/* infection events (what the medlabs engine applies from InfectionRecord.infectedPersons), ordered by (time, person);
+ * p = pInfection of the evaluation.  first = index of the first event wanted. */
+int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
+                             int16_t* sublocation, double* time, double* p, int64_t* n_out);
+/* disease-phase trajectory: every phase entered (incl. Exposed), ordered by (time, person) */
+int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, int32_t* person, uint8_t* phase,
+                              double* time, int64_t* n_out);
+/* DiseasePhase person counters (addPerson / removePerson, Covid19Progression.java:184-186,211) at the current time */
+int32_t heros_get_phase_counts(heros_handle h, int64_t counts[8]);
+/* the same counters at the end of every window processed so far: counts[w*8 + phase], times[w] = window end */
+int32_t heros_get_count_series(heros_handle h, int64_t capacity_windows, double* times, int64_t* counts,
+                               int64_t* n_windows_out);
+int32_t heros_get_agent_state(heros_handle h, uint8_t* phase, float* exposure_time, double* next_time,
+                              uint8_t* next_phase);
+/* debugging / restore: overwrite phase and exposure time of the listed persons (next transition re-drawn at `now`) */
+int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, const uint8_t* phase,
+                              const float* exposure_time, double now);
+int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out);
+int32_t heros_get_time(heros_handle h, double* now);
+
+/* ---- 1:1 shim of DiseaseTransmission.infectPeople(location, personsInSublocation, duration)
+ *      (Covid19TransmissionArea.java:133-248 / Covid19TransmissionDistance.java:115-248), evaluated on the GPU against
+ *      the engine's current agent state with simulator time `now`.  all_persons = location.getAllPersonIds() (only
+ *      read by the total-location branch; may be NULL when that branch is not taken).  Does not modify any state:
+ *      like the reference method it only returns the InfectionRecord. ---- */
+int32_t heros_infect_people(heros_handle h, int32_t location, int32_t n_persons, const int32_t* persons_in_sublocation,
+                            int32_t n_all, const int32_t* all_persons, double now, double duration,
+                            int32_t* calculated, int32_t* infectious_out, int32_t* n_infectious,
+                            int32_t* infected_out, int32_t* n_infected, double* p_infection);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEROS_GPU_H */

@@ -1,0 +1,1341 @@
+// engine.cu -- libheros_gpu.so: engine state, the window pipeline and the C ABI of include/heros_gpu.h.
+//
+// One window [T0, T1) of simulated time is processed as
+//   1. k_progress        disease-phase state machine of every agent up to T1 (Covid19Progression.java:182-346),
+//                        remembering the phase transmission must see (the phase at T0) and when illness ends
+//   2. k_build_keys      window list = pool of submitted stays + the open stay of every agent, keyed by sub-location
+//   3. radix sort        occupancy bucketing: stays grouped per sub-location (replaces the per-location TIntSets the
+//                        medlabs engine maintains on every addPerson / removePerson)
+//   4. k_gather_sorted   stays + packed agent words in bucket order; segment offsets
+//   5. k_transmit_*      transmit.cu: every infectPeople evaluation of the window, Philox draws -> candidates
+//   6. k_resolve*        earliest successful draw per person wins; expose() the winners
+//   7. retire            stays that ended before T1 leave the pool
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+namespace heros {
+
+void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches);
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int TPB = 256;
+inline int blocks_for(size_t n, int per = TPB) { return (int) std::max<size_t>(1, (n + per - 1) / per); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct AgentArrays
+{
+    uint64_t* view; double* next_time; double* ill_end;
+    const ProgParams* prog; uint64_t seed;
+    Counters* ctr;
+    uint32_t* tr_person; uint8_t* tr_phase; double* tr_time; unsigned long long tr_cap;
+};
+
+__device__ __forceinline__ void log_transition(const AgentArrays& A, uint32_t person, uint32_t phase, double t)
+{
+    const unsigned long long slot = atomicAdd(&A.ctr->n_tr_log, 1ull);
+    if (slot < A.tr_cap)
+    {
+        A.tr_person[slot] = person;
+        A.tr_phase[slot] = (uint8_t) phase;
+        A.tr_time[slot] = t;
+    }
+    else
+        atomicOr(&A.ctr->overflow, 4u);
+    atomicAdd(&A.ctr->transitions, 1ull);
+}
+
+__device__ __forceinline__ void count_move(const AgentArrays& A, uint32_t from, uint32_t to)
+{
+    atomicAdd((unsigned long long*) &A.ctr->phase_counts[from], (unsigned long long) -1ll);  // removePerson()
+    atomicAdd((unsigned long long*) &A.ctr->phase_counts[to], 1ull);                         // addPerson()
+}
+
+// Fire the pending changeDiseasePhase events of one agent with time < t_end (Covid19Progression.java:208-346).
+// v: packed word (phase / next_phase updated), nt: time of the pending event.  Returns true when the agent left the
+// ILL state, at *ill_end.
+__device__ __forceinline__ bool run_transitions(const AgentArrays& A, uint32_t person, uint64_t& v, double& nt,
+                                                double t_end, double* ill_end)
+{
+    bool ended = false;
+    while (nt < t_end)
+    {
+        const uint32_t from = view_phase(v), to = view_next_phase(v);
+        count_move(A, from, to);
+        log_transition(A, person, to, nt);
+        v = view_set(v, 0, 0xF, to);
+        if (!phase_is_ill(to))  // Recovered / Dead: terminal
+        {
+            *ill_end = nt;
+            ended = true;
+            nt = bits_f64(0x7ff0000000000000ull);
+            break;
+        }
+        uint32_t next_phase;
+        double next_time;
+        progression_next(*A.prog, A.seed, person, view_age(v), view_female(v), to, nt, next_phase, next_time);
+        v = view_set(v, 8, 0xF, next_phase);
+        nt = next_time;
+    }
+    return ended;
+}
+
+// DiseaseProgression.expose (Covid19Progression.java:182-201) at time t
+__device__ __forceinline__ void expose_agent(const AgentArrays& A, uint32_t person, uint64_t& v, double& nt, double t)
+{
+    count_move(A, view_phase(v), PH_E);
+    log_transition(A, person, PH_E, t);
+    v = view_set(v, 0, 0xF, PH_E);
+    v = view_set_exposure(v, (float) t);
+    uint32_t next_phase;
+    progression_next(*A.prog, A.seed, person, view_age(v), view_female(v), PH_E, t, next_phase, nt);
+    v = view_set(v, 8, 0xF, next_phase);
+}
+
+__global__ void __launch_bounds__(TPB) k_progress(const AgentArrays A, uint32_t n, double T1)
+{
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint64_t v0 = A.view[a];
+    const uint32_t ph = view_phase(v0);
+    uint64_t v = view_set(v0, 4, 0xF, ph);  // transmission of this window sees the phase held at its start
+    v = view_set(v, 13, 1, 0);
+    if (phase_is_ill(ph))
+    {
+        double nt = A.next_time[a];
+        if (nt < T1)
+        {
+            double ill_end;
+            if (run_transitions(A, a, v, nt, T1, &ill_end))
+            {
+                A.ill_end[a] = ill_end;
+                v = view_set(v, 13, 1, 1);
+            }
+            A.next_time[a] = nt;
+        }
+    }
+    if (v != v0) A.view[a] = v;
+}
+
+struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; };
+
+__global__ void __launch_bounds__(TPB) k_build_keys(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
+                                                    const double* open_tin, uint32_t n_agents, double T1,
+                                                    uint32_t inactive_key, uint32_t* wl_key, uint32_t* wl_idx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pool + n_agents) return;
+    uint32_t key;
+    double tin;
+    if (i < n_pool) { key = P.key[i]; tin = P.tin[i]; }
+    else { key = open_key[i - n_pool]; tin = open_tin[i - n_pool]; }
+    wl_key[i] = (key != KEY_NONE && tin < T1) ? key : inactive_key;
+    wl_idx[i] = i;
+}
+
+__global__ void __launch_bounds__(TPB) k_gather_sorted(PoolArrays P, uint32_t n_pool, const double* open_tin,
+                                                       uint32_t n_total, const uint32_t* s_idx, const uint64_t* view,
+                                                       uint32_t* s_person, double* s_tin, double* s_tout,
+                                                       uint64_t* s_view)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_total) return;
+    const uint32_t i = s_idx[j];
+    uint32_t person;
+    double tin, tout;
+    if (i < n_pool) { person = P.person[i]; tin = P.tin[i]; tout = P.tout[i]; }
+    else { person = i - n_pool; tin = open_tin[person]; tout = bits_f64(0x7ff0000000000000ull); }
+    s_person[j] = person;
+    s_tin[j] = tin;
+    s_tout[j] = tout;
+    s_view[j] = view[person];
+}
+
+struct HeadPred
+{
+    const uint32_t* k;
+    __device__ bool operator()(uint32_t j) const { return j == 0 || k[j] != k[j - 1]; }
+};
+
+struct KeepPred
+{
+    const uint32_t* key; const double* tout; double T1;
+    __device__ bool operator()(uint32_t i) const { return key[i] != KEY_NONE && !(tout[i] < T1); }
+};
+
+__global__ void k_finish_segments(const uint32_t* s_key, uint32_t* seg_start, const uint32_t* n_sel, uint32_t n_total,
+                                  uint32_t inactive_key, Counters* ctr)
+{
+    const uint32_t ns = *n_sel;
+    uint32_t n_seg = ns, n_active = n_total;
+    if (ns > 0 && s_key[seg_start[ns - 1]] == inactive_key) { n_seg = ns - 1; n_active = seg_start[ns - 1]; }
+    seg_start[n_seg] = n_active;
+    ctr->n_seg = n_seg;
+    ctr->n_active = n_active;
+}
+
+__global__ void __launch_bounds__(TPB) k_retire_gather(PoolArrays src, PoolArrays dst, const uint32_t* idx,
+                                                       const uint32_t* n_keep, Counters* ctr)
+{
+    const uint32_t n = *n_keep;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = idx[j];
+        dst.person[j] = src.person[i];
+        dst.key[j] = src.key[i];
+        dst.tin[j] = src.tin[i];
+        dst.tout[j] = src.tout[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_keep = n;
+}
+
+// ---- resolve: earliest successful draw wins (ties: lowest sub-location key) -------------------------------------------
+struct CandArrays { const uint32_t* person; const uint32_t* key; const double* t; const double* p; uint32_t cap; };
+
+__global__ void __launch_bounds__(TPB) k_resolve_time(CandArrays C, const Counters* ctr, unsigned long long* best_t)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicMin(&best_t[C.person[i]], (unsigned long long) f64_bits(C.t[i]));
+}
+
+__global__ void __launch_bounds__(TPB) k_resolve_key(CandArrays C, const Counters* ctr,
+                                                     const unsigned long long* best_t, uint32_t* best_key)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (f64_bits(C.t[i]) == best_t[C.person[i]]) atomicMin(&best_key[C.person[i]], C.key[i]);
+}
+
+struct InfLog { uint32_t* person; uint32_t* key; double* t; double* p; unsigned long long cap; };
+
+__global__ void __launch_bounds__(TPB) k_resolve_apply(CandArrays C, const AgentArrays A,
+                                                       const unsigned long long* best_t, const uint32_t* best_key,
+                                                       uint32_t* claim, InfLog log, double T1)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, A.ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t person = C.person[i];
+        if (f64_bits(C.t[i]) != best_t[person] || C.key[i] != best_key[person]) continue;
+        if (atomicExch(&claim[person], 1u) != 0u) continue;  // identical duplicate
+        uint64_t v = A.view[person];
+        if (!phase_is_susceptible(view_phase(v))) continue;
+        const double t = C.t[i];
+        double nt;
+        expose_agent(A, person, v, nt, t);  // exposure time := (float) now, then expose() (contract C4)
+        double ill_end;
+        run_transitions(A, person, v, nt, T1, &ill_end);
+        A.view[person] = v;
+        A.next_time[person] = nt;
+        const unsigned long long slot = atomicAdd(&A.ctr->n_inf_log, 1ull);
+        if (slot < log.cap)
+        {
+            log.person[slot] = person;
+            log.key[slot] = C.key[i];
+            log.t[slot] = t;
+            log.p[slot] = C.p[i];
+        }
+        else
+            atomicOr(&A.ctr->overflow, 8u);
+        atomicAdd(&A.ctr->infections, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_resolve_reset(CandArrays C, const Counters* ctr, unsigned long long* best_t,
+                                                       uint32_t* best_key, uint32_t* claim)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t person = C.person[i];
+        best_t[person] = BEST_NONE;
+        best_key[person] = KEY_NONE;
+        claim[person] = 0u;
+    }
+}
+
+// ---- inputs ------------------------------------------------------------------------------------------------------------
+struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub; const double* tin; const double* tout; };
+
+// pass 0: closed stays -> pool (and close the matching open stay); pass 1: open stays -> open slot of the person
+__global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, int pass, PoolArrays P, uint32_t pool_base,
+                                                uint32_t* open_key, double* open_tin, const uint32_t* loc_base,
+                                                const int16_t* loc_nsub, uint32_t n_loc, uint32_t n_agents,
+                                                double t_now, Counters* ctr)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t person = in.person[i], loc = in.loc[i];
+    const int32_t sub = in.sub[i];
+    const double tin = in.tin[i], tout = in.tout[i];
+    bool ok = person >= 0 && (uint32_t) person < n_agents && loc >= 0 && (uint32_t) loc < n_loc && sub >= 0 &&
+              tin >= 0.0 && tin < bits_f64(0x7ff0000000000000ull) && tout == tout;
+    if (ok) ok = sub < max((int) loc_nsub[loc], 1);
+    const bool open = ok && !(tout < bits_f64(0x7ff0000000000000ull));
+    const bool positive = ok && tout > tin;
+    const uint32_t key = ok ? loc_base[loc] + (uint32_t) sub : KEY_NONE;
+    if (pass == 0)
+    {
+        uint32_t k = KEY_NONE;
+        if (ok && positive && !open)
+        {
+            k = key;
+            if (open_key[person] == key && open_tin[person] == tin) open_key[person] = KEY_NONE;
+            if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
+        }
+        else if (!ok)
+            atomicAdd(&ctr->invalid_visits, 1u);
+        P.person[pool_base + i] = ok ? (uint32_t) person : 0u;
+        P.key[pool_base + i] = k;
+        P.tin[pool_base + i] = tin;
+        P.tout[pool_base + i] = tout;
+    }
+    else if (open)
+    {
+        open_key[person] = key;
+        open_tin[person] = tin;
+        if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_expose(const AgentArrays A, uint32_t n, const int32_t* person,
+                                                const double* at_time, uint32_t n_agents)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t p = person[i];
+    if (p < 0 || (uint32_t) p >= n_agents) return;
+    const uint64_t v0 = A.view[p];
+    if (!phase_is_susceptible(view_phase(v0))) return;  // ConstructHerosModel.java:1119
+    // claim the agent first so that a person listed twice is exposed once
+    const uint64_t claimed = view_set(v0, 0, 0xF, PH_E);
+    if (atomicCAS((unsigned long long*) &A.view[p], (unsigned long long) v0, (unsigned long long) claimed) != v0) return;
+    uint64_t v = v0;
+    double nt;
+    expose_agent(A, (uint32_t) p, v, nt, at_time[i]);
+    A.view[p] = v;
+    A.next_time[p] = nt;
+}
+
+__global__ void __launch_bounds__(TPB) k_set_agent_state(const AgentArrays A, uint32_t n, const int32_t* person,
+                                                         const uint8_t* phase, const float* exposure, double now,
+                                                         uint32_t n_agents)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t p = person[i];
+    if (p < 0 || (uint32_t) p >= n_agents) return;
+    uint64_t v = A.view[p];
+    const uint32_t ph = phase[i] & 7u;
+    count_move(A, view_phase(v), ph);
+    v = view_set(v, 0, 0xF, ph);
+    v = view_set(v, 4, 0xF, ph);
+    v = view_set(v, 13, 1, 0);
+    v = view_set_exposure(v, exposure[i]);
+    uint32_t next_phase;
+    double nt;
+    progression_next(*A.prog, A.seed, (uint32_t) p, view_age(v), view_female(v), ph, now, next_phase, nt);
+    v = view_set(v, 8, 0xF, next_phase);
+    A.view[p] = v;
+    A.next_time[p] = nt;
+}
+
+__global__ void __launch_bounds__(TPB) k_init_agents(uint64_t* view, double* next_time, unsigned long long* best_t,
+                                                     uint32_t* best_key, uint32_t* claim, uint32_t* open_key,
+                                                     double* open_tin, const int8_t* age, const uint8_t* female,
+                                                     const uint8_t* role, uint32_t n)
+{
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    uint64_t v = 0;  // Susceptible, exposure time 0.0f (ConstructHerosModel.java:744-747)
+    const int ag = age ? age[a] : 0;
+    v = view_set(v, 16, 0xFF, (uint32_t) (ag < 0 ? 0 : ag));
+    v = view_set(v, 12, 1, female ? (female[a] ? 1u : 0u) : 0u);
+    v = view_set(v, 24, 0xFF, role ? role[a] : 0u);
+    view[a] = v;
+    next_time[a] = bits_f64(0x7ff0000000000000ull);
+    best_t[a] = BEST_NONE;
+    best_key[a] = KEY_NONE;
+    claim[a] = 0u;
+    open_key[a] = KEY_NONE;
+    open_tin[a] = 0.0;
+}
+
+// 1:1 shim of infectPeople: a single thread walks the sets in the caller's order, exactly like the Java loops
+struct ShimOut { int32_t calculated, n_infectious, n_infected, pad; double p; };
+
+__global__ void k_infect_people(int model, AreaParams area, DistParams dist, double psi, double mu, uint64_t seed,
+                                int infect_sub, int n_sub_locations, double total_area, double corr,
+                                const uint64_t* view, int n_sub, const int32_t* sub_ids, int n_all,
+                                const int32_t* all_ids, double now, double duration, int32_t* infectious,
+                                int32_t* infected, ShimOut* out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ShimOut o = {0, 0, 0, 0, bits_f64(0x7ff8000000000000ull)};
+    const double thr = model == HEROS_MODEL_AREA ? area.threshold : dist.threshold;
+    if (duration < thr) { *out = o; return; }  // TArea:138 / TDist:120
+    o.calculated = 1;
+    const bool sub_branch = infect_sub || n_sub_locations < 2;  // TArea:149 / TDist:131
+    const int32_t* ids = sub_branch ? sub_ids : all_ids;
+    const int n = sub_branch ? n_sub : n_all;
+    double a = total_area;
+    if (sub_branch) a /= (double) n_sub_locations;  // TArea:155 / TDist:137
+    double p = 0.0;
+    bool have_p = false;
+    if (model == HEROS_MODEL_AREA)
+    {
+        const double factor = sub_branch ? area_factor(area, duration, corr * a) : area_factor_total(area, duration, corr * a);
+        if (factor != 0.0)
+        {
+            double sum = 0.0;
+            for (int k = 0; k < n; ++k)
+            {
+                const uint64_t v = view[ids[k]];
+                if (phase_is_ill(view_phase(v)))
+                {
+                    const double te = now - (double) view_exposure(v);
+                    sum += sub_branch ? area_contribution(area, te) : area_contribution_total(area, te);
+                    infectious[o.n_infectious++] = ids[k];  // TArea:175: every ill occupant
+                }
+            }
+            if (sum != 0.0) { p = 1.0 - hexp(factor * sum); have_p = true; }
+        }
+    }
+    else
+    {
+        const double factor = dist_factor(dist, psi, mu, a, n_sub);  // TDist:138 / :196 (sub-location head count)
+        if (factor != 0.0)
+        {
+            double sum = 0.0;
+            for (int k = 0; k < n; ++k)
+            {
+                const uint64_t v = view[ids[k]];
+                if (phase_is_ill(view_phase(v)))
+                {
+                    const double v_t = dist_viral_load(dist, now - (double) view_exposure(v));
+                    if (v_t > 0)
+                    {
+                        sum += dist_term(dist, factor, duration, v_t);
+                        infectious[o.n_infectious++] = ids[k];  // TDist:165: only contagious occupants
+                    }
+                }
+            }
+            if (sum != 0.0) { p = 1.0 - hexp(-sum); have_p = true; }
+        }
+    }
+    if (have_p)
+    {
+        o.p = p;
+        for (int k = 0; k < n; ++k)
+        {
+            const uint64_t v = view[ids[k]];
+            if (phase_is_susceptible(view_phase(v)) && u01(seed, (uint32_t) ids[k], f64_bits(now), TAG_TRANSMIT) < p)
+                infected[o.n_infected++] = ids[k];
+        }
+    }
+    *out = o;
+}
+
+}  // namespace
+}  // namespace heros
+
+// ---------------------------------------------------------------------------------------------------------------------
+// engine object
+// ---------------------------------------------------------------------------------------------------------------------
+using namespace heros;
+
+struct heros_engine
+{
+    heros_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4]{};
+    int n_sm = 148;
+    double t_now = 0.0;
+
+    bool have_area = false, have_dist = false, have_prog = false;
+    AreaParams area{};
+    DistParams dist{};
+    std::vector<PolicyChange> policy;
+    DevBuf<PolicyChange> d_policy;
+    DevBuf<ProgParams> d_prog;
+
+    int n_types = 0;
+    std::vector<uint8_t> type_infect_sub;
+    std::vector<double> type_corr;
+
+    uint32_t n_loc = 0, n_keys = 0;
+    std::vector<uint32_t> h_loc_base;
+    std::vector<uint8_t> h_loc_type;
+    std::vector<int16_t> h_loc_nsub;
+    std::vector<float> h_loc_area;
+    DevBuf<uint32_t> d_loc_base, d_key_loc;
+    DevBuf<int16_t> d_loc_nsub;
+    DevBuf<LocParam> d_loc_param;
+    DevBuf<double> d_last_calc;
+
+    uint32_t n_agents = 0;
+    DevBuf<uint64_t> d_view;
+    DevBuf<double> d_next_time, d_ill_end, d_open_tin;
+    DevBuf<unsigned long long> d_best_t;
+    DevBuf<uint32_t> d_best_key, d_claim, d_open_key;
+
+    // pool of submitted stays (double buffered)
+    DevBuf<uint32_t> pool_person[2], pool_key[2];
+    DevBuf<double> pool_tin[2], pool_tout[2];
+    int pool_cur = 0;
+    uint32_t n_pool = 0;
+
+    // window buffers
+    DevBuf<uint32_t> wl_key, wl_idx, s_key, s_idx, s_person, seg_start, keep_idx, d_nsel;
+    DevBuf<double> s_tin, s_tout;
+    DevBuf<uint64_t> s_view;
+    DevBuf<uint8_t> cub_temp;
+
+    // candidates, logs
+    DevBuf<uint32_t> cand_person, cand_key;
+    DevBuf<double> cand_t, cand_p;
+    DevBuf<uint32_t> inf_person, inf_key, tr_person;
+    DevBuf<double> inf_t, inf_p, tr_time;
+    DevBuf<uint8_t> tr_phase;
+
+    // big-segment scratch
+    DevBuf<uint32_t> big_seg, big_off, sc_evx, sc_j0, sc_j1, sc_node, sc_ill;
+    DevBuf<uint64_t> sc_evt;
+    DevBuf<int32_t> sc_pre;
+    DevBuf<double> sc_cand, sc_p, sc_dur;
+
+    DevBuf<Counters> d_ctr;
+    Counters* h_ctr = nullptr;  // pinned
+
+    // staging for host submissions
+    DevBuf<int32_t> st_person, st_loc;
+    DevBuf<int16_t> st_sub;
+    DevBuf<double> st_tin, st_tout;
+
+    std::vector<double> series_t;
+    std::vector<int64_t> series_counts;
+
+    // sorted output caches
+    std::vector<uint32_t> o_inf_person, o_inf_key, o_tr_person;
+    std::vector<double> o_inf_t, o_inf_p, o_tr_time;
+    std::vector<uint8_t> o_tr_phase;
+    unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
+};
+
+namespace heros_impl {
+
+#define CU(h, call)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return HEROS_ERR_CUDA;                                                                        \
+        }                                                                                                 \
+    } while (0)
+
+int32_t fail(heros_handle h, int32_t code, const std::string& msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+AgentArrays agent_arrays(heros_handle h)
+{
+    AgentArrays A;
+    A.view = h->d_view.p; A.next_time = h->d_next_time.p; A.ill_end = h->d_ill_end.p;
+    A.prog = h->d_prog.p; A.seed = h->cfg.seed; A.ctr = h->d_ctr.p;
+    A.tr_person = h->tr_person.p; A.tr_phase = h->tr_phase.p; A.tr_time = h->tr_time.p;
+    A.tr_cap = h->tr_person.n;
+    return A;
+}
+
+PoolArrays pool_arrays(heros_handle h, int which)
+{
+    return PoolArrays{h->pool_person[which].p, h->pool_key[which].p, h->pool_tin[which].p, h->pool_tout[which].p};
+}
+
+int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep)
+{
+    CU(h, h->pool_person[which].ensure(n, keep, h->stream));
+    CU(h, h->pool_key[which].ensure(n, keep, h->stream));
+    CU(h, h->pool_tin[which].ensure(n, keep, h->stream));
+    CU(h, h->pool_tout[which].ensure(n, keep, h->stream));
+    return HEROS_OK;
+}
+
+int32_t sync_counters(heros_handle h)
+{
+    CU(h, cudaMemcpyAsync(h->h_ctr, h->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+
+__global__ void k_zero_window(Counters* c)
+{
+    c->n_cand = 0; c->n_big = 0; c->scratch_top = 0; c->n_keep = 0; c->n_seg = 0; c->n_active = 0;
+}
+
+int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
+
+int32_t check_ready(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->n_agents == 0 || h->n_loc == 0 || h->n_types == 0)
+        return fail(h, HEROS_ERR_INVALID, "location types, locations and persons must be set first");
+    if (!h->have_prog) return fail(h, HEROS_ERR_INVALID, "heros_set_progression has not been called");
+    if (h->cfg.model == HEROS_MODEL_AREA && !h->have_area)
+        return fail(h, HEROS_ERR_INVALID, "heros_set_transmission_area has not been called");
+    if (h->cfg.model == HEROS_MODEL_DISTANCE && !h->have_dist)
+        return fail(h, HEROS_ERR_INVALID, "heros_set_transmission_distance has not been called");
+    return HEROS_OK;
+}
+
+// one window [T0, T1)
+int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& transmit_ms)
+{
+    cudaStream_t s = h->stream;
+    const uint32_t N = h->n_agents;
+    const uint32_t n_pool = h->n_pool;
+    const uint32_t n_total = n_pool + N;
+    const int cur = h->pool_cur, oth = cur ^ 1;
+    const uint32_t inactive_key = h->n_keys;
+
+    k_zero_window<<<1, 1, 0, s>>>(h->d_ctr.p);
+    ++launches;
+
+    // 1. disease-phase state machine
+    const AgentArrays A = agent_arrays(h);
+    k_progress<<<blocks_for(N), TPB, 0, s>>>(A, N, T1);
+    ++launches;
+
+    // 2. window list keys
+    CU(h, h->wl_key.ensure(n_total)); CU(h, h->wl_idx.ensure(n_total));
+    CU(h, h->s_key.ensure(n_total)); CU(h, h->s_idx.ensure(n_total));
+    CU(h, h->s_person.ensure(n_total)); CU(h, h->s_tin.ensure(n_total)); CU(h, h->s_tout.ensure(n_total));
+    CU(h, h->s_view.ensure(n_total)); CU(h, h->seg_start.ensure((size_t) n_total + 2));
+    CU(h, h->keep_idx.ensure(std::max<uint32_t>(n_pool, 1)));
+    { const int32_t rc_ = ensure_pool(h, oth, std::max<uint32_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
+    const PoolArrays P = pool_arrays(h, cur);
+    k_build_keys<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, T1, inactive_key,
+                                                     h->wl_key.p, h->wl_idx.p);
+    ++launches;
+
+    // 3. bucket by sub-location
+    const int end_bit = std::max(1, bit_length(inactive_key));
+    size_t temp_sort = 0, temp_sel = 0, temp_keep = 0;
+    thrust::counting_iterator<uint32_t> iota(0);
+    HeadPred head{h->s_key.p};
+    KeepPred keep{P.key, P.tout, T1};
+    CU(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, h->wl_key.p, h->s_key.p, h->wl_idx.p, h->s_idx.p,
+                                          (int) n_total, 0, end_bit, s));
+    CU(h, cub::DeviceSelect::If(nullptr, temp_sel, iota, h->seg_start.p, h->d_nsel.p, (int) n_total, head, s));
+    CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) n_pool, keep, s));
+    CU(h, h->cub_temp.ensure(std::max(temp_sort, std::max(temp_sel, temp_keep)) + 256));
+    size_t tb = h->cub_temp.n;
+    CU(h, cub::DeviceRadixSort::SortPairs(h->cub_temp.p, tb, h->wl_key.p, h->s_key.p, h->wl_idx.p, h->s_idx.p,
+                                          (int) n_total, 0, end_bit, s));
+    launches += 1 + (end_bit + 7) / 8 * 2;
+
+    // 4. stays in bucket order + segment offsets
+    k_gather_sorted<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_tin.p, n_total, h->s_idx.p, h->d_view.p,
+                                                        h->s_person.p, h->s_tin.p, h->s_tout.p, h->s_view.p);
+    tb = h->cub_temp.n;
+    CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->seg_start.p, h->d_nsel.p, (int) n_total, head, s));
+    k_finish_segments<<<1, 1, 0, s>>>(h->s_key.p, h->seg_start.p, h->d_nsel.p, n_total, inactive_key, h->d_ctr.p);
+    launches += 4;
+
+    // 5. transmission
+    const size_t scratch_want = 4 * (size_t) n_total + 4096;
+    CU(h, h->sc_evt.ensure(scratch_want)); CU(h, h->sc_evx.ensure(scratch_want)); CU(h, h->sc_pre.ensure(scratch_want));
+    CU(h, h->sc_j0.ensure(scratch_want)); CU(h, h->sc_j1.ensure(scratch_want)); CU(h, h->sc_cand.ensure(scratch_want));
+    CU(h, h->sc_node.ensure(scratch_want)); CU(h, h->sc_p.ensure(scratch_want)); CU(h, h->sc_dur.ensure(scratch_want));
+    CU(h, h->sc_ill.ensure(scratch_want));
+    CU(h, h->big_seg.ensure((size_t) n_total / 32 + 16)); CU(h, h->big_off.ensure((size_t) n_total / 32 + 16));
+
+    WindowCtx c{};
+    c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
+    c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
+    c.key_loc = h->d_key_loc.p; c.loc_param = h->d_loc_param.p; c.last_calc = h->d_last_calc.p; c.n_keys = h->n_keys;
+    c.view = h->d_view.p; c.ill_end = h->d_ill_end.p;
+    c.s_key = h->s_key.p; c.s_person = h->s_person.p; c.s_tin = h->s_tin.p; c.s_tout = h->s_tout.p;
+    c.s_view = h->s_view.p; c.seg_start = h->seg_start.p;
+    c.cand_person = h->cand_person.p; c.cand_key = h->cand_key.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
+    c.cand_cap = (uint32_t) h->cand_person.n;
+    c.big_seg = h->big_seg.p; c.big_off = h->big_off.p; c.big_cap = (uint32_t) h->big_seg.n;
+    c.sc_evt = h->sc_evt.p; c.sc_evx = h->sc_evx.p; c.sc_pre = h->sc_pre.p; c.sc_j0 = h->sc_j0.p; c.sc_j1 = h->sc_j1.p;
+    c.sc_cand = h->sc_cand.p; c.sc_node = h->sc_node.p; c.sc_p = h->sc_p.p; c.sc_dur = h->sc_dur.p;
+    c.sc_ill = h->sc_ill.p; c.scratch_cap = h->sc_evt.n;
+    c.ctr = h->d_ctr.p;
+    CU(h, cudaEventRecord(h->ev[2], s));
+    launch_transmit(c, h->n_sm, s, launches);
+    CU(h, cudaEventRecord(h->ev[3], s));
+
+    // 6. resolve: earliest successful draw per person wins
+    const CandArrays C{h->cand_person.p, h->cand_key.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    const InfLog log{h->inf_person.p, h->inf_key.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
+    const int rg = h->n_sm * 2;
+    k_resolve_time<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p);
+    k_resolve_key<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p);
+    k_resolve_apply<<<rg, TPB, 0, s>>>(C, A, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, log, T1);
+    k_resolve_reset<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->d_claim.p);
+    launches += 4;
+
+    // 7. retire the stays that ended before T1
+    if (n_pool > 0)
+    {
+        tb = h->cub_temp.n;
+        CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) n_pool, keep, s));
+        k_retire_gather<<<h->n_sm * 4, TPB, 0, s>>>(P, pool_arrays(h, oth), h->keep_idx.p, h->d_nsel.p + 1, h->d_ctr.p);
+        launches += 3;
+    }
+    CU(h, cudaGetLastError());
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    if (n_pool > 0)
+    {
+        h->n_pool = (uint32_t) h->h_ctr->n_keep;
+        h->pool_cur = oth;
+    }
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+    transmit_ms += ms;
+    if (h->h_ctr->overflow)
+    {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log)",
+                 h->h_ctr->overflow);
+        return fail(h, HEROS_ERR_CAPACITY, buf);
+    }
+    h->series_t.push_back(T1);
+    for (int k = 0; k < 8; ++k) h->series_counts.push_back((int64_t) h->h_ctr->phase_counts[k]);
+    return HEROS_OK;
+}
+
+}  // namespace heros_impl
+using namespace heros_impl;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t heros_abi_version(void) { return HEROS_ABI_VERSION; }
+
+const char* heros_last_error(heros_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t heros_create(const heros_config* cfg, heros_handle* out)
+{
+    if (!cfg || !out) return fail(nullptr, HEROS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != HEROS_ABI_VERSION) return fail(nullptr, HEROS_ERR_INVALID, "ABI version mismatch");
+    if (cfg->model != HEROS_MODEL_AREA && cfg->model != HEROS_MODEL_DISTANCE)
+        return fail(nullptr, HEROS_ERR_INVALID, "unknown transmission model");
+    if (cfg->trigger != HEROS_TRIGGER_EXIT_ONLY && cfg->trigger != HEROS_TRIGGER_ENTER_AND_EXIT)
+        return fail(nullptr, HEROS_ERR_INVALID, "unknown trigger");
+    if (!(cfg->window_hours > 0)) return fail(nullptr, HEROS_ERR_INVALID, "window_hours must be positive");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, HEROS_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                 " (the engine has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, HEROS_ERR_INVALID, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, HEROS_ERR_CUDA, cudaGetErrorString(e));
+    heros_handle h = new (std::nothrow) heros_engine();
+    if (!h) return fail(nullptr, HEROS_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        heros_destroy(h);
+        return (int32_t) HEROS_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (auto& ev : h->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
+    if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
+    if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMallocHost(&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("pinned counters", e);
+    if ((e = h->d_nsel.ensure(4)) != cudaSuccess) return bail("nsel", e);
+    if ((e = h->d_policy.ensure(16)) != cudaSuccess) return bail("policy", e);
+    if ((e = h->d_prog.ensure(1)) != cudaSuccess) return bail("prog", e);
+    *out = h;
+    return HEROS_OK;
+}
+
+int32_t heros_destroy(heros_handle h)
+{
+    if (!h) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_policy.release(); h->d_prog.release(); h->d_loc_base.release(); h->d_key_loc.release();
+    h->d_loc_nsub.release(); h->d_loc_param.release(); h->d_last_calc.release(); h->d_view.release();
+    h->d_next_time.release(); h->d_ill_end.release(); h->d_open_tin.release(); h->d_best_t.release();
+    h->d_best_key.release(); h->d_claim.release(); h->d_open_key.release();
+    for (int i = 0; i < 2; ++i)
+    {
+        h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
+    }
+    h->wl_key.release(); h->wl_idx.release(); h->s_key.release(); h->s_idx.release(); h->s_person.release();
+    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->s_tin.release(); h->s_tout.release();
+    h->s_view.release(); h->cub_temp.release(); h->cand_person.release(); h->cand_key.release(); h->cand_t.release();
+    h->cand_p.release(); h->inf_person.release(); h->inf_key.release(); h->tr_person.release(); h->inf_t.release();
+    h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->big_seg.release(); h->big_off.release();
+    h->sc_evx.release(); h->sc_j0.release(); h->sc_j1.release(); h->sc_node.release(); h->sc_ill.release();
+    h->sc_evt.release(); h->sc_pre.release(); h->sc_cand.release(); h->sc_p.release(); h->sc_dur.release();
+    h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
+    h->st_tout.release();
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return HEROS_OK;
+}
+
+int32_t heros_set_location_types(heros_handle h, int32_t n, const uint8_t* infect_sub, const double* corr,
+                                 const uint8_t*, const double*, const double*)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (n <= 0 || n > 256 || !infect_sub || !corr) return fail(h, HEROS_ERR_INVALID, "bad location type table");
+    h->n_types = n;
+    h->type_infect_sub.assign(infect_sub, infect_sub + n);
+    h->type_corr.assign(corr, corr + n);
+    return HEROS_OK;
+}
+
+int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, const int16_t* n_sub, const float* area,
+                            const float*, const float*)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->n_types == 0) return fail(h, HEROS_ERR_INVALID, "heros_set_location_types must be called first");
+    if (n <= 0 || !type || !n_sub || !area) return fail(h, HEROS_ERR_INVALID, "bad location table");
+    cudaSetDevice(h->cfg.device);
+    std::vector<uint32_t> base((size_t) n + 1);
+    std::vector<LocParam> lp(n);
+    uint64_t b = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        if (type[i] >= h->n_types) return fail(h, HEROS_ERR_INVALID, "location type id out of range");
+        if (n_sub[i] < 0) return fail(h, HEROS_ERR_INVALID, "negative number of sub-locations");
+        if (!h->type_infect_sub[type[i]] && n_sub[i] >= 2)
+            return fail(h, HEROS_ERR_UNSUPPORTED,
+                        "location with infectInSublocation = false and >= 2 sub-locations: the total-location branch "
+                        "(Covid19TransmissionArea.java:198-246) is only available through heros_infect_people");
+        base[i] = (uint32_t) b;
+        b += (uint64_t) std::max<int>(n_sub[i], 1);  // a location with 0 sub-locations still owns one key
+        double a = (double) area[i];                 // float getTotalSurfaceM2() widened (TArea:144)
+        a /= (double) n_sub[i];                      // TArea:155 / TDist:137 (inf or NaN for n_sub == 0, as in Java)
+        lp[i].area_sub = a;
+        lp[i].denom = h->type_corr[type[i]] * a;     // TArea:156
+    }
+    if (b >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_UNSUPPORTED, "more than 2^32 sub-locations");
+    base[n] = (uint32_t) b;
+    h->n_loc = (uint32_t) n;
+    h->n_keys = (uint32_t) b;
+    h->h_loc_base = base;
+    h->h_loc_type.assign(type, type + n);
+    h->h_loc_nsub.assign(n_sub, n_sub + n);
+    h->h_loc_area.assign(area, area + n);
+    std::vector<uint32_t> key_loc(h->n_keys);
+    for (int i = 0; i < n; ++i)
+        for (uint32_t k = base[i]; k < base[i + 1]; ++k) key_loc[k] = (uint32_t) i;
+    CU(h, h->d_loc_base.ensure((size_t) n + 1)); CU(h, h->d_key_loc.ensure(h->n_keys));
+    CU(h, h->d_loc_nsub.ensure(n)); CU(h, h->d_loc_param.ensure(n)); CU(h, h->d_last_calc.ensure(h->n_keys));
+    CU(h, cudaMemcpyAsync(h->d_loc_base.p, base.data(), ((size_t) n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_key_loc.p, key_loc.data(), (size_t) h->n_keys * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_loc_nsub.p, n_sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_loc_param.p, lp.data(), (size_t) n * sizeof(LocParam), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemsetAsync(h->d_last_calc.p, 0, (size_t) h->n_keys * 8, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const uint8_t* female, const uint8_t* role,
+                          const int32_t*, const int16_t*, const int32_t*)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (n <= 0) return fail(h, HEROS_ERR_INVALID, "bad person table");
+    cudaSetDevice(h->cfg.device);
+    const size_t N = (size_t) n;
+    h->n_agents = (uint32_t) n;
+    CU(h, h->d_view.ensure(N)); CU(h, h->d_next_time.ensure(N)); CU(h, h->d_ill_end.ensure(N));
+    CU(h, h->d_open_tin.ensure(N)); CU(h, h->d_best_t.ensure(N)); CU(h, h->d_best_key.ensure(N));
+    CU(h, h->d_claim.ensure(N)); CU(h, h->d_open_key.ensure(N));
+    CU(h, h->cand_person.ensure(N + 65536)); CU(h, h->cand_key.ensure(N + 65536));
+    CU(h, h->cand_t.ensure(N + 65536)); CU(h, h->cand_p.ensure(N + 65536));
+    CU(h, h->inf_person.ensure(N)); CU(h, h->inf_key.ensure(N)); CU(h, h->inf_t.ensure(N)); CU(h, h->inf_p.ensure(N));
+    CU(h, h->tr_person.ensure(5 * N)); CU(h, h->tr_phase.ensure(5 * N)); CU(h, h->tr_time.ensure(5 * N));
+    DevBuf<int8_t> d_age; DevBuf<uint8_t> d_female, d_role;
+    if (age) { CU(h, d_age.ensure(N)); CU(h, cudaMemcpyAsync(d_age.p, age, N, cudaMemcpyHostToDevice, h->stream)); }
+    if (female) { CU(h, d_female.ensure(N)); CU(h, cudaMemcpyAsync(d_female.p, female, N, cudaMemcpyHostToDevice, h->stream)); }
+    if (role) { CU(h, d_role.ensure(N)); CU(h, cudaMemcpyAsync(d_role.p, role, N, cudaMemcpyHostToDevice, h->stream)); }
+    k_init_agents<<<blocks_for(N), TPB, 0, h->stream>>>(h->d_view.p, h->d_next_time.p, h->d_best_t.p, h->d_best_key.p,
+                                                        h->d_claim.p, h->d_open_key.p, h->d_open_tin.p, d_age.p,
+                                                        d_female.p, d_role.p, (uint32_t) n);
+    Counters zero{};
+    zero.phase_counts[PH_S] = n;
+    CU(h, cudaMemcpyAsync(h->d_ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    d_age.release(); d_female.release(); d_role.release();
+    h->n_pool = 0; h->t_now = 0.0;
+    h->series_t.clear(); h->series_counts.clear();
+    return HEROS_OK;
+}
+
+int32_t heros_set_transmission_area(heros_handle h, const heros_area_params* p)
+{
+    if (!h || !p) return HEROS_ERR_INVALID;
+    h->area.contagiousness = p->contagiousness;                  // TArea:63
+    h->area.beta = p->beta;                                      // TArea:64
+    h->area.t_e_min = p->t_e_min * 24.0;                         // TArea:65
+    h->area.t_e_mode = p->t_e_mode * 24.0;                       // TArea:66
+    h->area.t_e_max = p->t_e_max * 24.0;                         // TArea:67
+    h->area.threshold = p->calculation_threshold / 3600.0;       // TArea:68
+    h->have_area = true;
+    return HEROS_OK;
+}
+
+int32_t heros_set_transmission_distance(heros_handle h, const heros_dist_params* p)
+{
+    if (!h || !p) return HEROS_ERR_INVALID;
+    h->dist.L = p->L * 24.0;                                     // TDist:59
+    h->dist.I = p->I * 24.0;                                     // TDist:60
+    h->dist.C = p->C * 24.0;                                     // TDist:61
+    h->dist.v_max = p->v_max; h->dist.v_0 = p->v_0; h->dist.r = p->r;
+    h->dist.psi = p->psi; h->dist.alpha = p->alpha; h->dist.mu = p->mu;
+    h->dist.threshold = p->calculation_threshold / 3600.0;       // TDist:68
+    h->have_dist = true;
+    return HEROS_OK;
+}
+
+int32_t heros_set_progression(heros_handle h, const heros_prog_params* p)
+{
+    if (!h || !p) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    ProgParams pp;
+    static_assert(sizeof(pp.fraction) == sizeof(p->fraction), "fraction table layout");
+    memcpy(pp.fraction, p->fraction, sizeof(pp.fraction));
+    for (int i = 0; i < N_PERIOD; ++i)
+    {
+        const heros_duration& d = p->period[i];
+        if (d.kind < HEROS_DIST_CONSTANT || d.kind > HEROS_DIST_TRIANGULAR)
+            return fail(h, HEROS_ERR_UNSUPPORTED, "unsupported duration distribution kind");
+        pp.period[i] = Duration{d.kind, 0, d.a, d.b, d.c};
+    }
+    CU(h, cudaMemcpyAsync(h->d_prog.p, &pp, sizeof(pp), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_prog = true;
+    return HEROS_OK;
+}
+
+int32_t heros_set_parameter(heros_handle h, const char* name, double value, double at_time)
+{
+    if (!h || !name) return HEROS_ERR_INVALID;
+    int which;
+    if (strcmp(name, "psi") == 0) which = 0;       // TDist:254
+    else if (strcmp(name, "mu") == 0) which = 1;   // TDist:258
+    else return fail(h, HEROS_ERR_UNKNOWN_PARAMETER, std::string("Unrecognized variable name ") + name);
+    if (h->cfg.model != HEROS_MODEL_DISTANCE)      // TArea:251-255 rejects every name
+        return fail(h, HEROS_ERR_UNKNOWN_PARAMETER, std::string("Unrecognized variable name ") + name);
+    cudaSetDevice(h->cfg.device);
+    PolicyChange pc{at_time, which, 0, value};
+    auto it = std::upper_bound(h->policy.begin(), h->policy.end(), pc,
+                               [](const PolicyChange& a, const PolicyChange& b) { return a.t < b.t; });
+    h->policy.insert(it, pc);
+    CU(h, h->d_policy.ensure(h->policy.size()));
+    CU(h, cudaMemcpyAsync(h->d_policy.p, h->policy.data(), h->policy.size() * sizeof(PolicyChange),
+                          cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_expose(heros_handle h, int32_t n, const int32_t* person, const double* at_time)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (n < 0 || (n > 0 && (!person || !at_time))) return fail(h, HEROS_ERR_INVALID, "null argument");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    CU(h, h->st_person.ensure(n)); CU(h, h->st_tin.ensure(n));
+    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->st_tin.p, at_time, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_expose<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, h->st_tin.p,
+                                                   h->n_agents);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_age, int32_t max_age,
+                              int32_t* selected_out)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (n_infected < 0) return fail(h, HEROS_ERR_INVALID, "negative number of infections");
+    cudaSetDevice(h->cfg.device);
+    std::vector<uint64_t> view(h->n_agents);
+    CU(h, cudaMemcpyAsync(view.data(), h->d_view.p, (size_t) h->n_agents * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // the n eligible persons with the smallest keyed hash: independent of table order, sharding and thread count
+    std::vector<std::pair<uint64_t, int32_t>> eligible;
+    for (uint32_t a = 0; a < h->n_agents; ++a)
+    {
+        const int age = (int) view_age(view[a]);
+        if (!phase_is_susceptible(view_phase(view[a])) || age < min_age || age > max_age) continue;
+        const Philox4 r = philox4x32_10(a, 0, 0, TAG_SEEDING, (uint32_t) h->cfg.seed, (uint32_t) (h->cfg.seed >> 32));
+        eligible.emplace_back(((uint64_t) r.x << 32) | r.y, (int32_t) a);
+    }
+    if ((size_t) n_infected > eligible.size())
+        return fail(h, HEROS_ERR_INVALID, "fewer eligible persons than infections requested");
+    std::partial_sort(eligible.begin(), eligible.begin() + n_infected, eligible.end());
+    std::vector<int32_t> chosen(n_infected);
+    for (int i = 0; i < n_infected; ++i) chosen[i] = eligible[i].second;
+    std::sort(chosen.begin(), chosen.end());
+    std::vector<double> t0(n_infected, 0.0);
+    if (selected_out) memcpy(selected_out, chosen.data(), (size_t) n_infected * 4);
+    return heros_expose(h, n_infected, chosen.data(), t0.data());
+}
+
+static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc,
+                                  const int16_t* sub, const double* tin, const double* tout)
+{
+    if ((uint64_t) h->n_pool + (uint64_t) n + h->n_agents >= 0xFFFFFFF0ull)
+        return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
+    int32_t rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + n, true);
+    if (rc != HEROS_OK) return rc;
+    const SubmitIn in{person, loc, sub, tin, tout};
+    const PoolArrays P = pool_arrays(h, h->pool_cur);
+    for (int pass = 0; pass < 2; ++pass)
+        k_submit<<<blocks_for(n), TPB, 0, h->stream>>>(in, (uint32_t) n, pass, P, h->n_pool, h->d_open_key.p,
+                                                       h->d_open_tin.p, h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc,
+                                                       h->n_agents, h->t_now, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    h->n_pool += (uint32_t) n;
+    return HEROS_OK;
+}
+
+int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc, const int16_t* sub,
+                            const double* tin, const double* tout)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    CU(h, h->st_person.ensure(n)); CU(h, h->st_loc.ensure(n)); CU(h, h->st_sub.ensure(n));
+    CU(h, h->st_tin.ensure(n)); CU(h, h->st_tout.ensure(n));
+    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->st_loc.p, loc, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->st_sub.p, sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->st_tin.p, tin, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->st_tout.p, tout, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = submit_from_device(h, n, h->st_person.p, h->st_loc.p, h->st_sub.p, h->st_tin.p, h->st_tout.p);
+    if (rc != HEROS_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));  // the caller may reuse its buffers
+    return HEROS_OK;
+}
+
+int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc,
+                                   const int16_t* sub, const double* tin, const double* tout)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    rc = submit_from_device(h, n, person, loc, sub, tin, tout);
+    if (rc != HEROS_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (!(t_until >= h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until lies before the engine time");
+    // batch == sequential only while an infection of the window cannot become contagious inside it;
+    // the float exposure time moves the onset by < 1e-3 h
+    const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
+    if (!(h->cfg.window_hours <= latent - 1e-3))
+        return fail(h, HEROS_ERR_UNSUPPORTED, "window_hours must be below the latent period of the transmission model");
+    cudaSetDevice(h->cfg.device);
+    rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    const Counters before = *h->h_ctr;
+    heros_step_stats st{};
+    int launches = 0;
+    float transmit_ms = 0.f;
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    while (h->t_now < t_until)
+    {
+        const double T0 = h->t_now;
+        const double T1 = std::min(T0 + h->cfg.window_hours, t_until);
+        rc = run_window(h, T0, T1, launches, transmit_ms);
+        if (rc != HEROS_OK) return rc;
+        h->t_now = T1;
+        st.windows++;
+        st.visits += (int64_t) h->h_ctr->n_active;
+        st.sublocations += (int64_t) h->h_ctr->n_seg;
+    }
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    const Counters& now = *h->h_ctr;
+    st.evaluations = (int64_t) (now.evaluations - before.evaluations);
+    st.draws = (int64_t) (now.draws - before.draws);
+    st.infections = (int64_t) (now.infections - before.infections);
+    st.transitions = (int64_t) (now.transitions - before.transitions);
+    st.near_ties = (int64_t) (now.near_ties - before.near_ties);
+    st.gpu_launches = launches;
+    st.gpu_ms = ms;
+    st.transmit_ms = transmit_ms;
+    if (stats) *stats = st;
+    return HEROS_OK;
+}
+
+int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
+                             int16_t* sublocation, double* time, double* p, int64_t* n_out)
+{
+    if (!h || !n_out || first < 0 || capacity < 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_inf_log, h->inf_person.n);
+    if (n != h->o_inf_n)
+    {
+        std::vector<uint32_t> per(n), key(n);
+        std::vector<double> t(n), pp(n);
+        if (n)
+        {
+            CU(h, cudaMemcpyAsync(per.data(), h->inf_person.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(key.data(), h->inf_key.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(t.data(), h->inf_t.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(pp.data(), h->inf_p.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+        }
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return t[a] < t[b] || (t[a] == t[b] && per[a] < per[b]);
+        });
+        h->o_inf_person.resize(n); h->o_inf_key.resize(n); h->o_inf_t.resize(n); h->o_inf_p.resize(n);
+        for (size_t i = 0; i < n; ++i)
+        {
+            h->o_inf_person[i] = per[order[i]]; h->o_inf_key[i] = key[order[i]];
+            h->o_inf_t[i] = t[order[i]]; h->o_inf_p[i] = pp[order[i]];
+        }
+        h->o_inf_n = n;
+    }
+    const int64_t avail = std::max<int64_t>(0, (int64_t) n - first);
+    const int64_t m = std::min(avail, capacity);
+    for (int64_t i = 0; i < m; ++i)
+    {
+        const size_t k = (size_t) (first + i);
+        const uint32_t key = h->o_inf_key[k];
+        const uint32_t loc = (uint32_t) (std::upper_bound(h->h_loc_base.begin(), h->h_loc_base.end(), key) -
+                                         h->h_loc_base.begin() - 1);
+        if (person) person[i] = (int32_t) h->o_inf_person[k];
+        if (location) location[i] = (int32_t) loc;
+        if (sublocation) sublocation[i] = (int16_t) (key - h->h_loc_base[loc]);
+        if (time) time[i] = h->o_inf_t[k];
+        if (p) p[i] = h->o_inf_p[k];
+    }
+    *n_out = avail;
+    return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, int32_t* person, uint8_t* phase,
+                              double* time, int64_t* n_out)
+{
+    if (!h || !n_out || first < 0 || capacity < 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_tr_log, h->tr_person.n);
+    if (n != h->o_tr_n)
+    {
+        std::vector<uint32_t> per(n);
+        std::vector<uint8_t> ph(n);
+        std::vector<double> t(n);
+        if (n)
+        {
+            CU(h, cudaMemcpyAsync(per.data(), h->tr_person.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(ph.data(), h->tr_phase.p, n, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(t.data(), h->tr_time.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+        }
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return t[a] < t[b] || (t[a] == t[b] && per[a] < per[b]);
+        });
+        h->o_tr_person.resize(n); h->o_tr_phase.resize(n); h->o_tr_time.resize(n);
+        for (size_t i = 0; i < n; ++i)
+        {
+            h->o_tr_person[i] = per[order[i]]; h->o_tr_phase[i] = ph[order[i]]; h->o_tr_time[i] = t[order[i]];
+        }
+        h->o_tr_n = n;
+    }
+    const int64_t avail = std::max<int64_t>(0, (int64_t) n - first);
+    const int64_t m = std::min(avail, capacity);
+    for (int64_t i = 0; i < m; ++i)
+    {
+        const size_t k = (size_t) (first + i);
+        if (person) person[i] = (int32_t) h->o_tr_person[k];
+        if (phase) phase[i] = h->o_tr_phase[k];
+        if (time) time[i] = h->o_tr_time[k];
+    }
+    *n_out = avail;
+    return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+int32_t heros_get_phase_counts(heros_handle h, int64_t counts[8])
+{
+    if (!h || !counts) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    for (int k = 0; k < 8; ++k) counts[k] = (int64_t) h->h_ctr->phase_counts[k];
+    return HEROS_OK;
+}
+
+int32_t heros_get_count_series(heros_handle h, int64_t capacity, double* times, int64_t* counts, int64_t* n_out)
+{
+    if (!h || !n_out || capacity < 0) return HEROS_ERR_INVALID;
+    const int64_t n = (int64_t) h->series_t.size();
+    const int64_t m = std::min(n, capacity);
+    if (times) memcpy(times, h->series_t.data(), (size_t) m * 8);
+    if (counts) memcpy(counts, h->series_counts.data(), (size_t) m * 64);
+    *n_out = n;
+    return m < n && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+int32_t heros_get_agent_state(heros_handle h, uint8_t* phase, float* exposure, double* next_time, uint8_t* next_phase)
+{
+    if (!h || h->n_agents == 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    std::vector<uint64_t> view(h->n_agents);
+    CU(h, cudaMemcpyAsync(view.data(), h->d_view.p, (size_t) h->n_agents * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (next_time)
+        CU(h, cudaMemcpyAsync(next_time, h->d_next_time.p, (size_t) h->n_agents * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t a = 0; a < h->n_agents; ++a)
+    {
+        if (phase) phase[a] = (uint8_t) view_phase(view[a]);
+        if (exposure) exposure[a] = view_exposure(view[a]);
+        if (next_phase) next_phase[a] = (uint8_t) view_next_phase(view[a]);
+    }
+    return HEROS_OK;
+}
+
+int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, const uint8_t* phase,
+                              const float* exposure, double now)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (n < 0 || (n > 0 && (!person || !phase || !exposure))) return fail(h, HEROS_ERR_INVALID, "null argument");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    DevBuf<uint8_t> d_phase; DevBuf<float> d_exp;
+    CU(h, h->st_person.ensure(n)); CU(h, d_phase.ensure(n)); CU(h, d_exp.ensure(n));
+    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(d_phase.p, phase, (size_t) n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(d_exp.p, exposure, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_set_agent_state<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, d_phase.p,
+                                                            d_exp.p, now, h->n_agents);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    d_phase.release(); d_exp.release();
+    return HEROS_OK;
+}
+
+int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out)
+{
+    if (!h || !out || location < 0 || (uint32_t) location >= h->n_loc || sublocation < 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    const uint32_t key = h->h_loc_base[location] + (uint32_t) sublocation;
+    if (key >= h->h_loc_base[location + 1]) return fail(h, HEROS_ERR_INVALID, "sub-location out of range");
+    CU(h, cudaMemcpyAsync(out, h->d_last_calc.p + key, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_get_time(heros_handle h, double* now)
+{
+    if (!h || !now) return HEROS_ERR_INVALID;
+    *now = h->t_now;
+    return HEROS_OK;
+}
+
+int32_t heros_infect_people(heros_handle h, int32_t location, int32_t n_persons, const int32_t* persons, int32_t n_all,
+                            const int32_t* all_persons, double now, double duration, int32_t* calculated,
+                            int32_t* infectious_out, int32_t* n_infectious, int32_t* infected_out, int32_t* n_infected,
+                            double* p_infection)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (location < 0 || (uint32_t) location >= h->n_loc || n_persons < 0 || n_all < 0 || (n_persons && !persons))
+        return fail(h, HEROS_ERR_INVALID, "bad argument");
+    const int type = h->h_loc_type[location];
+    const int infect_sub = h->type_infect_sub[type];
+    const int n_sub_locations = h->h_loc_nsub[location];
+    const bool total_branch = !(infect_sub || n_sub_locations < 2);
+    if (total_branch && n_all > 0 && !all_persons) return fail(h, HEROS_ERR_INVALID, "all_persons required for the total-location branch");
+    for (int i = 0; i < n_persons; ++i)
+        if (persons[i] < 0 || (uint32_t) persons[i] >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
+    for (int i = 0; i < (total_branch ? n_all : 0); ++i)
+        if (all_persons[i] < 0 || (uint32_t) all_persons[i] >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
+    cudaSetDevice(h->cfg.device);
+    const int cap = std::max(std::max(n_persons, n_all), 1);
+    DevBuf<int32_t> d_sub, d_all, d_infectious, d_infected;
+    DevBuf<ShimOut> d_out;
+    CU(h, d_sub.ensure(cap)); CU(h, d_all.ensure(cap)); CU(h, d_infectious.ensure(cap)); CU(h, d_infected.ensure(cap));
+    CU(h, d_out.ensure(1));
+    if (n_persons) CU(h, cudaMemcpyAsync(d_sub.p, persons, (size_t) n_persons * 4, cudaMemcpyHostToDevice, h->stream));
+    if (total_branch && n_all) CU(h, cudaMemcpyAsync(d_all.p, all_persons, (size_t) n_all * 4, cudaMemcpyHostToDevice, h->stream));
+    double psi = h->dist.psi, mu = h->dist.mu;
+    for (const PolicyChange& pc : h->policy)
+    {
+        if (!(pc.t <= now)) break;
+        if (pc.which == 0) psi = pc.value; else mu = pc.value;
+    }
+    k_infect_people<<<1, 32, 0, h->stream>>>(h->cfg.model, h->area, h->dist, psi, mu, h->cfg.seed, infect_sub,
+                                             n_sub_locations, (double) h->h_loc_area[location], h->type_corr[type],
+                                             h->d_view.p, n_persons, d_sub.p, total_branch ? n_all : 0, d_all.p, now,
+                                             duration, d_infectious.p, d_infected.p, d_out.p);
+    CU(h, cudaGetLastError());
+    ShimOut o{};
+    CU(h, cudaMemcpyAsync(&o, d_out.p, sizeof(o), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (infectious_out && o.n_infectious)
+        CU(h, cudaMemcpy(infectious_out, d_infectious.p, (size_t) o.n_infectious * 4, cudaMemcpyDeviceToHost));
+    if (infected_out && o.n_infected)
+        CU(h, cudaMemcpy(infected_out, d_infected.p, (size_t) o.n_infected * 4, cudaMemcpyDeviceToHost));
+    if (calculated) *calculated = o.calculated;
+    if (n_infectious) *n_infectious = o.n_infectious;
+    if (n_infected) *n_infected = o.n_infected;
+    if (p_infection) *p_infection = o.p;
+    d_sub.release(); d_all.release(); d_infectious.release(); d_infected.release(); d_out.release();
+    return HEROS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// engine.cuh -- engine state shared by the translation units of libheros_gpu.so
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/heros_gpu.h"
+#include "heros_math.cuh"
+
+namespace heros {
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr uint64_t BEST_NONE = ~0ull;
+
+// per-location constants of the transmission formulas, precomputed once (heros_set_locations)
+struct LocParam
+{
+    double area_sub;  // (double) totalSurfaceM2 / nSub         (TArea:155, TDist:137)
+    double denom;     // correctionFactorArea * area_sub        (TArea:156)
+};
+
+struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
+
+// device-side counters of one engine (zeroed per heros_step call, except the log cursors)
+struct Counters
+{
+    unsigned long long evaluations, draws, near_ties, infections, transitions;
+    unsigned long long n_cand;       // candidate infections of the current window
+    unsigned long long n_inf_log;    // cursor of the infection log
+    unsigned long long n_tr_log;     // cursor of the transition log
+    unsigned long long n_big;        // big segments of the current window
+    unsigned long long scratch_top;  // bump allocator for big-segment scratch (event slots)
+    unsigned long long n_keep;       // stays kept in the pool after the window
+    unsigned long long n_seg;        // occupied sub-locations of the current window
+    unsigned long long n_active;     // active stays of the current window
+    unsigned int overflow;           // bit 0 cand, 1 scratch, 2 transition log, 3 infection log
+    unsigned int invalid_visits;     // rejected by heros_submit_visits
+    unsigned int late_visits;        // t_in before the engine time
+    unsigned int pad;
+    long long phase_counts[8];
+};
+
+template <typename T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want, bool keep = false, cudaStream_t s = 0)
+    {
+        if (want <= n) return cudaSuccess;
+        size_t cap = want + want / 4 + 1024;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, cap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && n) e = cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+        p = q; n = cap;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// everything the window kernels need, passed by value
+struct WindowCtx
+{
+    // window
+    double T0, T1;
+    int model, trigger;
+    uint64_t seed;
+    AreaParams area;
+    DistParams dist;
+    const PolicyChange* policy; int n_policy;
+    // static tables
+    const uint32_t* key_loc; const LocParam* loc_param; double* last_calc; uint32_t n_keys;
+    // agents
+    const uint64_t* view; const double* ill_end;
+    // sorted stays of the window
+    const uint32_t* s_key; const uint32_t* s_person; const double* s_tin; const double* s_tout; const uint64_t* s_view;
+    const uint32_t* seg_start;  // n_seg + 1 entries
+    // candidates
+    uint32_t* cand_person; uint32_t* cand_key; double* cand_t; double* cand_p; uint32_t cand_cap;
+    // big-segment work list + scratch
+    uint32_t* big_seg; uint32_t* big_off; uint32_t big_cap;
+    uint64_t* sc_evt; uint32_t* sc_evx; int32_t* sc_pre; uint32_t* sc_j0; uint32_t* sc_j1; double* sc_cand;
+    uint32_t* sc_node; double* sc_p; double* sc_dur; uint32_t* sc_ill; uint64_t scratch_cap;
+    Counters* ctr;
+};
+
+}  // namespace heros

@@ -1,0 +1,219 @@
+"""numpy-facing wrapper of the C ABI (include/heros_gpu.h): one ``HerosEngine`` = one ``heros_handle``."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import HerosError
+
+
+def _arr(x, dtype):
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HerosEngine:
+    """The GPU engine for the transmission + progression hot path.  All compute happens in libheros_gpu.so."""
+
+    def __init__(self, model: int, seed: int, trigger: int = _lib.TRIGGER_EXIT_ONLY, device: int = 0,
+                 window_hours: float = 24.0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        cfg = _lib.Config(_lib.ABI_VERSION, int(model), int(trigger), int(device), int(seed) & (2 ** 64 - 1),
+                          float(window_hours))
+        rc = self._lib.heros_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.OK:
+            msg = self._lib.heros_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise HerosError(rc, msg)
+        self.model = int(model)
+        self.n_persons = 0
+        self.n_locations = 0
+
+    # ---- plumbing ----
+    def _check(self, rc: int):
+        if rc != _lib.OK:
+            raise HerosError(rc, self._lib.heros_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.heros_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- static inputs ----
+    def set_location_types(self, infect_sub, correction_factor_area, cap_constrained=None, cap_persons_per_m2=None,
+                           size_factor=None):
+        a = _arr(infect_sub, np.uint8)
+        b = _arr(correction_factor_area, np.float64)
+        c = None if cap_constrained is None else _arr(cap_constrained, np.uint8)
+        d = None if cap_persons_per_m2 is None else _arr(cap_persons_per_m2, np.float64)
+        e = None if size_factor is None else _arr(size_factor, np.float64)
+        self._check(self._lib.heros_set_location_types(self._h, len(a), _p(a), _p(b), _p(c), _p(d), _p(e)))
+
+    def set_locations(self, type_, n_sub, total_area, lat=None, lon=None):
+        a = _arr(type_, np.uint8)
+        b = _arr(n_sub, np.int16)
+        c = _arr(total_area, np.float32)
+        d = None if lat is None else _arr(lat, np.float32)
+        e = None if lon is None else _arr(lon, np.float32)
+        self._check(self._lib.heros_set_locations(self._h, len(a), _p(a), _p(b), _p(c), _p(d), _p(e)))
+        self.n_locations = len(a)
+
+    def set_persons(self, age, female, role=None, home_loc=None, home_sub=None, work_loc=None):
+        a = _arr(age, np.int8)
+        b = _arr(female, np.uint8)
+        c = None if role is None else _arr(role, np.uint8)
+        d = None if home_loc is None else _arr(home_loc, np.int32)
+        e = None if home_sub is None else _arr(home_sub, np.int16)
+        f = None if work_loc is None else _arr(work_loc, np.int32)
+        self._check(self._lib.heros_set_persons(self._h, len(a), _p(a), _p(b), _p(c), _p(d), _p(e), _p(f)))
+        self.n_persons = len(a)
+
+    # ---- parameters ----
+    def set_transmission_area(self, params: _lib.AreaParams):
+        self._check(self._lib.heros_set_transmission_area(self._h, C.byref(params)))
+
+    def set_transmission_distance(self, params: _lib.DistParams):
+        self._check(self._lib.heros_set_transmission_distance(self._h, C.byref(params)))
+
+    def set_progression(self, params: _lib.ProgParams):
+        self._check(self._lib.heros_set_progression(self._h, C.byref(params)))
+
+    def set_parameter(self, name: str, value: float, at_time: float) -> int:
+        """Returns the status instead of raising for unknown names (the reference only prints a message)."""
+        rc = self._lib.heros_set_parameter(self._h, name.encode(), float(value), float(at_time))
+        if rc not in (_lib.OK, _lib.ERR_UNKNOWN_PARAMETER):
+            self._check(rc)
+        return rc
+
+    # ---- dynamic inputs ----
+    def expose(self, person, at_time):
+        a = _arr(person, np.int32)
+        b = np.broadcast_to(_arr(at_time, np.float64), a.shape).copy()
+        self._check(self._lib.heros_expose(self._h, len(a), _p(a), _p(b)))
+
+    def seed_infections(self, n_infected: int, min_age: int = 0, max_age: int = 127) -> np.ndarray:
+        out = np.zeros(n_infected, np.int32)
+        self._check(self._lib.heros_seed_infections(self._h, n_infected, min_age, max_age, _p(out)))
+        return out
+
+    def submit_visits(self, person, loc, sub, t_in, t_out):
+        a = _arr(person, np.int32)
+        b = _arr(loc, np.int32)
+        c = _arr(sub, np.int16)
+        d = _arr(t_in, np.float64)
+        e = _arr(t_out, np.float64)
+        if not (len(a) == len(b) == len(c) == len(d) == len(e)):
+            raise ValueError("visit columns differ in length")
+        self._check(self._lib.heros_submit_visits(self._h, len(a), _p(a), _p(b), _p(c), _p(d), _p(e)))
+
+    def submit_visits_ptr(self, n: int, person: int, loc: int, sub: int, t_in: int, t_out: int, device: bool):
+        """Raw-pointer submission (pinned host buffers or device buffers, e.g. torch tensors' data_ptr())."""
+        fn = self._lib.heros_submit_visits_device if device else self._lib.heros_submit_visits
+        self._check(fn(self._h, n, C.c_void_p(person), C.c_void_p(loc), C.c_void_p(sub), C.c_void_p(t_in),
+                       C.c_void_p(t_out)))
+
+    # ---- hot path ----
+    def step(self, t_until: float) -> Dict[str, float]:
+        st = _lib.StepStats()
+        self._check(self._lib.heros_step(self._h, float(t_until), C.byref(st)))
+        return st.as_dict()
+
+    # ---- outputs ----
+    def infections(self, first: int = 0) -> Dict[str, np.ndarray]:
+        n = C.c_int64(0)
+        self._check(self._lib.heros_get_infections(self._h, first, 0, None, None, None, None, None, C.byref(n)))
+        m = n.value
+        person = np.zeros(m, np.int32)
+        loc = np.zeros(m, np.int32)
+        sub = np.zeros(m, np.int16)
+        t = np.zeros(m, np.float64)
+        p = np.zeros(m, np.float64)
+        if m:
+            self._check(self._lib.heros_get_infections(self._h, first, m, _p(person), _p(loc), _p(sub), _p(t), _p(p),
+                                                       C.byref(n)))
+        return dict(person=person, loc=loc, sub=sub, time=t, p=p)
+
+    def transitions(self, first: int = 0) -> Dict[str, np.ndarray]:
+        n = C.c_int64(0)
+        self._check(self._lib.heros_get_transitions(self._h, first, 0, None, None, None, C.byref(n)))
+        m = n.value
+        person = np.zeros(m, np.int32)
+        phase = np.zeros(m, np.uint8)
+        t = np.zeros(m, np.float64)
+        if m:
+            self._check(self._lib.heros_get_transitions(self._h, first, m, _p(person), _p(phase), _p(t), C.byref(n)))
+        return dict(person=person, phase=phase, time=t)
+
+    def phase_counts(self) -> np.ndarray:
+        c = np.zeros(8, np.int64)
+        self._check(self._lib.heros_get_phase_counts(self._h, _p(c)))
+        return c
+
+    def count_series(self):
+        n = C.c_int64(0)
+        self._check(self._lib.heros_get_count_series(self._h, 0, None, None, C.byref(n)))
+        m = n.value
+        t = np.zeros(m, np.float64)
+        c = np.zeros((m, 8), np.int64)
+        if m:
+            self._check(self._lib.heros_get_count_series(self._h, m, _p(t), _p(c), C.byref(n)))
+        return t, c
+
+    def agent_state(self) -> Dict[str, np.ndarray]:
+        n = self.n_persons
+        phase = np.zeros(n, np.uint8)
+        exposure = np.zeros(n, np.float32)
+        next_time = np.zeros(n, np.float64)
+        next_phase = np.zeros(n, np.uint8)
+        self._check(self._lib.heros_get_agent_state(self._h, _p(phase), _p(exposure), _p(next_time), _p(next_phase)))
+        return dict(phase=phase, exposure=exposure, next_time=next_time, next_phase=next_phase)
+
+    def set_agent_state(self, person, phase, exposure, now: float = 0.0):
+        a = _arr(person, np.int32)
+        b = _arr(phase, np.uint8)
+        c = _arr(exposure, np.float32)
+        self._check(self._lib.heros_set_agent_state(self._h, len(a), _p(a), _p(b), _p(c), float(now)))
+
+    def last_calculation(self, loc: int, sub: int) -> float:
+        out = C.c_double(0.0)
+        self._check(self._lib.heros_get_last_calculation(self._h, int(loc), int(sub), C.byref(out)))
+        return out.value
+
+    @property
+    def time(self) -> float:
+        out = C.c_double(0.0)
+        self._check(self._lib.heros_get_time(self._h, C.byref(out)))
+        return out.value
+
+    def infect_people(self, location: int, persons_in_sublocation, now: float, duration: float, all_persons=None):
+        """1:1 shim of DiseaseTransmission.infectPeople evaluated on the GPU; returns a dict."""
+        a = _arr(persons_in_sublocation, np.int32)
+        b = None if all_persons is None else _arr(all_persons, np.int32)
+        cap = max(len(a), 0 if b is None else len(b), 1)
+        infectious = np.zeros(cap, np.int32)
+        infected = np.zeros(cap, np.int32)
+        calc, n1, n2, p = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        self._check(self._lib.heros_infect_people(self._h, int(location), len(a), _p(a), 0 if b is None else len(b),
+                                                  _p(b), float(now), float(duration), C.byref(calc), _p(infectious),
+                                                  C.byref(n1), _p(infected), C.byref(n2), C.byref(p)))
+        return dict(calculated=bool(calc.value), infectious=infectious[:n1.value].copy(),
+                    infected=infected[:n2.value].copy(), p=p.value)
