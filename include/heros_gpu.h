@@ -98,8 +98,16 @@ typedef struct heros_step_stats {
     int64_t transitions;      /* disease-phase transitions applied (incl. exposures) */
     int64_t gpu_launches;     /* kernels launched by this call */
     double gpu_ms;            /* device time of this call (CUDA events on the engine stream) */
-    double transmit_ms;       /* of which: transmission kernels */
+    double transmit_ms;       /* of which: transmission kernels (small + big segments) */
     int64_t near_ties;        /* draws with |u - p| < 1e-13 (a flip could differ from the fp64 CPU result) */
+    /* device time per stage, summed over the windows of the call (CUDA events on the engine stream) */
+    double progress_ms;       /* disease-phase state machine */
+    double bucket_ms;         /* window list + radix sort by sub-location + gather + segment offsets */
+    double transmit_small_ms; /* warp-per-sub-location kernel */
+    double transmit_big_ms;   /* block-per-sub-location kernel */
+    double resolve_ms;        /* earliest-draw-wins + expose */
+    double retire_ms;         /* pool compaction */
+    int64_t big_sublocations; /* segments handled by the block kernel */
 } heros_step_stats;
 
 /* ---- lifecycle ---- */

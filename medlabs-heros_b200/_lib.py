@@ -46,7 +46,9 @@ class StepStats(C.Structure):
     _fields_ = [("windows", C.c_int64), ("visits", C.c_int64), ("sublocations", C.c_int64),
                 ("evaluations", C.c_int64), ("draws", C.c_int64), ("infections", C.c_int64),
                 ("transitions", C.c_int64), ("gpu_launches", C.c_int64), ("gpu_ms", C.c_double),
-                ("transmit_ms", C.c_double), ("near_ties", C.c_int64)]
+                ("transmit_ms", C.c_double), ("near_ties", C.c_int64), ("progress_ms", C.c_double),
+                ("bucket_ms", C.c_double), ("transmit_small_ms", C.c_double), ("transmit_big_ms", C.c_double),
+                ("resolve_ms", C.c_double), ("retire_ms", C.c_double), ("big_sublocations", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

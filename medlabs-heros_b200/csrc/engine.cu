@@ -24,7 +24,7 @@
 
 namespace heros {
 
-void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches);
+void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between);
 
 namespace {
 
@@ -464,7 +464,8 @@ struct heros_engine
     heros_config cfg{};
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4]{};
+    cudaEvent_t ev[10]{};
+    double stage_ms[6]{};  // progress, bucket, transmit small, transmit big, resolve, retire (current heros_step)
     int n_sm = 148;
     double t_now = 0.0;
 
@@ -608,7 +609,7 @@ int32_t check_ready(heros_handle h)
 }
 
 // one window [T0, T1)
-int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& transmit_ms)
+int32_t run_window(heros_handle h, double T0, double T1, int& launches)
 {
     cudaStream_t s = h->stream;
     const uint32_t N = h->n_agents;
@@ -617,6 +618,7 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
     const int cur = h->pool_cur, oth = cur ^ 1;
     const uint32_t inactive_key = h->n_keys;
 
+    CU(h, cudaEventRecord(h->ev[2], s));
     k_zero_window<<<1, 1, 0, s>>>(h->d_ctr.p);
     ++launches;
 
@@ -624,6 +626,8 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
     const AgentArrays A = agent_arrays(h);
     k_progress<<<blocks_for(N), TPB, 0, s>>>(A, N, T1);
     ++launches;
+
+    CU(h, cudaEventRecord(h->ev[3], s));
 
     // 2. window list keys
     CU(h, h->wl_key.ensure(n_total)); CU(h, h->wl_idx.ensure(n_total));
@@ -683,9 +687,9 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
     c.sc_cand = h->sc_cand.p; c.sc_node = h->sc_node.p; c.sc_p = h->sc_p.p; c.sc_dur = h->sc_dur.p;
     c.sc_ill = h->sc_ill.p; c.scratch_cap = h->sc_evt.n;
     c.ctr = h->d_ctr.p;
-    CU(h, cudaEventRecord(h->ev[2], s));
-    launch_transmit(c, h->n_sm, s, launches);
-    CU(h, cudaEventRecord(h->ev[3], s));
+    CU(h, cudaEventRecord(h->ev[4], s));
+    launch_transmit(c, h->n_sm, s, launches, h->ev[5]);
+    CU(h, cudaEventRecord(h->ev[6], s));
 
     // 6. resolve: earliest successful draw per person wins
     const CandArrays C{h->cand_person.p, h->cand_key.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
@@ -696,6 +700,7 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
     k_resolve_apply<<<rg, TPB, 0, s>>>(C, A, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, log, T1);
     k_resolve_reset<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->d_claim.p);
     launches += 4;
+    CU(h, cudaEventRecord(h->ev[7], s));
 
     // 7. retire the stays that ended before T1
     if (n_pool > 0)
@@ -705,6 +710,7 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
         k_retire_gather<<<h->n_sm * 4, TPB, 0, s>>>(P, pool_arrays(h, oth), h->keep_idx.p, h->d_nsel.p + 1, h->d_ctr.p);
         launches += 3;
     }
+    CU(h, cudaEventRecord(h->ev[8], s));
     CU(h, cudaGetLastError());
     int32_t rc = sync_counters(h);
     if (rc != HEROS_OK) return rc;
@@ -713,9 +719,12 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches, float& t
         h->n_pool = (uint32_t) h->h_ctr->n_keep;
         h->pool_cur = oth;
     }
-    float ms = 0.f;
-    CU(h, cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
-    transmit_ms += ms;
+    for (int k = 0; k < 6; ++k)
+    {
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, h->ev[2 + k], h->ev[3 + k]));
+        h->stage_ms[k] += ms;
+    }
     if (h->h_ctr->overflow)
     {
         char buf[160];
@@ -1082,18 +1091,20 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
     const Counters before = *h->h_ctr;
     heros_step_stats st{};
     int launches = 0;
-    float transmit_ms = 0.f;
+    int64_t n_big = 0;
+    for (double& m : h->stage_ms) m = 0.0;
     CU(h, cudaEventRecord(h->ev[0], h->stream));
     while (h->t_now < t_until)
     {
         const double T0 = h->t_now;
         const double T1 = std::min(T0 + h->cfg.window_hours, t_until);
-        rc = run_window(h, T0, T1, launches, transmit_ms);
+        rc = run_window(h, T0, T1, launches);
         if (rc != HEROS_OK) return rc;
         h->t_now = T1;
         st.windows++;
         st.visits += (int64_t) h->h_ctr->n_active;
         st.sublocations += (int64_t) h->h_ctr->n_seg;
+        n_big += (int64_t) h->h_ctr->n_big;
     }
     CU(h, cudaEventRecord(h->ev[1], h->stream));
     CU(h, cudaEventSynchronize(h->ev[1]));
@@ -1107,7 +1118,11 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
     st.near_ties = (int64_t) (now.near_ties - before.near_ties);
     st.gpu_launches = launches;
     st.gpu_ms = ms;
-    st.transmit_ms = transmit_ms;
+    st.progress_ms = h->stage_ms[0]; st.bucket_ms = h->stage_ms[1];
+    st.transmit_small_ms = h->stage_ms[2]; st.transmit_big_ms = h->stage_ms[3];
+    st.resolve_ms = h->stage_ms[4]; st.retire_ms = h->stage_ms[5];
+    st.transmit_ms = h->stage_ms[2] + h->stage_ms[3];
+    st.big_sublocations = n_big;
     if (stats) *stats = st;
     return HEROS_OK;
 }

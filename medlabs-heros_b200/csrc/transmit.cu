@@ -496,17 +496,19 @@ __global__ void __launch_bounds__(BIG_THREADS) k_transmit_big(const WindowCtx c)
 }
 
 // host-side launchers --------------------------------------------------------------------------------------------------
-void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches)
+void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between)
 {
     const int grid = n_sm * 8;
     if (c.model == HEROS_MODEL_AREA)
     {
         k_transmit_small<HEROS_MODEL_AREA><<<grid, 256, 0, s>>>(c);
+        cudaEventRecord(between, s);
         k_transmit_big<HEROS_MODEL_AREA><<<n_sm * 8, BIG_THREADS, 0, s>>>(c);
     }
     else
     {
         k_transmit_small<HEROS_MODEL_DISTANCE><<<grid, 256, 0, s>>>(c);
+        cudaEventRecord(between, s);
         k_transmit_big<HEROS_MODEL_DISTANCE><<<n_sm * 8, BIG_THREADS, 0, s>>>(c);
     }
     launches += 2;

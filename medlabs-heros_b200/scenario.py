@@ -1,0 +1,398 @@
+"""Synthetic populations and the host-side activity-schedule generator.
+
+The reference's population blobs (people.csv.gz / locations.csv.gz of The Hague, Haaglanden, Europe) are not shipped
+(/root/reference/.MISSING_LARGE_BLOBS), so every benchmark configuration runs on a synthetic city that follows the
+documented schema (metadata/DataDictionary.xlsx; ConstructHerosModel.java:300-395, 450-758):
+
+  * location mix, sub-location counts and per-sub-location areas scaled from the one real table that is shipped
+    (data/helsinki/locations.csv.gz: 69 508 locations, 431 470 sub-locations; per-category statistics in CATEGORIES),
+  * location type ids = row order of data/thehague/locations/locationtypes.csv,
+  * social roles 1..15 by age (ConstructHerosModel.java:565-743), households mapped to Accommodation sub-locations
+    (:531-552),
+  * daily stays produced from the reference's own activity schedule rows (policy 0 of activityschedules_cap.xlsx,
+    compiled to data/activity_patterns_thehague.json by tools/make_schedule_fixture.py) with counter-based Philox
+    draws keyed by (seed, person, day, activity), so the stream is reproducible on any device.
+
+This module is host-side set-up code (numpy); it stands in for the medlabs activity engine the Java host keeps.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+
+# type ids = row order of data/thehague/locations/locationtypes.csv
+TYPE_NAMES = ["Accommodation", "Workplace", "Retail", "Mall", "BarRestaurant", "FoodBeverage", "Supermarket",
+              "Kindergarten", "PrimarySchool", "SecondarySchool", "College", "University", "Religion", "Police",
+              "FireStation", "Pharmacy", "Healthcare", "Hospital", "Recreation", "Park", "Satellite accommodation",
+              "Satellite workplace"]
+TYPE_ID = {n: i for i, n in enumerate(TYPE_NAMES)}
+# locationtypes.csv columns infectSub / contagiousRateFactor (Park .. Satellite* have infectSub = FALSE)
+TYPE_INFECT_SUB = np.array([1] * 19 + [0, 0, 0], np.uint8)
+TYPE_CORRECTION = np.ones(22, np.float64)
+
+# (category, share of locations, sub-locations per location, m2 per sub-location) from data/helsinki/locations.csv.gz
+CATEGORIES = [
+    ("Workplace", 42169, None, 30.0), ("Accommodation", 20512, None, 100.0), ("BarRestaurant", 2255, 1, 200.0),
+    ("Retail", 2239, 1, 100.0), ("Park", 506, 1, 300000.0), ("Kindergarten", 356, 6, 50.0),
+    ("FoodBeverage", 355, 1, 100.0), ("Recreation", 293, 4, 250.0), ("Healthcare", 233, 3, 100.0),
+    ("PrimarySchool", 173, 10, 75.0), ("Supermarket", 89, 1, 200.0), ("SecondarySchool", 74, 30, 75.0),
+    ("Pharmacy", 67, 1, 75.0), ("Religion", 48, 1, 250.0), ("Mall", 37, 50, 100.0), ("University", 28, 100, 100.0),
+    ("FireStation", 25, 10, 100.0), ("Hospital", 24, 650, 75.0), ("College", 22, 50, 100.0), ("Police", 3, 25, 30.0),
+]
+HELSINKI_LOCATIONS = 69508
+
+ROLE_INFANT, ROLE_KINDERGARTEN, ROLE_PRIMARY, ROLE_SECONDARY, ROLE_COLLEGE, ROLE_UNIVERSITY, ROLE_WORKER, \
+    ROLE_PENSIONER, ROLE_UNEMPLOYED, ROLE_WEEKEND_WORKER, ROLE_ESSENTIAL_WORKER = range(1, 12)
+
+TAG_SCHEDULE = 0x300
+NONE = -1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vectorised Philox4x32-10 (same function as csrc/heros_math.cuh)
+# ---------------------------------------------------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    u64, u32 = np.uint64, np.uint32
+    c0 = np.asarray(c0, u32).astype(u64)
+    shape = c0.shape
+    c1 = np.broadcast_to(np.asarray(c1, u32), shape).astype(u64)
+    c2 = np.broadcast_to(np.asarray(c2, u32), shape).astype(u64)
+    c3 = np.broadcast_to(np.asarray(c3, u32), shape).astype(u64)
+    k0 = u64(int(k0) & 0xFFFFFFFF)
+    k1 = u64(int(k1) & 0xFFFFFFFF)
+    m0, m1, mask = u64(0xD2511F53), u64(0xCD9E8D57), u64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = m0 * c0
+        p1 = m1 * c2
+        n0 = (p1 >> u64(32)) ^ c1 ^ k0
+        n2 = (p0 >> u64(32)) ^ c3 ^ k1
+        c0, c1, c2, c3 = n0, p1 & mask, n2, p0 & mask
+        k0 = (k0 + u64(0x9E3779B9)) & mask
+        k1 = (k1 + u64(0xBB67AE85)) & mask
+    return c0, c1, c2, c3
+
+
+def u01_from_words(x, y):
+    return ((((x << np.uint64(32)) | y) >> np.uint64(11)).astype(np.float64)) * 2.0 ** -53
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# city
+# ---------------------------------------------------------------------------------------------------------------------
+class City:
+    """Static tables of a synthetic city, in the layout heros_set_location_types / _locations / _persons take."""
+
+    def __init__(self, n_persons: int, seed: int = 20240807, n_locations: Optional[int] = None,
+                 box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8):
+        rng = np.random.default_rng(seed)
+        self.n_persons = int(n_persons)
+        if n_locations is None:
+            n_locations = int(round(143178 * n_persons / 553667))  # The Hague: 143 178 locations for 553 667 persons
+        scale = n_locations / HELSINKI_LOCATIONS
+        self.type_infect_sub = TYPE_INFECT_SUB.copy()
+        self.type_correction = TYPE_CORRECTION.copy()
+
+        n_households = max(1, int(round(n_persons / 2.15)))
+        types, nsubs, per_sub_area = [], [], []
+        for name, count, nsub, area in CATEGORIES:
+            k = max(1, int(round(count * scale)))
+            if name == "Accommodation":
+                k = max(1, min(k, n_households))
+                sub = np.zeros(k, np.int64)  # filled below from the households
+            elif name == "Workplace":
+                sub = np.minimum(1 + np.floor(rng.exponential(1.75, k)).astype(np.int64), 100)
+            else:
+                sub = np.full(k, nsub, np.int64)
+            types.append(np.full(k, TYPE_ID[name], np.uint8))
+            nsubs.append(sub)
+            per_sub_area.append(np.full(k, area))
+        loc_type = np.concatenate(types)
+        loc_nsub = np.concatenate(nsubs)
+        area_sub = np.concatenate(per_sub_area)
+        n_loc = len(loc_type)
+        x = origin_m[0] + rng.random(n_loc) * box_m[0]
+        y = origin_m[1] + rng.random(n_loc) * box_m[1]
+
+        # households -> Accommodation sub-locations in order of first appearance (ConstructHerosModel.java:531-552)
+        acc = np.nonzero(loc_type == TYPE_ID["Accommodation"])[0]
+        hh_building = acc[rng.integers(0, len(acc), n_households)]
+        order = np.argsort(hh_building, kind="stable")
+        hh_sub = np.zeros(n_households, np.int64)
+        sorted_b = hh_building[order]
+        first = np.r_[True, sorted_b[1:] != sorted_b[:-1]]
+        start = np.maximum.accumulate(np.where(first, np.arange(n_households), 0))
+        hh_sub[order] = np.arange(n_households) - start
+        np.add.at(loc_nsub, hh_building, 1)
+        loc_nsub[acc] = np.maximum(loc_nsub[acc], 1)
+
+        # persons: ages, roles, households
+        age = self._draw_ages(rng, n_persons)
+        role = self._roles(rng, age)
+        adults = np.nonzero(age >= 18)[0]
+        rng.shuffle(adults)
+        hh = np.empty(n_persons, np.int64)
+        heads = adults[:min(len(adults), n_households)]
+        hh[heads] = np.arange(len(heads))
+        rest = np.setdiff1d(np.arange(n_persons), heads, assume_unique=False)
+        hh[rest] = rng.integers(0, n_households, len(rest))
+        self.household = hh.astype(np.int32)
+        home_loc = hh_building[hh]
+        home_sub = hh_sub[hh]
+
+        # work / school places
+        work_loc = np.full(n_persons, NONE, np.int64)
+        work_sub = np.zeros(n_persons, np.int64)
+        wp = np.nonzero(loc_type == TYPE_ID["Workplace"])[0]
+        workers = np.nonzero(np.isin(role, (ROLE_WORKER, ROLE_WEEKEND_WORKER, ROLE_ESSENTIAL_WORKER)))[0]
+        weights = loc_nsub[wp] / loc_nsub[wp].sum()
+        work_loc[workers] = wp[rng.choice(len(wp), len(workers), p=weights)]
+        from scipy.spatial import cKDTree
+        for r, tname in ((ROLE_KINDERGARTEN, "Kindergarten"), (ROLE_PRIMARY, "PrimarySchool"),
+                         (ROLE_SECONDARY, "SecondarySchool")):
+            who = np.nonzero(role == r)[0]
+            places = np.nonzero(loc_type == TYPE_ID[tname])[0]
+            if len(who) and len(places):
+                _, j = cKDTree(np.c_[x[places], y[places]]).query(np.c_[x[home_loc[who]], y[home_loc[who]]])
+                work_loc[who] = places[j]
+        for r, tname in ((ROLE_COLLEGE, "College"), (ROLE_UNIVERSITY, "University")):
+            who = np.nonzero(role == r)[0]
+            places = np.nonzero(loc_type == TYPE_ID[tname])[0]
+            if len(who) and len(places):
+                work_loc[who] = places[rng.integers(0, len(places), len(who))]
+        has = work_loc >= 0
+        work_sub[has] = rng.integers(0, 1 << 30, has.sum()) % loc_nsub[work_loc[has]]
+
+        # nearest / random candidate tables per Accommodation building (locators of the activity schedule)
+        self.n_random_candidates = K = n_random_candidates
+        n_types = len(TYPE_NAMES)
+        nearest = np.full((n_loc, n_types), NONE, np.int32)
+        cand = np.full((n_loc, n_types, K), NONE, np.int32)
+        n_cand = np.zeros((n_loc, n_types), np.int32)
+        pts = np.c_[x[acc], y[acc]]
+        for t in range(n_types):
+            places = np.nonzero(loc_type == t)[0]
+            if t in (TYPE_ID["Accommodation"], TYPE_ID["Workplace"]) or len(places) == 0:
+                continue
+            tree = cKDTree(np.c_[x[places], y[places]])
+            _, j = tree.query(pts)
+            nearest[acc, t] = places[j]
+            kk = min(K, len(places))
+            d, j = tree.query(pts, k=kk, distance_upper_bound=2500.0)  # RandomLocator max distance (xlsx column P)
+            d = d.reshape(len(acc), kk)
+            j = j.reshape(len(acc), kk)
+            ok = np.isfinite(d)
+            n_cand[acc, t] = ok.sum(axis=1)
+            jj = np.where(ok, j, 0)
+            cand[acc, t, :kk] = np.where(ok, places[jj], NONE)
+        self.nearest, self.cand, self.n_cand = nearest, cand, n_cand
+
+        self.loc_type = loc_type.astype(np.uint8)
+        self.loc_nsub = loc_nsub.astype(np.int16)
+        self.loc_area = (area_sub * loc_nsub).astype(np.float32)  # totalArea = area * nb_sublocations (java :381)
+        self.loc_x, self.loc_y = x.astype(np.float32), y.astype(np.float32)
+        self.n_locations = n_loc
+        self.age = age.astype(np.int8)
+        self.female = (rng.random(n_persons) < 0.5).astype(np.uint8)  # gender drawn U01 < 0.5 (java :513)
+        self.role = role.astype(np.uint8)
+        self.home_loc = home_loc.astype(np.int32)
+        self.home_sub = home_sub.astype(np.int16)
+        self.work_loc = work_loc.astype(np.int32)
+        self.work_sub = work_sub.astype(np.int16)
+
+    @staticmethod
+    def _draw_ages(rng, n):
+        # coarse Dutch age pyramid
+        edges = np.array([0, 4, 6, 12, 18, 23, 30, 40, 50, 60, 67, 75, 85, 96])
+        share = np.array([.040, .022, .066, .070, .062, .095, .125, .130, .140, .085, .080, .060, .025])
+        band = rng.choice(len(share), n, p=share / share.sum())
+        return (edges[band] + np.floor(rng.random(n) * (edges[band + 1] - edges[band]))).astype(np.int64)
+
+    @staticmethod
+    def _roles(rng, age):
+        n = len(age)
+        u = rng.random(n)
+        role = np.full(n, ROLE_PENSIONER, np.int64)
+        role[age < 4] = ROLE_INFANT
+        role[(age >= 4) & (age < 6)] = ROLE_KINDERGARTEN
+        role[(age >= 6) & (age < 12)] = ROLE_PRIMARY
+        role[(age >= 12) & (age < 18)] = ROLE_SECONDARY
+        young = (age >= 18) & (age < 23)
+        role[young] = np.select([u[young] < .3, u[young] < .6], [ROLE_COLLEGE, ROLE_UNIVERSITY], ROLE_WORKER)
+        adult = (age >= 23) & (age < 67)
+        role[adult] = np.select([u[adult] < .62, u[adult] < .74, u[adult] < .82],
+                                [ROLE_WORKER, ROLE_UNEMPLOYED, ROLE_WEEKEND_WORKER], ROLE_ESSENTIAL_WORKER)
+        return role
+
+    def install(self, engine):
+        """heros_set_location_types / heros_set_locations / heros_set_persons."""
+        engine.set_location_types(self.type_infect_sub, self.type_correction)
+        engine.set_locations(self.loc_type, self.loc_nsub, self.loc_area, self.loc_y, self.loc_x)
+        engine.set_persons(self.age, self.female, self.role, self.home_loc, self.home_sub, self.work_loc)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# activity schedules -> stays
+# ---------------------------------------------------------------------------------------------------------------------
+def load_patterns(path: Optional[str] = None) -> dict:
+    path = path or os.path.join(PKG_DIR, "data", "activity_patterns_thehague.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+class ScheduleGenerator:
+    """Produces, day by day, the stays (person, location, sub-location, t_in, t_out) of every person from the week
+    patterns ``0_<phase>_<role>`` (HerosModel.java:484-504; Mon-Thu use the Monday pattern, ConstructHerosModel.java
+    :931-940).  The phase that selects the pattern is the one held at midnight; a pattern switch therefore takes effect
+    at the next day boundary (driver contract C15 is not observable in the reference; this is the convention shared
+    with the windowed engine).  Travel time is spent outside every location; consecutive activities at the
+    same place form one stay (contract C7)."""
+
+    def __init__(self, city: City, seed: int, patterns: Optional[dict] = None):
+        self.city = city
+        self.seed = int(seed)
+        self.pat = patterns or load_patterns()
+        n = city.n_persons
+        # everybody is at home from t = 0 (open stay)
+        self.cur_loc = city.home_loc.astype(np.int64).copy()
+        self.cur_sub = city.home_sub.astype(np.int64).copy()
+        self.cur_tin = np.zeros(n, np.float64)
+        self.open_reported = np.zeros(n, bool)
+        self.day = 0
+        self._choice_tables = [self._compile_choice(c) for c in self.pat["choices"]]
+        self._day_names = ["Monday"] * 4 + ["Friday", "Saturday", "Sunday"]
+
+    @staticmethod
+    def _compile_choice(items):
+        types = np.array([TYPE_ID[name] for name, _ in items], np.int64)
+        cum = np.cumsum([p for _, p in items])
+        return types, cum
+
+    def _pattern(self, phase_name: str, role_name: str, weekday: int):
+        p = self.pat["patterns"]
+        key = f"{phase_name}|{role_name}|{self._day_names[weekday]}"
+        if key not in p:
+            key = f"{phase_name}|{role_name}|Monday"
+        return p.get(key)
+
+    def generate_day(self, phase: np.ndarray) -> Dict[str, np.ndarray]:
+        """Stays closed during day ``self.day`` plus the stays opened that day and still open at midnight
+        (t_out = +inf).  ``phase``: disease phase of every person at the start of the day."""
+        c = self.city
+        d = self.day
+        t0, t1 = 24.0 * d, 24.0 * (d + 1)
+        weekday = d % 7
+        out_p, out_l, out_s, out_a, out_b = [], [], [], [], []
+
+        def emit(idx, t_leave):
+            """close the current stay of persons idx at t_leave"""
+            real = self.cur_loc[idx] >= 0
+            idx, t_leave = idx[real], t_leave[real]
+            ok = t_leave > self.cur_tin[idx]
+            out_p.append(idx[ok]); out_l.append(self.cur_loc[idx[ok]]); out_s.append(self.cur_sub[idx[ok]])
+            out_a.append(self.cur_tin[idx[ok]]); out_b.append(t_leave[ok])
+            self.open_reported[idx] = False
+
+        roles = self.pat["roles"]
+        phases = self.pat["phases"]
+        group = phase.astype(np.int64) * 16 + c.role.astype(np.int64)
+        for g in np.unique(group):
+            ph, role = divmod(int(g), 16)
+            idx = np.nonzero(group == g)[0]
+            if ph == 6:  # Dead: the person leaves the model
+                emit(idx, np.full(len(idx), t0))
+                self.cur_loc[idx] = NONE
+                continue
+            if role < 1 or role > len(roles):
+                continue
+            acts = self._pattern(phases[ph], roles[role - 1], weekday)
+            if not acts:
+                continue
+            t = np.full(len(idx), t0)
+            alive = np.ones(len(idx), bool)  # still before midnight
+            for a_i, act in enumerate(acts):
+                if not alive.any():
+                    break
+                x, y, z, w = philox4x32_10(idx, d * 64 + a_i, 0, TAG_SCHEDULE, self.seed, self.seed >> 32)
+                u_dur = u01_from_words(x, y)
+                u_type = z.astype(np.float64) * 2.0 ** -32
+                u_cand = (w >> np.uint64(16)).astype(np.float64) * 2.0 ** -16
+                u_sub = (w & np.uint64(0xFFFF)).astype(np.float64) * 2.0 ** -16
+                dest_l, dest_s = self._locate(act, idx, u_type, u_cand, u_sub)
+                move = alive & ((dest_l != self.cur_loc[idx]) | (dest_s != self.cur_sub[idx]))
+                dur = self._duration(act, u_dur)
+                if act["kind"] == 1:  # travel: leave now, arrive after the travel time
+                    mv = np.nonzero(move)[0]
+                    emit(idx[mv], t[mv])
+                    t_arr = t[mv] + dur[mv]
+                    arrived = t_arr < t1
+                    self.cur_loc[idx[mv]] = np.where(arrived, dest_l[mv], NONE)
+                    self.cur_sub[idx[mv]] = np.where(arrived, dest_s[mv], 0)
+                    self.cur_tin[idx[mv]] = t_arr
+                    t[mv] = t_arr
+                    alive[mv] &= arrived
+                else:
+                    mv = np.nonzero(move)[0]
+                    emit(idx[mv], t[mv])
+                    self.cur_loc[idx[mv]] = dest_l[mv]
+                    self.cur_sub[idx[mv]] = dest_s[mv]
+                    self.cur_tin[idx[mv]] = t[mv]
+                    if act["kind"] == 0:
+                        t = np.where(alive, t + dur, t)
+                    else:
+                        t = np.where(alive, np.maximum(t, t0 + act["until"]), t)
+                    alive &= t < t1
+        # stays opened today that are still open at midnight
+        opened = np.nonzero((self.cur_loc >= 0) & (self.cur_tin >= t0) & (self.cur_tin < t1) & ~self.open_reported)[0]
+        if d == 0:
+            opened = np.nonzero((self.cur_loc >= 0) & (self.cur_tin < t1) & ~self.open_reported)[0]
+        out_p.append(opened); out_l.append(self.cur_loc[opened]); out_s.append(self.cur_sub[opened])
+        out_a.append(self.cur_tin[opened]); out_b.append(np.full(len(opened), np.inf))
+        self.open_reported[opened] = True
+        self.day += 1
+        return dict(person=np.concatenate(out_p).astype(np.int32), loc=np.concatenate(out_l).astype(np.int32),
+                    sub=np.concatenate(out_s).astype(np.int16), t_in=np.concatenate(out_a).astype(np.float64),
+                    t_out=np.concatenate(out_b).astype(np.float64))
+
+    def _duration(self, act, u):
+        if act["dist"] == 2:
+            mn, mode, mx = act["min"], act["mode"], act["max"]
+            if mx <= mn:
+                return np.full(len(u), mn)
+            fc = (mode - mn) / (mx - mn)
+            lo = mn + np.sqrt((mode - mn) * (mx - mn) * u)
+            hi = mx - np.sqrt((mx - mn) * (mx - mode) * (1.0 - u))
+            return np.where(u <= fc, lo, hi)
+        if act["dist"] == 1:
+            return act["min"] + (act["max"] - act["min"]) * u
+        return np.full(len(u), act["mode"])
+
+    def _locate(self, act, idx, u_type, u_cand, u_sub):
+        c = self.city
+        loc = act["locator"]
+        home_l, home_s = c.home_loc[idx].astype(np.int64), c.home_sub[idx].astype(np.int64)
+        if loc == 0:
+            return home_l, home_s
+        if loc == 1:  # Work / School; persons without one stay where they are
+            wl = c.work_loc[idx].astype(np.int64)
+            has = wl >= 0
+            return np.where(has, wl, self.cur_loc[idx]), np.where(has, c.work_sub[idx].astype(np.int64), self.cur_sub[idx])
+        if loc == 2 or act["choice"] < 0:
+            return self.cur_loc[idx].copy(), self.cur_sub[idx].copy()
+        types, cum = self._choice_tables[act["choice"]]
+        pick = np.minimum(np.searchsorted(cum, u_type * cum[-1], side="right"), len(types) - 1)
+        ty = types[pick]
+        if loc == 3:  # Nearest(type) to the home building
+            dl = c.nearest[home_l, ty].astype(np.int64)
+        else:  # Random(type) within max distance of the home building
+            n = c.n_cand[home_l, ty]
+            j = np.minimum((u_cand * n).astype(np.int64), np.maximum(n - 1, 0))
+            dl = np.where(n > 0, c.cand[home_l, ty, j], NONE).astype(np.int64)
+        go_home = (ty == TYPE_ID["Accommodation"]) | (dl < 0)
+        nsub = np.maximum(c.loc_nsub[np.maximum(dl, 0)].astype(np.int64), 1)
+        ds = np.minimum((u_sub * nsub).astype(np.int64), nsub - 1)
+        return np.where(go_home, home_l, dl), np.where(go_home, home_s, ds)
