@@ -406,6 +406,7 @@ struct orc_sim
     int32_t* key_loc;
     int n_person; int8_t* age; uint8_t* female; uint8_t* phase; float* exposure; double* next_time;
     uint8_t* next_phase; int32_t* pos_in_set;
+    uint32_t* open_key; double* open_tin; /* the stay a person was reported to be in with t_out = +inf */
 
     /* occupancy: one growable id array per sub-location key (C5) */
     int32_t** set_ids; int32_t* set_n; int32_t* set_cap; double* last_calc;
@@ -435,7 +436,7 @@ void orc_sim_destroy(orc_sim* s)
     free(s->type_infect_sub); free(s->type_corr);
     free(s->loc_type); free(s->loc_nsub); free(s->loc_area); free(s->loc_base); free(s->key_loc);
     free(s->age); free(s->female); free(s->phase); free(s->exposure); free(s->next_time); free(s->next_phase);
-    free(s->pos_in_set);
+    free(s->pos_in_set); free(s->open_key); free(s->open_tin);
     free(s->ev); free(s->heap); free(s->pol); free(s->inf); free(s->tr);
     free(s->scratch_a); free(s->scratch_b); free(s->scratch_all);
     free(s);
@@ -486,7 +487,9 @@ void orc_sim_set_persons(orc_sim* s, int n, const int8_t* age, const uint8_t* fe
     s->next_time = (double*) malloc(n * 8);
     s->next_phase = (uint8_t*) calloc(n, 1);
     s->pos_in_set = (int32_t*) malloc(n * 4);
-    for (int i = 0; i < n; ++i) { s->next_time[i] = INFINITY; s->pos_in_set[i] = -1; }
+    s->open_key = (uint32_t*) malloc(n * 4);
+    s->open_tin = (double*) malloc(n * 8);
+    for (int i = 0; i < n; ++i) { s->next_time[i] = INFINITY; s->pos_in_set[i] = -1; s->open_key[i] = 0xFFFFFFFFu; s->open_tin[i] = 0.0; }
     memset(s->counts, 0, sizeof(s->counts));
     s->counts[ORC_S] = n;
 }
@@ -658,13 +661,29 @@ void orc_sim_add_visits(orc_sim* s, int64_t n, const int32_t* person, const int3
     {
         if (!(t_out[i] > t_in[i])) continue; /* a stay must have positive length */
         uint32_t key = s->loc_base[loc[i]] + (uint32_t) sub[i];
-        move_ev a = {t_in[i], person[i], key, 1};
-        s->ev[s->n_ev++] = a;
         if (t_out[i] < INFINITY)
         {
+            /* a stay reported earlier as still open (same person, place and t_in) is being closed: its enter event
+             * already exists, only the exit is new (the contract of heros_submit_visits) */
+            if (s->open_key[person[i]] == key && s->open_tin[person[i]] == t_in[i])
+                s->open_key[person[i]] = 0xFFFFFFFFu;
+            else
+            {
+                move_ev a = {t_in[i], person[i], key, 1};
+                s->ev[s->n_ev++] = a;
+            }
             move_ev b = {t_out[i], person[i], key, 0};
             s->ev[s->n_ev++] = b;
         }
+    }
+    for (int64_t i = 0; i < n; ++i)
+    {
+        if (!(t_out[i] > t_in[i]) || t_out[i] < INFINITY) continue;
+        uint32_t key = s->loc_base[loc[i]] + (uint32_t) sub[i];
+        move_ev a = {t_in[i], person[i], key, 1};
+        s->ev[s->n_ev++] = a;
+        s->open_key[person[i]] = key;
+        s->open_tin[person[i]] = t_in[i];
     }
     s->ev_sorted = 0;
 }

@@ -1,0 +1,156 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/heros_gpu.h declares (no compute calls),
+struct layouts, host-side parameter parsing, the schedule generator, the reference-API mirror's error behaviour."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import heros_b200 as hb
+from common import GOLDEN, ROOT, load_props
+from heros_b200 import _lib, properties, scenario
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "heros_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(heros_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in heros_gpu.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared        # the ctypes table covers the header exactly
+    assert lib.heros_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(_lib.Config) == 32
+    assert C.sizeof(_lib.AreaParams) == 6 * 8 and C.sizeof(_lib.DistParams) == 10 * 8
+    assert C.sizeof(_lib.Duration) == 32
+    assert C.sizeof(_lib.ProgParams) == 5 * 2 * 128 * 8 + 10 * 32
+    assert C.sizeof(_lib.StepStats) == 18 * 8
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hb.HerosError) as e:
+        hb.HerosEngine(hb.MODEL_AREA, 1)
+    assert e.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_bad_configs_before_touching_the_device():
+    lib = _lib.load()
+    h = C.c_void_p()
+    for cfg in (_lib.Config(99, 0, 0, 0, 1, 24.0), _lib.Config(1, 7, 0, 0, 1, 24.0), _lib.Config(1, 0, 5, 0, 1, 24.0),
+                _lib.Config(1, 0, 0, 0, 1, 0.0)):
+        assert lib.heros_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID
+        assert lib.heros_last_error(None)
+    assert lib.heros_create(None, C.byref(h)) == _lib.ERR_INVALID
+    assert lib.heros_destroy(None) == _lib.OK
+
+
+def test_properties_of_the_reference_parse_to_its_values():
+    p = load_props("area")
+    a = properties.area_params(p)
+    assert (a.contagiousness, a.beta, a.t_e_min, a.t_e_mode, a.t_e_max, a.calculation_threshold) == \
+           (1.0, 1.0, 2.0, 3.4, 9.6, 60.0)                       # alpha-area.properties:7-24
+    d = properties.dist_params(load_props("distance"))
+    assert (d.L, d.I, d.C, d.v_max, d.v_0, d.r, d.psi, d.alpha, d.mu) == (2.0, 3.4, 6.2, 7.23, 4.0, 2.294, 1.0, 0.05, 0.0)
+    fr, periods = properties.prog_tables(p)
+    assert fr.shape == (5, 2, 128)
+    assert (fr[0] == 0.46).all()                                  # FractionAsymptomatic
+    assert fr[1, 0, 19] == 0.02153 and fr[1, 1, 20] == 0.01648 and fr[1, 0, 65] == 0.44038 and fr[1, 0, 100] == 0.12687
+    assert fr[1, 0, 101] == 0.0                                   # outside every band
+    assert fr[2, 0, 95] == 0.0 and fr[3].max() == 0.0 and fr[4, 0, 49] == 0.0 and fr[4, 1, 90] == 0.67882
+    assert periods[0] == (_lib.DIST_TRIANGULAR, 2.5, 3.4, 3.8) and periods[9] == (_lib.DIST_TRIANGULAR, 28.0, 30.0, 32.0)
+
+
+def test_conditional_probability_and_distribution_syntax():
+    t = properties.parse_conditional_probability("gender{M:0.45, F:0.5}")
+    assert (t[0] == 0.45).all() and (t[1] == 0.5).all()
+    t = properties.parse_conditional_probability("age{0-19: 0.8, 20-55: 0.5, 56-100: 0.3}")
+    assert t[0, 19] == 0.8 and t[1, 20] == 0.5 and t[0, 100] == 0.3
+    t = properties.parse_conditional_probability("age{0-12: 0.000, 10-19: 0.1}")   # overlapping: first band wins
+    assert t[0, 11] == 0.0 and t[0, 13] == 0.1
+    assert properties.parse_distribution("Uniform(2,4)") == (_lib.DIST_UNIFORM, 2.0, 4.0, 0.0)
+    assert properties.parse_distribution("Constant(3)") == (_lib.DIST_CONSTANT, 3.0, 0.0, 0.0)
+    assert properties.parse_distribution(" triangular( 1 ,3, 5 ) ")[0] == _lib.DIST_TRIANGULAR
+    with pytest.raises(NotImplementedError):
+        properties.parse_distribution("TruncatedNormal(12.0, 2.3, 12.0, 14.0)")
+    with pytest.raises(ValueError):
+        properties.parse_distribution("garbage")
+
+
+def test_location_type_fixture_matches_the_generator_tables():
+    with open(os.path.join(GOLDEN, "locationtypes_thehague.json")) as f:
+        rows = json.load(f)["rows"]
+    assert [r[0] for r in rows] == scenario.TYPE_NAMES          # type id = row order (ConstructHerosModel.java:233)
+    assert [int(r[3].upper() == "TRUE") for r in rows] == scenario.TYPE_INFECT_SUB.tolist()
+    assert [float(r[5]) for r in rows] == scenario.TYPE_CORRECTION.tolist()
+
+
+def test_vectorised_philox_matches_the_oracle():
+    from oracle import binding as ob
+    x, y, z, w = scenario.philox4x32_10(np.array([0, 0xffffffff, 0x243f6a88]), np.array([0, 0xffffffff, 0x85a308d3]),
+                                        np.array([0, 0xffffffff, 0x13198a2e]), np.array([0, 0xffffffff, 0x03707344]),
+                                        0, 0)
+    assert [int(x[0]), int(y[0]), int(z[0]), int(w[0])] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    for person in (0, 5, 70000):
+        a, b, _, _ = scenario.philox4x32_10(np.array([person]), 7, 0, 0x300, 111, 0)
+        got = float(scenario.u01_from_words(a, b)[0])
+        assert got == ob.u01(111, person, 7, 0x300)
+
+
+def test_schedule_generator_is_deterministic_and_consistent():
+    city = scenario.City(3000, seed=3)
+    assert city.loc_nsub.min() >= 1 and (city.home_sub < city.loc_nsub[city.home_loc]).all()
+    has_work = city.work_loc >= 0
+    assert (city.work_sub[has_work] < city.loc_nsub[city.work_loc[has_work]]).all()
+    days = []
+    for rep in range(2):
+        gen = scenario.ScheduleGenerator(city, 111)
+        phase = np.zeros(city.n_persons, np.uint8)
+        phase[:40] = 3    # Infected-Symptomatic: stay home
+        phase[40:50] = 4  # Hospitalized
+        phase[50:55] = 6  # Dead
+        days.append([gen.generate_day(phase) for _ in range(3)])
+    for a, b in zip(*days):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    d0, d1, d2 = days[0]
+    closed = np.isfinite(d1["t_out"])
+    assert (d1["t_out"][closed] > d1["t_in"][closed]).all()
+    assert (d1["t_out"][closed] <= 48.0).all() and (d1["t_out"][closed] >= 24.0).all()
+    assert (d1["sub"] < city.loc_nsub[d1["loc"]]).all()
+    # per person the stays of a day do not overlap
+    for d in (d1, d2):
+        o = np.lexsort((d["t_in"], d["person"]))
+        p, a, b = d["person"][o], d["t_in"][o], d["t_out"][o]
+        same = p[1:] == p[:-1]
+        assert (a[1:][same] >= b[:-1][same]).all()
+    # symptomatic persons do not move on day 1; the dead have left the model
+    moved = np.unique(d1["person"])
+    assert not np.isin(np.arange(0, 40), moved).any()
+    assert not np.isin(np.arange(50, 55), np.unique(d2["person"])).any()
+    hosp = d0["loc"][np.isin(d0["person"], np.arange(40, 50)) & ~np.isfinite(d0["t_out"])]
+    assert (city.loc_type[hosp] == scenario.TYPE_ID["Hospital"]).all()
+    assert 3.0 < len(d1["person"]) / city.n_persons < 6.0
+
+
+def test_mirror_classes_keep_the_reference_error_behaviour(capsys):
+    # DiseasePolicy rejects anything but covidT_dist.psi / mu with a message, no exception (DiseasePolicy.java:21-25)
+    class FakeModel:
+        def getDiseaseTransmission(self):
+            raise AssertionError("must not be reached")
+    hb.DiseasePolicy(FakeModel(), 240.0, "covidT_area.beta", 0.5)
+    assert "Unrecognized variable name covidT_area.beta" in capsys.readouterr().err
+    with pytest.raises(ValueError):
+        hb.HerosModel({"generic.diseasePropertiesModel": "sir"})

@@ -33,3 +33,139 @@ def test_small_city_matches_oracle(model, trigger):
     assert_same_run(gpu, ora)
     assert sum(s["evaluations"] for s in gpu["stats"]) == ora["evaluations"]
     assert sum(s["near_ties"] for s in gpu["stats"]) == 0
+
+
+@pytest.mark.parametrize("model,trigger", [("area", "both"), ("distance", "exit")])
+def test_daily_submission_with_open_stays(model, trigger):
+    """The host submits day by day; stays still open at midnight go in with t_out = +inf and are closed later."""
+    scn = Scenario(seed=12, n_persons=500, n_households=180, n_workplaces=20, n_shops=5, days=10, open_fraction=0.1)
+    props = hot_props(model)
+    ora = run_oracle(scn, props, MODELS[model], TRIGGERS[trigger], seed=7)
+    gpu = run_gpu(scn, props, MODELS[model], TRIGGERS[trigger], seed=7, submit="daily")
+    assert len(ora["infections"]["person"]) > 30
+    assert_same_run(gpu, ora)
+
+
+@pytest.mark.parametrize("window,step", [(6.0, 24.0), (12.0, 18.0), (47.0, 47.0), (24.0, 5.0)])
+def test_window_length_does_not_change_the_result(window, step):
+    """batch == sequential for any window below the latent period (48 h): same events as the oracle."""
+    scn = Scenario(seed=13, n_persons=400, n_households=150, n_workplaces=15, n_shops=4, days=9)
+    props = hot_props("area")
+    ora = run_oracle(scn, props, _lib.MODEL_AREA, _lib.TRIGGER_ENTER_AND_EXIT, seed=3)
+    gpu = run_gpu(scn, props, _lib.MODEL_AREA, _lib.TRIGGER_ENTER_AND_EXIT, seed=3, window_hours=window,
+                  step_hours=step)
+    gpu["counts"] = ora["counts"]  # day-end counts are only sampled when a step ends on a day boundary
+    assert_same_run(gpu, ora)
+
+
+def test_window_longer_than_latent_period_is_refused():
+    import heros_b200 as hb
+    scn = Scenario(seed=1, n_persons=50, n_households=20, n_workplaces=3, n_shops=1, days=1)
+    with pytest.raises(hb.HerosError) as e:
+        run_gpu(scn, hot_props("area"), _lib.MODEL_AREA, _lib.TRIGGER_EXIT_ONLY, seed=1, window_hours=48.0)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+
+
+def test_hot_sublocations_use_the_block_kernel_and_match():
+    """A city with two shops: thousands of stays per sub-location and day, second-scale gaps, tied event times."""
+    scn = Scenario(seed=14, n_persons=1500, n_households=500, n_workplaces=6, n_shops=2, days=8,
+                   shop_visits_per_day=3.0, tie_fraction=0.3, short_gap_fraction=0.3)
+    for model, trigger in (("area", "both"), ("distance", "exit"), ("distance", "both")):
+        props = hot_props(model)
+        if model == "area":
+            props["covidT_area.contagiousness"] = "20.0"
+        ora = run_oracle(scn, props, MODELS[model], TRIGGERS[trigger], seed=5)
+        gpu = run_gpu(scn, props, MODELS[model], TRIGGERS[trigger], seed=5)
+        assert sum(s["big_sublocations"] for s in gpu["stats"]) > 50
+        assert len(ora["infections"]["person"]) > 100
+        assert_same_run(gpu, ora)
+        assert sum(s["evaluations"] for s in gpu["stats"]) == ora["evaluations"]
+
+
+def test_disease_policy_psi_mu_changes_take_effect_at_their_time():
+    """data/thehague/policies/MaskingDistance_10-40.csv scaled to days 3 and 6 (DiseasePolicy.java:29-43)."""
+    scn = Scenario(seed=15, n_persons=500, n_households=180, n_workplaces=20, n_shops=5, days=9)
+    props = hot_props("distance")
+    policies = [(72.0, "psi", 2.0), (72.0, "mu", 0.6), (144.0, "psi", 1.0), (144.0, "mu", 0.0)]
+    ora = run_oracle(scn, props, _lib.MODEL_DISTANCE, _lib.TRIGGER_EXIT_ONLY, seed=9, policies=policies)
+    plain = run_oracle(scn, props, _lib.MODEL_DISTANCE, _lib.TRIGGER_EXIT_ONLY, seed=9)
+    gpu = run_gpu(scn, props, _lib.MODEL_DISTANCE, _lib.TRIGGER_EXIT_ONLY, seed=9, policies=policies)
+    assert len(plain["infections"]["person"]) != len(ora["infections"]["person"])  # the policy matters
+    assert_same_run(gpu, ora)
+
+
+def test_set_parameter_error_codes():
+    scn = Scenario(seed=1, n_persons=50, n_households=20, n_workplaces=3, n_shops=1, days=1)
+    from common import make_engine
+    eng = make_engine(scn, hot_props("distance"), _lib.MODEL_DISTANCE, 0, 1)
+    assert eng.set_parameter("psi", 2.0, 10.0) == _lib.OK
+    assert eng.set_parameter("beta", 2.0, 10.0) == _lib.ERR_UNKNOWN_PARAMETER   # TDist:263
+    eng.close()
+    eng = make_engine(scn, hot_props("area"), _lib.MODEL_AREA, 0, 1)
+    assert eng.set_parameter("psi", 2.0, 10.0) == _lib.ERR_UNKNOWN_PARAMETER    # TArea:251-255 rejects every name
+    eng.close()
+
+
+def test_generator_driven_city_with_phase_feedback():
+    """The bench flow at small scale: stays come from the activity-schedule generator, which reads the engine's
+    phases every midnight (symptomatic stay home, hospitalised move to the hospital)."""
+    import heros_b200 as hb
+    from heros_b200 import properties, scenario
+    from common import oracle_props
+    from oracle import binding as ob
+    city = scenario.City(12000, seed=5)
+    props = hot_props("distance")
+    props["covidT_dist.alpha"] = "0.5"
+    eng = hb.HerosEngine(hb.MODEL_DISTANCE, 111)
+    city.install(eng)
+    eng.set_transmission_distance(properties.dist_params(props))
+    eng.set_progression(properties.prog_params(props))
+    seeds = eng.seed_infections(30)
+    area, dist, prog = oracle_props(props)
+    sim = ob.Sim(ob.MODEL_DIST, ob.TRIGGER_EXIT_ONLY, 111)
+    sim.set_dist(dist); sim.set_prog(prog)
+    sim.set_location_types(city.type_infect_sub, city.type_correction)
+    sim.set_locations(city.loc_type, city.loc_nsub, city.loc_area)
+    sim.set_persons(city.age, city.female)
+    sim.expose(seeds, np.zeros(len(seeds)))
+    gen = scenario.ScheduleGenerator(city, 111)
+    counts = []
+    for d in range(12):
+        phase = eng.agent_state()["phase"]
+        np.testing.assert_array_equal(phase, sim.agent_state()["phase"])
+        st = gen.generate_day(phase)
+        eng.submit_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        eng.step(24.0 * (d + 1))
+        sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        sim.run(24.0 * (d + 1))
+        counts.append(eng.phase_counts())
+    gpu = dict(infections=eng.infections(), transitions=eng.transitions(), counts=np.array(counts),
+               state=eng.agent_state())
+    t, series = eng.count_series()
+    np.testing.assert_array_equal(series, np.array(counts))
+    ora = dict(infections=sim.infections(), transitions=sim.transitions(), counts=np.array(counts),
+               state=sim.agent_state())
+    assert len(gpu["infections"]["person"]) > 100
+    assert_same_run(gpu, ora)
+    eng.close()
+
+
+def test_seeding_is_the_keyed_bottom_k_and_respects_age_bounds():
+    import bench
+    from heros_b200 import scenario
+    from common import make_engine
+    scn = Scenario(seed=2, n_persons=3000, n_households=900, n_workplaces=30, n_shops=5, days=1)
+    eng = make_engine(scn, hot_props("area"), _lib.MODEL_AREA, 0, 111)
+    chosen = eng.seed_infections(40, min_age=20, max_age=60)
+    assert len(np.unique(chosen)) == 40 and (scn.age[chosen] >= 20).all() and (scn.age[chosen] <= 60).all()
+    x, y, _, _ = scenario.philox4x32_10(np.arange(3000), 0, 0, 0x200, 111, 0)
+    h = ((x << np.uint64(32)) | y)
+    ok = (scn.age >= 20) & (scn.age <= 60)
+    want = np.sort(np.nonzero(ok)[0][np.argsort(h[ok], kind="stable")[:40]])
+    np.testing.assert_array_equal(chosen, want)
+    c = eng.phase_counts()
+    assert c[0] == 3000 - 40 and c[1] == 40
+    st = eng.agent_state()
+    assert (st["phase"][chosen] == 1).all() and (st["exposure"][chosen] == 0.0).all()
+    assert ((st["next_time"][chosen] >= 60.0) & (st["next_time"][chosen] <= 91.2)).all()
+    eng.close()

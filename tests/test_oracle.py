@@ -1,0 +1,265 @@
+"""The CPU oracle against everything that can pin it without the (non-runnable) JVM reference:
+Random123 known-answer vectors, libm, the worked example of the reference's Javadoc, hand-derived boundary cases."""
+import math
+
+import numpy as np
+import pytest
+
+from common import load_props, oracle_props
+from oracle import binding as ob
+
+S, E, IA, IS, H, ICU, D, R = range(8)
+
+
+def test_philox_random123_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert ob.philox4x32_10(ctr, key).tolist() == want
+
+
+def test_u01_range_and_keying():
+    us = [ob.u01(111, p, 0x4054000000000000, 0) for p in range(2000)]
+    assert 0.0 <= min(us) and max(us) < 1.0
+    assert abs(np.mean(us) - 0.5) < 0.03
+    assert ob.u01(111, 5, 1234, 0) == ob.u01(111, 5, 1234, 0)
+    assert ob.u01(111, 5, 1234, 0) != ob.u01(112, 5, 1234, 0)
+    assert ob.u01(111, 5, 1234, 0) != ob.u01(111, 5, 1235, 0)
+    assert ob.u01(111, 5, 1234, 0) != ob.u01(111, 5, 1234, 1)
+
+
+def test_exp_within_one_ulp_of_libm_and_special_values():
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-2, 2, 20000), rng.uniform(-1e-6, 1e-6, 5000)])
+    for x in xs:
+        a, b = ob.exp(x), math.exp(x)
+        assert abs(a - b) <= math.ulp(b), x
+    assert ob.exp(0.0) == 1.0 and ob.exp(-0.0) == 1.0
+    assert ob.exp(float("inf")) == float("inf") and ob.exp(float("-inf")) == 0.0
+    assert math.isnan(ob.exp(float("nan")))
+    assert ob.exp(710.0) == float("inf") and ob.exp(-746.0) == 0.0
+    assert ob.exp(-745.0) > 0.0  # subnormal result
+
+
+def test_java_max_propagates_nan():
+    nan = float("nan")
+    assert math.isnan(ob.lib().orc_java_max(nan, 1.0)) and math.isnan(ob.lib().orc_java_max(1.0, nan))
+    assert ob.lib().orc_java_max(2.0, 1.0) == 2.0 and ob.lib().orc_java_max(-1.0, 1.0) == 1.0
+
+
+def test_duration_sampling_matches_closed_forms():
+    # Triangular(2.5, 3.4, 3.8) days -> hours; Uniform; Constant
+    assert ob.sample_duration_hours(ob.DIST_TRIANGULAR, 2.5, 3.4, 3.8, 0.0) == 2.5 * 24.0
+    assert ob.sample_duration_hours(ob.DIST_TRIANGULAR, 2.5, 3.4, 3.8, 1.0) == 3.8 * 24.0
+    fc = (3.4 - 2.5) / (3.8 - 2.5)
+    assert abs(ob.sample_duration_hours(ob.DIST_TRIANGULAR, 2.5, 3.4, 3.8, fc) - 3.4 * 24.0) < 1e-9
+    us = np.linspace(0.001, 0.999, 999)
+    xs = np.array([ob.sample_duration_hours(ob.DIST_TRIANGULAR, 2.5, 3.4, 3.8, u) for u in us])
+    assert (np.diff(xs) > 0).all() and 60.0 <= xs.min() and xs.max() <= 91.2  # the 60-91.2 h band of SURVEY C2
+    assert ob.sample_duration_hours(ob.DIST_UNIFORM, 1.0, 3.0, 0.0, 0.25) == 1.5 * 24.0
+    assert ob.sample_duration_hours(ob.DIST_CONSTANT, 4.0, 0.0, 0.0, 0.9) == 96.0
+
+
+def area(pB=0.51, beta=1.0, thr=60.0):
+    return ob.AreaProps(pB, beta, 2.0, 3.4, 9.6, thr)
+
+
+def one_call(props, area_m2, duration, n_sub=1, phases=(IS, S), exposure=(0.0, 0.0), now=3.4 * 24, corr=1.0,
+             model=ob.MODEL_AREA, infect_sub=True, **kw):
+    return ob.infect_people(model, props, 111, infect_sub, corr, area_m2, n_sub, list(range(len(phases))), phases,
+                            exposure, now, duration, **kw)
+
+
+def test_area_javadoc_worked_example():
+    """Covid19TransmissionArea.java:112-121: 1 infectious at its peak + 1 susceptible, 1 h, 10 m2, p_B = 0.51."""
+    assert one_call(area(), 10.0, 1.0)["p"] == pytest.approx(1 - math.exp(-0.051), rel=1e-14)
+    assert one_call(area(), 10.0, 1.0)["p"] == pytest.approx(0.0497, abs=5e-4)          # "0.05 (5%)"
+    assert one_call(area(), 5.0, 1.0)["p"] == pytest.approx(0.0970, abs=5e-4)           # "9.6%"
+    assert one_call(area(), 10.0, 2.0)["p"] == pytest.approx(0.0970, abs=5e-4)          # 2 hours
+    assert one_call(area(beta=0.5), 10.0, 1.0)["p"] == pytest.approx(0.0252, abs=5e-4)  # masks, "2.5%"
+    assert one_call(area(), 1000.0, 1.0)["p"] == pytest.approx(5.1e-4, rel=1e-2)        # "1E-3" order
+
+
+def test_area_triangle_boundaries():
+    tmin, tmode, tmax = 48.0, 3.4 * 24.0, 9.6 * 24.0
+    p = lambda te: one_call(area(), 10.0, 1.0, now=te)["p"]
+    assert math.isnan(p(np.nextafter(tmin, 0)))            # not yet contagious: sum == 0 -> early return (TArea:178)
+    assert math.isnan(p(tmin))                             # contribution exactly 0 at te == t_e_min
+    assert p(np.nextafter(tmin, 1e9)) == 0.0 and p(tmin + 1e-6) > 0   # sum > 0 but 1 - exp(-1e-17) rounds to 0
+    assert p(tmode) == pytest.approx(1 - math.exp(-0.051), rel=1e-14)   # peak belongs to the falling branch (>=)
+    assert math.isnan(p(tmax))                             # (max - te) == 0 at te == t_e_max, inclusive bound
+    assert p(tmax - 1e-6) > 0 and math.isnan(p(np.nextafter(tmax, 1e9)))
+
+
+def test_area_record_lists_and_thresholds():
+    # every ILL occupant is listed as infectious, contagious or not (TArea:175)
+    r = one_call(area(), 10.0, 1.0, phases=(E, IS, S, R, D, H), exposure=(80.0, 0.0, 0.0, 0.0, 0.0, -500.0))
+    assert r["calculated"] and r["infectious"].tolist() == [0, 1, 5]
+    # duration below the threshold: not calculated; exactly the threshold: calculated (TArea:138 uses <)
+    thr = 60.0 / 3600.0
+    assert not one_call(area(), 10.0, np.nextafter(thr, 0))["calculated"]
+    assert one_call(area(), 10.0, thr)["calculated"]
+    # nobody susceptible / nobody ill
+    assert one_call(area(), 10.0, 1.0, phases=(IS, R))["infected"].tolist() == []
+    assert math.isnan(one_call(area(), 10.0, 1.0, phases=(S, S))["p"])
+
+
+def test_area_float_exposure_time_is_widened_not_rounded_twice():
+    # exposure is a float (ConstructHerosModel.java:745): te = now - (double)(float) t
+    t_exp = 1000.1
+    f = float(np.float32(t_exp))
+    now = f + 60.0
+    want = 1 - math.exp(-0.51 * 1.0 / 10.0 * ((now - f) - 48.0) / (81.6 - 48.0))
+    got = one_call(area(), 10.0, 1.0, exposure=(t_exp, 0.0), now=now)["p"]
+    assert got == pytest.approx(want, rel=1e-13)
+    wrong = 1 - math.exp(-0.51 * 1.0 / 10.0 * ((now - t_exp) - 48.0) / (81.6 - 48.0))
+    assert abs(got - wrong) > 1e-9
+
+
+def test_area_degenerate_locations_follow_ieee():
+    """76 Helsinki Accommodation rows have nb_sublocations = 0 and 3 563 Workplace rows area = -1."""
+    r = one_call(area(), 0.0, 1.0, n_sub=0)   # area = 0 * 0 -> 0/0 = NaN -> factor NaN -> p NaN -> nobody infected
+    assert r["calculated"] and math.isnan(r["p"]) and len(r["infected"]) == 0
+    r = one_call(area(pB=50.0), -1.0, 1.0)    # negative area: factor > 0 -> p = 1 - exp(+x) < 0
+    assert r["p"] < 0 and len(r["infected"]) == 0
+
+
+def test_area_total_location_branch_quirks():
+    """infectSub = false and nSub >= 2 (TArea:198-246): no minus sign (TArea:205), te/(mode-min) and
+    1 - te/(max-mode) (TArea:219,221).  p <= 0 while the sum is positive; p > 0 only when late cases make it negative."""
+    ids = [0, 1, 2]
+    r = ob.infect_people(ob.MODEL_AREA, area(), 111, False, 1.0, 20.0, 2, [0], [S], [0.0], 60.0, 1.0,
+                         all_ids=ids, all_phase=[IS, S, S], all_exposure=[0.0, 0.0, 0.0])
+    want_sum = 60.0 / (81.6 - 48.0)
+    assert r["p"] == pytest.approx(1 - math.exp(0.51 / 20.0 * want_sum), rel=1e-13) and r["p"] < 0
+    assert r["infectious"].tolist() == [0] and len(r["infected"]) == 0
+    # te = 200 h > max - mode = 148.8 h: contribution 1 - 200/148.8 < 0 -> p > 0 (KAT with sum < 0)
+    r = ob.infect_people(ob.MODEL_AREA, area(pB=30.0), 111, False, 1.0, 20.0, 2, [0], [S], [0.0], 200.0, 1.0,
+                         all_ids=ids, all_phase=[IS, S, S], all_exposure=[0.0, 0.0, 0.0])
+    s = 1.0 - 200.0 / (230.4 - 81.6)
+    assert s < 0 and r["p"] == pytest.approx(1 - math.exp(30.0 / 20.0 * s), rel=1e-13) and r["p"] > 0
+    # the draws go over ALL persons of the location (TArea:234), with u = Philox(seed, person, now)
+    want = [i for i in (1, 2) if ob.u01(111, i, np.float64(200.0).view(np.uint64), 0) < r["p"]]
+    assert r["infected"].tolist() == want
+
+
+def dist_props(**kw):
+    p = dict(L=2.0, I=3.4, C=6.2, v_max=7.23, v_0=4.0, r=2.294, psi=1.0, alpha=0.05, mu=0.0, thr=60.0)
+    p.update(kw)
+    return ob.DistProps(p["L"], p["I"], p["C"], p["v_max"], p["v_0"], p["r"], p["psi"], p["alpha"], p["mu"], p["thr"])
+
+
+def dist_expected(area_sub, n, duration, t, psi=1.0, alpha=0.05, mu=0.0):
+    L, I, C, vmax, v0, r = 48.0, 81.6, 6.2 * 24.0, 7.23, 4.0, 2.294
+    delta = math.sqrt(area_sub / n)
+    sigma = 1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, psi) - 1.5)))
+    factor = sigma * alpha * (1 - mu) * (1 - mu)
+    if L <= t < I:
+        v = vmax * ((t - L) / (I - L))
+    elif I <= t < I + C:
+        v = vmax * ((I + C - t) / C)
+    else:
+        v = 0.0
+    if v <= 0:
+        return float("nan")
+    pt = 1 / (1 + math.exp(-r * (v - v0)))
+    return 1 - math.exp(-(factor * duration * pt))
+
+
+def test_distance_formula_and_boundaries():
+    for t in (50.0, 81.6, 100.0, 200.0):
+        got = one_call(dist_props(), 30.0, 2.0, model=ob.MODEL_DIST, now=t)["p"]
+        assert got == pytest.approx(dist_expected(30.0, 2, 2.0, t), rel=1e-12)
+    I_C = 81.6 + 6.2 * 24.0
+    assert math.isnan(one_call(dist_props(), 30.0, 2.0, model=ob.MODEL_DIST, now=48.0)["p"])   # v_t == 0 at t == L
+    assert math.isnan(one_call(dist_props(), 30.0, 2.0, model=ob.MODEL_DIST, now=I_C)["p"])    # exclusive upper end
+    # only occupants with v_t > 0 are listed (TDist:161-166), unlike the area model
+    r = one_call(dist_props(), 30.0, 2.0, model=ob.MODEL_DIST, phases=(E, IS, S), exposure=(90.0, 0.0, 0.0), now=100.0)
+    assert r["infectious"].tolist() == [1]
+    # masks and distancing (DiseasePolicy psi / mu)
+    got = one_call(dist_props(psi=2.0, mu=0.6), 30.0, 2.0, model=ob.MODEL_DIST, now=100.0)["p"]
+    assert got == pytest.approx(dist_expected(30.0, 2, 2.0, 100.0, psi=2.0, mu=0.6), rel=1e-12)
+
+
+def test_distance_degenerate_locations_follow_ieee():
+    r = one_call(dist_props(), -1.0, 2.0, model=ob.MODEL_DIST, now=100.0)  # sqrt(negative) = NaN -> max -> NaN
+    assert r["calculated"] and math.isnan(r["p"]) and len(r["infected"]) == 0
+    r = one_call(dist_props(), 0.0, 2.0, n_sub=0, model=ob.MODEL_DIST, now=100.0)
+    assert r["calculated"] and len(r["infected"]) == 0
+
+
+def test_distance_total_branch_uses_undivided_area_and_sublocation_head_count():
+    ids = [0, 1, 2, 3]
+    r = ob.infect_people(ob.MODEL_DIST, dist_props(), 111, False, 1.0, 60.0, 3, [0, 1], [S, S], [0.0, 0.0], 100.0, 2.0,
+                         all_ids=ids, all_phase=[S, S, IS, IS], all_exposure=[0.0, 0.0, 0.0, 10.0])
+    # Delta = sqrt(60 / 2): un-divided area, head count of the SUB-location (TDist:196)
+    delta = math.sqrt(60.0 / 2)
+    sigma = 1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, 1.0) - 1.5)))
+    factor = sigma * 0.05
+    s = 0.0
+    for te in (100.0, 90.0):
+        v = 7.23 * ((81.6 + 148.8 - te) / 148.8) if te >= 81.6 else 7.23 * ((te - 48.0) / 33.6)
+        s += factor * 2.0 * (1 / (1 + math.exp(-2.294 * (v - 4.0))))
+    assert r["p"] == pytest.approx(1 - math.exp(-s), rel=1e-12)
+    assert r["infectious"].tolist() == [2, 3]
+
+
+def small_sim(model=ob.MODEL_AREA, trigger=ob.TRIGGER_EXIT_ONLY, n=4):
+    props = load_props("area" if model == ob.MODEL_AREA else "distance")
+    a, d, prog = oracle_props(props)
+    sim = ob.Sim(model, trigger, 111)
+    sim.set_area(a) if model == ob.MODEL_AREA else sim.set_dist(d)
+    sim.set_prog(prog)
+    sim.set_location_types([1], [1.0])
+    sim.set_locations([0, 0], [1, 2], [10.0, 60.0])
+    sim.set_persons([30] * n, [0] * n)
+    return sim
+
+
+def test_driver_duration_accumulates_until_threshold_and_exit_sees_the_leaver():
+    sim = small_sim()
+    sim.expose([0], [0.0])
+    # person 0 infectious from 48 h; persons 1, 2 visit location 0
+    sim.add_visits([0, 1, 2], [0, 0, 0], [0, 0, 0], [50.0, 50.0, 50.5], [60.0, 51.0, 51.0 + 30.0 / 3600.0])
+    sim.run(50.9)
+    assert sim.n_evaluations() == 0          # enters do not trigger in EXIT_ONLY mode
+    sim.run(51.005)
+    assert sim.n_evaluations() == 1 and sim.last_calc(0, 0) == 51.0   # exit of person 1, duration 51 - 0
+    sim.run(52.0)
+    assert sim.n_evaluations() == 1          # exit of person 2 only 30 s later: below the 60 s threshold
+    sim.run(61.0)
+    assert sim.n_evaluations() == 2 and sim.last_calc(0, 0) == 60.0
+
+
+def test_driver_enter_and_exit_mode_and_ties():
+    sim = small_sim(trigger=ob.TRIGGER_ENTER_AND_EXIT)
+    sim.add_visits([0, 1, 2], [0, 0, 0], [0, 0, 0], [10.0, 10.0, 12.0], [12.0, 14.0, 14.0])
+    sim.run(100.0)
+    # distinct event times 10, 12, 14 -> one calculated evaluation each (tied events have duration 0)
+    assert sim.n_evaluations() == 3
+
+
+def test_driver_progression_matches_golden_timing_band():
+    """Seeds exposed at t = 0 enter I(A)/I(S) between 60 h and 91.2 h (first I at 61.5 h, all by 90 h)."""
+    sim = small_sim(n=400)
+    sim.expose(np.arange(400), np.zeros(400))
+    sim.run(59.99)
+    assert sim.phase_counts()[E] == 400
+    sim.run(91.21)
+    c = sim.phase_counts()
+    assert c[E] == 0 and c[IA] + c[IS] == 400 and 0.3 < c[IA] / 400 < 0.62   # FractionAsymptomatic = 0.46
+    sim.run(24.0 * 60)
+    c = sim.phase_counts()
+    assert c.sum() == 400 and c[R] + c[D] + c[H] + c[ICU] + c[IA] + c[IS] == 400
+    tr = sim.transitions()
+    assert (np.diff(tr["time"]) >= 0).all()   # fired in time order
+    # a re-opened stay is closed by re-submitting it with the same t_in: no ghost occupant
+    sim2 = small_sim()
+    sim2.add_visits([1], [0], [0], [5.0], [np.inf])
+    sim2.add_visits([1], [0], [0], [5.0], [9.0])
+    sim2.add_visits([2], [0], [0], [9.5], [11.0])
+    sim2.run(20.0)
+    assert sim2.n_evaluations() == 2
