@@ -60,7 +60,13 @@ typedef struct heros_config {
     int32_t device;        /* CUDA device ordinal */
     uint64_t seed;         /* generic.Seed; key of every Philox draw */
     double window_hours;   /* batch window; must be <= the latent period (t_e_min / L) of the transmission model */
+    uint32_t flags;        /* HEROS_FLAG_* */
+    uint32_t reserved;
 } heros_config;
+
+/* count every calculated evaluation in heros_step_stats.evaluations, also in sub-locations where nobody can be
+ * infected (there the engine otherwise only advances lastCalculation and skips the walk over the evaluations) */
+#define HEROS_FLAG_EXACT_STATS 1u
 
 /* covidT_area.* exactly as in the .properties file (days / seconds); converted as disease/Covid19TransmissionArea.java:63-68 */
 typedef struct heros_area_params {

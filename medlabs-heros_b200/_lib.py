@@ -14,6 +14,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_UNKNOWN_PARAMETER = 0, -1, -2, -3, -4, -5
 MODEL_AREA, MODEL_DISTANCE = 0, 1
 TRIGGER_EXIT_ONLY, TRIGGER_ENTER_AND_EXIT = 0, 1
+FLAG_EXACT_STATS = 1
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR = 0, 1, 2
 PHASE_NAMES = ("Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic", "Hospitalized", "ICU",
                "Dead", "Recovered")  # Covid19Progression.java:130-137
@@ -21,7 +22,7 @@ PHASE_NAMES = ("Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symp
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("model", C.c_int32), ("trigger", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64), ("window_hours", C.c_double)]
+                ("seed", C.c_uint64), ("window_hours", C.c_double), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AreaParams(C.Structure):

@@ -515,11 +515,10 @@ struct heros_engine
     DevBuf<double> inf_t, inf_p, tr_time;
     DevBuf<uint8_t> tr_phase;
 
-    // big-segment scratch
-    DevBuf<uint32_t> big_seg, big_off, sc_evx, sc_j0, sc_j1, sc_node, sc_ill;
-    DevBuf<uint64_t> sc_evt;
-    DevBuf<int32_t> sc_pre;
-    DevBuf<double> sc_cand, sc_p, sc_dur;
+    // work lists of the transmission kernels + global scratch of huge segments
+    DevBuf<uint32_t> warp_seg, blk_seg[3];
+    DevBuf<unsigned long long> huge_off;
+    DevBuf<unsigned char> scratch;
 
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;  // pinned
@@ -590,7 +589,8 @@ int32_t sync_counters(heros_handle h)
 
 __global__ void k_zero_window(Counters* c)
 {
-    c->n_cand = 0; c->n_big = 0; c->scratch_top = 0; c->n_keep = 0; c->n_seg = 0; c->n_active = 0;
+    c->n_cand = 0; c->n_warp = 0; c->n_blk[0] = c->n_blk[1] = c->n_blk[2] = 0; c->scratch_top = 0;
+    c->n_keep = 0; c->n_seg = 0; c->n_active = 0;
 }
 
 int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
@@ -666,12 +666,11 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     launches += 4;
 
     // 5. transmission
-    const size_t scratch_want = 4 * (size_t) n_total + 4096;
-    CU(h, h->sc_evt.ensure(scratch_want)); CU(h, h->sc_evx.ensure(scratch_want)); CU(h, h->sc_pre.ensure(scratch_want));
-    CU(h, h->sc_j0.ensure(scratch_want)); CU(h, h->sc_j1.ensure(scratch_want)); CU(h, h->sc_cand.ensure(scratch_want));
-    CU(h, h->sc_node.ensure(scratch_want)); CU(h, h->sc_p.ensure(scratch_want)); CU(h, h->sc_dur.ensure(scratch_want));
-    CU(h, h->sc_ill.ensure(scratch_want));
-    CU(h, h->big_seg.ensure((size_t) n_total / 32 + 16)); CU(h, h->big_off.ensure((size_t) n_total / 32 + 16));
+    const size_t list_cap = (size_t) n_total / 32 + 16;
+    CU(h, h->warp_seg.ensure((size_t) n_total / 8 + 16));
+    for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
+    CU(h, h->huge_off.ensure(list_cap));
+    CU(h, h->scratch.ensure(std::min<size_t>(128 * (size_t) n_total + (1u << 20), (size_t) 4 << 30)));
 
     WindowCtx c{};
     c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
@@ -682,10 +681,11 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.s_view = h->s_view.p; c.seg_start = h->seg_start.p;
     c.cand_person = h->cand_person.p; c.cand_key = h->cand_key.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
-    c.big_seg = h->big_seg.p; c.big_off = h->big_off.p; c.big_cap = (uint32_t) h->big_seg.n;
-    c.sc_evt = h->sc_evt.p; c.sc_evx = h->sc_evx.p; c.sc_pre = h->sc_pre.p; c.sc_j0 = h->sc_j0.p; c.sc_j1 = h->sc_j1.p;
-    c.sc_cand = h->sc_cand.p; c.sc_node = h->sc_node.p; c.sc_p = h->sc_p.p; c.sc_dur = h->sc_dur.p;
-    c.sc_ill = h->sc_ill.p; c.scratch_cap = h->sc_evt.n;
+    c.warp_seg = h->warp_seg.p; c.warp_cap = (uint32_t) h->warp_seg.n;
+    for (int k = 0; k < 3; ++k) c.blk_seg[k] = h->blk_seg[k].p;
+    c.blk_cap = (uint32_t) std::min(h->blk_seg[0].n, std::min(h->blk_seg[1].n, h->blk_seg[2].n));
+    c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
+    c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
     CU(h, cudaEventRecord(h->ev[4], s));
     launch_transmit(c, h->n_sm, s, launches, h->ev[5]);
@@ -806,9 +806,9 @@ int32_t heros_destroy(heros_handle h)
     h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->s_tin.release(); h->s_tout.release();
     h->s_view.release(); h->cub_temp.release(); h->cand_person.release(); h->cand_key.release(); h->cand_t.release();
     h->cand_p.release(); h->inf_person.release(); h->inf_key.release(); h->tr_person.release(); h->inf_t.release();
-    h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->big_seg.release(); h->big_off.release();
-    h->sc_evx.release(); h->sc_j0.release(); h->sc_j1.release(); h->sc_node.release(); h->sc_ill.release();
-    h->sc_evt.release(); h->sc_pre.release(); h->sc_cand.release(); h->sc_p.release(); h->sc_dur.release();
+    h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->warp_seg.release();
+    for (auto& b : h->blk_seg) b.release();
+    h->huge_off.release(); h->scratch.release();
     h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
     h->st_tout.release();
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -1104,7 +1104,7 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
         st.windows++;
         st.visits += (int64_t) h->h_ctr->n_active;
         st.sublocations += (int64_t) h->h_ctr->n_seg;
-        n_big += (int64_t) h->h_ctr->n_big;
+        n_big += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2]);
     }
     CU(h, cudaEventRecord(h->ev[1], h->stream));
     CU(h, cudaEventSynchronize(h->ev[1]));

@@ -32,8 +32,10 @@ struct Counters
     unsigned long long n_cand;       // candidate infections of the current window
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log
-    unsigned long long n_big;        // big segments of the current window
-    unsigned long long scratch_top;  // bump allocator for big-segment scratch (event slots)
+    unsigned long long n_warp;       // segments handed to the warp kernel in the current window
+    unsigned long long n_blk[3];     // segments handed to the block kernels (<= 1024 / <= 4096 events in shared
+                                     // memory, larger ones in global scratch)
+    unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
     unsigned long long n_active;     // active stays of the current window
@@ -83,10 +85,12 @@ struct WindowCtx
     const uint32_t* seg_start;  // n_seg + 1 entries
     // candidates
     uint32_t* cand_person; uint32_t* cand_key; double* cand_t; double* cand_p; uint32_t cand_cap;
-    // big-segment work list + scratch
-    uint32_t* big_seg; uint32_t* big_off; uint32_t big_cap;
-    uint64_t* sc_evt; uint32_t* sc_evx; int32_t* sc_pre; uint32_t* sc_j0; uint32_t* sc_j1; double* sc_cand;
-    uint32_t* sc_node; double* sc_p; double* sc_dur; uint32_t* sc_ill; uint64_t scratch_cap;
+    // work lists filled by k_transmit_thread
+    uint32_t* warp_seg; uint32_t warp_cap;
+    uint32_t* blk_seg[3]; uint32_t blk_cap;
+    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[2]
+    unsigned char* scratch; unsigned long long scratch_cap;
+    uint32_t flags;
     Counters* ctr;
 };
 

@@ -22,11 +22,11 @@ class HerosEngine:
     """The GPU engine for the transmission + progression hot path.  All compute happens in libheros_gpu.so."""
 
     def __init__(self, model: int, seed: int, trigger: int = _lib.TRIGGER_EXIT_ONLY, device: int = 0,
-                 window_hours: float = 24.0):
+                 window_hours: float = 24.0, flags: int = 0):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         cfg = _lib.Config(_lib.ABI_VERSION, int(model), int(trigger), int(device), int(seed) & (2 ** 64 - 1),
-                          float(window_hours))
+                          float(window_hours), int(flags), 0)
         rc = self._lib.heros_create(C.byref(cfg), C.byref(self._h))
         if rc != _lib.OK:
             msg = self._lib.heros_last_error(None).decode()

@@ -173,8 +173,9 @@ def run_oracle(scn: Scenario, props: dict, model: int, trigger: int, seed: int, 
                 state=sim.agent_state(), evaluations=sim.n_evaluations(), draws=sim.n_draws(), sim=sim)
 
 
-def make_engine(scn: Scenario, props: dict, model: int, trigger: int, seed: int, window_hours=24.0, policies=()):
-    eng = hb.HerosEngine(model, seed, trigger=trigger, window_hours=window_hours)
+def make_engine(scn: Scenario, props: dict, model: int, trigger: int, seed: int, window_hours=24.0, policies=(),
+                flags=_lib.FLAG_EXACT_STATS):
+    eng = hb.HerosEngine(model, seed, trigger=trigger, window_hours=window_hours, flags=flags)
     eng.set_location_types(scn.type_infect_sub, scn.type_corr)
     eng.set_locations(scn.loc_type, scn.loc_nsub, scn.loc_area)
     eng.set_persons(scn.age, scn.female)
@@ -189,10 +190,10 @@ def make_engine(scn: Scenario, props: dict, model: int, trigger: int, seed: int,
 
 
 def run_gpu(scn: Scenario, props: dict, model: int, trigger: int, seed: int, days=None, window_hours=24.0,
-            policies=(), submit="all", step_hours=24.0):
+            policies=(), submit="all", step_hours=24.0, flags=_lib.FLAG_EXACT_STATS):
     """submit: 'all' = every stay up-front; 'daily' = before each day only the stays that begin that day, stays still
     open at midnight first submitted as open (t_out = +inf) and re-submitted when they close."""
-    eng = make_engine(scn, props, model, trigger, seed, window_hours, policies)
+    eng = make_engine(scn, props, model, trigger, seed, window_hours, policies, flags)
     eng.expose(scn.seeds, np.zeros(len(scn.seeds)))
     days = scn.days if days is None else days
     stats = []

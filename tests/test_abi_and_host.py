@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert C.sizeof(_lib.Config) == 32
+    assert C.sizeof(_lib.Config) == 40
     assert C.sizeof(_lib.AreaParams) == 6 * 8 and C.sizeof(_lib.DistParams) == 10 * 8
     assert C.sizeof(_lib.Duration) == 32
     assert C.sizeof(_lib.ProgParams) == 5 * 2 * 128 * 8 + 10 * 32
@@ -49,8 +49,8 @@ def test_no_cpu_fallback_without_a_device():
 def test_create_rejects_bad_configs_before_touching_the_device():
     lib = _lib.load()
     h = C.c_void_p()
-    for cfg in (_lib.Config(99, 0, 0, 0, 1, 24.0), _lib.Config(1, 7, 0, 0, 1, 24.0), _lib.Config(1, 0, 5, 0, 1, 24.0),
-                _lib.Config(1, 0, 0, 0, 1, 0.0)):
+    for cfg in (_lib.Config(99, 0, 0, 0, 1, 24.0, 0, 0), _lib.Config(1, 7, 0, 0, 1, 24.0, 0, 0),
+                _lib.Config(1, 0, 5, 0, 1, 24.0, 0, 0), _lib.Config(1, 0, 0, 0, 1, 0.0, 0, 0)):
         assert lib.heros_create(C.byref(cfg), C.byref(h)) == _lib.ERR_INVALID
         assert lib.heros_last_error(None)
     assert lib.heros_create(None, C.byref(h)) == _lib.ERR_INVALID

@@ -169,3 +169,19 @@ def test_seeding_is_the_keyed_bottom_k_and_respects_age_bounds():
     assert (st["phase"][chosen] == 1).all() and (st["exposure"][chosen] == 0.0).all()
     assert ((st["next_time"][chosen] >= 60.0) & (st["next_time"][chosen] <= 91.2)).all()
     eng.close()
+
+
+@pytest.mark.parametrize("model,trigger", [("area", "exit"), ("distance", "both")])
+def test_fast_path_without_exact_stats_gives_identical_results(model, trigger):
+    """Default mode: sub-locations where nobody can be infected only advance lastCalculation (no chain walk).  The
+    infection events, trajectories and every lastCalculation must not change."""
+    scn = Scenario(seed=16, n_persons=1200, n_households=420, n_workplaces=30, n_shops=3, days=10,
+                   shop_visits_per_day=2.0, tie_fraction=0.3, short_gap_fraction=0.3)
+    props = hot_props(model)
+    ora = run_oracle(scn, props, MODELS[model], TRIGGERS[trigger], seed=21)
+    gpu = run_gpu(scn, props, MODELS[model], TRIGGERS[trigger], seed=21, flags=0)
+    assert_same_run(gpu, ora)
+    assert sum(s["evaluations"] for s in gpu["stats"]) < ora["evaluations"]  # chains were skipped somewhere
+    for loc in range(scn.n_loc):
+        for sub in range(int(scn.loc_nsub[loc])):
+            assert gpu["engine"].last_calculation(loc, sub) == ora["sim"].last_calc(loc, sub)
