@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
             const uint32_t slots = need_enters ? 2 * n : n;
             double r_bound = both ? 2.0 * n : (double) n;
             if (thr > 0 && (c.T1 - c.T0) / thr + 2.0 < r_bound) r_bound = (c.T1 - c.T0) / thr + 2.0;
-            const int cls = r_bound > (double) BLOCK_P_CAP ? 2 : (slots <= 1024 ? 0 : (slots <= 8192 ? 1 : 2));
+            const int cls = slots <= 1024 ? 0 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 1 : 2);
             const unsigned long long slot = atomicAdd(&c.ctr->n_blk[cls], 1ull);
             if (slot < c.blk_cap)
             {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
                 {
                     unsigned long long mp = 64;
                     while (mp < slots) mp <<= 1;
-                    const unsigned long long bytes = mp * 40 + 256;
+                    const unsigned long long bytes = (unsigned long long) slots * 56 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
                     const unsigned long long off = atomicAdd(&c.ctr->scratch_top, bytes);
                     if (off + bytes <= c.scratch_cap) c.huge_off[slot] = off;
                     else { c.blk_seg[cls][slot] = KEY_NONE; atomicOr(&c.ctr->overflow, 2u); }
@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-// out[i] = sum_{k<i} f(k) for i < n (exclusive), returns the total.  All threads of the block must call.
+// out[i] = sum_{k<i} f(k) for i < n (exclusive), returns the total.  All threads of the block must call.  `out` may be
+// the storage f reads from (every thread reads an element before it overwrites it, chunks are private).
 template <class F, class T>
 __device__ int block_exclusive_scan(int n, F f, T* out, int* s_warp /* 32 ints of shared memory */)
 {
@@ -415,27 +416,57 @@ __device__ int block_exclusive_scan(int n, F f, T* out, int* s_warp /* 32 ints o
     return total;
 }
 
-// order-preserving map of a double onto uint64 and back
-__device__ __forceinline__ uint64_t time_key(double t)
+// out[i] = min_{k >= i} f(k) for i < n (f returns an int; "none" = a large value).  All threads must call.
+template <class F, class T>
+__device__ void block_suffix_min(int n, F f, T* out, int* s_warp)
 {
-    const uint64_t b = f64_bits(t);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    const int tid = threadIdx.x, TH = blockDim.x;
+    const int chunk = (n + TH - 1) / TH;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int local = 0x7fffffff;
+    for (int i = lo; i < hi; ++i) local = min(local, f(i));
+    // suffix-min over the per-thread values: thread t needs min over threads > t
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int v = __shfl_down_sync(FULL, incl, o);
+        if ((tid & 31) + o < 32) incl = min(incl, v);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    int after = 0x7fffffff;  // min over the warps above mine
+    for (int w = (tid >> 5) + 1; w < (TH >> 5); ++w) after = min(after, s_warp[w]);
+    const int above_in_warp = __shfl_down_sync(FULL, incl, 1);
+    int run = after;
+    if ((tid & 31) < 31) run = min(run, above_in_warp);
+    for (int i = hi - 1; i >= lo; --i)
+    {
+        run = min(run, f(i));
+        out[i] = (T) run;
+    }
+    __syncthreads();
 }
-__device__ __forceinline__ double key_time(uint64_t k)
-{
-    return bits_f64((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k);
-}
+
+template <int CLS> struct BlockIdx { using type = uint16_t; };
+template <> struct BlockIdx<2> { using type = uint32_t; };
 
 }  // namespace
 
-// CLS 0: <= 1024 events in shared memory, 256 threads; CLS 1: <= 8192 events in shared memory, 1024 threads (16-bit
-// indices, 20 bytes per event + 16 KB of probabilities); CLS 2: anything larger, in global scratch (40 bytes per event)
-template <int CLS> struct BlockIdx { using type = uint16_t; using stype = int16_t; };
-template <> struct BlockIdx<2> { using type = uint32_t; using stype = int32_t; };
-
+// CLS 0: <= 1024 events, 256 threads, shared memory; CLS 1: <= 8192 events and <= 2048 evaluations, 1024 threads,
+// shared memory; CLS 2: anything larger, same algorithm in global scratch.
+//
+// The chain of calculated evaluations needs, from an evaluation at time e, the earliest later candidate event t with
+// !(t - e < threshold).  Events are grouped (not sorted) into time buckets by a counting sort; the successor of an
+// event is found by scanning the <= 3 buckets around e + threshold and otherwise jumping to the first candidate of the
+// next non-empty bucket; the chain start, next[start], next[next[start]] ... is then materialised in O(log n) rounds of
+// pointer doubling.
 template <int MODEL, int CLS>
 __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const WindowCtx c)
 {
+    using idx_t = typename BlockIdx<CLS>::type;
+    constexpr int P_CAP = CLS == 0 ? 1024 : BLOCK_P_CAP;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_warp[32];
     __shared__ double s_red[2 * 32];
@@ -516,67 +547,82 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         const LocParam lp = c.loc_param[c.key_loc[key]];
 
         const int slots = need_enters ? 2 * n : n;
-        int mp = 64;
-        while (mp < slots) mp <<= 1;
-        // scratch: evt u64[mp] | p f64[BLOCK_P_CAP or mp] | j0, j1 idx[mp + 2] (event -> stay, then the pointer-doubling
-        //          tables) | pre[mp] | aidx[mp] | node[mp] | ill[mp]
-        using idx_t = typename BlockIdx<CLS>::type;
-        using sidx_t = typename BlockIdx<CLS>::stype;
+        int NB = 32;
+        while (NB * 4 < slots && NB < (CLS == 2 ? 65536 : 2048)) NB <<= 1;
+        const double scale = (double) NB / (c.T1 - c.T0);
+        auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
+        auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
+        // scratch: ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
+        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | bmin idx[NB] | nne idx[NB+1] |
+        //          ev_k u8[slots]
         unsigned char* base = CLS == 2 ? c.scratch + c.huge_off[w] : smem;
-        uint64_t* evt = (uint64_t*) base;
-        double* pr = (double*) (evt + mp);
-        idx_t* j0 = (idx_t*) (pr + (CLS == 2 ? mp : BLOCK_P_CAP));
-        idx_t* j1 = j0 + (mp + 2);
-        sidx_t* pre = (sidx_t*) (j1 + (mp + 2));
-        idx_t* aidx = (idx_t*) (pre + mp);
-        idx_t* node = aidx + mp;
-        idx_t* illl = node + mp;
-        idx_t* evx = j0;
+        double* ev_t = (double*) base;
+        double* pr = ev_t + slots;
+        uint32_t* bstart = (uint32_t*) (pr + (CLS == 2 ? slots : P_CAP));
+        int32_t* bcur = (int32_t*) (bstart + NB + 1);
+        int32_t* bsign = bcur + NB;
+        idx_t* ja = (idx_t*) (bsign + NB);
+        idx_t* jb = ja + (slots + 1);
+        idx_t* node = jb + (slots + 1);
+        idx_t* illl = node + slots;
+        idx_t* bmin = illl + n;
+        idx_t* nne = bmin + NB;
+        uint8_t* ev_k = (uint8_t*) (nne + NB + 1);
 
-        // 1. movement events of the window: (time, stay << 1 | is_enter); padding sorts last
-        for (int i = tid; i < mp; i += TH)
+        // 1. histogram of the window's movement events over NB time buckets
+        for (int i = tid; i <= NB; i += TH) bstart[i] = 0;
+        for (int i = tid; i < NB; i += TH) bsign[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < slots; i += TH)
         {
-            uint64_t k = ~0ull;
             const int v = need_enters ? (i >> 1) : i;
             const int kind = need_enters ? (i & 1) : 0;
-            if (i < slots)
+            const double t = kind ? tin[v] : tout[v];
+            if (t >= c.T0 && t < c.T1)
             {
-                const double t = kind ? tin[v] : tout[v];
-                if (t >= c.T0 && t < c.T1) k = time_key(t);
+                const int bk = bucket_of(t);
+                atomicAdd(&bstart[bk], 1u);
+                if (MODEL == HEROS_MODEL_DISTANCE) atomicAdd(&bsign[bk], kind ? 1 : -1);
             }
-            evt[i] = k;
-            evx[i] = (idx_t) ((v << 1) | kind);
         }
         __syncthreads();
-        // 2. bitonic sort by time
-        for (int k = 2; k <= mp; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1)
-            {
-                for (int idx = tid; idx < (mp >> 1); idx += TH)
-                {
-                    const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
-                    const int q = i | j;
-                    const uint64_t ki = evt[i], kq = evt[q];
-                    const bool up = (i & k) == 0;
-                    if ((ki > kq) == up && ki != kq)
-                    {
-                        evt[i] = kq; evt[q] = ki;
-                        const idx_t xi = evx[i]; evx[i] = evx[q]; evx[q] = xi;
-                    }
-                }
-                __syncthreads();
-            }
-        int m_ev;
+        // 2. bucket offsets
+        const int m_ev = block_exclusive_scan(NB, [&](int i) { return (int) bstart[i]; }, bstart, s_warp);
+        if (tid == 0) bstart[NB] = (uint32_t) m_ev;
+        for (int i = tid; i < NB; i += TH) bcur[i] = (int32_t) bstart[i];
+        __syncthreads();
+        // 3. scatter the events into their buckets (order inside a bucket is irrelevant to every result)
+        for (int i = tid; i < slots; i += TH)
         {
-            int lo = 0, hi = mp;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (evt[mid] == ~0ull) hi = mid; else lo = mid + 1; }
-            m_ev = lo;
+            const int v = need_enters ? (i >> 1) : i;
+            const int kind = need_enters ? (i & 1) : 0;
+            const double t = kind ? tin[v] : tout[v];
+            if (t >= c.T0 && t < c.T1)
+            {
+                const int pos = atomicAdd(&bcur[bucket_of(t)], 1);
+                ev_t[pos] = t;
+                ev_k[pos] = (uint8_t) kind;
+            }
         }
-        // 3. occupancy change before every event (enter +1, exit -1) and the occupants carried into the window
+        __syncthreads();
+        const idx_t END = (idx_t) m_ev;
+        auto is_cand = [&](int j) { return both || ev_k[j] == 0; };
+        // 4. earliest candidate of every bucket, next bucket that has one, occupancy at the start of every bucket
+        for (int bk = tid; bk < NB; bk += TH)
+        {
+            double best_t = pos_inf();
+            int best = m_ev;
+            for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
+                if (is_cand(j) && (ev_t[j] < best_t || (ev_t[j] == best_t && j < best))) { best_t = ev_t[j]; best = j; }
+            bmin[bk] = (idx_t) best;
+        }
+        __syncthreads();
+        block_suffix_min(NB, [&](int i) { return bmin[i] != END ? i : NB; }, nne, s_warp);
+        if (tid == 0) nne[NB] = (idx_t) NB;
         int carried = 0;
         if (MODEL == HEROS_MODEL_DISTANCE)
         {
-            block_exclusive_scan(m_ev, [&](int i) { return (evx[i] & 1u) ? 1 : -1; }, pre, s_warp);
+            block_exclusive_scan(NB, [&](int i) { return bsign[i]; }, bcur, s_warp);  // bcur: occupancy change before bucket
             for (int v = tid; v < n; v += TH) carried += (tin[v] < c.T0);
             carried = (int) warp_sum((double) carried);
             if (tid == 0) s_flag[1] = 0;
@@ -585,33 +631,35 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             __syncthreads();
             carried = s_flag[1];
         }
-        // 4. the events that may trigger an evaluation, in time order: aidx[k] = event index of candidate k
-        const int mc = block_exclusive_scan(m_ev, [&](int i) { return (both || !(evx[i] & 1u)) ? 1 : 0; }, j1, s_warp);
-        for (int i = tid; i < m_ev; i += TH)
-            if (both || !(evx[i] & 1u)) aidx[j1[i]] = (idx_t) i;
         __syncthreads();
-        auto cand = [&](int k) { return key_time(evt[aidx[k]]); };
-        // 5. chain of calculated evaluations: next[i] = first candidate whose time since candidate i is not below
-        //    the threshold; the evaluations are start, next[start], next[next[start]], ... (pointer doubling)
-        for (int i = tid; i <= mc; i += TH)
-        {
-            idx_t nx = (idx_t) mc;
-            if (i < mc)
+        // successor of an evaluation at time e: the earliest candidate t > e with !(t - e < thr)
+        auto successor = [&](double e) -> int {
+            int b0 = bucket_raw(e + thr) - 1;
+            b0 = max(b0, 0);
+            double best_t = pos_inf();
+            int best = m_ev;
+            const int b_hi = min(b0 + 3, NB);
+            for (int bk = b0; bk < b_hi; ++bk)
             {
-                const double ti = cand(i);
-                int lo = i + 1, hi = mc;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (!(cand(mid) - ti < thr)) hi = mid; else lo = mid + 1; }
-                nx = (idx_t) lo;
+                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
+                {
+                    const double t = ev_t[j];
+                    if (is_cand(j) && t > e && !(t - e < thr) && (t < best_t || (t == best_t && j < best)))
+                    {
+                        best_t = t;
+                        best = j;
+                    }
+                }
+                if (best != m_ev) return best;  // buckets are ordered in time
             }
-            j0[i] = nx;  // the event -> stay table is dead from here on
-        }
-        int start;
-        {
-            int lo = 0, hi = mc;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (!(cand(mid) - L0 < thr)) hi = mid; else lo = mid + 1; }
-            start = lo;
-        }
-        int r_cap = mc;
+            if (b_hi >= NB) return m_ev;
+            const int bq = (int) nne[b_hi];
+            return bq < NB ? (int) bmin[bq] : m_ev;
+        };
+        // 5. next pointers, chain start, pointer doubling
+        for (int i = tid; i <= m_ev; i += TH) ja[i] = (i < m_ev && is_cand(i)) ? (idx_t) successor(ev_t[i]) : END;
+        const int start = successor(L0);
+        int r_cap = m_ev;
         if (thr > 0)
         {
             const double bound = (c.T1 - c.T0) / thr + 2.0;
@@ -620,69 +668,68 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         for (int r = tid; r < r_cap; r += TH) node[r] = (idx_t) start;
         __syncthreads();
         {
-            idx_t* ja = j0;
-            idx_t* jb = j1;
+            idx_t* pa = ja;
+            idx_t* pb = jb;
             for (int k = 0; (1 << k) < r_cap; ++k)
             {
                 for (int r = tid; r < r_cap; r += TH)
-                    if ((r >> k) & 1) node[r] = ja[node[r]];
-                for (int i = tid; i <= mc; i += TH) jb[i] = ja[ja[i]];
+                    if ((r >> k) & 1) node[r] = pa[node[r]];
+                for (int i = tid; i <= m_ev; i += TH) pb[i] = pa[pa[i]];
                 __syncthreads();
-                idx_t* t = ja; ja = jb; jb = t;
+                idx_t* t = pa; pa = pb; pb = t;
             }
         }
-        int R;  // chain length: node[r] < mc for r < R
+        int R;  // chain length: node[r] != END for r < R
         {
             int lo = 0, hi = r_cap;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int) node[mid] >= mc) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (node[mid] == END) hi = mid; else lo = mid + 1; }
             R = lo;
         }
-        __syncthreads();
-        // from here on node[r] is the EVENT index of evaluation r: its time is key_time(evt[node[r]])
-        for (int r = tid; r < R; r += TH) node[r] = aidx[node[r]];
-        __syncthreads();
         if (tid == 0)
         {
             st.evaluations += (unsigned long long) R;
-            if (R > 0) c.last_calc[key] = key_time(evt[node[R - 1]]);
+            if (R > 0) c.last_calc[key] = ev_t[node[R - 1]];
         }
         if (!need_eval || R == 0) continue;
-        // 6. list of the stays whose person can be ill (j1 as scan output; the doubling tables are dead)
-        const int n_ill = block_exclusive_scan(n, [&](int v) { return phase_is_ill(view_tphase(view[v])) ? 1 : 0; }, j1,
+        // 6. list of the stays whose person can be ill (ja as scan output; the doubling tables are dead)
+        __syncthreads();
+        const int n_ill = block_exclusive_scan(n, [&](int v) { return phase_is_ill(view_tphase(view[v])) ? 1 : 0; }, ja,
                                                s_warp);
         for (int v = tid; v < n; v += TH)
-            if (phase_is_ill(view_tphase(view[v]))) illl[j1[v]] = (idx_t) v;
+            if (phase_is_ill(view_tphase(view[v]))) illl[ja[v]] = (idx_t) v;
         __syncthreads();
         // 7. one thread per evaluation: duration, exposure sum, probability
         for (int r = tid; r < R; r += TH)
         {
-            const double now = key_time(evt[node[r]]);
-            const double duration = now - (r ? key_time(evt[node[r - 1]]) : L0);
+            const int q = (int) node[r];
+            const double now = ev_t[q];
+            const double duration = now - (r ? ev_t[node[r - 1]] : L0);
             double p = 0.0, factor, sum = 0.0;
             if (MODEL == HEROS_MODEL_AREA)
             {
                 factor = area_factor(c.area, duration, lp.denom);
                 if (factor != 0.0)
-                    for (int q = 0; q < n_ill; ++q)
+                    for (int k = 0; k < n_ill; ++k)
                     {
-                        const int v = (int) illl[q];
+                        const int v = (int) illl[k];
                         if (tin[v] < now && now <= tout[v] && ill_at(c, view[v], person[v], now))
                             sum += area_contribution(c.area, now - (double) view_exposure(view[v]));
                     }
             }
             else
             {
-                int lo = 0, hi = m_ev;
-                const uint64_t kn = time_key(now);
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (evt[mid] >= kn) hi = mid; else lo = mid + 1; }
-                const int head_count = carried + pre[lo];  // lo < m_ev: `now` is itself an event
+                // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
+                const int bk = bucket_of(now);
+                int head_count = carried + bcur[bk];
+                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
+                    if (ev_t[j] < now) head_count += ev_k[j] ? 1 : -1;
                 double psi, mu;
                 policy_at(c, now, psi, mu);
                 factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
                 if (factor != 0.0)
-                    for (int q = 0; q < n_ill; ++q)
+                    for (int k = 0; k < n_ill; ++k)
                     {
-                        const int v = (int) illl[q];
+                        const int v = (int) illl[k];
                         if (tin[v] < now && now <= tout[v] && ill_at(c, view[v], person[v], now))
                         {
                             const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(view[v]));
@@ -698,11 +745,15 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         for (int v = tid; v < n; v += TH)
         {
             if (!phase_is_susceptible(view_tphase(view[v]))) continue;
-            const uint64_t k_in = time_key(tin[v]), k_out = time_key(tout[v]);
+            const double t_in = tin[v], t_out = tout[v];
             int lo = 0, hi = R;  // first evaluation with time > t_in
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (evt[node[mid]] > k_in) hi = mid; else lo = mid + 1; }
-            for (int r = lo; r < R && evt[node[r]] <= k_out; ++r)
-                if (pr[r] > 0) draw_and_push(c, st, person[v], key, key_time(evt[node[r]]), pr[r]);
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev_t[node[mid]] > t_in) hi = mid; else lo = mid + 1; }
+            for (int r = lo; r < R; ++r)
+            {
+                const double now = ev_t[node[r]];
+                if (!(now <= t_out)) break;
+                if (pr[r] > 0) draw_and_push(c, st, person[v], key, now, pr[r]);
+            }
         }
     }
     flush_stats(c, st, tid & 31);
@@ -712,7 +763,8 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
 template <int MODEL>
 static void launch_model(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between)
 {
-    const size_t smem0 = 1024 * 20 + BLOCK_P_CAP * 8 + 64, smem1 = 8192 * 20 + BLOCK_P_CAP * 8 + 64;
+    // 17 bytes per event + 8 per kept probability + 16 per bucket (see the scratch layout in k_transmit_block)
+    const size_t smem0 = 1024 * 17 + 1024 * 8 + 256 * 16 + 256, smem1 = 8192 * 17 + BLOCK_P_CAP * 8 + 2048 * 16 + 256;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
