@@ -109,8 +109,8 @@ typedef struct heros_step_stats {
     /* device time per stage, summed over the windows of the call (CUDA events on the engine stream) */
     double progress_ms;       /* disease-phase state machine */
     double bucket_ms;         /* window list + radix sort by sub-location + gather + segment offsets */
-    double transmit_small_ms; /* warp-per-sub-location kernel */
-    double transmit_big_ms;   /* block-per-sub-location kernel */
+    double transmit_small_ms; /* all transmission kernels (thread / warp / block per sub-location, run side by side) */
+    double transmit_big_ms;   /* reserved (0) */
     double resolve_ms;        /* earliest-draw-wins + expose */
     double retire_ms;         /* pool compaction */
     int64_t big_sublocations; /* segments handled by the block kernel */

@@ -24,7 +24,7 @@
 
 namespace heros {
 
-void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between);
+void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches);
 
 namespace {
 
@@ -464,6 +464,7 @@ struct heros_engine
     heros_config cfg{};
     std::string err;
     cudaStream_t stream = nullptr;
+    TransmitStreams ts{};
     cudaEvent_t ev[10]{};
     double stage_ms[6]{};  // progress, bucket, transmit small, transmit big, resolve, retire (current heros_step)
     int n_sm = 148;
@@ -688,7 +689,8 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
     CU(h, cudaEventRecord(h->ev[4], s));
-    launch_transmit(c, h->n_sm, s, launches, h->ev[5]);
+    launch_transmit(c, h->n_sm, h->ts, launches);
+    CU(h, cudaEventRecord(h->ev[5], s));  // the kernels overlap: one interval for all of them
     CU(h, cudaEventRecord(h->ev[6], s));
 
     // 6. resolve: earliest successful draw per person wins
@@ -778,6 +780,12 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
+    h->ts.main = h->stream;
+    for (auto& a : h->ts.aux)
+        if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaEventCreateWithFlags(&h->ts.fork, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    for (auto& j : h->ts.join)
+        if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
     if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -813,6 +821,9 @@ int32_t heros_destroy(heros_handle h)
     h->st_tout.release();
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& a : h->ts.aux) if (a) cudaStreamDestroy(a);
+    if (h->ts.fork) cudaEventDestroy(h->ts.fork);
+    for (auto& j : h->ts.join) if (j) cudaEventDestroy(j);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HEROS_OK;

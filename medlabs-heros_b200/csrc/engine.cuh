@@ -94,4 +94,7 @@ struct WindowCtx
     Counters* ctr;
 };
 
+// the engine stream, three auxiliary streams for the kernels that run side by side, and the fork / join events
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[3]; cudaEvent_t fork; cudaEvent_t join[3]; };
+
 }  // namespace heros

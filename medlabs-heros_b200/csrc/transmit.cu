@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         bool any_ill = false, any_sus = false;
         Top2 top;
         top.init();
+#pragma unroll 4
         for (uint32_t j = a; j < b; ++j)
         {
             const uint32_t tph = view_tphase(c.s_view[j]);
@@ -760,8 +761,10 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
 }
 
 // host-side launcher ----------------------------------------------------------------------------------------------------
+// k_transmit_thread fills the work lists; the warp kernel and the three block kernels then run side by side on the
+// auxiliary streams (they touch disjoint sub-locations), and the main stream joins them.
 template <int MODEL>
-static void launch_model(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between)
+static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
 {
     // 17 bytes per event + 8 per kept probability + 16 per bucket (see the scratch layout in k_transmit_block)
     const size_t smem0 = 1024 * 17 + 1024 * 8 + 256 * 16 + 256, smem1 = 8192 * 17 + BLOCK_P_CAP * 8 + 2048 * 16 + 256;
@@ -774,19 +777,26 @@ static void launch_model(const WindowCtx& c, int n_sm, cudaStream_t s, int& laun
         cudaFuncSetAttribute(k_transmit_block<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
         configured[dev] = true;
     }
+    cudaStream_t s = ts.main;
     k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
-    k_transmit_warp<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
-    cudaEventRecord(between, s);
-    k_transmit_block<MODEL, 1><<<n_sm, 1024, smem1, s>>>(c);
-    k_transmit_block<MODEL, 2><<<n_sm, 1024, 0, s>>>(c);
-    k_transmit_block<MODEL, 0><<<n_sm * 4, 256, smem0, s>>>(c);
+    cudaEventRecord(ts.fork, s);
+    for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
+    k_transmit_block<MODEL, 1><<<n_sm, 1024, smem1, ts.aux[0]>>>(c);
+    k_transmit_block<MODEL, 2><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
+    k_transmit_block<MODEL, 0><<<n_sm * 6, 256, smem0, ts.aux[1]>>>(c);
+    k_transmit_warp<MODEL><<<n_sm * 8, 256, 0, ts.aux[2]>>>(c);
+    for (int k = 0; k < 3; ++k)
+    {
+        cudaEventRecord(ts.join[k], ts.aux[k]);
+        cudaStreamWaitEvent(s, ts.join[k], 0);
+    }
     launches += 5;
 }
 
-void launch_transmit(const WindowCtx& c, int n_sm, cudaStream_t s, int& launches, cudaEvent_t between)
+void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
 {
-    if (c.model == HEROS_MODEL_AREA) launch_model<HEROS_MODEL_AREA>(c, n_sm, s, launches, between);
-    else launch_model<HEROS_MODEL_DISTANCE>(c, n_sm, s, launches, between);
+    if (c.model == HEROS_MODEL_AREA) launch_model<HEROS_MODEL_AREA>(c, n_sm, ts, launches);
+    else launch_model<HEROS_MODEL_DISTANCE>(c, n_sm, ts, launches);
 }
 
 }  // namespace heros
