@@ -3,10 +3,11 @@
 // One window [T0, T1) of simulated time is processed as
 //   1. k_progress        disease-phase state machine of every agent up to T1 (Covid19Progression.java:182-346),
 //                        remembering the phase transmission must see (the phase at T0) and when illness ends
-//   2. k_build_keys      window list = pool of submitted stays + the open stay of every agent, keyed by sub-location
-//   3. radix sort        occupancy bucketing: stays grouped per sub-location (replaces the per-location TIntSets the
-//                        medlabs engine maintains on every addPerson / removePerson)
-//   4. k_gather_sorted   stays + packed agent words in bucket order; segment offsets
+//   2. k_bucket_count    window list = pool of submitted stays + the open stay of every agent; every active stay takes a
+//                        ticket at its sub-location (replaces the per-location TIntSets the medlabs engine maintains on
+//                        every addPerson / removePerson)
+//   3. k_scan_*          bucket offsets = prefix sum over the dense sub-location keys
+//   4. k_bucket_scatter  stays + packed agent words into bucket order
 //   5. k_transmit_*      transmit.cu: every infectPeople evaluation of the window, Philox draws -> candidates
 //   6. k_resolve*        earliest successful draw per person wins; expose() the winners
 //   7. retire            stays that ended before T1 leave the pool
@@ -18,7 +19,6 @@
 #include <limits>
 #include <numeric>
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -133,9 +133,16 @@ __global__ void __launch_bounds__(TPB) k_progress(const AgentArrays A, uint32_t 
 
 struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; };
 
-__global__ void __launch_bounds__(TPB) k_build_keys(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
-                                                    const double* open_tin, uint32_t n_agents, double T1,
-                                                    uint32_t inactive_key, uint32_t* wl_key, uint32_t* wl_idx)
+// ---- occupancy bucketing: a counting sort over the dense sub-location keys ---------------------------------------------
+// Replaces the per-location TIntSets the medlabs engine updates on every addPerson / removePerson.
+// 1. k_bucket_count   every active stay takes a ticket at its sub-location: rank = atomicAdd(count[key], 1)
+// 2. k_scan_*         seg_start = exclusive prefix sum of the counts (n_keys + 1 entries)
+// 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]
+// The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
+// (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
+__global__ void __launch_bounds__(TPB) k_bucket_count(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
+                                                      const double* open_tin, uint32_t n_agents, double T1,
+                                                      uint32_t* count, uint32_t* rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pool + n_agents) return;
@@ -143,50 +150,121 @@ __global__ void __launch_bounds__(TPB) k_build_keys(PoolArrays P, uint32_t n_poo
     double tin;
     if (i < n_pool) { key = P.key[i]; tin = P.tin[i]; }
     else { key = open_key[i - n_pool]; tin = open_tin[i - n_pool]; }
-    wl_key[i] = (key != KEY_NONE && tin < T1) ? key : inactive_key;
-    wl_idx[i] = i;
+    rank[i] = (key != KEY_NONE && tin < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
 }
 
-__global__ void __launch_bounds__(TPB) k_gather_sorted(PoolArrays P, uint32_t n_pool, const double* open_tin,
-                                                       uint32_t n_total, const uint32_t* s_idx, const uint64_t* view,
-                                                       uint32_t* s_person, double* s_tin, double* s_tout,
-                                                       uint64_t* s_view)
+__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
+                                                        const double* open_tin, uint32_t n_agents,
+                                                        const uint32_t* rank, const uint32_t* seg_start,
+                                                        const uint64_t* view, StayRec* rec)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_total) return;
-    const uint32_t i = s_idx[j];
-    uint32_t person;
-    double tin, tout;
-    if (i < n_pool) { person = P.person[i]; tin = P.tin[i]; tout = P.tout[i]; }
-    else { person = i - n_pool; tin = open_tin[person]; tout = bits_f64(0x7ff0000000000000ull); }
-    s_person[j] = person;
-    s_tin[j] = tin;
-    s_tout[j] = tout;
-    s_view[j] = view[person];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pool + n_agents) return;
+    const uint32_t r = rank[i];
+    if (r == KEY_NONE) return;
+    StayRec o;
+    uint32_t key;
+    if (i < n_pool) { o.person = P.person[i]; key = P.key[i]; o.tin = P.tin[i]; o.tout = P.tout[i]; }
+    else
+    {
+        o.person = i - n_pool;
+        key = open_key[o.person];
+        o.tin = open_tin[o.person];
+        o.tout = bits_f64(0x7ff0000000000000ull);
+    }
+    o.view = view[o.person];
+    o.pad = 0;
+    rec[seg_start[key] + r] = o;
 }
 
-struct HeadPred
+// exclusive prefix sum of count[0..n) into out[0..n], out[n] = total: tile sums, scan of the tile sums, tile scans
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_reduce_add(uint32_t v, uint32_t* s_w)
 {
-    const uint32_t* k;
-    __device__ bool operator()(uint32_t j) const { return j == 0 || k[j] != k[j - 1]; }
-};
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (int w = 0; w < (int) (blockDim.x >> 5); ++w) t += s_w[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_tile_sums(const uint32_t* count, uint32_t n, uint32_t* tile_sum)
+{
+    __shared__ uint32_t s_w[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) v += (base + k < n) ? count[base + k] : 0u;
+    v = block_reduce_add(v, s_w);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_sum, uint32_t n_tiles, uint32_t* out_total,
+                                                     Counters* ctr)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += blockDim.x)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? tile_sum[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t off = s_carry;
+        for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) off += s_w[w];
+        if (i < n_tiles) tile_sum[i] = off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *out_total = s_carry; ctr->n_active = s_carry; }
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_apply(const uint32_t* count, uint32_t n, const uint32_t* tile_off,
+                                                    uint32_t* out)
+{
+    __shared__ uint32_t s_w[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], local = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? count[base + k] : 0u; local += v[k]; }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t run = tile_off[blockIdx.x] + incl - local;
+    for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) run += s_w[w];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+    {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
 
 struct KeepPred
 {
     const uint32_t* key; const double* tout; double T1;
     __device__ bool operator()(uint32_t i) const { return key[i] != KEY_NONE && !(tout[i] < T1); }
 };
-
-__global__ void k_finish_segments(const uint32_t* s_key, uint32_t* seg_start, const uint32_t* n_sel, uint32_t n_total,
-                                  uint32_t inactive_key, Counters* ctr)
-{
-    const uint32_t ns = *n_sel;
-    uint32_t n_seg = ns, n_active = n_total;
-    if (ns > 0 && s_key[seg_start[ns - 1]] == inactive_key) { n_seg = ns - 1; n_active = seg_start[ns - 1]; }
-    seg_start[n_seg] = n_active;
-    ctr->n_seg = n_seg;
-    ctr->n_active = n_active;
-}
 
 __global__ void __launch_bounds__(TPB) k_retire_gather(PoolArrays src, PoolArrays dst, const uint32_t* idx,
                                                        const uint32_t* n_keep, Counters* ctr)
@@ -504,9 +582,8 @@ struct heros_engine
     uint32_t n_pool = 0;
 
     // window buffers
-    DevBuf<uint32_t> wl_key, wl_idx, s_key, s_idx, s_person, seg_start, keep_idx, d_nsel;
-    DevBuf<double> s_tin, s_tout;
-    DevBuf<uint64_t> s_view;
+    DevBuf<uint32_t> bk_count, bk_rank, seg_start, tile_sum, keep_idx, d_nsel;
+    DevBuf<StayRec> rec;
     DevBuf<uint8_t> cub_temp;
 
     // candidates, logs
@@ -617,7 +694,6 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     const uint32_t n_pool = h->n_pool;
     const uint32_t n_total = n_pool + N;
     const int cur = h->pool_cur, oth = cur ^ 1;
-    const uint32_t inactive_key = h->n_keys;
 
     CU(h, cudaEventRecord(h->ev[2], s));
     k_zero_window<<<1, 1, 0, s>>>(h->d_ctr.p);
@@ -630,41 +706,31 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
 
     CU(h, cudaEventRecord(h->ev[3], s));
 
-    // 2. window list keys
-    CU(h, h->wl_key.ensure(n_total)); CU(h, h->wl_idx.ensure(n_total));
-    CU(h, h->s_key.ensure(n_total)); CU(h, h->s_idx.ensure(n_total));
-    CU(h, h->s_person.ensure(n_total)); CU(h, h->s_tin.ensure(n_total)); CU(h, h->s_tout.ensure(n_total));
-    CU(h, h->s_view.ensure(n_total)); CU(h, h->seg_start.ensure((size_t) n_total + 2));
+    // 2-4. occupancy bucketing: counting sort of the window's stays over the dense sub-location keys
+    const uint32_t n_keys = h->n_keys;
+    const uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
+    CU(h, h->bk_count.ensure((size_t) n_keys + 1)); CU(h, h->seg_start.ensure((size_t) n_keys + 2));
+    CU(h, h->tile_sum.ensure((size_t) n_tiles + 1));
+    CU(h, h->bk_rank.ensure(n_total)); CU(h, h->rec.ensure(n_total));
     CU(h, h->keep_idx.ensure(std::max<uint32_t>(n_pool, 1)));
     { const int32_t rc_ = ensure_pool(h, oth, std::max<uint32_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
     const PoolArrays P = pool_arrays(h, cur);
-    k_build_keys<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, T1, inactive_key,
-                                                     h->wl_key.p, h->wl_idx.p);
-    ++launches;
-
-    // 3. bucket by sub-location
-    const int end_bit = std::max(1, bit_length(inactive_key));
-    size_t temp_sort = 0, temp_sel = 0, temp_keep = 0;
+    CU(h, cudaMemsetAsync(h->bk_count.p, 0, (size_t) n_keys * 4, s));
+    k_bucket_count<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, T1,
+                                                       h->bk_count.p, h->bk_rank.p);
+    k_scan_tile_sums<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p);
+    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_sum.p, n_tiles, h->seg_start.p + n_keys, h->d_ctr.p);
+    k_scan_apply<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p, h->seg_start.p);
+    k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, h->bk_rank.p,
+                                                         h->seg_start.p, h->d_view.p, h->rec.p);
+    launches += 6;
     thrust::counting_iterator<uint32_t> iota(0);
-    HeadPred head{h->s_key.p};
     KeepPred keep{P.key, P.tout, T1};
-    CU(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, h->wl_key.p, h->s_key.p, h->wl_idx.p, h->s_idx.p,
-                                          (int) n_total, 0, end_bit, s));
-    CU(h, cub::DeviceSelect::If(nullptr, temp_sel, iota, h->seg_start.p, h->d_nsel.p, (int) n_total, head, s));
-    CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) n_pool, keep, s));
-    CU(h, h->cub_temp.ensure(std::max(temp_sort, std::max(temp_sel, temp_keep)) + 256));
+    size_t temp_keep = 0;
+    CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) std::max<uint32_t>(n_pool, 1), keep, s));
+    CU(h, h->cub_temp.ensure(temp_keep + 256));
     size_t tb = h->cub_temp.n;
-    CU(h, cub::DeviceRadixSort::SortPairs(h->cub_temp.p, tb, h->wl_key.p, h->s_key.p, h->wl_idx.p, h->s_idx.p,
-                                          (int) n_total, 0, end_bit, s));
-    launches += 1 + (end_bit + 7) / 8 * 2;
-
-    // 4. stays in bucket order + segment offsets
-    k_gather_sorted<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_tin.p, n_total, h->s_idx.p, h->d_view.p,
-                                                        h->s_person.p, h->s_tin.p, h->s_tout.p, h->s_view.p);
-    tb = h->cub_temp.n;
-    CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->seg_start.p, h->d_nsel.p, (int) n_total, head, s));
-    k_finish_segments<<<1, 1, 0, s>>>(h->s_key.p, h->seg_start.p, h->d_nsel.p, n_total, inactive_key, h->d_ctr.p);
-    launches += 4;
+    (void) tb;
 
     // 5. transmission
     const size_t list_cap = (size_t) n_total / 32 + 16;
@@ -678,8 +744,7 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
     c.key_loc = h->d_key_loc.p; c.loc_param = h->d_loc_param.p; c.last_calc = h->d_last_calc.p; c.n_keys = h->n_keys;
     c.view = h->d_view.p; c.ill_end = h->d_ill_end.p;
-    c.s_key = h->s_key.p; c.s_person = h->s_person.p; c.s_tin = h->s_tin.p; c.s_tout = h->s_tout.p;
-    c.s_view = h->s_view.p; c.seg_start = h->seg_start.p;
+    c.rec = h->rec.p; c.seg_start = h->seg_start.p;
     c.cand_person = h->cand_person.p; c.cand_key = h->cand_key.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
     c.warp_seg = h->warp_seg.p; c.warp_cap = (uint32_t) h->warp_seg.n;
@@ -810,9 +875,8 @@ int32_t heros_destroy(heros_handle h)
     {
         h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
     }
-    h->wl_key.release(); h->wl_idx.release(); h->s_key.release(); h->s_idx.release(); h->s_person.release();
-    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->s_tin.release(); h->s_tout.release();
-    h->s_view.release(); h->cub_temp.release(); h->cand_person.release(); h->cand_key.release(); h->cand_t.release();
+    h->bk_count.release(); h->bk_rank.release(); h->tile_sum.release(); h->rec.release();
+    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->cub_temp.release(); h->cand_person.release(); h->cand_key.release(); h->cand_t.release();
     h->cand_p.release(); h->inf_person.release(); h->inf_key.release(); h->tr_person.release(); h->inf_t.release();
     h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->warp_seg.release();
     for (auto& b : h->blk_seg) b.release();

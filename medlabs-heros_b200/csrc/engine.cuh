@@ -23,6 +23,15 @@ struct LocParam
     double denom;     // correctionFactorArea * area_sub        (TArea:156)
 };
 
+// one stay of the window in bucket order: everything transmission needs from it in one 32-byte sector
+struct alignas(16) StayRec
+{
+    double tin, tout;
+    uint64_t view;    // packed agent word of the person (phase at window start, exposure time, ...)
+    uint32_t person;
+    uint32_t pad;
+};
+
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
 // device-side counters of one engine (zeroed per heros_step call, except the log cursors)
@@ -80,14 +89,14 @@ struct WindowCtx
     const uint32_t* key_loc; const LocParam* loc_param; double* last_calc; uint32_t n_keys;
     // agents
     const uint64_t* view; const double* ill_end;
-    // sorted stays of the window
-    const uint32_t* s_key; const uint32_t* s_person; const double* s_tin; const double* s_tout; const uint64_t* s_view;
-    const uint32_t* seg_start;  // n_seg + 1 entries
+    // the window's stays bucketed by sub-location: stays of key k are rec[seg_start[k] .. seg_start[k + 1])
+    StayRec* rec;
+    const uint32_t* seg_start;  // n_keys + 1 entries
     // candidates
     uint32_t* cand_person; uint32_t* cand_key; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
-    uint32_t* warp_seg; uint32_t warp_cap;
-    uint32_t* blk_seg[3]; uint32_t blk_cap;
+    uint32_t* warp_seg; uint32_t warp_cap;           // sub-location keys queued for the warp kernel
+    uint32_t* blk_seg[3]; uint32_t blk_cap;          // ... and for the three block kernels
     unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[2]
     unsigned char* scratch; unsigned long long scratch_cap;
     uint32_t flags;

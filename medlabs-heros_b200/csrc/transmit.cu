@@ -147,24 +147,37 @@ __device__ __forceinline__ bool probability(double factor, double sum, double& p
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------------
-// one thread per sub-location
+// one thread per sub-location key
 // ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// canonical order of the stays of a sub-location: by (person, t_in).  Exposure sums are accumulated in this order, so
+// probabilities do not depend on the order in which stays were submitted, exchanged between GPUs or scattered.
+__device__ __forceinline__ bool stay_before(uint32_t pa, double ta, uint32_t pb, double tb)
+{
+    return pa < pb || (pa == pb && ta < tb);
+}
+
+}  // namespace
+
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
 {
-    const uint32_t n_seg = (uint32_t) c.ctr->n_seg;
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
     Local st;
+    unsigned occupied = 0;
 
-    for (uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x; seg < n_seg; seg += gridDim.x * blockDim.x)
+    for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
     {
-        const uint32_t a = c.seg_start[seg], b = c.seg_start[seg + 1];
+        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
         const uint32_t n = b - a;
+        if (n == 0) continue;
+        ++occupied;
         if (n > 32)
         {
-            // block kernels: by the power of two that holds the segment's events and the bound on its evaluations
+            // block kernels: by the number of events of the sub-location and the bound on its evaluations
             const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
             const uint32_t slots = need_enters ? 2 * n : n;
             double r_bound = both ? 2.0 * n : (double) n;
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
             const unsigned long long slot = atomicAdd(&c.ctr->n_blk[cls], 1ull);
             if (slot < c.blk_cap)
             {
-                c.blk_seg[cls][slot] = seg;
+                c.blk_seg[cls][slot] = key;
                 if (cls == 2)
                 {
                     unsigned long long mp = 64;
@@ -188,25 +201,21 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
                 atomicOr(&c.ctr->overflow, 2u);
             continue;
         }
-        const uint32_t key = c.s_key[a];
+        StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
         // pass 1: who is here, and the two latest events
         bool any_ill = false, any_sus = false;
         Top2 top;
         top.init();
 #pragma unroll 4
-        for (uint32_t j = a; j < b; ++j)
+        for (uint32_t j = 0; j < n; ++j)
         {
-            const uint32_t tph = view_tphase(c.s_view[j]);
+            const StayRec r = rec[j];
+            const uint32_t tph = view_tphase(r.view);
             any_ill |= phase_is_ill(tph);
             any_sus |= phase_is_susceptible(tph);
-            const double tout = c.s_tout[j];
-            if (tout >= c.T0 && tout < c.T1) top.add(tout);
-            if (both)
-            {
-                const double tin = c.s_tin[j];
-                if (tin >= c.T0 && tin < c.T1) top.add(tin);
-            }
+            if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
+            if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
         }
         if (!(top.m1 > neg_inf())) continue;  // no movement in this window
         const bool need_eval = any_ill && any_sus;
@@ -222,23 +231,31 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         if (n > THREAD_SLOW_MAX)
         {
             const unsigned long long slot = atomicAdd(&c.ctr->n_warp, 1ull);
-            if (slot < c.warp_cap) c.warp_seg[slot] = seg;
+            if (slot < c.warp_cap) c.warp_seg[slot] = key;
             else atomicOr(&c.ctr->overflow, 2u);
             continue;
         }
+        if (need_eval)  // canonical order (insertion sort in place, n <= 8)
+            for (uint32_t i = 1; i < n; ++i)
+            {
+                const StayRec r = rec[i];
+                uint32_t j = i;
+                while (j > 0 && stay_before(r.person, r.tin, rec[j - 1].person, rec[j - 1].tin)) { rec[j] = rec[j - 1]; --j; }
+                if (j != i) rec[j] = r;
+            }
         // walk the chain of calculated evaluations sequentially
         const LocParam lp = c.loc_param[c.key_loc[key]];
         double L = L0, done = neg_inf();
         for (;;)
         {
             double now = pos_inf();
-            for (uint32_t j = a; j < b; ++j)
+            for (uint32_t j = 0; j < n; ++j)
             {
-                const double tout = c.s_tout[j];
+                const double tout = rec[j].tout;
                 if (tout >= c.T0 && tout < c.T1 && tout > done && !(tout - L < thr) && tout < now) now = tout;
                 if (both)
                 {
-                    const double tin = c.s_tin[j];
+                    const double tin = rec[j].tin;
                     if (tin >= c.T0 && tin < c.T1 && tin > done && !(tin - L < thr) && tin < now) now = tin;
                 }
             }
@@ -253,48 +270,54 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
             {
                 factor = area_factor(c.area, duration, lp.denom);  // TArea:156
                 if (factor == 0.0) continue;                       // TArea:157
-                for (uint32_t j = a; j < b; ++j)
+                for (uint32_t j = 0; j < n; ++j)
                 {
-                    const uint64_t v = c.s_view[j];
-                    if (c.s_tin[j] < now && now <= c.s_tout[j] && ill_at(c, v, c.s_person[j], now))
-                        sum += area_contribution(c.area, now - (double) view_exposure(v));  // TArea:167-174
+                    const StayRec r = rec[j];
+                    if (r.tin < now && now <= r.tout && ill_at(c, r.view, r.person, now))
+                        sum += area_contribution(c.area, now - (double) view_exposure(r.view));  // TArea:167-174
                 }
             }
             else
             {
                 int head_count = 0;
-                for (uint32_t j = a; j < b; ++j) head_count += (c.s_tin[j] < now && now <= c.s_tout[j]);
+                for (uint32_t j = 0; j < n; ++j) head_count += (rec[j].tin < now && now <= rec[j].tout);
                 double psi, mu;
                 policy_at(c, now, psi, mu);
                 factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);  // TDist:138-143
                 if (factor == 0.0) continue;                                     // TDist:144
-                for (uint32_t j = a; j < b; ++j)
+                for (uint32_t j = 0; j < n; ++j)
                 {
-                    const uint64_t v = c.s_view[j];
-                    if (c.s_tin[j] < now && now <= c.s_tout[j] && ill_at(c, v, c.s_person[j], now))
+                    const StayRec r = rec[j];
+                    if (r.tin < now && now <= r.tout && ill_at(c, r.view, r.person, now))
                     {
-                        const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(v));  // TDist:155-159
-                        if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);                 // TDist:161-164
+                        const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(r.view));  // TDist:155-159
+                        if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);                      // TDist:161-164
                     }
                 }
             }
             double p;
             if (!probability<MODEL>(factor, sum, p) || !(p > 0)) continue;
-            for (uint32_t j = a; j < b; ++j)
-                if (c.s_tin[j] < now && now <= c.s_tout[j] && phase_is_susceptible(view_tphase(c.s_view[j])))
-                    draw_and_push(c, st, c.s_person[j], key, now, p);  // TArea:190 / TDist:181
+            for (uint32_t j = 0; j < n; ++j)
+            {
+                const StayRec r = rec[j];
+                if (r.tin < now && now <= r.tout && phase_is_susceptible(view_tphase(r.view)))
+                    draw_and_push(c, st, r.person, key, now, p);  // TArea:190 / TDist:181
+            }
         }
         if (L != L0) c.last_calc[key] = L;
     }
     flush_stats(c, st, threadIdx.x & 31);
+    occupied = __reduce_add_sync(FULL, occupied);
+    if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// one warp per queued sub-location of 9..32 stays, lane i holds stay i
+// one warp per queued sub-location of 9..32 stays, lane i holds stay i (in canonical order)
 // ------------------------------------------------------------------------------------------------------------------
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
 {
+    __shared__ StayRec s_rec[8][32];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -304,30 +327,43 @@ __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
 
     for (uint32_t w = warp; w < n_list; w += n_warps)
     {
-        const uint32_t seg = c.warp_seg[w];
-        const uint32_t a = c.seg_start[seg], b = c.seg_start[seg + 1];
+        const uint32_t key = c.warp_seg[w];
+        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
         const uint32_t n = b - a;
-        const uint32_t key = c.s_key[a];
         const bool have = (uint32_t) lane < n;
-        double tin = pos_inf(), tout = neg_inf();
-        uint64_t view = 0;
-        uint32_t person = 0;
-        if (have)
+        StayRec r;
+        r.tin = pos_inf(); r.tout = neg_inf(); r.view = 0; r.person = 0xFFFFFFFFu; r.pad = 0;
+        if (have) r = c.rec[a + lane];
+        const bool need_eval = __any_sync(FULL, have && phase_is_ill(view_tphase(r.view))) &&
+                               __any_sync(FULL, have && phase_is_susceptible(view_tphase(r.view)));
+        if (need_eval)
         {
-            tin = c.s_tin[a + lane];
-            tout = c.s_tout[a + lane];
-            view = c.s_view[a + lane];
-            person = c.s_person[a + lane];
+            // canonical order: lane <- stay with that rank by (person, t_in); empty lanes sort last
+            int rank = 0;
+            for (int j = 0; j < 32; ++j)
+            {
+                const uint32_t pj = __shfl_sync(FULL, r.person, j);
+                const double tj = __shfl_sync(FULL, r.tin, j);
+                rank += (stay_before(pj, tj, r.person, r.tin) || (pj == r.person && tj == r.tin && j < lane)) ? 1 : 0;
+            }
+            __syncwarp();
+            s_rec[threadIdx.x >> 5][rank] = r;
+            __syncwarp();
+            r = s_rec[threadIdx.x >> 5][lane];
+            __syncwarp();
         }
+        const double tin = r.tin, tout = r.tout;
+        const uint64_t view = r.view;
+        const uint32_t person = r.person;
+        const bool here = person != 0xFFFFFFFFu;
         const LocParam lp = c.loc_param[c.key_loc[key]];
         double L = c.last_calc[key];
         const double L_in = L;
         // movement events of this window that can trigger an evaluation
         double e_in = (c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT && tin >= c.T0 && tin < c.T1) ? tin : pos_inf();
         double e_out = (tout >= c.T0 && tout < c.T1) ? tout : pos_inf();
-        const bool susceptible = have && phase_is_susceptible(view_tphase(view));
-        const bool maybe_ill = have && phase_is_ill(view_tphase(view));
-        const bool need_eval = __any_sync(FULL, maybe_ill) && __any_sync(FULL, susceptible);
+        const bool susceptible = here && phase_is_susceptible(view_tphase(view));
+        const bool maybe_ill = here && phase_is_ill(view_tphase(view));
 
         for (;;)
         {
@@ -482,15 +518,11 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
 
     for (uint32_t w = blockIdx.x; w < n_list; w += gridDim.x)
     {
-        const uint32_t seg = c.blk_seg[CLS][w];
-        if (seg == KEY_NONE) continue;
-        const uint32_t a = c.seg_start[seg], b = c.seg_start[seg + 1];
+        const uint32_t key = c.blk_seg[CLS][w];
+        if (key == KEY_NONE) continue;
+        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
         const int n = (int) (b - a);
-        const double* tin = c.s_tin + a;
-        const double* tout = c.s_tout + a;
-        const uint64_t* view = c.s_view + a;
-        const uint32_t* person = c.s_person + a;
-        const uint32_t key = c.s_key[a];
+        const StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
 
         // 0. who is here and the two latest events; most segments only need lastCalculation advanced
@@ -501,14 +533,14 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             top.init();
             for (int v = tid; v < n; v += TH)
             {
-                const uint32_t tph = view_tphase(view[v]);
+                const uint32_t tph = view_tphase(rec[v].view);
                 ill |= phase_is_ill(tph);
                 sus |= phase_is_susceptible(tph);
-                const double to = tout[v];
+                const double to = rec[v].tout;
                 if (to >= c.T0 && to < c.T1) top.add(to);
                 if (both)
                 {
-                    const double ti = tin[v];
+                    const double ti = rec[v].tin;
                     if (ti >= c.T0 && ti < c.T1) top.add(ti);
                 }
             }
@@ -578,7 +610,7 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         {
             const int v = need_enters ? (i >> 1) : i;
             const int kind = need_enters ? (i & 1) : 0;
-            const double t = kind ? tin[v] : tout[v];
+            const double t = kind ? rec[v].tin : rec[v].tout;
             if (t >= c.T0 && t < c.T1)
             {
                 const int bk = bucket_of(t);
@@ -597,7 +629,7 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         {
             const int v = need_enters ? (i >> 1) : i;
             const int kind = need_enters ? (i & 1) : 0;
-            const double t = kind ? tin[v] : tout[v];
+            const double t = kind ? rec[v].tin : rec[v].tout;
             if (t >= c.T0 && t < c.T1)
             {
                 const int pos = atomicAdd(&bcur[bucket_of(t)], 1);
@@ -624,7 +656,7 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         if (MODEL == HEROS_MODEL_DISTANCE)
         {
             block_exclusive_scan(NB, [&](int i) { return bsign[i]; }, bcur, s_warp);  // bcur: occupancy change before bucket
-            for (int v = tid; v < n; v += TH) carried += (tin[v] < c.T0);
+            for (int v = tid; v < n; v += TH) carried += (rec[v].tin < c.T0);
             carried = (int) warp_sum((double) carried);
             if (tid == 0) s_flag[1] = 0;
             __syncthreads();
@@ -694,10 +726,28 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         if (!need_eval || R == 0) continue;
         // 6. list of the stays whose person can be ill (ja as scan output; the doubling tables are dead)
         __syncthreads();
-        const int n_ill = block_exclusive_scan(n, [&](int v) { return phase_is_ill(view_tphase(view[v])) ? 1 : 0; }, ja,
+        const int n_ill = block_exclusive_scan(n, [&](int v) { return phase_is_ill(view_tphase(rec[v].view)) ? 1 : 0; }, ja,
                                                s_warp);
         for (int v = tid; v < n; v += TH)
-            if (phase_is_ill(view_tphase(view[v]))) illl[ja[v]] = (idx_t) v;
+            if (phase_is_ill(view_tphase(rec[v].view))) jb[ja[v]] = (idx_t) v;
+        __syncthreads();
+        // ... in canonical (person, t_in) order, by rank counting, so that the exposure sums do not depend on the order
+        // in which the stays were scattered into the bucket
+        for (int k = tid; k < n_ill; k += TH)
+        {
+            const int v = (int) jb[k];
+            const uint32_t pv = rec[v].person;
+            const double tv = rec[v].tin;
+            int rank = 0;
+            for (int k2 = 0; k2 < n_ill; ++k2)
+            {
+                const int v2 = (int) jb[k2];
+                const uint32_t p2 = rec[v2].person;
+                const double t2 = rec[v2].tin;
+                rank += (stay_before(p2, t2, pv, tv) || (p2 == pv && t2 == tv && k2 < k)) ? 1 : 0;
+            }
+            illl[rank] = (idx_t) v;
+        }
         __syncthreads();
         // 7. one thread per evaluation: duration, exposure sum, probability
         for (int r = tid; r < R; r += TH)
@@ -713,8 +763,8 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                     for (int k = 0; k < n_ill; ++k)
                     {
                         const int v = (int) illl[k];
-                        if (tin[v] < now && now <= tout[v] && ill_at(c, view[v], person[v], now))
-                            sum += area_contribution(c.area, now - (double) view_exposure(view[v]));
+                        if (rec[v].tin < now && now <= rec[v].tout && ill_at(c, rec[v].view, rec[v].person, now))
+                            sum += area_contribution(c.area, now - (double) view_exposure(rec[v].view));
                     }
             }
             else
@@ -731,9 +781,9 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                     for (int k = 0; k < n_ill; ++k)
                     {
                         const int v = (int) illl[k];
-                        if (tin[v] < now && now <= tout[v] && ill_at(c, view[v], person[v], now))
+                        if (rec[v].tin < now && now <= rec[v].tout && ill_at(c, rec[v].view, rec[v].person, now))
                         {
-                            const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(view[v]));
+                            const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(rec[v].view));
                             if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
                         }
                     }
@@ -745,15 +795,15 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out]
         for (int v = tid; v < n; v += TH)
         {
-            if (!phase_is_susceptible(view_tphase(view[v]))) continue;
-            const double t_in = tin[v], t_out = tout[v];
+            if (!phase_is_susceptible(view_tphase(rec[v].view))) continue;
+            const double t_in = rec[v].tin, t_out = rec[v].tout;
             int lo = 0, hi = R;  // first evaluation with time > t_in
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev_t[node[mid]] > t_in) hi = mid; else lo = mid + 1; }
             for (int r = lo; r < R; ++r)
             {
                 const double now = ev_t[node[r]];
                 if (!(now <= t_out)) break;
-                if (pr[r] > 0) draw_and_push(c, st, person[v], key, now, pr[r]);
+                if (pr[r] > 0) draw_and_push(c, st, rec[v].person, key, now, pr[r]);
             }
         }
     }
