@@ -67,6 +67,8 @@ typedef struct heros_config {
 /* count every calculated evaluation in heros_step_stats.evaluations, also in sub-locations where nobody can be
  * infected (there the engine otherwise only advances lastCalculation and skips the walk over the evaluations) */
 #define HEROS_FLAG_EXACT_STATS 1u
+/* development aid: record the longest duration (SM cycles) of every phase of the group kernels */
+#define HEROS_FLAG_PHASE_CLOCKS 2u
 
 /* covidT_area.* exactly as in the .properties file (days / seconds); converted as disease/Covid19TransmissionArea.java:63-68 */
 typedef struct heros_area_params {
@@ -186,6 +188,8 @@ int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, 
                               const float* exposure_time, double now);
 int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out);
 int32_t heros_get_time(heros_handle h, double* now);
+/* HEROS_FLAG_PHASE_CLOCKS: clocks[class * 16 + phase], 64 entries, of the last window */
+int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks);
 
 /* ---- 1:1 shim of DiseaseTransmission.infectPeople(location, personsInSublocation, duration)
  *      (Covid19TransmissionArea.java:133-248 / Covid19TransmissionDistance.java:115-248), evaluated on the GPU against

@@ -15,6 +15,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_UNKNOWN_PARAMETER 
 MODEL_AREA, MODEL_DISTANCE = 0, 1
 TRIGGER_EXIT_ONLY, TRIGGER_ENTER_AND_EXIT = 0, 1
 FLAG_EXACT_STATS = 1
+FLAG_PHASE_CLOCKS = 2
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR = 0, 1, 2
 PHASE_NAMES = ("Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic", "Hospitalized", "ICU",
                "Dead", "Recovered")  # Covid19Progression.java:130-137
@@ -82,6 +83,7 @@ SIGNATURES = {
     "heros_set_agent_state": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_double]),
     "heros_get_last_calculation": (C.c_int32, [_P, C.c_int32, C.c_int16, C.POINTER(C.c_double)]),
     "heros_get_time": (C.c_int32, [_P, C.POINTER(C.c_double)]),
+    "heros_get_phase_clocks": (C.c_int32, [_P, _P]),
     "heros_infect_people": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_double, C.c_double,
                                         C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_double)]),

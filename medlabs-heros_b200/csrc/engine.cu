@@ -594,7 +594,7 @@ struct heros_engine
     DevBuf<uint8_t> tr_phase;
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> warp_seg, blk_seg[3];
+    DevBuf<uint32_t> warp_seg, blk_seg[4];
     DevBuf<unsigned long long> huge_off;
     DevBuf<unsigned char> scratch;
 
@@ -667,8 +667,9 @@ int32_t sync_counters(heros_handle h)
 
 __global__ void k_zero_window(Counters* c)
 {
-    c->n_cand = 0; c->n_warp = 0; c->n_blk[0] = c->n_blk[1] = c->n_blk[2] = 0; c->scratch_top = 0;
+    c->n_cand = 0; c->n_warp = 0; c->n_blk[0] = c->n_blk[1] = c->n_blk[2] = c->n_blk[3] = 0; c->scratch_top = 0;
     c->n_keep = 0; c->n_seg = 0; c->n_active = 0;
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 16; ++b) c->dbg_clk[a][b] = 0;
 }
 
 int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
@@ -748,8 +749,9 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.cand_person = h->cand_person.p; c.cand_key = h->cand_key.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
     c.warp_seg = h->warp_seg.p; c.warp_cap = (uint32_t) h->warp_seg.n;
-    for (int k = 0; k < 3; ++k) c.blk_seg[k] = h->blk_seg[k].p;
-    c.blk_cap = (uint32_t) std::min(h->blk_seg[0].n, std::min(h->blk_seg[1].n, h->blk_seg[2].n));
+    for (int k = 0; k < 4; ++k) c.blk_seg[k] = h->blk_seg[k].p;
+    c.blk_cap = (uint32_t) h->blk_seg[0].n;
+    for (int k = 1; k < 4; ++k) c.blk_cap = (uint32_t) std::min<size_t>(c.blk_cap, h->blk_seg[k].n);
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
@@ -1179,7 +1181,7 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
         st.windows++;
         st.visits += (int64_t) h->h_ctr->n_active;
         st.sublocations += (int64_t) h->h_ctr->n_seg;
-        n_big += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2]);
+        n_big += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2] + h->h_ctr->n_blk[3]);
     }
     CU(h, cudaEventRecord(h->ev[1], h->stream));
     CU(h, cudaEventSynchronize(h->ev[1]));
@@ -1366,6 +1368,16 @@ int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sub
     if (key >= h->h_loc_base[location + 1]) return fail(h, HEROS_ERR_INVALID, "sub-location out of range");
     CU(h, cudaMemcpyAsync(out, h->d_last_calc.p + key, 8, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
+{
+    if (!h || !clocks) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    memcpy(clocks, h->h_ctr->dbg_clk, sizeof(h->h_ctr->dbg_clk));
     return HEROS_OK;
 }
 

@@ -42,7 +42,7 @@ struct Counters
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log
     unsigned long long n_warp;       // segments handed to the warp kernel in the current window
-    unsigned long long n_blk[3];     // segments handed to the block kernels (<= 1024 / <= 4096 events in shared
+    unsigned long long n_blk[4];     // segments handed to the group kernels (<= 256 / 1024 / 8192 events in shared
                                      // memory, larger ones in global scratch)
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
@@ -53,6 +53,7 @@ struct Counters
     unsigned int late_visits;        // t_in before the engine time
     unsigned int pad;
     long long phase_counts[8];
+    unsigned long long dbg_clk[4][16];  // HEROS_FLAG_PHASE_CLOCKS: max cycles per phase of k_transmit_group, per class
 };
 
 template <typename T>
@@ -96,14 +97,14 @@ struct WindowCtx
     uint32_t* cand_person; uint32_t* cand_key; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
     uint32_t* warp_seg; uint32_t warp_cap;           // sub-location keys queued for the warp kernel
-    uint32_t* blk_seg[3]; uint32_t blk_cap;          // ... and for the three block kernels
-    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[2]
+    uint32_t* blk_seg[4]; uint32_t blk_cap;          // ... and for the four group kernels
+    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[3]
     unsigned char* scratch; unsigned long long scratch_cap;
     uint32_t flags;
     Counters* ctr;
 };
 
-// the engine stream, three auxiliary streams for the kernels that run side by side, and the fork / join events
-struct TransmitStreams { cudaStream_t main; cudaStream_t aux[3]; cudaEvent_t fork; cudaEvent_t join[3]; };
+// the engine stream, four auxiliary streams for the kernels that run side by side, and the fork / join events
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[4]; cudaEvent_t fork; cudaEvent_t join[4]; };
 
 }  // namespace heros

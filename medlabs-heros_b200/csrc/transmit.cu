@@ -15,9 +15,9 @@
 //                       larger ones are queued for the warp kernel.  Segments of > 32 stays are queued for the block
 //                       kernels.
 //   k_transmit_warp   : one warp per queued segment (9..32 stays), lane i holds stay i, shuffles + REDUX
-//   k_transmit_block  : one block per segment of > 32 stays: bitonic sort of its events in shared memory, the chain of
-//                       calculated evaluations by pointer doubling, exposure sums per evaluation, then per stay the
-//                       draws of exactly the evaluations it was present at
+//   k_transmit_group  : one warp or block per segment of > 32 stays: its events bucketed by time in shared memory, the
+//                       chain of calculated evaluations by successor search + pointer doubling, exposure sums per
+//                       evaluation, then per stay the draws of exactly the evaluations it was present at
 // Output: candidate infections (person, key, time, p); engine.cu keeps the earliest per person.
 #include "engine.cuh"
 
@@ -182,12 +182,12 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
             const uint32_t slots = need_enters ? 2 * n : n;
             double r_bound = both ? 2.0 * n : (double) n;
             if (thr > 0 && (c.T1 - c.T0) / thr + 2.0 < r_bound) r_bound = (c.T1 - c.T0) / thr + 2.0;
-            const int cls = slots <= 1024 ? 0 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 1 : 2);
+            const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
             const unsigned long long slot = atomicAdd(&c.ctr->n_blk[cls], 1ull);
             if (slot < c.blk_cap)
             {
                 c.blk_seg[cls][slot] = key;
-                if (cls == 2)
+                if (cls == 3)
                 {
                     unsigned long long mp = 64;
                     while (mp < slots) mp <<= 1;
@@ -411,17 +411,34 @@ __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// one block per sub-location of > 32 stays
+// one thread group (a warp or a block) per sub-location of > 32 stays
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-// out[i] = sum_{k<i} f(k) for i < n (exclusive), returns the total.  All threads of the block must call.  `out` may be
-// the storage f reads from (every thread reads an element before it overwrites it, chunks are private).
-template <class F, class T>
-__device__ int block_exclusive_scan(int n, F f, T* out, int* s_warp /* 32 ints of shared memory */)
+// G = 32: the group is a warp (several groups per block, no block barrier is ever used); G > 32: the whole block
+template <int G> __device__ __forceinline__ void gsync() { if (G == 32) __syncwarp(); else __syncthreads(); }
+template <int G> __device__ __forceinline__ int grank() { return G == 32 ? (int) (threadIdx.x & 31) : (int) threadIdx.x; }
+
+// sum of v over the group, returned to every thread.  s_w: 33 ints of shared memory per block (unused for G = 32)
+template <int G>
+__device__ __forceinline__ int group_sum(int v, int* s_w)
 {
-    const int tid = threadIdx.x, TH = blockDim.x;
-    const int chunk = (n + TH - 1) / TH;
+    v = __reduce_add_sync(FULL, v);
+    if (G == 32) return v;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = (threadIdx.x & 31) < (G >> 5) ? s_w[threadIdx.x & 31] : 0;
+    return __reduce_add_sync(FULL, t);
+}
+
+// out[i] = sum_{k<i} f(k) for i < n (exclusive), returns the total.  All threads of the group must call.  `out` may be
+// the storage f reads from (every thread reads an element before it overwrites it, chunks are private).
+template <int G, class F, class T>
+__device__ int group_exclusive_scan(int n, F f, T* out, int* s_w)
+{
+    const int tid = grank<G>();
+    const int chunk = (n + G - 1) / G;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
     int local = 0;
     for (int i = lo; i < hi; ++i) local += f(i);
@@ -432,15 +449,25 @@ __device__ int block_exclusive_scan(int n, F f, T* out, int* s_warp /* 32 ints o
         const int v = __shfl_up_sync(FULL, incl, o);
         if ((tid & 31) >= o) incl += v;
     }
-    __syncthreads();
-    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-    __syncthreads();
-    int warp_off = 0, total = 0;
-    for (int w = 0; w < (TH >> 5); ++w)
+    int warp_off = 0, total;
+    if (G == 32)
+        total = __shfl_sync(FULL, incl, 31);
+    else
     {
-        const int v = s_warp[w];
-        if (w < (tid >> 5)) warp_off += v;
-        total += v;
+        __syncthreads();
+        if ((tid & 31) == 31) s_w[tid >> 5] = incl;
+        __syncthreads();
+        // every warp scans the (at most 32) warp totals
+        const int wt = (tid & 31) < (G >> 5) ? s_w[tid & 31] : 0;
+        int wi = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int v = __shfl_up_sync(FULL, wi, o);
+            if ((tid & 31) >= o) wi += v;
+        }
+        total = __shfl_sync(FULL, wi, 31);
+        warp_off = __shfl_sync(FULL, wi - wt, tid >> 5);
     }
     int run = warp_off + incl - local;
     for (int i = lo; i < hi; ++i)
@@ -449,74 +476,52 @@ __device__ int block_exclusive_scan(int n, F f, T* out, int* s_warp /* 32 ints o
         out[i] = (T) run;
         run += v;
     }
-    __syncthreads();
+    gsync<G>();
     return total;
 }
 
-// out[i] = min_{k >= i} f(k) for i < n (f returns an int; "none" = a large value).  All threads must call.
-template <class F, class T>
-__device__ void block_suffix_min(int n, F f, T* out, int* s_warp)
-{
-    const int tid = threadIdx.x, TH = blockDim.x;
-    const int chunk = (n + TH - 1) / TH;
-    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
-    int local = 0x7fffffff;
-    for (int i = lo; i < hi; ++i) local = min(local, f(i));
-    // suffix-min over the per-thread values: thread t needs min over threads > t
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const int v = __shfl_down_sync(FULL, incl, o);
-        if ((tid & 31) + o < 32) incl = min(incl, v);
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) s_warp[tid >> 5] = incl;
-    __syncthreads();
-    int after = 0x7fffffff;  // min over the warps above mine
-    for (int w = (tid >> 5) + 1; w < (TH >> 5); ++w) after = min(after, s_warp[w]);
-    const int above_in_warp = __shfl_down_sync(FULL, incl, 1);
-    int run = after;
-    if ((tid & 31) < 31) run = min(run, above_in_warp);
-    for (int i = hi - 1; i >= lo; --i)
-    {
-        run = min(run, f(i));
-        out[i] = (T) run;
-    }
-    __syncthreads();
-}
+// per class: group size, groups per block, capacity in events and in kept probabilities
+template <int CLS> struct GroupCfg;
+template <> struct GroupCfg<0> { static constexpr int G = 32, PER_BLOCK = 4, S_CAP = 256, P_CAP = 256, NB_CAP = 512; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 8192, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
+template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536; using idx_t = uint32_t; };
 
-template <int CLS> struct BlockIdx { using type = uint16_t; };
-template <> struct BlockIdx<2> { using type = uint32_t; };
+// bytes of scratch of one group: 17 per event + 8 per kept probability + 12 per bucket (budgeted 16; + slack)
+template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
+{
+    return (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 8 + (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
+}
 
 }  // namespace
 
-// CLS 0: <= 1024 events, 256 threads, shared memory; CLS 1: <= 8192 events and <= 2048 evaluations, 1024 threads,
-// shared memory; CLS 2: anything larger, same algorithm in global scratch.
-//
 // The chain of calculated evaluations needs, from an evaluation at time e, the earliest later candidate event t with
-// !(t - e < threshold).  Events are grouped (not sorted) into time buckets by a counting sort; the successor of an
-// event is found by scanning the <= 3 buckets around e + threshold and otherwise jumping to the first candidate of the
-// next non-empty bucket; the chain start, next[start], next[next[start]] ... is then materialised in O(log n) rounds of
-// pointer doubling.
+// !(t - e < threshold).  Events are put in time order by a counting sort into time buckets (no wider than the threshold
+// where affordable) followed by a rank sort inside every bucket; the successor of an event is then a binary search over
+// the <= 3 buckets around e + threshold; the chain start, next[start], next[next[start]] ... is materialised in
+// O(log n) rounds of pointer doubling.  Classes 0-2 keep everything in shared memory, class 3 (anything larger) in global scratch.
 template <int MODEL, int CLS>
-__global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const WindowCtx c)
+__global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k_transmit_group(const WindowCtx c)
 {
-    using idx_t = typename BlockIdx<CLS>::type;
-    constexpr int P_CAP = CLS == 0 ? 1024 : BLOCK_P_CAP;
+    using Cfg = GroupCfg<CLS>;
+    using idx_t = typename Cfg::idx_t;
+    constexpr int G = Cfg::G;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_warp[32];
+    __shared__ int s_w[33];
     __shared__ double s_red[2 * 32];
-    __shared__ int s_flag[2];
-    const int tid = threadIdx.x, TH = blockDim.x;
+    const int tid = grank<G>();
+    const int group_in_block = G == 32 ? (int) (threadIdx.x >> 5) : 0;
     const uint32_t n_list = (uint32_t) min((unsigned long long) c.blk_cap, c.ctr->n_blk[CLS]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
+    const bool dbg = (c.flags & HEROS_FLAG_PHASE_CLOCKS) != 0;
     Local st;
+    long long clk = 0;
+#define PHASE_CLOCK(k) do { if (dbg && tid == 0) { const long long t_ = clock64(); atomicMax(&c.ctr->dbg_clk[CLS][k], (unsigned long long) (t_ - clk)); clk = t_; } } while (0)
 
-    for (uint32_t w = blockIdx.x; w < n_list; w += gridDim.x)
+    for (uint32_t w = blockIdx.x * Cfg::PER_BLOCK + group_in_block; w < n_list; w += gridDim.x * Cfg::PER_BLOCK)
     {
         const uint32_t key = c.blk_seg[CLS][w];
         if (key == KEY_NONE) continue;
@@ -525,46 +530,51 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
         const StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
 
+        if (dbg) clk = clock64();
         // 0. who is here and the two latest events; most segments only need lastCalculation advanced
         bool need_eval;
         {
             int ill = 0, sus = 0;
             Top2 top;
             top.init();
-            for (int v = tid; v < n; v += TH)
+            for (int v = tid; v < n; v += G)
             {
-                const uint32_t tph = view_tphase(rec[v].view);
+                const StayRec r = rec[v];
+                const uint32_t tph = view_tphase(r.view);
                 ill |= phase_is_ill(tph);
                 sus |= phase_is_susceptible(tph);
-                const double to = rec[v].tout;
-                if (to >= c.T0 && to < c.T1) top.add(to);
-                if (both)
-                {
-                    const double ti = rec[v].tin;
-                    if (ti >= c.T0 && ti < c.T1) top.add(ti);
-                }
+                if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
+                if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
             }
             for (int o = 16; o > 0; o >>= 1)
             {
                 const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
                 top.merge(o1, o2);
             }
-            ill = __any_sync(FULL, ill);
-            sus = __any_sync(FULL, sus);
-            __syncthreads();  // the previous segment is finished with the shared arrays
-            if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
-            __syncthreads();
-            if ((tid & 31) == 0)
+            int flags = (__any_sync(FULL, ill) ? 1 : 0) | (__any_sync(FULL, sus) ? 2 : 0);
+            if (G > 32)
             {
-                s_red[2 * (tid >> 5)] = top.m1;
-                s_red[2 * (tid >> 5) + 1] = top.m2;
-                if (ill) atomicOr(&s_flag[0], 1);
-                if (sus) atomicOr(&s_flag[1], 1);
+                __syncthreads();  // the previous segment is finished with the shared arrays
+                if ((tid & 31) == 0)
+                {
+                    s_red[2 * (tid >> 5)] = top.m1;
+                    s_red[2 * (tid >> 5) + 1] = top.m2;
+                    s_w[tid >> 5] = flags;
+                }
+                __syncthreads();
+                const bool in = (tid & 31) < (G >> 5);
+                top.m1 = in ? s_red[2 * (tid & 31)] : neg_inf();
+                top.m2 = in ? s_red[2 * (tid & 31) + 1] : neg_inf();
+                flags = in ? s_w[tid & 31] : 0;
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
+                    top.merge(o1, o2);
+                    flags |= __shfl_xor_sync(FULL, flags, o);
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            top.init();
-            for (int k = 0; k < (TH >> 5); ++k) top.merge(s_red[2 * k], s_red[2 * k + 1]);
-            need_eval = s_flag[0] && s_flag[1];
+            need_eval = flags == 3;
             if (!(top.m1 > neg_inf())) continue;  // no movement in this window
             if (!need_eval && !exact)
             {
@@ -576,37 +586,40 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                 }
             }
         }
-        __syncthreads();
+        gsync<G>();
+        PHASE_CLOCK(0);
         const LocParam lp = c.loc_param[c.key_loc[key]];
 
         const int slots = need_enters ? 2 * n : n;
+        // buckets: about four events per bucket, and where affordable no wider than the threshold, so that the
+        // successor search below looks at a handful of events even when they come in bursts
         int NB = 32;
-        while (NB * 4 < slots && NB < (CLS == 2 ? 65536 : 2048)) NB <<= 1;
+        {
+            const double want = thr > 0 ? (c.T1 - c.T0) / thr : 0.0;
+            while ((NB * 4 < slots || (double) NB < want) && NB < Cfg::NB_CAP) NB <<= 1;
+        }
         const double scale = (double) NB / (c.T1 - c.T0);
         auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
         // scratch: ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
-        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | bmin idx[NB] | nne idx[NB+1] |
-        //          ev_k u8[slots]
-        unsigned char* base = CLS == 2 ? c.scratch + c.huge_off[w] : smem;
+        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]
+        unsigned char* base = CLS == 3 ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
         double* ev_t = (double*) base;
         double* pr = ev_t + slots;
-        uint32_t* bstart = (uint32_t*) (pr + (CLS == 2 ? slots : P_CAP));
+        uint32_t* bstart = (uint32_t*) (pr + (CLS == 3 ? slots : Cfg::P_CAP));
         int32_t* bcur = (int32_t*) (bstart + NB + 1);
         int32_t* bsign = bcur + NB;
         idx_t* ja = (idx_t*) (bsign + NB);
         idx_t* jb = ja + (slots + 1);
         idx_t* node = jb + (slots + 1);
         idx_t* illl = node + slots;
-        idx_t* bmin = illl + n;
-        idx_t* nne = bmin + NB;
-        uint8_t* ev_k = (uint8_t*) (nne + NB + 1);
+        uint8_t* ev_k = (uint8_t*) (illl + n);
 
         // 1. histogram of the window's movement events over NB time buckets
-        for (int i = tid; i <= NB; i += TH) bstart[i] = 0;
-        for (int i = tid; i < NB; i += TH) bsign[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < slots; i += TH)
+        for (int i = tid; i <= NB; i += G) bstart[i] = 0;
+        for (int i = tid; i < NB; i += G) bsign[i] = 0;
+        gsync<G>();
+        for (int i = tid; i < slots; i += G)
         {
             const int v = need_enters ? (i >> 1) : i;
             const int kind = need_enters ? (i & 1) : 0;
@@ -618,14 +631,16 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                 if (MODEL == HEROS_MODEL_DISTANCE) atomicAdd(&bsign[bk], kind ? 1 : -1);
             }
         }
-        __syncthreads();
+        gsync<G>();
+        PHASE_CLOCK(1);
         // 2. bucket offsets
-        const int m_ev = block_exclusive_scan(NB, [&](int i) { return (int) bstart[i]; }, bstart, s_warp);
+        const int m_ev = group_exclusive_scan<G>(NB, [&](int i) { return (int) bstart[i]; }, bstart, s_w);
         if (tid == 0) bstart[NB] = (uint32_t) m_ev;
-        for (int i = tid; i < NB; i += TH) bcur[i] = (int32_t) bstart[i];
-        __syncthreads();
+        for (int i = tid; i < NB; i += G) bcur[i] = (int32_t) bstart[i];
+        gsync<G>();
+        PHASE_CLOCK(2);
         // 3. scatter the events into their buckets (order inside a bucket is irrelevant to every result)
-        for (int i = tid; i < slots; i += TH)
+        for (int i = tid; i < slots; i += G)
         {
             const int v = need_enters ? (i >> 1) : i;
             const int kind = need_enters ? (i & 1) : 0;
@@ -637,60 +652,85 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                 ev_k[pos] = (uint8_t) kind;
             }
         }
-        __syncthreads();
+        gsync<G>();
+        PHASE_CLOCK(3);
         const idx_t END = (idx_t) m_ev;
         auto is_cand = [&](int j) { return both || ev_k[j] == 0; };
-        // 4. earliest candidate of every bucket, next bucket that has one, occupancy at the start of every bucket
-        for (int bk = tid; bk < NB; bk += TH)
+        // 4. sort inside every bucket: each event counts the events of its bucket that precede it and moves to that
+        //    rank.  Buckets hold a handful of events, so this is a few compares per event, all events in parallel.
+        if (CLS == 3)
         {
-            double best_t = pos_inf();
-            int best = m_ev;
-            for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
-                if (is_cand(j) && (ev_t[j] < best_t || (ev_t[j] == best_t && j < best))) { best_t = ev_t[j]; best = j; }
-            bmin[bk] = (idx_t) best;
+            double* tmp_t = pr;                  // f64[slots]
+            uint8_t* tmp_k = (uint8_t*) node;    // idx[slots] >= slots bytes
+            for (int i = tid; i < m_ev; i += G) { tmp_t[i] = ev_t[i]; tmp_k[i] = ev_k[i]; }
+            gsync<G>();
+            for (int i = tid; i < m_ev; i += G)
+            {
+                const double t = tmp_t[i];
+                const int bk = bucket_of(t);
+                const int lo = (int) bstart[bk], hi = (int) bstart[bk + 1];
+                int rank = 0;
+                for (int q = lo; q < hi; ++q) rank += (tmp_t[q] < t || (tmp_t[q] == t && q < i)) ? 1 : 0;
+                ev_t[lo + rank] = t;
+                ev_k[lo + rank] = tmp_k[i];
+            }
         }
-        __syncthreads();
-        block_suffix_min(NB, [&](int i) { return bmin[i] != END ? i : NB; }, nne, s_warp);
-        if (tid == 0) nne[NB] = (idx_t) NB;
+        else
+        {
+            constexpr int MAXE = Cfg::S_CAP / G;  // events per thread
+            double e_t[MAXE > 0 ? MAXE : 1];
+            int e_dst[MAXE > 0 ? MAXE : 1];
+            uint8_t e_k[MAXE > 0 ? MAXE : 1];
+#pragma unroll
+            for (int k = 0; k < MAXE; ++k)
+            {
+                const int i = tid + k * G;
+                e_dst[k] = -1;
+                if (i < m_ev)
+                {
+                    const double t = ev_t[i];
+                    const int bk = bucket_of(t);
+                    const int lo = (int) bstart[bk], hi = (int) bstart[bk + 1];
+                    int rank = 0;
+                    for (int q = lo; q < hi; ++q) rank += (ev_t[q] < t || (ev_t[q] == t && q < i)) ? 1 : 0;
+                    e_t[k] = t;
+                    e_k[k] = ev_k[i];
+                    e_dst[k] = lo + rank;
+                }
+            }
+            gsync<G>();
+#pragma unroll
+            for (int k = 0; k < MAXE; ++k)
+                if (e_dst[k] >= 0) { ev_t[e_dst[k]] = e_t[k]; ev_k[e_dst[k]] = e_k[k]; }
+        }
+        gsync<G>();
         int carried = 0;
         if (MODEL == HEROS_MODEL_DISTANCE)
         {
-            block_exclusive_scan(NB, [&](int i) { return bsign[i]; }, bcur, s_warp);  // bcur: occupancy change before bucket
-            for (int v = tid; v < n; v += TH) carried += (rec[v].tin < c.T0);
-            carried = (int) warp_sum((double) carried);
-            if (tid == 0) s_flag[1] = 0;
-            __syncthreads();
-            if ((tid & 31) == 0) atomicAdd(&s_flag[1], carried);
-            __syncthreads();
-            carried = s_flag[1];
+            group_exclusive_scan<G>(NB, [&](int i) { return bsign[i]; }, bcur, s_w);  // occupancy change before bucket
+            for (int v = tid; v < n; v += G) carried += (rec[v].tin < c.T0);
+            carried = group_sum<G>(carried, s_w);
         }
-        __syncthreads();
+        gsync<G>();
+        PHASE_CLOCK(4);
         // successor of an evaluation at time e: the earliest candidate t > e with !(t - e < thr)
         auto successor = [&](double e) -> int {
             int b0 = bucket_raw(e + thr) - 1;
-            b0 = max(b0, 0);
-            double best_t = pos_inf();
-            int best = m_ev;
-            const int b_hi = min(b0 + 3, NB);
-            for (int bk = b0; bk < b_hi; ++bk)
+            b0 = min(max(b0, 0), NB);
+            // the events are in time order; the first one that qualifies lies in buckets b0 .. b0 + 2 or, if none of those
+            // does, is the first event after them (everything later is more than a threshold away)
+            int lo = (int) bstart[b0], hi = (int) bstart[min(b0 + 3, NB)];
+            while (lo < hi)
             {
-                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
-                {
-                    const double t = ev_t[j];
-                    if (is_cand(j) && t > e && !(t - e < thr) && (t < best_t || (t == best_t && j < best)))
-                    {
-                        best_t = t;
-                        best = j;
-                    }
-                }
-                if (best != m_ev) return best;  // buckets are ordered in time
+                const int mid = (lo + hi) >> 1;
+                const double t = ev_t[mid];
+                if (t > e && !(t - e < thr)) hi = mid; else lo = mid + 1;
             }
-            if (b_hi >= NB) return m_ev;
-            const int bq = (int) nne[b_hi];
-            return bq < NB ? (int) bmin[bq] : m_ev;
+            while (lo < m_ev && !is_cand(lo)) ++lo;  // enter events are not candidates in EXIT_ONLY mode
+            return lo;
         };
         // 5. next pointers, chain start, pointer doubling
-        for (int i = tid; i <= m_ev; i += TH) ja[i] = (i < m_ev && is_cand(i)) ? (idx_t) successor(ev_t[i]) : END;
+        for (int i = tid; i <= m_ev; i += G) ja[i] = (i < m_ev && is_cand(i)) ? (idx_t) successor(ev_t[i]) : END;
         const int start = successor(L0);
         int r_cap = m_ev;
         if (thr > 0)
@@ -698,20 +738,22 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             const double bound = (c.T1 - c.T0) / thr + 2.0;
             if (bound < (double) r_cap) r_cap = (int) bound;
         }
-        for (int r = tid; r < r_cap; r += TH) node[r] = (idx_t) start;
-        __syncthreads();
+        for (int r = tid; r < r_cap; r += G) node[r] = (idx_t) start;
+        gsync<G>();
+        PHASE_CLOCK(5);
         {
             idx_t* pa = ja;
             idx_t* pb = jb;
             for (int k = 0; (1 << k) < r_cap; ++k)
             {
-                for (int r = tid; r < r_cap; r += TH)
+                for (int r = tid; r < r_cap; r += G)
                     if ((r >> k) & 1) node[r] = pa[node[r]];
-                for (int i = tid; i <= m_ev; i += TH) pb[i] = pa[pa[i]];
-                __syncthreads();
+                for (int i = tid; i <= m_ev; i += G) pb[i] = pa[pa[i]];
+                gsync<G>();
                 idx_t* t = pa; pa = pb; pb = t;
             }
         }
+        PHASE_CLOCK(6);
         int R;  // chain length: node[r] != END for r < R
         {
             int lo = 0, hi = r_cap;
@@ -723,17 +765,17 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             st.evaluations += (unsigned long long) R;
             if (R > 0) c.last_calc[key] = ev_t[node[R - 1]];
         }
-        if (!need_eval || R == 0) continue;
-        // 6. list of the stays whose person can be ill (ja as scan output; the doubling tables are dead)
-        __syncthreads();
-        const int n_ill = block_exclusive_scan(n, [&](int v) { return phase_is_ill(view_tphase(rec[v].view)) ? 1 : 0; }, ja,
-                                               s_warp);
-        for (int v = tid; v < n; v += TH)
+        if (!need_eval || R == 0) { gsync<G>(); continue; }
+        // 6. list of the stays whose person can be ill (ja as scan output; the doubling tables are dead) ...
+        gsync<G>();
+        const int n_ill = group_exclusive_scan<G>(n, [&](int v) { return phase_is_ill(view_tphase(rec[v].view)) ? 1 : 0; },
+                                                  ja, s_w);
+        for (int v = tid; v < n; v += G)
             if (phase_is_ill(view_tphase(rec[v].view))) jb[ja[v]] = (idx_t) v;
-        __syncthreads();
+        gsync<G>();
         // ... in canonical (person, t_in) order, by rank counting, so that the exposure sums do not depend on the order
         // in which the stays were scattered into the bucket
-        for (int k = tid; k < n_ill; k += TH)
+        for (int k = tid; k < n_ill; k += G)
         {
             const int v = (int) jb[k];
             const uint32_t pv = rec[v].person;
@@ -748,9 +790,10 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             }
             illl[rank] = (idx_t) v;
         }
-        __syncthreads();
+        gsync<G>();
+        PHASE_CLOCK(7);
         // 7. one thread per evaluation: duration, exposure sum, probability
-        for (int r = tid; r < R; r += TH)
+        for (int r = tid; r < R; r += G)
         {
             const int q = (int) node[r];
             const double now = ev_t[q];
@@ -762,9 +805,9 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                 if (factor != 0.0)
                     for (int k = 0; k < n_ill; ++k)
                     {
-                        const int v = (int) illl[k];
-                        if (rec[v].tin < now && now <= rec[v].tout && ill_at(c, rec[v].view, rec[v].person, now))
-                            sum += area_contribution(c.area, now - (double) view_exposure(rec[v].view));
+                        const StayRec s = rec[illl[k]];
+                        if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
+                            sum += area_contribution(c.area, now - (double) view_exposure(s.view));
                     }
             }
             else
@@ -772,18 +815,18 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
                 // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
                 const int bk = bucket_of(now);
                 int head_count = carried + bcur[bk];
-                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
-                    if (ev_t[j] < now) head_count += ev_k[j] ? 1 : -1;
+                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
+                    head_count += ev_k[j] ? 1 : -1;
                 double psi, mu;
                 policy_at(c, now, psi, mu);
                 factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
                 if (factor != 0.0)
                     for (int k = 0; k < n_ill; ++k)
                     {
-                        const int v = (int) illl[k];
-                        if (rec[v].tin < now && now <= rec[v].tout && ill_at(c, rec[v].view, rec[v].person, now))
+                        const StayRec s = rec[illl[k]];
+                        if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
                         {
-                            const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(rec[v].view));
+                            const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(s.view));
                             if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
                         }
                     }
@@ -791,56 +834,80 @@ __global__ void __launch_bounds__(CLS == 0 ? 256 : 1024) k_transmit_block(const 
             if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
             pr[r] = p;
         }
-        __syncthreads();
-        // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out]
-        for (int v = tid; v < n; v += TH)
+        gsync<G>();
+        PHASE_CLOCK(8);
+        // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out].  Each lane
+        //    finds the evaluation range of one stay; the warp then shares out the (stay, evaluation) pairs
+        for (int v0 = (tid & ~31); v0 < n; v0 += G)
         {
-            if (!phase_is_susceptible(view_tphase(rec[v].view))) continue;
-            const double t_in = rec[v].tin, t_out = rec[v].tout;
-            int lo = 0, hi = R;  // first evaluation with time > t_in
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev_t[node[mid]] > t_in) hi = mid; else lo = mid + 1; }
-            for (int r = lo; r < R; ++r)
+            const int v = v0 + (tid & 31);
+            int lo = 0, hi = 0;
+            uint32_t person = 0;
+            if (v < n)
             {
-                const double now = ev_t[node[r]];
-                if (!(now <= t_out)) break;
-                if (pr[r] > 0) draw_and_push(c, st, rec[v].person, key, now, pr[r]);
+                const StayRec s = rec[v];
+                if (phase_is_susceptible(view_tphase(s.view)))
+                {
+                    person = s.person;
+                    int l = 0, h = R;  // first evaluation with time > t_in
+                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
+                    lo = l;
+                    l = lo; h = R;     // first evaluation with time > t_out
+                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
+                    hi = l;
+                }
+            }
+            unsigned pending = __ballot_sync(FULL, hi > lo);
+            while (pending)
+            {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int s_lo = __shfl_sync(FULL, lo, src), s_hi = __shfl_sync(FULL, hi, src);
+                const uint32_t s_person = __shfl_sync(FULL, person, src);
+                for (int r = s_lo + (tid & 31); r < s_hi; r += 32)
+                    if (pr[r] > 0) draw_and_push(c, st, s_person, key, ev_t[node[r]], pr[r]);
             }
         }
+        gsync<G>();
+        PHASE_CLOCK(9);
     }
-    flush_stats(c, st, tid & 31);
+#undef PHASE_CLOCK
+    flush_stats(c, st, threadIdx.x & 31);
 }
 
 // host-side launcher ----------------------------------------------------------------------------------------------------
-// k_transmit_thread fills the work lists; the warp kernel and the three block kernels then run side by side on the
-// auxiliary streams (they touch disjoint sub-locations), and the main stream joins them.
+// k_transmit_thread fills the work lists; the warp kernel and the group kernels then run side by side on the auxiliary
+// streams (they touch disjoint sub-locations), and the main stream joins them.
 template <int MODEL>
 static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
 {
-    // 17 bytes per event + 8 per kept probability + 16 per bucket (see the scratch layout in k_transmit_block)
-    const size_t smem0 = 1024 * 17 + 1024 * 8 + 256 * 16 + 256, smem1 = 8192 * 17 + BLOCK_P_CAP * 8 + 2048 * 16 + 256;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
+    const size_t smem0 = group_smem_bytes<0>() * GroupCfg<0>::PER_BLOCK, smem1 = group_smem_bytes<1>(),
+                 smem2 = group_smem_bytes<2>();
     if (dev >= 0 && dev < 64 && !configured[dev])
     {
-        cudaFuncSetAttribute(k_transmit_block<MODEL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem0);
-        cudaFuncSetAttribute(k_transmit_block<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
+        cudaFuncSetAttribute(k_transmit_group<MODEL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem0);
+        cudaFuncSetAttribute(k_transmit_group<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
+        cudaFuncSetAttribute(k_transmit_group<MODEL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
         configured[dev] = true;
     }
     cudaStream_t s = ts.main;
     k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
     cudaEventRecord(ts.fork, s);
-    for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
-    k_transmit_block<MODEL, 1><<<n_sm, 1024, smem1, ts.aux[0]>>>(c);
-    k_transmit_block<MODEL, 2><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
-    k_transmit_block<MODEL, 0><<<n_sm * 6, 256, smem0, ts.aux[1]>>>(c);
-    k_transmit_warp<MODEL><<<n_sm * 8, 256, 0, ts.aux[2]>>>(c);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
+    k_transmit_group<MODEL, 2><<<n_sm, 1024, smem2, ts.aux[0]>>>(c);
+    k_transmit_group<MODEL, 3><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
+    k_transmit_group<MODEL, 1><<<n_sm * 6, 256, smem1, ts.aux[1]>>>(c);
+    k_transmit_group<MODEL, 0><<<n_sm * 8, 128, smem0, ts.aux[2]>>>(c);
+    k_transmit_warp<MODEL><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
+    for (int k = 0; k < 4; ++k)
     {
         cudaEventRecord(ts.join[k], ts.aux[k]);
         cudaStreamWaitEvent(s, ts.join[k], 0);
     }
-    launches += 5;
+    launches += 6;
 }
 
 void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)

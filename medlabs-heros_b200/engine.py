@@ -198,6 +198,11 @@ class HerosEngine:
         self._check(self._lib.heros_get_last_calculation(self._h, int(loc), int(sub), C.byref(out)))
         return out.value
 
+    def phase_clocks(self) -> np.ndarray:
+        out = np.zeros((4, 16), np.uint64)
+        self._check(self._lib.heros_get_phase_clocks(self._h, _p(out)))
+        return out
+
     @property
     def time(self) -> float:
         out = C.c_double(0.0)
