@@ -304,22 +304,29 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the engine stream) ----
-    stage = {k: float(np.sum([s[k] for s in stats])) for k in
-             ("progress_ms", "bucket_ms", "transmit_small_ms", "transmit_big_ms", "resolve_ms", "retire_ms", "gpu_ms")}
+    keys = ("progress_ms", "bucket_ms", "bucket_count_ms", "bucket_scan_ms", "bucket_scatter_ms", "transmit_small_ms",
+            "transmit_big_ms", "resolve_ms", "retire_ms", "gpu_ms")
+    stage = {k: float(np.sum([s[k] for s in stats])) for k in keys}
     visits = float(np.sum([s["visits"] for s in stats]))
+    big_stays = float(np.sum([s["big_stays"] for s in stats]))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         with open(peaks_path) as f:
             peak, peak_source = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_source = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    dominant = max(("transmit_small_ms", "transmit_big_ms", "bucket_ms"), key=lambda k: stage[k])
-    bytes_per_visit = 16.0 if dominant == "bucket_ms" else 32.0
-    achieved = bytes_per_visit * visits / (stage[dominant] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"transmit_small_ms": "k_transmit_small", "transmit_big_ms": "k_transmit_big",
-                                             "bucket_ms": "bucket (radix sort + gather)"}[dominant],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_visit": bytes_per_visit, "peak_source": peak_source,
+    # single kernels with their algorithmic bytes: k_transmit_thread streams every stay record once
+    # (32 B / stay); k_bucket_scatter is the bucketing pass proper (16 B / stay: key + index in, out); the group kernels
+    # handle the stays of the large sub-locations (32 B / stay)
+    kernels = {"k_transmit_thread": (stage["transmit_small_ms"], 32.0 * visits),
+               "k_bucket_scatter": (stage["bucket_scatter_ms"], 16.0 * visits),
+               "k_bucket_count": (stage["bucket_count_ms"], 16.0 * visits),
+               "k_transmit_group+k_transmit_warp (concurrent)": (stage["transmit_big_ms"], 32.0 * big_stays)}
+    dominant = max(kernels, key=lambda k: kernels[k][0])
+    achieved = kernels[dominant][1] / (kernels[dominant][0] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_source,
+                "per_kernel_gbs": {k: (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None) for k, v in kernels.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
 
     # ---- cpu_baseline: the oracle on a bounded sample (first cpu_days days), checked against the GPU run ----

@@ -111,11 +111,13 @@ typedef struct heros_step_stats {
     /* device time per stage, summed over the windows of the call (CUDA events on the engine stream) */
     double progress_ms;       /* disease-phase state machine */
     double bucket_ms;         /* window list + radix sort by sub-location + gather + segment offsets */
-    double transmit_small_ms; /* all transmission kernels (thread / warp / block per sub-location, run side by side) */
-    double transmit_big_ms;   /* reserved (0) */
+    double transmit_small_ms; /* k_transmit_thread: streams every stay of the window once */
+    double transmit_big_ms;   /* the warp / group kernels of the larger sub-locations, run side by side */
     double resolve_ms;        /* earliest-draw-wins + expose */
     double retire_ms;         /* pool compaction */
-    int64_t big_sublocations; /* segments handled by the block kernel */
+    int64_t big_sublocations; /* sub-locations handled by the group kernels */
+    int64_t big_stays;        /* ... and their stays */
+    double bucket_count_ms, bucket_scan_ms, bucket_scatter_ms; /* the three parts of bucket_ms */
 } heros_step_stats;
 
 /* ---- lifecycle ---- */

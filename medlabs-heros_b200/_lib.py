@@ -50,7 +50,9 @@ class StepStats(C.Structure):
                 ("transitions", C.c_int64), ("gpu_launches", C.c_int64), ("gpu_ms", C.c_double),
                 ("transmit_ms", C.c_double), ("near_ties", C.c_int64), ("progress_ms", C.c_double),
                 ("bucket_ms", C.c_double), ("transmit_small_ms", C.c_double), ("transmit_big_ms", C.c_double),
-                ("resolve_ms", C.c_double), ("retire_ms", C.c_double), ("big_sublocations", C.c_int64)]
+                ("resolve_ms", C.c_double), ("retire_ms", C.c_double), ("big_sublocations", C.c_int64),
+                ("big_stays", C.c_int64), ("bucket_count_ms", C.c_double), ("bucket_scan_ms", C.c_double),
+                ("bucket_scatter_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

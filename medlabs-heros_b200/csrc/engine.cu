@@ -544,7 +544,9 @@ struct heros_engine
     cudaStream_t stream = nullptr;
     TransmitStreams ts{};
     cudaEvent_t ev[10]{};
-    double stage_ms[6]{};  // progress, bucket, transmit small, transmit big, resolve, retire (current heros_step)
+    cudaEvent_t ev_bk[2]{};  // after k_bucket_count, after the prefix sum
+    double stage_ms[6]{};  // progress, bucket, transmit thread kernel, other transmit kernels, resolve, retire
+    double bucket_part_ms[3]{};  // ticket count, prefix sum, scatter
     int n_sm = 148;
     double t_now = 0.0;
 
@@ -719,9 +721,11 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     CU(h, cudaMemsetAsync(h->bk_count.p, 0, (size_t) n_keys * 4, s));
     k_bucket_count<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, T1,
                                                        h->bk_count.p, h->bk_rank.p);
+    CU(h, cudaEventRecord(h->ev_bk[0], s));
     k_scan_tile_sums<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p);
     k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_sum.p, n_tiles, h->seg_start.p + n_keys, h->d_ctr.p);
     k_scan_apply<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p, h->seg_start.p);
+    CU(h, cudaEventRecord(h->ev_bk[1], s));
     k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, h->bk_rank.p,
                                                          h->seg_start.p, h->d_view.p, h->rec.p);
     launches += 6;
@@ -757,7 +761,6 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.ctr = h->d_ctr.p;
     CU(h, cudaEventRecord(h->ev[4], s));
     launch_transmit(c, h->n_sm, h->ts, launches);
-    CU(h, cudaEventRecord(h->ev[5], s));  // the kernels overlap: one interval for all of them
     CU(h, cudaEventRecord(h->ev[6], s));
 
     // 6. resolve: earliest successful draw per person wins
@@ -788,11 +791,23 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
         h->n_pool = (uint32_t) h->h_ctr->n_keep;
         h->pool_cur = oth;
     }
-    for (int k = 0; k < 6; ++k)
     {
-        float ms = 0.f;
-        CU(h, cudaEventElapsedTime(&ms, h->ev[2 + k], h->ev[3 + k]));
-        h->stage_ms[k] += ms;
+        // ev[2] start, [3] after progress, [4] after bucketing, ts.fork after k_transmit_thread, [6] after the joined
+        // warp / group kernels, [7] after resolve, [8] after retire
+        cudaEvent_t marks[7] = {h->ev[2], h->ev[3], h->ev[4], h->ts.fork, h->ev[6], h->ev[7], h->ev[8]};
+        for (int k = 0; k < 6; ++k)
+        {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
+            h->stage_ms[k] += ms;
+        }
+        cudaEvent_t bk[4] = {h->ev[3], h->ev_bk[0], h->ev_bk[1], h->ev[4]};
+        for (int k = 0; k < 3; ++k)
+        {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, bk[k], bk[k + 1]));
+            h->bucket_part_ms[k] += ms;
+        }
     }
     if (h->h_ctr->overflow)
     {
@@ -847,10 +862,12 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
+    for (auto& ev : h->ev_bk)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
     h->ts.main = h->stream;
     for (auto& a : h->ts.aux)
         if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-    if ((e = cudaEventCreateWithFlags(&h->ts.fork, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreate(&h->ts.fork)) != cudaSuccess) return bail("event", e);
     for (auto& j : h->ts.join)
         if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -887,6 +904,7 @@ int32_t heros_destroy(heros_handle h)
     h->st_tout.release();
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_bk) if (ev) cudaEventDestroy(ev);
     for (auto& a : h->ts.aux) if (a) cudaStreamDestroy(a);
     if (h->ts.fork) cudaEventDestroy(h->ts.fork);
     for (auto& j : h->ts.join) if (j) cudaEventDestroy(j);
@@ -1170,6 +1188,7 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
     int launches = 0;
     int64_t n_big = 0;
     for (double& m : h->stage_ms) m = 0.0;
+    for (double& m : h->bucket_part_ms) m = 0.0;
     CU(h, cudaEventRecord(h->ev[0], h->stream));
     while (h->t_now < t_until)
     {
@@ -1199,6 +1218,9 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
     st.transmit_small_ms = h->stage_ms[2]; st.transmit_big_ms = h->stage_ms[3];
     st.resolve_ms = h->stage_ms[4]; st.retire_ms = h->stage_ms[5];
     st.transmit_ms = h->stage_ms[2] + h->stage_ms[3];
+    st.bucket_count_ms = h->bucket_part_ms[0]; st.bucket_scan_ms = h->bucket_part_ms[1];
+    st.bucket_scatter_ms = h->bucket_part_ms[2];
+    st.big_stays = (int64_t) (now.big_stays - before.big_stays);
     st.big_sublocations = n_big;
     if (stats) *stats = st;
     return HEROS_OK;

@@ -38,6 +38,7 @@ struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  //
 struct Counters
 {
     unsigned long long evaluations, draws, near_ties, infections, transitions;
+    unsigned long long big_stays;    // stays of the sub-locations handed to the group kernels
     unsigned long long n_cand;       // candidate infections of the current window
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
     Local st;
-    unsigned occupied = 0;
+    unsigned occupied = 0, big = 0;
 
     for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
     {
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         ++occupied;
         if (n > 32)
         {
-            // block kernels: by the number of events of the sub-location and the bound on its evaluations
+            // group kernels: by the number of events of the sub-location and the bound on its evaluations
+            big += n;
             const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
             const uint32_t slots = need_enters ? 2 * n : n;
             double r_bound = both ? 2.0 * n : (double) n;
@@ -308,7 +309,9 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
     }
     flush_stats(c, st, threadIdx.x & 31);
     occupied = __reduce_add_sync(FULL, occupied);
+    big = __reduce_add_sync(FULL, big);
     if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
+    if ((threadIdx.x & 31) == 0 && big) atomicAdd(&c.ctr->big_stays, (unsigned long long) big);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -480,17 +483,63 @@ __device__ int group_exclusive_scan(int n, F f, T* out, int* s_w)
     return total;
 }
 
+// out[i] = min_{k >= i} f(k) for i < n (f returns an int <= INT_MAX).  All threads of the group must call.
+template <int G, class F, class T>
+__device__ void group_suffix_min(int n, F f, T* out, int* s_w)
+{
+    const int tid = grank<G>();
+    const int chunk = (n + G - 1) / G;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int local = 0x7fffffff;
+    for (int i = lo; i < hi; ++i) local = min(local, f(i));
+    int incl = local;  // min over the lanes >= mine of my warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int v = __shfl_down_sync(FULL, incl, o);
+        if ((tid & 31) + o < 32) incl = min(incl, v);
+    }
+    int after = 0x7fffffff;  // min over the warps above mine
+    if (G > 32)
+    {
+        __syncthreads();
+        if ((tid & 31) == 0) s_w[tid >> 5] = incl;
+        __syncthreads();
+        const int wv = (tid & 31) < (G >> 5) ? s_w[tid & 31] : 0x7fffffff;
+        int ws = wv;  // suffix-min over the warp values
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int v = __shfl_down_sync(FULL, ws, o);
+            if ((tid & 31) + o < 32) ws = min(ws, v);
+        }
+        const int nxt = __shfl_sync(FULL, ws, min((tid >> 5) + 1, 31));
+        after = (tid >> 5) + 1 < (G >> 5) ? nxt : 0x7fffffff;
+    }
+    const int above_in_warp = __shfl_down_sync(FULL, incl, 1);
+    int run = after;
+    if ((tid & 31) < 31) run = min(run, above_in_warp);
+    for (int i = hi - 1; i >= lo; --i)
+    {
+        run = min(run, f(i));
+        out[i] = (T) run;
+    }
+    gsync<G>();
+}
+
 // per class: group size, groups per block, capacity in events and in kept probabilities
 template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 32, PER_BLOCK = 4, S_CAP = 256, P_CAP = 256, NB_CAP = 512; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 8192, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
-template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536; using idx_t = uint32_t; };
+template <> struct GroupCfg<0> { static constexpr int G = 32, PER_BLOCK = 4, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 8192, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 1024; using idx_t = uint16_t; };
+template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
 
-// bytes of scratch of one group: 17 per event + 8 per kept probability + 12 per bucket (budgeted 16; + slack)
+// bytes of scratch of one group: 32 per staged ill stay + 17 per event + 8 per kept probability + 12 per bucket
+// (budgeted 16; + slack)
 template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
 {
-    return (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 8 + (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
+    return (size_t) GroupCfg<CLS>::ILL_CAP * 32 + (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 8 +
+           (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
 }
 
 }  // namespace
@@ -601,10 +650,11 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
         const double scale = (double) NB / (c.T1 - c.T0);
         auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
-        // scratch: ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
+        // scratch: ill_rec StayRec[ILL_CAP] | ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
         //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]
         unsigned char* base = CLS == 3 ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
-        double* ev_t = (double*) base;
+        StayRec* ill_rec = (StayRec*) base;  // the ill stays, staged next to the SM (classes 0-2)
+        double* ev_t = (double*) (base + (size_t) Cfg::ILL_CAP * sizeof(StayRec));
         double* pr = ev_t + slots;
         uint32_t* bstart = (uint32_t*) (pr + (CLS == 3 ? slots : Cfg::P_CAP));
         int32_t* bcur = (int32_t*) (bstart + NB + 1);
@@ -713,6 +763,9 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
         }
         gsync<G>();
         PHASE_CLOCK(4);
+        // next candidate at or after every event (kept in jb until the pointer doubling needs that table)
+        idx_t* nextc = jb;
+        group_suffix_min<G>(m_ev, [&](int i) { return is_cand(i) ? i : m_ev; }, nextc, s_w);
         // successor of an evaluation at time e: the earliest candidate t > e with !(t - e < thr)
         auto successor = [&](double e) -> int {
             int b0 = bucket_raw(e + thr) - 1;
@@ -726,8 +779,7 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                 const double t = ev_t[mid];
                 if (t > e && !(t - e < thr)) hi = mid; else lo = mid + 1;
             }
-            while (lo < m_ev && !is_cand(lo)) ++lo;  // enter events are not candidates in EXIT_ONLY mode
-            return lo;
+            return lo < m_ev ? (int) nextc[lo] : m_ev;  // enter events are not candidates in EXIT_ONLY mode
         };
         // 5. next pointers, chain start, pointer doubling
         for (int i = tid; i <= m_ev; i += G) ja[i] = (i < m_ev && is_cand(i)) ? (idx_t) successor(ev_t[i]) : END;
@@ -774,74 +826,119 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
             if (phase_is_ill(view_tphase(rec[v].view))) jb[ja[v]] = (idx_t) v;
         gsync<G>();
         // ... in canonical (person, t_in) order, by rank counting, so that the exposure sums do not depend on the order
-        // in which the stays were scattered into the bucket
+        // in which the stays were scattered into the bucket.  When they fit, the ill stays are staged in shared memory:
+        // every evaluation below scans all of them.
+        const bool staged = n_ill <= Cfg::ILL_CAP;
+        if (staged)
+        {
+            for (int k = tid; k < n_ill; k += G) ill_rec[k] = rec[jb[k]];
+            gsync<G>();
+        }
+        const StayRec* ill_src = staged ? ill_rec : rec;
         for (int k = tid; k < n_ill; k += G)
         {
-            const int v = (int) jb[k];
-            const uint32_t pv = rec[v].person;
-            const double tv = rec[v].tin;
+            const int v = staged ? k : (int) jb[k];
+            const uint32_t pv = ill_src[v].person;
+            const double tv = ill_src[v].tin;
             int rank = 0;
             for (int k2 = 0; k2 < n_ill; ++k2)
             {
-                const int v2 = (int) jb[k2];
-                const uint32_t p2 = rec[v2].person;
-                const double t2 = rec[v2].tin;
+                const int v2 = staged ? k2 : (int) jb[k2];
+                const uint32_t p2 = ill_src[v2].person;
+                const double t2 = ill_src[v2].tin;
                 rank += (stay_before(p2, t2, pv, tv) || (p2 == pv && t2 == tv && k2 < k)) ? 1 : 0;
             }
             illl[rank] = (idx_t) v;
         }
         gsync<G>();
         PHASE_CLOCK(7);
-        // 7. one thread per evaluation: duration, exposure sum, probability
-        for (int r = tid; r < R; r += G)
+        // 7. duration, exposure sum and probability of every evaluation: the fixed part (sqrt, exp, divisions) is a long
+        //    dependent fp64 chain, so evaluations run in as many threads as possible; when the group has more threads
+        //    than evaluations, LPN = 2^k lanes share one evaluation and split the ill stays between them (lane partial
+        //    sums in canonical order, combined by a fixed butterfly).
         {
-            const int q = (int) node[r];
-            const double now = ev_t[q];
-            const double duration = now - (r ? ev_t[node[r - 1]] : L0);
-            double p = 0.0, factor, sum = 0.0;
-            if (MODEL == HEROS_MODEL_AREA)
+            int lpn = 1;
+            while (lpn < 32 && 2 * lpn * R <= G) lpn <<= 1;
+            const int sub = tid & (lpn - 1), per_pass = G / lpn;
+            for (int r0 = 0; r0 < R; r0 += per_pass)
             {
-                factor = area_factor(c.area, duration, lp.denom);
-                if (factor != 0.0)
-                    for (int k = 0; k < n_ill; ++k)
+                const int r = r0 + tid / lpn;
+                const bool active = r < R;
+                double p = 0.0, factor = 0.0, sum = 0.0, now = 0.0, duration = 0.0;
+                if (active)
+                {
+                    now = ev_t[node[r]];
+                    duration = now - (r ? ev_t[node[r - 1]] : L0);
+                    if (MODEL == HEROS_MODEL_AREA)
+                        factor = area_factor(c.area, duration, lp.denom);
+                    else
                     {
-                        const StayRec s = rec[illl[k]];
-                        if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
-                            sum += area_contribution(c.area, now - (double) view_exposure(s.view));
+                        // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
+                        const int bk = bucket_of(now);
+                        int head_count = carried + bcur[bk];
+                        for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
+                            head_count += ev_k[j] ? 1 : -1;
+                        double psi, mu;
+                        policy_at(c, now, psi, mu);
+                        factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
                     }
-            }
-            else
-            {
-                // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
-                const int bk = bucket_of(now);
-                int head_count = carried + bcur[bk];
-                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
-                    head_count += ev_k[j] ? 1 : -1;
-                double psi, mu;
-                policy_at(c, now, psi, mu);
-                factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
-                if (factor != 0.0)
-                    for (int k = 0; k < n_ill; ++k)
-                    {
-                        const StayRec s = rec[illl[k]];
-                        if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
+                    if (factor != 0.0)
+                        for (int k = sub; k < n_ill; k += lpn)
                         {
-                            const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(s.view));
-                            if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
+                            const StayRec& s = ill_src[illl[k]];
+                            if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
+                            {
+                                const double te = now - (double) view_exposure(s.view);
+                                if (MODEL == HEROS_MODEL_AREA)
+                                    sum += area_contribution(c.area, te);
+                                else
+                                {
+                                    const double v_t = dist_viral_load(c.dist, te);
+                                    if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
+                                }
+                            }
                         }
-                    }
+                }
+                for (int o = lpn >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+                if (active && sub == 0)
+                {
+                    if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
+                    pr[r] = p;
+                }
             }
-            if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
-            pr[r] = p;
         }
         gsync<G>();
-        PHASE_CLOCK(8);
-        // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out].  Each lane
-        //    finds the evaluation range of one stay; the warp then shares out the (stay, evaluation) pairs
-        for (int v0 = (tid & ~31); v0 < n; v0 += G)
+        if (dbg && tid == 0)
         {
-            const int v = v0 + (tid & 31);
-            int lo = 0, hi = 0;
+            const long long t_ = clock64();
+            const unsigned long long d_ = (unsigned long long) (t_ - clk);
+            if (atomicMax(&c.ctr->dbg_clk[CLS][8], d_) < d_)
+            {
+                c.ctr->dbg_clk[CLS][10] = (unsigned long long) n; c.ctr->dbg_clk[CLS][11] = (unsigned long long) n_ill;
+                c.ctr->dbg_clk[CLS][12] = (unsigned long long) R; c.ctr->dbg_clk[CLS][13] = (unsigned long long) m_ev;
+                c.ctr->dbg_clk[CLS][14] = (unsigned long long) key;
+            }
+            clk = t_;
+        }
+        // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out].  Each lane
+        //    finds the evaluation range of one stay; the warp then deals out the (stay, evaluation) pairs evenly
+        if (G > 32)
+        {
+            if (tid == 0) s_w[32] = 0;
+            __syncthreads();
+        }
+        for (int v0 = (tid & ~31);; v0 += G)
+        {
+            const int lane = tid & 31;
+            if (G > 32)  // batches of 32 stays are handed out on demand: their pair counts differ widely
+            {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&s_w[32], 1);
+                v0 = __shfl_sync(FULL, b, 0) * 32;
+            }
+            if (v0 >= n) break;
+            const int v = v0 + lane;
+            int lo = 0, cnt = 0;
             uint32_t person = 0;
             if (v < n)
             {
@@ -852,20 +949,38 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                     int l = 0, h = R;  // first evaluation with time > t_in
                     while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
                     lo = l;
-                    l = lo; h = R;     // first evaluation with time > t_out
+                    h = R;             // first evaluation with time > t_out
                     while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
-                    hi = l;
+                    cnt = l - lo;
                 }
             }
-            unsigned pending = __ballot_sync(FULL, hi > lo);
-            while (pending)
+            int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const int s_lo = __shfl_sync(FULL, lo, src), s_hi = __shfl_sync(FULL, hi, src);
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            for (int p0 = 0; p0 < total; p0 += 32)
+            {
+                const int pi = p0 + lane;
+                int src = 0;  // first lane whose inclusive prefix exceeds pi
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                {
+                    const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
+                    if (probe <= pi) src += step;
+                }
+                src = min(src, 31);
+                const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
+                const int s_lo = __shfl_sync(FULL, lo, src);
                 const uint32_t s_person = __shfl_sync(FULL, person, src);
-                for (int r = s_lo + (tid & 31); r < s_hi; r += 32)
+                if (pi < total)
+                {
+                    const int r = s_lo + (pi - (s_incl - s_cnt));
                     if (pr[r] > 0) draw_and_push(c, st, s_person, key, ev_t[node[r]], pr[r]);
+                }
             }
         }
         gsync<G>();
