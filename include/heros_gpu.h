@@ -12,7 +12,8 @@
  *   - every function returns an int32 status: 0 = HEROS_OK, < 0 = error; heros_last_error() returns a description.
  *     No C++ exception and no exit() crosses the ABI.
  *   - all times are fp64 simulation hours (the DSOL simulator time unit, model/HerosApplication.java:170);
- *     person / location ids are int32 indices 0..n-1 in the order of heros_set_persons / heros_set_locations.
+ *     person / location ids are int32 indices 0..n-1 in the order of heros_set_persons / heros_set_locations
+ *     (plus the id bases of heros_set_id_bases when the population is sharded over several engines).
  *   - host buffers are caller-owned and only read (or written, for outputs) during the call; the engine owns all
  *     device memory.  Output buffers are caller-allocated with a capacity; the element count is returned.
  *   - a handle is not thread-safe (matches the single DSOL simulator thread); distinct handles are independent
@@ -169,6 +170,33 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
  *      sub-location, evaluate infectPeople for every movement event of the window, draw, resolve (earliest successful
  *      draw wins), run the disease-phase state machine.  stats may be NULL. ---- */
 int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats);
+
+/* ---- multi-GPU: one engine per GPU owns a shard of persons and locations.  Every person / location id that
+ *      crosses this ABI is GLOBAL: the engine owns persons [person_base, person_base + n) and locations
+ *      [location_base, location_base + n).  With the default bases (0, 0) nothing changes for a single engine.
+ *      Draws are keyed by the global person id and exposure sums are formed in (person, t_in) order, so the results do
+ *      not depend on how the population is sharded.
+ *      A window then runs in three phases, and the host exchanges data between them (NCCL all-to-all):
+ *        heros_window_begin            disease-phase state machine up to t_until
+ *        heros_export_agent_words      packed agent words of the persons whose stays go to other shards   -> all-to-all
+ *        heros_submit_guest_visits_device   stays of other shards' persons in this shard's locations (this window only)
+ *        heros_window_transmit         bucketing + every evaluation + draws
+ *        heros_export_guest_candidates successful draws on guests                                         -> all-to-all
+ *        heros_import_candidates_device     ... received by the shard that owns the person
+ *        heros_window_finish           earliest draw wins, expose, retire
+ *      heros_step(t) == begin / transmit / finish per window.  All pointers of these calls are DEVICE pointers. ---- */
+int32_t heros_set_id_bases(heros_handle h, int32_t person_base, int32_t location_base);
+int32_t heros_window_begin(heros_handle h, double t_until);
+int32_t heros_export_agent_words(heros_handle h, int64_t n, const int32_t* person, uint64_t* word_out, double* ill_end_out);
+int32_t heros_submit_guest_visits_device(heros_handle h, int64_t n, const int32_t* person, const uint64_t* word,
+                                         const double* ill_end, const int32_t* location, const int16_t* sublocation,
+                                         const double* t_in, const double* t_out);
+int32_t heros_window_transmit(heros_handle h);
+int32_t heros_export_guest_candidates(heros_handle h, int64_t capacity, int32_t* person, int32_t* location,
+                                      int16_t* sublocation, double* time, double* p, int64_t* n_out);
+int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
+                                       const int16_t* sublocation, const double* time, const double* p);
+int32_t heros_window_finish(heros_handle h, heros_step_stats* stats);
 
 /* ---- outputs ---- */
 /* infection events (what the medlabs engine applies from InfectionRecord.infectedPersons), ordered by (time, person);

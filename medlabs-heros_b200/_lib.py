@@ -77,6 +77,14 @@ SIGNATURES = {
     "heros_submit_visits": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_submit_visits_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_step": (C.c_int32, [_P, C.c_double, C.POINTER(StepStats)]),
+    "heros_set_id_bases": (C.c_int32, [_P, C.c_int32, C.c_int32]),
+    "heros_window_begin": (C.c_int32, [_P, C.c_double]),
+    "heros_export_agent_words": (C.c_int32, [_P, C.c_int64, _P, _P, _P]),
+    "heros_submit_guest_visits_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "heros_window_transmit": (C.c_int32, [_P]),
+    "heros_export_guest_candidates": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
+    "heros_import_candidates_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "heros_window_finish": (C.c_int32, [_P, C.POINTER(StepStats)]),
     "heros_get_infections": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_transitions": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_phase_counts": (C.c_int32, [_P, _P]),

@@ -41,6 +41,7 @@ struct AgentArrays
 {
     uint64_t* view; double* next_time; double* ill_end;
     const ProgParams* prog; uint64_t seed;
+    uint32_t person_base;  // global id of agent 0: every draw and every log entry uses global person ids
     Counters* ctr;
     uint32_t* tr_person; uint8_t* tr_phase; double* tr_time; unsigned long long tr_cap;
 };
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TPB) k_progress(const AgentArrays A, uint32_t 
         if (nt < T1)
         {
             double ill_end;
-            if (run_transitions(A, a, v, nt, T1, &ill_end))
+            if (run_transitions(A, A.person_base + a, v, nt, T1, &ill_end))
             {
                 A.ill_end[a] = ill_end;
                 v = view_set(v, 13, 1, 1);
@@ -140,40 +141,61 @@ struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; 
 // 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]
 // The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
 // (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
+struct GuestArrays
+{
+    const uint32_t* gid; const uint64_t* view; const uint32_t* key; const double* tin; const double* tout; uint32_t n;
+};
+
 __global__ void __launch_bounds__(TPB) k_bucket_count(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
-                                                      const double* open_tin, uint32_t n_agents, double T1,
-                                                      uint32_t* count, uint32_t* rank)
+                                                      const double* open_tin, uint32_t n_agents, GuestArrays G,
+                                                      double T1, uint32_t* count, uint32_t* rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pool + n_agents) return;
+    if (i >= n_pool + n_agents + G.n) return;
     uint32_t key;
     double tin;
     if (i < n_pool) { key = P.key[i]; tin = P.tin[i]; }
-    else { key = open_key[i - n_pool]; tin = open_tin[i - n_pool]; }
+    else if (i < n_pool + n_agents) { key = open_key[i - n_pool]; tin = open_tin[i - n_pool]; }
+    else { key = G.key[i - n_pool - n_agents]; tin = G.tin[i - n_pool - n_agents]; }
     rank[i] = (key != KEY_NONE && tin < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
 }
 
 __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
-                                                        const double* open_tin, uint32_t n_agents,
-                                                        const uint32_t* rank, const uint32_t* seg_start,
-                                                        const uint64_t* view, StayRec* rec)
+                                                        const double* open_tin, uint32_t n_agents, GuestArrays G,
+                                                        uint32_t person_base, const uint32_t* rank,
+                                                        const uint32_t* seg_start, const uint64_t* view, StayRec* rec)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pool + n_agents) return;
+    if (i >= n_pool + n_agents + G.n) return;
     const uint32_t r = rank[i];
     if (r == KEY_NONE) return;
     StayRec o;
     uint32_t key;
-    if (i < n_pool) { o.person = P.person[i]; key = P.key[i]; o.tin = P.tin[i]; o.tout = P.tout[i]; }
+    o.pad = 0;
+    if (i < n_pool)
+    {
+        const uint32_t local = P.person[i];
+        key = P.key[i]; o.tin = P.tin[i]; o.tout = P.tout[i];
+        o.person = person_base + local;
+        o.view = view[local];
+    }
+    else if (i < n_pool + n_agents)
+    {
+        const uint32_t local = i - n_pool;
+        key = open_key[local];
+        o.tin = open_tin[local];
+        o.tout = bits_f64(0x7ff0000000000000ull);
+        o.person = person_base + local;
+        o.view = view[local];
+    }
     else
     {
-        o.person = i - n_pool;
-        key = open_key[o.person];
-        o.tin = open_tin[o.person];
-        o.tout = bits_f64(0x7ff0000000000000ull);
+        const uint32_t j = i - n_pool - n_agents;
+        key = G.key[j]; o.tin = G.tin[j]; o.tout = G.tout[j];
+        o.person = G.gid[j];
+        o.view = G.view[j];
+        o.pad = REC_GUEST | j;
     }
-    o.view = view[o.person];
-    o.pad = 0;
     rec[seg_start[key] + r] = o;
 }
 
@@ -282,49 +304,62 @@ __global__ void __launch_bounds__(TPB) k_retire_gather(PoolArrays src, PoolArray
 }
 
 // ---- resolve: earliest successful draw wins (ties: lowest sub-location key) -------------------------------------------
-struct CandArrays { const uint32_t* person; const uint32_t* key; const double* t; const double* p; uint32_t cap; };
+struct CandArrays { const uint32_t* person; const uint64_t* gkey; const double* t; const double* p; uint32_t cap; };
 
-__global__ void __launch_bounds__(TPB) k_resolve_time(CandArrays C, const Counters* ctr, unsigned long long* best_t)
+// candidates carry global person ids; the ones of other shards' persons (guests) are skipped here and sent home
+__global__ void __launch_bounds__(TPB) k_resolve_time(CandArrays C, const Counters* ctr, unsigned long long* best_t,
+                                                      uint32_t person_base, uint32_t n_agents)
 {
     const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicMin(&best_t[C.person[i]], (unsigned long long) f64_bits(C.t[i]));
+    {
+        const uint32_t local = C.person[i] - person_base;
+        if (local < n_agents) atomicMin(&best_t[local], (unsigned long long) f64_bits(C.t[i]));
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_resolve_key(CandArrays C, const Counters* ctr,
-                                                     const unsigned long long* best_t, uint32_t* best_key)
+                                                     const unsigned long long* best_t, unsigned long long* best_gkey,
+                                                     uint32_t person_base, uint32_t n_agents)
 {
     const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        if (f64_bits(C.t[i]) == best_t[C.person[i]]) atomicMin(&best_key[C.person[i]], C.key[i]);
+    {
+        const uint32_t local = C.person[i] - person_base;
+        if (local < n_agents && f64_bits(C.t[i]) == best_t[local])
+            atomicMin(&best_gkey[local], (unsigned long long) C.gkey[i]);
+    }
 }
 
-struct InfLog { uint32_t* person; uint32_t* key; double* t; double* p; unsigned long long cap; };
+struct InfLog { uint32_t* person; uint64_t* gkey; double* t; double* p; unsigned long long cap; };
 
 __global__ void __launch_bounds__(TPB) k_resolve_apply(CandArrays C, const AgentArrays A,
-                                                       const unsigned long long* best_t, const uint32_t* best_key,
-                                                       uint32_t* claim, InfLog log, double T1)
+                                                       const unsigned long long* best_t,
+                                                       const unsigned long long* best_gkey, uint32_t* claim, InfLog log,
+                                                       double T1, uint32_t n_agents)
 {
     const uint32_t n = (uint32_t) min((unsigned long long) C.cap, A.ctr->n_cand);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        const uint32_t person = C.person[i];
-        if (f64_bits(C.t[i]) != best_t[person] || C.key[i] != best_key[person]) continue;
+        const uint32_t gid = C.person[i];
+        const uint32_t person = gid - A.person_base;
+        if (person >= n_agents) continue;
+        if (f64_bits(C.t[i]) != best_t[person] || C.gkey[i] != best_gkey[person]) continue;
         if (atomicExch(&claim[person], 1u) != 0u) continue;  // identical duplicate
         uint64_t v = A.view[person];
         if (!phase_is_susceptible(view_phase(v))) continue;
         const double t = C.t[i];
         double nt;
-        expose_agent(A, person, v, nt, t);  // exposure time := (float) now, then expose() (contract C4)
+        expose_agent(A, gid, v, nt, t);  // exposure time := (float) now, then expose() (contract C4)
         double ill_end;
-        run_transitions(A, person, v, nt, T1, &ill_end);
+        run_transitions(A, gid, v, nt, T1, &ill_end);
         A.view[person] = v;
         A.next_time[person] = nt;
         const unsigned long long slot = atomicAdd(&A.ctr->n_inf_log, 1ull);
         if (slot < log.cap)
         {
-            log.person[slot] = person;
-            log.key[slot] = C.key[i];
+            log.person[slot] = gid;
+            log.gkey[slot] = C.gkey[i];
             log.t[slot] = t;
             log.p[slot] = C.p[i];
         }
@@ -335,16 +370,88 @@ __global__ void __launch_bounds__(TPB) k_resolve_apply(CandArrays C, const Agent
 }
 
 __global__ void __launch_bounds__(TPB) k_resolve_reset(CandArrays C, const Counters* ctr, unsigned long long* best_t,
-                                                       uint32_t* best_key, uint32_t* claim)
+                                                       unsigned long long* best_gkey, uint32_t* claim,
+                                                       uint32_t person_base, uint32_t n_agents)
 {
     const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        const uint32_t person = C.person[i];
+        const uint32_t person = C.person[i] - person_base;
+        if (person >= n_agents) continue;
         best_t[person] = BEST_NONE;
-        best_key[person] = KEY_NONE;
+        best_gkey[person] = BEST_NONE;
         claim[person] = 0u;
     }
+}
+
+// ---- multi-GPU: stays of this shard's persons in other shards' locations, and the way back -----------------------------
+// the packed agent words (and the end of illness, if inside the window) of the listed persons, after k_progress
+__global__ void __launch_bounds__(TPB) k_export_words(uint32_t n, const int32_t* person, uint32_t person_base,
+                                                      uint32_t n_agents, const uint64_t* view, const double* ill_end,
+                                                      uint64_t* view_out, double* ill_end_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t local = (uint32_t) person[i] - person_base;
+    uint64_t v = 0;
+    double e = bits_f64(0x7ff0000000000000ull);
+    if (local < n_agents)
+    {
+        v = view[local];
+        if (view_ends(v)) e = ill_end[local];
+    }
+    view_out[i] = v;
+    ill_end_out[i] = e;
+}
+
+__global__ void __launch_bounds__(TPB) k_guest_keys(uint32_t n, const int32_t* loc, const int16_t* sub, int32_t loc_base,
+                                                    const uint32_t* loc_first_key, const int16_t* loc_nsub, uint32_t n_loc,
+                                                    const double* tin, const double* tout, uint32_t* key_out,
+                                                    Counters* ctr)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t l = loc[i] - loc_base;
+    const int32_t sb = sub[i];
+    bool ok = l >= 0 && (uint32_t) l < n_loc && sb >= 0 && tin[i] >= 0.0 && tout[i] > tin[i];
+    if (ok) ok = sb < max((int) loc_nsub[l], 1);
+    key_out[i] = ok ? loc_first_key[l] + (uint32_t) sb : KEY_NONE;
+    if (!ok) atomicAdd(&ctr->invalid_visits, 1u);
+}
+
+// candidates whose person lives on another shard, compacted for the exchange
+__global__ void __launch_bounds__(TPB) k_export_guest_candidates(CandArrays C, const Counters* ctr, uint32_t person_base,
+                                                                 uint32_t n_agents, uint32_t cap, uint32_t* gid,
+                                                                 int32_t* loc, int16_t* sub, double* t, double* p,
+                                                                 unsigned long long* n_out)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        if (C.person[i] - person_base < n_agents) continue;
+        const unsigned long long slot = atomicAdd(n_out, 1ull);
+        if (slot >= cap) continue;
+        gid[slot] = C.person[i];
+        loc[slot] = (int32_t) (C.gkey[i] >> 16);
+        sub[slot] = (int16_t) (C.gkey[i] & 0xFFFFu);
+        t[slot] = C.t[i];
+        p[slot] = C.p[i];
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_import_candidates(uint32_t n, const uint32_t* gid, const int32_t* loc,
+                                                           const int16_t* sub, const double* t, const double* p,
+                                                           uint32_t* cand_person, uint64_t* cand_gkey, double* cand_t,
+                                                           double* cand_p, uint32_t cand_cap, Counters* ctr)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long slot = atomicAdd(&ctr->n_cand, 1ull);
+    if (slot >= cand_cap) { atomicOr(&ctr->overflow, 1u); return; }
+    cand_person[slot] = gid[i];
+    cand_gkey[slot] = ((uint64_t) (uint32_t) loc[i] << 16) | (uint64_t) (uint16_t) sub[i];
+    cand_t[slot] = t[i];
+    cand_p[slot] = p[i];
 }
 
 // ---- inputs ------------------------------------------------------------------------------------------------------------
@@ -354,11 +461,11 @@ struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub;
 __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, int pass, PoolArrays P, uint32_t pool_base,
                                                 uint32_t* open_key, double* open_tin, const uint32_t* loc_base,
                                                 const int16_t* loc_nsub, uint32_t n_loc, uint32_t n_agents,
-                                                double t_now, Counters* ctr)
+                                                uint32_t person_base, int32_t loc_origin, double t_now, Counters* ctr)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t person = in.person[i], loc = in.loc[i];
+    const int32_t person = (int32_t) ((uint32_t) in.person[i] - person_base), loc = in.loc[i] - loc_origin;
     const int32_t sub = in.sub[i];
     const double tin = in.tin[i], tout = in.tout[i];
     bool ok = person >= 0 && (uint32_t) person < n_agents && loc >= 0 && (uint32_t) loc < n_loc && sub >= 0 &&
@@ -396,7 +503,7 @@ __global__ void __launch_bounds__(TPB) k_expose(const AgentArrays A, uint32_t n,
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t p = person[i];
+    const int32_t p = (int32_t) ((uint32_t) person[i] - A.person_base);
     if (p < 0 || (uint32_t) p >= n_agents) return;
     const uint64_t v0 = A.view[p];
     if (!phase_is_susceptible(view_phase(v0))) return;  // ConstructHerosModel.java:1119
@@ -405,7 +512,7 @@ __global__ void __launch_bounds__(TPB) k_expose(const AgentArrays A, uint32_t n,
     if (atomicCAS((unsigned long long*) &A.view[p], (unsigned long long) v0, (unsigned long long) claimed) != v0) return;
     uint64_t v = v0;
     double nt;
-    expose_agent(A, (uint32_t) p, v, nt, at_time[i]);
+    expose_agent(A, A.person_base + (uint32_t) p, v, nt, at_time[i]);
     A.view[p] = v;
     A.next_time[p] = nt;
 }
@@ -416,7 +523,7 @@ __global__ void __launch_bounds__(TPB) k_set_agent_state(const AgentArrays A, ui
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t p = person[i];
+    const int32_t p = (int32_t) ((uint32_t) person[i] - A.person_base);
     if (p < 0 || (uint32_t) p >= n_agents) return;
     uint64_t v = A.view[p];
     const uint32_t ph = phase[i] & 7u;
@@ -427,14 +534,14 @@ __global__ void __launch_bounds__(TPB) k_set_agent_state(const AgentArrays A, ui
     v = view_set_exposure(v, exposure[i]);
     uint32_t next_phase;
     double nt;
-    progression_next(*A.prog, A.seed, (uint32_t) p, view_age(v), view_female(v), ph, now, next_phase, nt);
+    progression_next(*A.prog, A.seed, A.person_base + (uint32_t) p, view_age(v), view_female(v), ph, now, next_phase, nt);
     v = view_set(v, 8, 0xF, next_phase);
     A.view[p] = v;
     A.next_time[p] = nt;
 }
 
 __global__ void __launch_bounds__(TPB) k_init_agents(uint64_t* view, double* next_time, unsigned long long* best_t,
-                                                     uint32_t* best_key, uint32_t* claim, uint32_t* open_key,
+                                                     unsigned long long* best_key, uint32_t* claim, uint32_t* open_key,
                                                      double* open_tin, const int8_t* age, const uint8_t* female,
                                                      const uint8_t* role, uint32_t n)
 {
@@ -448,7 +555,7 @@ __global__ void __launch_bounds__(TPB) k_init_agents(uint64_t* view, double* nex
     view[a] = v;
     next_time[a] = bits_f64(0x7ff0000000000000ull);
     best_t[a] = BEST_NONE;
-    best_key[a] = KEY_NONE;
+    best_key[a] = BEST_NONE;
     claim[a] = 0u;
     open_key[a] = KEY_NONE;
     open_tin[a] = 0.0;
@@ -459,7 +566,7 @@ struct ShimOut { int32_t calculated, n_infectious, n_infected, pad; double p; };
 
 __global__ void k_infect_people(int model, AreaParams area, DistParams dist, double psi, double mu, uint64_t seed,
                                 int infect_sub, int n_sub_locations, double total_area, double corr,
-                                const uint64_t* view, int n_sub, const int32_t* sub_ids, int n_all,
+                                const uint64_t* view, uint32_t person_base, int n_sub, const int32_t* sub_ids, int n_all,
                                 const int32_t* all_ids, double now, double duration, int32_t* infectious,
                                 int32_t* infected, ShimOut* out)
 {
@@ -483,7 +590,7 @@ __global__ void k_infect_people(int model, AreaParams area, DistParams dist, dou
             double sum = 0.0;
             for (int k = 0; k < n; ++k)
             {
-                const uint64_t v = view[ids[k]];
+                const uint64_t v = view[(uint32_t) ids[k] - person_base];
                 if (phase_is_ill(view_phase(v)))
                 {
                     const double te = now - (double) view_exposure(v);
@@ -502,7 +609,7 @@ __global__ void k_infect_people(int model, AreaParams area, DistParams dist, dou
             double sum = 0.0;
             for (int k = 0; k < n; ++k)
             {
-                const uint64_t v = view[ids[k]];
+                const uint64_t v = view[(uint32_t) ids[k] - person_base];
                 if (phase_is_ill(view_phase(v)))
                 {
                     const double v_t = dist_viral_load(dist, now - (double) view_exposure(v));
@@ -521,7 +628,7 @@ __global__ void k_infect_people(int model, AreaParams area, DistParams dist, dou
         o.p = p;
         for (int k = 0; k < n; ++k)
         {
-            const uint64_t v = view[ids[k]];
+            const uint64_t v = view[(uint32_t) ids[k] - person_base];
             if (phase_is_susceptible(view_phase(v)) && u01(seed, (uint32_t) ids[k], f64_bits(now), TAG_TRANSMIT) < p)
                 infected[o.n_infected++] = ids[k];
         }
@@ -574,8 +681,21 @@ struct heros_engine
     uint32_t n_agents = 0;
     DevBuf<uint64_t> d_view;
     DevBuf<double> d_next_time, d_ill_end, d_open_tin;
-    DevBuf<unsigned long long> d_best_t;
-    DevBuf<uint32_t> d_best_key, d_claim, d_open_key;
+    DevBuf<unsigned long long> d_best_t, d_best_key;
+    DevBuf<uint32_t> d_claim, d_open_key;
+    uint32_t person_base = 0;   // global id of agent 0
+    int32_t location_base = 0;  // global id of location 0
+
+    // guests: stays of other shards' persons in this shard's locations, valid for the window in progress
+    DevBuf<uint32_t> g_gid, g_key;
+    DevBuf<uint64_t> g_view;
+    DevBuf<double> g_ill_end, g_tin, g_tout;
+    uint32_t n_guest = 0;
+    int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
+    double win_T0 = 0.0, win_T1 = 0.0;
+    int win_launches = 0;
+    uint32_t win_n_pool = 0;
+    Counters win_before{};
 
     // pool of submitted stays (double buffered)
     DevBuf<uint32_t> pool_person[2], pool_key[2];
@@ -589,9 +709,11 @@ struct heros_engine
     DevBuf<uint8_t> cub_temp;
 
     // candidates, logs
-    DevBuf<uint32_t> cand_person, cand_key;
+    DevBuf<uint32_t> cand_person;
+    DevBuf<uint64_t> cand_gkey, inf_gkey;
     DevBuf<double> cand_t, cand_p;
-    DevBuf<uint32_t> inf_person, inf_key, tr_person;
+    DevBuf<uint32_t> inf_person, tr_person;
+    DevBuf<unsigned long long> d_nguest_cand;
     DevBuf<double> inf_t, inf_p, tr_time;
     DevBuf<uint8_t> tr_phase;
 
@@ -612,7 +734,8 @@ struct heros_engine
     std::vector<int64_t> series_counts;
 
     // sorted output caches
-    std::vector<uint32_t> o_inf_person, o_inf_key, o_tr_person;
+    std::vector<uint32_t> o_inf_person, o_tr_person;
+    std::vector<uint64_t> o_inf_gkey;
     std::vector<double> o_inf_t, o_inf_p, o_tr_time;
     std::vector<uint8_t> o_tr_phase;
     unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
@@ -639,7 +762,7 @@ AgentArrays agent_arrays(heros_handle h)
 {
     AgentArrays A;
     A.view = h->d_view.p; A.next_time = h->d_next_time.p; A.ill_end = h->d_ill_end.p;
-    A.prog = h->d_prog.p; A.seed = h->cfg.seed; A.ctr = h->d_ctr.p;
+    A.prog = h->d_prog.p; A.seed = h->cfg.seed; A.person_base = h->person_base; A.ctr = h->d_ctr.p;
     A.tr_person = h->tr_person.p; A.tr_phase = h->tr_phase.p; A.tr_time = h->tr_time.p;
     A.tr_cap = h->tr_person.n;
     return A;
@@ -689,25 +812,36 @@ int32_t check_ready(heros_handle h)
     return HEROS_OK;
 }
 
-// one window [T0, T1)
-int32_t run_window(heros_handle h, double T0, double T1, int& launches)
+// A window [T0, T1) runs in three phases so that a multi-GPU host can exchange stays and candidate infections between
+// them: begin (disease-phase state machine; agent words final for the window) -> [guests in] -> transmit (bucketing +
+// every evaluation; candidates out / in) -> finish (resolve, retire).  heros_step runs the three back to back.
+int32_t window_begin(heros_handle h, double T1)
 {
     cudaStream_t s = h->stream;
-    const uint32_t N = h->n_agents;
-    const uint32_t n_pool = h->n_pool;
-    const uint32_t n_total = n_pool + N;
-    const int cur = h->pool_cur, oth = cur ^ 1;
-
+    h->win_T0 = h->t_now;
+    h->win_T1 = T1;
+    h->win_launches = 0;
+    h->n_guest = 0;
     CU(h, cudaEventRecord(h->ev[2], s));
     k_zero_window<<<1, 1, 0, s>>>(h->d_ctr.p);
-    ++launches;
-
     // 1. disease-phase state machine
-    const AgentArrays A = agent_arrays(h);
-    k_progress<<<blocks_for(N), TPB, 0, s>>>(A, N, T1);
-    ++launches;
-
+    k_progress<<<blocks_for(h->n_agents), TPB, 0, s>>>(agent_arrays(h), h->n_agents, T1);
+    h->win_launches += 2;
     CU(h, cudaEventRecord(h->ev[3], s));
+    CU(h, cudaGetLastError());
+    h->win_state = 1;
+    return HEROS_OK;
+}
+
+int32_t window_transmit(heros_handle h)
+{
+    cudaStream_t s = h->stream;
+    const double T0 = h->win_T0, T1 = h->win_T1;
+    const uint32_t N = h->n_agents;
+    const uint32_t n_pool = h->n_pool;
+    const uint32_t n_total = n_pool + N + h->n_guest;
+    int& launches = h->win_launches;
+    h->win_n_pool = n_pool;
 
     // 2-4. occupancy bucketing: counting sort of the window's stays over the dense sub-location keys
     const uint32_t n_keys = h->n_keys;
@@ -715,27 +849,20 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     CU(h, h->bk_count.ensure((size_t) n_keys + 1)); CU(h, h->seg_start.ensure((size_t) n_keys + 2));
     CU(h, h->tile_sum.ensure((size_t) n_tiles + 1));
     CU(h, h->bk_rank.ensure(n_total)); CU(h, h->rec.ensure(n_total));
-    CU(h, h->keep_idx.ensure(std::max<uint32_t>(n_pool, 1)));
-    { const int32_t rc_ = ensure_pool(h, oth, std::max<uint32_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
-    const PoolArrays P = pool_arrays(h, cur);
+    const PoolArrays P = pool_arrays(h, h->pool_cur);
+    const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->n_guest};
     CU(h, cudaMemsetAsync(h->bk_count.p, 0, (size_t) n_keys * 4, s));
-    k_bucket_count<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, T1,
+    k_bucket_count<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, G, T1,
                                                        h->bk_count.p, h->bk_rank.p);
     CU(h, cudaEventRecord(h->ev_bk[0], s));
     k_scan_tile_sums<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p);
     k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_sum.p, n_tiles, h->seg_start.p + n_keys, h->d_ctr.p);
     k_scan_apply<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p, h->seg_start.p);
     CU(h, cudaEventRecord(h->ev_bk[1], s));
-    k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, h->bk_rank.p,
-                                                         h->seg_start.p, h->d_view.p, h->rec.p);
+    k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, G,
+                                                         h->person_base, h->bk_rank.p, h->seg_start.p, h->d_view.p,
+                                                         h->rec.p);
     launches += 6;
-    thrust::counting_iterator<uint32_t> iota(0);
-    KeepPred keep{P.key, P.tout, T1};
-    size_t temp_keep = 0;
-    CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) std::max<uint32_t>(n_pool, 1), keep, s));
-    CU(h, h->cub_temp.ensure(temp_keep + 256));
-    size_t tb = h->cub_temp.n;
-    (void) tb;
 
     // 5. transmission
     const size_t list_cap = (size_t) n_total / 32 + 16;
@@ -748,9 +875,11 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
     c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
     c.key_loc = h->d_key_loc.p; c.loc_param = h->d_loc_param.p; c.last_calc = h->d_last_calc.p; c.n_keys = h->n_keys;
-    c.view = h->d_view.p; c.ill_end = h->d_ill_end.p;
+    c.view = h->d_view.p; c.ill_end = h->d_ill_end.p; c.guest_ill_end = h->g_ill_end.p;
+    c.person_base = h->person_base; c.n_agents = N;
+    c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
     c.rec = h->rec.p; c.seg_start = h->seg_start.p;
-    c.cand_person = h->cand_person.p; c.cand_key = h->cand_key.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
+    c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
     c.warp_seg = h->warp_seg.p; c.warp_cap = (uint32_t) h->warp_seg.n;
     for (int k = 0; k < 4; ++k) c.blk_seg[k] = h->blk_seg[k].p;
@@ -762,23 +891,45 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     CU(h, cudaEventRecord(h->ev[4], s));
     launch_transmit(c, h->n_sm, h->ts, launches);
     CU(h, cudaEventRecord(h->ev[6], s));
+    CU(h, cudaGetLastError());
+    h->win_state = 2;
+    return HEROS_OK;
+}
+
+int32_t window_finish(heros_handle h)
+{
+    cudaStream_t s = h->stream;
+    const double T1 = h->win_T1;
+    const uint32_t N = h->n_agents;
+    const uint32_t n_pool = h->win_n_pool;
+    const int cur = h->pool_cur, oth = cur ^ 1;
+    int& launches = h->win_launches;
+    const AgentArrays A = agent_arrays(h);
 
     // 6. resolve: earliest successful draw per person wins
-    const CandArrays C{h->cand_person.p, h->cand_key.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
-    const InfLog log{h->inf_person.p, h->inf_key.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
+    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    const InfLog log{h->inf_person.p, h->inf_gkey.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
     const int rg = h->n_sm * 2;
-    k_resolve_time<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p);
-    k_resolve_key<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p);
-    k_resolve_apply<<<rg, TPB, 0, s>>>(C, A, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, log, T1);
-    k_resolve_reset<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->d_claim.p);
+    k_resolve_time<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->person_base, N);
+    k_resolve_key<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->person_base, N);
+    k_resolve_apply<<<rg, TPB, 0, s>>>(C, A, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, log, T1, N);
+    k_resolve_reset<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, h->person_base, N);
     launches += 4;
     CU(h, cudaEventRecord(h->ev[7], s));
 
-    // 7. retire the stays that ended before T1
+    // 7. retire the stays that ended before T1 (stays submitted after the transmit phase belong to later windows)
     if (n_pool > 0)
     {
-        tb = h->cub_temp.n;
-        CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) n_pool, keep, s));
+        const PoolArrays P = pool_arrays(h, cur);
+        CU(h, h->keep_idx.ensure(h->n_pool));
+        { const int32_t rc_ = ensure_pool(h, oth, h->n_pool, false); if (rc_ != HEROS_OK) return rc_; }
+        thrust::counting_iterator<uint32_t> iota(0);
+        KeepPred keep{P.key, P.tout, T1};
+        size_t temp_keep = 0;
+        CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) h->n_pool, keep, s));
+        CU(h, h->cub_temp.ensure(temp_keep + 256));
+        size_t tb = h->cub_temp.n;
+        CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) h->n_pool, keep, s));
         k_retire_gather<<<h->n_sm * 4, TPB, 0, s>>>(P, pool_arrays(h, oth), h->keep_idx.p, h->d_nsel.p + 1, h->d_ctr.p);
         launches += 3;
     }
@@ -793,7 +944,8 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     }
     {
         // ev[2] start, [3] after progress, [4] after bucketing, ts.fork after k_transmit_thread, [6] after the joined
-        // warp / group kernels, [7] after resolve, [8] after retire
+        // warp / group kernels, [7] after resolve, [8] after retire.  (With a multi-GPU host the intervals also contain
+        // the time the engine waited for the exchanges.)
         cudaEvent_t marks[7] = {h->ev[2], h->ev[3], h->ev[4], h->ts.fork, h->ev[6], h->ev[7], h->ev[8]};
         for (int k = 0; k < 6; ++k)
         {
@@ -809,6 +961,9 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
             h->bucket_part_ms[k] += ms;
         }
     }
+    h->win_state = 0;
+    h->n_guest = 0;
+    h->t_now = T1;
     if (h->h_ctr->overflow)
     {
         char buf[160];
@@ -818,6 +973,16 @@ int32_t run_window(heros_handle h, double T0, double T1, int& launches)
     }
     h->series_t.push_back(T1);
     for (int k = 0; k < 8; ++k) h->series_counts.push_back((int64_t) h->h_ctr->phase_counts[k]);
+    return HEROS_OK;
+}
+
+int32_t check_window_length(heros_handle h, double T1)
+{
+    // batch == sequential only while an infection of the window cannot become contagious inside it (SURVEY.md 7.1);
+    // the float exposure time moves the onset by < 1e-3 h
+    const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
+    if (!(h->cfg.window_hours <= latent - 1e-3) || !(T1 - h->t_now <= latent - 1e-3))
+        return fail(h, HEROS_ERR_UNSUPPORTED, "the window must be shorter than the latent period of the transmission model");
     return HEROS_OK;
 }
 
@@ -895,8 +1060,11 @@ int32_t heros_destroy(heros_handle h)
         h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
     }
     h->bk_count.release(); h->bk_rank.release(); h->tile_sum.release(); h->rec.release();
-    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->cub_temp.release(); h->cand_person.release(); h->cand_key.release(); h->cand_t.release();
-    h->cand_p.release(); h->inf_person.release(); h->inf_key.release(); h->tr_person.release(); h->inf_t.release();
+    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->cub_temp.release(); h->cand_person.release();
+    h->cand_gkey.release(); h->cand_t.release();
+    h->cand_p.release(); h->inf_person.release(); h->inf_gkey.release(); h->tr_person.release(); h->inf_t.release();
+    h->g_gid.release(); h->g_key.release(); h->g_view.release(); h->g_ill_end.release(); h->g_tin.release();
+    h->g_tout.release(); h->d_nguest_cand.release();
     h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->warp_seg.release();
     for (auto& b : h->blk_seg) b.release();
     h->huge_off.release(); h->scratch.release();
@@ -982,9 +1150,9 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     CU(h, h->d_view.ensure(N)); CU(h, h->d_next_time.ensure(N)); CU(h, h->d_ill_end.ensure(N));
     CU(h, h->d_open_tin.ensure(N)); CU(h, h->d_best_t.ensure(N)); CU(h, h->d_best_key.ensure(N));
     CU(h, h->d_claim.ensure(N)); CU(h, h->d_open_key.ensure(N));
-    CU(h, h->cand_person.ensure(N + 65536)); CU(h, h->cand_key.ensure(N + 65536));
+    CU(h, h->cand_person.ensure(N + 65536)); CU(h, h->cand_gkey.ensure(N + 65536));
     CU(h, h->cand_t.ensure(N + 65536)); CU(h, h->cand_p.ensure(N + 65536));
-    CU(h, h->inf_person.ensure(N)); CU(h, h->inf_key.ensure(N)); CU(h, h->inf_t.ensure(N)); CU(h, h->inf_p.ensure(N));
+    CU(h, h->inf_person.ensure(N)); CU(h, h->inf_gkey.ensure(N)); CU(h, h->inf_t.ensure(N)); CU(h, h->inf_p.ensure(N));
     CU(h, h->tr_person.ensure(5 * N)); CU(h, h->tr_phase.ensure(5 * N)); CU(h, h->tr_time.ensure(5 * N));
     DevBuf<int8_t> d_age; DevBuf<uint8_t> d_female, d_role;
     if (age) { CU(h, d_age.ensure(N)); CU(h, cudaMemcpyAsync(d_age.p, age, N, cudaMemcpyHostToDevice, h->stream)); }
@@ -1103,8 +1271,9 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
     {
         const int age = (int) view_age(view[a]);
         if (!phase_is_susceptible(view_phase(view[a])) || age < min_age || age > max_age) continue;
-        const Philox4 r = philox4x32_10(a, 0, 0, TAG_SEEDING, (uint32_t) h->cfg.seed, (uint32_t) (h->cfg.seed >> 32));
-        eligible.emplace_back(((uint64_t) r.x << 32) | r.y, (int32_t) a);
+        const uint32_t gid = h->person_base + a;
+        const Philox4 r = philox4x32_10(gid, 0, 0, TAG_SEEDING, (uint32_t) h->cfg.seed, (uint32_t) (h->cfg.seed >> 32));
+        eligible.emplace_back(((uint64_t) r.x << 32) | r.y, (int32_t) gid);
     }
     if ((size_t) n_infected > eligible.size())
         return fail(h, HEROS_ERR_INVALID, "fewer eligible persons than infections requested");
@@ -1129,7 +1298,8 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     for (int pass = 0; pass < 2; ++pass)
         k_submit<<<blocks_for(n), TPB, 0, h->stream>>>(in, (uint32_t) n, pass, P, h->n_pool, h->d_open_key.p,
                                                        h->d_open_tin.p, h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc,
-                                                       h->n_agents, h->t_now, h->d_ctr.p);
+                                                       h->n_agents, h->person_base, h->location_base, h->t_now,
+                                                       h->d_ctr.p);
     CU(h, cudaGetLastError());
     h->n_pool += (uint32_t) n;
     return HEROS_OK;
@@ -1170,58 +1340,196 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
     return HEROS_OK;
 }
 
-int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
+static void begin_stats(heros_handle h, Counters& before)
 {
-    int32_t rc = check_ready(h);
-    if (rc != HEROS_OK) return rc;
-    if (!(t_until >= h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until lies before the engine time");
-    // batch == sequential only while an infection of the window cannot become contagious inside it (SURVEY.md 7.1);
-    // the float exposure time moves the onset by < 1e-3 h
-    const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
-    if (!(h->cfg.window_hours <= latent - 1e-3))
-        return fail(h, HEROS_ERR_UNSUPPORTED, "window_hours must be below the latent period of the transmission model");
-    cudaSetDevice(h->cfg.device);
-    rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
-    const Counters before = *h->h_ctr;
-    heros_step_stats st{};
-    int launches = 0;
-    int64_t n_big = 0;
+    before = *h->h_ctr;
     for (double& m : h->stage_ms) m = 0.0;
     for (double& m : h->bucket_part_ms) m = 0.0;
-    CU(h, cudaEventRecord(h->ev[0], h->stream));
-    while (h->t_now < t_until)
-    {
-        const double T0 = h->t_now;
-        const double T1 = std::min(T0 + h->cfg.window_hours, t_until);
-        rc = run_window(h, T0, T1, launches);
-        if (rc != HEROS_OK) return rc;
-        h->t_now = T1;
-        st.windows++;
-        st.visits += (int64_t) h->h_ctr->n_active;
-        st.sublocations += (int64_t) h->h_ctr->n_seg;
-        n_big += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2] + h->h_ctr->n_blk[3]);
-    }
-    CU(h, cudaEventRecord(h->ev[1], h->stream));
-    CU(h, cudaEventSynchronize(h->ev[1]));
-    float ms = 0.f;
-    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+}
+
+static void fill_stats(heros_handle h, const Counters& before, heros_step_stats& st)
+{
     const Counters& now = *h->h_ctr;
     st.evaluations = (int64_t) (now.evaluations - before.evaluations);
     st.draws = (int64_t) (now.draws - before.draws);
     st.infections = (int64_t) (now.infections - before.infections);
     st.transitions = (int64_t) (now.transitions - before.transitions);
     st.near_ties = (int64_t) (now.near_ties - before.near_ties);
-    st.gpu_launches = launches;
-    st.gpu_ms = ms;
+    st.big_stays = (int64_t) (now.big_stays - before.big_stays);
     st.progress_ms = h->stage_ms[0]; st.bucket_ms = h->stage_ms[1];
     st.transmit_small_ms = h->stage_ms[2]; st.transmit_big_ms = h->stage_ms[3];
     st.resolve_ms = h->stage_ms[4]; st.retire_ms = h->stage_ms[5];
     st.transmit_ms = h->stage_ms[2] + h->stage_ms[3];
     st.bucket_count_ms = h->bucket_part_ms[0]; st.bucket_scan_ms = h->bucket_part_ms[1];
     st.bucket_scatter_ms = h->bucket_part_ms[2];
-    st.big_stays = (int64_t) (now.big_stays - before.big_stays);
-    st.big_sublocations = n_big;
+}
+
+static void add_window_stats(heros_handle h, heros_step_stats& st)
+{
+    st.windows++;
+    st.visits += (int64_t) h->h_ctr->n_active;
+    st.sublocations += (int64_t) h->h_ctr->n_seg;
+    st.big_sublocations += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2] + h->h_ctr->n_blk[3]);
+    st.gpu_launches += h->win_launches;
+}
+
+int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (h->win_state != 0) return fail(h, HEROS_ERR_INVALID, "a window opened by heros_window_begin is still in progress");
+    if (!(t_until >= h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until lies before the engine time");
+    const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
+    if (!(h->cfg.window_hours <= latent - 1e-3))
+        return fail(h, HEROS_ERR_UNSUPPORTED, "window_hours must be below the latent period of the transmission model");
+    cudaSetDevice(h->cfg.device);
+    rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    Counters before;
+    begin_stats(h, before);
+    heros_step_stats st{};
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    while (h->t_now < t_until)
+    {
+        const double T1 = std::min(h->t_now + h->cfg.window_hours, t_until);
+        if ((rc = window_begin(h, T1)) != HEROS_OK) return rc;
+        if ((rc = window_transmit(h)) != HEROS_OK) return rc;
+        if ((rc = window_finish(h)) != HEROS_OK) return rc;
+        add_window_stats(h, st);
+    }
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    fill_stats(h, before, st);
+    st.gpu_ms = ms;
+    if (stats) *stats = st;
+    return HEROS_OK;
+}
+
+int32_t heros_set_id_bases(heros_handle h, int32_t person_base, int32_t location_base)
+{
+    if (!h || person_base < 0 || location_base < 0) return HEROS_ERR_INVALID;
+    if (h->n_pool != 0 || h->t_now != 0.0) return fail(h, HEROS_ERR_INVALID, "id bases must be set before any stay is submitted");
+    h->person_base = (uint32_t) person_base;
+    h->location_base = location_base;
+    return HEROS_OK;
+}
+
+int32_t heros_window_begin(heros_handle h, double t_until)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (h->win_state != 0) return fail(h, HEROS_ERR_INVALID, "a window is already in progress");
+    if (!(t_until > h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until must lie after the engine time");
+    if ((rc = check_window_length(h, t_until)) != HEROS_OK) return rc;
+    cudaSetDevice(h->cfg.device);
+    if ((rc = sync_counters(h)) != HEROS_OK) return rc;
+    begin_stats(h, h->win_before);
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    return window_begin(h, t_until);
+}
+
+int32_t heros_export_agent_words(heros_handle h, int64_t n, const int32_t* person, uint64_t* view_out, double* ill_end_out)
+{
+    if (!h || n < 0 || (n > 0 && (!person || !view_out || !ill_end_out))) return HEROS_ERR_INVALID;
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "agent words are exported between heros_window_begin and heros_window_transmit");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    k_export_words<<<blocks_for(n), TPB, 0, h->stream>>>((uint32_t) n, person, h->person_base, h->n_agents, h->d_view.p,
+                                                         h->d_ill_end.p, view_out, ill_end_out);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_submit_guest_visits_device(heros_handle h, int64_t n, const int32_t* person, const uint64_t* view,
+                                         const double* ill_end, const int32_t* location, const int16_t* sublocation,
+                                         const double* t_in, const double* t_out)
+{
+    if (!h || n < 0 || (n > 0 && (!person || !view || !ill_end || !location || !sublocation || !t_in || !t_out)))
+        return HEROS_ERR_INVALID;
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are submitted between heros_window_begin and heros_window_transmit");
+    if (n == 0) return HEROS_OK;
+    if ((uint64_t) h->n_guest + (uint64_t) n >= 0x7fffffffull) return fail(h, HEROS_ERR_CAPACITY, "too many guest stays");
+    cudaSetDevice(h->cfg.device);
+    const size_t tot = (size_t) h->n_guest + (size_t) n, off = h->n_guest;
+    CU(h, h->g_gid.ensure(tot, true, h->stream)); CU(h, h->g_key.ensure(tot, true, h->stream));
+    CU(h, h->g_view.ensure(tot, true, h->stream)); CU(h, h->g_ill_end.ensure(tot, true, h->stream));
+    CU(h, h->g_tin.ensure(tot, true, h->stream)); CU(h, h->g_tout.ensure(tot, true, h->stream));
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->g_gid.p + off, person, (size_t) n * 4, cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(h->g_view.p + off, view, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(h->g_ill_end.p + off, ill_end, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(h->g_tin.p + off, t_in, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    CU(h, cudaMemcpyAsync(h->g_tout.p + off, t_out, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    k_guest_keys<<<blocks_for(n), TPB, 0, s>>>((uint32_t) n, location, sublocation, h->location_base, h->d_loc_base.p,
+                                               h->d_loc_nsub.p, h->n_loc, t_in, t_out, h->g_key.p + off, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(s));
+    h->n_guest += (uint32_t) n;
+    return HEROS_OK;
+}
+
+int32_t heros_window_transmit(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "heros_window_begin has not been called");
+    cudaSetDevice(h->cfg.device);
+    return window_transmit(h);
+}
+
+int32_t heros_export_guest_candidates(heros_handle h, int64_t capacity, int32_t* person, int32_t* location,
+                                      int16_t* sublocation, double* time, double* p, int64_t* n_out)
+{
+    if (!h || !n_out || capacity < 0) return HEROS_ERR_INVALID;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are exported between heros_window_transmit and heros_window_finish");
+    cudaSetDevice(h->cfg.device);
+    CU(h, h->d_nguest_cand.ensure(1));
+    CU(h, cudaMemsetAsync(h->d_nguest_cand.p, 0, 8, h->stream));
+    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    k_export_guest_candidates<<<h->n_sm * 2, TPB, 0, h->stream>>>(C, h->d_ctr.p, h->person_base, h->n_agents,
+                                                                 (uint32_t) std::min<int64_t>(capacity, 0x7fffffff),
+                                                                 (uint32_t*) person, location, sublocation, time, p,
+                                                                 h->d_nguest_cand.p);
+    CU(h, cudaGetLastError());
+    unsigned long long n = 0;
+    CU(h, cudaMemcpyAsync(&n, h->d_nguest_cand.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *n_out = (int64_t) n;
+    return (int64_t) n > capacity ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
+                                       const int16_t* sublocation, const double* time, const double* p)
+{
+    if (!h || n < 0 || (n > 0 && (!person || !location || !sublocation || !time || !p))) return HEROS_ERR_INVALID;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are imported between heros_window_transmit and heros_window_finish");
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    k_import_candidates<<<blocks_for(n), TPB, 0, h->stream>>>((uint32_t) n, (const uint32_t*) person, location, sublocation,
+                                                              time, p, h->cand_person.p, h->cand_gkey.p, h->cand_t.p,
+                                                              h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_window_finish(heros_handle h, heros_step_stats* stats)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "heros_window_transmit has not been called");
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = window_finish(h);
+    if (rc != HEROS_OK) return rc;
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    heros_step_stats st{};
+    add_window_stats(h, st);
+    fill_stats(h, h->win_before, st);
+    st.gpu_ms = ms;
     if (stats) *stats = st;
     return HEROS_OK;
 }
@@ -1236,12 +1544,13 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
     const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_inf_log, h->inf_person.n);
     if (n != h->o_inf_n)
     {
-        std::vector<uint32_t> per(n), key(n);
+        std::vector<uint32_t> per(n);
+        std::vector<uint64_t> key(n);
         std::vector<double> t(n), pp(n);
         if (n)
         {
             CU(h, cudaMemcpyAsync(per.data(), h->inf_person.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(key.data(), h->inf_key.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaMemcpyAsync(key.data(), h->inf_gkey.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
             CU(h, cudaMemcpyAsync(t.data(), h->inf_t.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
             CU(h, cudaMemcpyAsync(pp.data(), h->inf_p.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
             CU(h, cudaStreamSynchronize(h->stream));
@@ -1251,10 +1560,10 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return t[a] < t[b] || (t[a] == t[b] && per[a] < per[b]);
         });
-        h->o_inf_person.resize(n); h->o_inf_key.resize(n); h->o_inf_t.resize(n); h->o_inf_p.resize(n);
+        h->o_inf_person.resize(n); h->o_inf_gkey.resize(n); h->o_inf_t.resize(n); h->o_inf_p.resize(n);
         for (size_t i = 0; i < n; ++i)
         {
-            h->o_inf_person[i] = per[order[i]]; h->o_inf_key[i] = key[order[i]];
+            h->o_inf_person[i] = per[order[i]]; h->o_inf_gkey[i] = key[order[i]];
             h->o_inf_t[i] = t[order[i]]; h->o_inf_p[i] = pp[order[i]];
         }
         h->o_inf_n = n;
@@ -1264,12 +1573,10 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
     for (int64_t i = 0; i < m; ++i)
     {
         const size_t k = (size_t) (first + i);
-        const uint32_t key = h->o_inf_key[k];
-        const uint32_t loc = (uint32_t) (std::upper_bound(h->h_loc_base.begin(), h->h_loc_base.end(), key) -
-                                         h->h_loc_base.begin() - 1);
+        const uint64_t gkey = h->o_inf_gkey[k];  // (global location id << 16) | sub-location
         if (person) person[i] = (int32_t) h->o_inf_person[k];
-        if (location) location[i] = (int32_t) loc;
-        if (sublocation) sublocation[i] = (int16_t) (key - h->h_loc_base[loc]);
+        if (location) location[i] = (int32_t) (gkey >> 16);
+        if (sublocation) sublocation[i] = (int16_t) (gkey & 0xFFFFu);
         if (time) time[i] = h->o_inf_t[k];
         if (p) p[i] = h->o_inf_p[k];
     }
@@ -1384,7 +1691,9 @@ int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, 
 
 int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out)
 {
-    if (!h || !out || location < 0 || (uint32_t) location >= h->n_loc || sublocation < 0) return HEROS_ERR_INVALID;
+    if (!h || !out) return HEROS_ERR_INVALID;
+    location -= h->location_base;
+    if (location < 0 || (uint32_t) location >= h->n_loc || sublocation < 0) return HEROS_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
     const uint32_t key = h->h_loc_base[location] + (uint32_t) sublocation;
     if (key >= h->h_loc_base[location + 1]) return fail(h, HEROS_ERR_INVALID, "sub-location out of range");
@@ -1417,6 +1726,7 @@ int32_t heros_infect_people(heros_handle h, int32_t location, int32_t n_persons,
 {
     int32_t rc = check_ready(h);
     if (rc != HEROS_OK) return rc;
+    location -= h->location_base;
     if (location < 0 || (uint32_t) location >= h->n_loc || n_persons < 0 || n_all < 0 || (n_persons && !persons))
         return fail(h, HEROS_ERR_INVALID, "bad argument");
     const int type = h->h_loc_type[location];
@@ -1425,9 +1735,9 @@ int32_t heros_infect_people(heros_handle h, int32_t location, int32_t n_persons,
     const bool total_branch = !(infect_sub || n_sub_locations < 2);
     if (total_branch && n_all > 0 && !all_persons) return fail(h, HEROS_ERR_INVALID, "all_persons required for the total-location branch");
     for (int i = 0; i < n_persons; ++i)
-        if (persons[i] < 0 || (uint32_t) persons[i] >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
+        if ((uint32_t) persons[i] - h->person_base >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
     for (int i = 0; i < (total_branch ? n_all : 0); ++i)
-        if (all_persons[i] < 0 || (uint32_t) all_persons[i] >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
+        if ((uint32_t) all_persons[i] - h->person_base >= h->n_agents) return fail(h, HEROS_ERR_INVALID, "person id out of range");
     cudaSetDevice(h->cfg.device);
     const int cap = std::max(std::max(n_persons, n_all), 1);
     DevBuf<int32_t> d_sub, d_all, d_infectious, d_infected;
@@ -1444,7 +1754,8 @@ int32_t heros_infect_people(heros_handle h, int32_t location, int32_t n_persons,
     }
     k_infect_people<<<1, 32, 0, h->stream>>>(h->cfg.model, h->area, h->dist, psi, mu, h->cfg.seed, infect_sub,
                                              n_sub_locations, (double) h->h_loc_area[location], h->type_corr[type],
-                                             h->d_view.p, n_persons, d_sub.p, total_branch ? n_all : 0, d_all.p, now,
+                                             h->d_view.p, h->person_base, n_persons, d_sub.p, total_branch ? n_all : 0,
+                                             d_all.p, now,
                                              duration, d_infectious.p, d_infected.p, d_out.p);
     CU(h, cudaGetLastError());
     ShimOut o{};

@@ -28,9 +28,10 @@ struct alignas(16) StayRec
 {
     double tin, tout;
     uint64_t view;    // packed agent word of the person (phase at window start, exposure time, ...)
-    uint32_t person;
-    uint32_t pad;
+    uint32_t person;  // GLOBAL person id (person_base + local index for the engine's own agents)
+    uint32_t pad;     // bit 31: guest (a person of another shard, submitted for this window only); bits 0..30: its index
 };
+constexpr uint32_t REC_GUEST = 0x80000000u;
 
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
@@ -89,13 +90,15 @@ struct WindowCtx
     const PolicyChange* policy; int n_policy;
     // static tables
     const uint32_t* key_loc; const LocParam* loc_param; double* last_calc; uint32_t n_keys;
-    // agents
-    const uint64_t* view; const double* ill_end;
+    // agents (own: indexed by global id - person_base; guests: by the index in StayRec::pad)
+    const uint64_t* view; const double* ill_end; const double* guest_ill_end;
+    uint32_t person_base, n_agents;
+    const uint32_t* loc_first_key; int32_t location_base;  // for the global sub-location id of a candidate
     // the window's stays bucketed by sub-location: stays of key k are rec[seg_start[k] .. seg_start[k + 1])
     StayRec* rec;
     const uint32_t* seg_start;  // n_keys + 1 entries
     // candidates
-    uint32_t* cand_person; uint32_t* cand_key; double* cand_t; double* cand_p; uint32_t cand_cap;
+    uint32_t* cand_person; uint64_t* cand_gkey; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
     uint32_t* warp_seg; uint32_t warp_cap;           // sub-location keys queued for the warp kernel
     uint32_t* blk_seg[4]; uint32_t blk_cap;          // ... and for the four group kernels

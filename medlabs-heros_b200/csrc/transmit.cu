@@ -66,8 +66,10 @@ __device__ __forceinline__ void push_candidate(const WindowCtx& c, uint32_t pers
     const unsigned long long slot = atomicAdd(&c.ctr->n_cand, 1ull);
     if (slot < c.cand_cap)
     {
+        // global sub-location id: (global location id << 16) | sub-location index
+        const uint32_t loc = c.key_loc[key];
         c.cand_person[slot] = person;
-        c.cand_key[slot] = key;
+        c.cand_gkey[slot] = ((uint64_t) (uint32_t) (c.location_base + (int32_t) loc) << 16) | (uint64_t) (key - c.loc_first_key[loc]);
         c.cand_t[slot] = t;
         c.cand_p[slot] = p;
     }
@@ -76,10 +78,11 @@ __device__ __forceinline__ void push_candidate(const WindowCtx& c, uint32_t pers
 }
 
 // is the stay's person ill at time t, as infectPeople would see it (person.getDiseasePhase().isIll())?
-__device__ __forceinline__ bool ill_at(const WindowCtx& c, uint64_t view, uint32_t person, double t)
+__device__ __forceinline__ bool ill_at(const WindowCtx& c, const StayRec& r, double t)
 {
-    if (!phase_is_ill(view_tphase(view))) return false;
-    if (view_ends(view)) return t < c.ill_end[person];  // recovers / dies inside this window
+    if (!phase_is_ill(view_tphase(r.view))) return false;
+    if (view_ends(r.view))  // recovers / dies inside this window
+        return t < ((r.pad & REC_GUEST) ? c.guest_ill_end[r.pad & ~REC_GUEST] : c.ill_end[r.person - c.person_base]);
     return true;
 }
 
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
                 for (uint32_t j = 0; j < n; ++j)
                 {
                     const StayRec r = rec[j];
-                    if (r.tin < now && now <= r.tout && ill_at(c, r.view, r.person, now))
+                    if (r.tin < now && now <= r.tout && ill_at(c, r, now))
                         sum += area_contribution(c.area, now - (double) view_exposure(r.view));  // TArea:167-174
                 }
             }
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
                 for (uint32_t j = 0; j < n; ++j)
                 {
                     const StayRec r = rec[j];
-                    if (r.tin < now && now <= r.tout && ill_at(c, r.view, r.person, now))
+                    if (r.tin < now && now <= r.tout && ill_at(c, r, now))
                     {
                         const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(r.view));  // TDist:155-159
                         if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);                      // TDist:161-164
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
             {
                 factor = area_factor(c.area, duration, lp.denom);  // TArea:156
                 if (factor == 0.0) continue;                       // TArea:157
-                if (in_set && maybe_ill && ill_at(c, view, person, now))
+                if (in_set && maybe_ill && ill_at(c, r, now))
                     term = area_contribution(c.area, now - (double) view_exposure(view));  // TArea:167-172
             }
             else
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
                 policy_at(c, now, psi, mu);
                 factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);  // TDist:138-143
                 if (factor == 0.0) continue;                                     // TDist:144
-                if (in_set && maybe_ill && ill_at(c, view, person, now))
+                if (in_set && maybe_ill && ill_at(c, r, now))
                 {
                     const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(view));  // TDist:155-159
                     if (v_t > 0) term = dist_term(c.dist, factor, duration, v_t);                    // TDist:161-164
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                         for (int k = sub; k < n_ill; k += lpn)
                         {
                             const StayRec& s = ill_src[illl[k]];
-                            if (s.tin < now && now <= s.tout && ill_at(c, s.view, s.person, now))
+                            if (s.tin < now && now <= s.tout && ill_at(c, s, now))
                             {
                                 const double te = now - (double) view_exposure(s.view);
                                 if (MODEL == HEROS_MODEL_AREA)

@@ -137,6 +137,40 @@ class HerosEngine:
         self._check(self._lib.heros_step(self._h, float(t_until), C.byref(st)))
         return st.as_dict()
 
+    # ---- multi-GPU window phases (device pointers, e.g. torch tensors' data_ptr()) ----
+    def set_id_bases(self, person_base: int, location_base: int):
+        self._check(self._lib.heros_set_id_bases(self._h, int(person_base), int(location_base)))
+
+    def window_begin(self, t_until: float):
+        self._check(self._lib.heros_window_begin(self._h, float(t_until)))
+
+    def export_agent_words(self, n: int, person_ptr: int, word_out_ptr: int, ill_end_out_ptr: int):
+        self._check(self._lib.heros_export_agent_words(self._h, n, C.c_void_p(person_ptr), C.c_void_p(word_out_ptr),
+                                                       C.c_void_p(ill_end_out_ptr)))
+
+    def submit_guest_visits(self, n: int, person: int, word: int, ill_end: int, loc: int, sub: int, t_in: int,
+                            t_out: int):
+        self._check(self._lib.heros_submit_guest_visits_device(self._h, n, *(C.c_void_p(x) for x in
+                                                               (person, word, ill_end, loc, sub, t_in, t_out))))
+
+    def window_transmit(self):
+        self._check(self._lib.heros_window_transmit(self._h))
+
+    def export_guest_candidates(self, capacity: int, person: int, loc: int, sub: int, t: int, p: int) -> int:
+        n = C.c_int64(0)
+        self._check(self._lib.heros_export_guest_candidates(self._h, capacity, *(C.c_void_p(x) for x in
+                                                            (person, loc, sub, t, p)), C.byref(n)))
+        return n.value
+
+    def import_candidates(self, n: int, person: int, loc: int, sub: int, t: int, p: int):
+        self._check(self._lib.heros_import_candidates_device(self._h, n, *(C.c_void_p(x) for x in
+                                                             (person, loc, sub, t, p))))
+
+    def window_finish(self) -> Dict[str, float]:
+        st = _lib.StepStats()
+        self._check(self._lib.heros_window_finish(self._h, C.byref(st)))
+        return st.as_dict()
+
     # ---- outputs ----
     def infections(self, first: int = 0) -> Dict[str, np.ndarray]:
         n = C.c_int64(0)
