@@ -13,5 +13,6 @@ from .disease import (Covid19Progression, Covid19TransmissionArea, Covid19Transm
                       DiseaseTransmission, HerosModel, InfectionRecord, construct_disease_model)
 from .engine import HerosEngine  # noqa: F401
 from .policy import DiseasePolicy  # noqa: F401
+from . import sharded  # noqa: F401
 
 __version__ = "0.1.0"

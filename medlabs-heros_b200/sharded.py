@@ -1,0 +1,158 @@
+"""Sharded multi-GPU runs: one engine per GPU, geography-partitioned persons and locations.
+
+Per window every shard
+  1. runs the disease-phase state machine of its own persons                     (heros_window_begin),
+  2. sends the stays its persons spend in OTHER shards' locations, with the packed agent word of the person, to
+     the owner of the location                                                    (all-to-all #1, 40 B per stay),
+  3. evaluates every sub-location it owns, guests included                        (heros_window_transmit),
+  4. sends the successful draws on guests back to the shard that owns the person  (all-to-all #2, 26 B per candidate),
+  5. resolves earliest-draw-wins over local and returned candidates               (heros_window_finish).
+The only collectives on the data path are these two all-to-alls (NCCL over NVLink when the tensors live on GPUs);
+nothing else is exchanged, and because draws are keyed by global person id and exposure sums are formed in canonical
+order the sharded run is bit-identical to the same population on a single engine.
+
+The routing helpers are plain torch and run on CPU tensors too (gloo), which is how tests/test_sharded_host.py
+exercises them without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+GUEST_COLUMNS = (("person", torch.int32), ("word", torch.int64), ("ill_end", torch.float64), ("loc", torch.int32),
+                 ("sub", torch.int16), ("t_in", torch.float64), ("t_out", torch.float64))
+CANDIDATE_COLUMNS = (("person", torch.int32), ("loc", torch.int32), ("sub", torch.int16), ("time", torch.float64),
+                     ("p", torch.float64))
+
+
+def owner_of(ids: torch.Tensor, bases: torch.Tensor) -> torch.Tensor:
+    """Rank that owns each global id; ``bases`` = first id of every rank followed by the total (ascending)."""
+    return torch.bucketize(ids.to(torch.int64), bases[1:].to(ids.device), right=True)
+
+
+def route(columns: Dict[str, torch.Tensor], dest: torch.Tensor, world: int):
+    """Stable grouping of the rows by destination rank: (columns in destination order, rows per destination)."""
+    order = torch.sort(dest, stable=True).indices
+    counts = torch.bincount(dest, minlength=world)[:world]
+    return {k: v[order].contiguous() for k, v in columns.items()}, counts
+
+
+def split_by_counts(columns: Dict[str, torch.Tensor], counts: Sequence[int]) -> List[Dict[str, torch.Tensor]]:
+    out, start = [], 0
+    for c in counts:
+        out.append({k: v[start:start + int(c)] for k, v in columns.items()})
+        start += int(c)
+    return out
+
+
+def concat_columns(parts: List[Dict[str, torch.Tensor]], schema, device) -> Dict[str, torch.Tensor]:
+    return {k: (torch.cat([p[k] for p in parts]) if parts else torch.empty(0, dtype=dt, device=device))
+            for k, dt in schema}
+
+
+def all_to_all_rows(columns: Dict[str, torch.Tensor], send_counts: torch.Tensor, group=None):
+    """Variable-size all-to-all of row-aligned columns (torch.distributed: NCCL on GPU tensors, gloo on CPU tensors).
+    Returns (received columns, rows received per source rank)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    device = next(iter(columns.values())).device
+    send = send_counts.to(device=device, dtype=torch.int64)
+    recv = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    out = {}
+    for k, v in columns.items():
+        es = v.element_size()  # exchanged as raw bytes: every backend moves uint8, not every backend moves int16
+        buf = torch.empty(int(sum(recv_l)), dtype=v.dtype, device=device)
+        dist.all_to_all_single(buf.view(torch.uint8), v.contiguous().view(torch.uint8),
+                               output_split_sizes=[r * es for r in recv_l], input_split_sizes=[c * es for c in send_l],
+                               group=group)
+        out[k] = buf
+    return out, recv_l
+
+
+class ShardedEngine:
+    """One shard: a HerosEngine plus the routing tables.  ``person_bases`` / ``location_bases``: first global id of every
+    rank followed by the total."""
+
+    def __init__(self, engine, rank: int, world: int, person_bases, location_bases, device="cuda"):
+        self.engine, self.rank, self.world, self.device = engine, rank, world, torch.device(device)
+        self.person_bases = torch.as_tensor(person_bases, dtype=torch.int64)
+        self.location_bases = torch.as_tensor(location_bases, dtype=torch.int64)
+        engine.set_id_bases(int(self.person_bases[rank]), int(self.location_bases[rank]))
+        self.sent_stays = 0
+        self.sent_candidates = 0
+
+    # ---- phase 1: state machine, then the stays that leave the shard ----
+    def begin_and_route(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]]):
+        """remote: this shard's persons' stays in other shards' locations that are active in the window (device tensors
+        person i32, loc i32, sub i16, t_in f64, t_out f64, global ids).  Returns (columns by destination, counts)."""
+        eng = self.engine
+        eng.window_begin(t_until)
+        n = 0 if remote is None else int(remote["person"].numel())
+        word = torch.empty(n, dtype=torch.int64, device=self.device)
+        ill_end = torch.empty(n, dtype=torch.float64, device=self.device)
+        if n:
+            eng.export_agent_words(n, remote["person"].data_ptr(), word.data_ptr(), ill_end.data_ptr())
+            cols = {"person": remote["person"], "word": word, "ill_end": ill_end, "loc": remote["loc"],
+                    "sub": remote["sub"], "t_in": remote["t_in"], "t_out": remote["t_out"]}
+            dest = owner_of(remote["loc"], self.location_bases)
+        else:
+            cols = concat_columns([], GUEST_COLUMNS, self.device)
+            dest = torch.empty(0, dtype=torch.int64, device=self.device)
+        self.sent_stays += n
+        return route(cols, dest, self.world)
+
+    # ---- phase 2: guests in, every evaluation, candidates out ----
+    def transmit_and_route(self, guests: Dict[str, torch.Tensor]):
+        eng = self.engine
+        n = int(guests["person"].numel())
+        if n:
+            g = {k: guests[k].contiguous() for k, _ in GUEST_COLUMNS}
+            eng.submit_guest_visits(n, *(g[k].data_ptr() for k, _ in GUEST_COLUMNS))
+        eng.window_transmit()
+        cap = max(4096, 4 * n)
+        while True:
+            out = {k: torch.empty(cap, dtype=dt, device=self.device) for k, dt in CANDIDATE_COLUMNS}
+            try:
+                m = eng.export_guest_candidates(cap, *(out[k].data_ptr() for k, _ in CANDIDATE_COLUMNS))
+                break
+            except Exception as e:  # HEROS_ERR_CAPACITY: retry with the count the engine reported
+                if getattr(e, "code", None) != -4:
+                    raise
+                cap *= 4
+        cols = {k: v[:m] for k, v in out.items()}
+        dest = owner_of(cols["person"], self.person_bases)
+        self.sent_candidates += m
+        return route(cols, dest, self.world)
+
+    # ---- phase 3: candidates in, resolve ----
+    def finish(self, candidates: Dict[str, torch.Tensor]):
+        n = int(candidates["person"].numel())
+        if n:
+            c = {k: candidates[k].contiguous() for k, _ in CANDIDATE_COLUMNS}
+            self.engine.import_candidates(n, *(c[k].data_ptr() for k, _ in CANDIDATE_COLUMNS))
+        return self.engine.window_finish()
+
+    # ---- one window over torch.distributed ----
+    def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], group=None):
+        cols, counts = self.begin_and_route(t_until, remote)
+        guests, _ = all_to_all_rows(cols, counts, group)
+        cols, counts = self.transmit_and_route(guests)
+        cands, _ = all_to_all_rows(cols, counts, group)
+        return self.finish(cands)
+
+
+def step_window_in_process(shards: List[ShardedEngine], t_until: float, remotes: List[Optional[Dict[str, torch.Tensor]]]):
+    """The same window for several shards living in ONE process (e.g. all on one GPU): the all-to-alls become list
+    shuffles.  Used to check that a sharded run equals the unsharded one without needing several GPUs."""
+    world = len(shards)
+    dev = shards[0].device
+    out1 = [s.begin_and_route(t_until, r) for s, r in zip(shards, remotes)]
+    parts = [split_by_counts(c, n.tolist()) for c, n in out1]
+    inbox = [concat_columns([parts[src][dst] for src in range(world)], GUEST_COLUMNS, dev) for dst in range(world)]
+    out2 = [s.transmit_and_route(g) for s, g in zip(shards, inbox)]
+    parts = [split_by_counts(c, n.tolist()) for c, n in out2]
+    inbox = [concat_columns([parts[src][dst] for src in range(world)], CANDIDATE_COLUMNS, dev) for dst in range(world)]
+    return [s.finish(c) for s, c in zip(shards, inbox)]

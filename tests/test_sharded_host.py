@@ -1,0 +1,82 @@
+"""Host-side logic of the sharded (multi-GPU) path on CPU: ownership lookup, routing, and the variable-size
+all-to-all over torch.distributed with the gloo backend, world_size 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from heros_b200 import sharded
+
+
+def test_owner_of_and_route():
+    bases = torch.tensor([0, 10, 25, 40])  # three ranks: [0,10) [10,25) [25,40)
+    ids = torch.tensor([0, 9, 10, 24, 25, 39, 12], dtype=torch.int32)
+    assert sharded.owner_of(ids, bases).tolist() == [0, 0, 1, 1, 2, 2, 1]
+    cols = {"person": ids, "x": torch.arange(7, dtype=torch.float64)}
+    routed, counts = sharded.route(cols, sharded.owner_of(ids, bases), 3)
+    assert counts.tolist() == [2, 3, 2]
+    assert routed["person"].tolist() == [0, 9, 10, 24, 12, 25, 39]      # stable inside a destination
+    assert routed["x"].tolist() == [0.0, 1.0, 2.0, 3.0, 6.0, 4.0, 5.0]
+    parts = sharded.split_by_counts(routed, counts.tolist())
+    assert [p["person"].tolist() for p in parts] == [[0, 9], [10, 24, 12], [25, 39]]
+    empty = sharded.concat_columns([], sharded.CANDIDATE_COLUMNS, "cpu")
+    assert all(v.numel() == 0 for v in empty.values()) and empty["sub"].dtype == torch.int16
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank owns persons [100 r, 100 r + 100) and sends rows about persons of both ranks
+        g = torch.Generator().manual_seed(1234 + rank)
+        n = 37 + 11 * rank
+        person = torch.randint(0, 100 * world, (n,), generator=g, dtype=torch.int32)
+        cols = {"person": person, "time": person.to(torch.float64) * 0.5 + rank,
+                "sub": (person % 7).to(torch.int16)}
+        bases = torch.arange(0, 100 * (world + 1), 100)
+        routed, counts = sharded.route(cols, sharded.owner_of(person, bases), world)
+        got, recv = sharded.all_to_all_rows(routed, counts)
+        # everything received belongs to me, and sender r's rows arrive in r's order
+        assert (sharded.owner_of(got["person"], bases) == rank).all()
+        assert sum(recv) == got["person"].numel()
+        start = 0
+        for src in range(world):
+            gs = torch.Generator().manual_seed(1234 + src)
+            p_src = torch.randint(0, 100 * world, (37 + 11 * src,), generator=gs, dtype=torch.int32)
+            mine = p_src[sharded.owner_of(p_src, bases) == rank]
+            assert got["person"][start:start + recv[src]].tolist() == mine.tolist()
+            assert torch.equal(got["time"][start:start + recv[src]], mine.to(torch.float64) * 0.5 + src)
+            start += recv[src]
+        assert got["sub"].dtype == torch.int16
+        # an empty exchange must work too
+        none = {k: v[:0] for k, v in cols.items()}
+        got, recv = sharded.all_to_all_rows(none, torch.zeros(world, dtype=torch.int64))
+        assert got["person"].numel() == 0 and recv == [0] * world
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_to_all_rows_gloo_world_size_2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as m:
+        out = m.dict()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(out) == {0: 1, 1: 1}
