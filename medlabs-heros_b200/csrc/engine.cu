@@ -19,8 +19,7 @@
 #include <limits>
 #include <numeric>
 
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
+#include <cooperative_groups.h>
 
 namespace heros {
 
@@ -31,6 +30,7 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int TPB = 256;
+constexpr unsigned long long OPEN_CLOSED = 0x7ff8000000000000ull;  // t_in of an open-stay slot nobody is in (NaN)
 inline int blocks_for(size_t n, int per = TPB) { return (int) std::max<size_t>(1, (n + per - 1) / per); }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -107,10 +107,10 @@ __device__ __forceinline__ void expose_agent(const AgentArrays& A, uint32_t pers
     v = view_set(v, 8, 0xF, next_phase);
 }
 
-__global__ void __launch_bounds__(TPB) k_progress(const AgentArrays A, uint32_t n, double T1)
+// the disease-phase state machine of one agent up to T1; leaves in the packed word the phase transmission must see
+// (the one held at the start of the window) and whether / when the agent stops being ill inside the window
+__device__ __forceinline__ void progress_agent(const AgentArrays& A, uint32_t a, double T1)
 {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
     const uint64_t v0 = A.view[a];
     const uint32_t ph = view_phase(v0);
     uint64_t v = view_set(v0, 4, 0xF, ph);  // transmission of this window sees the phase held at its start
@@ -136,28 +136,54 @@ struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; 
 
 // ---- occupancy bucketing: a counting sort over the dense sub-location keys ---------------------------------------------
 // Replaces the per-location TIntSets the medlabs engine updates on every addPerson / removePerson.
-// 1. k_bucket_count   every active stay takes a ticket at its sub-location: rank = atomicAdd(count[key], 1)
-// 2. k_scan_*         seg_start = exclusive prefix sum of the counts (n_keys + 1 entries)
+// 1. k_window_open    every active stay takes a ticket at its sub-location: rank = atomicAdd(count[key], 1).  The same
+//                     pass runs the disease-phase state machine of every agent (its open stay is one of the stays) and
+//                     moves the pool stays that outlive the window into the other pool buffer (retire).
+// 2. k_scan_lookback  seg_start = exclusive prefix sum of the counts (n_keys + 1 entries), single pass
 // 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]
 // The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
 // (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
 struct GuestArrays
 {
-    const uint32_t* gid; const uint64_t* view; const uint32_t* key; const double* tin; const double* tout; uint32_t n;
+    const uint32_t* gid; const uint64_t* view; const uint32_t* key; const double* tin; const double* tout;
+    const uint32_t* rank; uint32_t n;
 };
 
-__global__ void __launch_bounds__(TPB) k_bucket_count(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
-                                                      const double* open_tin, uint32_t n_agents, GuestArrays G,
-                                                      double T1, uint32_t* count, uint32_t* rank)
+__global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32_t n_agents, double T1, PoolArrays P,
+                                                     PoolArrays keep, uint32_t n_pool, const uint32_t* open_key,
+                                                     const double* open_tin, uint32_t* count, uint32_t* rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pool + n_agents + G.n) return;
-    uint32_t key;
-    double tin;
-    if (i < n_pool) { key = P.key[i]; tin = P.tin[i]; }
-    else if (i < n_pool + n_agents) { key = open_key[i - n_pool]; tin = open_tin[i - n_pool]; }
-    else { key = G.key[i - n_pool - n_agents]; tin = G.tin[i - n_pool - n_agents]; }
-    rank[i] = (key != KEY_NONE && tin < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
+    bool kept = false;
+    uint32_t person = 0, key = KEY_NONE;
+    double tin = 0.0, tout = 0.0;
+    if (i < n_pool)
+    {
+        person = P.person[i]; key = P.key[i]; tin = P.tin[i]; tout = P.tout[i];
+        rank[i] = (key != KEY_NONE && tin < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
+        kept = key != KEY_NONE && !(tout < T1);
+    }
+    else if (i < n_pool + n_agents)
+    {
+        const uint32_t a = i - n_pool;
+        progress_agent(A, a, T1);
+        const uint32_t k = open_key[a];
+        rank[i] = (k != KEY_NONE && open_tin[a] < T1) ? atomicAdd(&count[k], 1u) : KEY_NONE;  // a closed slot holds NaN
+    }
+    // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
+    const unsigned m = __ballot_sync(0xffffffffu, kept);
+    if (m)
+    {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&A.ctr->n_keep, (unsigned long long) __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (kept)
+        {
+            const uint32_t j = (uint32_t) base + __popc(m & ((1u << lane) - 1u));
+            keep.person[j] = person; keep.key[j] = key; keep.tin[j] = tin; keep.tout[j] = tout;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
@@ -167,13 +193,12 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pool + n_agents + G.n) return;
-    const uint32_t r = rank[i];
-    if (r == KEY_NONE) return;
     StayRec o;
-    uint32_t key;
+    uint32_t key, r;
     o.pad = 0;
     if (i < n_pool)
     {
+        if ((r = rank[i]) == KEY_NONE) return;
         const uint32_t local = P.person[i];
         key = P.key[i]; o.tin = P.tin[i]; o.tout = P.tout[i];
         o.person = person_base + local;
@@ -181,6 +206,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
     }
     else if (i < n_pool + n_agents)
     {
+        if ((r = rank[i]) == KEY_NONE) return;
         const uint32_t local = i - n_pool;
         key = open_key[local];
         o.tin = open_tin[local];
@@ -191,6 +217,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
     else
     {
         const uint32_t j = i - n_pool - n_agents;
+        if ((r = G.rank[j]) == KEY_NONE) return;
         key = G.key[j]; o.tin = G.tin[j]; o.tout = G.tout[j];
         o.person = G.gid[j];
         o.view = G.view[j];
@@ -199,70 +226,43 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
     rec[seg_start[key] + r] = o;
 }
 
-// exclusive prefix sum of count[0..n) into out[0..n], out[n] = total: tile sums, scan of the tile sums, tile scans
+// Exclusive prefix sum of count[0..n) into out[0..n], out[n] = total, in ONE pass: tiles are handed out in order, every
+// tile publishes its sum and then its inclusive prefix in a 64-bit status word, and looks back over the statuses of the
+// tiles before it (decoupled look-back).  The counts are zeroed on the way (the next window starts from zero), and the
+// block that finishes last resets the status words.
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+#define SCAN_SUM (1ull << 32)
+#define SCAN_PREFIX (2ull << 32)
 
-__device__ __forceinline__ uint32_t block_reduce_add(uint32_t v, uint32_t* s_w)
+__global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t n, uint32_t* out,
+                                                       unsigned long long* status, uint32_t n_tiles, Counters* ctr)
 {
-    v = __reduce_add_sync(0xffffffffu, v);
+    __shared__ uint32_t s_w[TPB / 32];
+    __shared__ uint32_t s_tile, s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scan_tile, 1u);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    for (int w = 0; w < (int) (blockDim.x >> 5); ++w) t += s_w[w];
-    return t;
-}
-
-__global__ void __launch_bounds__(TPB) k_scan_tile_sums(const uint32_t* count, uint32_t n, uint32_t* tile_sum)
-{
-    __shared__ uint32_t s_w[32];
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) v += (base + k < n) ? count[base + k] : 0u;
-    v = block_reduce_add(v, s_w);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = v;
-}
-
-__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_sum, uint32_t n_tiles, uint32_t* out_total,
-                                                     Counters* ctr)
-{
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += blockDim.x)
-    {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_tiles ? tile_sum[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
-        }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        uint32_t off = s_carry;
-        for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) off += s_w[w];
-        if (i < n_tiles) tile_sum[i] = off + incl - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = off + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { *out_total = s_carry; ctr->n_active = s_carry; }
-}
-
-__global__ void __launch_bounds__(TPB) k_scan_apply(const uint32_t* count, uint32_t n, const uint32_t* tile_off,
-                                                    uint32_t* out)
-{
-    __shared__ uint32_t s_w[32];
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS], local = 0;
+    if (base + SCAN_ITEMS <= n)
+    {
+        const uint4 lo = *reinterpret_cast<const uint4*>(count + base), hi = *reinterpret_cast<const uint4*>(count + base + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        *reinterpret_cast<uint4*>(count + base) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(count + base + 4) = make_uint4(0, 0, 0, 0);
+    }
+    else
+    {
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? count[base + k] : 0u; local += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+        {
+            v[k] = (base + k < n) ? count[base + k] : 0u;
+            if (base + k < n) count[base + k] = 0u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) local += v[k];
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -272,85 +272,108 @@ __global__ void __launch_bounds__(TPB) k_scan_apply(const uint32_t* count, uint3
     }
     if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t run = tile_off[blockIdx.x] + incl - local;
-    for (int w = 0; w < (int) (threadIdx.x >> 5); ++w) run += s_w[w];
+    uint32_t warp_off = 0, tile_sum = 0;
+#pragma unroll
+    for (int w = 0; w < TPB / 32; ++w)
+    {
+        if (w < (int) (threadIdx.x >> 5)) warp_off += s_w[w];
+        tile_sum += s_w[w];
+    }
+    if (threadIdx.x < 32)  // warp 0 publishes the tile sum and looks back
+    {
+        volatile unsigned long long* st = status;
+        if (threadIdx.x == 0) st[tile] = (tile == 0 ? SCAN_PREFIX : SCAN_SUM) | tile_sum;
+        uint32_t excl = 0;
+        int look = (int) tile - 1;
+        while (look >= 0)
+        {
+            const int j = look - (int) threadIdx.x;
+            unsigned long long w = j >= 0 ? st[j] : SCAN_PREFIX;
+            while (__any_sync(0xffffffffu, (w >> 32) == 0)) w = j >= 0 ? st[j] : SCAN_PREFIX;  // not published yet
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+            const int stop = has_prefix ? __ffs(has_prefix) - 1 : 32;  // nearest tile whose prefix is complete
+            const uint32_t add = ((int) threadIdx.x <= stop && j >= 0) ? (uint32_t) w : 0u;
+            excl += __reduce_add_sync(0xffffffffu, add);
+            if (has_prefix) break;
+            look -= 32;
+        }
+        if (threadIdx.x == 0)
+        {
+            if (tile > 0) st[tile] = SCAN_PREFIX | (unsigned long long) (excl + tile_sum);
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_excl + warp_off + incl - local;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k)
     {
         if (base + k < n) out[base + k] = run;
         run += v[k];
     }
-}
-
-struct KeepPred
-{
-    const uint32_t* key; const double* tout; double T1;
-    __device__ bool operator()(uint32_t i) const { return key[i] != KEY_NONE && !(tout[i] < T1); }
-};
-
-__global__ void __launch_bounds__(TPB) k_retire_gather(PoolArrays src, PoolArrays dst, const uint32_t* idx,
-                                                       const uint32_t* n_keep, Counters* ctr)
-{
-    const uint32_t n = *n_keep;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    if (tile == n_tiles - 1 && threadIdx.x == TPB - 1)
     {
-        const uint32_t i = idx[j];
-        dst.person[j] = src.person[i];
-        dst.key[j] = src.key[i];
-        dst.tin[j] = src.tin[i];
-        dst.tout[j] = src.tout[i];
+        out[n] = run;  // the last thread of the last tile has seen everything
+        ctr->n_active = run;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_keep = n;
+    // the last block to finish resets the scan state for the next window
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scan_done, 1u);
+    __syncthreads();
+    if (s_tile == n_tiles - 1)
+    {
+        for (uint32_t t = threadIdx.x; t < n_tiles; t += TPB) status[t] = 0ull;
+        if (threadIdx.x == 0) { ctr->scan_tile = 0; ctr->scan_done = 0; }
+    }
 }
 
 // ---- resolve: earliest successful draw wins (ties: lowest sub-location key) -------------------------------------------
 struct CandArrays { const uint32_t* person; const uint64_t* gkey; const double* t; const double* p; uint32_t cap; };
-
-// candidates carry global person ids; the ones of other shards' persons (guests) are skipped here and sent home
-__global__ void __launch_bounds__(TPB) k_resolve_time(CandArrays C, const Counters* ctr, unsigned long long* best_t,
-                                                      uint32_t person_base, uint32_t n_agents)
-{
-    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const uint32_t local = C.person[i] - person_base;
-        if (local < n_agents) atomicMin(&best_t[local], (unsigned long long) f64_bits(C.t[i]));
-    }
-}
-
-__global__ void __launch_bounds__(TPB) k_resolve_key(CandArrays C, const Counters* ctr,
-                                                     const unsigned long long* best_t, unsigned long long* best_gkey,
-                                                     uint32_t person_base, uint32_t n_agents)
-{
-    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const uint32_t local = C.person[i] - person_base;
-        if (local < n_agents && f64_bits(C.t[i]) == best_t[local])
-            atomicMin(&best_gkey[local], (unsigned long long) C.gkey[i]);
-    }
-}
-
 struct InfLog { uint32_t* person; uint64_t* gkey; double* t; double* p; unsigned long long cap; };
 
-__global__ void __launch_bounds__(TPB) k_resolve_apply(CandArrays C, const AgentArrays A,
-                                                       const unsigned long long* best_t,
-                                                       const unsigned long long* best_gkey, uint32_t* claim, InfLog log,
-                                                       double T1, uint32_t n_agents)
+constexpr uint32_t RESOLVE_SOLO = 8192;  // up to this many candidates one block resolves everything without grid barriers
+
+// Candidates carry global person ids; the ones of other shards' persons (guests) are skipped here and sent home.
+// Four phases separated by barriers: earliest time per person, lowest sub-location among those, expose() the winner
+// (exposure time := (float) now, contract C4) and run its state machine to the end of the window, reset the scratch.
+// Launched cooperatively (the grid barrier needs every block resident).
+__global__ void __launch_bounds__(1024) k_resolve(CandArrays C, const AgentArrays A, unsigned long long* best_t,
+                                                  unsigned long long* best_gkey, uint32_t* claim, InfLog log, double T1,
+                                                  uint32_t n_agents)
 {
     const uint32_t n = (uint32_t) min((unsigned long long) C.cap, A.ctr->n_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (n == 0) return;
+    const bool solo = n <= RESOLVE_SOLO;
+    if (solo && blockIdx.x != 0) return;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t first = solo ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = solo ? blockDim.x : gridDim.x * blockDim.x;
+#define RESOLVE_BARRIER() do { if (solo) __syncthreads(); else grid.sync(); } while (0)
+    for (uint32_t i = first; i < n; i += stride)
+    {
+        const uint32_t local = C.person[i] - A.person_base;
+        if (local < n_agents) atomicMin(&best_t[local], (unsigned long long) f64_bits(C.t[i]));
+    }
+    RESOLVE_BARRIER();
+    for (uint32_t i = first; i < n; i += stride)
+    {
+        const uint32_t local = C.person[i] - A.person_base;
+        if (local < n_agents && f64_bits(C.t[i]) == __ldcg(&best_t[local]))
+            atomicMin(&best_gkey[local], (unsigned long long) C.gkey[i]);
+    }
+    RESOLVE_BARRIER();
+    for (uint32_t i = first; i < n; i += stride)
     {
         const uint32_t gid = C.person[i];
         const uint32_t person = gid - A.person_base;
         if (person >= n_agents) continue;
-        if (f64_bits(C.t[i]) != best_t[person] || C.gkey[i] != best_gkey[person]) continue;
+        if (f64_bits(C.t[i]) != __ldcg(&best_t[person]) || C.gkey[i] != __ldcg(&best_gkey[person])) continue;
         if (atomicExch(&claim[person], 1u) != 0u) continue;  // identical duplicate
         uint64_t v = A.view[person];
         if (!phase_is_susceptible(view_phase(v))) continue;
         const double t = C.t[i];
         double nt;
-        expose_agent(A, gid, v, nt, t);  // exposure time := (float) now, then expose() (contract C4)
+        expose_agent(A, gid, v, nt, t);
         double ill_end;
         run_transitions(A, gid, v, nt, T1, &ill_end);
         A.view[person] = v;
@@ -367,21 +390,16 @@ __global__ void __launch_bounds__(TPB) k_resolve_apply(CandArrays C, const Agent
             atomicOr(&A.ctr->overflow, 8u);
         atomicAdd(&A.ctr->infections, 1ull);
     }
-}
-
-__global__ void __launch_bounds__(TPB) k_resolve_reset(CandArrays C, const Counters* ctr, unsigned long long* best_t,
-                                                       unsigned long long* best_gkey, uint32_t* claim,
-                                                       uint32_t person_base, uint32_t n_agents)
-{
-    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    RESOLVE_BARRIER();
+    for (uint32_t i = first; i < n; i += stride)
     {
-        const uint32_t person = C.person[i] - person_base;
+        const uint32_t person = C.person[i] - A.person_base;
         if (person >= n_agents) continue;
         best_t[person] = BEST_NONE;
         best_gkey[person] = BEST_NONE;
         claim[person] = 0u;
     }
+#undef RESOLVE_BARRIER
 }
 
 // ---- multi-GPU: stays of this shard's persons in other shards' locations, and the way back -----------------------------
@@ -406,7 +424,8 @@ __global__ void __launch_bounds__(TPB) k_export_words(uint32_t n, const int32_t*
 
 __global__ void __launch_bounds__(TPB) k_guest_keys(uint32_t n, const int32_t* loc, const int16_t* sub, int32_t loc_base,
                                                     const uint32_t* loc_first_key, const int16_t* loc_nsub, uint32_t n_loc,
-                                                    const double* tin, const double* tout, uint32_t* key_out,
+                                                    const double* tin, const double* tout, double T1,
+                                                    uint32_t* key_out, uint32_t* count, uint32_t* rank_out,
                                                     Counters* ctr)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,7 +434,10 @@ __global__ void __launch_bounds__(TPB) k_guest_keys(uint32_t n, const int32_t* l
     const int32_t sb = sub[i];
     bool ok = l >= 0 && (uint32_t) l < n_loc && sb >= 0 && tin[i] >= 0.0 && tout[i] > tin[i];
     if (ok) ok = sb < max((int) loc_nsub[l], 1);
-    key_out[i] = ok ? loc_first_key[l] + (uint32_t) sb : KEY_NONE;
+    const uint32_t key = ok ? loc_first_key[l] + (uint32_t) sb : KEY_NONE;
+    key_out[i] = key;
+    // guests take their tickets at the sub-location when they are submitted (the window's own stays did in k_window_open)
+    rank_out[i] = (ok && tin[i] < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
     if (!ok) atomicAdd(&ctr->invalid_visits, 1u);
 }
 
@@ -457,8 +479,11 @@ __global__ void __launch_bounds__(TPB) k_import_candidates(uint32_t n, const uin
 // ---- inputs ------------------------------------------------------------------------------------------------------------
 struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub; const double* tin; const double* tout; };
 
-// pass 0: closed stays -> pool (and close the matching open stay); pass 1: open stays -> open slot of the person
-__global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, int pass, PoolArrays P, uint32_t pool_base,
+// Closed stays go to the pool; a closed stay also closes the matching open stay of its person (same t_in), an open
+// stay (t_out = +inf) becomes the open stay of its person.  One pass: closing is a compare-and-swap of the slot's t_in
+// to NaN ("nobody there"), opening overwrites key and t_in, so any interleaving of the close of the old stay and the
+// opening of the next one (t_in differs) ends with the new stay in the slot.
+__global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArrays P, uint32_t pool_base,
                                                 uint32_t* open_key, double* open_tin, const uint32_t* loc_base,
                                                 const int16_t* loc_nsub, uint32_t n_loc, uint32_t n_agents,
                                                 uint32_t person_base, int32_t loc_origin, double t_now, Counters* ctr)
@@ -474,28 +499,25 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, int pas
     const bool open = ok && !(tout < bits_f64(0x7ff0000000000000ull));
     const bool positive = ok && tout > tin;
     const uint32_t key = ok ? loc_base[loc] + (uint32_t) sub : KEY_NONE;
-    if (pass == 0)
-    {
-        uint32_t k = KEY_NONE;
-        if (ok && positive && !open)
-        {
-            k = key;
-            if (open_key[person] == key && open_tin[person] == tin) open_key[person] = KEY_NONE;
-            if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
-        }
-        else if (!ok)
-            atomicAdd(&ctr->invalid_visits, 1u);
-        P.person[pool_base + i] = ok ? (uint32_t) person : 0u;
-        P.key[pool_base + i] = k;
-        P.tin[pool_base + i] = tin;
-        P.tout[pool_base + i] = tout;
-    }
-    else if (open)
+    uint32_t k = KEY_NONE;
+    if (open)
     {
         open_key[person] = key;
         open_tin[person] = tin;
         if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
     }
+    else if (positive)
+    {
+        k = key;
+        atomicCAS((unsigned long long*) &open_tin[person], (unsigned long long) f64_bits(tin), OPEN_CLOSED);
+        if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
+    }
+    else if (!ok)
+        atomicAdd(&ctr->invalid_visits, 1u);
+    P.person[pool_base + i] = ok ? (uint32_t) person : 0u;
+    P.key[pool_base + i] = k;
+    P.tin[pool_base + i] = tin;
+    P.tout[pool_base + i] = tout;
 }
 
 __global__ void __launch_bounds__(TPB) k_expose(const AgentArrays A, uint32_t n, const int32_t* person,
@@ -651,9 +673,10 @@ struct heros_engine
     cudaStream_t stream = nullptr;
     TransmitStreams ts{};
     cudaEvent_t ev[10]{};
-    cudaEvent_t ev_bk[2]{};  // after k_bucket_count, after the prefix sum
-    double stage_ms[6]{};  // progress, bucket, transmit thread kernel, other transmit kernels, resolve, retire
-    double bucket_part_ms[3]{};  // ticket count, prefix sum, scatter
+    cudaEvent_t ev_bk[2]{};  // before / after the prefix sum
+    double stage_ms[6]{};  // window open (state machine + tickets + retire), prefix sum + scatter, transmit thread
+                           // kernel, other transmit kernels + draws, resolve, (unused)
+    double bucket_part_ms[3]{};  // (unused), prefix sum, scatter
     int n_sm = 148;
     double t_now = 0.0;
 
@@ -687,7 +710,7 @@ struct heros_engine
     int32_t location_base = 0;  // global id of location 0
 
     // guests: stays of other shards' persons in this shard's locations, valid for the window in progress
-    DevBuf<uint32_t> g_gid, g_key;
+    DevBuf<uint32_t> g_gid, g_key, g_rank;
     DevBuf<uint64_t> g_view;
     DevBuf<double> g_ill_end, g_tin, g_tout;
     uint32_t n_guest = 0;
@@ -704,9 +727,10 @@ struct heros_engine
     uint32_t n_pool = 0;
 
     // window buffers
-    DevBuf<uint32_t> bk_count, bk_rank, seg_start, tile_sum, keep_idx, d_nsel;
+    DevBuf<uint32_t> bk_count, bk_rank, seg_start;
+    DevBuf<unsigned long long> scan_status;
     DevBuf<StayRec> rec;
-    DevBuf<uint8_t> cub_temp;
+    int resolve_grid = 0;  // blocks of the cooperative k_resolve launch
 
     // candidates, logs
     DevBuf<uint32_t> cand_person;
@@ -718,7 +742,8 @@ struct heros_engine
     DevBuf<uint8_t> tr_phase;
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> warp_seg, blk_seg[4];
+    DevBuf<uint32_t> sub_seg[2], blk_seg[4], draw_person, draw_key;
+    DevBuf<double> draw_t, draw_p;
     DevBuf<unsigned long long> huge_off;
     DevBuf<unsigned char> scratch;
 
@@ -790,13 +815,6 @@ int32_t sync_counters(heros_handle h)
 }
 
 
-__global__ void k_zero_window(Counters* c)
-{
-    c->n_cand = 0; c->n_warp = 0; c->n_blk[0] = c->n_blk[1] = c->n_blk[2] = c->n_blk[3] = 0; c->scratch_top = 0;
-    c->n_keep = 0; c->n_seg = 0; c->n_active = 0;
-    for (int a = 0; a < 4; ++a) for (int b = 0; b < 16; ++b) c->dbg_clk[a][b] = 0;
-}
-
 int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
 
 int32_t check_ready(heros_handle h)
@@ -813,20 +831,33 @@ int32_t check_ready(heros_handle h)
 }
 
 // A window [T0, T1) runs in three phases so that a multi-GPU host can exchange stays and candidate infections between
-// them: begin (disease-phase state machine; agent words final for the window) -> [guests in] -> transmit (bucketing +
-// every evaluation; candidates out / in) -> finish (resolve, retire).  heros_step runs the three back to back.
+// them: begin (disease-phase state machine + tickets of the shard's own stays + retire; agent words final for the
+// window) -> [guests in] -> transmit (prefix sum, scatter, every evaluation; candidates out / in) -> finish (resolve).
+// heros_step runs the three back to back: 11 launches per window.
 int32_t window_begin(heros_handle h, double T1)
 {
     cudaStream_t s = h->stream;
+    const uint32_t N = h->n_agents, n_pool = h->n_pool, n_keys = h->n_keys;
+    const int cur = h->pool_cur, oth = cur ^ 1;
     h->win_T0 = h->t_now;
     h->win_T1 = T1;
     h->win_launches = 0;
     h->n_guest = 0;
+    h->win_n_pool = n_pool;
+    if (h->bk_count.n < (size_t) n_keys + 1)
+    {
+        CU(h, h->bk_count.ensure((size_t) n_keys + 1));
+        CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, s));  // k_scan_lookback leaves it zeroed from then on
+    }
+    CU(h, h->bk_rank.ensure((size_t) n_pool + N));
+    { const int32_t rc_ = ensure_pool(h, oth, std::max<size_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
     CU(h, cudaEventRecord(h->ev[2], s));
-    k_zero_window<<<1, 1, 0, s>>>(h->d_ctr.p);
-    // 1. disease-phase state machine
-    k_progress<<<blocks_for(h->n_agents), TPB, 0, s>>>(agent_arrays(h), h->n_agents, T1);
-    h->win_launches += 2;
+    CU(h, cudaMemsetAsync(&h->d_ctr.p->n_cand, 0, sizeof(Counters) - offsetof(Counters, n_cand), s));
+    // 1. disease-phase state machine, tickets, retire
+    k_window_open<<<blocks_for((size_t) n_pool + N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur),
+                                                                  pool_arrays(h, oth), n_pool, h->d_open_key.p,
+                                                                  h->d_open_tin.p, h->bk_count.p, h->bk_rank.p);
+    h->win_launches += 1;
     CU(h, cudaEventRecord(h->ev[3], s));
     CU(h, cudaGetLastError());
     h->win_state = 1;
@@ -838,37 +869,40 @@ int32_t window_transmit(heros_handle h)
     cudaStream_t s = h->stream;
     const double T0 = h->win_T0, T1 = h->win_T1;
     const uint32_t N = h->n_agents;
-    const uint32_t n_pool = h->n_pool;
+    const uint32_t n_pool = h->win_n_pool;
     const uint32_t n_total = n_pool + N + h->n_guest;
     int& launches = h->win_launches;
-    h->win_n_pool = n_pool;
 
-    // 2-4. occupancy bucketing: counting sort of the window's stays over the dense sub-location keys
+    // 2-3. bucket offsets and the scatter into bucket order
     const uint32_t n_keys = h->n_keys;
     const uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
-    CU(h, h->bk_count.ensure((size_t) n_keys + 1)); CU(h, h->seg_start.ensure((size_t) n_keys + 2));
-    CU(h, h->tile_sum.ensure((size_t) n_tiles + 1));
-    CU(h, h->bk_rank.ensure(n_total)); CU(h, h->rec.ensure(n_total));
+    CU(h, h->seg_start.ensure((size_t) n_keys + 2));
+    if (h->scan_status.n < n_tiles)
+    {
+        CU(h, h->scan_status.ensure(n_tiles));
+        CU(h, cudaMemsetAsync(h->scan_status.p, 0, h->scan_status.n * 8, s));
+    }
+    CU(h, h->rec.ensure(n_total));
     const PoolArrays P = pool_arrays(h, h->pool_cur);
-    const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->n_guest};
-    CU(h, cudaMemsetAsync(h->bk_count.p, 0, (size_t) n_keys * 4, s));
-    k_bucket_count<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, G, T1,
-                                                       h->bk_count.p, h->bk_rank.p);
+    const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->g_rank.p, h->n_guest};
     CU(h, cudaEventRecord(h->ev_bk[0], s));
-    k_scan_tile_sums<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p);
-    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_sum.p, n_tiles, h->seg_start.p + n_keys, h->d_ctr.p);
-    k_scan_apply<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->tile_sum.p, h->seg_start.p);
+    k_scan_lookback<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->seg_start.p, h->scan_status.p, n_tiles, h->d_ctr.p);
     CU(h, cudaEventRecord(h->ev_bk[1], s));
     k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, G,
                                                          h->person_base, h->bk_rank.p, h->seg_start.p, h->d_view.p,
                                                          h->rec.p);
-    launches += 6;
+    launches += 2;
 
-    // 5. transmission
+    // 4. transmission
     const size_t list_cap = (size_t) n_total / 32 + 16;
-    CU(h, h->warp_seg.ensure((size_t) n_total / 8 + 16));
+    const size_t occupied_cap = std::min<size_t>(n_keys, n_total) + 16;
+    CU(h, h->sub_seg[0].ensure(occupied_cap));
+    CU(h, h->sub_seg[1].ensure((size_t) n_total / 8 + 16));
     for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
+    const size_t draw_cap = (size_t) n_total + (1u << 20);
+    CU(h, h->draw_person.ensure(draw_cap)); CU(h, h->draw_key.ensure(draw_cap));
+    CU(h, h->draw_t.ensure(draw_cap)); CU(h, h->draw_p.ensure(draw_cap));
     CU(h, h->scratch.ensure(std::min<size_t>(128 * (size_t) n_total + (1u << 20), (size_t) 4 << 30)));
 
     WindowCtx c{};
@@ -881,10 +915,13 @@ int32_t window_transmit(heros_handle h)
     c.rec = h->rec.p; c.seg_start = h->seg_start.p;
     c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
-    c.warp_seg = h->warp_seg.p; c.warp_cap = (uint32_t) h->warp_seg.n;
+    for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
+    c.sub_cap = (uint32_t) std::min(h->sub_seg[0].n, h->sub_seg[1].n);
     for (int k = 0; k < 4; ++k) c.blk_seg[k] = h->blk_seg[k].p;
     c.blk_cap = (uint32_t) h->blk_seg[0].n;
     for (int k = 1; k < 4; ++k) c.blk_cap = (uint32_t) std::min<size_t>(c.blk_cap, h->blk_seg[k].n);
+    c.draw_person = h->draw_person.p; c.draw_key = h->draw_key.p; c.draw_t = h->draw_t.p; c.draw_p = h->draw_p.p;
+    c.draw_cap = std::min(std::min(h->draw_person.n, h->draw_key.n), std::min(h->draw_t.n, h->draw_p.n));
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
@@ -899,66 +936,51 @@ int32_t window_transmit(heros_handle h)
 int32_t window_finish(heros_handle h)
 {
     cudaStream_t s = h->stream;
-    const double T1 = h->win_T1;
-    const uint32_t N = h->n_agents;
-    const uint32_t n_pool = h->win_n_pool;
-    const int cur = h->pool_cur, oth = cur ^ 1;
+    double T1 = h->win_T1;
+    uint32_t N = h->n_agents;
     int& launches = h->win_launches;
-    const AgentArrays A = agent_arrays(h);
+    AgentArrays A = agent_arrays(h);
 
-    // 6. resolve: earliest successful draw per person wins
-    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
-    const InfLog log{h->inf_person.p, h->inf_gkey.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
-    const int rg = h->n_sm * 2;
-    k_resolve_time<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->person_base, N);
-    k_resolve_key<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->person_base, N);
-    k_resolve_apply<<<rg, TPB, 0, s>>>(C, A, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, log, T1, N);
-    k_resolve_reset<<<rg, TPB, 0, s>>>(C, h->d_ctr.p, h->d_best_t.p, h->d_best_key.p, h->d_claim.p, h->person_base, N);
-    launches += 4;
-    CU(h, cudaEventRecord(h->ev[7], s));
-
-    // 7. retire the stays that ended before T1 (stays submitted after the transmit phase belong to later windows)
-    if (n_pool > 0)
+    // 5. resolve: earliest successful draw per person wins
+    CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    InfLog log{h->inf_person.p, h->inf_gkey.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
+    unsigned long long* best_t = h->d_best_t.p;
+    unsigned long long* best_key = h->d_best_key.p;
+    uint32_t* claim = h->d_claim.p;
+    if (h->resolve_grid == 0)
     {
-        const PoolArrays P = pool_arrays(h, cur);
-        CU(h, h->keep_idx.ensure(h->n_pool));
-        { const int32_t rc_ = ensure_pool(h, oth, h->n_pool, false); if (rc_ != HEROS_OK) return rc_; }
-        thrust::counting_iterator<uint32_t> iota(0);
-        KeepPred keep{P.key, P.tout, T1};
-        size_t temp_keep = 0;
-        CU(h, cub::DeviceSelect::If(nullptr, temp_keep, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) h->n_pool, keep, s));
-        CU(h, h->cub_temp.ensure(temp_keep + 256));
-        size_t tb = h->cub_temp.n;
-        CU(h, cub::DeviceSelect::If(h->cub_temp.p, tb, iota, h->keep_idx.p, h->d_nsel.p + 1, (int) h->n_pool, keep, s));
-        k_retire_gather<<<h->n_sm * 4, TPB, 0, s>>>(P, pool_arrays(h, oth), h->keep_idx.p, h->d_nsel.p + 1, h->d_ctr.p);
-        launches += 3;
+        int per_sm = 0;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, 1024, 0));
+        if (per_sm < 1) return fail(h, HEROS_ERR_CUDA, "k_resolve does not fit on an SM");
+        h->resolve_grid = h->n_sm;
     }
-    CU(h, cudaEventRecord(h->ev[8], s));
+    void* args[] = {&C, &A, &best_t, &best_key, &claim, &log, &T1, &N};
+    CU(h, cudaLaunchCooperativeKernel((const void*) k_resolve, dim3(h->resolve_grid), dim3(1024), args, 0, s));
+    launches += 1;
+    CU(h, cudaEventRecord(h->ev[7], s));
     CU(h, cudaGetLastError());
     int32_t rc = sync_counters(h);
     if (rc != HEROS_OK) return rc;
-    if (n_pool > 0)
+    // the stays that outlive the window were moved to the other pool buffer by k_window_open
+    h->n_pool = (uint32_t) h->h_ctr->n_keep;
+    h->pool_cur ^= 1;
     {
-        h->n_pool = (uint32_t) h->h_ctr->n_keep;
-        h->pool_cur = oth;
-    }
-    {
-        // ev[2] start, [3] after progress, [4] after bucketing, ts.fork after k_transmit_thread, [6] after the joined
-        // warp / group kernels, [7] after resolve, [8] after retire.  (With a multi-GPU host the intervals also contain
-        // the time the engine waited for the exchanges.)
-        cudaEvent_t marks[7] = {h->ev[2], h->ev[3], h->ev[4], h->ts.fork, h->ev[6], h->ev[7], h->ev[8]};
-        for (int k = 0; k < 6; ++k)
+        // ev[2] start, [3] after k_window_open, [4] after bucketing, ts.fork after k_transmit_thread, [6] after the joined
+        // sub-warp / group kernels, [7] after resolve.  (With a multi-GPU host the intervals also contain the time the
+        // engine waited for the exchanges.)
+        cudaEvent_t marks[6] = {h->ev[2], h->ev[3], h->ev[4], h->ts.fork, h->ev[6], h->ev[7]};
+        for (int k = 0; k < 5; ++k)
         {
             float ms = 0.f;
             CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
             h->stage_ms[k] += ms;
         }
-        cudaEvent_t bk[4] = {h->ev[3], h->ev_bk[0], h->ev_bk[1], h->ev[4]};
-        for (int k = 0; k < 3; ++k)
+        cudaEvent_t bk[3] = {h->ev_bk[0], h->ev_bk[1], h->ev[4]};
+        for (int k = 0; k < 2; ++k)
         {
             float ms = 0.f;
             CU(h, cudaEventElapsedTime(&ms, bk[k], bk[k + 1]));
-            h->bucket_part_ms[k] += ms;
+            h->bucket_part_ms[k + 1] += ms;
         }
     }
     h->win_state = 0;
@@ -1039,7 +1061,6 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
     if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = cudaMallocHost(&h->h_ctr, sizeof(Counters))) != cudaSuccess) return bail("pinned counters", e);
-    if ((e = h->d_nsel.ensure(4)) != cudaSuccess) return bail("nsel", e);
     if ((e = h->d_policy.ensure(16)) != cudaSuccess) return bail("policy", e);
     if ((e = h->d_prog.ensure(1)) != cudaSuccess) return bail("prog", e);
     *out = h;
@@ -1059,13 +1080,14 @@ int32_t heros_destroy(heros_handle h)
     {
         h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
     }
-    h->bk_count.release(); h->bk_rank.release(); h->tile_sum.release(); h->rec.release();
-    h->seg_start.release(); h->keep_idx.release(); h->d_nsel.release(); h->cub_temp.release(); h->cand_person.release();
+    h->bk_count.release(); h->bk_rank.release(); h->scan_status.release(); h->rec.release();
+    h->seg_start.release(); h->g_rank.release(); h->cand_person.release();
     h->cand_gkey.release(); h->cand_t.release();
     h->cand_p.release(); h->inf_person.release(); h->inf_gkey.release(); h->tr_person.release(); h->inf_t.release();
     h->g_gid.release(); h->g_key.release(); h->g_view.release(); h->g_ill_end.release(); h->g_tin.release();
     h->g_tout.release(); h->d_nguest_cand.release();
-    h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->warp_seg.release();
+    h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->sub_seg[0].release(); h->sub_seg[1].release();
+    h->draw_person.release(); h->draw_key.release(); h->draw_t.release(); h->draw_p.release();
     for (auto& b : h->blk_seg) b.release();
     h->huge_off.release(); h->scratch.release();
     h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
@@ -1289,17 +1311,17 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
 static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc,
                                   const int16_t* sub, const double* tin, const double* tout)
 {
+    if (h->win_state != 0)
+        return fail(h, HEROS_ERR_INVALID, "stays cannot be submitted while a window opened by heros_window_begin is in progress");
     if ((uint64_t) h->n_pool + (uint64_t) n + h->n_agents >= 0xFFFFFFF0ull)
         return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
     int32_t rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + n, true);
     if (rc != HEROS_OK) return rc;
     const SubmitIn in{person, loc, sub, tin, tout};
     const PoolArrays P = pool_arrays(h, h->pool_cur);
-    for (int pass = 0; pass < 2; ++pass)
-        k_submit<<<blocks_for(n), TPB, 0, h->stream>>>(in, (uint32_t) n, pass, P, h->n_pool, h->d_open_key.p,
-                                                       h->d_open_tin.p, h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc,
-                                                       h->n_agents, h->person_base, h->location_base, h->t_now,
-                                                       h->d_ctr.p);
+    k_submit<<<blocks_for(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
+                                                   h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc, h->n_agents,
+                                                   h->person_base, h->location_base, h->t_now, h->d_ctr.p);
     CU(h, cudaGetLastError());
     h->n_pool += (uint32_t) n;
     return HEROS_OK;
@@ -1455,6 +1477,7 @@ int32_t heros_submit_guest_visits_device(heros_handle h, int64_t n, const int32_
     cudaSetDevice(h->cfg.device);
     const size_t tot = (size_t) h->n_guest + (size_t) n, off = h->n_guest;
     CU(h, h->g_gid.ensure(tot, true, h->stream)); CU(h, h->g_key.ensure(tot, true, h->stream));
+    CU(h, h->g_rank.ensure(tot, true, h->stream));
     CU(h, h->g_view.ensure(tot, true, h->stream)); CU(h, h->g_ill_end.ensure(tot, true, h->stream));
     CU(h, h->g_tin.ensure(tot, true, h->stream)); CU(h, h->g_tout.ensure(tot, true, h->stream));
     cudaStream_t s = h->stream;
@@ -1464,7 +1487,8 @@ int32_t heros_submit_guest_visits_device(heros_handle h, int64_t n, const int32_
     CU(h, cudaMemcpyAsync(h->g_tin.p + off, t_in, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
     CU(h, cudaMemcpyAsync(h->g_tout.p + off, t_out, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
     k_guest_keys<<<blocks_for(n), TPB, 0, s>>>((uint32_t) n, location, sublocation, h->location_base, h->d_loc_base.p,
-                                               h->d_loc_nsub.p, h->n_loc, t_in, t_out, h->g_key.p + off, h->d_ctr.p);
+                                               h->d_loc_nsub.p, h->n_loc, t_in, t_out, h->win_T1, h->g_key.p + off,
+                                               h->bk_count.p, h->g_rank.p + off, h->d_ctr.p);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(s));
     h->n_guest += (uint32_t) n;

@@ -35,29 +35,31 @@ constexpr uint32_t REC_GUEST = 0x80000000u;
 
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
-// device-side counters of one engine (zeroed per heros_step call, except the log cursors)
+// device-side counters of one engine.  The block from `n_cand` on is zeroed at the start of every window.
 struct Counters
 {
     unsigned long long evaluations, draws, near_ties, infections, transitions;
     unsigned long long big_stays;    // stays of the sub-locations handed to the group kernels
-    unsigned long long n_cand;       // candidate infections of the current window
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log
-    unsigned long long n_warp;       // segments handed to the warp kernel in the current window
+    unsigned int overflow;           // bit 0 cand, 1 scratch, 2 transition log, 3 infection log
+    unsigned int invalid_visits;     // rejected by heros_submit_visits
+    unsigned int late_visits;        // t_in before the engine time
+    unsigned int pad;
+    long long phase_counts[8];
+    // ---- per window ----
+    unsigned long long n_cand;       // candidate infections of the current window (first field of the window block)
+    unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
     unsigned long long n_blk[4];     // segments handed to the group kernels (<= 256 / 1024 / 8192 events in shared
                                      // memory, larger ones in global scratch)
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
     unsigned long long n_active;     // active stays of the current window
-    unsigned int overflow;           // bit 0 cand, 1 scratch, 2 transition log, 3 infection log
-    unsigned int invalid_visits;     // rejected by heros_submit_visits
-    unsigned int late_visits;        // t_in before the engine time
-    unsigned int pad;
-    long long phase_counts[8];
+    unsigned long long n_draw;       // (stay, evaluation) pairs in the draw list
+    unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
     unsigned long long dbg_clk[4][16];  // HEROS_FLAG_PHASE_CLOCKS: max cycles per phase of k_transmit_group, per class
 };
-
 template <typename T>
 struct DevBuf
 {
@@ -100,8 +102,10 @@ struct WindowCtx
     // candidates
     uint32_t* cand_person; uint64_t* cand_gkey; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
-    uint32_t* warp_seg; uint32_t warp_cap;           // sub-location keys queued for the warp kernel
+    uint32_t* sub_seg[2]; uint32_t sub_cap;          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
     uint32_t* blk_seg[4]; uint32_t blk_cap;          // ... and for the four group kernels
+    // (stay, evaluation) pairs queued by the group kernels for k_draw
+    uint32_t* draw_person; uint32_t* draw_key; double* draw_t; double* draw_p; unsigned long long draw_cap;
     unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[3]
     unsigned char* scratch; unsigned long long scratch_cap;
     uint32_t flags;

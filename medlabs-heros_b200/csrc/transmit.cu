@@ -9,15 +9,18 @@
 // calculated evaluation is >= the threshold, over the occupants S(t-) = { stays : t_in < t <= t_out }.
 //
 // Input: the window's stays sorted by sub-location key (one contiguous segment per occupied sub-location).
-//   k_transmit_thread : one THREAD per segment of <= 32 stays.  Where nobody can be infected (no ill or no
-//                       susceptible occupant -- the vast majority) only lastCalculation has to advance, which needs
-//                       just the two latest event times; otherwise segments of <= 8 stays are evaluated in place and
-//                       larger ones are queued for the warp kernel.  Segments of > 32 stays are queued for the block
-//                       kernels.
-//   k_transmit_warp   : one warp per queued segment (9..32 stays), lane i holds stay i, shuffles + REDUX
+//   k_transmit_thread : one THREAD per segment of <= 32 stays streams its records once.  Where nobody can be infected
+//                       (no ill or no susceptible occupant -- the vast majority) only lastCalculation has to advance,
+//                       which needs just the two latest event times; the other segments are queued for the sub-warp
+//                       kernels, segments of > 32 stays for the group kernels.
+//   k_transmit_sub    : 8 or 32 lanes per queued segment (<= 8 / 9..32 stays): the lanes walk the chain of calculated
+//                       evaluations together (REDUX), then every lane computes ONE evaluation of the chain -- the long
+//                       dependent fp64 chains (sqrt, exp) of up to 32 evaluations run side by side -- then lane = stay
+//                       for the draws
 //   k_transmit_group  : one warp or block per segment of > 32 stays: its events bucketed by time in shared memory, the
 //                       chain of calculated evaluations by successor search + pointer doubling, exposure sums per
-//                       evaluation, then per stay the draws of exactly the evaluations it was present at
+//                       evaluation, then per stay the (stay, evaluation) pairs with p > 0 go to the draw list
+//   k_draw            : the Philox draws of the draw list, spread evenly over the whole GPU
 // Output: candidate infections (person, key, time, p); engine.cu keeps the earliest per person.
 #include "engine.cuh"
 
@@ -26,21 +29,11 @@ namespace heros {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int THREAD_SLOW_MAX = 8;  // largest segment a single thread evaluates itself
+constexpr int THREAD_SLOW_MAX = 8;  // largest segment handled by 8 lanes (four per warp) in k_transmit_sub
 constexpr int BLOCK_P_CAP = 2048;   // evaluations per segment the shared-memory block kernels keep probabilities for
 
 __device__ __forceinline__ double pos_inf() { return bits_f64(0x7ff0000000000000ull); }
 __device__ __forceinline__ double neg_inf() { return bits_f64(0xfff0000000000000ull); }
-
-// min over the warp of non-negative doubles (or +inf): their bit patterns order like unsigned integers
-__device__ __forceinline__ double warp_min_time(double v)
-{
-    const uint64_t b = f64_bits(v);
-    const uint32_t hi = (uint32_t) (b >> 32), lo = (uint32_t) b;
-    const uint32_t mhi = __reduce_min_sync(FULL, hi);
-    const uint32_t mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
-    return bits_f64(((uint64_t) mhi << 32) | mlo);
-}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -95,6 +88,30 @@ __device__ __forceinline__ void draw_and_push(const WindowCtx& c, Local& st, uin
     st.draws++;
     if (fabs(u - p) < 1e-13) st.near++;
     if (u < p) push_candidate(c, person, key, t, p);
+}
+
+// (stay, evaluation) pairs of the group kernels: appended to the draw list, one atomic per warp; when the list is full
+// the draw is made on the spot
+__device__ __forceinline__ void emit_draw(const WindowCtx& c, Local& st, bool active, uint32_t person, uint32_t key,
+                                          double t, double p)
+{
+    const unsigned m = __ballot_sync(FULL, active);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&c.ctr->n_draw, (unsigned long long) __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (!active) return;
+    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot < c.draw_cap)
+    {
+        c.draw_person[slot] = person;
+        c.draw_key[slot] = key;
+        c.draw_t[slot] = t;
+        c.draw_p[slot] = p;
+    }
+    else
+        draw_and_push(c, st, person, key, t, p);
 }
 
 __device__ __forceinline__ void flush_stats(const WindowCtx& c, Local st, int lane)
@@ -169,7 +186,6 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    Local st;
     unsigned occupied = 0, big = 0;
 
     for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
@@ -205,9 +221,8 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
                 atomicOr(&c.ctr->overflow, 2u);
             continue;
         }
-        StayRec* rec = c.rec + a;
-        const double L0 = c.last_calc[key];
-        // pass 1: who is here, and the two latest events
+        const StayRec* rec = c.rec + a;
+        // who is here, and the two latest events
         bool any_ill = false, any_sus = false;
         Top2 top;
         top.init();
@@ -226,91 +241,18 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         if (!need_eval && !exact)
         {
             double L;
-            if (advance_only(top, L0, thr, L))
+            if (advance_only(top, c.last_calc[key], thr, L))
             {
                 c.last_calc[key] = L;
                 continue;
             }
         }
-        if (n > THREAD_SLOW_MAX)
-        {
-            const unsigned long long slot = atomicAdd(&c.ctr->n_warp, 1ull);
-            if (slot < c.warp_cap) c.warp_seg[slot] = key;
-            else atomicOr(&c.ctr->overflow, 2u);
-            continue;
-        }
-        if (need_eval)  // canonical order (insertion sort in place, n <= 8)
-            for (uint32_t i = 1; i < n; ++i)
-            {
-                const StayRec r = rec[i];
-                uint32_t j = i;
-                while (j > 0 && stay_before(r.person, r.tin, rec[j - 1].person, rec[j - 1].tin)) { rec[j] = rec[j - 1]; --j; }
-                if (j != i) rec[j] = r;
-            }
-        // walk the chain of calculated evaluations sequentially
-        const LocParam lp = c.loc_param[c.key_loc[key]];
-        double L = L0, done = neg_inf();
-        for (;;)
-        {
-            double now = pos_inf();
-            for (uint32_t j = 0; j < n; ++j)
-            {
-                const double tout = rec[j].tout;
-                if (tout >= c.T0 && tout < c.T1 && tout > done && !(tout - L < thr) && tout < now) now = tout;
-                if (both)
-                {
-                    const double tin = rec[j].tin;
-                    if (tin >= c.T0 && tin < c.T1 && tin > done && !(tin - L < thr) && tin < now) now = tin;
-                }
-            }
-            if (!(now < pos_inf())) break;
-            const double duration = now - L;
-            L = now;
-            done = now;
-            st.evaluations++;
-            if (!need_eval) continue;
-            double factor, sum = 0.0;
-            if (MODEL == HEROS_MODEL_AREA)
-            {
-                factor = area_factor(c.area, duration, lp.denom);  // TArea:156
-                if (factor == 0.0) continue;                       // TArea:157
-                for (uint32_t j = 0; j < n; ++j)
-                {
-                    const StayRec r = rec[j];
-                    if (r.tin < now && now <= r.tout && ill_at(c, r, now))
-                        sum += area_contribution(c.area, now - (double) view_exposure(r.view));  // TArea:167-174
-                }
-            }
-            else
-            {
-                int head_count = 0;
-                for (uint32_t j = 0; j < n; ++j) head_count += (rec[j].tin < now && now <= rec[j].tout);
-                double psi, mu;
-                policy_at(c, now, psi, mu);
-                factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);  // TDist:138-143
-                if (factor == 0.0) continue;                                     // TDist:144
-                for (uint32_t j = 0; j < n; ++j)
-                {
-                    const StayRec r = rec[j];
-                    if (r.tin < now && now <= r.tout && ill_at(c, r, now))
-                    {
-                        const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(r.view));  // TDist:155-159
-                        if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);                      // TDist:161-164
-                    }
-                }
-            }
-            double p;
-            if (!probability<MODEL>(factor, sum, p) || !(p > 0)) continue;
-            for (uint32_t j = 0; j < n; ++j)
-            {
-                const StayRec r = rec[j];
-                if (r.tin < now && now <= r.tout && phase_is_susceptible(view_tphase(r.view)))
-                    draw_and_push(c, st, r.person, key, now, p);  // TArea:190 / TDist:181
-            }
-        }
-        if (L != L0) c.last_calc[key] = L;
+        // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
+        const int which = n > THREAD_SLOW_MAX ? 1 : 0;
+        const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
+        if (slot < c.sub_cap) c.sub_seg[which][slot] = key;
+        else atomicOr(&c.ctr->overflow, 2u);
     }
-    flush_stats(c, st, threadIdx.x & 31);
     occupied = __reduce_add_sync(FULL, occupied);
     big = __reduce_add_sync(FULL, big);
     if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
@@ -318,102 +260,171 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// one warp per queued sub-location of 9..32 stays, lane i holds stay i (in canonical order)
+// S = 8 or 32 lanes per queued sub-location (<= 8 / 9..32 stays); lane i of the group holds stay i (canonical order)
 // ------------------------------------------------------------------------------------------------------------------
-template <int MODEL>
-__global__ void __launch_bounds__(256) k_transmit_warp(const WindowCtx c)
+template <int MODEL, int S>
+__global__ void __launch_bounds__(256) k_transmit_sub(const WindowCtx c)
 {
+    constexpr int GPW = 32 / S;  // groups per warp
     __shared__ StayRec s_rec[8][32];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane / S, gl = lane % S, g0 = g * S;
+    const unsigned gmask = S == 32 ? FULL : (((1u << S) - 1u) << g0);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n_list = (uint32_t) min((unsigned long long) c.warp_cap, c.ctr->n_warp);
+    constexpr int WHICH = S == 8 ? 0 : 1;
+    const uint32_t n_list = (uint32_t) min((unsigned long long) c.sub_cap, c.ctr->n_sub[WHICH]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
+    const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
+    StayRec* my = &s_rec[wib][g0];
     Local st;
 
-    for (uint32_t w = warp; w < n_list; w += n_warps)
+    for (uint32_t w0 = warp * GPW; w0 < n_list; w0 += n_warps * GPW)
     {
-        const uint32_t key = c.warp_seg[w];
-        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
-        const uint32_t n = b - a;
-        const bool have = (uint32_t) lane < n;
+        const uint32_t w = w0 + g;
+        const bool valid = w < n_list;
+        uint32_t key = 0, a = 0, n = 0;
+        if (valid)
+        {
+            key = c.sub_seg[WHICH][w];
+            a = c.seg_start[key];
+            n = c.seg_start[key + 1] - a;
+        }
+        const bool have = (uint32_t) gl < n;
         StayRec r;
         r.tin = pos_inf(); r.tout = neg_inf(); r.view = 0; r.person = 0xFFFFFFFFu; r.pad = 0;
-        if (have) r = c.rec[a + lane];
-        const bool need_eval = __any_sync(FULL, have && phase_is_ill(view_tphase(r.view))) &&
-                               __any_sync(FULL, have && phase_is_susceptible(view_tphase(r.view)));
-        if (need_eval)
+        if (have) r = c.rec[a + gl];
         {
             // canonical order: lane <- stay with that rank by (person, t_in); empty lanes sort last
             int rank = 0;
-            for (int j = 0; j < 32; ++j)
+#pragma unroll
+            for (int j = 0; j < S; ++j)
             {
-                const uint32_t pj = __shfl_sync(FULL, r.person, j);
-                const double tj = __shfl_sync(FULL, r.tin, j);
-                rank += (stay_before(pj, tj, r.person, r.tin) || (pj == r.person && tj == r.tin && j < lane)) ? 1 : 0;
+                const uint32_t pj = __shfl_sync(FULL, r.person, g0 + j);
+                const double tj = __shfl_sync(FULL, r.tin, g0 + j);
+                rank += (stay_before(pj, tj, r.person, r.tin) || (pj == r.person && tj == r.tin && j < gl)) ? 1 : 0;
             }
             __syncwarp();
-            s_rec[threadIdx.x >> 5][rank] = r;
+            my[rank] = r;
             __syncwarp();
-            r = s_rec[threadIdx.x >> 5][lane];
-            __syncwarp();
+            r = my[gl];  // my[0..S) keeps the group's stays for the evaluations below
         }
-        const double tin = r.tin, tout = r.tout;
-        const uint64_t view = r.view;
-        const uint32_t person = r.person;
-        const bool here = person != 0xFFFFFFFFu;
-        const LocParam lp = c.loc_param[c.key_loc[key]];
-        double L = c.last_calc[key];
+        const uint32_t tph = view_tphase(r.view);
+        const bool here = r.person != 0xFFFFFFFFu;
+        const bool susceptible = here && phase_is_susceptible(tph);
+        const unsigned ill_b = __ballot_sync(FULL, here && phase_is_ill(tph)), sus_b = __ballot_sync(FULL, susceptible);
+        const bool need_eval = (ill_b & gmask) != 0 && (sus_b & gmask) != 0;
+        LocParam lp;
+        lp.area_sub = lp.denom = 1.0;
+        double L = 0.0;
+        if (valid) { lp = c.loc_param[c.key_loc[key]]; L = c.last_calc[key]; }
         const double L_in = L;
         // movement events of this window that can trigger an evaluation
-        double e_in = (c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT && tin >= c.T0 && tin < c.T1) ? tin : pos_inf();
-        double e_out = (tout >= c.T0 && tout < c.T1) ? tout : pos_inf();
-        const bool susceptible = here && phase_is_susceptible(view_tphase(view));
-        const bool maybe_ill = here && phase_is_ill(view_tphase(view));
+        double e_in = (both && r.tin >= c.T0 && r.tin < c.T1) ? r.tin : pos_inf();
+        double e_out = (r.tout >= c.T0 && r.tout < c.T1) ? r.tout : pos_inf();
 
         for (;;)
         {
-            // next evaluation: the earliest event whose time since the last calculation is not below the threshold
-            const double c_in = !(e_in - L < thr) ? e_in : pos_inf();
-            const double c_out = !(e_out - L < thr) ? e_out : pos_inf();
-            const double now = warp_min_time(c_in < c_out ? c_in : c_out);
-            if (!(now < pos_inf())) break;
-            const double duration = now - L;
-            L = now;
-            st.evaluations += (lane == 0);
-            if (e_in <= now) e_in = pos_inf();
-            if (e_out <= now) e_out = pos_inf();
-            if (!need_eval) continue;
-
-            const bool in_set = tin < now && now <= tout;  // present during the interval that ends at `now`
-            double factor, term = 0.0;
-            if (MODEL == HEROS_MODEL_AREA)
+            // 1. the lanes walk the next (up to) S links of the chain together: the next evaluation is the earliest
+            //    event whose time since the last calculation is not below the threshold.  Lane k keeps evaluation k.
+            double my_now = pos_inf(), my_dur = 0.0;
+            int n_ev = 0;
+#pragma unroll 1
+            for (int k = 0; k < S; ++k)
             {
-                factor = area_factor(c.area, duration, lp.denom);  // TArea:156
-                if (factor == 0.0) continue;                       // TArea:157
-                if (in_set && maybe_ill && ill_at(c, r, now))
-                    term = area_contribution(c.area, now - (double) view_exposure(view));  // TArea:167-172
-            }
-            else
-            {
-                const int head_count = __popc(__ballot_sync(FULL, in_set));  // personsInSublocation.size()
-                double psi, mu;
-                policy_at(c, now, psi, mu);
-                factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);  // TDist:138-143
-                if (factor == 0.0) continue;                                     // TDist:144
-                if (in_set && maybe_ill && ill_at(c, r, now))
+                const double c_in = !(e_in - L < thr) ? e_in : pos_inf();
+                const double c_out = !(e_out - L < thr) ? e_out : pos_inf();
+                const double cand = c_in < c_out ? c_in : c_out;
+                const uint64_t cb = f64_bits(cand);
+                const uint32_t hi = (uint32_t) (cb >> 32), lo = (uint32_t) cb;
+                const uint32_t mhi = __reduce_min_sync(gmask, hi);
+                const uint32_t mlo = __reduce_min_sync(gmask, hi == mhi ? lo : 0xffffffffu);
+                const double now = bits_f64(((uint64_t) mhi << 32) | mlo);
+                const bool got = now < pos_inf();
+                if (__all_sync(FULL, !got)) break;
+                if (got)
                 {
-                    const double v_t = dist_viral_load(c.dist, now - (double) view_exposure(view));  // TDist:155-159
-                    if (v_t > 0) term = dist_term(c.dist, factor, duration, v_t);                    // TDist:161-164
+                    if (gl == k) { my_now = now; my_dur = now - L; }
+                    L = now;
+                    ++n_ev;
+                    if (e_in <= now) e_in = pos_inf();
+                    if (e_out <= now) e_out = pos_inf();
                 }
             }
-            double p;
-            if (!probability<MODEL>(factor, warp_sum(term), p)) continue;
-            if (p > 0 && in_set && susceptible) draw_and_push(c, st, person, key, now, p);  // TArea:190 / TDist:181
+            if (gl == 0) st.evaluations += (unsigned long long) n_ev;
+            if (!__any_sync(FULL, n_ev > 0)) break;
+            if (__any_sync(FULL, need_eval && n_ev > 0))
+            {
+                // 2. every lane computes its own evaluation over the stays of its group (TArea:155-182 / TDist:137-173)
+                double p = 0.0;
+                if (need_eval && my_now < pos_inf())
+                {
+                    double factor;
+                    if (MODEL == HEROS_MODEL_AREA)
+                        factor = area_factor(c.area, my_dur, lp.denom);  // TArea:156
+                    else
+                    {
+                        int head_count = 0;  // personsInSublocation.size()
+#pragma unroll
+                        for (int j = 0; j < S; ++j) head_count += (my[j].tin < my_now && my_now <= my[j].tout) ? 1 : 0;
+                        double psi, mu;
+                        policy_at(c, my_now, psi, mu);
+                        factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);  // TDist:138-143
+                    }
+                    if (factor != 0.0)  // TArea:157 / TDist:144
+                    {
+                        double sum = 0.0;
+#pragma unroll 1
+                        for (int j = 0; j < S; ++j)
+                        {
+                            if (!((ill_b >> (g0 + j)) & 1u)) continue;
+                            const StayRec q = my[j];
+                            if (q.tin < my_now && my_now <= q.tout && ill_at(c, q, my_now))
+                            {
+                                const double te = my_now - (double) view_exposure(q.view);
+                                if (MODEL == HEROS_MODEL_AREA)
+                                    sum += area_contribution(c.area, te);  // TArea:167-172
+                                else
+                                {
+                                    const double v_t = dist_viral_load(c.dist, te);                  // TDist:155-159
+                                    if (v_t > 0) sum += dist_term(c.dist, factor, my_dur, v_t);      // TDist:161-164
+                                }
+                            }
+                        }
+                        if (!(probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
+                    }
+                }
+                // 3. draws: lane = stay again, against the evaluations of the batch it was present at
+                const unsigned pos = __ballot_sync(FULL, p > 0.0);
+#pragma unroll 1
+                for (int k = 0; k < S; ++k)
+                {
+                    unsigned at_k = 0;  // any group whose k-th evaluation has p > 0 ?
+#pragma unroll
+                    for (int q = 0; q < GPW; ++q) at_k |= (pos >> (q * S + k)) & 1u;
+                    if (!at_k) continue;
+                    const double now_k = __shfl_sync(FULL, my_now, g0 + k);
+                    const double p_k = __shfl_sync(FULL, p, g0 + k);
+                    if (p_k > 0 && susceptible && r.tin < now_k && now_k <= r.tout)
+                        draw_and_push(c, st, r.person, key, now_k, p_k);  // TArea:190 / TDist:181
+                }
+            }
+            if (__all_sync(FULL, n_ev < S)) break;
         }
-        if (lane == 0 && L != L_in) c.last_calc[key] = L;
+        if (valid && gl == 0 && L != L_in) c.last_calc[key] = L;
+        __syncwarp();  // the staged stays are overwritten by the next sub-location
     }
     flush_stats(c, st, lane);
+}
+
+// the Philox draws of the (stay, evaluation) pairs the group kernels queued
+__global__ void __launch_bounds__(256) k_draw(const WindowCtx c)
+{
+    const unsigned long long n = min((unsigned long long) c.draw_cap, c.ctr->n_draw);
+    Local st;
+    for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x)
+        draw_and_push(c, st, c.draw_person[i], c.draw_key[i], c.draw_t[i], c.draw_p[i]);
+    flush_stats(c, st, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -923,13 +934,18 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
             }
             clk = t_;
         }
-        // 8. draws: every susceptible stay against exactly the evaluations it was present at, (t_in, t_out].  Each lane
-        //    finds the evaluation range of one stay; the warp then deals out the (stay, evaluation) pairs evenly
-        if (G > 32)
-        {
-            if (tid == 0) s_w[32] = 0;
-            __syncthreads();
-        }
+        // 8. draws: every susceptible stay against exactly the evaluations with p > 0 it was present at, (t_in, t_out].
+        //    The evaluations with p > 0 are compacted first (ja = how many precede each evaluation, jb = their list;
+        //    the tables of steps 5-6 are dead); nothing is left to do when nobody ill was ever present.
+        const int n_pos = group_exclusive_scan<G>(R, [&](int r) { return pr[r] > 0 ? 1 : 0; }, ja, s_w);
+        if (n_pos == 0) { gsync<G>(); continue; }
+        if (tid == 0) ja[R] = (idx_t) n_pos;
+        for (int r = tid; r < R; r += G)
+            if (pr[r] > 0) jb[ja[r]] = (idx_t) r;
+        if (G > 32 && tid == 0) s_w[32] = 0;
+        gsync<G>();
+        //    Each lane finds the range of one stay; the warp then deals out the (stay, evaluation) pairs evenly and
+        //    appends them to the draw list (k_draw makes the draws, spread over the whole GPU).
         for (int v0 = (tid & ~31);; v0 += G)
         {
             const int lane = tid & 31;
@@ -951,10 +967,10 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                     person = s.person;
                     int l = 0, h = R;  // first evaluation with time > t_in
                     while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
-                    lo = l;
+                    lo = (int) ja[l];
                     h = R;             // first evaluation with time > t_out
                     while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
-                    cnt = l - lo;
+                    cnt = (int) ja[l] - lo;
                 }
             }
             int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
@@ -979,11 +995,10 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                 const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
                 const int s_lo = __shfl_sync(FULL, lo, src);
                 const uint32_t s_person = __shfl_sync(FULL, person, src);
-                if (pi < total)
-                {
-                    const int r = s_lo + (pi - (s_incl - s_cnt));
-                    if (pr[r] > 0) draw_and_push(c, st, s_person, key, ev_t[node[r]], pr[r]);
-                }
+                const bool active = pi < total;
+                int r = 0;
+                if (active) r = (int) jb[s_lo + (pi - (s_incl - s_cnt))];
+                emit_draw(c, st, active, s_person, key, active ? ev_t[node[r]] : 0.0, active ? pr[r] : 0.0);
             }
         }
         gsync<G>();
@@ -1019,13 +1034,15 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     k_transmit_group<MODEL, 3><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
     k_transmit_group<MODEL, 1><<<n_sm * 6, 256, smem1, ts.aux[1]>>>(c);
     k_transmit_group<MODEL, 0><<<n_sm * 8, 128, smem0, ts.aux[2]>>>(c);
-    k_transmit_warp<MODEL><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
+    k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
+    k_transmit_sub<MODEL, 8><<<n_sm * 8, 256, 0, s>>>(c);
     for (int k = 0; k < 4; ++k)
     {
         cudaEventRecord(ts.join[k], ts.aux[k]);
         cudaStreamWaitEvent(s, ts.join[k], 0);
     }
-    launches += 6;
+    k_draw<<<n_sm * 4, 256, 0, s>>>(c);
+    launches += 8;
 }
 
 void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
