@@ -149,81 +149,152 @@ struct GuestArrays
     const uint32_t* rank; uint32_t n;
 };
 
+// These kernels are bound by the latency of dependent memory operations (load key -> atomic -> store) and by the
+// number of L2 sectors they touch, not by DRAM bandwidth, so every thread handles IPT items whose loads and atomics
+// are in flight together.  Blocks [0, pool_blocks) take the pool stays, the following ones the agents (then the guests).
+constexpr int IPT = 4;
+inline int item_blocks(size_t n) { return (int) ((n + (size_t) TPB * IPT - 1) / ((size_t) TPB * IPT)); }
+
 __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32_t n_agents, double T1, PoolArrays P,
-                                                     PoolArrays keep, uint32_t n_pool, const uint32_t* open_key,
-                                                     const double* open_tin, uint32_t* count, uint32_t* rank)
+                                                     PoolArrays keep, uint32_t n_pool, uint32_t pool_blocks,
+                                                     const uint32_t* __restrict__ open_key,
+                                                     const double* __restrict__ open_tin, uint32_t* count,
+                                                     uint32_t* __restrict__ rank)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool kept = false;
-    uint32_t person = 0, key = KEY_NONE;
-    double tin = 0.0, tout = 0.0;
-    if (i < n_pool)
+    if (blockIdx.x < pool_blocks)
     {
-        person = P.person[i]; key = P.key[i]; tin = P.tin[i]; tout = P.tout[i];
-        rank[i] = (key != KEY_NONE && tin < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
-        kept = key != KEY_NONE && !(tout < T1);
-    }
-    else if (i < n_pool + n_agents)
-    {
-        const uint32_t a = i - n_pool;
-        progress_agent(A, a, T1);
-        const uint32_t k = open_key[a];
-        rank[i] = (k != KEY_NONE && open_tin[a] < T1) ? atomicAdd(&count[k], 1u) : KEY_NONE;  // a closed slot holds NaN
-    }
-    // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
-    const unsigned m = __ballot_sync(0xffffffffu, kept);
-    if (m)
-    {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(&A.ctr->n_keep, (unsigned long long) __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (kept)
+        const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
+        uint32_t person[IPT], key[IPT], r[IPT];
+        double tin[IPT], tout[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
         {
-            const uint32_t j = (uint32_t) base + __popc(m & ((1u << lane) - 1u));
-            keep.person[j] = person; keep.key[j] = key; keep.tin[j] = tin; keep.tout[j] = tout;
+            const uint32_t i = base + k * TPB;
+            key[k] = KEY_NONE; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0;
+            if (i < n_pool) { key[k] = P.key[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; person[k] = P.person[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+            r[k] = (key[k] != KEY_NONE && tin[k] < T1) ? atomicAdd(&count[key[k]], 1u) : KEY_NONE;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t i = base + k * TPB;
+            if (i < n_pool) rank[i] = r[k];
+        }
+        // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const bool kept = key[k] != KEY_NONE && !(tout[k] < T1);
+            const unsigned m = __ballot_sync(0xffffffffu, kept);
+            if (m)
+            {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                unsigned long long at = 0;
+                if (lane == leader) at = atomicAdd(&A.ctr->n_keep, (unsigned long long) __popc(m));
+                at = __shfl_sync(0xffffffffu, at, leader);
+                if (kept)
+                {
+                    const uint32_t j = (uint32_t) at + __popc(m & ((1u << lane) - 1u));
+                    keep.person[j] = person[k]; keep.key[j] = key[k]; keep.tin[j] = tin[k]; keep.tout[j] = tout[k];
+                }
+            }
+        }
+    }
+    else
+    {
+        const uint32_t base = (blockIdx.x - pool_blocks) * (TPB * IPT) + threadIdx.x;
+        uint32_t key[IPT], r[IPT];
+        double tin[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t a = base + k * TPB;
+            key[k] = KEY_NONE; tin[k] = 0.0;
+            if (a < n_agents) { key[k] = open_key[a]; tin[k] = open_tin[a]; }  // a closed slot holds NaN
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+            r[k] = (key[k] != KEY_NONE && tin[k] < T1) ? atomicAdd(&count[key[k]], 1u) : KEY_NONE;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t a = base + k * TPB;
+            if (a < n_agents) rank[n_pool + a] = r[k];
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t a = base + k * TPB;
+            if (a < n_agents) progress_agent(A, a, T1);
         }
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, const uint32_t* open_key,
-                                                        const double* open_tin, uint32_t n_agents, GuestArrays G,
-                                                        uint32_t person_base, const uint32_t* rank,
-                                                        const uint32_t* seg_start, const uint64_t* view, StayRec* rec)
+__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, uint32_t pool_blocks,
+                                                        const uint32_t* __restrict__ open_key,
+                                                        const double* __restrict__ open_tin, uint32_t n_agents,
+                                                        uint32_t agent_blocks, GuestArrays G, uint32_t person_base,
+                                                        const uint32_t* __restrict__ rank,
+                                                        const uint32_t* __restrict__ seg_start,
+                                                        const uint64_t* __restrict__ view, StayRec* __restrict__ rec)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pool + n_agents + G.n) return;
-    StayRec o;
-    uint32_t key, r;
-    o.pad = 0;
-    if (i < n_pool)
+    uint32_t r[IPT], key[IPT], person[IPT], pad[IPT], dst[IPT];
+    double tin[IPT], tout[IPT];
+    uint64_t vw[IPT];
+    if (blockIdx.x < pool_blocks)
     {
-        if ((r = rank[i]) == KEY_NONE) return;
-        const uint32_t local = P.person[i];
-        key = P.key[i]; o.tin = P.tin[i]; o.tout = P.tout[i];
-        o.person = person_base + local;
-        o.view = view[local];
+        const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t i = base + k * TPB;
+            r[k] = KEY_NONE; key[k] = 0; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = 0;
+            if (i < n_pool) { r[k] = rank[i]; key[k] = P.key[i]; person[k] = P.person[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; }
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            vw[k] = 0; dst[k] = 0;
+            if (r[k] != KEY_NONE) { vw[k] = view[person[k]]; dst[k] = seg_start[key[k]] + r[k]; person[k] += person_base; }
+        }
     }
-    else if (i < n_pool + n_agents)
+    else if (blockIdx.x < pool_blocks + agent_blocks)
     {
-        if ((r = rank[i]) == KEY_NONE) return;
-        const uint32_t local = i - n_pool;
-        key = open_key[local];
-        o.tin = open_tin[local];
-        o.tout = bits_f64(0x7ff0000000000000ull);
-        o.person = person_base + local;
-        o.view = view[local];
+        const uint32_t base = (blockIdx.x - pool_blocks) * (TPB * IPT) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t a = base + k * TPB;
+            r[k] = KEY_NONE; key[k] = 0; person[k] = person_base + a; tin[k] = 0.0; pad[k] = 0; vw[k] = 0;
+            tout[k] = bits_f64(0x7ff0000000000000ull);
+            if (a < n_agents) { r[k] = rank[n_pool + a]; key[k] = open_key[a]; tin[k] = open_tin[a]; vw[k] = view[a]; }
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
     }
     else
     {
-        const uint32_t j = i - n_pool - n_agents;
-        if ((r = G.rank[j]) == KEY_NONE) return;
-        key = G.key[j]; o.tin = G.tin[j]; o.tout = G.tout[j];
-        o.person = G.gid[j];
-        o.view = G.view[j];
-        o.pad = REC_GUEST | j;
+        const uint32_t base = (blockIdx.x - pool_blocks - agent_blocks) * (TPB * IPT) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const uint32_t j = base + k * TPB;
+            r[k] = KEY_NONE; key[k] = 0; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = REC_GUEST | j; vw[k] = 0;
+            if (j < G.n) { r[k] = G.rank[j]; key[k] = G.key[j]; person[k] = G.gid[j]; tin[k] = G.tin[j]; tout[k] = G.tout[j]; vw[k] = G.view[j]; }
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
     }
-    rec[seg_start[key] + r] = o;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+        if (r[k] != KEY_NONE)
+        {
+            StayRec o;
+            o.tin = tin[k]; o.tout = tout[k]; o.view = vw[k]; o.person = person[k]; o.pad = pad[k];
+            rec[dst[k]] = o;
+        }
 }
 
 // Exclusive prefix sum of count[0..n) into out[0..n], out[n] = total, in ONE pass: tiles are handed out in order, every
@@ -236,7 +307,8 @@ constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
 #define SCAN_PREFIX (2ull << 32)
 
 __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t n, uint32_t* out,
-                                                       unsigned long long* status, uint32_t n_tiles, Counters* ctr)
+                                                       unsigned long long* status, uint32_t n_tiles, Counters* ctr,
+                                                       const BigLists big)
 {
     __shared__ uint32_t s_w[TPB / 32];
     __shared__ uint32_t s_tile, s_excl;
@@ -262,7 +334,11 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
         }
     }
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) local += v[k];
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+    {
+        local += v[k];
+        if (v[k] > 32) queue_big(big, ctr, base + k, v[k]);  // a few thousand of half a million sub-locations
+    }
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -484,40 +560,77 @@ struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub;
 // to NaN ("nobody there"), opening overwrites key and t_in, so any interleaving of the close of the old stay and the
 // opening of the next one (t_in differs) ends with the new stay in the slot.
 __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArrays P, uint32_t pool_base,
-                                                uint32_t* open_key, double* open_tin, const uint32_t* loc_base,
-                                                const int16_t* loc_nsub, uint32_t n_loc, uint32_t n_agents,
+                                                uint32_t* open_key, double* open_tin,
+                                                const uint32_t* __restrict__ loc_base,
+                                                const int16_t* __restrict__ loc_nsub, uint32_t n_loc, uint32_t n_agents,
                                                 uint32_t person_base, int32_t loc_origin, double t_now, Counters* ctr)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t person = (int32_t) ((uint32_t) in.person[i] - person_base), loc = in.loc[i] - loc_origin;
-    const int32_t sub = in.sub[i];
-    const double tin = in.tin[i], tout = in.tout[i];
-    bool ok = person >= 0 && (uint32_t) person < n_agents && loc >= 0 && (uint32_t) loc < n_loc && sub >= 0 &&
-              tin >= 0.0 && tin < bits_f64(0x7ff0000000000000ull) && tout == tout;
-    if (ok) ok = sub < max((int) loc_nsub[loc], 1);
-    const bool open = ok && !(tout < bits_f64(0x7ff0000000000000ull));
-    const bool positive = ok && tout > tin;
-    const uint32_t key = ok ? loc_base[loc] + (uint32_t) sub : KEY_NONE;
-    uint32_t k = KEY_NONE;
-    if (open)
+    const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
+    const double inf = bits_f64(0x7ff0000000000000ull);
+    int32_t person[IPT], loc[IPT], sub[IPT];
+    double tin[IPT], tout[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
     {
-        open_key[person] = key;
-        open_tin[person] = tin;
-        if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
+        const uint32_t i = base + k * TPB;
+        person[k] = -1; loc[k] = -1; sub[k] = 0; tin[k] = 0.0; tout[k] = 0.0;
+        if (i < n)
+        {
+            person[k] = (int32_t) ((uint32_t) in.person[i] - person_base);
+            loc[k] = in.loc[i] - loc_origin;
+            sub[k] = in.sub[i]; tin[k] = in.tin[i]; tout[k] = in.tout[i];
+        }
     }
-    else if (positive)
+    bool ok[IPT];
+    int nsub[IPT];
+    uint32_t key[IPT];
+    double cur_tin[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
     {
-        k = key;
-        atomicCAS((unsigned long long*) &open_tin[person], (unsigned long long) f64_bits(tin), OPEN_CLOSED);
-        if (tin < t_now) atomicAdd(&ctr->late_visits, 1u);
+        ok[k] = person[k] >= 0 && (uint32_t) person[k] < n_agents && loc[k] >= 0 && (uint32_t) loc[k] < n_loc &&
+                sub[k] >= 0 && tin[k] >= 0.0 && tin[k] < inf && tout[k] == tout[k];
+        nsub[k] = ok[k] ? (int) loc_nsub[loc[k]] : 0;
+        key[k] = ok[k] ? loc_base[loc[k]] : 0u;
+        cur_tin[k] = ok[k] ? open_tin[person[k]] : 0.0;  // the open stay this one may close
     }
-    else if (!ok)
-        atomicAdd(&ctr->invalid_visits, 1u);
-    P.person[pool_base + i] = ok ? (uint32_t) person : 0u;
-    P.key[pool_base + i] = k;
-    P.tin[pool_base + i] = tin;
-    P.tout[pool_base + i] = tout;
+    unsigned late = 0, invalid = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+    {
+        const uint32_t i = base + k * TPB;
+        if (i >= n) continue;
+        const bool good = ok[k] && sub[k] < max(nsub[k], 1);
+        const bool open = good && !(tout[k] < inf);
+        const bool positive = good && tout[k] > tin[k];
+        uint32_t pk = KEY_NONE;
+        if (open)
+        {
+            open_key[person[k]] = key[k] + (uint32_t) sub[k];
+            open_tin[person[k]] = tin[k];
+            late += tin[k] < t_now;
+        }
+        else if (positive)
+        {
+            pk = key[k] + (uint32_t) sub[k];
+            if (f64_bits(cur_tin[k]) == f64_bits(tin[k]))
+                atomicCAS((unsigned long long*) &open_tin[person[k]], (unsigned long long) f64_bits(tin[k]), OPEN_CLOSED);
+            late += tin[k] < t_now;
+        }
+        else if (!good)
+            ++invalid;
+        P.person[pool_base + i] = good ? (uint32_t) person[k] : 0u;
+        P.key[pool_base + i] = pk;
+        P.tin[pool_base + i] = tin[k];
+        P.tout[pool_base + i] = tout[k];
+    }
+    late = __reduce_add_sync(0xffffffffu, late);
+    invalid = __reduce_add_sync(0xffffffffu, invalid);
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (late) atomicAdd(&ctr->late_visits, late);
+        if (invalid) atomicAdd(&ctr->invalid_visits, invalid);
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_expose(const AgentArrays A, uint32_t n, const int32_t* person,
@@ -854,9 +967,11 @@ int32_t window_begin(heros_handle h, double T1)
     CU(h, cudaEventRecord(h->ev[2], s));
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_cand, 0, sizeof(Counters) - offsetof(Counters, n_cand), s));
     // 1. disease-phase state machine, tickets, retire
-    k_window_open<<<blocks_for((size_t) n_pool + N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur),
-                                                                  pool_arrays(h, oth), n_pool, h->d_open_key.p,
-                                                                  h->d_open_tin.p, h->bk_count.p, h->bk_rank.p);
+    const int pool_blocks = item_blocks(n_pool);
+    k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur),
+                                                               pool_arrays(h, oth), n_pool, (uint32_t) pool_blocks,
+                                                               h->d_open_key.p, h->d_open_tin.p, h->bk_count.p,
+                                                               h->bk_rank.p);
     h->win_launches += 1;
     CU(h, cudaEventRecord(h->ev[3], s));
     CU(h, cudaGetLastError());
@@ -885,15 +1000,6 @@ int32_t window_transmit(heros_handle h)
     CU(h, h->rec.ensure(n_total));
     const PoolArrays P = pool_arrays(h, h->pool_cur);
     const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->g_rank.p, h->n_guest};
-    CU(h, cudaEventRecord(h->ev_bk[0], s));
-    k_scan_lookback<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->seg_start.p, h->scan_status.p, n_tiles, h->d_ctr.p);
-    CU(h, cudaEventRecord(h->ev_bk[1], s));
-    k_bucket_scatter<<<blocks_for(n_total), TPB, 0, s>>>(P, n_pool, h->d_open_key.p, h->d_open_tin.p, N, G,
-                                                         h->person_base, h->bk_rank.p, h->seg_start.p, h->d_view.p,
-                                                         h->rec.p);
-    launches += 2;
-
-    // 4. transmission
     const size_t list_cap = (size_t) n_total / 32 + 16;
     const size_t occupied_cap = std::min<size_t>(n_keys, n_total) + 16;
     CU(h, h->sub_seg[0].ensure(occupied_cap));
@@ -905,6 +1011,28 @@ int32_t window_transmit(heros_handle h)
     CU(h, h->draw_t.ensure(draw_cap)); CU(h, h->draw_p.ensure(draw_cap));
     CU(h, h->scratch.ensure(std::min<size_t>(128 * (size_t) n_total + (1u << 20), (size_t) 4 << 30)));
 
+    BigLists big{};
+    for (int k = 0; k < 4; ++k) big.blk_seg[k] = h->blk_seg[k].p;
+    big.blk_cap = (uint32_t) h->blk_seg[0].n;
+    for (int k = 1; k < 4; ++k) big.blk_cap = (uint32_t) std::min<size_t>(big.blk_cap, h->blk_seg[k].n);
+    big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
+    big.both = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
+    big.need_enters = big.both || h->cfg.model == HEROS_MODEL_DISTANCE;
+    {
+        const double thr = h->cfg.model == HEROS_MODEL_AREA ? h->area.threshold : h->dist.threshold;
+        big.r_window = thr > 0 ? (T1 - T0) / thr + 2.0 : std::numeric_limits<double>::infinity();
+    }
+    CU(h, cudaEventRecord(h->ev_bk[0], s));
+    k_scan_lookback<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->seg_start.p, h->scan_status.p, n_tiles, h->d_ctr.p,
+                                            big);
+    CU(h, cudaEventRecord(h->ev_bk[1], s));
+    const int pool_blocks = item_blocks(n_pool), agent_blocks = item_blocks(N);
+    k_bucket_scatter<<<pool_blocks + agent_blocks + item_blocks(h->n_guest), TPB, 0, s>>>(
+        P, n_pool, (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p, N, (uint32_t) agent_blocks, G,
+        h->person_base, h->bk_rank.p, h->seg_start.p, h->d_view.p, h->rec.p);
+    launches += 2;
+
+    // 4. transmission
     WindowCtx c{};
     c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
     c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
@@ -918,8 +1046,7 @@ int32_t window_transmit(heros_handle h)
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
     c.sub_cap = (uint32_t) std::min(h->sub_seg[0].n, h->sub_seg[1].n);
     for (int k = 0; k < 4; ++k) c.blk_seg[k] = h->blk_seg[k].p;
-    c.blk_cap = (uint32_t) h->blk_seg[0].n;
-    for (int k = 1; k < 4; ++k) c.blk_cap = (uint32_t) std::min<size_t>(c.blk_cap, h->blk_seg[k].n);
+    c.blk_cap = big.blk_cap;
     c.draw_person = h->draw_person.p; c.draw_key = h->draw_key.p; c.draw_t = h->draw_t.p; c.draw_p = h->draw_p.p;
     c.draw_cap = std::min(std::min(h->draw_person.n, h->draw_key.n), std::min(h->draw_t.n, h->draw_p.n));
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
@@ -965,10 +1092,10 @@ int32_t window_finish(heros_handle h)
     h->n_pool = (uint32_t) h->h_ctr->n_keep;
     h->pool_cur ^= 1;
     {
-        // ev[2] start, [3] after k_window_open, [4] after bucketing, ts.fork after k_transmit_thread, [6] after the joined
+        // ev[2] start, [3] after k_window_open, [4] after bucketing, ts.mid after k_transmit_thread, [6] after the joined
         // sub-warp / group kernels, [7] after resolve.  (With a multi-GPU host the intervals also contain the time the
         // engine waited for the exchanges.)
-        cudaEvent_t marks[6] = {h->ev[2], h->ev[3], h->ev[4], h->ts.fork, h->ev[6], h->ev[7]};
+        cudaEvent_t marks[6] = {h->ev[2], h->ev[3], h->ev[4], h->ts.mid, h->ev[6], h->ev[7]};
         for (int k = 0; k < 5; ++k)
         {
             float ms = 0.f;
@@ -1055,6 +1182,7 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     for (auto& a : h->ts.aux)
         if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaEventCreate(&h->ts.fork)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreate(&h->ts.mid)) != cudaSuccess) return bail("event", e);
     for (auto& j : h->ts.join)
         if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -1097,6 +1225,7 @@ int32_t heros_destroy(heros_handle h)
     for (auto& ev : h->ev_bk) if (ev) cudaEventDestroy(ev);
     for (auto& a : h->ts.aux) if (a) cudaStreamDestroy(a);
     if (h->ts.fork) cudaEventDestroy(h->ts.fork);
+    if (h->ts.mid) cudaEventDestroy(h->ts.mid);
     for (auto& j : h->ts.join) if (j) cudaEventDestroy(j);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1319,7 +1448,7 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     if (rc != HEROS_OK) return rc;
     const SubmitIn in{person, loc, sub, tin, tout};
     const PoolArrays P = pool_arrays(h, h->pool_cur);
-    k_submit<<<blocks_for(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
+    k_submit<<<item_blocks(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
                                                    h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc, h->n_agents,
                                                    h->person_base, h->location_base, h->t_now, h->d_ctr.p);
     CU(h, cudaGetLastError());
@@ -1733,6 +1862,7 @@ int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
     int32_t rc = sync_counters(h);
     if (rc != HEROS_OK) return rc;
     memcpy(clocks, h->h_ctr->dbg_clk, sizeof(h->h_ctr->dbg_clk));
+    for (int k = 0; k < 4; ++k) clocks[k * 16 + 15] = h->h_ctr->n_blk[k];  // sub-locations per class, last window
     return HEROS_OK;
 }
 

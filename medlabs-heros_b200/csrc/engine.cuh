@@ -112,7 +112,43 @@ struct WindowCtx
     Counters* ctr;
 };
 
+// Sub-locations of > 32 stays go to the group kernels, by the number of events of the sub-location and the bound on
+// its evaluations: class 0 / 1 / 2 keep <= 256 / 1024 / 8192 events in shared memory, class 3 works in global scratch.
+// The lists are filled by the prefix-sum kernel (it sees every bucket size), so the group kernels can start as soon as
+// the stays are in bucket order, side by side with the kernel that streams the small sub-locations.
+constexpr int BLOCK_P_CAP = 2048;  // evaluations per segment the shared-memory group kernels keep probabilities for
+struct BigLists
+{
+    uint32_t* blk_seg[4]; uint32_t blk_cap;
+    unsigned long long* huge_off; unsigned long long scratch_cap;
+    int need_enters, both;  // enter events are needed (distance model head counts / ENTER_AND_EXIT trigger)
+    double r_window;        // (T1 - T0) / threshold + 2: no window holds more evaluations of one sub-location
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint32_t key, uint32_t n)
+{
+    const uint32_t slots = b.need_enters ? 2 * n : n;
+    double r_bound = b.both ? 2.0 * n : (double) n;
+    if (b.r_window < r_bound) r_bound = b.r_window;
+    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
+    const unsigned long long slot = atomicAdd(&ctr->n_blk[cls], 1ull);
+    if (slot >= b.blk_cap) { atomicOr(&ctr->overflow, 2u); return; }
+    b.blk_seg[cls][slot] = key;
+    if (cls == 3)
+    {
+        unsigned long long mp = 64;
+        while (mp < slots) mp <<= 1;
+        const unsigned long long bytes = (unsigned long long) slots * 56 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
+        const unsigned long long off = atomicAdd(&ctr->scratch_top, bytes);
+        if (off + bytes <= b.scratch_cap) b.huge_off[slot] = off;
+        else { b.blk_seg[cls][slot] = KEY_NONE; atomicOr(&ctr->overflow, 2u); }
+    }
+    atomicAdd(&ctr->big_stays, (unsigned long long) n);
+}
+#endif
+
 // the engine stream, four auxiliary streams for the kernels that run side by side, and the fork / join events
-struct TransmitStreams { cudaStream_t main; cudaStream_t aux[4]; cudaEvent_t fork; cudaEvent_t join[4]; };
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[4]; cudaEvent_t fork, mid; cudaEvent_t join[4]; };
 
 }  // namespace heros

@@ -30,7 +30,6 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int THREAD_SLOW_MAX = 8;  // largest segment handled by 8 lanes (four per warp) in k_transmit_sub
-constexpr int BLOCK_P_CAP = 2048;   // evaluations per segment the shared-memory block kernels keep probabilities for
 
 __device__ __forceinline__ double pos_inf() { return bits_f64(0x7ff0000000000000ull); }
 __device__ __forceinline__ double neg_inf() { return bits_f64(0xfff0000000000000ull); }
@@ -88,30 +87,6 @@ __device__ __forceinline__ void draw_and_push(const WindowCtx& c, Local& st, uin
     st.draws++;
     if (fabs(u - p) < 1e-13) st.near++;
     if (u < p) push_candidate(c, person, key, t, p);
-}
-
-// (stay, evaluation) pairs of the group kernels: appended to the draw list, one atomic per warp; when the list is full
-// the draw is made on the spot
-__device__ __forceinline__ void emit_draw(const WindowCtx& c, Local& st, bool active, uint32_t person, uint32_t key,
-                                          double t, double p)
-{
-    const unsigned m = __ballot_sync(FULL, active);
-    if (!m) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(&c.ctr->n_draw, (unsigned long long) __popc(m));
-    base = __shfl_sync(FULL, base, leader);
-    if (!active) return;
-    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-    if (slot < c.draw_cap)
-    {
-        c.draw_person[slot] = person;
-        c.draw_key[slot] = key;
-        c.draw_t[slot] = t;
-        c.draw_p[slot] = p;
-    }
-    else
-        draw_and_push(c, st, person, key, t, p);
 }
 
 __device__ __forceinline__ void flush_stats(const WindowCtx& c, Local st, int lane)
@@ -186,7 +161,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    unsigned occupied = 0, big = 0;
+    unsigned occupied = 0;
 
     for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
     {
@@ -194,33 +169,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         const uint32_t n = b - a;
         if (n == 0) continue;
         ++occupied;
-        if (n > 32)
-        {
-            // group kernels: by the number of events of the sub-location and the bound on its evaluations
-            big += n;
-            const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
-            const uint32_t slots = need_enters ? 2 * n : n;
-            double r_bound = both ? 2.0 * n : (double) n;
-            if (thr > 0 && (c.T1 - c.T0) / thr + 2.0 < r_bound) r_bound = (c.T1 - c.T0) / thr + 2.0;
-            const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
-            const unsigned long long slot = atomicAdd(&c.ctr->n_blk[cls], 1ull);
-            if (slot < c.blk_cap)
-            {
-                c.blk_seg[cls][slot] = key;
-                if (cls == 3)
-                {
-                    unsigned long long mp = 64;
-                    while (mp < slots) mp <<= 1;
-                    const unsigned long long bytes = (unsigned long long) slots * 56 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
-                    const unsigned long long off = atomicAdd(&c.ctr->scratch_top, bytes);
-                    if (off + bytes <= c.scratch_cap) c.huge_off[slot] = off;
-                    else { c.blk_seg[cls][slot] = KEY_NONE; atomicOr(&c.ctr->overflow, 2u); }
-                }
-            }
-            else
-                atomicOr(&c.ctr->overflow, 2u);
-            continue;
-        }
+        if (n > 32) continue;  // queued for the group kernels by the prefix-sum kernel
         const StayRec* rec = c.rec + a;
         // who is here, and the two latest events
         bool any_ill = false, any_sus = false;
@@ -254,9 +203,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         else atomicOr(&c.ctr->overflow, 2u);
     }
     occupied = __reduce_add_sync(FULL, occupied);
-    big = __reduce_add_sync(FULL, big);
     if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
-    if ((threadIdx.x & 31) == 0 && big) atomicAdd(&c.ctr->big_stays, (unsigned long long) big);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -543,8 +490,8 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 
 // per class: group size, groups per block, capacity in events and in kept probabilities
 template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 32, PER_BLOCK = 4, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
 template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 8192, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 1024; using idx_t = uint16_t; };
 template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
 
@@ -981,6 +928,10 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                 if (lane >= o) incl += t;
             }
             const int total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) continue;
+            unsigned long long at = 0;  // room in the draw list for the pairs of the whole batch
+            if (lane == 0) at = atomicAdd(&c.ctr->n_draw, (unsigned long long) total);
+            at = __shfl_sync(FULL, at, 0);
             for (int p0 = 0; p0 < total; p0 += 32)
             {
                 const int pi = p0 + lane;
@@ -995,10 +946,20 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                 const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
                 const int s_lo = __shfl_sync(FULL, lo, src);
                 const uint32_t s_person = __shfl_sync(FULL, person, src);
-                const bool active = pi < total;
-                int r = 0;
-                if (active) r = (int) jb[s_lo + (pi - (s_incl - s_cnt))];
-                emit_draw(c, st, active, s_person, key, active ? ev_t[node[r]] : 0.0, active ? pr[r] : 0.0);
+                if (pi < total)
+                {
+                    const int r = (int) jb[s_lo + (pi - (s_incl - s_cnt))];
+                    const unsigned long long slot = at + (unsigned long long) pi;
+                    if (slot < c.draw_cap)
+                    {
+                        c.draw_person[slot] = s_person;
+                        c.draw_key[slot] = key;
+                        c.draw_t[slot] = ev_t[node[r]];
+                        c.draw_p[slot] = pr[r];
+                    }
+                    else  // the list is full (its tail stays unused): draw on the spot
+                        draw_and_push(c, st, s_person, key, ev_t[node[r]], pr[r]);
+                }
             }
         }
         gsync<G>();
@@ -1026,14 +987,18 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
         cudaFuncSetAttribute(k_transmit_group<MODEL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
         configured[dev] = true;
     }
+    // the group kernels (their work lists were filled by the prefix-sum kernel) start at once on the auxiliary streams,
+    // side by side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds
     cudaStream_t s = ts.main;
-    k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
     cudaEventRecord(ts.fork, s);
     for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
     k_transmit_group<MODEL, 2><<<n_sm, 1024, smem2, ts.aux[0]>>>(c);
     k_transmit_group<MODEL, 3><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
-    k_transmit_group<MODEL, 1><<<n_sm * 6, 256, smem1, ts.aux[1]>>>(c);
-    k_transmit_group<MODEL, 0><<<n_sm * 8, 128, smem0, ts.aux[2]>>>(c);
+    k_transmit_group<MODEL, 1><<<n_sm * 4, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
+    k_transmit_group<MODEL, 0><<<n_sm * 8, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
+    k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
+    cudaEventRecord(ts.mid, s);
+    cudaStreamWaitEvent(ts.aux[3], ts.mid, 0);
     k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
     k_transmit_sub<MODEL, 8><<<n_sm * 8, 256, 0, s>>>(c);
     for (int k = 0; k < 4; ++k)

@@ -20,6 +20,7 @@ ap.add_argument("--trigger", type=int, default=0)
 ap.add_argument("--seeds", type=int, default=100)
 ap.add_argument("--contagiousness", type=float, default=None)
 ap.add_argument("--clocks", action="store_true")
+ap.add_argument("--flags", type=int, default=0)
 args = ap.parse_args()
 
 with open(os.path.join(ROOT, "tests", "golden", f"params_alpha_{'area' if args.model == 'area' else 'distance'}.json")) as f:
@@ -30,7 +31,7 @@ t = time.time()
 city = scenario.City(args.persons)
 print(f"city: {city.n_persons} persons, {city.n_locations} locations, {int(city.loc_nsub.sum())} sub-locations, {time.time()-t:.1f}s")
 model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
-eng = hb.HerosEngine(model, 111, trigger=args.trigger, flags=2 if args.clocks else 0)
+eng = hb.HerosEngine(model, 111, trigger=args.trigger, flags=(2 if args.clocks else 0) | args.flags)
 city.install(eng)
 if model == hb.MODEL_AREA:
     eng.set_transmission_area(properties.area_params(props))
@@ -54,7 +55,12 @@ for d in range(args.days):
           f"progress {s['progress_ms']:.3f} bucket {s['bucket_ms']:.3f} small {s['transmit_small_ms']:.3f} big {s['transmit_big_ms']:.3f} "
           f"resolve {s['resolve_ms']:.3f} retire {s['retire_ms']:.3f} | visits {s['visits']} segs {s['sublocations']} big {s['big_sublocations']} "
           f"evals {s['evaluations']} draws {s['draws']} inf {s['infections']} launches {s['gpu_launches']}")
-if args.clocks:
+    if args.clocks and d >= args.days - 3:
+        np.set_printoptions(linewidth=200, suppress=True)
+        pc = eng.phase_clocks()
+        print("  phase kcycles (rows = class 0..3):"); print((pc[:, :10] / 1e3).round(1))
+        print("  slowest evaluation phase: n, n_ill, R, m_ev, key | sub-locations of the class"); print(pc[:, 10:16])
+if False:
     np.set_printoptions(linewidth=200)
     print("phase clocks (kcycles, max over groups) rows = class 0..3, cols = phase 0..9")
     print((eng.phase_clocks()[:, :10] / 1e3).round(1))
