@@ -15,12 +15,18 @@ engine the Java host keeps); they are recorded once, untimed, and replayed, so t
   --impl reference : the CPU oracle (sequential event-by-event restatement of the reference, one core) on the same
           city and days
 
+N > 1 (launched by torch.distributed.run, one rank per GPU): weak scaling.  Every rank owns one city tile of the
+configured size (persons + locations, tiles side by side); --commute of the workers of a tile work in the next tile,
+so every window exchanges the stays of those commuters (with their packed agent words) and sends the candidate
+infections back -- two NCCL all-to-alls per window (heros_b200.sharded).  Timing: CUDA events on the engine stream,
+max over ranks.
+
 usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-       (N > 1: launched by torch.distributed.run, one rank per GPU; every rank simulates its own city tile)
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -36,6 +42,7 @@ sys.path.insert(0, ROOT)
 HAGUE_PERSONS = 553667
 SEED = 111
 N_INFECTED = 100
+CITY_SEED = 20240807
 
 
 def parse_args():
@@ -44,11 +51,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--persons", type=int, default=HAGUE_PERSONS)
+    ap.add_argument("--persons", type=int, default=HAGUE_PERSONS, help="persons per city tile (per GPU)")
     ap.add_argument("--preroll", type=int, default=7, help="untimed simulated days before the warm-up steps")
     ap.add_argument("--model", default="distance", choices=["area", "distance"])
     ap.add_argument("--trigger", default="exit", choices=["exit", "both"])
     ap.add_argument("--cpu-days", type=int, default=6, help="days of the bounded cpu_baseline sample")
+    ap.add_argument("--commute", type=float, default=0.05,
+                    help="N > 1: fraction of a tile's workers whose workplace lies in the next tile")
     return ap.parse_args()
 
 
@@ -88,9 +97,10 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
+        self._sample()
         self._thread.start()
         return self
 
@@ -141,7 +151,7 @@ def run_reference(args):
         return
     from heros_b200 import scenario
     props = load_props(args.model)
-    city = scenario.City(args.persons)
+    city = scenario.City(args.persons, seed=CITY_SEED)
     sim = oracle_objects(args, props, city)
     seeds = keyed_seeds(city, SEED, N_INFECTED)
     sim.expose(seeds, np.zeros(len(seeds)))
@@ -163,10 +173,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, city),
+        "config": workload_config(args, city, 1, 0),
         "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": 1, "kind": "port",
                          "sample": f"{args.steps} simulated days (days {args.preroll + args.warmup}.."
-                                   f"{total - 1}) of the same city, oracle/heros_oracle.c single-threaded"},
+                                   f"{total - 1}) of one city tile, oracle/heros_oracle.c single-threaded (a replication "
+                                   f"of the reference is single-threaded by construction)"},
         "e2e": {"value": value, "unit": "person-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "infections": int(sim.phase_counts()[1:].sum()),
@@ -174,13 +185,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, city):
-    return {"workload": f"thehague-synthetic N={city.n_persons} locations={city.n_locations} "
-                        f"sublocations={int(city.loc_nsub.sum())} model={args.model} trigger={args.trigger} seed={SEED} "
-                        f"infected0={N_INFECTED}",
-            "step": "one simulated day (24 h window)", "first_timed_day": args.preroll + args.warmup,
-            "l2": "inputs larger than L2: each step reads that day's fresh stay buffers and rewrites the bucketed copies "
-                  "(~200 MB per step)"}
+def workload_config(args, city, world, n_commuters):
+    cfg = {"workload": f"thehague-synthetic N={city.n_persons} locations={city.n_locations} "
+                       f"sublocations={int(city.loc_nsub.sum())} model={args.model} trigger={args.trigger} seed={SEED} "
+                       f"infected0={N_INFECTED}" + (f" per GPU, {world} tiles" if world > 1 else ""),
+           "step": "one simulated day (24 h window)", "first_timed_day": args.preroll + args.warmup,
+           "l2": "inputs larger than L2: every step reads a fresh day of stays (61 MB, written to HBM before the timed "
+                 "region) and streams ~0.4 GB through the pool, ticket and bucket buffers (L2: 126 MB)"}
+    if world > 1:
+        cfg["cross_tile"] = (f"{args.commute:.3f} of each tile's workers ({n_commuters} on rank 0) work in the next tile: "
+                             "2 NCCL all-to-alls per window (guest stays out, candidate infections back)")
+    return cfg
 
 
 def make_engine(args, props, city, device):
@@ -195,7 +210,6 @@ def make_engine(args, props, city, device):
     else:
         eng.set_transmission_distance(properties.dist_params(props))
     eng.set_progression(properties.prog_params(props))
-    eng.seed_infections(N_INFECTED)
     return eng
 
 
@@ -205,8 +219,7 @@ COLS = (("person", np.int32), ("loc", np.int32), ("sub", np.int16), ("t_in", np.
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import heros_b200 as hb
-    from heros_b200 import scenario
+    from heros_b200 import scenario, sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,29 +227,80 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the HEROS engine has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
     props = load_props(args.model)
-    # weak scaling: every rank simulates its own city tile of the configured size
-    city = scenario.City(args.persons, seed=20240807 + rank, origin_m=(12000.0 * rank, 0.0))
+    # weak scaling: every rank owns one city tile of the configured size, tiles side by side
+    city = scenario.City(args.persons, seed=CITY_SEED + rank, origin_m=(12000.0 * rank, 0.0))
+    n_commuters = 0
+    nxt = (rank + 1) % world
+    if world > 1 and args.commute > 0:
+        other = scenario.City(args.persons, seed=CITY_SEED + nxt, origin_m=(12000.0 * nxt, 0.0))
+        n_commuters = city.add_commuters(other, args.commute, seed=1000 + rank)
+        del other
+    if world > 1:
+        sizes = torch.tensor([city.n_persons, city.n_locations], dtype=torch.int64, device=dev)
+        gathered = [torch.empty_like(sizes) for _ in range(world)]
+        dist.all_gather(gathered, sizes)
+        gathered = torch.stack(gathered).cpu().numpy()
+        person_bases = np.concatenate([[0], np.cumsum(gathered[:, 0])])
+        loc_bases = np.concatenate([[0], np.cumsum(gathered[:, 1])])
+    else:
+        person_bases = np.array([0, city.n_persons])
+        loc_bases = np.array([0, city.n_locations])
     total = args.preroll + args.warmup + args.steps
     first_timed = args.preroll + args.warmup
 
+    def new_engine():
+        eng = make_engine(args, props, city, local)
+        sh = None
+        if world > 1:
+            sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
+        eng.seed_infections(N_INFECTED)
+        return eng, sh, torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def day_step(eng, sh, d, local_cols, remote_cols, device):
+        eng.submit_visits_ptr(local_cols["person"].numel(), *(local_cols[k].data_ptr() for k, _ in COLS), device=device)
+        if sh is None:
+            return eng.step(24.0 * (d + 1))
+        return sh.step_window(24.0 * (d + 1), remote_cols)  # pinned host columns are copied on the engine stream
+
+    def split_day(st, open_remote):
+        """global ids; the stays in the next tile's locations are the remote ones (kept while they are open)"""
+        person = (st["person"].astype(np.int64) + person_bases[rank]).astype(np.int32)
+        loc = city.global_location_ids(st["loc"], int(loc_bases[rank]), int(loc_bases[nxt]))
+        is_remote = st["loc"] >= city.n_locations
+        cols = {"person": person, "loc": loc, "sub": st["sub"], "t_in": st["t_in"], "t_out": st["t_out"]}
+        loc_cols = {k: v[~is_remote] for k, v in cols.items()}
+        rem = {k: v[is_remote] for k, v in cols.items()}
+        if open_remote is not None and len(open_remote["person"]):
+            # an open remote stay of an earlier day stays a guest until its closed version arrives
+            closed_now = set(zip(rem["person"].tolist(), rem["t_in"].tolist()))
+            keep = np.array([(p, t) not in closed_now for p, t in zip(open_remote["person"].tolist(),
+                                                                      open_remote["t_in"].tolist())], bool)
+            rem = {k: np.concatenate([open_remote[k][keep], rem[k]]) for k in rem}
+        still_open = np.isinf(rem["t_out"])
+        return loc_cols, rem, {k: v[still_open] for k, v in rem.items()}
+
+    def pin(cols):
+        return {k: torch.from_numpy(np.ascontiguousarray(cols[k])).pin_memory() for k, _ in COLS}
+
     # ---- record pass (untimed): the medlabs activity engine's job, done once on the host ----
-    eng = make_engine(args, props, city, local)
+    eng, sh, _ = new_engine()
     gen = scenario.ScheduleGenerator(city, SEED)
-    days = []
+    days, open_remote = [], None
     for d in range(total):
         st = gen.generate_day(eng.agent_state()["phase"])
-        pinned = {k: torch.from_numpy(st[k]).pin_memory() for k, _ in COLS}
-        days.append(pinned)
-        eng.submit_visits_ptr(len(st["person"]), *(pinned[k].data_ptr() for k, _ in COLS), device=False)
-        eng.step(24.0 * (d + 1))
+        loc_cols, rem_cols, open_remote = split_day(st, open_remote)
+        days.append((pin(loc_cols), pin(rem_cols)))
+        day_step(eng, sh, d, days[-1][0], days[-1][1], device=False)
     ref_counts = eng.phase_counts()
     ref_infections = eng.infections()
     eng.close()
-    h2d_bytes = [sum(days[d][k].numel() * days[d][k].element_size() for k, _ in COLS) for d in range(total)]
+    h2d_bytes = [sum(c[k].numel() * c[k].element_size() for c in days[d] for k, _ in COLS) for d in range(total)]
+    remote_rows = float(np.mean([days[d][1]["person"].numel() for d in range(first_timed, total)]))
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,54 +311,55 @@ def run_ours(args):
     def max_over_ranks(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: stays resident in HBM ----
-    eng = make_engine(args, props, city, local)
-    dev_days = [{k: days[d][k].cuda() for k, _ in COLS} for d in range(total)]
-    stats = []
-    for d in range(first_timed):
-        eng.submit_visits_ptr(dev_days[d]["person"].numel(), *(dev_days[d][k].data_ptr() for k, _ in COLS), device=True)
-        eng.step(24.0 * (d + 1))
-    barrier()
-    with ClockSampler(local) as clocks:
-        t0 = time.perf_counter()
-        for d in range(first_timed, total):
-            eng.submit_visits_ptr(dev_days[d]["person"].numel(), *(dev_days[d][k].data_ptr() for k, _ in COLS),
-                                  device=True)
-            stats.append(eng.step(24.0 * (d + 1)))
+    def timed_days(eng, sh, stream, cols_of_day, device, after_step=None):
+        """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream."""
+        stats = []
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        seconds = time.perf_counter() - t0
-    seconds = max_over_ranks(seconds)
-    counts_value = eng.phase_counts()
-    assert (counts_value == ref_counts).all(), "replay diverged from the recorded run"
+        t0 = time.perf_counter()
+        start.record(stream)
+        for d in range(first_timed, total):
+            stats.append(day_step(eng, sh, d, *cols_of_day(d), device=device))
+            if after_step:
+                after_step()
+        end.record(stream)
+        end.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        return max_over_ranks(start.elapsed_time(end) * 1e-3), max_over_ranks(wall), stats
+
+    # ---- value: stays resident in HBM ----
+    eng, sh, stream = new_engine()
+    dev_days = [tuple({k: c[k].to(dev) for k, _ in COLS} for c in days[d]) for d in range(total)]
+    for d in range(first_timed):
+        day_step(eng, sh, d, dev_days[d][0], dev_days[d][1], device=True)
+    with ClockSampler(local) as clocks:
+        seconds, wall_seconds, stats = timed_days(eng, sh, stream, lambda d: dev_days[d], True)
+    assert (eng.phase_counts() == ref_counts).all(), "replay diverged from the recorded run"
     eng.close()
     del dev_days
 
     # ---- e2e: through the C ABI with pinned host buffers, copies inside the timed region ----
-    eng = make_engine(args, props, city, local)
+    eng, sh, stream = new_engine()
     for d in range(first_timed):
-        eng.submit_visits_ptr(days[d]["person"].numel(), *(days[d][k].data_ptr() for k, _ in COLS), device=False)
-        eng.step(24.0 * (d + 1))
-    n_inf = len(eng.infections()["person"])
-    d2h = 0
-    barrier()
-    t0 = time.perf_counter()
-    for d in range(first_timed, total):
-        eng.submit_visits_ptr(days[d]["person"].numel(), *(days[d][k].data_ptr() for k, _ in COLS), device=False)
-        eng.step(24.0 * (d + 1))
-        counts = eng.phase_counts()             # D2H: the DiseaseMonitor counters
-        new = eng.infections(first=n_inf)       # D2H: the day's infection events
-        n_inf += len(new["person"])
-        d2h += 64 + len(new["person"]) * 26
-    barrier()
-    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-    assert (counts == ref_counts).all()
+        day_step(eng, sh, d, days[d][0], days[d][1], device=False)
+    box = {"n_inf": len(eng.infections()["person"]), "d2h": 0, "counts": None}
+
+    def read_results():
+        box["counts"] = eng.phase_counts()          # D2H: the DiseaseMonitor counters
+        new = eng.infections(first=box["n_inf"])    # D2H: the day's infection events
+        box["n_inf"] += len(new["person"])
+        box["d2h"] += 64 + len(new["person"]) * 26
+
+    e2e_seconds, e2e_wall, _ = timed_days(eng, sh, stream, lambda d: days[d], False, read_results)
+    assert (box["counts"] == ref_counts).all()
     eng.close()
 
-    n_total_persons = city.n_persons * world
+    n_total_persons = int(person_bases[-1])
     value = n_total_persons * 24.0 * args.steps / seconds
     e2e_value = n_total_persons * 24.0 * args.steps / e2e_seconds
 
@@ -304,8 +369,8 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the engine stream) ----
-    keys = ("progress_ms", "bucket_ms", "bucket_count_ms", "bucket_scan_ms", "bucket_scatter_ms", "transmit_small_ms",
-            "transmit_big_ms", "resolve_ms", "retire_ms", "gpu_ms")
+    keys = ("progress_ms", "bucket_ms", "bucket_scan_ms", "bucket_scatter_ms", "transmit_small_ms",
+            "transmit_big_ms", "resolve_ms", "gpu_ms")
     stage = {k: float(np.sum([s[k] for s in stats])) for k in keys}
     visits = float(np.sum([s["visits"] for s in stats]))
     big_stays = float(np.sum([s["big_stays"] for s in stats]))
@@ -315,55 +380,71 @@ def run_ours(args):
             peak, peak_source = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_source = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    # single kernels with their algorithmic bytes: k_transmit_thread streams every stay record once
-    # (32 B / stay); k_bucket_scatter is the bucketing pass proper (16 B / stay: key + index in, out); the group kernels
-    # handle the stays of the large sub-locations (32 B / stay)
-    kernels = {"k_transmit_thread": (stage["transmit_small_ms"], 32.0 * visits),
+    # Algorithmic bytes: bucketing 16 B per stay (key + index in, out), spent once per
+    # pass that touches every stay (tickets: k_window_open, which also runs the state machine, 16 B per agent; move:
+    # k_bucket_scatter); transmission 32 B per stay (24 B stay + 8 B agent word), streamed once by k_transmit_thread;
+    # the sub-warp / group kernels re-read only the stays of the sub-locations they evaluate.
+    agents = float(city.n_persons * args.steps)
+    kernels = {"k_window_open": (stage["progress_ms"], 16.0 * visits + 16.0 * agents),
                "k_bucket_scatter": (stage["bucket_scatter_ms"], 16.0 * visits),
-               "k_bucket_count": (stage["bucket_count_ms"], 16.0 * visits),
-               "k_transmit_group+k_transmit_warp (concurrent)": (stage["transmit_big_ms"], 32.0 * big_stays)}
+               "k_transmit_thread": (stage["transmit_small_ms"], 32.0 * visits),
+               "k_transmit_sub+k_transmit_group+k_draw (concurrent)": (stage["transmit_big_ms"], 32.0 * big_stays)}
     dominant = max(kernels, key=lambda k: kernels[k][0])
     achieved = kernels[dominant][1] / (kernels[dominant][0] * 1e-3) / 1e9
+    traffic, traffic_source = None, None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_full.json")), reverse=True):
+        with open(path) as f:
+            rows = [r for r in json.load(f) if dominant.split("+")[0] in r["kernel"]]
+        if rows:
+            traffic = float(np.mean([r["traffic_B"] for r in rows]))
+            traffic_source = f"profiles/{os.path.basename(path)} (ncu --set full, dram bytes read + written per launch)"
+            break
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_source,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                "algorithmic_bytes_per_launch": kernels[dominant][1] / args.steps, "peak_source": peak_source,
                 "per_kernel_gbs": {k: (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None) for k, v in kernels.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
-
-    # ---- cpu_baseline: the oracle on a bounded sample (first cpu_days days), checked against the GPU run ----
-    cpu_days = min(args.cpu_days, total)
-    sim = oracle_objects(args, props, city)
-    seeds = keyed_seeds(city, SEED, N_INFECTED)
-    sim.expose(seeds, np.zeros(len(seeds)))
-    t_cpu = 0.0
-    for d in range(cpu_days):
-        t0 = time.perf_counter()
-        sim.add_visits(*(days[d][k].numpy() for k, _ in COLS))
-        sim.run(24.0 * (d + 1))
-        t_cpu += time.perf_counter() - t0
-    oi = sim.infections()
-    keep = ref_infections["time"] < 24.0 * cpu_days
-    order = np.lexsort((oi["person"], oi["time"]))
-    parity = bool(len(order) == int(keep.sum()) and (oi["person"][order] == ref_infections["person"][keep]).all()
-                  and (oi["time"][order] == ref_infections["time"][keep]).all())
-    cpu_value = city.n_persons * 24.0 * cpu_days / t_cpu
 
     line = {
         "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city, world, n_commuters),
         "clocks": clocks.summary(),
+        "timing": "CUDA events on the engine stream around the K steps, max over ranks; wall clock of the same region: "
+                  f"{1e3 * wall_seconds / args.steps:.4f} ms/step",
         "e2e": {"value": e2e_value, "unit": "person-hours/s",
-                "h2d_bytes_per_step": int(np.mean(h2d_bytes[first_timed:])), "d2h_bytes_per_step": int(d2h / args.steps),
-                "ms_per_step": 1e3 * e2e_seconds / args.steps},
-        "gpu_launches": int(np.sum([s["gpu_launches"] for s in stats])) + 2 * args.steps,
+                "h2d_bytes_per_step": int(np.mean(h2d_bytes[first_timed:])), "d2h_bytes_per_step": int(box["d2h"] / args.steps),
+                "ms_per_step": 1e3 * e2e_seconds / args.steps, "wall_ms_per_step": 1e3 * e2e_wall / args.steps},
+        "gpu_launches": int(np.sum([s["gpu_launches"] for s in stats])) + args.steps,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_value, "unit": "person-hours/s", "cores": 1, "kind": "port",
-                         "sample": f"first {cpu_days} simulated days of the same city and stays, oracle/heros_oracle.c "
-                                   f"single-threaded ({t_cpu:.1f} s)", "infection_lists_identical": parity},
         "infections_total": int(ref_counts[1:].sum()), "visits_per_step": visits / args.steps,
         "device_ms_per_step": stage["gpu_ms"] / args.steps,
     }
+    if world > 1:
+        line["cross_tile_stays_per_step_rank0"] = remote_rows
+    else:
+        # ---- cpu_baseline: the oracle on a bounded sample (first cpu_days days), checked against the GPU run ----
+        cpu_days = min(args.cpu_days, total)
+        sim = oracle_objects(args, props, city)
+        seeds = keyed_seeds(city, SEED, N_INFECTED)
+        sim.expose(seeds, np.zeros(len(seeds)))
+        t_cpu = 0.0
+        for d in range(cpu_days):
+            t0 = time.perf_counter()
+            sim.add_visits(*(days[d][0][k].numpy() for k, _ in COLS))
+            sim.run(24.0 * (d + 1))
+            t_cpu += time.perf_counter() - t0
+        oi = sim.infections()
+        keep = ref_infections["time"] < 24.0 * cpu_days
+        order = np.lexsort((oi["person"], oi["time"]))
+        parity = bool(len(order) == int(keep.sum()) and (oi["person"][order] == ref_infections["person"][keep]).all()
+                      and (oi["time"][order] == ref_infections["time"][keep]).all())
+        line["cpu_baseline"] = {"value": city.n_persons * 24.0 * cpu_days / t_cpu, "unit": "person-hours/s", "cores": 1,
+                                "kind": "port",
+                                "sample": f"first {cpu_days} simulated days of the same city and stays, "
+                                          f"oracle/heros_oracle.c single-threaded ({t_cpu:.1f} s)",
+                                "infection_lists_identical": parity}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -218,6 +218,9 @@ int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, 
                               const float* exposure_time, double now);
 int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out);
 int32_t heros_get_time(heros_handle h, double* now);
+/* the CUDA stream (cudaStream_t) every kernel and copy of this engine is ordered on: hosts that time the engine with
+ * CUDA events, or that chain their own device work (exchange buffers of a sharded run), use it */
+int32_t heros_get_stream(heros_handle h, void** stream_out);
 /* HEROS_FLAG_PHASE_CLOCKS: clocks[class * 16 + phase], 64 entries, of the last window */
 int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks);
 

@@ -93,6 +93,7 @@ SIGNATURES = {
     "heros_set_agent_state": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_double]),
     "heros_get_last_calculation": (C.c_int32, [_P, C.c_int32, C.c_int16, C.POINTER(C.c_double)]),
     "heros_get_time": (C.c_int32, [_P, C.POINTER(C.c_double)]),
+    "heros_get_stream": (C.c_int32, [_P, C.POINTER(_P)]),
     "heros_get_phase_clocks": (C.c_int32, [_P, _P]),
     "heros_infect_people": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_double, C.c_double,
                                         C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32),

@@ -1866,6 +1866,13 @@ int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
     return HEROS_OK;
 }
 
+int32_t heros_get_stream(heros_handle h, void** stream_out)
+{
+    if (!h || !stream_out) return HEROS_ERR_INVALID;
+    *stream_out = (void*) h->stream;
+    return HEROS_OK;
+}
+
 int32_t heros_get_time(heros_handle h, double* now)
 {
     if (!h || !now) return HEROS_ERR_INVALID;

@@ -238,6 +238,13 @@ class HerosEngine:
         return out
 
     @property
+    def stream(self) -> int:
+        """cudaStream_t of the engine as an integer (e.g. for ``torch.cuda.ExternalStream``)."""
+        out = C.c_void_p()
+        self._check(self._lib.heros_get_stream(self._h, C.byref(out)))
+        return int(out.value or 0)
+
+    @property
     def time(self) -> float:
         out = C.c_double(0.0)
         self._check(self._lib.heros_get_time(self._h, C.byref(out)))

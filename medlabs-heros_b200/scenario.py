@@ -228,6 +228,26 @@ class City:
                                 [ROLE_WORKER, ROLE_UNEMPLOYED, ROLE_WEEKEND_WORKER], ROLE_ESSENTIAL_WORKER)
         return role
 
+    def add_commuters(self, other: "City", fraction: float, seed: int = 77) -> int:
+        """Gives ``fraction`` of the workers of this city tile a workplace in the neighbouring tile ``other`` (cross-shard
+        travel of a geographically sharded run).  A remote workplace is coded as ``n_locations + its id in
+        the other tile``; ``global_location_ids`` turns the codes into global ids.  Returns the number of commuters."""
+        rng = np.random.default_rng(seed)
+        workers = np.nonzero(self.role == ROLE_WORKER)[0]
+        pick = workers[rng.random(len(workers)) < fraction]
+        wp = np.nonzero(other.loc_type == TYPE_ID["Workplace"])[0]
+        weights = other.loc_nsub[wp].astype(np.float64)
+        dest = wp[rng.choice(len(wp), len(pick), p=weights / weights.sum())]
+        self.work_loc[pick] = (self.n_locations + dest).astype(np.int32)
+        self.work_sub[pick] = (rng.integers(0, 1 << 30, len(pick)) % other.loc_nsub[dest]).astype(np.int16)
+        self.n_commuters = len(pick)
+        return len(pick)
+
+    def global_location_ids(self, loc: np.ndarray, own_base: int, other_base: int) -> np.ndarray:
+        """Location codes of the schedule generator -> global location ids of a sharded run."""
+        loc = loc.astype(np.int64)
+        return np.where(loc >= self.n_locations, loc - self.n_locations + other_base, loc + own_base).astype(np.int32)
+
     def install(self, engine):
         """heros_set_location_types / heros_set_locations / heros_set_persons."""
         engine.set_location_types(self.type_infect_sub, self.type_correction)

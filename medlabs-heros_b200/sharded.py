@@ -12,10 +12,13 @@ nothing else is exchanged, and because draws are keyed by global person id and e
 order the sharded run is bit-identical to the same population on a single engine.
 
 The routing helpers are plain torch and run on CPU tensors too (gloo), which is how tests/test_sharded_host.py
-exercises them without a GPU.
+exercises them without a GPU.  On a GPU every torch operation of a shard (routing, packing, the NCCL collectives) is
+issued on the engine's own CUDA stream (heros_get_stream), so it is ordered with the engine's kernels without any
+extra synchronisation.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -53,7 +56,9 @@ def concat_columns(parts: List[Dict[str, torch.Tensor]], schema, device) -> Dict
 
 def all_to_all_rows(columns: Dict[str, torch.Tensor], send_counts: torch.Tensor, group=None):
     """Variable-size all-to-all of row-aligned columns (torch.distributed: NCCL on GPU tensors, gloo on CPU tensors).
-    Returns (received columns, rows received per source rank)."""
+    Two collectives per exchange: the row counts, then ONE payload in which the rows for a destination travel as a
+    block of column slices (widest columns first, the block padded to 8 bytes, so every slice is aligned for its
+    dtype on arrival).  Returns (received columns in source-rank order, rows received per source rank)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     device = next(iter(columns.values())).device
@@ -61,15 +66,36 @@ def all_to_all_rows(columns: Dict[str, torch.Tensor], send_counts: torch.Tensor,
     recv = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_to_all_single(recv, send, group=group)
     send_l, recv_l = send.tolist(), recv.tolist()
-    out = {}
-    for k, v in columns.items():
-        es = v.element_size()  # exchanged as raw bytes: every backend moves uint8, not every backend moves int16
-        buf = torch.empty(int(sum(recv_l)), dtype=v.dtype, device=device)
-        dist.all_to_all_single(buf.view(torch.uint8), v.contiguous().view(torch.uint8),
-                               output_split_sizes=[r * es for r in recv_l], input_split_sizes=[c * es for c in send_l],
-                               group=group)
-        out[k] = buf
-    return out, recv_l
+    names = sorted(columns, key=lambda k: -columns[k].element_size())
+    widths = [columns[k].element_size() for k in names]
+    row_bytes = sum(widths)
+
+    def block(rows):
+        return (rows * row_bytes + 7) // 8 * 8
+
+    pieces, start = [], 0
+    for d in range(world):
+        c = send_l[d]
+        used = 0
+        for k, w in zip(names, widths):
+            pieces.append(columns[k][start:start + c].contiguous().view(torch.uint8))
+            used += c * w
+        if block(c) > used:
+            pieces.append(torch.zeros(block(c) - used, dtype=torch.uint8, device=device))
+        start += c
+    sbuf = torch.cat(pieces) if pieces else torch.empty(0, dtype=torch.uint8, device=device)
+    rbuf = torch.empty(sum(block(r) for r in recv_l), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(rbuf, sbuf, output_split_sizes=[block(r) for r in recv_l],
+                           input_split_sizes=[block(c) for c in send_l], group=group)
+    parts = {k: [] for k in names}
+    pos = 0
+    for r in recv_l:
+        off = pos
+        for k, w in zip(names, widths):
+            parts[k].append(rbuf[off:off + r * w].view(columns[k].dtype))
+            off += r * w
+        pos += block(r)
+    return {k: torch.cat(parts[k]) for k in columns}, recv_l
 
 
 class ShardedEngine:
@@ -81,8 +107,13 @@ class ShardedEngine:
         self.person_bases = torch.as_tensor(person_bases, dtype=torch.int64)
         self.location_bases = torch.as_tensor(location_bases, dtype=torch.int64)
         engine.set_id_bases(int(self.person_bases[rank]), int(self.location_bases[rank]))
+        self.stream = torch.cuda.ExternalStream(engine.stream, device=self.device) if self.device.type == "cuda" else None
         self.sent_stays = 0
         self.sent_candidates = 0
+
+    def on_stream(self):
+        """Context in which torch work is issued on the engine's CUDA stream."""
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     # ---- phase 1: state machine, then the stays that leave the shard ----
     def begin_and_route(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]]):
@@ -90,6 +121,8 @@ class ShardedEngine:
         person i32, loc i32, sub i16, t_in f64, t_out f64, global ids).  Returns (columns by destination, counts)."""
         eng = self.engine
         eng.window_begin(t_until)
+        if remote is not None and remote["person"].device != self.device:  # pinned host buffers: H2D on the engine stream
+            remote = {k: v.to(self.device, non_blocking=True) for k, v in remote.items()}
         n = 0 if remote is None else int(remote["person"].numel())
         word = torch.empty(n, dtype=torch.int64, device=self.device)
         ill_end = torch.empty(n, dtype=torch.float64, device=self.device)
@@ -137,11 +170,12 @@ class ShardedEngine:
 
     # ---- one window over torch.distributed ----
     def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], group=None):
-        cols, counts = self.begin_and_route(t_until, remote)
-        guests, _ = all_to_all_rows(cols, counts, group)
-        cols, counts = self.transmit_and_route(guests)
-        cands, _ = all_to_all_rows(cols, counts, group)
-        return self.finish(cands)
+        with self.on_stream():
+            cols, counts = self.begin_and_route(t_until, remote)
+            guests, _ = all_to_all_rows(cols, counts, group)
+            cols, counts = self.transmit_and_route(guests)
+            cands, _ = all_to_all_rows(cols, counts, group)
+            return self.finish(cands)
 
 
 def step_window_in_process(shards: List[ShardedEngine], t_until: float, remotes: List[Optional[Dict[str, torch.Tensor]]]):
@@ -149,10 +183,20 @@ def step_window_in_process(shards: List[ShardedEngine], t_until: float, remotes:
     shuffles.  Used to check that a sharded run equals the unsharded one without needing several GPUs."""
     world = len(shards)
     dev = shards[0].device
-    out1 = [s.begin_and_route(t_until, r) for s, r in zip(shards, remotes)]
+
+    def run(fn, args):
+        out = []
+        for s, a in zip(shards, args):
+            with s.on_stream():
+                out.append(fn(s, a))
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)  # the shards' streams meet here, as they would in the collective
+        return out
+
+    out1 = run(lambda s, r: s.begin_and_route(t_until, r), remotes)
     parts = [split_by_counts(c, n.tolist()) for c, n in out1]
     inbox = [concat_columns([parts[src][dst] for src in range(world)], GUEST_COLUMNS, dev) for dst in range(world)]
-    out2 = [s.transmit_and_route(g) for s, g in zip(shards, inbox)]
+    out2 = run(lambda s, g: s.transmit_and_route(g), inbox)
     parts = [split_by_counts(c, n.tolist()) for c, n in out2]
     inbox = [concat_columns([parts[src][dst] for src in range(world)], CANDIDATE_COLUMNS, dev) for dst in range(world)]
-    return [s.finish(c) for s, c in zip(shards, inbox)]
+    return run(lambda s, c: s.finish(c), inbox)
