@@ -194,7 +194,8 @@ def workload_config(args, city, world, n_commuters):
                  "region) and streams ~0.4 GB through the pool, ticket and bucket buffers (L2: 126 MB)"}
     if world > 1:
         cfg["cross_tile"] = (f"{args.commute:.3f} of each tile's workers ({n_commuters} on rank 0) work in the next tile: "
-                             "2 NCCL all-to-alls per window (guest stays out, candidate infections back)")
+                             "2 equal-split NCCL all-to-alls per window on the engine stream (guest-stay blocks out, candidate blocks "
+                             "back), no host synchronisation inside a window")
     return cfg
 
 
@@ -253,19 +254,30 @@ def run_ours(args):
     total = args.preroll + args.warmup + args.steps
     first_timed = args.preroll + args.warmup
 
+    guest_capacity = [4096]
+    engines = []  # at N > 1 the engines (and their streams, which NCCL has seen) live until the process group is gone
+
     def new_engine():
         eng = make_engine(args, props, city, local)
-        sh = None
+        bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
+            bx = sharded.BlockExchange(sh, guest_capacity[0])
         eng.seed_infections(N_INFECTED)
-        return eng, sh, torch.cuda.ExternalStream(eng.stream, device=dev)
+        engines.append(eng)
+        return eng, bx, torch.cuda.ExternalStream(eng.stream, device=dev)
 
-    def day_step(eng, sh, d, local_cols, remote_cols, device):
+    def release(eng):
+        if world == 1:
+            eng.close()
+
+    def day_step(eng, bx, d, local_cols, remote_cols, offsets, device):
         eng.submit_visits_ptr(local_cols["person"].numel(), *(local_cols[k].data_ptr() for k, _ in COLS), device=device)
-        if sh is None:
+        if bx is None:
             return eng.step(24.0 * (d + 1))
-        return sh.step_window(24.0 * (d + 1), remote_cols)  # pinned host columns are copied on the engine stream
+        # block exchange: two equal-split NCCL all-to-alls per window, everything enqueued on the engine stream
+        # (pinned host columns of the commuters' stays are copied on that stream too)
+        return bx.step_window(24.0 * (d + 1), remote_cols, offsets)
 
     def split_day(st, open_remote):
         """global ids; the stays in the next tile's locations are the remote ones (kept while they are open)"""
@@ -282,24 +294,31 @@ def run_ours(args):
                                                                       open_remote["t_in"].tolist())], bool)
             rem = {k: np.concatenate([open_remote[k][keep], rem[k]]) for k in rem}
         still_open = np.isinf(rem["t_out"])
-        return loc_cols, rem, {k: v[still_open] for k, v in rem.items()}
+        open_next = {k: v[still_open] for k, v in rem.items()}
+        rem, offsets = sharded.sort_by_destination(rem, loc_bases, world)  # the producer groups by destination shard
+        return loc_cols, rem, offsets, open_next
 
     def pin(cols):
         return {k: torch.from_numpy(np.ascontiguousarray(cols[k])).pin_memory() for k, _ in COLS}
 
     # ---- record pass (untimed): the medlabs activity engine's job, done once on the host ----
-    eng, sh, _ = new_engine()
+    if world > 1:
+        # block capacity of the guest exchange: the commuters' stays of a day, with head-room, agreed by all ranks
+        cap = torch.tensor([int(4 * max(n_commuters, 1024))], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        guest_capacity[0] = int(cap.item())
+    eng, bx, _ = new_engine()
     gen = scenario.ScheduleGenerator(city, SEED)
     days, open_remote = [], None
     for d in range(total):
         st = gen.generate_day(eng.agent_state()["phase"])
-        loc_cols, rem_cols, open_remote = split_day(st, open_remote)
-        days.append((pin(loc_cols), pin(rem_cols)))
-        day_step(eng, sh, d, days[-1][0], days[-1][1], device=False)
+        loc_cols, rem_cols, offsets, open_remote = split_day(st, open_remote)
+        days.append((pin(loc_cols), pin(rem_cols), offsets))
+        day_step(eng, bx, d, *days[-1], device=False)
     ref_counts = eng.phase_counts()
     ref_infections = eng.infections()
-    eng.close()
-    h2d_bytes = [sum(c[k].numel() * c[k].element_size() for c in days[d] for k, _ in COLS) for d in range(total)]
+    release(eng)
+    h2d_bytes = [sum(c[k].numel() * c[k].element_size() for c in days[d][:2] for k, _ in COLS) for d in range(total)]
     remote_rows = float(np.mean([days[d][1]["person"].numel() for d in range(first_timed, total)]))
 
     def barrier():
@@ -315,7 +334,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed_days(eng, sh, stream, cols_of_day, device, after_step=None):
+    def timed_days(eng, bx, stream, cols_of_day, device, after_step=None):
         """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream."""
         stats = []
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,7 +342,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         start.record(stream)
         for d in range(first_timed, total):
-            stats.append(day_step(eng, sh, d, *cols_of_day(d), device=device))
+            stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))
             if after_step:
                 after_step()
         end.record(stream)
@@ -333,20 +352,21 @@ def run_ours(args):
         return max_over_ranks(start.elapsed_time(end) * 1e-3), max_over_ranks(wall), stats
 
     # ---- value: stays resident in HBM ----
-    eng, sh, stream = new_engine()
-    dev_days = [tuple({k: c[k].to(dev) for k, _ in COLS} for c in days[d]) for d in range(total)]
+    eng, bx, stream = new_engine()
+    dev_days = [({k: days[d][0][k].to(dev) for k, _ in COLS}, {k: days[d][1][k].to(dev) for k, _ in COLS}, days[d][2])
+                for d in range(total)]
     for d in range(first_timed):
-        day_step(eng, sh, d, dev_days[d][0], dev_days[d][1], device=True)
+        day_step(eng, bx, d, *dev_days[d], device=True)
     with ClockSampler(local) as clocks:
-        seconds, wall_seconds, stats = timed_days(eng, sh, stream, lambda d: dev_days[d], True)
+        seconds, wall_seconds, stats = timed_days(eng, bx, stream, lambda d: dev_days[d], True)
     assert (eng.phase_counts() == ref_counts).all(), "replay diverged from the recorded run"
-    eng.close()
+    release(eng)
     del dev_days
 
     # ---- e2e: through the C ABI with pinned host buffers, copies inside the timed region ----
-    eng, sh, stream = new_engine()
+    eng, bx, stream = new_engine()
     for d in range(first_timed):
-        day_step(eng, sh, d, days[d][0], days[d][1], device=False)
+        day_step(eng, bx, d, *days[d], device=False)
     box = {"n_inf": len(eng.infections()["person"]), "d2h": 0, "counts": None}
 
     def read_results():
@@ -355,17 +375,27 @@ def run_ours(args):
         box["n_inf"] += len(new["person"])
         box["d2h"] += 64 + len(new["person"]) * 26
 
-    e2e_seconds, e2e_wall, _ = timed_days(eng, sh, stream, lambda d: days[d], False, read_results)
+    e2e_seconds, e2e_wall, _ = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
     assert (box["counts"] == ref_counts).all()
-    eng.close()
+    release(eng)
 
     n_total_persons = int(person_bases[-1])
     value = n_total_persons * 24.0 * args.steps / seconds
     e2e_value = n_total_persons * 24.0 * args.steps / e2e_seconds
 
-    if rank != 0:
+    def shutdown():
         if world > 1:
+            # leave in an orderly way: everything the engine streams have touched is released before the streams go, and
+            # the interpreter is left without running destructors against a CUDA context that is being torn down
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel (device time from CUDA events on the engine stream) ----
@@ -445,9 +475,8 @@ def run_ours(args):
                                 "sample": f"first {cpu_days} simulated days of the same city and stays, "
                                           f"oracle/heros_oracle.c single-threaded ({t_cpu:.1f} s)",
                                 "infection_lists_identical": parity}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 def main():

@@ -162,7 +162,9 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
  * must be submitted before heros_step passes its t_in.  t_out <= t_in stays are ignored. */
 int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                             const int16_t* sublocation, const double* t_in, const double* t_out);
-/* same, from device memory of the engine's GPU (multi-GPU exchange buffers, device-side schedule generators) */
+/* same, from device memory of the engine's GPU (multi-GPU exchange buffers, device-side schedule generators).  The
+ * buffers are read asynchronously on the engine's stream (heros_get_stream): they must stay unchanged until the next
+ * call that synchronises (heros_step, heros_window_finish, any heros_get_*). */
 int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                                    const int16_t* sublocation, const double* t_in, const double* t_out);
 
@@ -197,6 +199,30 @@ int32_t heros_export_guest_candidates(heros_handle h, int64_t capacity, int32_t*
 int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                                        const int16_t* sublocation, const double* time, const double* p);
 int32_t heros_window_finish(heros_handle h, heros_step_stats* stats);
+
+/* The same exchange as FIXED-CAPACITY BLOCKS, one per peer, so that the host can run both all-to-alls of a window as
+ * equal-split collectives on the engine's stream with nothing to negotiate and no host synchronisation before
+ * heros_window_finish.  All block pointers are DEVICE pointers to n_blocks consecutive blocks of
+ * heros_*_block_bytes(capacity) bytes (block d belongs to peer / shard d; capacity a multiple of 4):
+ *   guest block     u64 count | pad | t_in f64[C] | t_out f64[C] | word u64[C] | ill_end f64[C] | person i32[C] |
+ *                   location i32[C] | sublocation i16[C]
+ *   candidate block u64 count | pad | time f64[C] | p f64[C] | person i32[C] | location i32[C] | sublocation i16[C]
+ *   heros_pack_guest_blocks_device        rows (device columns, sorted by destination; row_offsets: n_blocks + 1 HOST
+ *                                         integers) + the packed agent words of the persons -> one block per destination
+ *   heros_submit_guest_blocks_device      the blocks received from the peers -> guest stays of the window
+ *   heros_export_candidate_blocks_device  successful draws on guests -> the block of the shard that owns the person
+ *                                         (person_bases: n_blocks + 1 HOST integers, first global person id per shard)
+ *   heros_import_candidate_blocks_device  the blocks received from the peers -> candidates of the window
+ * A block that overflows is reported by heros_window_finish (HEROS_ERR_CAPACITY). */
+int64_t heros_guest_block_bytes(int64_t capacity);
+int64_t heros_candidate_block_bytes(int64_t capacity);
+int32_t heros_pack_guest_blocks_device(heros_handle h, int32_t n_blocks, const int64_t* row_offsets, const int32_t* person,
+                                       const int32_t* location, const int16_t* sublocation, const double* t_in,
+                                       const double* t_out, int64_t capacity, void* blocks_out);
+int32_t heros_submit_guest_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks);
+int32_t heros_export_candidate_blocks_device(heros_handle h, int32_t n_blocks, const int32_t* person_bases,
+                                             int64_t capacity, void* blocks_out);
+int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks);
 
 /* ---- outputs ---- */
 /* infection events (what the medlabs engine applies from InfectionRecord.infectedPersons), ordered by (time, person);

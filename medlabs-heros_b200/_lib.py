@@ -85,6 +85,12 @@ SIGNATURES = {
     "heros_export_guest_candidates": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_import_candidates_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_window_finish": (C.c_int32, [_P, C.POINTER(StepStats)]),
+    "heros_guest_block_bytes": (C.c_int64, [C.c_int64]),
+    "heros_candidate_block_bytes": (C.c_int64, [C.c_int64]),
+    "heros_pack_guest_blocks_device": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "heros_submit_guest_blocks_device": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
+    "heros_export_candidate_blocks_device": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P]),
+    "heros_import_candidate_blocks_device": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
     "heros_get_infections": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_transitions": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_phase_counts": (C.c_int32, [_P, _P]),

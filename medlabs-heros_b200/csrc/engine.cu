@@ -552,6 +552,140 @@ __global__ void __launch_bounds__(TPB) k_import_candidates(uint32_t n, const uin
     cand_p[slot] = p[i];
 }
 
+// ---- multi-GPU, block exchange: fixed-capacity blocks, one per peer, so that a window's two all-to-alls are
+//      equal-split collectives with nothing to negotiate and no host synchronisation in between --------------------------
+// guest block   : u64 count | pad | t_in f64[C] | t_out f64[C] | word u64[C] | ill_end f64[C] | person i32[C] |
+//                 loc i32[C] | sub i16[C]                                  (C a multiple of 4: every column 8-byte aligned)
+// candidate block: u64 count | pad | time f64[C] | p f64[C] | person i32[C] | loc i32[C] | sub i16[C]
+constexpr int MAX_PEERS = 64;
+__host__ __device__ inline size_t guest_block_bytes(size_t C) { return 16 + 42 * C; }
+__host__ __device__ inline size_t candidate_block_bytes(size_t C) { return 16 + 26 * C; }
+struct PeerOffsets { long long v[MAX_PEERS + 1]; };
+struct PeerBases { int v[MAX_PEERS + 1]; };
+
+__global__ void __launch_bounds__(TPB) k_pack_guest_blocks(uint32_t n_rows, PeerOffsets off, int n_blocks,
+                                                           const int32_t* person, const int32_t* loc, const int16_t* sub,
+                                                           const double* tin, const double* tout, uint32_t person_base,
+                                                           uint32_t n_agents, const uint64_t* view, const double* ill_end,
+                                                           uint32_t C, unsigned char* out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t bb = guest_block_bytes(C);
+    if (i < (uint32_t) n_blocks)
+        *reinterpret_cast<unsigned long long*>(out + (size_t) i * bb) = (unsigned long long) (off.v[i + 1] - off.v[i]);
+    if (i >= n_rows) return;
+    int d = 0;
+    while (d + 1 < n_blocks && (long long) i >= off.v[d + 1]) ++d;
+    const uint32_t j = i - (uint32_t) off.v[d];
+    if (j >= C) return;
+    unsigned char* b = out + (size_t) d * bb + 16;
+    const uint32_t local = (uint32_t) person[i] - person_base;
+    uint64_t v = 0;
+    double e = bits_f64(0x7ff0000000000000ull);
+    if (local < n_agents)
+    {
+        v = view[local];
+        if (view_ends(v)) e = ill_end[local];
+    }
+    reinterpret_cast<double*>(b)[j] = tin[i];
+    reinterpret_cast<double*>(b + 8 * (size_t) C)[j] = tout[i];
+    reinterpret_cast<uint64_t*>(b + 16 * (size_t) C)[j] = v;
+    reinterpret_cast<double*>(b + 24 * (size_t) C)[j] = e;
+    reinterpret_cast<int32_t*>(b + 32 * (size_t) C)[j] = person[i];
+    reinterpret_cast<int32_t*>(b + 36 * (size_t) C)[j] = loc[i];
+    reinterpret_cast<int16_t*>(b + 40 * (size_t) C)[j] = sub[i];
+}
+
+__global__ void __launch_bounds__(TPB) k_submit_guest_blocks(int n_blocks, uint32_t C, const unsigned char* blocks,
+                                                             double T1, int32_t loc_base, const uint32_t* loc_first_key,
+                                                             const int16_t* loc_nsub, uint32_t n_loc, uint32_t* gid,
+                                                             uint64_t* gview, double* gill_end, uint32_t* gkey,
+                                                             double* gtin, double* gtout, uint32_t* grank, uint32_t* count,
+                                                             Counters* ctr)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t) n_blocks * C) return;
+    const uint32_t bk = idx / C, j = idx % C;
+    const size_t bb = guest_block_bytes(C);
+    const unsigned char* b = blocks + (size_t) bk * bb;
+    const unsigned long long cnt = *reinterpret_cast<const unsigned long long*>(b);
+    if (j == 0 && cnt > C) atomicOr(&ctr->overflow, 16u);
+    uint32_t key = KEY_NONE, rank = KEY_NONE;
+    if (j < cnt)
+    {
+        b += 16;
+        const double tin = reinterpret_cast<const double*>(b)[j], tout = reinterpret_cast<const double*>(b + 8 * (size_t) C)[j];
+        const int32_t l = reinterpret_cast<const int32_t*>(b + 36 * (size_t) C)[j] - loc_base;
+        const int32_t sb = reinterpret_cast<const int16_t*>(b + 40 * (size_t) C)[j];
+        bool ok = l >= 0 && (uint32_t) l < n_loc && sb >= 0 && tin >= 0.0 && tout > tin;
+        if (ok) ok = sb < max((int) loc_nsub[l], 1);
+        if (ok)
+        {
+            key = loc_first_key[l] + (uint32_t) sb;
+            if (tin < T1) rank = atomicAdd(&count[key], 1u);
+        }
+        else
+            atomicAdd(&ctr->invalid_visits, 1u);
+        gid[idx] = (uint32_t) reinterpret_cast<const int32_t*>(b + 32 * (size_t) C)[j];
+        gview[idx] = reinterpret_cast<const uint64_t*>(b + 16 * (size_t) C)[j];
+        gill_end[idx] = reinterpret_cast<const double*>(b + 24 * (size_t) C)[j];
+        gtin[idx] = tin;
+        gtout[idx] = tout;
+    }
+    gkey[idx] = key;
+    grank[idx] = rank;
+}
+
+__global__ void k_zero_block_headers(int n_blocks, size_t block_bytes, unsigned char* out)
+{
+    if ((int) threadIdx.x < n_blocks) *reinterpret_cast<unsigned long long*>(out + threadIdx.x * block_bytes) = 0ull;
+}
+
+// successful draws on guests, routed to the block of the shard that owns the person
+__global__ void __launch_bounds__(TPB) k_export_candidate_blocks(CandArrays Cd, Counters* ctr, PeerBases bases, int n_blocks,
+                                                                 uint32_t person_base, uint32_t n_agents, uint32_t C,
+                                                                 unsigned char* out)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) Cd.cap, ctr->n_cand);
+    const size_t bb = candidate_block_bytes(C);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t gid = Cd.person[i];
+        if (gid - person_base < n_agents) continue;
+        int d = 0;
+        while (d + 1 < n_blocks && (int) gid >= bases.v[d + 1]) ++d;
+        unsigned char* b = out + (size_t) d * bb;
+        const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(b), 1ull);
+        if (slot >= C) { atomicOr(&ctr->overflow, 16u); continue; }
+        b += 16;
+        reinterpret_cast<double*>(b)[slot] = Cd.t[i];
+        reinterpret_cast<double*>(b + 8 * (size_t) C)[slot] = Cd.p[i];
+        reinterpret_cast<int32_t*>(b + 16 * (size_t) C)[slot] = (int32_t) gid;
+        reinterpret_cast<int32_t*>(b + 20 * (size_t) C)[slot] = (int32_t) (Cd.gkey[i] >> 16);
+        reinterpret_cast<int16_t*>(b + 24 * (size_t) C)[slot] = (int16_t) (Cd.gkey[i] & 0xFFFFu);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_import_candidate_blocks(int n_blocks, uint32_t C, const unsigned char* blocks,
+                                                                 uint32_t* cand_person, uint64_t* cand_gkey, double* cand_t,
+                                                                 double* cand_p, uint32_t cand_cap, Counters* ctr)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t) n_blocks * C) return;
+    const uint32_t bk = idx / C, j = idx % C;
+    const unsigned char* b = blocks + (size_t) bk * candidate_block_bytes(C);
+    const unsigned long long cnt = *reinterpret_cast<const unsigned long long*>(b);
+    if (j >= cnt) return;
+    b += 16;
+    const unsigned long long slot = atomicAdd(&ctr->n_cand, 1ull);
+    if (slot >= cand_cap) { atomicOr(&ctr->overflow, 1u); return; }
+    cand_person[slot] = (uint32_t) reinterpret_cast<const int32_t*>(b + 16 * (size_t) C)[j];
+    cand_gkey[slot] = ((uint64_t) (uint32_t) reinterpret_cast<const int32_t*>(b + 20 * (size_t) C)[j] << 16) |
+                      (uint64_t) (uint16_t) reinterpret_cast<const int16_t*>(b + 24 * (size_t) C)[j];
+    cand_t[slot] = reinterpret_cast<const double*>(b)[j];
+    cand_p[slot] = reinterpret_cast<const double*>(b + 8 * (size_t) C)[j];
+}
+
 // ---- inputs ------------------------------------------------------------------------------------------------------------
 struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub; const double* tin; const double* tout; };
 
@@ -1116,7 +1250,7 @@ int32_t window_finish(heros_handle h)
     if (h->h_ctr->overflow)
     {
         char buf[160];
-        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log)",
+        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log, 16 exchange block)",
                  h->h_ctr->overflow);
         return fail(h, HEROS_ERR_CAPACITY, buf);
     }
@@ -1315,7 +1449,7 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     Counters zero{};
     zero.phase_counts[PH_S] = n;
     CU(h, cudaMemcpyAsync(h->d_ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    { const int32_t rc_ = sync_counters(h); if (rc_ != HEROS_OK) return rc_; }
     d_age.release(); d_female.release(); d_role.release();
     h->n_pool = 0; h->t_now = 0.0;
     h->series_t.clear(); h->series_counts.clear();
@@ -1402,8 +1536,7 @@ int32_t heros_expose(heros_handle h, int32_t n, const int32_t* person, const dou
     k_expose<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, h->st_tin.p,
                                                    h->n_agents);
     CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(h->stream));
-    return HEROS_OK;
+    return sync_counters(h);  // also refreshes the host copy of the counters (transitions, phase counts)
 }
 
 int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_age, int32_t max_age,
@@ -1485,10 +1618,7 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
     if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
     if (n == 0) return HEROS_OK;
     cudaSetDevice(h->cfg.device);
-    rc = submit_from_device(h, n, person, loc, sub, tin, tout);
-    if (rc != HEROS_OK) return rc;
-    CU(h, cudaStreamSynchronize(h->stream));
-    return HEROS_OK;
+    return submit_from_device(h, n, person, loc, sub, tin, tout);  // asynchronous on the engine stream
 }
 
 static void begin_stats(heros_handle h, Counters& before)
@@ -1534,10 +1664,8 @@ int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
     if (!(h->cfg.window_hours <= latent - 1e-3))
         return fail(h, HEROS_ERR_UNSUPPORTED, "window_hours must be below the latent period of the transmission model");
     cudaSetDevice(h->cfg.device);
-    rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
     Counters before;
-    begin_stats(h, before);
+    begin_stats(h, before);  // the host copy of the counters is current: every call that changes them refreshes it
     heros_step_stats st{};
     CU(h, cudaEventRecord(h->ev[0], h->stream));
     while (h->t_now < t_until)
@@ -1575,7 +1703,6 @@ int32_t heros_window_begin(heros_handle h, double t_until)
     if (!(t_until > h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until must lie after the engine time");
     if ((rc = check_window_length(h, t_until)) != HEROS_OK) return rc;
     cudaSetDevice(h->cfg.device);
-    if ((rc = sync_counters(h)) != HEROS_OK) return rc;
     begin_stats(h, h->win_before);
     CU(h, cudaEventRecord(h->ev[0], h->stream));
     return window_begin(h, t_until);
@@ -1665,6 +1792,92 @@ int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t*
                                                               h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int64_t heros_guest_block_bytes(int64_t capacity) { return capacity > 0 ? (int64_t) guest_block_bytes((size_t) capacity) : 0; }
+int64_t heros_candidate_block_bytes(int64_t capacity) { return capacity > 0 ? (int64_t) candidate_block_bytes((size_t) capacity) : 0; }
+
+static int32_t check_blocks(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
+{
+    if (!h || !blocks) return HEROS_ERR_INVALID;
+    if (n_blocks < 1 || n_blocks > MAX_PEERS) return fail(h, HEROS_ERR_INVALID, "between 1 and 64 peer blocks");
+    if (capacity < 4 || (capacity & 3) || capacity > (1 << 28)) return fail(h, HEROS_ERR_INVALID, "block capacity must be a multiple of 4");
+    return HEROS_OK;
+}
+
+int32_t heros_pack_guest_blocks_device(heros_handle h, int32_t n_blocks, const int64_t* row_offsets, const int32_t* person,
+                                       const int32_t* location, const int16_t* sublocation, const double* t_in,
+                                       const double* t_out, int64_t capacity, void* blocks_out)
+{
+    int32_t rc = check_blocks(h, n_blocks, capacity, blocks_out);
+    if (rc != HEROS_OK) return rc;
+    if (!row_offsets) return HEROS_ERR_INVALID;
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest blocks are packed between heros_window_begin and heros_window_transmit");
+    PeerOffsets off{};
+    for (int d = 0; d <= n_blocks; ++d) off.v[d] = row_offsets[d];
+    for (int d = 0; d < n_blocks; ++d)
+    {
+        if (off.v[d + 1] < off.v[d] || off.v[0] != 0) return fail(h, HEROS_ERR_INVALID, "row offsets must ascend from 0");
+        if (off.v[d + 1] - off.v[d] > capacity) return fail(h, HEROS_ERR_CAPACITY, "more rows for a peer than the block capacity");
+    }
+    const int64_t n = off.v[n_blocks];
+    if (n > 0 && (!person || !location || !sublocation || !t_in || !t_out)) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    k_pack_guest_blocks<<<blocks_for((size_t) std::max<int64_t>(n, n_blocks)), TPB, 0, h->stream>>>(
+        (uint32_t) n, off, n_blocks, person, location, sublocation, t_in, t_out, h->person_base, h->n_agents, h->d_view.p,
+        h->d_ill_end.p, (uint32_t) capacity, (unsigned char*) blocks_out);
+    CU(h, cudaGetLastError());
+    return HEROS_OK;
+}
+
+int32_t heros_submit_guest_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
+{
+    int32_t rc = check_blocks(h, n_blocks, capacity, blocks);
+    if (rc != HEROS_OK) return rc;
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are submitted between heros_window_begin and heros_window_transmit");
+    if (h->n_guest != 0) return fail(h, HEROS_ERR_INVALID, "guest blocks cannot be combined with other guest submissions of the window");
+    cudaSetDevice(h->cfg.device);
+    const size_t tot = (size_t) n_blocks * (size_t) capacity;
+    CU(h, h->g_gid.ensure(tot)); CU(h, h->g_key.ensure(tot)); CU(h, h->g_rank.ensure(tot)); CU(h, h->g_view.ensure(tot));
+    CU(h, h->g_ill_end.ensure(tot)); CU(h, h->g_tin.ensure(tot)); CU(h, h->g_tout.ensure(tot));
+    k_submit_guest_blocks<<<blocks_for(tot), TPB, 0, h->stream>>>(
+        n_blocks, (uint32_t) capacity, (const unsigned char*) blocks, h->win_T1, h->location_base, h->d_loc_base.p,
+        h->d_loc_nsub.p, h->n_loc, h->g_gid.p, h->g_view.p, h->g_ill_end.p, h->g_key.p, h->g_tin.p, h->g_tout.p,
+        h->g_rank.p, h->bk_count.p, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    h->n_guest = (uint32_t) tot;
+    return HEROS_OK;
+}
+
+int32_t heros_export_candidate_blocks_device(heros_handle h, int32_t n_blocks, const int32_t* person_bases, int64_t capacity,
+                                             void* blocks_out)
+{
+    int32_t rc = check_blocks(h, n_blocks, capacity, blocks_out);
+    if (rc != HEROS_OK) return rc;
+    if (!person_bases) return HEROS_ERR_INVALID;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are exported between heros_window_transmit and heros_window_finish");
+    PeerBases bases{};
+    for (int d = 0; d <= n_blocks; ++d) bases.v[d] = person_bases[d];
+    cudaSetDevice(h->cfg.device);
+    k_zero_block_headers<<<1, MAX_PEERS, 0, h->stream>>>(n_blocks, candidate_block_bytes((size_t) capacity), (unsigned char*) blocks_out);
+    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    k_export_candidate_blocks<<<h->n_sm * 2, TPB, 0, h->stream>>>(C, h->d_ctr.p, bases, n_blocks, h->person_base, h->n_agents,
+                                                                 (uint32_t) capacity, (unsigned char*) blocks_out);
+    CU(h, cudaGetLastError());
+    return HEROS_OK;
+}
+
+int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
+{
+    int32_t rc = check_blocks(h, n_blocks, capacity, blocks);
+    if (rc != HEROS_OK) return rc;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are imported between heros_window_transmit and heros_window_finish");
+    cudaSetDevice(h->cfg.device);
+    k_import_candidate_blocks<<<blocks_for((size_t) n_blocks * (size_t) capacity), TPB, 0, h->stream>>>(
+        n_blocks, (uint32_t) capacity, (const unsigned char*) blocks, h->cand_person.p, h->cand_gkey.p, h->cand_t.p,
+        h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
+    CU(h, cudaGetLastError());
     return HEROS_OK;
 }
 
@@ -1837,9 +2050,9 @@ int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, 
     k_set_agent_state<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, d_phase.p,
                                                             d_exp.p, now, h->n_agents);
     CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(h->stream));
+    rc = sync_counters(h);
     d_phase.release(); d_exp.release();
-    return HEROS_OK;
+    return rc;
 }
 
 int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sublocation, double* out)

@@ -166,6 +166,32 @@ class HerosEngine:
         self._check(self._lib.heros_import_candidates_device(self._h, n, *(C.c_void_p(x) for x in
                                                              (person, loc, sub, t, p))))
 
+    # ---- the same exchange as fixed-capacity blocks (no host synchronisation inside a window) ----
+    def guest_block_bytes(self, capacity: int) -> int:
+        return int(self._lib.heros_guest_block_bytes(int(capacity)))
+
+    def candidate_block_bytes(self, capacity: int) -> int:
+        return int(self._lib.heros_candidate_block_bytes(int(capacity)))
+
+    def pack_guest_blocks(self, row_offsets, person: int, loc: int, sub: int, t_in: int, t_out: int, capacity: int,
+                          blocks_out: int):
+        off = _arr(row_offsets, np.int64)
+        self._check(self._lib.heros_pack_guest_blocks_device(self._h, len(off) - 1, _p(off), *(C.c_void_p(x) for x in
+                                                             (person, loc, sub, t_in, t_out)), int(capacity),
+                                                             C.c_void_p(blocks_out)))
+
+    def submit_guest_blocks(self, n_blocks: int, capacity: int, blocks: int):
+        self._check(self._lib.heros_submit_guest_blocks_device(self._h, int(n_blocks), int(capacity), C.c_void_p(blocks)))
+
+    def export_candidate_blocks(self, person_bases, capacity: int, blocks_out: int):
+        b = _arr(person_bases, np.int32)
+        self._check(self._lib.heros_export_candidate_blocks_device(self._h, len(b) - 1, _p(b), int(capacity),
+                                                                   C.c_void_p(blocks_out)))
+
+    def import_candidate_blocks(self, n_blocks: int, capacity: int, blocks: int):
+        self._check(self._lib.heros_import_candidate_blocks_device(self._h, int(n_blocks), int(capacity),
+                                                                   C.c_void_p(blocks)))
+
     def window_finish(self) -> Dict[str, float]:
         st = _lib.StepStats()
         self._check(self._lib.heros_window_finish(self._h, C.byref(st)))

@@ -200,3 +200,101 @@ def step_window_in_process(shards: List[ShardedEngine], t_until: float, remotes:
     parts = [split_by_counts(c, n.tolist()) for c, n in out2]
     inbox = [concat_columns([parts[src][dst] for src in range(world)], CANDIDATE_COLUMNS, dev) for dst in range(world)]
     return run(lambda s, c: s.finish(c), inbox)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the same window with fixed-capacity blocks: two equal-split all-to-alls, no host synchronisation inside the window
+# ---------------------------------------------------------------------------------------------------------------------
+def sort_by_destination(columns: Dict[str, "np.ndarray"], location_bases, world: int):
+    """Host-side (numpy) preparation of a shard's remote stays: rows grouped by the rank that owns the location, plus the
+    world + 1 row offsets heros_pack_guest_blocks_device takes.  Done by whoever produces the stays (the schedule)."""
+    import numpy as np
+    bases = np.asarray(location_bases, np.int64)
+    dest = np.searchsorted(bases[1:], columns["loc"].astype(np.int64), side="right")
+    order = np.argsort(dest, kind="stable")
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(dest, minlength=world)[:world])]).astype(np.int64)
+    return {k: v[order] for k, v in columns.items()}, offsets
+
+
+class BlockExchange:
+    """Per-shard buffers and the window driver of the block exchange (heros_pack_guest_blocks_device and friends).
+    ``guest_capacity`` / ``candidate_capacity``: rows per peer block, the same on every rank."""
+
+    VISIT_COLUMNS = ("person", "loc", "sub", "t_in", "t_out")
+
+    def __init__(self, shard: ShardedEngine, guest_capacity: int, candidate_capacity: int = 16384):
+        self.shard = shard
+        eng, world, dev = shard.engine, shard.world, shard.device
+        self.gc = max(4, (int(guest_capacity) + 3) // 4 * 4)
+        self.cc = max(4, (int(candidate_capacity) + 3) // 4 * 4)
+        self.g_bytes, self.c_bytes = eng.guest_block_bytes(self.gc), eng.candidate_block_bytes(self.cc)
+        self.g_send = torch.zeros(world * self.g_bytes, dtype=torch.uint8, device=dev)
+        self.g_recv = torch.zeros_like(self.g_send)
+        self.c_send = torch.zeros(world * self.c_bytes, dtype=torch.uint8, device=dev)
+        self.c_recv = torch.zeros_like(self.c_send)
+        self.person_bases = shard.person_bases.to(torch.int32).numpy()
+
+    # the three phases, separated by the two exchanges
+    def begin_and_pack(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets):
+        sh, eng = self.shard, self.shard.engine
+        eng.window_begin(t_until)
+        if remote is not None and remote["person"].device != sh.device:  # pinned host columns: H2D on the engine stream
+            remote = {k: v.to(sh.device, non_blocking=True) for k, v in remote.items()}
+        self._keep = remote  # read asynchronously by the pack kernel
+        ptrs = [0] * 5 if remote is None or remote["person"].numel() == 0 else [remote[k].data_ptr() for k in self.VISIT_COLUMNS]
+        sh.sent_stays += int(row_offsets[-1])
+        eng.pack_guest_blocks(row_offsets, *ptrs, self.gc, self.g_send.data_ptr())
+
+    def guests_in_and_transmit(self):
+        sh, eng = self.shard, self.shard.engine
+        eng.submit_guest_blocks(sh.world, self.gc, self.g_recv.data_ptr())
+        eng.window_transmit()
+        eng.export_candidate_blocks(self.person_bases, self.cc, self.c_send.data_ptr())
+
+    def candidates_in_and_finish(self):
+        sh, eng = self.shard, self.shard.engine
+        eng.import_candidate_blocks(sh.world, self.cc, self.c_recv.data_ptr())
+        return eng.window_finish()
+
+    def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets, group=None):
+        """One window over torch.distributed; everything is enqueued on the engine stream, the only host
+        synchronisation is the one at the end of heros_window_finish."""
+        import torch.distributed as dist
+        with self.shard.on_stream():
+            self.begin_and_pack(t_until, remote, row_offsets)
+            dist.all_to_all_single(self.g_recv, self.g_send, group=group)
+            self.guests_in_and_transmit()
+            dist.all_to_all_single(self.c_recv, self.c_send, group=group)
+            return self.candidates_in_and_finish()
+
+
+def step_window_blocks_in_process(exchanges: List[BlockExchange], t_until: float, remotes, offsets):
+    """The block exchange for several shards living in ONE process: the all-to-alls become block transposes."""
+    world = len(exchanges)
+    dev = exchanges[0].shard.device
+
+    def run(fn):
+        out = []
+        for x in exchanges:
+            with x.shard.on_stream():
+                out.append(fn(x))
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        return out
+
+    def transpose(send_of, recv_of, nbytes):
+        for dst in range(world):
+            for src in range(world):
+                recv_of(exchanges[dst])[src * nbytes:(src + 1) * nbytes] = send_of(exchanges[src])[dst * nbytes:(dst + 1) * nbytes]
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
+    for x, r, o in zip(exchanges, remotes, offsets):
+        with x.shard.on_stream():
+            x.begin_and_pack(t_until, r, o)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    transpose(lambda x: x.g_send, lambda x: x.g_recv, exchanges[0].g_bytes)
+    run(lambda x: x.guests_in_and_transmit())
+    transpose(lambda x: x.c_send, lambda x: x.c_recv, exchanges[0].c_bytes)
+    return run(lambda x: x.candidates_in_and_finish())
