@@ -453,7 +453,7 @@ def run_ours(args):
     }
     if world > 1:
         line["cross_tile_stays_per_step_rank0"] = remote_rows
-    else:
+    elif args.cpu_days > 0:
         # ---- cpu_baseline: the oracle on a bounded sample (first cpu_days days), checked against the GPU run ----
         cpu_days = min(args.cpu_days, total)
         sim = oracle_objects(args, props, city)
