@@ -132,15 +132,17 @@ __device__ __forceinline__ void progress_agent(const AgentArrays& A, uint32_t a,
     if (v != v0) A.view[a] = v;
 }
 
-struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; };
+struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; uint32_t* rank; };
 
 // ---- occupancy bucketing: a counting sort over the dense sub-location keys ---------------------------------------------
 // Replaces the per-location TIntSets the medlabs engine updates on every addPerson / removePerson.
-// 1. k_window_open    every active stay takes a ticket at its sub-location: rank = atomicAdd(count[key], 1).  The same
-//                     pass runs the disease-phase state machine of every agent (its open stay is one of the stays) and
-//                     moves the pool stays that outlive the window into the other pool buffer (retire).
+// 1. tickets          every stay of the window takes a ticket at its sub-location: rank = atomicAdd(count[key], 1).
+//                     A submitted stay takes it on arrival (k_submit); k_window_open does it for the open stay of every
+//                     agent and for the stays carried over from earlier windows, and runs the disease-phase state machine.
 // 2. k_scan_lookback  seg_start = exclusive prefix sum of the counts (n_keys + 1 entries), single pass
-// 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]
+// 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]; the stays
+//                     that outlive the window move to the other pool buffer on the way (retire).  A stay that took a
+//                     ticket on arrival but only begins after the window leaves a dead record in its slot.
 // The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
 // (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
 struct GuestArrays
@@ -156,22 +158,23 @@ constexpr int IPT = 4;
 inline int item_blocks(size_t n) { return (int) ((n + (size_t) TPB * IPT - 1) / ((size_t) TPB * IPT)); }
 
 __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32_t n_agents, double T1, PoolArrays P,
-                                                     PoolArrays keep, uint32_t n_pool, uint32_t pool_blocks,
+                                                     uint32_t n_carried, uint32_t pool_blocks,
                                                      const uint32_t* __restrict__ open_key,
                                                      const double* __restrict__ open_tin, uint32_t* count,
-                                                     uint32_t* __restrict__ rank)
+                                                     uint32_t* __restrict__ agent_rank)
 {
     if (blockIdx.x < pool_blocks)
     {
+        // stays carried over from earlier windows (the newer ones took their ticket when they were submitted)
         const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
-        uint32_t person[IPT], key[IPT], r[IPT];
-        double tin[IPT], tout[IPT];
+        uint32_t key[IPT], r[IPT];
+        double tin[IPT];
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
         {
             const uint32_t i = base + k * TPB;
-            key[k] = KEY_NONE; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0;
-            if (i < n_pool) { key[k] = P.key[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; person[k] = P.person[i]; }
+            key[k] = KEY_NONE; tin[k] = 0.0;
+            if (i < n_carried) { key[k] = P.key[i]; tin[k] = P.tin[i]; }
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
@@ -180,26 +183,7 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
         for (int k = 0; k < IPT; ++k)
         {
             const uint32_t i = base + k * TPB;
-            if (i < n_pool) rank[i] = r[k];
-        }
-        // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
-#pragma unroll
-        for (int k = 0; k < IPT; ++k)
-        {
-            const bool kept = key[k] != KEY_NONE && !(tout[k] < T1);
-            const unsigned m = __ballot_sync(0xffffffffu, kept);
-            if (m)
-            {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                unsigned long long at = 0;
-                if (lane == leader) at = atomicAdd(&A.ctr->n_keep, (unsigned long long) __popc(m));
-                at = __shfl_sync(0xffffffffu, at, leader);
-                if (kept)
-                {
-                    const uint32_t j = (uint32_t) at + __popc(m & ((1u << lane) - 1u));
-                    keep.person[j] = person[k]; keep.key[j] = key[k]; keep.tin[j] = tin[k]; keep.tout[j] = tout[k];
-                }
-            }
+            if (i < n_carried) P.rank[i] = r[k];
         }
     }
     else
@@ -221,7 +205,7 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
         for (int k = 0; k < IPT; ++k)
         {
             const uint32_t a = base + k * TPB;
-            if (a < n_agents) rank[n_pool + a] = r[k];
+            if (a < n_agents) agent_rank[a] = r[k];
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
@@ -232,13 +216,16 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n_pool, uint32_t pool_blocks,
-                                                        const uint32_t* __restrict__ open_key,
+constexpr uint64_t DEAD_VIEW = (uint64_t) PH_R << 4;  // neither ill nor susceptible: the record of a slot nobody is in
+
+__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, PoolArrays keep, uint32_t n_pool,
+                                                        uint32_t pool_blocks, const uint32_t* __restrict__ open_key,
                                                         const double* __restrict__ open_tin, uint32_t n_agents,
-                                                        uint32_t agent_blocks, GuestArrays G, uint32_t person_base,
-                                                        const uint32_t* __restrict__ rank,
+                                                        uint32_t agent_blocks, const uint32_t* __restrict__ agent_rank,
+                                                        GuestArrays G, uint32_t person_base, double T1,
                                                         const uint32_t* __restrict__ seg_start,
-                                                        const uint64_t* __restrict__ view, StayRec* __restrict__ rec)
+                                                        const uint64_t* __restrict__ view, StayRec* __restrict__ rec,
+                                                        Counters* ctr)
 {
     uint32_t r[IPT], key[IPT], person[IPT], pad[IPT], dst[IPT];
     double tin[IPT], tout[IPT];
@@ -250,14 +237,42 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
         for (int k = 0; k < IPT; ++k)
         {
             const uint32_t i = base + k * TPB;
-            r[k] = KEY_NONE; key[k] = 0; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = 0;
-            if (i < n_pool) { r[k] = rank[i]; key[k] = P.key[i]; person[k] = P.person[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; }
+            r[k] = KEY_NONE; key[k] = KEY_NONE; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = 0;
+            if (i < n_pool) { r[k] = P.rank[i]; key[k] = P.key[i]; person[k] = P.person[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; }
+        }
+        // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+        {
+            const bool kept = key[k] != KEY_NONE && !(tout[k] < T1);
+            const unsigned m = __ballot_sync(0xffffffffu, kept);
+            if (m)
+            {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                unsigned long long at = 0;
+                if (lane == leader) at = atomicAdd(&ctr->n_keep, (unsigned long long) __popc(m));
+                at = __shfl_sync(0xffffffffu, at, leader);
+                if (kept)
+                {
+                    const uint32_t j = (uint32_t) at + __popc(m & ((1u << lane) - 1u));
+                    keep.person[j] = person[k]; keep.key[j] = key[k]; keep.tin[j] = tin[k]; keep.tout[j] = tout[k];
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
         {
             vw[k] = 0; dst[k] = 0;
-            if (r[k] != KEY_NONE) { vw[k] = view[person[k]]; dst[k] = seg_start[key[k]] + r[k]; person[k] += person_base; }
+            if (r[k] != KEY_NONE)
+            {
+                dst[k] = seg_start[key[k]] + r[k];
+                if (tin[k] < T1) { vw[k] = view[person[k]]; person[k] += person_base; }
+                else  // took its ticket on arrival but begins after this window: nobody is in the slot
+                {
+                    vw[k] = DEAD_VIEW; person[k] = 0xFFFFFFFFu;
+                    tin[k] = bits_f64(0x7ff0000000000000ull); tout[k] = bits_f64(0xfff0000000000000ull);
+                }
+            }
         }
     }
     else if (blockIdx.x < pool_blocks + agent_blocks)
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, uint32_t n
             const uint32_t a = base + k * TPB;
             r[k] = KEY_NONE; key[k] = 0; person[k] = person_base + a; tin[k] = 0.0; pad[k] = 0; vw[k] = 0;
             tout[k] = bits_f64(0x7ff0000000000000ull);
-            if (a < n_agents) { r[k] = rank[n_pool + a]; key[k] = open_key[a]; tin[k] = open_tin[a]; vw[k] = view[a]; }
+            if (a < n_agents) { r[k] = agent_rank[a]; key[k] = open_key[a]; tin[k] = open_tin[a]; vw[k] = view[a]; }
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
@@ -697,7 +712,8 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
                                                 uint32_t* open_key, double* open_tin,
                                                 const uint32_t* __restrict__ loc_base,
                                                 const int16_t* __restrict__ loc_nsub, uint32_t n_loc, uint32_t n_agents,
-                                                uint32_t person_base, int32_t loc_origin, double t_now, Counters* ctr)
+                                                uint32_t person_base, int32_t loc_origin, double t_now, uint32_t* count,
+                                                Counters* ctr)
 {
     const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
     const double inf = bits_f64(0x7ff0000000000000ull);
@@ -757,6 +773,7 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
         P.key[pool_base + i] = pk;
         P.tin[pool_base + i] = tin[k];
         P.tout[pool_base + i] = tout[k];
+        P.rank[pool_base + i] = pk != KEY_NONE ? atomicAdd(&count[pk], 1u) : KEY_NONE;  // its ticket for the next window
     }
     late = __reduce_add_sync(0xffffffffu, late);
     invalid = __reduce_add_sync(0xffffffffu, invalid);
@@ -968,7 +985,8 @@ struct heros_engine
     Counters win_before{};
 
     // pool of submitted stays (double buffered)
-    DevBuf<uint32_t> pool_person[2], pool_key[2];
+    DevBuf<uint32_t> pool_person[2], pool_key[2], pool_rank[2];  // rank: the ticket of the stay at its sub-location
+    uint32_t n_carried = 0;  // pool[0 .. n_carried) came over from earlier windows; the rest was submitted since
     DevBuf<double> pool_tin[2], pool_tout[2];
     int pool_cur = 0;
     uint32_t n_pool = 0;
@@ -1042,7 +1060,8 @@ AgentArrays agent_arrays(heros_handle h)
 
 PoolArrays pool_arrays(heros_handle h, int which)
 {
-    return PoolArrays{h->pool_person[which].p, h->pool_key[which].p, h->pool_tin[which].p, h->pool_tout[which].p};
+    return PoolArrays{h->pool_person[which].p, h->pool_key[which].p, h->pool_tin[which].p, h->pool_tout[which].p,
+                      h->pool_rank[which].p};
 }
 
 int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep)
@@ -1051,6 +1070,7 @@ int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep)
     CU(h, h->pool_key[which].ensure(n, keep, h->stream));
     CU(h, h->pool_tin[which].ensure(n, keep, h->stream));
     CU(h, h->pool_tout[which].ensure(n, keep, h->stream));
+    CU(h, h->pool_rank[which].ensure(n, keep, h->stream));
     return HEROS_OK;
 }
 
@@ -1091,21 +1111,16 @@ int32_t window_begin(heros_handle h, double T1)
     h->win_launches = 0;
     h->n_guest = 0;
     h->win_n_pool = n_pool;
-    if (h->bk_count.n < (size_t) n_keys + 1)
-    {
-        CU(h, h->bk_count.ensure((size_t) n_keys + 1));
-        CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, s));  // k_scan_lookback leaves it zeroed from then on
-    }
-    CU(h, h->bk_rank.ensure((size_t) n_pool + N));
+    (void) n_keys;
+    CU(h, h->bk_rank.ensure(N));
     { const int32_t rc_ = ensure_pool(h, oth, std::max<size_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
     CU(h, cudaEventRecord(h->ev[2], s));
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_cand, 0, sizeof(Counters) - offsetof(Counters, n_cand), s));
     // 1. disease-phase state machine, tickets, retire
-    const int pool_blocks = item_blocks(n_pool);
-    k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur),
-                                                               pool_arrays(h, oth), n_pool, (uint32_t) pool_blocks,
-                                                               h->d_open_key.p, h->d_open_tin.p, h->bk_count.p,
-                                                               h->bk_rank.p);
+    const int pool_blocks = item_blocks(h->n_carried);
+    k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur), h->n_carried,
+                                                               (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p,
+                                                               h->bk_count.p, h->bk_rank.p);
     h->win_launches += 1;
     CU(h, cudaEventRecord(h->ev[3], s));
     CU(h, cudaGetLastError());
@@ -1162,8 +1177,8 @@ int32_t window_transmit(heros_handle h)
     CU(h, cudaEventRecord(h->ev_bk[1], s));
     const int pool_blocks = item_blocks(n_pool), agent_blocks = item_blocks(N);
     k_bucket_scatter<<<pool_blocks + agent_blocks + item_blocks(h->n_guest), TPB, 0, s>>>(
-        P, n_pool, (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p, N, (uint32_t) agent_blocks, G,
-        h->person_base, h->bk_rank.p, h->seg_start.p, h->d_view.p, h->rec.p);
+        P, pool_arrays(h, h->pool_cur ^ 1), n_pool, (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p, N,
+        (uint32_t) agent_blocks, h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p);
     launches += 2;
 
     // 4. transmission
@@ -1222,8 +1237,8 @@ int32_t window_finish(heros_handle h)
     CU(h, cudaGetLastError());
     int32_t rc = sync_counters(h);
     if (rc != HEROS_OK) return rc;
-    // the stays that outlive the window were moved to the other pool buffer by k_window_open
-    h->n_pool = (uint32_t) h->h_ctr->n_keep;
+    // the stays that outlive the window were moved to the other pool buffer by k_bucket_scatter
+    h->n_pool = h->n_carried = (uint32_t) h->h_ctr->n_keep;
     h->pool_cur ^= 1;
     {
         // ev[2] start, [3] after k_window_open, [4] after bucketing, ts.mid after k_transmit_thread, [6] after the joined
@@ -1235,6 +1250,16 @@ int32_t window_finish(heros_handle h)
             float ms = 0.f;
             CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
             h->stage_ms[k] += ms;
+        }
+        if (h->cfg.flags & HEROS_FLAG_PHASE_CLOCKS)
+        {
+            // development aid: when did the kernels of the auxiliary streams finish, relative to the fork after the scatter
+            float a[4] = {0, 0, 0, 0}, mid = 0, end = 0;
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&a[k], h->ts.fork, h->ts.join[k]);
+            cudaEventElapsedTime(&mid, h->ts.fork, h->ts.mid);
+            cudaEventElapsedTime(&end, h->ts.fork, h->ev[6]);
+            fprintf(stderr, "[heros] after fork: group<2,3> %.1f us, group<1> %.1f, group<0> %.1f, thread %.1f, sub<32> %.1f, all + draw %.1f\n",
+                    a[0] * 1e3, a[1] * 1e3, a[2] * 1e3, mid * 1e3, a[3] * 1e3, end * 1e3);
         }
         cudaEvent_t bk[3] = {h->ev_bk[0], h->ev_bk[1], h->ev[4]};
         for (int k = 0; k < 2; ++k)
@@ -1318,7 +1343,7 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     if ((e = cudaEventCreate(&h->ts.fork)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreate(&h->ts.mid)) != cudaSuccess) return bail("event", e);
     for (auto& j : h->ts.join)
-        if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+        if ((e = cudaEventCreate(&j)) != cudaSuccess) return bail("event", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
     if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -1341,6 +1366,7 @@ int32_t heros_destroy(heros_handle h)
     for (int i = 0; i < 2; ++i)
     {
         h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
+        h->pool_rank[i].release();
     }
     h->bk_count.release(); h->bk_rank.release(); h->scan_status.release(); h->rec.release();
     h->seg_start.release(); h->g_rank.release(); h->cand_person.release();
@@ -1420,6 +1446,8 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
     CU(h, cudaMemcpyAsync(h->d_loc_nsub.p, n_sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_loc_param.p, lp.data(), (size_t) n * sizeof(LocParam), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->d_last_calc.p, 0, (size_t) h->n_keys * 8, h->stream));
+    CU(h, h->bk_count.ensure((size_t) h->n_keys + 1));
+    CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, h->stream));  // k_scan_lookback leaves it zeroed from then on
     CU(h, cudaStreamSynchronize(h->stream));
     return HEROS_OK;
 }
@@ -1451,7 +1479,8 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     CU(h, cudaMemcpyAsync(h->d_ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
     { const int32_t rc_ = sync_counters(h); if (rc_ != HEROS_OK) return rc_; }
     d_age.release(); d_female.release(); d_role.release();
-    h->n_pool = 0; h->t_now = 0.0;
+    h->n_pool = h->n_carried = 0; h->t_now = 0.0;
+    if (h->bk_count.p) CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, h->stream));  // tickets of dropped stays
     h->series_t.clear(); h->series_counts.clear();
     return HEROS_OK;
 }
@@ -1583,7 +1612,7 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     const PoolArrays P = pool_arrays(h, h->pool_cur);
     k_submit<<<item_blocks(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
                                                    h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc, h->n_agents,
-                                                   h->person_base, h->location_base, h->t_now, h->d_ctr.p);
+                                                   h->person_base, h->location_base, h->t_now, h->bk_count.p, h->d_ctr.p);
     CU(h, cudaGetLastError());
     h->n_pool += (uint32_t) n;
     return HEROS_OK;

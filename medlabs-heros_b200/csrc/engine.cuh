@@ -113,10 +113,12 @@ struct WindowCtx
 };
 
 // Sub-locations of > 32 stays go to the group kernels, by the number of events of the sub-location and the bound on
-// its evaluations: class 0 / 1 / 2 keep <= 256 / 1024 / 8192 events in shared memory, class 3 works in global scratch.
+// its evaluations: class 0 / 1 / 2 keep <= 256 / 1024 / 4096 events in shared memory (17 / 66 / 126 KB per group, so
+// that groups of all classes fit on an SM side by side), class 3 works in global scratch.
 // The lists are filled by the prefix-sum kernel (it sees every bucket size), so the group kernels can start as soon as
 // the stays are in bucket order, side by side with the kernel that streams the small sub-locations.
 constexpr int BLOCK_P_CAP = 2048;  // evaluations per segment the shared-memory group kernels keep probabilities for
+constexpr int BLOCK_S_CAP = 4096;  // events per segment of the largest shared-memory class
 struct BigLists
 {
     uint32_t* blk_seg[4]; uint32_t blk_cap;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
     const uint32_t slots = b.need_enters ? 2 * n : n;
     double r_bound = b.both ? 2.0 * n : (double) n;
     if (b.r_window < r_bound) r_bound = b.r_window;
-    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= 8192 && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
+    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= (uint32_t) BLOCK_S_CAP && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
     const unsigned long long slot = atomicAdd(&ctr->n_blk[cls], 1ull);
     if (slot >= b.blk_cap) { atomicOr(&ctr->overflow, 2u); return; }
     b.blk_seg[cls][slot] = key;

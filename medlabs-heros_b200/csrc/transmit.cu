@@ -492,7 +492,7 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 template <int CLS> struct GroupCfg;
 template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
 template <> struct GroupCfg<1> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 8192, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 1024; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
 template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
 
 // bytes of scratch of one group: 32 per staged ill stay + 17 per event + 8 per kept probability + 12 per bucket
