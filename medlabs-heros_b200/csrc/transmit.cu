@@ -490,9 +490,9 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 
 // per class: group size, groups per block, capacity in events and in kept probabilities
 template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 128, ILL_CAP = 64; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 512, ILL_CAP = 128; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 1024, ILL_CAP = 256; using idx_t = uint16_t; };
 template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
 
 // bytes of scratch of one group: 32 per staged ill stay + 17 per event + 8 per kept probability + 12 per bucket
@@ -992,9 +992,9 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     cudaStream_t s = ts.main;
     cudaEventRecord(ts.fork, s);
     for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
-    k_transmit_group<MODEL, 2><<<n_sm, 1024, smem2, ts.aux[0]>>>(c);
+    k_transmit_group<MODEL, 2><<<n_sm * 2, GroupCfg<2>::G, smem2, ts.aux[0]>>>(c);
     k_transmit_group<MODEL, 3><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
-    k_transmit_group<MODEL, 1><<<n_sm * 4, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
+    k_transmit_group<MODEL, 1><<<n_sm * 8, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
     k_transmit_group<MODEL, 0><<<n_sm * 8, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
     k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
     cudaEventRecord(ts.mid, s);
