@@ -168,6 +168,39 @@ int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, co
 int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                                    const int16_t* sublocation, const double* t_in, const double* t_out);
 
+/* ---- device-side activity schedule (the producer of the stays).  Replaces, for the locators the
+ *      engine implements, the per-person activity loop of the medlabs engine: week patterns "0_<phase>_<role>"
+ *      (model/HerosModel.java:484-504; Mon-Thu use the Monday pattern, factory/ConstructHerosModel.java:931-940), activity
+ *      rows (:763-942: duration / travel / until-fixed-time activities with Constant / Uniform / Triangular durations),
+ *      locators (:944-1072: 0 Home, 1 Work / School, 2 Current, 3 Nearest(type choice), 4 Random(type choice) among the
+ *      candidates within the maximum distance of the home building).  The phase that selects a day pattern is the one
+ *      held at midnight; travel time is spent outside every location.  Draws are Philox numbers keyed by
+ *      (seed, person, day, activity), so the stays do not depend on the device or the thread layout.
+ *      heros_advance_schedule(day) produces the stays of simulated day `day` for every person directly in HBM (what
+ *      heros_submit_visits would have received); heros_step then processes the day.  Capacity-constrained locators and
+ *      LocationPolicy closures are not implemented (they stay with the host-driven path). ---- */
+typedef struct heros_activity {
+    int32_t kind;      /* 0 duration activity, 1 travel, 2 until fixed time */
+    int32_t locator;   /* 0 home, 1 work / school, 2 current, 3 nearest, 4 random */
+    int32_t choice;    /* index of the location-type choice table, -1 none */
+    int32_t dist;      /* heros_distribution of the duration (hours) */
+    double min, mode, max, until;
+} heros_activity;
+/* pattern_start / pattern_count: [phase 8][role 16][day type 4 = Mon-Thu, Fri, Sat, Sun] -> slice of activities[];
+ * choice table c = entries choice_start[c] .. choice_start[c+1]) of (choice_type, choice_cum = cumulative weights);
+ * nearest / n_cand: [location][type], cand: [location][type][n_candidates] (-1 = none; only rows of home buildings are
+ * read); work_sublocation: [person]. */
+int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_activity* activities,
+                           const int32_t* pattern_start, const int32_t* pattern_count, int32_t n_choices,
+                           const int32_t* choice_start, const int32_t* choice_type, const double* choice_cum,
+                           int32_t n_types, int32_t accommodation_type, int32_t n_candidates, const int32_t* nearest,
+                           const int32_t* n_cand, const int32_t* cand, const int16_t* work_sublocation, uint64_t seed);
+int32_t heros_advance_schedule(heros_handle h, int32_t day);
+/* debugging / tests: every stay the engine currently holds (pending closed stays, then the open stay of every person
+ * with t_out = +inf), in no particular order */
+int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,
+                              double* t_in, double* t_out, int64_t* n_out);
+
 /* ---- the hot path: advance simulated time to t_until in windows of cfg.window_hours: bucket stays by
  *      sub-location, evaluate infectPeople for every movement event of the window, draw, resolve (earliest successful
  *      draw wins), run the disease-phase state machine.  stats may be NULL. ---- */

@@ -44,6 +44,11 @@ class ProgParams(C.Structure):
     _fields_ = [("fraction", C.c_double * 128 * 2 * 5), ("period", Duration * 10)]
 
 
+class Activity(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("locator", C.c_int32), ("choice", C.c_int32), ("dist", C.c_int32),
+                ("min", C.c_double), ("mode", C.c_double), ("max", C.c_double), ("until", C.c_double)]
+
+
 class StepStats(C.Structure):
     _fields_ = [("windows", C.c_int64), ("visits", C.c_int64), ("sublocations", C.c_int64),
                 ("evaluations", C.c_int64), ("draws", C.c_int64), ("infections", C.c_int64),
@@ -76,6 +81,10 @@ SIGNATURES = {
     "heros_seed_infections": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "heros_submit_visits": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_submit_visits_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "heros_set_schedule": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                       _P, _P, _P, _P, C.c_uint64]),
+    "heros_advance_schedule": (C.c_int32, [_P, C.c_int32]),
+    "heros_debug_get_stays": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_step": (C.c_int32, [_P, C.c_double, C.POINTER(StepStats)]),
     "heros_set_id_bases": (C.c_int32, [_P, C.c_int32, C.c_int32]),
     "heros_window_begin": (C.c_int32, [_P, C.c_double]),

@@ -42,7 +42,8 @@ struct Counters
     unsigned long long big_stays;    // stays of the sub-locations handed to the group kernels
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log
-    unsigned int overflow;           // bit 0 cand, 1 scratch, 2 transition log, 3 infection log
+    unsigned long long n_sched;      // closed stays produced by the last heros_advance_schedule
+    unsigned int overflow;           // bit 0 cand, 1 scratch, 2 transition log, 3 infection log, 4 exchange block, 5 pool
     unsigned int invalid_visits;     // rejected by heros_submit_visits
     unsigned int late_visits;        // t_in before the engine time
     unsigned int pad;

@@ -131,6 +131,35 @@ class HerosEngine:
         self._check(fn(self._h, n, C.c_void_p(person), C.c_void_p(loc), C.c_void_p(sub), C.c_void_p(t_in),
                        C.c_void_p(t_out)))
 
+    # ---- device-side activity schedule ----
+    def set_schedule(self, tables: Dict[str, np.ndarray], seed: int):
+        """``tables``: the arrays of ``scenario.compile_schedule`` (heros_set_schedule)."""
+        t = tables
+        acts = np.ascontiguousarray(t["activities"])
+        assert acts.dtype.itemsize == C.sizeof(_lib.Activity)
+        ps, pc = _arr(t["pattern_start"], np.int32), _arr(t["pattern_count"], np.int32)
+        cs, ct, cc = _arr(t["choice_start"], np.int32), _arr(t["choice_type"], np.int32), _arr(t["choice_cum"], np.float64)
+        near, ncand, cand = _arr(t["nearest"], np.int32), _arr(t["n_cand"], np.int32), _arr(t["cand"], np.int32)
+        wsub = _arr(t["work_sub"], np.int16)
+        self._check(self._lib.heros_set_schedule(self._h, len(acts), _p(acts), _p(ps), _p(pc), len(cs) - 1, _p(cs), _p(ct),
+                                                 _p(cc), int(t["n_types"]), int(t["accommodation_type"]),
+                                                 int(t["n_candidates"]), _p(near), _p(ncand), _p(cand), _p(wsub),
+                                                 int(seed) & (2 ** 64 - 1)))
+
+    def advance_schedule(self, day: int):
+        self._check(self._lib.heros_advance_schedule(self._h, int(day)))
+
+    def debug_stays(self) -> Dict[str, np.ndarray]:
+        n = C.c_int64(0)
+        self._check(self._lib.heros_debug_get_stays(self._h, 0, None, None, None, None, None, C.byref(n)))
+        m = n.value
+        person, loc, sub = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros(m, np.int16)
+        t_in, t_out = np.zeros(m, np.float64), np.zeros(m, np.float64)
+        if m:
+            self._check(self._lib.heros_debug_get_stays(self._h, m, _p(person), _p(loc), _p(sub), _p(t_in), _p(t_out),
+                                                        C.byref(n)))
+        return dict(person=person, loc=loc, sub=sub, t_in=t_in, t_out=t_out)
+
     # ---- hot path ----
     def step(self, t_until: float) -> Dict[str, float]:
         st = _lib.StepStats()

@@ -264,6 +264,38 @@ def load_patterns(path: Optional[str] = None) -> dict:
         return json.load(f)
 
 
+ACTIVITY_DTYPE = np.dtype([("kind", np.int32), ("locator", np.int32), ("choice", np.int32), ("dist", np.int32),
+                           ("min", np.float64), ("mode", np.float64), ("max", np.float64), ("until", np.float64)])
+DAY_TYPES = ("Monday", "Friday", "Saturday", "Sunday")  # Mon-Thu share the Monday pattern
+
+
+def compile_schedule(city: "City", patterns: Optional[dict] = None) -> Dict[str, np.ndarray]:
+    """The activity patterns and locator tables of a city as the flat arrays heros_set_schedule takes: the same rows the
+    host-side ScheduleGenerator interprets, so that the device-side schedule (heros_advance_schedule) produces the same
+    stays bit for bit."""
+    pat = patterns or load_patterns()
+    acts, start, count = [], np.zeros((8, 16, 4), np.int32), np.zeros((8, 16, 4), np.int32)
+    for ph, ph_name in enumerate(pat["phases"]):
+        for r, role_name in enumerate(pat["roles"], start=1):
+            for d, day in enumerate(DAY_TYPES):
+                rows = pat["patterns"].get(f"{ph_name}|{role_name}|{day}") or pat["patterns"].get(f"{ph_name}|{role_name}|Monday")
+                if not rows:
+                    continue
+                start[ph, r, d], count[ph, r, d] = len(acts), len(rows)
+                for a in rows:
+                    acts.append((a["kind"], a["locator"], a["choice"], a["dist"], a["min"], a["mode"], a["max"], a["until"]))
+    c_start, c_type, c_cum = [0], [], []
+    for items in pat["choices"]:
+        c_type += [TYPE_ID[name] for name, _ in items]
+        c_cum += np.cumsum([p for _, p in items]).tolist()
+        c_start.append(len(c_type))
+    return dict(activities=np.array(acts, ACTIVITY_DTYPE), pattern_start=start.ravel(), pattern_count=count.ravel(),
+                choice_start=np.array(c_start, np.int32), choice_type=np.array(c_type, np.int32),
+                choice_cum=np.array(c_cum, np.float64), n_types=len(TYPE_NAMES), accommodation_type=TYPE_ID["Accommodation"],
+                n_candidates=city.n_random_candidates, nearest=city.nearest, n_cand=city.n_cand, cand=city.cand,
+                work_sub=city.work_sub)
+
+
 class ScheduleGenerator:
     """Produces, day by day, the stays (person, location, sub-location, t_in, t_out) of every person from the week
     patterns ``0_<phase>_<role>`` (HerosModel.java:484-504; Mon-Thu use the Monday pattern, ConstructHerosModel.java

@@ -1,0 +1,84 @@
+"""Device-side activity schedule (heros_advance_schedule) against the host-side schedule generator that interprets the
+same activity rows: the stays of every day must be the same set, bit for bit, and so must the epidemic they produce
+(the phase held at midnight selects the next day's pattern, so the comparison covers the feedback too)."""
+import numpy as np
+import pytest
+
+import heros_b200 as hb
+from common import load_props, sort_events
+from heros_b200 import properties, scenario
+
+pytestmark = pytest.mark.gpu
+
+
+def make(city, props, model):
+    eng = hb.HerosEngine(model, 111)
+    city.install(eng)
+    if model == hb.MODEL_AREA:
+        eng.set_transmission_area(properties.area_params(props))
+    else:
+        eng.set_transmission_distance(properties.dist_params(props))
+    eng.set_progression(properties.prog_params(props))
+    eng.seed_infections(60)
+    return eng
+
+
+def stay_table(st):
+    order = np.lexsort((st["t_out"], st["t_in"], st["sub"], st["loc"], st["person"]))
+    return np.stack([st["person"][order].astype(np.float64), st["loc"][order].astype(np.float64),
+                     st["sub"][order].astype(np.float64), st["t_in"][order], st["t_out"][order]])
+
+
+@pytest.mark.parametrize("model", ["area", "distance"])
+def test_device_schedule_equals_host_generator(model):
+    city = scenario.City(6000, seed=7)
+    props = load_props(model)
+    props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "6.0" if model == "area" else "2.5"
+    kind = hb.MODEL_AREA if model == "area" else hb.MODEL_DISTANCE
+    days = 16  # two weekends; the first seeds turn symptomatic (home all day) and change their pattern
+    host, dev = make(city, props, kind), make(city, props, kind)
+    gen = scenario.ScheduleGenerator(city, 111)
+    dev.set_schedule(scenario.compile_schedule(city), 111)
+    n_stays = 0
+    for d in range(days):
+        st = gen.generate_day(host.agent_state()["phase"])
+        host.submit_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        dev.advance_schedule(d)
+        a, b = stay_table(host.debug_stays()), stay_table(dev.debug_stays())
+        assert a.shape == b.shape, (d, a.shape, b.shape)
+        np.testing.assert_array_equal(a, b)   # same stays, bit-identical times
+        n_stays += a.shape[1]
+        host.step(24.0 * (d + 1))
+        dev.step(24.0 * (d + 1))
+        np.testing.assert_array_equal(host.phase_counts(), dev.phase_counts())
+    assert n_stays > 100000
+    hi, di = sort_events(host.infections()), sort_events(dev.infections())
+    assert len(hi["person"]) > 200
+    for k in ("person", "loc", "sub", "time", "p"):
+        np.testing.assert_array_equal(hi[k], di[k])
+    ht, dt = sort_events(host.transitions()), sort_events(dev.transitions())
+    for k in ("person", "phase", "time"):
+        np.testing.assert_array_equal(ht[k], dt[k])
+    assert (host.agent_state()["phase"] >= 3).sum() > 10   # symptomatic / hospitalised persons changed their patterns
+    host.close()
+    dev.close()
+
+
+def test_schedule_errors():
+    city = scenario.City(800, seed=3)
+    props = load_props("distance")
+    eng = make(city, props, hb.MODEL_DISTANCE)
+    with pytest.raises(hb.HerosError):
+        eng.advance_schedule(0)               # heros_set_schedule has not been called
+    tables = scenario.compile_schedule(city)
+    bad = dict(tables)
+    bad["pattern_count"] = tables["pattern_count"].copy()
+    bad["pattern_count"][5] = 10 ** 6
+    with pytest.raises(hb.HerosError):
+        eng.set_schedule(bad, 1)
+    eng.set_schedule(tables, 1)
+    eng.advance_schedule(0)
+    eng.step(24.0)
+    with pytest.raises(hb.HerosError):
+        eng.advance_schedule(0)               # the day lies before the engine time
+    eng.close()
