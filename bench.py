@@ -377,7 +377,36 @@ def run_ours(args):
 
     e2e_seconds, e2e_wall, _ = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
     assert (box["counts"] == ref_counts).all()
+    e2e_d2h = int(box["d2h"] / args.steps)
     release(eng)
+
+    # ---- the same days with the activity schedule advanced on the device (heros_advance_schedule): no stays cross
+    #      PCIe, the host only reads the counters and the infection events of each day (single engine only) ----
+    dev_sched = None
+    if world == 1:
+        eng, _, stream = new_engine()
+        eng.set_schedule(scenario.compile_schedule(city), SEED)
+        for d in range(first_timed):
+            eng.advance_schedule(d)
+            eng.step(24.0 * (d + 1))
+        box = {"n_inf": len(eng.infections()["person"]), "d2h": 0, "counts": None}
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record(stream)
+        for d in range(first_timed, total):
+            eng.advance_schedule(d)
+            eng.step(24.0 * (d + 1))
+            read_results()
+        end.record(stream)
+        end.synchronize()
+        assert (box["counts"] == ref_counts).all(), "the device-side schedule diverged from the host-side generator"
+        ds_seconds = start.elapsed_time(end) * 1e-3
+        dev_sched = {"value": city.n_persons * 24.0 * args.steps / ds_seconds, "unit": "person-hours/s",
+                     "ms_per_step": 1e3 * ds_seconds / args.steps, "h2d_bytes_per_step": 0,
+                     "d2h_bytes_per_step": int(box["d2h"] / args.steps),
+                     "what": "heros_advance_schedule + heros_step + D2H of the phase counters and the day's infection "
+                             "events; same stays and results as the host-generated days, bit for bit"}
+        release(eng)
 
     n_total_persons = int(person_bases[-1])
     value = n_total_persons * 24.0 * args.steps / seconds
@@ -444,13 +473,15 @@ def run_ours(args):
         "timing": "CUDA events on the engine stream around the K steps, max over ranks; wall clock of the same region: "
                   f"{1e3 * wall_seconds / args.steps:.4f} ms/step",
         "e2e": {"value": e2e_value, "unit": "person-hours/s",
-                "h2d_bytes_per_step": int(np.mean(h2d_bytes[first_timed:])), "d2h_bytes_per_step": int(box["d2h"] / args.steps),
+                "h2d_bytes_per_step": int(np.mean(h2d_bytes[first_timed:])), "d2h_bytes_per_step": e2e_d2h,
                 "ms_per_step": 1e3 * e2e_seconds / args.steps, "wall_ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": int(np.sum([s["gpu_launches"] for s in stats])) + args.steps,
         "roofline": roofline,
         "infections_total": int(ref_counts[1:].sum()), "visits_per_step": visits / args.steps,
         "device_ms_per_step": stage["gpu_ms"] / args.steps,
     }
+    if dev_sched is not None:
+        line["e2e_device_schedule"] = dev_sched
     if world > 1:
         line["cross_tile_stays_per_step_rank0"] = remote_rows
     elif args.cpu_days > 0:

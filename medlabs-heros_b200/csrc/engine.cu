@@ -737,6 +737,136 @@ __device__ __forceinline__ double activity_duration(const Activity& a, double u)
     return a.mode;
 }
 
+// The day of one person.  EMIT = false only counts the stays that end; EMIT = true writes them to the pool from slot
+// `first` on (each with its ticket) and updates the open stay of the person.  Both passes make the same draws.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
+                                             double* open_tin, const PoolArrays& P, uint32_t first, uint32_t pool_end,
+                                             uint32_t* count, Counters* ctr, int day, int day_type)
+{
+    const uint64_t v = view[a];
+    const uint32_t ph = view_phase(v), role = view_role(v);
+    const double t0 = 24.0 * day, t1 = 24.0 * (day + 1);
+    uint32_t cur_key = open_key[a];
+    double cur_tin = open_tin[a];
+    if (cur_tin != cur_tin) cur_key = KEY_NONE;  // nobody in the slot
+    const uint32_t key0 = cur_key;
+    const double tin0 = cur_tin;
+    uint32_t n_e = 0;
+    auto leave = [&](double t_leave) {  // the current stay ends
+        if (cur_key != KEY_NONE && t_leave > cur_tin)
+        {
+            if (EMIT)
+            {
+                const uint32_t slot = first + n_e;
+                if (slot < pool_end)
+                {
+                    P.person[slot] = a;
+                    P.key[slot] = cur_key;
+                    P.tin[slot] = cur_tin;
+                    P.tout[slot] = t_leave;
+                    P.rank[slot] = atomicAdd(&count[cur_key], 1u);  // its ticket for the next window
+                }
+                else
+                    atomicOr(&ctr->overflow, 32u);
+            }
+            ++n_e;
+        }
+    };
+    int n_act = 0, start = 0;
+    if (ph == PH_D)  // a dead person leaves the model
+    {
+        leave(t0);
+        cur_key = KEY_NONE;
+    }
+    else if (role >= 1 && role <= 15)
+    {
+        const int idx = ((int) ph * 16 + (int) role) * 4 + day_type;
+        n_act = S.pat_count[idx];
+        start = S.pat_start[idx];
+    }
+    const int32_t home_l = S.home_loc[a];
+    const uint32_t home_key = S.loc_base[home_l] + (uint32_t) S.home_sub[a];
+    double t = t0;
+    for (int i = 0; i < n_act; ++i)
+    {
+        const Activity act = S.acts[start + i];
+        // destination
+        uint32_t dest = cur_key;  // CurrentLocator, and whoever has nowhere else to go
+        Philox4 r{0, 0, 0, 0};
+        const bool needs_draw = act.dist != 0 || (act.locator >= 3 && act.choice >= 0);
+        if (needs_draw)
+            r = philox4x32_10(a, (uint32_t) (day * 64 + i), 0u, TAG_SCHEDULE, (uint32_t) S.seed, (uint32_t) (S.seed >> 32));
+        if (act.locator == 0)
+            dest = home_key;
+        else if (act.locator == 1)
+        {
+            const int32_t wl = S.work_loc[a];
+            if (wl >= 0) dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
+        }
+        else if (act.locator >= 3 && act.choice >= 0)
+        {
+            const double u_type = (double) r.z * 0x1.0p-32;
+            const double u_cand = (double) (r.w >> 16) * 0x1.0p-16, u_sub = (double) (r.w & 0xFFFFu) * 0x1.0p-16;
+            const int c0 = S.choice_start[act.choice], c1 = S.choice_start[act.choice + 1];
+            const double x = u_type * S.choice_cum[c1 - 1];
+            int pick = 0;  // number of cumulative weights <= x (searchsorted, side = right)
+            while (pick < c1 - c0 && S.choice_cum[c0 + pick] <= x) ++pick;
+            if (pick > c1 - c0 - 1) pick = c1 - c0 - 1;
+            const int ty = S.choice_type[c0 + pick];
+            int32_t dl;
+            if (act.locator == 3)  // Nearest(type) to the home building
+                dl = S.nearest[(size_t) home_l * S.n_types + ty];
+            else  // Random(type) within the maximum distance of the home building
+            {
+                const int n = S.n_cand[(size_t) home_l * S.n_types + ty];
+                long long j = (long long) (u_cand * (double) n);
+                if (j > n - 1) j = n - 1;
+                if (j < 0) j = 0;
+                dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
+            }
+            if (ty == S.accommodation_type || dl < 0)
+                dest = home_key;
+            else
+            {
+                const int nsub = max((int) S.loc_nsub[dl], 1);
+                int ds = (int) (u_sub * (double) nsub);
+                if (ds > nsub - 1) ds = nsub - 1;
+                dest = S.loc_base[dl] + (uint32_t) ds;
+            }
+        }
+        const bool move = dest != cur_key;
+        const double u_dur = (double) ((((uint64_t) r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+        const double dur = activity_duration(act, u_dur);
+        if (act.kind == 1)  // travel: leave now, arrive after the travel time (spent outside every location)
+        {
+            if (move)
+            {
+                leave(t);
+                const double t_arr = t + dur;
+                const bool arrived = t_arr < t1;
+                cur_key = arrived ? dest : KEY_NONE;
+                cur_tin = t_arr;
+                t = t_arr;
+                if (!arrived) break;
+            }
+        }
+        else
+        {
+            if (move) { leave(t); cur_key = dest; cur_tin = t; }
+            if (act.kind == 0) t = t + dur;
+            else { const double until = t0 + act.until; t = t > until ? t : until; }
+            if (!(t < t1)) break;
+        }
+    }
+    if (EMIT && (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0))))
+    {
+        open_key[a] = cur_key;
+        open_tin[a] = cur_key != KEY_NONE ? cur_tin : bits_f64(OPEN_CLOSED);
+    }
+    return n_e;
+}
+
 __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint64_t* view,
                                                      uint32_t* open_key, double* open_tin, PoolArrays P,
                                                      uint32_t pool_base, uint32_t pool_cap, uint32_t* count, Counters* ctr,
@@ -745,112 +875,8 @@ __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uin
     __shared__ uint32_t s_w[TPB / 32];
     __shared__ uint32_t s_base;
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t e_key[MAX_DAY_ACTIVITIES];
-    double e_tin[MAX_DAY_ACTIVITIES], e_tout[MAX_DAY_ACTIVITIES];
-    uint32_t n_e = 0;
-    if (a < n_agents)
-    {
-        const uint64_t v = view[a];
-        const uint32_t ph = view_phase(v), role = view_role(v);
-        const double t0 = 24.0 * day, t1 = 24.0 * (day + 1);
-        uint32_t cur_key = open_key[a];
-        double cur_tin = open_tin[a];
-        if (cur_tin != cur_tin) cur_key = KEY_NONE;  // nobody in the slot
-        const uint32_t key0 = cur_key;
-        const double tin0 = cur_tin;
-        auto leave = [&](double t_leave) {  // the current stay ends
-            if (cur_key != KEY_NONE && t_leave > cur_tin) { e_key[n_e] = cur_key; e_tin[n_e] = cur_tin; e_tout[n_e] = t_leave; ++n_e; }
-        };
-        int n_act = 0, start = 0;
-        if (ph == PH_D)  // a dead person leaves the model
-        {
-            leave(t0);
-            cur_key = KEY_NONE;
-        }
-        else if (role >= 1 && role <= 15)
-        {
-            const int idx = ((int) ph * 16 + (int) role) * 4 + day_type;
-            n_act = S.pat_count[idx];
-            start = S.pat_start[idx];
-        }
-        const int32_t home_l = S.home_loc[a];
-        const uint32_t home_key = S.loc_base[home_l] + (uint32_t) S.home_sub[a];
-        double t = t0;
-        for (int i = 0; i < n_act; ++i)
-        {
-            const Activity act = S.acts[start + i];
-            const Philox4 r = philox4x32_10(a, (uint32_t) (day * 64 + i), 0u, TAG_SCHEDULE, (uint32_t) S.seed,
-                                            (uint32_t) (S.seed >> 32));
-            const double u_dur = (double) ((((uint64_t) r.x << 32) | r.y) >> 11) * 0x1.0p-53;
-            // destination
-            uint32_t dest = cur_key;  // CurrentLocator, and whoever has nowhere else to go
-            if (act.locator == 0)
-                dest = home_key;
-            else if (act.locator == 1)
-            {
-                const int32_t wl = S.work_loc[a];
-                if (wl >= 0) dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
-            }
-            else if (act.locator >= 3 && act.choice >= 0)
-            {
-                const double u_type = (double) r.z * 0x1.0p-32;
-                const double u_cand = (double) (r.w >> 16) * 0x1.0p-16, u_sub = (double) (r.w & 0xFFFFu) * 0x1.0p-16;
-                const int c0 = S.choice_start[act.choice], c1 = S.choice_start[act.choice + 1];
-                const double x = u_type * S.choice_cum[c1 - 1];
-                int pick = 0;  // number of cumulative weights <= x (searchsorted, side = right)
-                while (pick < c1 - c0 && S.choice_cum[c0 + pick] <= x) ++pick;
-                if (pick > c1 - c0 - 1) pick = c1 - c0 - 1;
-                const int ty = S.choice_type[c0 + pick];
-                int32_t dl;
-                if (act.locator == 3)  // Nearest(type) to the home building
-                    dl = S.nearest[(size_t) home_l * S.n_types + ty];
-                else  // Random(type) within the maximum distance of the home building
-                {
-                    const int n = S.n_cand[(size_t) home_l * S.n_types + ty];
-                    long long j = (long long) (u_cand * (double) n);
-                    if (j > n - 1) j = n - 1;
-                    if (j < 0) j = 0;
-                    dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
-                }
-                if (ty == S.accommodation_type || dl < 0)
-                    dest = home_key;
-                else
-                {
-                    const int nsub = max((int) S.loc_nsub[dl], 1);
-                    int ds = (int) (u_sub * (double) nsub);
-                    if (ds > nsub - 1) ds = nsub - 1;
-                    dest = S.loc_base[dl] + (uint32_t) ds;
-                }
-            }
-            const bool move = dest != cur_key;
-            const double dur = activity_duration(act, u_dur);
-            if (act.kind == 1)  // travel: leave now, arrive after the travel time (spent outside every location)
-            {
-                if (move)
-                {
-                    leave(t);
-                    const double t_arr = t + dur;
-                    const bool arrived = t_arr < t1;
-                    cur_key = arrived ? dest : KEY_NONE;
-                    cur_tin = t_arr;
-                    t = t_arr;
-                    if (!arrived) break;
-                }
-            }
-            else
-            {
-                if (move) { leave(t); cur_key = dest; cur_tin = t; }
-                if (act.kind == 0) t = t + dur;
-                else { const double until = t0 + act.until; t = t > until ? t : until; }
-                if (!(t < t1)) break;
-            }
-        }
-        if (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0)))
-        {
-            open_key[a] = cur_key;
-            open_tin[a] = cur_key != KEY_NONE ? cur_tin : bits_f64(OPEN_CLOSED);
-        }
-    }
+    // pass 1: how many stays end today
+    const uint32_t n_e = a < n_agents ? walk_day<false>(S, a, view, open_key, open_tin, P, 0u, 0u, count, ctr, day, day_type) : 0u;
     // room in the pool for the stays of the block: one atomic per block
     uint32_t incl = n_e;
 #pragma unroll
@@ -869,17 +895,10 @@ __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uin
     }
     if (threadIdx.x == 0) s_base = total ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) total) : 0u;
     __syncthreads();
-    const uint32_t first = s_base + off + incl - n_e;
-    for (uint32_t j = 0; j < n_e; ++j)
-    {
-        const uint32_t slot = first + j;
-        if (slot >= pool_cap) { atomicOr(&ctr->overflow, 32u); break; }
-        P.person[pool_base + slot] = a;
-        P.key[pool_base + slot] = e_key[j];
-        P.tin[pool_base + slot] = e_tin[j];
-        P.tout[pool_base + slot] = e_tout[j];
-        P.rank[pool_base + slot] = atomicAdd(&count[e_key[j]], 1u);  // its ticket for the next window
-    }
+    // pass 2: the same day again, now writing the stays
+    if (a < n_agents)
+        walk_day<true>(S, a, view, open_key, open_tin, P, pool_base + s_base + off + incl - n_e, pool_base + pool_cap, count,
+                       ctr, day, day_type);
 }
 
 // ---- inputs ------------------------------------------------------------------------------------------------------------
@@ -1188,8 +1207,9 @@ struct heros_engine
     DevBuf<uint8_t> tr_phase;
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], blk_seg[4], draw_person, draw_key;
-    DevBuf<double> draw_t, draw_p;
+    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], item_person, item_key;
+    DevBuf<unsigned long long> item_tab, item_pair;
+    DevBuf<double> tab_t, tab_p;
     DevBuf<unsigned long long> huge_off;
     DevBuf<unsigned char> scratch;
 
@@ -1205,6 +1225,7 @@ struct heros_engine
 
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;  // pinned
+    bool ctr_current = false;   // nothing that changes the counters was enqueued since h_ctr was refreshed
 
     // staging for host submissions
     DevBuf<int32_t> st_person, st_loc;
@@ -1215,9 +1236,10 @@ struct heros_engine
     std::vector<int64_t> series_counts;
 
     // sorted output caches
-    std::vector<uint32_t> o_inf_person, o_tr_person;
-    std::vector<uint64_t> o_inf_gkey;
-    std::vector<double> o_inf_t, o_inf_p, o_tr_time;
+    struct InfEvent { double t, p; uint64_t gkey; uint32_t person; };
+    std::vector<InfEvent> o_inf;
+    std::vector<uint32_t> o_tr_person;
+    std::vector<double> o_tr_time;
     std::vector<uint8_t> o_tr_phase;
     unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
 };
@@ -1269,8 +1291,13 @@ int32_t sync_counters(heros_handle h)
 {
     CU(h, cudaMemcpyAsync(h->h_ctr, h->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    h->ctr_current = true;
     return HEROS_OK;
 }
+
+// the host copy of the counters is refreshed by every call that ends with a synchronisation; getters only pay for a
+// round trip when something was enqueued since
+int32_t current_counters(heros_handle h) { return h->ctr_current ? HEROS_OK : sync_counters(h); }
 
 
 int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
@@ -1299,6 +1326,7 @@ int32_t window_begin(heros_handle h, double T1)
     const int cur = h->pool_cur, oth = cur ^ 1;
     h->win_T0 = h->t_now;
     h->win_T1 = T1;
+    h->ctr_current = false;
     h->win_launches = 0;
     h->n_guest = 0;
     h->win_n_pool = n_pool;
@@ -1346,15 +1374,16 @@ int32_t window_transmit(heros_handle h)
     CU(h, h->sub_seg[1].ensure((size_t) n_total / 8 + 16));
     for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
-    const size_t draw_cap = (size_t) n_total + (1u << 20);
-    CU(h, h->draw_person.ensure(draw_cap)); CU(h, h->draw_key.ensure(draw_cap));
-    CU(h, h->draw_t.ensure(draw_cap)); CU(h, h->draw_p.ensure(draw_cap));
+    // exact bounds: a stay leaves at most one draw item, a sub-location at most one table entry per movement event
+    CU(h, h->item_person.ensure((size_t) n_total + 1)); CU(h, h->item_key.ensure((size_t) n_total + 1));
+    CU(h, h->item_tab.ensure((size_t) n_total + 1)); CU(h, h->item_pair.ensure((size_t) n_total + 1));
+    CU(h, h->tab_t.ensure(2 * (size_t) n_total + 1)); CU(h, h->tab_p.ensure(2 * (size_t) n_total + 1));
     CU(h, h->scratch.ensure(std::min<size_t>(128 * (size_t) n_total + (1u << 20), (size_t) 4 << 30)));
 
     BigLists big{};
-    for (int k = 0; k < 4; ++k) big.blk_seg[k] = h->blk_seg[k].p;
+    for (int k = 0; k < N_CLS; ++k) big.blk_seg[k] = h->blk_seg[k].p;
     big.blk_cap = (uint32_t) h->blk_seg[0].n;
-    for (int k = 1; k < 4; ++k) big.blk_cap = (uint32_t) std::min<size_t>(big.blk_cap, h->blk_seg[k].n);
+    for (int k = 1; k < N_CLS; ++k) big.blk_cap = (uint32_t) std::min<size_t>(big.blk_cap, h->blk_seg[k].n);
     big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
     big.both = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     big.need_enters = big.both || h->cfg.model == HEROS_MODEL_DISTANCE;
@@ -1385,10 +1414,11 @@ int32_t window_transmit(heros_handle h)
     c.cand_cap = (uint32_t) h->cand_person.n;
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
     c.sub_cap = (uint32_t) std::min(h->sub_seg[0].n, h->sub_seg[1].n);
-    for (int k = 0; k < 4; ++k) c.blk_seg[k] = h->blk_seg[k].p;
+    for (int k = 0; k < N_CLS; ++k) c.blk_seg[k] = h->blk_seg[k].p;
     c.blk_cap = big.blk_cap;
-    c.draw_person = h->draw_person.p; c.draw_key = h->draw_key.p; c.draw_t = h->draw_t.p; c.draw_p = h->draw_p.p;
-    c.draw_cap = std::min(std::min(h->draw_person.n, h->draw_key.n), std::min(h->draw_t.n, h->draw_p.n));
+    c.tab_t = h->tab_t.p; c.tab_p = h->tab_p.p; c.tab_cap = std::min(h->tab_t.n, h->tab_p.n);
+    c.item_person = h->item_person.p; c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_pair = h->item_pair.p;
+    c.item_cap = std::min(std::min(h->item_person.n, h->item_key.n), std::min(h->item_tab.n, h->item_pair.n));
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
@@ -1445,12 +1475,12 @@ int32_t window_finish(heros_handle h)
         if (h->cfg.flags & HEROS_FLAG_PHASE_CLOCKS)
         {
             // development aid: when did the kernels of the auxiliary streams finish, relative to the fork after the scatter
-            float a[4] = {0, 0, 0, 0}, mid = 0, end = 0;
-            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&a[k], h->ts.fork, h->ts.join[k]);
+            float a[N_AUX] = {0, 0, 0, 0, 0}, mid = 0, end = 0;
+            for (int k = 0; k < N_AUX; ++k) cudaEventElapsedTime(&a[k], h->ts.fork, h->ts.join[k]);
             cudaEventElapsedTime(&mid, h->ts.fork, h->ts.mid);
             cudaEventElapsedTime(&end, h->ts.fork, h->ev[6]);
-            fprintf(stderr, "[heros] after fork: group<2,3> %.1f us, group<1> %.1f, group<0> %.1f, thread %.1f, sub<32> %.1f, all + draw %.1f\n",
-                    a[0] * 1e3, a[1] * 1e3, a[2] * 1e3, mid * 1e3, a[3] * 1e3, end * 1e3);
+            fprintf(stderr, "[heros] after fork: group<2> %.1f us, group<3> %.1f, group<1> %.1f, group<0> %.1f, thread %.1f, sub<32> %.1f, all + draw %.1f\n",
+                    a[0] * 1e3, a[4] * 1e3, a[1] * 1e3, a[2] * 1e3, mid * 1e3, a[3] * 1e3, end * 1e3);
         }
         cudaEvent_t bk[3] = {h->ev_bk[0], h->ev_bk[1], h->ev[4]};
         for (int k = 0; k < 2; ++k)
@@ -1566,7 +1596,8 @@ int32_t heros_destroy(heros_handle h)
     h->g_gid.release(); h->g_key.release(); h->g_view.release(); h->g_ill_end.release(); h->g_tin.release();
     h->g_tout.release(); h->d_nguest_cand.release();
     h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->sub_seg[0].release(); h->sub_seg[1].release();
-    h->draw_person.release(); h->draw_key.release(); h->draw_t.release(); h->draw_p.release();
+    h->item_person.release(); h->item_key.release(); h->item_tab.release(); h->item_pair.release();
+    h->tab_t.release(); h->tab_p.release();
     for (auto& b : h->blk_seg) b.release();
     h->huge_off.release(); h->scratch.release();
     h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
@@ -1813,6 +1844,7 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     if (rc != HEROS_OK) return rc;
     const SubmitIn in{person, loc, sub, tin, tout};
     const PoolArrays P = pool_arrays(h, h->pool_cur);
+    h->ctr_current = false;
     k_submit<<<item_blocks(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
                                                    h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc, h->n_agents,
                                                    h->person_base, h->location_base, h->t_now, h->bk_count.p, h->d_ctr.p);
@@ -1882,7 +1914,7 @@ static void add_window_stats(heros_handle h, heros_step_stats& st)
     st.windows++;
     st.visits += (int64_t) h->h_ctr->n_active;
     st.sublocations += (int64_t) h->h_ctr->n_seg;
-    st.big_sublocations += (int64_t) (h->h_ctr->n_blk[0] + h->h_ctr->n_blk[1] + h->h_ctr->n_blk[2] + h->h_ctr->n_blk[3]);
+    for (int k = 0; k < N_CLS; ++k) st.big_sublocations += (int64_t) h->h_ctr->n_blk[k];
     st.gpu_launches += h->win_launches;
 }
 
@@ -2265,33 +2297,31 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
 {
     if (!h || !n_out || first < 0 || capacity < 0) return HEROS_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
-    int32_t rc = sync_counters(h);
+    int32_t rc = current_counters(h);
     if (rc != HEROS_OK) return rc;
     const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_inf_log, h->inf_person.n);
+    if (n < h->o_inf_n || h->o_inf_n == ~0ull) { h->o_inf.clear(); h->o_inf_n = 0; }  // the log was reset
     if (n != h->o_inf_n)
     {
-        std::vector<uint32_t> per(n);
-        std::vector<uint64_t> key(n);
-        std::vector<double> t(n), pp(n);
-        if (n)
-        {
-            CU(h, cudaMemcpyAsync(per.data(), h->inf_person.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(key.data(), h->inf_gkey.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(t.data(), h->inf_t.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(pp.data(), h->inf_p.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaStreamSynchronize(h->stream));
-        }
-        std::vector<uint32_t> order(n);
-        std::iota(order.begin(), order.end(), 0u);
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return t[a] < t[b] || (t[a] == t[b] && per[a] < per[b]);
-        });
-        h->o_inf_person.resize(n); h->o_inf_gkey.resize(n); h->o_inf_t.resize(n); h->o_inf_p.resize(n);
-        for (size_t i = 0; i < n; ++i)
-        {
-            h->o_inf_person[i] = per[order[i]]; h->o_inf_gkey[i] = key[order[i]];
-            h->o_inf_t[i] = t[order[i]]; h->o_inf_p[i] = pp[order[i]];
-        }
+        // only the events logged since the last call are fetched; they are sorted and merged behind the older ones
+        // (the events of a later window are later, so the merge normally has nothing to move)
+        const size_t old = (size_t) h->o_inf_n, add = (size_t) (n - h->o_inf_n);
+        std::vector<uint32_t> per(add);
+        std::vector<uint64_t> key(add);
+        std::vector<double> t(add), pp(add);
+        CU(h, cudaMemcpyAsync(per.data(), h->inf_person.p + old, add * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(key.data(), h->inf_gkey.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(t.data(), h->inf_t.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(pp.data(), h->inf_p.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->o_inf.resize(old + add);
+        for (size_t i = 0; i < add; ++i) h->o_inf[old + i] = heros_engine::InfEvent{t[i], pp[i], key[i], per[i]};
+        auto before = [](const heros_engine::InfEvent& x, const heros_engine::InfEvent& y) {
+            return x.t < y.t || (x.t == y.t && x.person < y.person);
+        };
+        std::sort(h->o_inf.begin() + old, h->o_inf.end(), before);
+        if (old && add && before(h->o_inf[old], h->o_inf[old - 1]))
+            std::inplace_merge(h->o_inf.begin(), h->o_inf.begin() + old, h->o_inf.end(), before);
         h->o_inf_n = n;
     }
     const int64_t avail = std::max<int64_t>(0, (int64_t) n - first);
@@ -2299,12 +2329,12 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
     for (int64_t i = 0; i < m; ++i)
     {
         const size_t k = (size_t) (first + i);
-        const uint64_t gkey = h->o_inf_gkey[k];  // (global location id << 16) | sub-location
-        if (person) person[i] = (int32_t) h->o_inf_person[k];
+        const uint64_t gkey = h->o_inf[k].gkey;  // (global location id << 16) | sub-location
+        if (person) person[i] = (int32_t) h->o_inf[k].person;
         if (location) location[i] = (int32_t) (gkey >> 16);
         if (sublocation) sublocation[i] = (int16_t) (gkey & 0xFFFFu);
-        if (time) time[i] = h->o_inf_t[k];
-        if (p) p[i] = h->o_inf_p[k];
+        if (time) time[i] = h->o_inf[k].t;
+        if (p) p[i] = h->o_inf[k].p;
     }
     *n_out = avail;
     return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
@@ -2315,7 +2345,7 @@ int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, i
 {
     if (!h || !n_out || first < 0 || capacity < 0) return HEROS_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
-    int32_t rc = sync_counters(h);
+    int32_t rc = current_counters(h);
     if (rc != HEROS_OK) return rc;
     const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_tr_log, h->tr_person.n);
     if (n != h->o_tr_n)
@@ -2359,7 +2389,7 @@ int32_t heros_get_phase_counts(heros_handle h, int64_t counts[8])
 {
     if (!h || !counts) return HEROS_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
-    int32_t rc = sync_counters(h);
+    int32_t rc = current_counters(h);
     if (rc != HEROS_OK) return rc;
     for (int k = 0; k < 8; ++k) counts[k] = (int64_t) h->h_ctr->phase_counts[k];
     return HEROS_OK;
@@ -2434,8 +2464,9 @@ int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
     cudaSetDevice(h->cfg.device);
     int32_t rc = sync_counters(h);
     if (rc != HEROS_OK) return rc;
-    memcpy(clocks, h->h_ctr->dbg_clk, sizeof(h->h_ctr->dbg_clk));
+    memcpy(clocks, h->h_ctr->dbg_clk, 64 * sizeof(uint64_t));  // classes 0 - 3
     for (int k = 0; k < 4; ++k) clocks[k * 16 + 15] = h->h_ctr->n_blk[k];  // sub-locations per class, last window
+    clocks[3 * 16 + 15] += h->h_ctr->n_blk[CLS_HUGE];
     return HEROS_OK;
 }
 

@@ -35,6 +35,9 @@ constexpr uint32_t REC_GUEST = 0x80000000u;
 
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
+constexpr int N_CLS = 5;     // classes of sub-locations of > 32 stays (the group kernels)
+constexpr int CLS_HUGE = 4;  // ... the last one works in global scratch
+
 // device-side counters of one engine.  The block from `n_cand` on is zeroed at the start of every window.
 struct Counters
 {
@@ -51,15 +54,16 @@ struct Counters
     // ---- per window ----
     unsigned long long n_cand;       // candidate infections of the current window (first field of the window block)
     unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
-    unsigned long long n_blk[4];     // segments handed to the group kernels (<= 256 / 1024 / 8192 events in shared
+    unsigned long long n_blk[N_CLS]; // segments handed to the group kernels (<= 256 / 1024 / 4096 / 8192 events in shared
                                      // memory, larger ones in global scratch)
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
     unsigned long long n_active;     // active stays of the current window
-    unsigned long long n_draw;       // (stay, evaluation) pairs in the draw list
+    unsigned long long n_draw;       // draw items << 40 | (stay, evaluation) pairs they stand for
+    unsigned long long tab_top;      // entries of the table of evaluations with p > 0
     unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
-    unsigned long long dbg_clk[4][16];  // HEROS_FLAG_PHASE_CLOCKS: max cycles per phase of k_transmit_group, per class
+    unsigned long long dbg_clk[N_CLS][16];  // HEROS_FLAG_PHASE_CLOCKS: max cycles per phase of k_transmit_group, per class
 };
 template <typename T>
 struct DevBuf
@@ -104,9 +108,12 @@ struct WindowCtx
     uint32_t* cand_person; uint64_t* cand_gkey; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
     uint32_t* sub_seg[2]; uint32_t sub_cap;          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
-    uint32_t* blk_seg[4]; uint32_t blk_cap;          // ... and for the four group kernels
-    // (stay, evaluation) pairs queued by the group kernels for k_draw
-    uint32_t* draw_person; uint32_t* draw_key; double* draw_t; double* draw_p; unsigned long long draw_cap;
+    uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;      // ... and for the group kernels
+    // draws queued by the group kernels for k_draw: the evaluations with p > 0 of every sub-location (time, p), and one
+    // item per susceptible stay = a run of table entries, numbered by its first (stay, evaluation) pair
+    double* tab_t; double* tab_p; unsigned long long tab_cap;
+    uint32_t* item_person; uint32_t* item_key; unsigned long long* item_tab; unsigned long long* item_pair;
+    unsigned long long item_cap;
     unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[3]
     unsigned char* scratch; unsigned long long scratch_cap;
     uint32_t flags;
@@ -114,15 +121,16 @@ struct WindowCtx
 };
 
 // Sub-locations of > 32 stays go to the group kernels, by the number of events of the sub-location and the bound on
-// its evaluations: class 0 / 1 / 2 keep <= 256 / 1024 / 4096 events in shared memory (17 / 66 / 126 KB per group, so
-// that groups of all classes fit on an SM side by side), class 3 works in global scratch.
+// its evaluations: classes 0 - 3 keep <= 256 / 1024 / 4096 / 8192 events in shared memory (17 / 66 / 126 / 196 KB per
+// group; groups of classes 0 - 2 fit on an SM side by side), class 4 works in global scratch.
 // The lists are filled by the prefix-sum kernel (it sees every bucket size), so the group kernels can start as soon as
 // the stays are in bucket order, side by side with the kernel that streams the small sub-locations.
 constexpr int BLOCK_P_CAP = 2048;  // evaluations per segment the shared-memory group kernels keep probabilities for
-constexpr int BLOCK_S_CAP = 4096;  // events per segment of the largest shared-memory class
+constexpr int BLOCK_S_CAP = 4096;  // events per segment of class 2
+constexpr int BLOCK_S_CAP3 = 8192; // ... and of class 3, the largest shared-memory class
 struct BigLists
 {
-    uint32_t* blk_seg[4]; uint32_t blk_cap;
+    uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;
     unsigned long long* huge_off; unsigned long long scratch_cap;
     int need_enters, both;  // enter events are needed (distance model head counts / ENTER_AND_EXIT trigger)
     double r_window;        // (T1 - T0) / threshold + 2: no window holds more evaluations of one sub-location
@@ -134,11 +142,13 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
     const uint32_t slots = b.need_enters ? 2 * n : n;
     double r_bound = b.both ? 2.0 * n : (double) n;
     if (b.r_window < r_bound) r_bound = b.r_window;
-    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= (uint32_t) BLOCK_S_CAP && r_bound <= (double) BLOCK_P_CAP) ? 2 : 3));
+    const bool r_fits = r_bound <= (double) BLOCK_P_CAP;
+    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= (uint32_t) BLOCK_S_CAP && r_fits) ? 2 :
+                    ((slots <= (uint32_t) BLOCK_S_CAP3 && r_fits) ? 3 : CLS_HUGE)));
     const unsigned long long slot = atomicAdd(&ctr->n_blk[cls], 1ull);
     if (slot >= b.blk_cap) { atomicOr(&ctr->overflow, 2u); return; }
     b.blk_seg[cls][slot] = key;
-    if (cls == 3)
+    if (cls == CLS_HUGE)
     {
         unsigned long long mp = 64;
         while (mp < slots) mp <<= 1;
@@ -152,6 +162,9 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
 #endif
 
 // the engine stream, four auxiliary streams for the kernels that run side by side, and the fork / join events
-struct TransmitStreams { cudaStream_t main; cudaStream_t aux[4]; cudaEvent_t fork, mid; cudaEvent_t join[4]; };
+constexpr int N_AUX = 5;
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid; cudaEvent_t join[N_AUX]; };
+constexpr int DRAW_ITEM_SHIFT = 40;
+constexpr unsigned long long DRAW_PAIR_MASK = (1ull << DRAW_ITEM_SHIFT) - 1ull;
 
 }  // namespace heros

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
 // S = 8 or 32 lanes per queued sub-location (<= 8 / 9..32 stays); lane i of the group holds stay i (canonical order)
 // ------------------------------------------------------------------------------------------------------------------
 template <int MODEL, int S>
-__global__ void __launch_bounds__(256) k_transmit_sub(const WindowCtx c)
+__global__ void __launch_bounds__(256, 4) k_transmit_sub(const WindowCtx c)
 {
     constexpr int GPW = 32 / S;  // groups per warp
     __shared__ StayRec s_rec[8][32];
@@ -364,13 +364,25 @@ __global__ void __launch_bounds__(256) k_transmit_sub(const WindowCtx c)
     flush_stats(c, st, lane);
 }
 
-// the Philox draws of the (stay, evaluation) pairs the group kernels queued
+// The Philox draws of the group kernels' items: pair q belongs to the last item whose first pair number is <= q (the
+// items were reserved in ascending pair order) and is the (q - first pair)-th table entry from the item's first one.
 __global__ void __launch_bounds__(256) k_draw(const WindowCtx c)
 {
-    const unsigned long long n = min((unsigned long long) c.draw_cap, c.ctr->n_draw);
+    const unsigned long long packed = c.ctr->n_draw;
+    const unsigned long long n_items = min(packed >> DRAW_ITEM_SHIFT, c.item_cap), n_pairs = packed & DRAW_PAIR_MASK;
     Local st;
-    for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x)
-        draw_and_push(c, st, c.draw_person[i], c.draw_key[i], c.draw_t[i], c.draw_p[i]);
+    if (n_items)
+        for (unsigned long long q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += (unsigned long long) gridDim.x * blockDim.x)
+        {
+            unsigned long long lo = 0, hi = n_items - 1;  // item_pair[0] == 0 <= q
+            while (lo < hi)
+            {
+                const unsigned long long mid = (lo + hi + 1) >> 1;
+                if (c.item_pair[mid] <= q) lo = mid; else hi = mid - 1;
+            }
+            const unsigned long long e = c.item_tab[lo] + (q - c.item_pair[lo]);
+            draw_and_push(c, st, c.item_person[lo], c.item_key[lo], c.tab_t[e], c.tab_p[e]);
+        }
     flush_stats(c, st, threadIdx.x & 31);
 }
 
@@ -490,10 +502,11 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 
 // per class: group size, groups per block, capacity in events and in kept probabilities
 template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 128, ILL_CAP = 64; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 512, ILL_CAP = 128; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 1024, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
+template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP3, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
+template <> struct GroupCfg<4> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
 
 // bytes of scratch of one group: 32 per staged ill stay + 17 per event + 8 per kept probability + 12 per bucket
 // (budgeted 16; + slack)
@@ -511,7 +524,8 @@ template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
 // the <= 3 buckets around e + threshold; the chain start, next[start], next[next[start]] ... is materialised in
 // O(log n) rounds of pointer doubling.  Classes 0-2 keep everything in shared memory, class 3 (anything larger) in global scratch.
 template <int MODEL, int CLS>
-__global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k_transmit_group(const WindowCtx c)
+__global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK, 1024 / (GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK))
+k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register file, not the work, limits how many groups run side by side
 {
     using Cfg = GroupCfg<CLS>;
     using idx_t = typename Cfg::idx_t;
@@ -519,6 +533,7 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_w[33];
     __shared__ double s_red[2 * 32];
+    __shared__ unsigned long long s_tab;
     const int tid = grank<G>();
     const int group_in_block = G == 32 ? (int) (threadIdx.x >> 5) : 0;
     const uint32_t n_list = (uint32_t) min((unsigned long long) c.blk_cap, c.ctr->n_blk[CLS]);
@@ -613,11 +628,11 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
         // scratch: ill_rec StayRec[ILL_CAP] | ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
         //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]
-        unsigned char* base = CLS == 3 ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
+        unsigned char* base = CLS == CLS_HUGE ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
         StayRec* ill_rec = (StayRec*) base;  // the ill stays, staged next to the SM (classes 0-2)
         double* ev_t = (double*) (base + (size_t) Cfg::ILL_CAP * sizeof(StayRec));
         double* pr = ev_t + slots;
-        uint32_t* bstart = (uint32_t*) (pr + (CLS == 3 ? slots : Cfg::P_CAP));
+        uint32_t* bstart = (uint32_t*) (pr + (CLS == CLS_HUGE ? slots : Cfg::P_CAP));
         int32_t* bcur = (int32_t*) (bstart + NB + 1);
         int32_t* bsign = bcur + NB;
         idx_t* ja = (idx_t*) (bsign + NB);
@@ -669,7 +684,7 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
         auto is_cand = [&](int j) { return both || ev_k[j] == 0; };
         // 4. sort inside every bucket: each event counts the events of its bucket that precede it and moves to that
         //    rank.  Buckets hold a handful of events, so this is a few compares per event, all events in parallel.
-        if (CLS == 3)
+        if (CLS == CLS_HUGE)
         {
             double* tmp_t = pr;                  // f64[slots]
             uint8_t* tmp_k = (uint8_t*) node;    // idx[slots] >= slots bytes
@@ -882,27 +897,30 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
             clk = t_;
         }
         // 8. draws: every susceptible stay against exactly the evaluations with p > 0 it was present at, (t_in, t_out].
-        //    The evaluations with p > 0 are compacted first (ja = how many precede each evaluation, jb = their list;
-        //    the tables of steps 5-6 are dead); nothing is left to do when nobody ill was ever present.
+        //    The (stay, evaluation) pairs can be a hundred times the stays, so they are not expanded here: the
+        //    evaluations with p > 0 go to a table in global memory (ja = how many precede each evaluation; the tables of
+        //    steps 5-6 are dead), every susceptible stay leaves ONE item (person, first table entry, first pair number),
+        //    and k_draw expands the items into draws over the whole GPU.  Nothing is left to do when nobody ill was ever
+        //    present.
         const int n_pos = group_exclusive_scan<G>(R, [&](int r) { return pr[r] > 0 ? 1 : 0; }, ja, s_w);
         if (n_pos == 0) { gsync<G>(); continue; }
-        if (tid == 0) ja[R] = (idx_t) n_pos;
-        for (int r = tid; r < R; r += G)
-            if (pr[r] > 0) jb[ja[r]] = (idx_t) r;
-        if (G > 32 && tid == 0) s_w[32] = 0;
+        if (tid == 0)
+        {
+            ja[R] = (idx_t) n_pos;
+            s_tab = atomicAdd(&c.ctr->tab_top, (unsigned long long) n_pos);
+        }
         gsync<G>();
-        //    Each lane finds the range of one stay; the warp then deals out the (stay, evaluation) pairs evenly and
-        //    appends them to the draw list (k_draw makes the draws, spread over the whole GPU).
-        for (int v0 = (tid & ~31);; v0 += G)
+        const unsigned long long tab0 = s_tab;
+        for (int r = tid; r < R; r += G)
+            if (pr[r] > 0)
+            {
+                const unsigned long long e = tab0 + ja[r];
+                if (e < c.tab_cap) { c.tab_t[e] = ev_t[node[r]]; c.tab_p[e] = pr[r]; }
+                else atomicOr(&c.ctr->overflow, 2u);
+            }
+        for (int v0 = tid & ~31; v0 < n; v0 += G)
         {
             const int lane = tid & 31;
-            if (G > 32)  // batches of 32 stays are handed out on demand: their pair counts differ widely
-            {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&s_w[32], 1);
-                v0 = __shfl_sync(FULL, b, 0) * 32;
-            }
-            if (v0 >= n) break;
             const int v = v0 + lane;
             int lo = 0, cnt = 0;
             uint32_t person = 0;
@@ -928,38 +946,24 @@ __global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK) k
                 if (lane >= o) incl += t;
             }
             const int total = __shfl_sync(FULL, incl, 31);
+            const unsigned has = __ballot_sync(FULL, cnt > 0);
             if (total == 0) continue;
-            unsigned long long at = 0;  // room in the draw list for the pairs of the whole batch
-            if (lane == 0) at = atomicAdd(&c.ctr->n_draw, (unsigned long long) total);
+            // one atomic reserves items and pair numbers together, so that both ascend in the same order
+            unsigned long long at = 0;
+            if (lane == 0) at = atomicAdd(&c.ctr->n_draw, ((unsigned long long) __popc(has) << DRAW_ITEM_SHIFT) | (unsigned long long) total);
             at = __shfl_sync(FULL, at, 0);
-            for (int p0 = 0; p0 < total; p0 += 32)
+            if (cnt > 0)
             {
-                const int pi = p0 + lane;
-                int src = 0;  // first lane whose inclusive prefix exceeds pi
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
+                const unsigned long long item = (at >> DRAW_ITEM_SHIFT) + __popc(has & ((1u << lane) - 1u));
+                if (item < c.item_cap && tab0 + lo + cnt <= c.tab_cap)
                 {
-                    const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
-                    if (probe <= pi) src += step;
+                    c.item_person[item] = person;
+                    c.item_key[item] = key;
+                    c.item_tab[item] = tab0 + (unsigned long long) lo;
+                    c.item_pair[item] = (at & DRAW_PAIR_MASK) + (unsigned long long) (incl - cnt);
                 }
-                src = min(src, 31);
-                const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
-                const int s_lo = __shfl_sync(FULL, lo, src);
-                const uint32_t s_person = __shfl_sync(FULL, person, src);
-                if (pi < total)
-                {
-                    const int r = (int) jb[s_lo + (pi - (s_incl - s_cnt))];
-                    const unsigned long long slot = at + (unsigned long long) pi;
-                    if (slot < c.draw_cap)
-                    {
-                        c.draw_person[slot] = s_person;
-                        c.draw_key[slot] = key;
-                        c.draw_t[slot] = ev_t[node[r]];
-                        c.draw_p[slot] = pr[r];
-                    }
-                    else  // the list is full (its tail stays unused): draw on the spot
-                        draw_and_push(c, st, s_person, key, ev_t[node[r]], pr[r]);
-                }
+                else
+                    atomicOr(&c.ctr->overflow, 2u);
             }
         }
         gsync<G>();
@@ -979,21 +983,24 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     int dev = 0;
     cudaGetDevice(&dev);
     const size_t smem0 = group_smem_bytes<0>() * GroupCfg<0>::PER_BLOCK, smem1 = group_smem_bytes<1>(),
-                 smem2 = group_smem_bytes<2>();
+                 smem2 = group_smem_bytes<2>(), smem3 = group_smem_bytes<3>();
     if (dev >= 0 && dev < 64 && !configured[dev])
     {
         cudaFuncSetAttribute(k_transmit_group<MODEL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem0);
         cudaFuncSetAttribute(k_transmit_group<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
         cudaFuncSetAttribute(k_transmit_group<MODEL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
+        cudaFuncSetAttribute(k_transmit_group<MODEL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem3);
         configured[dev] = true;
     }
     // the group kernels (their work lists were filled by the prefix-sum kernel) start at once on the auxiliary streams,
     // side by side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds
     cudaStream_t s = ts.main;
     cudaEventRecord(ts.fork, s);
-    for (int k = 0; k < 4; ++k) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
+    for (int k = 0; k < N_AUX; ++k)
+        if (k != 3) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
     k_transmit_group<MODEL, 2><<<n_sm * 2, GroupCfg<2>::G, smem2, ts.aux[0]>>>(c);
-    k_transmit_group<MODEL, 3><<<n_sm, 1024, 0, ts.aux[0]>>>(c);
+    k_transmit_group<MODEL, 3><<<n_sm, GroupCfg<3>::G, smem3, ts.aux[4]>>>(c);
+    k_transmit_group<MODEL, 4><<<n_sm, 1024, 0, ts.aux[4]>>>(c);
     k_transmit_group<MODEL, 1><<<n_sm * 8, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
     k_transmit_group<MODEL, 0><<<n_sm * 8, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
     k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
@@ -1001,13 +1008,13 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     cudaStreamWaitEvent(ts.aux[3], ts.mid, 0);
     k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
     k_transmit_sub<MODEL, 8><<<n_sm * 8, 256, 0, s>>>(c);
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < N_AUX; ++k)
     {
         cudaEventRecord(ts.join[k], ts.aux[k]);
         cudaStreamWaitEvent(s, ts.join[k], 0);
     }
     k_draw<<<n_sm * 4, 256, 0, s>>>(c);
-    launches += 8;
+    launches += 9;
 }
 
 void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
