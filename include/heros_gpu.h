@@ -110,15 +110,20 @@ typedef struct heros_step_stats {
     double transmit_ms;       /* of which: transmission kernels (small + big segments) */
     int64_t near_ties;        /* draws with |u - p| < 1e-13 (a flip could differ from the fp64 CPU result) */
     /* device time per stage, summed over the windows of the call (CUDA events on the engine stream) */
-    double progress_ms;       /* disease-phase state machine */
-    double bucket_ms;         /* window list + radix sort by sub-location + gather + segment offsets */
-    double transmit_small_ms; /* k_transmit_thread: streams every stay of the window once */
-    double transmit_big_ms;   /* the warp / group kernels of the larger sub-locations, run side by side */
+    double progress_ms;       /* k_window_open: disease-phase state machine + tickets of open / carried-over stays */
+    double bucket_ms;         /* k_scan_lookback + k_bucket_scatter (+ retire) */
+    double transmit_small_ms; /* k_transmit_thread: streams every stay of the window once (group kernels run beside it) */
+    double transmit_big_ms;   /* from the end of k_transmit_thread to the end of k_draw: sub-warp kernels, the rest of
+                                 the group kernels, the draws */
     double resolve_ms;        /* earliest-draw-wins + expose */
-    double retire_ms;         /* pool compaction */
+    double retire_ms;         /* 0 (retire is part of k_bucket_scatter) */
     int64_t big_sublocations; /* sub-locations handled by the group kernels */
     int64_t big_stays;        /* ... and their stays */
     double bucket_count_ms, bucket_scan_ms, bucket_scatter_ms; /* the three parts of bucket_ms */
+    /* the group kernels run on auxiliary streams, side by side with k_transmit_thread and the sub-warp kernels: time
+     * from the fork (after the scatter) until each of them finished -- classes 0, 1, 2, 3 + 4 -- and until the 32-lane
+     * sub-warp kernel finished (it starts after k_transmit_thread) */
+    double group_done_ms[4], sub32_done_ms;
 } heros_step_stats;
 
 /* ---- lifecycle ---- */

@@ -57,10 +57,12 @@ class StepStats(C.Structure):
                 ("bucket_ms", C.c_double), ("transmit_small_ms", C.c_double), ("transmit_big_ms", C.c_double),
                 ("resolve_ms", C.c_double), ("retire_ms", C.c_double), ("big_sublocations", C.c_int64),
                 ("big_stays", C.c_int64), ("bucket_count_ms", C.c_double), ("bucket_scan_ms", C.c_double),
-                ("bucket_scatter_ms", C.c_double)]
+                ("bucket_scatter_ms", C.c_double), ("group_done_ms", C.c_double * 4), ("sub32_done_ms", C.c_double)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        out = {n: getattr(self, n) for n, _ in self._fields_}
+        out["group_done_ms"] = list(self.group_done_ms)
+        return out
 
 
 # every symbol include/heros_gpu.h declares: name -> (restype, argtypes)

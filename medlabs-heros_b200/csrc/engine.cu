@@ -867,14 +867,17 @@ __device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a
     return n_e;
 }
 
-__global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint64_t* view,
-                                                     uint32_t* open_key, double* open_tin, PoolArrays P,
-                                                     uint32_t pool_base, uint32_t pool_cap, uint32_t* count, Counters* ctr,
-                                                     int day, int day_type)
+__global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint32_t* order,
+                                                     const uint64_t* view, uint32_t* open_key, double* open_tin,
+                                                     PoolArrays P, uint32_t pool_base, uint32_t pool_cap, uint32_t* count,
+                                                     Counters* ctr, int day, int day_type)
 {
     __shared__ uint32_t s_w[TPB / 32];
     __shared__ uint32_t s_base;
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    // persons are visited grouped by social role: the threads of a warp then walk the same day pattern (the phase that
+    // also selects it is Susceptible for most) instead of 32 different ones
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t a = slot < n_agents ? order[slot] : n_agents;
     // pass 1: how many stays end today
     const uint32_t n_e = a < n_agents ? walk_day<false>(S, a, view, open_key, open_tin, P, 0u, 0u, count, ctr, day, day_type) : 0u;
     // room in the pool for the stays of the block: one atomic per block
@@ -1141,6 +1144,7 @@ struct heros_engine
     double stage_ms[6]{};  // window open (state machine + tickets + retire), prefix sum + scatter, transmit thread
                            // kernel, other transmit kernels + draws, resolve, (unused)
     double bucket_part_ms[3]{};  // (unused), prefix sum, scatter
+    double aux_done_ms[N_AUX]{}; // fork -> end of the work of every auxiliary stream
     int n_sm = 148;
     double t_now = 0.0;
 
@@ -1222,6 +1226,8 @@ struct heros_engine
         d_work_loc;
     DevBuf<double> s_choice_cum;
     DevBuf<int16_t> d_home_sub, d_work_sub;
+    DevBuf<uint32_t> s_order;      // persons grouped by social role
+    std::vector<uint8_t> h_role;   // host copy of the roles (heros_set_persons)
 
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;  // pinned
@@ -1472,6 +1478,12 @@ int32_t window_finish(heros_handle h)
             CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
             h->stage_ms[k] += ms;
         }
+        for (int k = 0; k < N_AUX; ++k)
+        {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, h->ts.fork, h->ts.join[k]));
+            h->aux_done_ms[k] += ms;
+        }
         if (h->cfg.flags & HEROS_FLAG_PHASE_CLOCKS)
         {
             // development aid: when did the kernels of the auxiliary streams finish, relative to the fork after the scatter
@@ -1600,7 +1612,7 @@ int32_t heros_destroy(heros_handle h)
     h->tab_t.release(); h->tab_p.release();
     for (auto& b : h->blk_seg) b.release();
     h->huge_off.release(); h->scratch.release();
-    h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
+    h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
     h->s_choice_type.release(); h->s_nearest.release(); h->s_ncand.release(); h->s_cand.release(); h->d_home_loc.release();
     h->d_work_loc.release(); h->s_choice_cum.release(); h->d_home_sub.release(); h->d_work_sub.release();
     h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
@@ -1686,6 +1698,8 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     const size_t N = (size_t) n;
     h->n_agents = (uint32_t) n;
     h->have_schedule = false;
+    h->h_role.assign((size_t) n, 0);
+    if (role) h->h_role.assign(role, role + n);
     h->d_home_loc.release(); h->d_home_sub.release(); h->d_work_loc.release();
     if (home_loc && home_sub && work_loc)  // only read by the device-side activity schedule
     {
@@ -1890,6 +1904,7 @@ static void begin_stats(heros_handle h, Counters& before)
     before = *h->h_ctr;
     for (double& m : h->stage_ms) m = 0.0;
     for (double& m : h->bucket_part_ms) m = 0.0;
+    for (double& m : h->aux_done_ms) m = 0.0;
 }
 
 static void fill_stats(heros_handle h, const Counters& before, heros_step_stats& st)
@@ -1907,6 +1922,10 @@ static void fill_stats(heros_handle h, const Counters& before, heros_step_stats&
     st.transmit_ms = h->stage_ms[2] + h->stage_ms[3];
     st.bucket_count_ms = h->bucket_part_ms[0]; st.bucket_scan_ms = h->bucket_part_ms[1];
     st.bucket_scatter_ms = h->bucket_part_ms[2];
+    // aux streams: 0 class 2, 1 class 1, 2 class 0, 3 sub-warp 32, 4 classes 3 + 4
+    st.group_done_ms[0] = h->aux_done_ms[2]; st.group_done_ms[1] = h->aux_done_ms[1];
+    st.group_done_ms[2] = h->aux_done_ms[0]; st.group_done_ms[3] = h->aux_done_ms[4];
+    st.sub32_done_ms = h->aux_done_ms[3];
 }
 
 static void add_window_stats(heros_handle h, heros_step_stats& st)
@@ -1964,6 +1983,16 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
     if (n_candidates > 0)
         CU(h, cudaMemcpyAsync(h->s_cand.p, cand, L * n_types * (size_t) n_candidates * 4, cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->d_work_sub.p, work_sublocation, N * 2, cudaMemcpyHostToDevice, s));
+    {
+        std::vector<uint32_t> order(N);  // counting sort of the persons by role, stable
+        size_t first[257] = {};
+        for (size_t a = 0; a < N; ++a) ++first[(size_t) h->h_role[a] + 1];
+        for (int r = 0; r < 256; ++r) first[r + 1] += first[r];
+        for (size_t a = 0; a < N; ++a) order[first[h->h_role[a]]++] = (uint32_t) a;
+        CU(h, h->s_order.ensure(N));
+        CU(h, cudaMemcpyAsync(h->s_order.p, order.data(), N * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaStreamSynchronize(s));
+    }
     CU(h, cudaStreamSynchronize(s));
     h->sched_max_acts = max_acts; h->sched_n_types = n_types; h->sched_n_cand = n_candidates;
     h->sched_accommodation = accommodation_type; h->sched_seed = seed;
@@ -1994,7 +2023,7 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
     S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
     static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));
-    k_advance_day<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(S, h->n_agents, h->d_view.p, h->d_open_key.p,
+    k_advance_day<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
                                                                   h->d_open_tin.p, pool_arrays(h, h->pool_cur), h->n_pool,
                                                                   (uint32_t) room, h->bk_count.p, h->d_ctr.p, day,
                                                                   DAY_TYPE[day % 7]);

@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_lib.AreaParams) == 6 * 8 and C.sizeof(_lib.DistParams) == 10 * 8
     assert C.sizeof(_lib.Duration) == 32
     assert C.sizeof(_lib.ProgParams) == 5 * 2 * 128 * 8 + 10 * 32
-    assert C.sizeof(_lib.StepStats) == 22 * 8
+    assert C.sizeof(_lib.StepStats) == 27 * 8
 
 
 def test_no_cpu_fallback_without_a_device():
