@@ -230,6 +230,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     props = load_props(args.model)
@@ -262,7 +263,7 @@ def run_ours(args):
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
-            bx = sharded.BlockExchange(sh, guest_capacity[0])
+            bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
         eng.seed_infections(N_INFECTED)
         engines.append(eng)
         return eng, bx, torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -304,7 +305,7 @@ def run_ours(args):
     # ---- record pass (untimed): the medlabs activity engine's job, done once on the host ----
     if world > 1:
         # block capacity of the guest exchange: the commuters' stays of a day, with head-room, agreed by all ranks
-        cap = torch.tensor([int(4 * max(n_commuters, 1024))], dtype=torch.int64, device=dev)
+        cap = torch.tensor([int(2 * max(n_commuters, 1024))], dtype=torch.int64, device=dev)
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
         guest_capacity[0] = int(cap.item())
     eng, bx, _ = new_engine()
