@@ -12,6 +12,7 @@ from .build import build  # noqa: F401
 from .disease import (Covid19Progression, Covid19TransmissionArea, Covid19TransmissionDistance,  # noqa: F401
                       DiseaseTransmission, HerosModel, InfectionRecord, construct_disease_model)
 from .engine import HerosEngine  # noqa: F401
+from .monitor import DiseaseMonitor, compartment_series  # noqa: F401
 from .policy import DiseasePolicy  # noqa: F401
 from . import sharded  # noqa: F401
 

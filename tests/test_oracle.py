@@ -263,3 +263,23 @@ def test_driver_progression_matches_golden_timing_band():
     sim2.add_visits([2], [0], [0], [9.5], [11.0])
     sim2.run(20.0)
     assert sim2.n_evaluations() == 2
+
+
+def test_compartment_series_from_the_transition_log():
+    """DiseaseMonitor mirror (ConstructHerosModel.java:145): the 0.5 h compartment series rebuilt from the transition
+    log equals the live phase counters at every day boundary, keeps the population constant, and has the column
+    layout of the golden spreadsheets."""
+    from common import Scenario, load_props, run_oracle
+    from heros_b200 import monitor
+    scn = Scenario(seed=3, n_persons=500, n_households=180, n_workplaces=20, n_shops=4, days=12)
+    props = load_props("area")
+    props["covidT_area.contagiousness"] = "5.0"
+    ora = run_oracle(scn, props, ob.MODEL_AREA, ob.TRIGGER_EXIT_ONLY, seed=9)
+    times, counts = monitor.compartment_series(ora["transitions"], scn.n_persons, 24.0 * scn.days, 0.5)
+    assert len(times) == 2 * 24 * scn.days + 1 and times[1] == 0.5
+    assert (counts.sum(axis=1) == scn.n_persons).all()
+    assert counts[0, 0] == scn.n_persons - len(scn.seeds) and counts[0, 1] == len(scn.seeds)   # seeds exposed at t = 0
+    np.testing.assert_array_equal(counts[48::48], ora["counts"])      # every midnight = the engine's own counters
+    assert (np.diff(counts[:, 0]) <= 0).all()                          # nobody becomes susceptible again
+    assert monitor.HEADER == ("Time(h)", "Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic",
+                              "Hospitalized", "ICU", "Dead", "Recovered")
