@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
     for (int k = 0; k < SCAN_ITEMS; ++k)
     {
         local += v[k];
-        if (v[k] > 32) queue_big(big, ctr, base + k, v[k]);  // a few thousand of half a million sub-locations
+        if (v[k] > 32 && !(big.key_total && big.key_total[base + k]))
+            queue_big(big, ctr, base + k, v[k]);  // a few thousand of half a million sub-locations
     }
     uint32_t incl = local;
 #pragma unroll
@@ -1168,6 +1169,9 @@ struct heros_engine
     DevBuf<int16_t> d_loc_nsub;
     DevBuf<LocParam> d_loc_param;
     DevBuf<double> d_last_calc;
+    DevBuf<uint8_t> d_key_total;     // total-branch locations (usually none)
+    DevBuf<TotalLoc> d_total_loc;
+    uint32_t n_total_loc = 0;
 
     uint32_t n_agents = 0;
     DevBuf<uint64_t> d_view;
@@ -1391,6 +1395,7 @@ int32_t window_transmit(heros_handle h)
     big.blk_cap = (uint32_t) h->blk_seg[0].n;
     for (int k = 1; k < N_CLS; ++k) big.blk_cap = (uint32_t) std::min<size_t>(big.blk_cap, h->blk_seg[k].n);
     big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
+    big.key_total = h->n_total_loc ? h->d_key_total.p : nullptr;
     big.both = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     big.need_enters = big.both || h->cfg.model == HEROS_MODEL_DISTANCE;
     {
@@ -1412,6 +1417,7 @@ int32_t window_transmit(heros_handle h)
     c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
     c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
     c.key_loc = h->d_key_loc.p; c.loc_param = h->d_loc_param.p; c.last_calc = h->d_last_calc.p; c.n_keys = h->n_keys;
+    c.key_total = h->n_total_loc ? h->d_key_total.p : nullptr; c.total_loc = h->d_total_loc.p; c.n_total_loc = h->n_total_loc;
     c.view = h->d_view.p; c.ill_end = h->d_ill_end.p; c.guest_ill_end = h->g_ill_end.p;
     c.person_base = h->person_base; c.n_agents = N;
     c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
@@ -1594,6 +1600,7 @@ int32_t heros_destroy(heros_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_policy.release(); h->d_prog.release(); h->d_loc_base.release(); h->d_key_loc.release();
     h->d_loc_nsub.release(); h->d_loc_param.release(); h->d_last_calc.release(); h->d_view.release();
+    h->d_key_total.release(); h->d_total_loc.release();
     h->d_next_time.release(); h->d_ill_end.release(); h->d_open_tin.release(); h->d_best_t.release();
     h->d_best_key.release(); h->d_claim.release(); h->d_open_key.release();
     for (int i = 0; i < 2; ++i)
@@ -1649,15 +1656,20 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
     cudaSetDevice(h->cfg.device);
     std::vector<uint32_t> base((size_t) n + 1);
     std::vector<LocParam> lp(n);
+    std::vector<TotalLoc> total;
     uint64_t b = 0;
     for (int i = 0; i < n; ++i)
     {
         if (type[i] >= h->n_types) return fail(h, HEROS_ERR_INVALID, "location type id out of range");
         if (n_sub[i] < 0) return fail(h, HEROS_ERR_INVALID, "negative number of sub-locations");
-        if (!h->type_infect_sub[type[i]] && n_sub[i] >= 2)
-            return fail(h, HEROS_ERR_UNSUPPORTED,
-                        "location with infectInSublocation = false and >= 2 sub-locations: the total-location branch "
-                        "(Covid19TransmissionArea.java:198-246) is only available through heros_infect_people");
+        if (!h->type_infect_sub[type[i]] && n_sub[i] >= 2)  // total-location branch (TArea:149 / TDist:131)
+        {
+            TotalLoc t{};
+            t.first_key = (uint32_t) b; t.end_key = (uint32_t) (b + (uint64_t) n_sub[i]);
+            t.area_total = (double) area[i];
+            t.denom_total = h->type_corr[type[i]] * t.area_total;
+            total.push_back(t);
+        }
         base[i] = (uint32_t) b;
         b += (uint64_t) std::max<int>(n_sub[i], 1);  // a location with 0 sub-locations still owns one key
         double a = (double) area[i];                 // float getTotalSurfaceM2() widened (TArea:144)
@@ -1683,6 +1695,18 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
     CU(h, cudaMemcpyAsync(h->d_loc_nsub.p, n_sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_loc_param.p, lp.data(), (size_t) n * sizeof(LocParam), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->d_last_calc.p, 0, (size_t) h->n_keys * 8, h->stream));
+    h->n_total_loc = (uint32_t) total.size();
+    h->d_key_total.release(); h->d_total_loc.release();
+    if (!total.empty())
+    {
+        std::vector<uint8_t> flag(h->n_keys, 0);
+        for (const TotalLoc& t : total)
+            for (uint32_t k = t.first_key; k < t.end_key; ++k) flag[k] = 1;
+        CU(h, h->d_key_total.ensure(h->n_keys)); CU(h, h->d_total_loc.ensure(total.size()));
+        CU(h, cudaMemcpyAsync(h->d_key_total.p, flag.data(), h->n_keys, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->d_total_loc.p, total.data(), total.size() * sizeof(TotalLoc), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
     CU(h, h->bk_count.ensure((size_t) h->n_keys + 1));
     CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, h->stream));  // k_scan_lookback leaves it zeroed from then on
     CU(h, cudaStreamSynchronize(h->stream));

@@ -23,6 +23,15 @@ struct LocParam
     double denom;     // correctionFactorArea * area_sub        (TArea:156)
 };
 
+// a location evaluated by the total-location branch (infectInSublocation = false and >= 2 sub-locations,
+// TArea:198-246 / TDist:189-246): every evaluation of one of its sub-locations scans the persons of ALL of them
+struct TotalLoc
+{
+    uint32_t first_key, end_key;  // its sub-location keys
+    double area_total;            // (double) totalSurfaceM2, not divided  (TArea:144, TDist:126)
+    double denom_total;           // correctionFactorArea * area_total     (TArea:205)
+};
+
 // one stay of the window in bucket order: everything transmission needs from it in one 32-byte sector
 struct alignas(16) StayRec
 {
@@ -97,6 +106,8 @@ struct WindowCtx
     const PolicyChange* policy; int n_policy;
     // static tables
     const uint32_t* key_loc; const LocParam* loc_param; double* last_calc; uint32_t n_keys;
+    const uint8_t* key_total;  // per key: 1 = its location takes the total-location branch (nullptr: no such location)
+    const TotalLoc* total_loc; uint32_t n_total_loc;
     // agents (own: indexed by global id - person_base; guests: by the index in StayRec::pad)
     const uint64_t* view; const double* ill_end; const double* guest_ill_end;
     uint32_t person_base, n_agents;
@@ -132,6 +143,7 @@ struct BigLists
 {
     uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;
     unsigned long long* huge_off; unsigned long long scratch_cap;
+    const uint8_t* key_total;  // sub-locations of total-branch locations are not queued here
     int need_enters, both;  // enter events are needed (distance model head counts / ENTER_AND_EXIT trigger)
     double r_window;        // (T1 - T0) / threshold + 2: no window holds more evaluations of one sub-location
 };

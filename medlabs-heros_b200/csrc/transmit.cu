@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         if (n == 0) continue;
         ++occupied;
         if (n > 32) continue;  // queued for the group kernels by the prefix-sum kernel
+        if (c.key_total && c.key_total[key]) continue;  // evaluated per location by k_transmit_total
         const StayRec* rec = c.rec + a;
         // who is here, and the two latest events
         bool any_ill = false, any_sus = false;
@@ -973,6 +974,173 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
     flush_stats(c, st, threadIdx.x & 31);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// total-location branch (Covid19TransmissionArea.java:198-246, Covid19TransmissionDistance.java:189-246): one block per
+// location with infectInSublocation = false and >= 2 sub-locations.  The movement events of every sub-location drive
+// their own chain of calculated evaluations (lastCalculation is per sub-location), but every evaluation scans the
+// persons of ALL sub-locations of the location (location.getAllPersonIds()) with the un-divided area, the formulas of
+// that branch (sign and shape quirks included) and, in the distance model, the head count of the sub-location.
+// The stays of a location are contiguous in bucket order (its keys are consecutive).  This is a rarely taken path (no
+// location of the shipped data takes it), written for exactness rather than speed: sums are formed in canonical
+// (person, t_in) order, thread t adds elements t, t + 256, ... and the partial sums are combined in a fixed tree.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double block_sum_fixed(double v, double* s_red)
+{
+    __syncthreads();
+    s_red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int) threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return s_red[0];
+}
+
+__device__ __forceinline__ double block_min_time(double v, double* s_red)
+{
+    __syncthreads();
+    s_red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int) threadIdx.x < o) { const double w = s_red[threadIdx.x + o]; if (w < s_red[threadIdx.x]) s_red[threadIdx.x] = w; }
+        __syncthreads();
+    }
+    return s_red[0];
+}
+
+}  // namespace
+
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
+{
+    __shared__ double s_red[256];
+    __shared__ unsigned long long s_off;
+    const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
+    const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
+    const int tid = threadIdx.x;
+    Local st;
+    for (uint32_t li = blockIdx.x; li < c.n_total_loc; li += gridDim.x)
+    {
+        const TotalLoc L = c.total_loc[li];
+        const uint32_t a0 = c.seg_start[L.first_key], a1 = c.seg_start[L.end_key];
+        const uint32_t n_all = a1 - a0;
+        if (n_all == 0) continue;
+        const StayRec* all = c.rec + a0;
+        // canonical order of the location's stays: order[rank] = index (rank counting, in global scratch)
+        if (tid == 0)
+        {
+            const unsigned long long off = atomicAdd(&c.ctr->scratch_top, (unsigned long long) n_all * 8 + 16);
+            s_off = off + (unsigned long long) n_all * 8 + 16 <= c.scratch_cap ? off : ~0ull;
+            if (s_off == ~0ull) atomicOr(&c.ctr->overflow, 2u);
+        }
+        __syncthreads();
+        if (s_off == ~0ull) continue;
+        uint32_t* order = reinterpret_cast<uint32_t*>(c.scratch + ((s_off + 15) & ~15ull));
+        uint32_t* skey = order + n_all;  // sub-location key of every stay of the location
+        for (uint32_t key = L.first_key; key < L.end_key; ++key)
+            for (uint32_t i = c.seg_start[key] - a0 + tid; i < c.seg_start[key + 1] - a0; i += 256) skey[i] = key;
+        for (uint32_t i = tid; i < n_all; i += 256)
+        {
+            const uint32_t pi = all[i].person;
+            const double ti = all[i].tin;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n_all; ++j)
+            {
+                const uint32_t pj = all[j].person;
+                const double tj = all[j].tin;
+                rank += (stay_before(pj, tj, pi, ti) || (pj == pi && tj == ti && j < i)) ? 1u : 0u;
+            }
+            order[rank] = i;
+        }
+        __syncthreads();
+        for (uint32_t key = L.first_key; key < L.end_key; ++key)
+        {
+            const uint32_t b0 = c.seg_start[key] - a0, b1 = c.seg_start[key + 1] - a0;  // the sub-location's own stays
+            if (b1 == b0) continue;
+            double Lc = c.last_calc[key];
+            const double L_in = Lc;
+            double done = neg_inf();
+            for (;;)
+            {
+                // next calculated evaluation of this sub-location: its earliest movement event after the last one
+                // whose time since the last calculation is not below the threshold
+                double cand = pos_inf();
+                for (uint32_t i = b0 + tid; i < b1; i += 256)
+                {
+                    const double tout = all[i].tout, tin = all[i].tin;
+                    if (tout >= c.T0 && tout < c.T1 && tout > done && !(tout - Lc < thr) && tout < cand) cand = tout;
+                    if (both && tin >= c.T0 && tin < c.T1 && tin > done && !(tin - Lc < thr) && tin < cand) cand = tin;
+                }
+                const double now = block_min_time(cand, s_red);
+                if (!(now < pos_inf())) break;
+                // The evaluation is triggered by the first movement of this sub-location at `now`: an exit if there is
+                // one (exits are handled before enters of the same time).  Who of the OTHER sub-locations is in
+                // location.getAllPersonIds() at that moment follows from the order of simultaneous movements (by
+                // sub-location key): a person who left another sub-location at exactly `now` is still there iff that
+                // sub-location comes later; a person who entered one at exactly `now` is already there iff the
+                // trigger is an enter and that sub-location comes earlier.
+                double any_exit = 0.0;
+                for (uint32_t i = b0 + tid; i < b1; i += 256) any_exit += all[i].tout == now ? 1.0 : 0.0;
+                const bool by_exit = block_sum_fixed(any_exit, s_red) > 0.0;
+                auto present = [&](const StayRec& q, uint32_t kq) {
+                    if (kq == key) return q.tin < now && now <= q.tout;
+                    if (by_exit) return q.tin < now && (q.tout > now || (q.tout == now && kq > key));
+                    return q.tout > now && (q.tin < now || (q.tin == now && kq < key));
+                };
+                const double duration = now - Lc;
+                Lc = now;
+                done = now;
+                if (tid == 0) st.evaluations++;
+                double factor;
+                if (MODEL == HEROS_MODEL_AREA)
+                    factor = area_factor_total(c.area, duration, L.denom_total);  // TArea:205
+                else
+                {
+                    double head = 0.0;  // personsInSublocation.size(): the sub-location's own head count (TDist:196)
+                    for (uint32_t i = b0 + tid; i < b1; i += 256) head += (all[i].tin < now && now <= all[i].tout) ? 1.0 : 0.0;
+                    const int head_count = (int) block_sum_fixed(head, s_red);
+                    double psi, mu;
+                    policy_at(c, now, psi, mu);
+                    factor = dist_factor(c.dist, psi, mu, L.area_total, head_count);  // TDist:196-201
+                }
+                if (factor == 0.0) continue;
+                double part = 0.0;
+                for (uint32_t r = tid; r < n_all; r += 256)  // every person of the location (TArea:211 / TDist:207)
+                {
+                    const StayRec q = all[order[r]];
+                    if (present(q, skey[order[r]]) && ill_at(c, q, now))
+                    {
+                        const double te = now - (double) view_exposure(q.view);
+                        if (MODEL == HEROS_MODEL_AREA)
+                            part += area_contribution_total(c.area, te);  // TArea:216-221
+                        else
+                        {
+                            const double v_t = dist_viral_load(c.dist, te);
+                            if (v_t > 0) part += dist_term(c.dist, factor, duration, v_t);
+                        }
+                    }
+                }
+                const double sum = block_sum_fixed(part, s_red);
+                double p;
+                if (!probability<MODEL>(factor, sum, p) || !(p > 0)) continue;  // p = 1 - exp(+factor * sum) in the area model
+                for (uint32_t i = tid; i < n_all; i += 256)
+                {
+                    const StayRec q = all[i];
+                    if (present(q, skey[i]) && phase_is_susceptible(view_tphase(q.view)))
+                        draw_and_push(c, st, q.person, key, now, p);  // TArea:234-245 / TDist:234-245
+                }
+            }
+            if (tid == 0 && Lc != L_in) c.last_calc[key] = Lc;
+        }
+        __syncthreads();
+    }
+    flush_stats(c, st, tid & 31);
+}
+
 // host-side launcher ----------------------------------------------------------------------------------------------------
 // k_transmit_thread fills the work lists; the warp kernel and the group kernels then run side by side on the auxiliary
 // streams (they touch disjoint sub-locations), and the main stream joins them.
@@ -1012,6 +1180,11 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     {
         cudaEventRecord(ts.join[k], ts.aux[k]);
         cudaStreamWaitEvent(s, ts.join[k], 0);
+    }
+    if (c.n_total_loc)
+    {
+        k_transmit_total<MODEL><<<(int) min((uint32_t) (n_sm * 4), c.n_total_loc), 256, 0, s>>>(c);
+        ++launches;
     }
     k_draw<<<n_sm * 4, 256, 0, s>>>(c);
     launches += 9;

@@ -694,8 +694,10 @@ static int move_cmp(const void* pa, const void* pb)
     const move_ev* b = (const move_ev*) pb;
     if (a->t != b->t) return a->t < b->t ? -1 : 1;
     if (a->kind != b->kind) return a->kind < b->kind ? -1 : 1; /* exits before enters at equal time */
-    if (a->person != b->person) return a->person < b->person ? -1 : 1;
+    /* movements at an identical time: by sub-location, then by person.  The order only matters for the total-location
+     * branch, where evaluations of different sub-locations of one location draw for the same persons. */
     if (a->key != b->key) return a->key < b->key ? -1 : 1;
+    if (a->person != b->person) return a->person < b->person ? -1 : 1;
     return 0;
 }
 

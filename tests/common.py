@@ -53,12 +53,14 @@ class Scenario:
 
     def __init__(self, seed: int, n_persons: int, n_households: int, n_workplaces: int, n_shops: int, days: int,
                  shop_visits_per_day: float = 1.0, tie_fraction: float = 0.1, short_gap_fraction: float = 0.05,
-                 open_fraction: float = 0.02):
+                 open_fraction: float = 0.02, n_parks: int = 0, park_nsub: int = 3):
         rng = np.random.default_rng(seed)
         self.days = days
-        # location types: 0 Accommodation (sub-location = household), 1 Workplace, 2 Retail (single sub-location)
-        self.type_infect_sub = np.array([1, 1, 1], np.uint8)
-        self.type_corr = np.array([1.0, 0.8, 1.25], np.float64)
+        # location types: 0 Accommodation (sub-location = household), 1 Workplace, 2 Retail (single sub-location),
+        # 3 (only with n_parks > 0) a type with infectInSublocation = false and several sub-locations: the
+        # total-location branch (TArea:198-246 / TDist:189-246)
+        self.type_infect_sub = np.array([1, 1, 1] + ([0] if n_parks else []), np.uint8)
+        self.type_corr = np.array([1.0, 0.8, 1.25] + ([0.9] if n_parks else []), np.float64)
         n_home_loc = max(1, n_households // 4)
         home_nsub = np.full(n_home_loc, 0, np.int64)
         hh_loc = rng.integers(0, n_home_loc, n_households)
@@ -69,10 +71,11 @@ class Scenario:
         home_nsub = np.maximum(home_nsub, 1)
         work_nsub = rng.integers(1, 6, n_workplaces)
         shop_nsub = np.ones(n_shops, np.int64)
-        self.loc_type = np.concatenate([np.zeros(n_home_loc), np.ones(n_workplaces), np.full(n_shops, 2)]).astype(np.uint8)
-        self.loc_nsub = np.concatenate([home_nsub, work_nsub, shop_nsub]).astype(np.int16)
+        self.loc_type = np.concatenate([np.zeros(n_home_loc), np.ones(n_workplaces), np.full(n_shops, 2),
+                                        np.full(n_parks, 3)]).astype(np.uint8)
+        self.loc_nsub = np.concatenate([home_nsub, work_nsub, shop_nsub, np.full(n_parks, park_nsub)]).astype(np.int16)
         per_sub = np.concatenate([np.full(n_home_loc, 100.0), np.full(n_workplaces, 30.0),
-                                  rng.uniform(50, 400, n_shops)])
+                                  rng.uniform(50, 400, n_shops), np.full(n_parks, 60.0)])
         self.loc_area = (per_sub * self.loc_nsub).astype(np.float32)  # ConstructHerosModel.java:381
         self.n_loc = len(self.loc_type)
         w0, s0 = n_home_loc, n_home_loc + n_workplaces
@@ -119,10 +122,16 @@ class Scenario:
                 k = rng.poisson(shop_visits_per_day)
                 for _ in range(k):
                     shop = s0 + rng.integers(0, n_shops)
+                    zone = 0
+                    if n_parks and rng.random() < 0.6:  # a walk in one of the zones of a park
+                        shop = s0 + n_shops + rng.integers(0, n_parks)
+                        zone = rng.integers(0, park_nsub)
                     d = rng.uniform(0.2, 1.0)
                     if rng.random() < short_gap_fraction:
                         d = rng.uniform(0.002, 0.02)
-                    add(p, shop, 0, t, t + d)
+                    if n_parks and rng.random() < tie_fraction:
+                        d = np.ceil((t + d) * 4.0) / 4.0 - t  # leave on the quarter hour: ties across the zones of a park
+                    add(p, shop, zone, t, t + d)
                     t += d + rng.uniform(0.1, 0.3)
                 if rng.random() < tie_fraction:
                     t = np.ceil(t)  # arrive home on the hour: ties across persons

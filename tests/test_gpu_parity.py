@@ -185,3 +185,27 @@ def test_fast_path_without_exact_stats_gives_identical_results(model, trigger):
     for loc in range(scn.n_loc):
         for sub in range(int(scn.loc_nsub[loc])):
             assert gpu["engine"].last_calculation(loc, sub) == ora["sim"].last_calc(loc, sub)
+
+
+@pytest.mark.parametrize("model,trigger", [("area", _lib.TRIGGER_EXIT_ONLY), ("distance", _lib.TRIGGER_EXIT_ONLY),
+                                           ("distance", _lib.TRIGGER_ENTER_AND_EXIT)])
+def test_total_location_branch_in_windows(model, trigger):
+    """Locations with infectInSublocation = false and >= 2 sub-locations (TArea:198-246 / TDist:189-246): every
+    evaluation of a sub-location scans the persons of the whole location.  In the area model that branch can only
+    infect when late-stage cases make the sum negative (sign quirk), in the distance model it infects normally."""
+    scn = Scenario(seed=31, n_persons=700, n_households=260, n_workplaces=20, n_shops=2, days=12,
+                   shop_visits_per_day=3.0, tie_fraction=0.3, n_parks=3, park_nsub=3)
+    props = load_props(model)
+    props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "6.0" if model == "area" else "2.5"
+    kind = _lib.MODEL_AREA if model == "area" else _lib.MODEL_DISTANCE
+    ora = run_oracle(scn, props, kind, trigger, seed=13)
+    gpu = run_gpu(scn, props, kind, trigger, seed=13)
+    assert_same_run(gpu, ora)
+    assert sum(s["evaluations"] for s in gpu["stats"]) == ora["evaluations"]
+    park0 = int(np.nonzero(scn.loc_type == 3)[0][0])
+    in_parks = (ora["infections"]["loc"] >= park0).sum()
+    assert len(ora["infections"]["person"]) > 100
+    if model == "distance":
+        assert in_parks > 20          # the total branch infected people, in several zones
+        assert len(np.unique(ora["infections"]["sub"][ora["infections"]["loc"] >= park0])) > 1
+    gpu["engine"].close()

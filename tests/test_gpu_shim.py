@@ -61,16 +61,15 @@ def test_shim_matches_oracle_on_random_sets(model):
 
 
 @pytest.mark.parametrize("model", ["area", "distance"])
-def test_shim_total_location_branch(model):
-    """infectSub = false and nSub >= 2 is only reachable through the shim (heros_set_locations refuses it for the
-    windowed engine); build it with a type-1 location of 3 sub-locations via a second model."""
+def test_total_location_branch_is_accepted_by_the_windowed_engine(model):
+    """infectSub = false and nSub >= 2 (the total-location branch): heros_set_locations used to refuse it, the windowed
+    engine now evaluates such locations per location (tests/test_gpu_parity.py::test_total_location_branch_in_windows);
+    the 1:1 shim on the same tables is covered by test_shim_matches_oracle_call_by_call."""
     props = load_props(model)
     props["covidT_area.contagiousness"] = "30.0"
     m = hb.HerosModel(props, seed=111)
     m.engine.set_location_types([1, 0], [1.0, 1.0])
-    with pytest.raises(hb.HerosError) as e:
-        m.engine.set_locations([1], [3], [60.0])
-    assert e.value.code == _lib.ERR_UNSUPPORTED
+    m.engine.set_locations([1], [3], [60.0])
     m.close()
 
 
