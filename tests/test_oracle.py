@@ -283,3 +283,56 @@ def test_compartment_series_from_the_transition_log():
     assert (np.diff(counts[:, 0]) <= 0).all()                          # nobody becomes susceptible again
     assert monitor.HEADER == ("Time(h)", "Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic",
                               "Hospitalized", "ICU", "Dead", "Recovered")
+
+
+def test_driver_contract_against_the_reference_epidemic_curves():
+    """The only numbers the reference publishes for this path are the epidemic curves of seed comparison.xlsx
+    (tests/golden/seed_comparison.json, made by tools/make_golden_curves.py).  They pin three observable consequences
+    of the driver contract the oracle restates, in all four seeds:
+      * nobody is exposed before the seeds become contagious (48 h); the first secondary exposure comes with the first
+        morning movements after that (54.5 h in the reference);
+      * the seeds turn infectious between 60 h and 91.2 h (Triangular(2.5, 3.4, 3.8) days in hours);
+      * exposures only happen at movement events: none between 00:00 and 06:00 of any day (the half-hour-of-day
+        histogram of new exposures is empty there), while the bin of midnight itself is not (activities that end at
+        24:00).
+    The same three properties must hold for the oracle driven by the schedule generator on a synthetic city."""
+    import json
+    import os
+    import heros_b200 as hb
+    from heros_b200 import scenario
+    from common import GOLDEN
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
+        gold = json.load(f)
+    assert tuple(gold["header"]) == ("Time(h)",) + hb.PHASE_NAMES   # column order = phase registration order
+    for seed, g in gold["seeds"].items():
+        assert g["daily_counts"][0] == [553567, 100, 0, 0, 0, 0, 0, 0]
+        assert all(sum(row) == 553667 for row in g["daily_counts"])
+        assert 48.0 < g["first_exposure_h"] <= 55.0
+        assert 60.0 <= g["first_infectious_h"] <= 62.0 and g["all_seeds_infectious_by_h"] <= 91.5
+        hist = np.array(g["new_exposures_by_half_hour_of_day"])
+        assert hist[1:13].sum() == 0 and hist[0] > 0 and hist[13:44].sum() > 0.99 * hist.sum()
+
+    city = scenario.City(5000, seed=11)
+    props = load_props("distance")
+    props["covidT_dist.alpha"] = "2.0"
+    _, dist, prog = oracle_props(props)
+    sim = ob.Sim(ob.MODEL_DIST, ob.TRIGGER_EXIT_ONLY, 111)
+    sim.set_dist(dist)
+    sim.set_prog(prog)
+    sim.set_location_types(city.type_infect_sub, city.type_correction)
+    sim.set_locations(city.loc_type, city.loc_nsub, city.loc_area)
+    sim.set_persons(city.age, city.female)
+    seeds = np.arange(0, 5000, 50, dtype=np.int32)
+    sim.expose(seeds, np.zeros(len(seeds)))
+    gen = scenario.ScheduleGenerator(city, 111)
+    for d in range(12):
+        st = gen.generate_day(sim.agent_state()["phase"])
+        sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        sim.run(24.0 * (d + 1))
+    inf, tr = sim.infections(), sim.transitions()
+    assert len(inf["time"]) > 300
+    assert 48.0 < inf["time"].min() < 60.0                      # first morning after the seeds became contagious
+    became_infectious = tr["time"][np.isin(tr["person"], seeds) & np.isin(tr["phase"], (2, 3))]
+    assert len(became_infectious) == len(seeds) and 60.0 <= became_infectious.min() and became_infectious.max() <= 91.2
+    hour = inf["time"] % 24.0
+    assert not ((hour > 0.0) & (hour <= 6.0)).any()             # nothing happens while everybody sleeps

@@ -1,0 +1,36 @@
+"""Extracts the reference-produced epidemic curve of seed 111 from /root/reference/"seed comparison.xlsx" (the only
+numbers the reference publishes for this path) into tests/golden/seed_comparison_111.json: the daily compartment
+counts, the hour-of-day histogram of new exposures (decrease of Susceptible between two 0.5 h samples, binned by the
+time of day of the later sample) and the first exposure / first infectious times.  Run in the build container
+(the reference tree does not travel to the GPU box); the JSON is committed."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from xlsx_reader import read_xlsx  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+book = read_xlsx("/root/reference/seed comparison.xlsx")
+out = {"source": "seed comparison.xlsx, sheets 111-114 (The Hague, N = 553 667, 120 days, 0.5 h samples)",
+       "header": book["111"][0][:9], "seeds": {}}
+for sheet in ("111", "112", "113", "114"):
+    a = np.array([[float(x) for x in r[:9]] for r in book[sheet][1:] if r and r[0] not in (None, "")])
+    t, s = a[:, 0], a[:, 1]
+    new = -np.diff(s)
+    hist = np.zeros(48)
+    for h, n in zip(t[1:] % 24.0, new):
+        hist[int(round(h * 2)) % 48] += n
+    infectious = a[:, 3] + a[:, 4]
+    out["seeds"][sheet] = {
+        "daily_counts": a[::48, 1:].astype(int).tolist(),
+        "new_exposures_by_half_hour_of_day": hist.astype(int).tolist(),
+        "first_exposure_h": float(t[1:][new > 0][0]), "first_infectious_h": float(t[infectious > 0][0]),
+        "all_seeds_infectious_by_h": float(t[a[:, 2] + 0 * t < 1e9][np.argmax(infectious >= 100)]),
+        "peak_symptomatic": [float(t[np.argmax(a[:, 4])]), int(a[:, 4].max())], "final_recovered": int(a[-1, 8])}
+with open(os.path.join(ROOT, "tests", "golden", "seed_comparison.json"), "w") as f:
+    json.dump(out, f, indent=1)
+print({k: (v["first_exposure_h"], v["first_infectious_h"], v["peak_symptomatic"], v["final_recovered"])
+       for k, v in out["seeds"].items()})
