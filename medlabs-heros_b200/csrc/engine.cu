@@ -11,7 +11,7 @@
 //   5. k_transmit_*      transmit.cu: every infectPeople evaluation of the window, Philox draws -> candidates
 //   6. k_resolve*        earliest successful draw per person wins; expose() the winners
 //   7. retire            stays that ended before T1 leave the pool
-#include "engine.cuh"
+#include "engine_state.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -29,22 +29,9 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int TPB = 256;
-constexpr unsigned long long OPEN_CLOSED = 0x7ff8000000000000ull;  // t_in of an open-stay slot nobody is in (NaN)
-inline int blocks_for(size_t n, int per = TPB) { return (int) std::max<size_t>(1, (n + per - 1) / per); }
-
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------------
-
-struct AgentArrays
-{
-    uint64_t* view; double* next_time; double* ill_end;
-    const ProgParams* prog; uint64_t seed;
-    uint32_t person_base;  // global id of agent 0: every draw and every log entry uses global person ids
-    Counters* ctr;
-    uint32_t* tr_person; uint8_t* tr_phase; double* tr_time; unsigned long long tr_cap;
-};
 
 __device__ __forceinline__ void log_transition(const AgentArrays& A, uint32_t person, uint32_t phase, double t)
 {
@@ -132,8 +119,6 @@ __device__ __forceinline__ void progress_agent(const AgentArrays& A, uint32_t a,
     if (v != v0) A.view[a] = v;
 }
 
-struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; uint32_t* rank; };
-
 // ---- occupancy bucketing: a counting sort over the dense sub-location keys ---------------------------------------------
 // Replaces the per-location TIntSets the medlabs engine updates on every addPerson / removePerson.
 // 1. tickets          every stay of the window takes a ticket at its sub-location: rank = atomicAdd(count[key], 1).
@@ -145,18 +130,9 @@ struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; 
 //                     ticket on arrival but only begins after the window leaves a dead record in its slot.
 // The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
 // (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
-struct GuestArrays
-{
-    const uint32_t* gid; const uint64_t* view; const uint32_t* key; const double* tin; const double* tout;
-    const uint32_t* rank; uint32_t n;
-};
-
 // These kernels are bound by the latency of dependent memory operations (load key -> atomic -> store) and by the
 // number of L2 sectors they touch, not by DRAM bandwidth, so every thread handles IPT items whose loads and atomics
 // are in flight together.  Blocks [0, pool_blocks) take the pool stays, the following ones the agents (then the guests).
-constexpr int IPT = 4;
-inline int item_blocks(size_t n) { return (int) ((n + (size_t) TPB * IPT - 1) / ((size_t) TPB * IPT)); }
-
 __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32_t n_agents, double T1, PoolArrays P,
                                                      uint32_t n_carried, uint32_t pool_blocks,
                                                      const uint32_t* __restrict__ open_key,
@@ -420,9 +396,6 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
 }
 
 // ---- resolve: earliest successful draw wins (ties: lowest sub-location key) -------------------------------------------
-struct CandArrays { const uint32_t* person; const uint64_t* gkey; const double* t; const double* p; uint32_t cap; };
-struct InfLog { uint32_t* person; uint64_t* gkey; double* t; double* p; unsigned long long cap; };
-
 constexpr uint32_t RESOLVE_SOLO = 8192;  // up to this many candidates one block resolves everything without grid barriers
 
 // Candidates carry global person ids; the ones of other shards' persons (guests) are skipped here and sent home.
@@ -492,417 +465,6 @@ __global__ void __launch_bounds__(1024) k_resolve(CandArrays C, const AgentArray
         claim[person] = 0u;
     }
 #undef RESOLVE_BARRIER
-}
-
-// ---- multi-GPU: stays of this shard's persons in other shards' locations, and the way back -----------------------------
-// the packed agent words (and the end of illness, if inside the window) of the listed persons, after k_progress
-__global__ void __launch_bounds__(TPB) k_export_words(uint32_t n, const int32_t* person, uint32_t person_base,
-                                                      uint32_t n_agents, const uint64_t* view, const double* ill_end,
-                                                      uint64_t* view_out, double* ill_end_out)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t local = (uint32_t) person[i] - person_base;
-    uint64_t v = 0;
-    double e = bits_f64(0x7ff0000000000000ull);
-    if (local < n_agents)
-    {
-        v = view[local];
-        if (view_ends(v)) e = ill_end[local];
-    }
-    view_out[i] = v;
-    ill_end_out[i] = e;
-}
-
-__global__ void __launch_bounds__(TPB) k_guest_keys(uint32_t n, const int32_t* loc, const int16_t* sub, int32_t loc_base,
-                                                    const uint32_t* loc_first_key, const int16_t* loc_nsub, uint32_t n_loc,
-                                                    const double* tin, const double* tout, double T1,
-                                                    uint32_t* key_out, uint32_t* count, uint32_t* rank_out,
-                                                    Counters* ctr)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t l = loc[i] - loc_base;
-    const int32_t sb = sub[i];
-    bool ok = l >= 0 && (uint32_t) l < n_loc && sb >= 0 && tin[i] >= 0.0 && tout[i] > tin[i];
-    if (ok) ok = sb < max((int) loc_nsub[l], 1);
-    const uint32_t key = ok ? loc_first_key[l] + (uint32_t) sb : KEY_NONE;
-    key_out[i] = key;
-    // guests take their tickets at the sub-location when they are submitted (the window's own stays did in k_window_open)
-    rank_out[i] = (ok && tin[i] < T1) ? atomicAdd(&count[key], 1u) : KEY_NONE;
-    if (!ok) atomicAdd(&ctr->invalid_visits, 1u);
-}
-
-// candidates whose person lives on another shard, compacted for the exchange
-__global__ void __launch_bounds__(TPB) k_export_guest_candidates(CandArrays C, const Counters* ctr, uint32_t person_base,
-                                                                 uint32_t n_agents, uint32_t cap, uint32_t* gid,
-                                                                 int32_t* loc, int16_t* sub, double* t, double* p,
-                                                                 unsigned long long* n_out)
-{
-    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, ctr->n_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        if (C.person[i] - person_base < n_agents) continue;
-        const unsigned long long slot = atomicAdd(n_out, 1ull);
-        if (slot >= cap) continue;
-        gid[slot] = C.person[i];
-        loc[slot] = (int32_t) (C.gkey[i] >> 16);
-        sub[slot] = (int16_t) (C.gkey[i] & 0xFFFFu);
-        t[slot] = C.t[i];
-        p[slot] = C.p[i];
-    }
-}
-
-__global__ void __launch_bounds__(TPB) k_import_candidates(uint32_t n, const uint32_t* gid, const int32_t* loc,
-                                                           const int16_t* sub, const double* t, const double* p,
-                                                           uint32_t* cand_person, uint64_t* cand_gkey, double* cand_t,
-                                                           double* cand_p, uint32_t cand_cap, Counters* ctr)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long slot = atomicAdd(&ctr->n_cand, 1ull);
-    if (slot >= cand_cap) { atomicOr(&ctr->overflow, 1u); return; }
-    cand_person[slot] = gid[i];
-    cand_gkey[slot] = ((uint64_t) (uint32_t) loc[i] << 16) | (uint64_t) (uint16_t) sub[i];
-    cand_t[slot] = t[i];
-    cand_p[slot] = p[i];
-}
-
-// ---- multi-GPU, block exchange: fixed-capacity blocks, one per peer, so that a window's two all-to-alls are
-//      equal-split collectives with nothing to negotiate and no host synchronisation in between --------------------------
-// guest block   : u64 count | pad | t_in f64[C] | t_out f64[C] | word u64[C] | ill_end f64[C] | person i32[C] |
-//                 loc i32[C] | sub i16[C]                                  (C a multiple of 4: every column 8-byte aligned)
-// candidate block: u64 count | pad | time f64[C] | p f64[C] | person i32[C] | loc i32[C] | sub i16[C]
-constexpr int MAX_PEERS = 64;
-__host__ __device__ inline size_t guest_block_bytes(size_t C) { return 16 + 42 * C; }
-__host__ __device__ inline size_t candidate_block_bytes(size_t C) { return 16 + 26 * C; }
-struct PeerOffsets { long long v[MAX_PEERS + 1]; };
-struct PeerBases { int v[MAX_PEERS + 1]; };
-
-__global__ void __launch_bounds__(TPB) k_pack_guest_blocks(uint32_t n_rows, PeerOffsets off, int n_blocks,
-                                                           const int32_t* person, const int32_t* loc, const int16_t* sub,
-                                                           const double* tin, const double* tout, uint32_t person_base,
-                                                           uint32_t n_agents, const uint64_t* view, const double* ill_end,
-                                                           uint32_t C, unsigned char* out)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t bb = guest_block_bytes(C);
-    if (i < (uint32_t) n_blocks)
-        *reinterpret_cast<unsigned long long*>(out + (size_t) i * bb) = (unsigned long long) (off.v[i + 1] - off.v[i]);
-    if (i >= n_rows) return;
-    int d = 0;
-    while (d + 1 < n_blocks && (long long) i >= off.v[d + 1]) ++d;
-    const uint32_t j = i - (uint32_t) off.v[d];
-    if (j >= C) return;
-    unsigned char* b = out + (size_t) d * bb + 16;
-    const uint32_t local = (uint32_t) person[i] - person_base;
-    uint64_t v = 0;
-    double e = bits_f64(0x7ff0000000000000ull);
-    if (local < n_agents)
-    {
-        v = view[local];
-        if (view_ends(v)) e = ill_end[local];
-    }
-    reinterpret_cast<double*>(b)[j] = tin[i];
-    reinterpret_cast<double*>(b + 8 * (size_t) C)[j] = tout[i];
-    reinterpret_cast<uint64_t*>(b + 16 * (size_t) C)[j] = v;
-    reinterpret_cast<double*>(b + 24 * (size_t) C)[j] = e;
-    reinterpret_cast<int32_t*>(b + 32 * (size_t) C)[j] = person[i];
-    reinterpret_cast<int32_t*>(b + 36 * (size_t) C)[j] = loc[i];
-    reinterpret_cast<int16_t*>(b + 40 * (size_t) C)[j] = sub[i];
-}
-
-__global__ void __launch_bounds__(TPB) k_submit_guest_blocks(int n_blocks, uint32_t C, const unsigned char* blocks,
-                                                             double T1, int32_t loc_base, const uint32_t* loc_first_key,
-                                                             const int16_t* loc_nsub, uint32_t n_loc, uint32_t* gid,
-                                                             uint64_t* gview, double* gill_end, uint32_t* gkey,
-                                                             double* gtin, double* gtout, uint32_t* grank, uint32_t* count,
-                                                             Counters* ctr)
-{
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint32_t) n_blocks * C) return;
-    const uint32_t bk = idx / C, j = idx % C;
-    const size_t bb = guest_block_bytes(C);
-    const unsigned char* b = blocks + (size_t) bk * bb;
-    const unsigned long long cnt = *reinterpret_cast<const unsigned long long*>(b);
-    if (j == 0 && cnt > C) atomicOr(&ctr->overflow, 16u);
-    uint32_t key = KEY_NONE, rank = KEY_NONE;
-    if (j < cnt)
-    {
-        b += 16;
-        const double tin = reinterpret_cast<const double*>(b)[j], tout = reinterpret_cast<const double*>(b + 8 * (size_t) C)[j];
-        const int32_t l = reinterpret_cast<const int32_t*>(b + 36 * (size_t) C)[j] - loc_base;
-        const int32_t sb = reinterpret_cast<const int16_t*>(b + 40 * (size_t) C)[j];
-        bool ok = l >= 0 && (uint32_t) l < n_loc && sb >= 0 && tin >= 0.0 && tout > tin;
-        if (ok) ok = sb < max((int) loc_nsub[l], 1);
-        if (ok)
-        {
-            key = loc_first_key[l] + (uint32_t) sb;
-            if (tin < T1) rank = atomicAdd(&count[key], 1u);
-        }
-        else
-            atomicAdd(&ctr->invalid_visits, 1u);
-        gid[idx] = (uint32_t) reinterpret_cast<const int32_t*>(b + 32 * (size_t) C)[j];
-        gview[idx] = reinterpret_cast<const uint64_t*>(b + 16 * (size_t) C)[j];
-        gill_end[idx] = reinterpret_cast<const double*>(b + 24 * (size_t) C)[j];
-        gtin[idx] = tin;
-        gtout[idx] = tout;
-    }
-    gkey[idx] = key;
-    grank[idx] = rank;
-}
-
-__global__ void k_zero_block_headers(int n_blocks, size_t block_bytes, unsigned char* out)
-{
-    if ((int) threadIdx.x < n_blocks) *reinterpret_cast<unsigned long long*>(out + threadIdx.x * block_bytes) = 0ull;
-}
-
-// successful draws on guests, routed to the block of the shard that owns the person
-__global__ void __launch_bounds__(TPB) k_export_candidate_blocks(CandArrays Cd, Counters* ctr, PeerBases bases, int n_blocks,
-                                                                 uint32_t person_base, uint32_t n_agents, uint32_t C,
-                                                                 unsigned char* out)
-{
-    const uint32_t n = (uint32_t) min((unsigned long long) Cd.cap, ctr->n_cand);
-    const size_t bb = candidate_block_bytes(C);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const uint32_t gid = Cd.person[i];
-        if (gid - person_base < n_agents) continue;
-        int d = 0;
-        while (d + 1 < n_blocks && (int) gid >= bases.v[d + 1]) ++d;
-        unsigned char* b = out + (size_t) d * bb;
-        const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(b), 1ull);
-        if (slot >= C) { atomicOr(&ctr->overflow, 16u); continue; }
-        b += 16;
-        reinterpret_cast<double*>(b)[slot] = Cd.t[i];
-        reinterpret_cast<double*>(b + 8 * (size_t) C)[slot] = Cd.p[i];
-        reinterpret_cast<int32_t*>(b + 16 * (size_t) C)[slot] = (int32_t) gid;
-        reinterpret_cast<int32_t*>(b + 20 * (size_t) C)[slot] = (int32_t) (Cd.gkey[i] >> 16);
-        reinterpret_cast<int16_t*>(b + 24 * (size_t) C)[slot] = (int16_t) (Cd.gkey[i] & 0xFFFFu);
-    }
-}
-
-__global__ void __launch_bounds__(TPB) k_import_candidate_blocks(int n_blocks, uint32_t C, const unsigned char* blocks,
-                                                                 uint32_t* cand_person, uint64_t* cand_gkey, double* cand_t,
-                                                                 double* cand_p, uint32_t cand_cap, Counters* ctr)
-{
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint32_t) n_blocks * C) return;
-    const uint32_t bk = idx / C, j = idx % C;
-    const unsigned char* b = blocks + (size_t) bk * candidate_block_bytes(C);
-    const unsigned long long cnt = *reinterpret_cast<const unsigned long long*>(b);
-    if (j >= cnt) return;
-    b += 16;
-    const unsigned long long slot = atomicAdd(&ctr->n_cand, 1ull);
-    if (slot >= cand_cap) { atomicOr(&ctr->overflow, 1u); return; }
-    cand_person[slot] = (uint32_t) reinterpret_cast<const int32_t*>(b + 16 * (size_t) C)[j];
-    cand_gkey[slot] = ((uint64_t) (uint32_t) reinterpret_cast<const int32_t*>(b + 20 * (size_t) C)[j] << 16) |
-                      (uint64_t) (uint16_t) reinterpret_cast<const int16_t*>(b + 24 * (size_t) C)[j];
-    cand_t[slot] = reinterpret_cast<const double*>(b)[j];
-    cand_p[slot] = reinterpret_cast<const double*>(b + 8 * (size_t) C)[j];
-}
-
-// ---- activity-schedule advancement ------------------------------------------------------------------------------------
-// One simulated day of the activity loop the medlabs engine runs per person (week pattern "0_<phase>_<role>",
-// model/HerosModel.java:484-504; activity rows and locators, factory/ConstructHerosModel.java:763-1072): one thread per
-// person walks the day pattern selected by the phase held at midnight, draws durations and destinations from
-// counter-based Philox numbers keyed by (seed, person, day, activity) and turns every move into a closed stay in the
-// pool (with its ticket, like k_submit) and a new open stay.  The stays of a thread are collected in local memory and
-// written out with one atomic per block.
-constexpr int MAX_DAY_ACTIVITIES = 32;
-constexpr uint32_t TAG_SCHEDULE = 0x300u;
-
-struct Activity { int32_t kind, locator, choice, dist; double mn, mode, mx, until; };  // = heros_activity
-
-struct ScheduleTables
-{
-    const Activity* acts; const int32_t* pat_start; const int32_t* pat_count;  // [phase 8][role 16][day type 4]
-    const int32_t* choice_start; const int32_t* choice_type; const double* choice_cum;
-    int n_types, n_candidates, accommodation_type;
-    const int32_t* nearest; const int32_t* n_cand; const int32_t* cand;  // per location: [type], [type], [type][candidate]
-    const int32_t* home_loc; const int16_t* home_sub; const int32_t* work_loc; const int16_t* work_sub;
-    const uint32_t* loc_base; const int16_t* loc_nsub; uint32_t n_loc;
-    uint64_t seed;
-};
-
-__device__ __forceinline__ double activity_duration(const Activity& a, double u)
-{
-    if (a.dist == 2)  // Triangular(min, mode, max)
-    {
-        if (a.mx <= a.mn) return a.mn;
-        const double fc = (a.mode - a.mn) / (a.mx - a.mn);
-        if (u <= fc) return a.mn + hsqrt((a.mode - a.mn) * (a.mx - a.mn) * u);
-        return a.mx - hsqrt((a.mx - a.mn) * (a.mx - a.mode) * (1.0 - u));
-    }
-    if (a.dist == 1) return a.mn + (a.mx - a.mn) * u;  // Uniform(min, max)
-    return a.mode;
-}
-
-// The day of one person.  EMIT = false only counts the stays that end; EMIT = true writes them to the pool from slot
-// `first` on (each with its ticket) and updates the open stay of the person.  Both passes make the same draws.
-template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
-                                             double* open_tin, const PoolArrays& P, uint32_t first, uint32_t pool_end,
-                                             uint32_t* count, Counters* ctr, int day, int day_type)
-{
-    const uint64_t v = view[a];
-    const uint32_t ph = view_phase(v), role = view_role(v);
-    const double t0 = 24.0 * day, t1 = 24.0 * (day + 1);
-    uint32_t cur_key = open_key[a];
-    double cur_tin = open_tin[a];
-    if (cur_tin != cur_tin) cur_key = KEY_NONE;  // nobody in the slot
-    const uint32_t key0 = cur_key;
-    const double tin0 = cur_tin;
-    uint32_t n_e = 0;
-    auto leave = [&](double t_leave) {  // the current stay ends
-        if (cur_key != KEY_NONE && t_leave > cur_tin)
-        {
-            if (EMIT)
-            {
-                const uint32_t slot = first + n_e;
-                if (slot < pool_end)
-                {
-                    P.person[slot] = a;
-                    P.key[slot] = cur_key;
-                    P.tin[slot] = cur_tin;
-                    P.tout[slot] = t_leave;
-                    P.rank[slot] = atomicAdd(&count[cur_key], 1u);  // its ticket for the next window
-                }
-                else
-                    atomicOr(&ctr->overflow, 32u);
-            }
-            ++n_e;
-        }
-    };
-    int n_act = 0, start = 0;
-    if (ph == PH_D)  // a dead person leaves the model
-    {
-        leave(t0);
-        cur_key = KEY_NONE;
-    }
-    else if (role >= 1 && role <= 15)
-    {
-        const int idx = ((int) ph * 16 + (int) role) * 4 + day_type;
-        n_act = S.pat_count[idx];
-        start = S.pat_start[idx];
-    }
-    const int32_t home_l = S.home_loc[a];
-    const uint32_t home_key = S.loc_base[home_l] + (uint32_t) S.home_sub[a];
-    double t = t0;
-    for (int i = 0; i < n_act; ++i)
-    {
-        const Activity act = S.acts[start + i];
-        // destination
-        uint32_t dest = cur_key;  // CurrentLocator, and whoever has nowhere else to go
-        Philox4 r{0, 0, 0, 0};
-        const bool needs_draw = act.dist != 0 || (act.locator >= 3 && act.choice >= 0);
-        if (needs_draw)
-            r = philox4x32_10(a, (uint32_t) (day * 64 + i), 0u, TAG_SCHEDULE, (uint32_t) S.seed, (uint32_t) (S.seed >> 32));
-        if (act.locator == 0)
-            dest = home_key;
-        else if (act.locator == 1)
-        {
-            const int32_t wl = S.work_loc[a];
-            if (wl >= 0) dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
-        }
-        else if (act.locator >= 3 && act.choice >= 0)
-        {
-            const double u_type = (double) r.z * 0x1.0p-32;
-            const double u_cand = (double) (r.w >> 16) * 0x1.0p-16, u_sub = (double) (r.w & 0xFFFFu) * 0x1.0p-16;
-            const int c0 = S.choice_start[act.choice], c1 = S.choice_start[act.choice + 1];
-            const double x = u_type * S.choice_cum[c1 - 1];
-            int pick = 0;  // number of cumulative weights <= x (searchsorted, side = right)
-            while (pick < c1 - c0 && S.choice_cum[c0 + pick] <= x) ++pick;
-            if (pick > c1 - c0 - 1) pick = c1 - c0 - 1;
-            const int ty = S.choice_type[c0 + pick];
-            int32_t dl;
-            if (act.locator == 3)  // Nearest(type) to the home building
-                dl = S.nearest[(size_t) home_l * S.n_types + ty];
-            else  // Random(type) within the maximum distance of the home building
-            {
-                const int n = S.n_cand[(size_t) home_l * S.n_types + ty];
-                long long j = (long long) (u_cand * (double) n);
-                if (j > n - 1) j = n - 1;
-                if (j < 0) j = 0;
-                dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
-            }
-            if (ty == S.accommodation_type || dl < 0)
-                dest = home_key;
-            else
-            {
-                const int nsub = max((int) S.loc_nsub[dl], 1);
-                int ds = (int) (u_sub * (double) nsub);
-                if (ds > nsub - 1) ds = nsub - 1;
-                dest = S.loc_base[dl] + (uint32_t) ds;
-            }
-        }
-        const bool move = dest != cur_key;
-        const double u_dur = (double) ((((uint64_t) r.x << 32) | r.y) >> 11) * 0x1.0p-53;
-        const double dur = activity_duration(act, u_dur);
-        if (act.kind == 1)  // travel: leave now, arrive after the travel time (spent outside every location)
-        {
-            if (move)
-            {
-                leave(t);
-                const double t_arr = t + dur;
-                const bool arrived = t_arr < t1;
-                cur_key = arrived ? dest : KEY_NONE;
-                cur_tin = t_arr;
-                t = t_arr;
-                if (!arrived) break;
-            }
-        }
-        else
-        {
-            if (move) { leave(t); cur_key = dest; cur_tin = t; }
-            if (act.kind == 0) t = t + dur;
-            else { const double until = t0 + act.until; t = t > until ? t : until; }
-            if (!(t < t1)) break;
-        }
-    }
-    if (EMIT && (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0))))
-    {
-        open_key[a] = cur_key;
-        open_tin[a] = cur_key != KEY_NONE ? cur_tin : bits_f64(OPEN_CLOSED);
-    }
-    return n_e;
-}
-
-__global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint32_t* order,
-                                                     const uint64_t* view, uint32_t* open_key, double* open_tin,
-                                                     PoolArrays P, uint32_t pool_base, uint32_t pool_cap, uint32_t* count,
-                                                     Counters* ctr, int day, int day_type)
-{
-    __shared__ uint32_t s_w[TPB / 32];
-    __shared__ uint32_t s_base;
-    // persons are visited grouped by social role: the threads of a warp then walk the same day pattern (the phase that
-    // also selects it is Susceptible for most) instead of 32 different ones
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t a = slot < n_agents ? order[slot] : n_agents;
-    // pass 1: how many stays end today
-    const uint32_t n_e = a < n_agents ? walk_day<false>(S, a, view, open_key, open_tin, P, 0u, 0u, count, ctr, day, day_type) : 0u;
-    // room in the pool for the stays of the block: one atomic per block
-    uint32_t incl = n_e;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
-    }
-    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t off = 0, total = 0;
-    for (int w = 0; w < TPB / 32; ++w)
-    {
-        if (w < (int) (threadIdx.x >> 5)) off += s_w[w];
-        total += s_w[w];
-    }
-    if (threadIdx.x == 0) s_base = total ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) total) : 0u;
-    __syncthreads();
-    // pass 2: the same day again, now writing the stays
-    if (a < n_agents)
-        walk_day<true>(S, a, view, open_key, open_tin, P, pool_base + s_base + off + incl - n_e, pool_base + pool_cap, count,
-                       ctr, day, day_type);
 }
 
 // ---- inputs ------------------------------------------------------------------------------------------------------------
@@ -1134,136 +696,7 @@ __global__ void k_infect_people(int model, AreaParams area, DistParams dist, dou
 // ---------------------------------------------------------------------------------------------------------------------
 using namespace heros;
 
-struct heros_engine
-{
-    heros_config cfg{};
-    std::string err;
-    cudaStream_t stream = nullptr;
-    TransmitStreams ts{};
-    cudaEvent_t ev[10]{};
-    cudaEvent_t ev_bk[2]{};  // before / after the prefix sum
-    double stage_ms[6]{};  // window open (state machine + tickets + retire), prefix sum + scatter, transmit thread
-                           // kernel, other transmit kernels + draws, resolve, (unused)
-    double bucket_part_ms[3]{};  // (unused), prefix sum, scatter
-    double aux_done_ms[N_AUX]{}; // fork -> end of the work of every auxiliary stream
-    int n_sm = 148;
-    double t_now = 0.0;
-
-    bool have_area = false, have_dist = false, have_prog = false;
-    AreaParams area{};
-    DistParams dist{};
-    std::vector<PolicyChange> policy;
-    DevBuf<PolicyChange> d_policy;
-    DevBuf<ProgParams> d_prog;
-
-    int n_types = 0;
-    std::vector<uint8_t> type_infect_sub;
-    std::vector<double> type_corr;
-
-    uint32_t n_loc = 0, n_keys = 0;
-    std::vector<uint32_t> h_loc_base;
-    std::vector<uint8_t> h_loc_type;
-    std::vector<int16_t> h_loc_nsub;
-    std::vector<float> h_loc_area;
-    DevBuf<uint32_t> d_loc_base, d_key_loc;
-    DevBuf<int16_t> d_loc_nsub;
-    DevBuf<LocParam> d_loc_param;
-    DevBuf<double> d_last_calc;
-    DevBuf<uint8_t> d_key_total;     // total-branch locations (usually none)
-    DevBuf<TotalLoc> d_total_loc;
-    uint32_t n_total_loc = 0;
-
-    uint32_t n_agents = 0;
-    DevBuf<uint64_t> d_view;
-    DevBuf<double> d_next_time, d_ill_end, d_open_tin;
-    DevBuf<unsigned long long> d_best_t, d_best_key;
-    DevBuf<uint32_t> d_claim, d_open_key;
-    uint32_t person_base = 0;   // global id of agent 0
-    int32_t location_base = 0;  // global id of location 0
-
-    // guests: stays of other shards' persons in this shard's locations, valid for the window in progress
-    DevBuf<uint32_t> g_gid, g_key, g_rank;
-    DevBuf<uint64_t> g_view;
-    DevBuf<double> g_ill_end, g_tin, g_tout;
-    uint32_t n_guest = 0;
-    int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
-    double win_T0 = 0.0, win_T1 = 0.0;
-    int win_launches = 0;
-    uint32_t win_n_pool = 0;
-    Counters win_before{};
-
-    // pool of submitted stays (double buffered)
-    DevBuf<uint32_t> pool_person[2], pool_key[2], pool_rank[2];  // rank: the ticket of the stay at its sub-location
-    uint32_t n_carried = 0;  // pool[0 .. n_carried) came over from earlier windows; the rest was submitted since
-    DevBuf<double> pool_tin[2], pool_tout[2];
-    int pool_cur = 0;
-    uint32_t n_pool = 0;
-
-    // window buffers
-    DevBuf<uint32_t> bk_count, bk_rank, seg_start;
-    DevBuf<unsigned long long> scan_status;
-    DevBuf<StayRec> rec;
-    int resolve_grid = 0;  // blocks of the cooperative k_resolve launch
-
-    // candidates, logs
-    DevBuf<uint32_t> cand_person;
-    DevBuf<uint64_t> cand_gkey, inf_gkey;
-    DevBuf<double> cand_t, cand_p;
-    DevBuf<uint32_t> inf_person, tr_person;
-    DevBuf<unsigned long long> d_nguest_cand;
-    DevBuf<double> inf_t, inf_p, tr_time;
-    DevBuf<uint8_t> tr_phase;
-
-    // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], item_person, item_key;
-    DevBuf<unsigned long long> item_tab, item_pair;
-    DevBuf<double> tab_t, tab_p;
-    DevBuf<unsigned long long> huge_off;
-    DevBuf<unsigned char> scratch;
-
-    // activity schedule (heros_set_schedule)
-    bool have_schedule = false;
-    int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
-    uint64_t sched_seed = 0;
-    DevBuf<Activity> s_acts;
-    DevBuf<int32_t> s_pat_start, s_pat_count, s_choice_start, s_choice_type, s_nearest, s_ncand, s_cand, d_home_loc,
-        d_work_loc;
-    DevBuf<double> s_choice_cum;
-    DevBuf<int16_t> d_home_sub, d_work_sub;
-    DevBuf<uint32_t> s_order;      // persons grouped by social role
-    std::vector<uint8_t> h_role;   // host copy of the roles (heros_set_persons)
-
-    DevBuf<Counters> d_ctr;
-    Counters* h_ctr = nullptr;  // pinned
-    bool ctr_current = false;   // nothing that changes the counters was enqueued since h_ctr was refreshed
-
-    // staging for host submissions
-    DevBuf<int32_t> st_person, st_loc;
-    DevBuf<int16_t> st_sub;
-    DevBuf<double> st_tin, st_tout;
-
-    std::vector<double> series_t;
-    std::vector<int64_t> series_counts;
-
-    // sorted output caches
-    struct InfEvent { double t, p; uint64_t gkey; uint32_t person; };
-    std::vector<InfEvent> o_inf;
-    std::vector<uint32_t> o_tr_person;
-    std::vector<double> o_tr_time;
-    std::vector<uint8_t> o_tr_phase;
-    unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
-};
-
 namespace heros_impl {
-
-#define CU(h, call)                                                                                       \
-    do {                                                                                                  \
-        cudaError_t e_ = (call);                                                                          \
-        if (e_ != cudaSuccess) {                                                                          \
-            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
-            return HEROS_ERR_CUDA;                                                                        \
-        }                                                                                                 \
-    } while (0)
 
 int32_t fail(heros_handle h, int32_t code, const std::string& msg)
 {
@@ -1961,104 +1394,6 @@ static void add_window_stats(heros_handle h, heros_step_stats& st)
     st.gpu_launches += h->win_launches;
 }
 
-int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_activity* activities,
-                           const int32_t* pattern_start, const int32_t* pattern_count, int32_t n_choices,
-                           const int32_t* choice_start, const int32_t* choice_type, const double* choice_cum,
-                           int32_t n_types, int32_t accommodation_type, int32_t n_candidates, const int32_t* nearest,
-                           const int32_t* n_cand, const int32_t* cand, const int16_t* work_sublocation, uint64_t seed)
-{
-    if (!h) return HEROS_ERR_INVALID;
-    if (h->n_agents == 0 || h->n_loc == 0) return fail(h, HEROS_ERR_INVALID, "locations and persons must be set first");
-    if (!h->d_home_loc.p) return fail(h, HEROS_ERR_INVALID, "heros_set_persons was called without home / work locations");
-    if (n_activities <= 0 || !activities || !pattern_start || !pattern_count || n_choices < 0 || !choice_start ||
-        n_types <= 0 || n_candidates < 0 || !nearest || !n_cand || (n_candidates > 0 && !cand) || !work_sublocation)
-        return fail(h, HEROS_ERR_INVALID, "bad schedule tables");
-    static_assert(sizeof(heros_activity) == sizeof(Activity), "activity layout");
-    int max_acts = 0;
-    for (int i = 0; i < 8 * 16 * 4; ++i)
-    {
-        if (pattern_count[i] < 0 || pattern_start[i] < 0 || pattern_start[i] + pattern_count[i] > n_activities)
-            return fail(h, HEROS_ERR_INVALID, "day pattern outside the activity table");
-        max_acts = std::max(max_acts, pattern_count[i]);
-    }
-    if (max_acts > MAX_DAY_ACTIVITIES) return fail(h, HEROS_ERR_UNSUPPORTED, "more than 32 activities in a day pattern");
-    for (int i = 0; i < n_activities; ++i)
-        if (activities[i].choice >= n_choices) return fail(h, HEROS_ERR_INVALID, "choice table index out of range");
-    for (int i = 0; i < n_choices; ++i)
-        if (choice_start[i + 1] <= choice_start[i]) return fail(h, HEROS_ERR_INVALID, "empty choice table");
-    cudaSetDevice(h->cfg.device);
-    const size_t N = h->n_agents, L = h->n_loc, n_ch = n_choices ? (size_t) choice_start[n_choices] : 0;
-    cudaStream_t s = h->stream;
-    CU(h, h->s_acts.ensure(n_activities)); CU(h, h->s_pat_start.ensure(512)); CU(h, h->s_pat_count.ensure(512));
-    CU(h, h->s_choice_start.ensure((size_t) n_choices + 1)); CU(h, h->s_choice_type.ensure(n_ch + 1));
-    CU(h, h->s_choice_cum.ensure(n_ch + 1)); CU(h, h->s_nearest.ensure(L * n_types)); CU(h, h->s_ncand.ensure(L * n_types));
-    CU(h, h->s_cand.ensure(L * n_types * (size_t) std::max(n_candidates, 1))); CU(h, h->d_work_sub.ensure(N));
-    CU(h, cudaMemcpyAsync(h->s_acts.p, activities, (size_t) n_activities * sizeof(Activity), cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->s_pat_start.p, pattern_start, 512 * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->s_pat_count.p, pattern_count, 512 * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->s_choice_start.p, choice_start, ((size_t) n_choices + 1) * 4, cudaMemcpyHostToDevice, s));
-    if (n_ch)
-    {
-        CU(h, cudaMemcpyAsync(h->s_choice_type.p, choice_type, n_ch * 4, cudaMemcpyHostToDevice, s));
-        CU(h, cudaMemcpyAsync(h->s_choice_cum.p, choice_cum, n_ch * 8, cudaMemcpyHostToDevice, s));
-    }
-    CU(h, cudaMemcpyAsync(h->s_nearest.p, nearest, L * n_types * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->s_ncand.p, n_cand, L * n_types * 4, cudaMemcpyHostToDevice, s));
-    if (n_candidates > 0)
-        CU(h, cudaMemcpyAsync(h->s_cand.p, cand, L * n_types * (size_t) n_candidates * 4, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->d_work_sub.p, work_sublocation, N * 2, cudaMemcpyHostToDevice, s));
-    {
-        std::vector<uint32_t> order(N);  // counting sort of the persons by role, stable
-        size_t first[257] = {};
-        for (size_t a = 0; a < N; ++a) ++first[(size_t) h->h_role[a] + 1];
-        for (int r = 0; r < 256; ++r) first[r + 1] += first[r];
-        for (size_t a = 0; a < N; ++a) order[first[h->h_role[a]]++] = (uint32_t) a;
-        CU(h, h->s_order.ensure(N));
-        CU(h, cudaMemcpyAsync(h->s_order.p, order.data(), N * 4, cudaMemcpyHostToDevice, s));
-        CU(h, cudaStreamSynchronize(s));
-    }
-    CU(h, cudaStreamSynchronize(s));
-    h->sched_max_acts = max_acts; h->sched_n_types = n_types; h->sched_n_cand = n_candidates;
-    h->sched_accommodation = accommodation_type; h->sched_seed = seed;
-    h->have_schedule = true;
-    return HEROS_OK;
-}
-
-int32_t heros_advance_schedule(heros_handle h, int32_t day)
-{
-    int32_t rc = check_ready(h);
-    if (rc != HEROS_OK) return rc;
-    if (!h->have_schedule) return fail(h, HEROS_ERR_INVALID, "heros_set_schedule has not been called");
-    if (h->win_state != 0) return fail(h, HEROS_ERR_INVALID, "a window opened by heros_window_begin is still in progress");
-    if (day < 0 || 24.0 * day < h->t_now) return fail(h, HEROS_ERR_INVALID, "the day lies before the engine time");
-    if (h->person_base != 0 || h->location_base != 0)
-        return fail(h, HEROS_ERR_UNSUPPORTED, "the device-side schedule runs on an unsharded engine");
-    cudaSetDevice(h->cfg.device);
-    const size_t room = (size_t) h->n_agents * (size_t) std::max(h->sched_max_acts, 1);
-    if ((uint64_t) h->n_pool + room + h->n_agents >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
-    rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + room, true);
-    if (rc != HEROS_OK) return rc;
-    ScheduleTables S{};
-    S.acts = h->s_acts.p; S.pat_start = h->s_pat_start.p; S.pat_count = h->s_pat_count.p;
-    S.choice_start = h->s_choice_start.p; S.choice_type = h->s_choice_type.p; S.choice_cum = h->s_choice_cum.p;
-    S.n_types = h->sched_n_types; S.n_candidates = h->sched_n_cand; S.accommodation_type = h->sched_accommodation;
-    S.nearest = h->s_nearest.p; S.n_cand = h->s_ncand.p; S.cand = h->s_cand.p;
-    S.home_loc = h->d_home_loc.p; S.home_sub = h->d_home_sub.p; S.work_loc = h->d_work_loc.p; S.work_sub = h->d_work_sub.p;
-    S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
-    static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
-    CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));
-    k_advance_day<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
-                                                                  h->d_open_tin.p, pool_arrays(h, h->pool_cur), h->n_pool,
-                                                                  (uint32_t) room, h->bk_count.p, h->d_ctr.p, day,
-                                                                  DAY_TYPE[day % 7]);
-    CU(h, cudaGetLastError());
-    rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
-    if (h->h_ctr->overflow) return fail(h, HEROS_ERR_CAPACITY, "pool overflow in heros_advance_schedule");
-    h->n_pool += (uint32_t) h->h_ctr->n_sched;
-    return HEROS_OK;
-}
-
 int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,
                               double* t_in, double* t_out, int64_t* n_out)
 {
@@ -2153,177 +1488,12 @@ int32_t heros_window_begin(heros_handle h, double t_until)
     return window_begin(h, t_until);
 }
 
-int32_t heros_export_agent_words(heros_handle h, int64_t n, const int32_t* person, uint64_t* view_out, double* ill_end_out)
-{
-    if (!h || n < 0 || (n > 0 && (!person || !view_out || !ill_end_out))) return HEROS_ERR_INVALID;
-    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "agent words are exported between heros_window_begin and heros_window_transmit");
-    if (n == 0) return HEROS_OK;
-    cudaSetDevice(h->cfg.device);
-    k_export_words<<<blocks_for(n), TPB, 0, h->stream>>>((uint32_t) n, person, h->person_base, h->n_agents, h->d_view.p,
-                                                         h->d_ill_end.p, view_out, ill_end_out);
-    CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(h->stream));
-    return HEROS_OK;
-}
-
-int32_t heros_submit_guest_visits_device(heros_handle h, int64_t n, const int32_t* person, const uint64_t* view,
-                                         const double* ill_end, const int32_t* location, const int16_t* sublocation,
-                                         const double* t_in, const double* t_out)
-{
-    if (!h || n < 0 || (n > 0 && (!person || !view || !ill_end || !location || !sublocation || !t_in || !t_out)))
-        return HEROS_ERR_INVALID;
-    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are submitted between heros_window_begin and heros_window_transmit");
-    if (n == 0) return HEROS_OK;
-    if ((uint64_t) h->n_guest + (uint64_t) n >= 0x7fffffffull) return fail(h, HEROS_ERR_CAPACITY, "too many guest stays");
-    cudaSetDevice(h->cfg.device);
-    const size_t tot = (size_t) h->n_guest + (size_t) n, off = h->n_guest;
-    CU(h, h->g_gid.ensure(tot, true, h->stream)); CU(h, h->g_key.ensure(tot, true, h->stream));
-    CU(h, h->g_rank.ensure(tot, true, h->stream));
-    CU(h, h->g_view.ensure(tot, true, h->stream)); CU(h, h->g_ill_end.ensure(tot, true, h->stream));
-    CU(h, h->g_tin.ensure(tot, true, h->stream)); CU(h, h->g_tout.ensure(tot, true, h->stream));
-    cudaStream_t s = h->stream;
-    CU(h, cudaMemcpyAsync(h->g_gid.p + off, person, (size_t) n * 4, cudaMemcpyDeviceToDevice, s));
-    CU(h, cudaMemcpyAsync(h->g_view.p + off, view, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
-    CU(h, cudaMemcpyAsync(h->g_ill_end.p + off, ill_end, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
-    CU(h, cudaMemcpyAsync(h->g_tin.p + off, t_in, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
-    CU(h, cudaMemcpyAsync(h->g_tout.p + off, t_out, (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
-    k_guest_keys<<<blocks_for(n), TPB, 0, s>>>((uint32_t) n, location, sublocation, h->location_base, h->d_loc_base.p,
-                                               h->d_loc_nsub.p, h->n_loc, t_in, t_out, h->win_T1, h->g_key.p + off,
-                                               h->bk_count.p, h->g_rank.p + off, h->d_ctr.p);
-    CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(s));
-    h->n_guest += (uint32_t) n;
-    return HEROS_OK;
-}
-
 int32_t heros_window_transmit(heros_handle h)
 {
     if (!h) return HEROS_ERR_INVALID;
     if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "heros_window_begin has not been called");
     cudaSetDevice(h->cfg.device);
     return window_transmit(h);
-}
-
-int32_t heros_export_guest_candidates(heros_handle h, int64_t capacity, int32_t* person, int32_t* location,
-                                      int16_t* sublocation, double* time, double* p, int64_t* n_out)
-{
-    if (!h || !n_out || capacity < 0) return HEROS_ERR_INVALID;
-    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are exported between heros_window_transmit and heros_window_finish");
-    cudaSetDevice(h->cfg.device);
-    CU(h, h->d_nguest_cand.ensure(1));
-    CU(h, cudaMemsetAsync(h->d_nguest_cand.p, 0, 8, h->stream));
-    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
-    k_export_guest_candidates<<<h->n_sm * 2, TPB, 0, h->stream>>>(C, h->d_ctr.p, h->person_base, h->n_agents,
-                                                                 (uint32_t) std::min<int64_t>(capacity, 0x7fffffff),
-                                                                 (uint32_t*) person, location, sublocation, time, p,
-                                                                 h->d_nguest_cand.p);
-    CU(h, cudaGetLastError());
-    unsigned long long n = 0;
-    CU(h, cudaMemcpyAsync(&n, h->d_nguest_cand.p, 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    *n_out = (int64_t) n;
-    return (int64_t) n > capacity ? HEROS_ERR_CAPACITY : HEROS_OK;
-}
-
-int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
-                                       const int16_t* sublocation, const double* time, const double* p)
-{
-    if (!h || n < 0 || (n > 0 && (!person || !location || !sublocation || !time || !p))) return HEROS_ERR_INVALID;
-    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are imported between heros_window_transmit and heros_window_finish");
-    if (n == 0) return HEROS_OK;
-    cudaSetDevice(h->cfg.device);
-    k_import_candidates<<<blocks_for(n), TPB, 0, h->stream>>>((uint32_t) n, (const uint32_t*) person, location, sublocation,
-                                                              time, p, h->cand_person.p, h->cand_gkey.p, h->cand_t.p,
-                                                              h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
-    CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(h->stream));
-    return HEROS_OK;
-}
-
-int64_t heros_guest_block_bytes(int64_t capacity) { return capacity > 0 ? (int64_t) guest_block_bytes((size_t) capacity) : 0; }
-int64_t heros_candidate_block_bytes(int64_t capacity) { return capacity > 0 ? (int64_t) candidate_block_bytes((size_t) capacity) : 0; }
-
-static int32_t check_blocks(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
-{
-    if (!h || !blocks) return HEROS_ERR_INVALID;
-    if (n_blocks < 1 || n_blocks > MAX_PEERS) return fail(h, HEROS_ERR_INVALID, "between 1 and 64 peer blocks");
-    if (capacity < 4 || (capacity & 3) || capacity > (1 << 28)) return fail(h, HEROS_ERR_INVALID, "block capacity must be a multiple of 4");
-    return HEROS_OK;
-}
-
-int32_t heros_pack_guest_blocks_device(heros_handle h, int32_t n_blocks, const int64_t* row_offsets, const int32_t* person,
-                                       const int32_t* location, const int16_t* sublocation, const double* t_in,
-                                       const double* t_out, int64_t capacity, void* blocks_out)
-{
-    int32_t rc = check_blocks(h, n_blocks, capacity, blocks_out);
-    if (rc != HEROS_OK) return rc;
-    if (!row_offsets) return HEROS_ERR_INVALID;
-    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest blocks are packed between heros_window_begin and heros_window_transmit");
-    PeerOffsets off{};
-    for (int d = 0; d <= n_blocks; ++d) off.v[d] = row_offsets[d];
-    for (int d = 0; d < n_blocks; ++d)
-    {
-        if (off.v[d + 1] < off.v[d] || off.v[0] != 0) return fail(h, HEROS_ERR_INVALID, "row offsets must ascend from 0");
-        if (off.v[d + 1] - off.v[d] > capacity) return fail(h, HEROS_ERR_CAPACITY, "more rows for a peer than the block capacity");
-    }
-    const int64_t n = off.v[n_blocks];
-    if (n > 0 && (!person || !location || !sublocation || !t_in || !t_out)) return HEROS_ERR_INVALID;
-    cudaSetDevice(h->cfg.device);
-    k_pack_guest_blocks<<<blocks_for((size_t) std::max<int64_t>(n, n_blocks)), TPB, 0, h->stream>>>(
-        (uint32_t) n, off, n_blocks, person, location, sublocation, t_in, t_out, h->person_base, h->n_agents, h->d_view.p,
-        h->d_ill_end.p, (uint32_t) capacity, (unsigned char*) blocks_out);
-    CU(h, cudaGetLastError());
-    return HEROS_OK;
-}
-
-int32_t heros_submit_guest_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
-{
-    int32_t rc = check_blocks(h, n_blocks, capacity, blocks);
-    if (rc != HEROS_OK) return rc;
-    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are submitted between heros_window_begin and heros_window_transmit");
-    if (h->n_guest != 0) return fail(h, HEROS_ERR_INVALID, "guest blocks cannot be combined with other guest submissions of the window");
-    cudaSetDevice(h->cfg.device);
-    const size_t tot = (size_t) n_blocks * (size_t) capacity;
-    CU(h, h->g_gid.ensure(tot)); CU(h, h->g_key.ensure(tot)); CU(h, h->g_rank.ensure(tot)); CU(h, h->g_view.ensure(tot));
-    CU(h, h->g_ill_end.ensure(tot)); CU(h, h->g_tin.ensure(tot)); CU(h, h->g_tout.ensure(tot));
-    k_submit_guest_blocks<<<blocks_for(tot), TPB, 0, h->stream>>>(
-        n_blocks, (uint32_t) capacity, (const unsigned char*) blocks, h->win_T1, h->location_base, h->d_loc_base.p,
-        h->d_loc_nsub.p, h->n_loc, h->g_gid.p, h->g_view.p, h->g_ill_end.p, h->g_key.p, h->g_tin.p, h->g_tout.p,
-        h->g_rank.p, h->bk_count.p, h->d_ctr.p);
-    CU(h, cudaGetLastError());
-    h->n_guest = (uint32_t) tot;
-    return HEROS_OK;
-}
-
-int32_t heros_export_candidate_blocks_device(heros_handle h, int32_t n_blocks, const int32_t* person_bases, int64_t capacity,
-                                             void* blocks_out)
-{
-    int32_t rc = check_blocks(h, n_blocks, capacity, blocks_out);
-    if (rc != HEROS_OK) return rc;
-    if (!person_bases) return HEROS_ERR_INVALID;
-    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are exported between heros_window_transmit and heros_window_finish");
-    PeerBases bases{};
-    for (int d = 0; d <= n_blocks; ++d) bases.v[d] = person_bases[d];
-    cudaSetDevice(h->cfg.device);
-    k_zero_block_headers<<<1, MAX_PEERS, 0, h->stream>>>(n_blocks, candidate_block_bytes((size_t) capacity), (unsigned char*) blocks_out);
-    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
-    k_export_candidate_blocks<<<h->n_sm * 2, TPB, 0, h->stream>>>(C, h->d_ctr.p, bases, n_blocks, h->person_base, h->n_agents,
-                                                                 (uint32_t) capacity, (unsigned char*) blocks_out);
-    CU(h, cudaGetLastError());
-    return HEROS_OK;
-}
-
-int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
-{
-    int32_t rc = check_blocks(h, n_blocks, capacity, blocks);
-    if (rc != HEROS_OK) return rc;
-    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are imported between heros_window_transmit and heros_window_finish");
-    cudaSetDevice(h->cfg.device);
-    k_import_candidate_blocks<<<blocks_for((size_t) n_blocks * (size_t) capacity), TPB, 0, h->stream>>>(
-        n_blocks, (uint32_t) capacity, (const unsigned char*) blocks, h->cand_person.p, h->cand_gkey.p, h->cand_t.p,
-        h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
-    CU(h, cudaGetLastError());
-    return HEROS_OK;
 }
 
 int32_t heros_window_finish(heros_handle h, heros_step_stats* stats)

@@ -1,0 +1,193 @@
+// engine_state.cuh -- the engine object and the small shared definitions of the translation units that implement the
+// C ABI (engine.cu: lifecycle, inputs, the window pipeline, outputs; exchange.cu: multi-GPU exchange; schedule.cu: the
+// device-side activity schedule).  transmit.cu only needs engine.cuh.
+#pragma once
+
+#include "engine.cuh"
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace heros {
+
+constexpr int TPB = 256;
+constexpr unsigned long long OPEN_CLOSED = 0x7ff8000000000000ull;  // t_in of an open-stay slot nobody is in (NaN)
+inline int blocks_for(size_t n, int per = TPB) { return (int) std::max<size_t>(1, (n + per - 1) / per); }
+
+// per-agent state and the transition log, as the kernels that change disease phases see them
+struct AgentArrays
+{
+    uint64_t* view; double* next_time; double* ill_end;
+    const ProgParams* prog; uint64_t seed;
+    uint32_t person_base;  // global id of agent 0: every draw and every log entry uses global person ids
+    Counters* ctr;
+    uint32_t* tr_person; uint8_t* tr_phase; double* tr_time; unsigned long long tr_cap;
+};
+
+// the pool of submitted stays (rank = the ticket of the stay at its sub-location)
+struct PoolArrays { uint32_t* person; uint32_t* key; double* tin; double* tout; uint32_t* rank; };
+
+// stays of other shards' persons in this shard's locations, valid for the window in progress
+struct GuestArrays
+{
+    const uint32_t* gid; const uint64_t* view; const uint32_t* key; const double* tin; const double* tout;
+    const uint32_t* rank; uint32_t n;
+};
+
+// the streaming kernels handle IPT items per thread (their loads and atomics are in flight together)
+constexpr int IPT = 4;
+inline int item_blocks(size_t n) { return (int) ((n + (size_t) TPB * IPT - 1) / ((size_t) TPB * IPT)); }
+
+// candidate infections of the window / the infection log
+struct CandArrays { const uint32_t* person; const uint64_t* gkey; const double* t; const double* p; uint32_t cap; };
+struct InfLog { uint32_t* person; uint64_t* gkey; double* t; double* p; unsigned long long cap; };
+
+struct Activity { int32_t kind, locator, choice, dist; double mn, mode, mx, until; };  // = heros_activity
+
+}  // namespace heros
+
+using namespace heros;
+
+struct heros_engine
+{
+    heros_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    TransmitStreams ts{};
+    cudaEvent_t ev[10]{};
+    cudaEvent_t ev_bk[2]{};  // before / after the prefix sum
+    double stage_ms[6]{};  // window open (state machine + tickets + retire), prefix sum + scatter, transmit thread
+                           // kernel, other transmit kernels + draws, resolve, (unused)
+    double bucket_part_ms[3]{};  // (unused), prefix sum, scatter
+    double aux_done_ms[N_AUX]{}; // fork -> end of the work of every auxiliary stream
+    int n_sm = 148;
+    double t_now = 0.0;
+
+    bool have_area = false, have_dist = false, have_prog = false;
+    AreaParams area{};
+    DistParams dist{};
+    std::vector<PolicyChange> policy;
+    DevBuf<PolicyChange> d_policy;
+    DevBuf<ProgParams> d_prog;
+
+    int n_types = 0;
+    std::vector<uint8_t> type_infect_sub;
+    std::vector<double> type_corr;
+
+    uint32_t n_loc = 0, n_keys = 0;
+    std::vector<uint32_t> h_loc_base;
+    std::vector<uint8_t> h_loc_type;
+    std::vector<int16_t> h_loc_nsub;
+    std::vector<float> h_loc_area;
+    DevBuf<uint32_t> d_loc_base, d_key_loc;
+    DevBuf<int16_t> d_loc_nsub;
+    DevBuf<LocParam> d_loc_param;
+    DevBuf<double> d_last_calc;
+    DevBuf<uint8_t> d_key_total;     // total-branch locations (usually none)
+    DevBuf<TotalLoc> d_total_loc;
+    uint32_t n_total_loc = 0;
+
+    uint32_t n_agents = 0;
+    DevBuf<uint64_t> d_view;
+    DevBuf<double> d_next_time, d_ill_end, d_open_tin;
+    DevBuf<unsigned long long> d_best_t, d_best_key;
+    DevBuf<uint32_t> d_claim, d_open_key;
+    uint32_t person_base = 0;   // global id of agent 0
+    int32_t location_base = 0;  // global id of location 0
+
+    // guests: stays of other shards' persons in this shard's locations, valid for the window in progress
+    DevBuf<uint32_t> g_gid, g_key, g_rank;
+    DevBuf<uint64_t> g_view;
+    DevBuf<double> g_ill_end, g_tin, g_tout;
+    uint32_t n_guest = 0;
+    int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
+    double win_T0 = 0.0, win_T1 = 0.0;
+    int win_launches = 0;
+    uint32_t win_n_pool = 0;
+    Counters win_before{};
+
+    // pool of submitted stays (double buffered)
+    DevBuf<uint32_t> pool_person[2], pool_key[2], pool_rank[2];  // rank: the ticket of the stay at its sub-location
+    uint32_t n_carried = 0;  // pool[0 .. n_carried) came over from earlier windows; the rest was submitted since
+    DevBuf<double> pool_tin[2], pool_tout[2];
+    int pool_cur = 0;
+    uint32_t n_pool = 0;
+
+    // window buffers
+    DevBuf<uint32_t> bk_count, bk_rank, seg_start;
+    DevBuf<unsigned long long> scan_status;
+    DevBuf<StayRec> rec;
+    int resolve_grid = 0;  // blocks of the cooperative k_resolve launch
+
+    // candidates, logs
+    DevBuf<uint32_t> cand_person;
+    DevBuf<uint64_t> cand_gkey, inf_gkey;
+    DevBuf<double> cand_t, cand_p;
+    DevBuf<uint32_t> inf_person, tr_person;
+    DevBuf<unsigned long long> d_nguest_cand;
+    DevBuf<double> inf_t, inf_p, tr_time;
+    DevBuf<uint8_t> tr_phase;
+
+    // work lists of the transmission kernels + global scratch of huge segments
+    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], item_person, item_key;
+    DevBuf<unsigned long long> item_tab, item_pair;
+    DevBuf<double> tab_t, tab_p;
+    DevBuf<unsigned long long> huge_off;
+    DevBuf<unsigned char> scratch;
+
+    // activity schedule (heros_set_schedule)
+    bool have_schedule = false;
+    int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
+    uint64_t sched_seed = 0;
+    DevBuf<Activity> s_acts;
+    DevBuf<int32_t> s_pat_start, s_pat_count, s_choice_start, s_choice_type, s_nearest, s_ncand, s_cand, d_home_loc,
+        d_work_loc;
+    DevBuf<double> s_choice_cum;
+    DevBuf<int16_t> d_home_sub, d_work_sub;
+    DevBuf<uint32_t> s_order;      // persons grouped by social role
+    std::vector<uint8_t> h_role;   // host copy of the roles (heros_set_persons)
+
+    DevBuf<Counters> d_ctr;
+    Counters* h_ctr = nullptr;  // pinned
+    bool ctr_current = false;   // nothing that changes the counters was enqueued since h_ctr was refreshed
+
+    // staging for host submissions
+    DevBuf<int32_t> st_person, st_loc;
+    DevBuf<int16_t> st_sub;
+    DevBuf<double> st_tin, st_tout;
+
+    std::vector<double> series_t;
+    std::vector<int64_t> series_counts;
+
+    // sorted output caches
+    struct InfEvent { double t, p; uint64_t gkey; uint32_t person; };
+    std::vector<InfEvent> o_inf;
+    std::vector<uint32_t> o_tr_person;
+    std::vector<double> o_tr_time;
+    std::vector<uint8_t> o_tr_phase;
+    unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
+};
+
+namespace heros_impl {
+using namespace heros;
+
+#define CU(h, call)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return HEROS_ERR_CUDA;                                                                        \
+        }                                                                                                 \
+    } while (0)
+
+int32_t fail(heros_handle h, int32_t code, const std::string& msg);
+heros::AgentArrays agent_arrays(heros_handle h);
+heros::PoolArrays pool_arrays(heros_handle h, int which);
+int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep);
+int32_t sync_counters(heros_handle h);     // D2H of the counters + stream synchronisation
+int32_t current_counters(heros_handle h);  // ... only if something was enqueued since the last one
+int32_t check_ready(heros_handle h);
+
+}  // namespace heros_impl

@@ -1,0 +1,316 @@
+// schedule.cu -- device-side activity schedule (row A9 / SURVEY.md 8f row 1): heros_set_schedule,
+// heros_advance_schedule.
+#include "engine_state.cuh"
+
+namespace heros {
+namespace {
+
+// ---- activity-schedule advancement ------------------------------------------------------------------------------------
+// One simulated day of the activity loop the medlabs engine runs per person (week pattern "0_<phase>_<role>",
+// model/HerosModel.java:484-504; activity rows and locators, factory/ConstructHerosModel.java:763-1072): one thread per
+// person walks the day pattern selected by the phase held at midnight, draws durations and destinations from
+// counter-based Philox numbers keyed by (seed, person, day, activity) and turns every move into a closed stay in the
+// pool (with its ticket, like k_submit) and a new open stay.  The stays of a thread are collected in local memory and
+// written out with one atomic per block.
+constexpr int MAX_DAY_ACTIVITIES = 32;
+constexpr uint32_t TAG_SCHEDULE = 0x300u;
+
+
+struct ScheduleTables
+{
+    const Activity* acts; const int32_t* pat_start; const int32_t* pat_count;  // [phase 8][role 16][day type 4]
+    const int32_t* choice_start; const int32_t* choice_type; const double* choice_cum;
+    int n_types, n_candidates, accommodation_type;
+    const int32_t* nearest; const int32_t* n_cand; const int32_t* cand;  // per location: [type], [type], [type][candidate]
+    const int32_t* home_loc; const int16_t* home_sub; const int32_t* work_loc; const int16_t* work_sub;
+    const uint32_t* loc_base; const int16_t* loc_nsub; uint32_t n_loc;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ double activity_duration(const Activity& a, double u)
+{
+    if (a.dist == 2)  // Triangular(min, mode, max)
+    {
+        if (a.mx <= a.mn) return a.mn;
+        const double fc = (a.mode - a.mn) / (a.mx - a.mn);
+        if (u <= fc) return a.mn + hsqrt((a.mode - a.mn) * (a.mx - a.mn) * u);
+        return a.mx - hsqrt((a.mx - a.mn) * (a.mx - a.mode) * (1.0 - u));
+    }
+    if (a.dist == 1) return a.mn + (a.mx - a.mn) * u;  // Uniform(min, max)
+    return a.mode;
+}
+
+// The day of one person.  EMIT = false only counts the stays that end; EMIT = true writes them to the pool from slot
+// `first` on (each with its ticket) and updates the open stay of the person.  Both passes make the same draws.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
+                                             double* open_tin, const PoolArrays& P, uint32_t first, uint32_t pool_end,
+                                             uint32_t* count, Counters* ctr, int day, int day_type)
+{
+    const uint64_t v = view[a];
+    const uint32_t ph = view_phase(v), role = view_role(v);
+    const double t0 = 24.0 * day, t1 = 24.0 * (day + 1);
+    uint32_t cur_key = open_key[a];
+    double cur_tin = open_tin[a];
+    if (cur_tin != cur_tin) cur_key = KEY_NONE;  // nobody in the slot
+    const uint32_t key0 = cur_key;
+    const double tin0 = cur_tin;
+    uint32_t n_e = 0;
+    auto leave = [&](double t_leave) {  // the current stay ends
+        if (cur_key != KEY_NONE && t_leave > cur_tin)
+        {
+            if (EMIT)
+            {
+                const uint32_t slot = first + n_e;
+                if (slot < pool_end)
+                {
+                    P.person[slot] = a;
+                    P.key[slot] = cur_key;
+                    P.tin[slot] = cur_tin;
+                    P.tout[slot] = t_leave;
+                    P.rank[slot] = atomicAdd(&count[cur_key], 1u);  // its ticket for the next window
+                }
+                else
+                    atomicOr(&ctr->overflow, 32u);
+            }
+            ++n_e;
+        }
+    };
+    int n_act = 0, start = 0;
+    if (ph == PH_D)  // a dead person leaves the model
+    {
+        leave(t0);
+        cur_key = KEY_NONE;
+    }
+    else if (role >= 1 && role <= 15)
+    {
+        const int idx = ((int) ph * 16 + (int) role) * 4 + day_type;
+        n_act = S.pat_count[idx];
+        start = S.pat_start[idx];
+    }
+    const int32_t home_l = S.home_loc[a];
+    const uint32_t home_key = S.loc_base[home_l] + (uint32_t) S.home_sub[a];
+    double t = t0;
+    for (int i = 0; i < n_act; ++i)
+    {
+        const Activity act = S.acts[start + i];
+        // destination
+        uint32_t dest = cur_key;  // CurrentLocator, and whoever has nowhere else to go
+        Philox4 r{0, 0, 0, 0};
+        const bool needs_draw = act.dist != 0 || (act.locator >= 3 && act.choice >= 0);
+        if (needs_draw)
+            r = philox4x32_10(a, (uint32_t) (day * 64 + i), 0u, TAG_SCHEDULE, (uint32_t) S.seed, (uint32_t) (S.seed >> 32));
+        if (act.locator == 0)
+            dest = home_key;
+        else if (act.locator == 1)
+        {
+            const int32_t wl = S.work_loc[a];
+            if (wl >= 0) dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
+        }
+        else if (act.locator >= 3 && act.choice >= 0)
+        {
+            const double u_type = (double) r.z * 0x1.0p-32;
+            const double u_cand = (double) (r.w >> 16) * 0x1.0p-16, u_sub = (double) (r.w & 0xFFFFu) * 0x1.0p-16;
+            const int c0 = S.choice_start[act.choice], c1 = S.choice_start[act.choice + 1];
+            const double x = u_type * S.choice_cum[c1 - 1];
+            int pick = 0;  // number of cumulative weights <= x (searchsorted, side = right)
+            while (pick < c1 - c0 && S.choice_cum[c0 + pick] <= x) ++pick;
+            if (pick > c1 - c0 - 1) pick = c1 - c0 - 1;
+            const int ty = S.choice_type[c0 + pick];
+            int32_t dl;
+            if (act.locator == 3)  // Nearest(type) to the home building
+                dl = S.nearest[(size_t) home_l * S.n_types + ty];
+            else  // Random(type) within the maximum distance of the home building
+            {
+                const int n = S.n_cand[(size_t) home_l * S.n_types + ty];
+                long long j = (long long) (u_cand * (double) n);
+                if (j > n - 1) j = n - 1;
+                if (j < 0) j = 0;
+                dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
+            }
+            if (ty == S.accommodation_type || dl < 0)
+                dest = home_key;
+            else
+            {
+                const int nsub = max((int) S.loc_nsub[dl], 1);
+                int ds = (int) (u_sub * (double) nsub);
+                if (ds > nsub - 1) ds = nsub - 1;
+                dest = S.loc_base[dl] + (uint32_t) ds;
+            }
+        }
+        const bool move = dest != cur_key;
+        const double u_dur = (double) ((((uint64_t) r.x << 32) | r.y) >> 11) * 0x1.0p-53;
+        const double dur = activity_duration(act, u_dur);
+        if (act.kind == 1)  // travel: leave now, arrive after the travel time (spent outside every location)
+        {
+            if (move)
+            {
+                leave(t);
+                const double t_arr = t + dur;
+                const bool arrived = t_arr < t1;
+                cur_key = arrived ? dest : KEY_NONE;
+                cur_tin = t_arr;
+                t = t_arr;
+                if (!arrived) break;
+            }
+        }
+        else
+        {
+            if (move) { leave(t); cur_key = dest; cur_tin = t; }
+            if (act.kind == 0) t = t + dur;
+            else { const double until = t0 + act.until; t = t > until ? t : until; }
+            if (!(t < t1)) break;
+        }
+    }
+    if (EMIT && (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0))))
+    {
+        open_key[a] = cur_key;
+        open_tin[a] = cur_key != KEY_NONE ? cur_tin : bits_f64(OPEN_CLOSED);
+    }
+    return n_e;
+}
+
+__global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint32_t* order,
+                                                     const uint64_t* view, uint32_t* open_key, double* open_tin,
+                                                     PoolArrays P, uint32_t pool_base, uint32_t pool_cap, uint32_t* count,
+                                                     Counters* ctr, int day, int day_type)
+{
+    __shared__ uint32_t s_w[TPB / 32];
+    __shared__ uint32_t s_base;
+    // persons are visited grouped by social role: the threads of a warp then walk the same day pattern (the phase that
+    // also selects it is Susceptible for most) instead of 32 different ones
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t a = slot < n_agents ? order[slot] : n_agents;
+    // pass 1: how many stays end today
+    const uint32_t n_e = a < n_agents ? walk_day<false>(S, a, view, open_key, open_tin, P, 0u, 0u, count, ctr, day, day_type) : 0u;
+    // room in the pool for the stays of the block: one atomic per block
+    uint32_t incl = n_e;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+    for (int w = 0; w < TPB / 32; ++w)
+    {
+        if (w < (int) (threadIdx.x >> 5)) off += s_w[w];
+        total += s_w[w];
+    }
+    if (threadIdx.x == 0) s_base = total ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) total) : 0u;
+    __syncthreads();
+    // pass 2: the same day again, now writing the stays
+    if (a < n_agents)
+        walk_day<true>(S, a, view, open_key, open_tin, P, pool_base + s_base + off + incl - n_e, pool_base + pool_cap, count,
+                       ctr, day, day_type);
+}
+
+}  // namespace
+}  // namespace heros
+
+using namespace heros;
+using namespace heros_impl;
+
+extern "C" {
+
+int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_activity* activities,
+                           const int32_t* pattern_start, const int32_t* pattern_count, int32_t n_choices,
+                           const int32_t* choice_start, const int32_t* choice_type, const double* choice_cum,
+                           int32_t n_types, int32_t accommodation_type, int32_t n_candidates, const int32_t* nearest,
+                           const int32_t* n_cand, const int32_t* cand, const int16_t* work_sublocation, uint64_t seed)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->n_agents == 0 || h->n_loc == 0) return fail(h, HEROS_ERR_INVALID, "locations and persons must be set first");
+    if (!h->d_home_loc.p) return fail(h, HEROS_ERR_INVALID, "heros_set_persons was called without home / work locations");
+    if (n_activities <= 0 || !activities || !pattern_start || !pattern_count || n_choices < 0 || !choice_start ||
+        n_types <= 0 || n_candidates < 0 || !nearest || !n_cand || (n_candidates > 0 && !cand) || !work_sublocation)
+        return fail(h, HEROS_ERR_INVALID, "bad schedule tables");
+    static_assert(sizeof(heros_activity) == sizeof(Activity), "activity layout");
+    int max_acts = 0;
+    for (int i = 0; i < 8 * 16 * 4; ++i)
+    {
+        if (pattern_count[i] < 0 || pattern_start[i] < 0 || pattern_start[i] + pattern_count[i] > n_activities)
+            return fail(h, HEROS_ERR_INVALID, "day pattern outside the activity table");
+        max_acts = std::max(max_acts, pattern_count[i]);
+    }
+    if (max_acts > MAX_DAY_ACTIVITIES) return fail(h, HEROS_ERR_UNSUPPORTED, "more than 32 activities in a day pattern");
+    for (int i = 0; i < n_activities; ++i)
+        if (activities[i].choice >= n_choices) return fail(h, HEROS_ERR_INVALID, "choice table index out of range");
+    for (int i = 0; i < n_choices; ++i)
+        if (choice_start[i + 1] <= choice_start[i]) return fail(h, HEROS_ERR_INVALID, "empty choice table");
+    cudaSetDevice(h->cfg.device);
+    const size_t N = h->n_agents, L = h->n_loc, n_ch = n_choices ? (size_t) choice_start[n_choices] : 0;
+    cudaStream_t s = h->stream;
+    CU(h, h->s_acts.ensure(n_activities)); CU(h, h->s_pat_start.ensure(512)); CU(h, h->s_pat_count.ensure(512));
+    CU(h, h->s_choice_start.ensure((size_t) n_choices + 1)); CU(h, h->s_choice_type.ensure(n_ch + 1));
+    CU(h, h->s_choice_cum.ensure(n_ch + 1)); CU(h, h->s_nearest.ensure(L * n_types)); CU(h, h->s_ncand.ensure(L * n_types));
+    CU(h, h->s_cand.ensure(L * n_types * (size_t) std::max(n_candidates, 1))); CU(h, h->d_work_sub.ensure(N));
+    CU(h, cudaMemcpyAsync(h->s_acts.p, activities, (size_t) n_activities * sizeof(Activity), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->s_pat_start.p, pattern_start, 512 * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->s_pat_count.p, pattern_count, 512 * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->s_choice_start.p, choice_start, ((size_t) n_choices + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (n_ch)
+    {
+        CU(h, cudaMemcpyAsync(h->s_choice_type.p, choice_type, n_ch * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(h->s_choice_cum.p, choice_cum, n_ch * 8, cudaMemcpyHostToDevice, s));
+    }
+    CU(h, cudaMemcpyAsync(h->s_nearest.p, nearest, L * n_types * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->s_ncand.p, n_cand, L * n_types * 4, cudaMemcpyHostToDevice, s));
+    if (n_candidates > 0)
+        CU(h, cudaMemcpyAsync(h->s_cand.p, cand, L * n_types * (size_t) n_candidates * 4, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->d_work_sub.p, work_sublocation, N * 2, cudaMemcpyHostToDevice, s));
+    {
+        std::vector<uint32_t> order(N);  // counting sort of the persons by role, stable
+        size_t first[257] = {};
+        for (size_t a = 0; a < N; ++a) ++first[(size_t) h->h_role[a] + 1];
+        for (int r = 0; r < 256; ++r) first[r + 1] += first[r];
+        for (size_t a = 0; a < N; ++a) order[first[h->h_role[a]]++] = (uint32_t) a;
+        CU(h, h->s_order.ensure(N));
+        CU(h, cudaMemcpyAsync(h->s_order.p, order.data(), N * 4, cudaMemcpyHostToDevice, s));
+        CU(h, cudaStreamSynchronize(s));
+    }
+    CU(h, cudaStreamSynchronize(s));
+    h->sched_max_acts = max_acts; h->sched_n_types = n_types; h->sched_n_cand = n_candidates;
+    h->sched_accommodation = accommodation_type; h->sched_seed = seed;
+    h->have_schedule = true;
+    return HEROS_OK;
+}
+
+int32_t heros_advance_schedule(heros_handle h, int32_t day)
+{
+    int32_t rc = check_ready(h);
+    if (rc != HEROS_OK) return rc;
+    if (!h->have_schedule) return fail(h, HEROS_ERR_INVALID, "heros_set_schedule has not been called");
+    if (h->win_state != 0) return fail(h, HEROS_ERR_INVALID, "a window opened by heros_window_begin is still in progress");
+    if (day < 0 || 24.0 * day < h->t_now) return fail(h, HEROS_ERR_INVALID, "the day lies before the engine time");
+    if (h->person_base != 0 || h->location_base != 0)
+        return fail(h, HEROS_ERR_UNSUPPORTED, "the device-side schedule runs on an unsharded engine");
+    cudaSetDevice(h->cfg.device);
+    const size_t room = (size_t) h->n_agents * (size_t) std::max(h->sched_max_acts, 1);
+    if ((uint64_t) h->n_pool + room + h->n_agents >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
+    rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + room, true);
+    if (rc != HEROS_OK) return rc;
+    ScheduleTables S{};
+    S.acts = h->s_acts.p; S.pat_start = h->s_pat_start.p; S.pat_count = h->s_pat_count.p;
+    S.choice_start = h->s_choice_start.p; S.choice_type = h->s_choice_type.p; S.choice_cum = h->s_choice_cum.p;
+    S.n_types = h->sched_n_types; S.n_candidates = h->sched_n_cand; S.accommodation_type = h->sched_accommodation;
+    S.nearest = h->s_nearest.p; S.n_cand = h->s_ncand.p; S.cand = h->s_cand.p;
+    S.home_loc = h->d_home_loc.p; S.home_sub = h->d_home_sub.p; S.work_loc = h->d_work_loc.p; S.work_sub = h->d_work_sub.p;
+    S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
+    static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
+    CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));
+    k_advance_day<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
+                                                                  h->d_open_tin.p, pool_arrays(h, h->pool_cur), h->n_pool,
+                                                                  (uint32_t) room, h->bk_count.p, h->d_ctr.p, day,
+                                                                  DAY_TYPE[day % 7]);
+    CU(h, cudaGetLastError());
+    rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    if (h->h_ctr->overflow) return fail(h, HEROS_ERR_CAPACITY, "pool overflow in heros_advance_schedule");
+    h->n_pool += (uint32_t) h->h_ctr->n_sched;
+    return HEROS_OK;
+}
+
+}  // extern "C"
