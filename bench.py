@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--model", default="distance", choices=["area", "distance"])
     ap.add_argument("--trigger", default="exit", choices=["exit", "both"])
     ap.add_argument("--cpu-days", type=int, default=6, help="days of the bounded cpu_baseline sample")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: kernels write into the peers' memory over NVLink (CUDA IPC), or NCCL all-to-alls")
     ap.add_argument("--commute", type=float, default=0.05,
                     help="N > 1: fraction of a tile's workers whose workplace lies in the next tile")
     return ap.parse_args()
@@ -194,8 +196,11 @@ def workload_config(args, city, world, n_commuters):
                  "region) and streams ~0.4 GB through the pool, ticket and bucket buffers (L2: 126 MB)"}
     if world > 1:
         cfg["cross_tile"] = (f"{args.commute:.3f} of each tile's workers ({n_commuters} on rank 0) work in the next tile: "
-                             "2 equal-split NCCL all-to-alls per window on the engine stream (guest-stay blocks out, candidate blocks "
-                             "back), no host synchronisation inside a window")
+                             "guest-stay blocks out, candidate blocks back every window, " +
+                             ("written by the pack / export kernels straight into the peers' memory over NVLink (CUDA IPC), "
+                              "flags instead of collectives" if args.exchange == "p2p" else
+                              "2 equal-split NCCL all-to-alls on the engine stream") +
+                             ", no host synchronisation inside a window")
     return cfg
 
 
@@ -263,7 +268,11 @@ def run_ours(args):
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
-            bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
+            if args.exchange == "p2p":
+                bx = sharded.PeerExchange(sh, guest_capacity[0], candidate_capacity=4096)
+                bx.connect()
+            else:
+                bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
         eng.seed_infections(N_INFECTED)
         engines.append(eng)
         return eng, bx, torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -276,8 +285,8 @@ def run_ours(args):
         eng.submit_visits_ptr(local_cols["person"].numel(), *(local_cols[k].data_ptr() for k, _ in COLS), device=device)
         if bx is None:
             return eng.step(24.0 * (d + 1))
-        # block exchange: two equal-split NCCL all-to-alls per window, everything enqueued on the engine stream
-        # (pinned host columns of the commuters' stays are copied on that stream too)
+        # block exchange (peer-to-peer stores over NVLink, or two equal-split NCCL all-to-alls): everything of a window is
+        # enqueued on the engine stream (pinned host columns of the commuters' stays are copied on that stream too)
         return bx.step_window(24.0 * (d + 1), remote_cols, offsets)
 
     def split_day(st, open_remote):

@@ -262,6 +262,27 @@ int32_t heros_export_candidate_blocks_device(heros_handle h, int32_t n_blocks, c
                                              int64_t capacity, void* blocks_out);
 int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks);
 
+/* The block exchange WITHOUT any collective call: the shards of one node map each other's receive regions (CUDA IPC over
+ * NVLink / NVSwitch) and the pack / export kernels store every row straight into the memory of the shard it is meant
+ * for; the kernel's last block raises a flag at every peer, the receiver waits for the flags of all peers with a
+ * one-block kernel.  Everything is enqueued on the engine's stream; the host is not in the loop.
+ *   heros_exchange_create   allocates this shard's receive region (rank of n_peers, block capacities as above) and
+ *                           returns its 64-byte CUDA IPC handle (and the device pointer, for peers in the same process)
+ *   heros_exchange_connect  ipc_handles: n_peers x 64 bytes gathered from all shards (own entry ignored);
+ *                           local_regions (optional, may be NULL): device pointers of peers living in THIS process
+ *   per window:  heros_window_begin -> heros_window_send_guests (rows sorted by destination, as for
+ *                heros_pack_guest_blocks_device) -> heros_window_recv_guests -> heros_window_transmit ->
+ *                heros_window_send_candidates (person_bases: n_peers + 1 HOST integers) -> heros_window_recv_candidates
+ *                -> heros_window_finish.  A peer that does not answer within ~4 s fails the window (HEROS_ERR_CAPACITY). */
+int32_t heros_exchange_create(heros_handle h, int32_t rank, int32_t n_peers, int64_t guest_capacity,
+                              int64_t candidate_capacity, void* ipc_handle_out, void** region_out);
+int32_t heros_exchange_connect(heros_handle h, const void* ipc_handles, void* const* local_regions);
+int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, const int32_t* person, const int32_t* location,
+                                 const int16_t* sublocation, const double* t_in, const double* t_out);
+int32_t heros_window_recv_guests(heros_handle h);
+int32_t heros_window_send_candidates(heros_handle h, const int32_t* person_bases);
+int32_t heros_window_recv_candidates(heros_handle h);
+
 /* ---- outputs ---- */
 /* infection events (what the medlabs engine applies from InfectionRecord.infectedPersons), ordered by (time, person);
  * p = pInfection of the evaluation.  first = index of the first event wanted. */

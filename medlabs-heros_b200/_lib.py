@@ -102,6 +102,12 @@ SIGNATURES = {
     "heros_submit_guest_blocks_device": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
     "heros_export_candidate_blocks_device": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P]),
     "heros_import_candidate_blocks_device": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
+    "heros_exchange_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
+    "heros_exchange_connect": (C.c_int32, [_P, _P, _P]),
+    "heros_window_send_guests": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P]),
+    "heros_window_recv_guests": (C.c_int32, [_P]),
+    "heros_window_send_candidates": (C.c_int32, [_P, _P]),
+    "heros_window_recv_candidates": (C.c_int32, [_P]),
     "heros_get_infections": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_transitions": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_phase_counts": (C.c_int32, [_P, _P]),

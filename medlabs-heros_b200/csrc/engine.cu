@@ -947,7 +947,7 @@ int32_t window_finish(heros_handle h)
     if (h->h_ctr->overflow)
     {
         char buf[160];
-        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log, 16 exchange block, 32 pool)",
+        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log, 16 exchange block, 32 pool, 64 a peer did not answer)",
                  h->h_ctr->overflow);
         return fail(h, HEROS_ERR_CAPACITY, buf);
     }
@@ -1057,6 +1057,9 @@ int32_t heros_destroy(heros_handle h)
     h->d_work_loc.release(); h->s_choice_cum.release(); h->d_home_sub.release(); h->d_work_sub.release();
     h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
     h->st_tout.release();
+    for (int d = 0; d < 64; ++d)
+        if (h->xc.opened[d]) cudaIpcCloseMemHandle(h->xc.peer[d]);
+    if (h->xc.region) cudaFree(h->xc.region);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_bk) if (ev) cudaEventDestroy(ev);

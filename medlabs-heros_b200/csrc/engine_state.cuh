@@ -102,6 +102,12 @@ struct heros_engine
     DevBuf<uint64_t> g_view;
     DevBuf<double> g_ill_end, g_tin, g_tout;
     uint32_t n_guest = 0;
+    // peer-to-peer exchange region (heros_exchange_create / _connect): this shard's receive region and the peers'
+    struct PeerExchange
+    {
+        unsigned char* region = nullptr; size_t bytes = 0; int rank = 0, n = 0; size_t gc = 0, cc = 0;
+        unsigned char* peer[64] = {}; bool opened[64] = {}; bool connected = false; unsigned long long seq = 0;
+    } xc;
     int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
     double win_T0 = 0.0, win_T1 = 0.0;
     int win_launches = 0;

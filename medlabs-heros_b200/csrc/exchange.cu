@@ -215,6 +215,130 @@ __global__ void __launch_bounds__(TPB) k_import_candidate_blocks(int n_blocks, u
     cand_p[slot] = reinterpret_cast<const double*>(b + 8 * (size_t) C)[j];
 }
 
+// ---- the same blocks written STRAIGHT INTO THE PEERS' MEMORY over NVLink (peer pointers from CUDA IPC): the pack /
+//      export kernel stores every row in the receive region of the shard it is meant for, the block that finishes
+//      last publishes the counts and raises this shard's flag at every peer, and the receiver waits for the flags of
+//      all its peers with a one-block kernel before it parses its region.  No collective call, no host in the loop.
+//      Region of a shard: guest flags u64[64] | candidate flags u64[64] | local counters u64[64] | done counter |
+//      (pad to 4096) | guest blocks [n_peers] | candidate blocks [n_peers]  (block s is written by shard s).
+//      A flag carries the window number, so nothing is ever reset; a shard cannot run ahead by more than one exchange
+//      (it needs every peer's flag of the previous one), so a block is never overwritten before it was parsed. ----
+constexpr size_t REGION_HEADER = 4096;
+struct PeerPtrs { unsigned char* p[MAX_PEERS]; };
+struct PeerFlags { unsigned long long* p[MAX_PEERS]; };
+
+__device__ __forceinline__ void publish_when_last(unsigned int* done, int n_peers, const PeerFlags& flags, unsigned long long seq)
+{
+    __threadfence_system();  // this thread's rows are visible to the peers ...
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1)  // ... and so are everybody's by the time the last block gets here
+        {
+            *done = 0u;
+            __threadfence_system();
+            for (int d = 0; d < n_peers; ++d) *reinterpret_cast<volatile unsigned long long*>(flags.p[d]) = seq;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_p2p_pack_guests(uint32_t n_rows, PeerOffsets off, int n_peers, const int32_t* person,
+                                                         const int32_t* loc, const int16_t* sub, const double* tin,
+                                                         const double* tout, uint32_t person_base, uint32_t n_agents,
+                                                         const uint64_t* view, const double* ill_end, uint32_t C,
+                                                         PeerPtrs dst, PeerFlags flags, unsigned long long seq,
+                                                         unsigned int* done)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint32_t) n_peers)
+        *reinterpret_cast<unsigned long long*>(dst.p[i]) = (unsigned long long) (off.v[i + 1] - off.v[i]);
+    if (i < n_rows)
+    {
+        int d = 0;
+        while (d + 1 < n_peers && (long long) i >= off.v[d + 1]) ++d;
+        const uint32_t j = i - (uint32_t) off.v[d];
+        if (j < C)
+        {
+            unsigned char* b = dst.p[d] + 16;
+            const uint32_t local = (uint32_t) person[i] - person_base;
+            uint64_t v = 0;
+            double e = bits_f64(0x7ff0000000000000ull);
+            if (local < n_agents)
+            {
+                v = view[local];
+                if (view_ends(v)) e = ill_end[local];
+            }
+            reinterpret_cast<double*>(b)[j] = tin[i];
+            reinterpret_cast<double*>(b + 8 * (size_t) C)[j] = tout[i];
+            reinterpret_cast<uint64_t*>(b + 16 * (size_t) C)[j] = v;
+            reinterpret_cast<double*>(b + 24 * (size_t) C)[j] = e;
+            reinterpret_cast<int32_t*>(b + 32 * (size_t) C)[j] = person[i];
+            reinterpret_cast<int32_t*>(b + 36 * (size_t) C)[j] = loc[i];
+            reinterpret_cast<int16_t*>(b + 40 * (size_t) C)[j] = sub[i];
+        }
+    }
+    publish_when_last(done, n_peers, flags, seq);
+}
+
+__global__ void __launch_bounds__(TPB) k_p2p_export_candidates(CandArrays Cd, Counters* ctr, PeerBases bases, int n_peers,
+                                                               uint32_t person_base, uint32_t n_agents, uint32_t C,
+                                                               PeerPtrs dst, PeerFlags flags, unsigned long long seq,
+                                                               unsigned long long* local_cnt, unsigned int* done)
+{
+    const uint32_t n = (uint32_t) min((unsigned long long) Cd.cap, ctr->n_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t gid = Cd.person[i];
+        if (gid - person_base < n_agents) continue;
+        int d = 0;
+        while (d + 1 < n_peers && (int) gid >= bases.v[d + 1]) ++d;
+        const unsigned long long slot = atomicAdd(&local_cnt[d], 1ull);
+        if (slot >= C) { atomicOr(&ctr->overflow, 16u); continue; }
+        unsigned char* b = dst.p[d] + 16;
+        reinterpret_cast<double*>(b)[slot] = Cd.t[i];
+        reinterpret_cast<double*>(b + 8 * (size_t) C)[slot] = Cd.p[i];
+        reinterpret_cast<int32_t*>(b + 16 * (size_t) C)[slot] = (int32_t) gid;
+        reinterpret_cast<int32_t*>(b + 20 * (size_t) C)[slot] = (int32_t) (Cd.gkey[i] >> 16);
+        reinterpret_cast<int16_t*>(b + 24 * (size_t) C)[slot] = (int16_t) (Cd.gkey[i] & 0xFFFFu);
+    }
+    // the last block writes the counts into the headers at the peers, then raises the flags
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if ((int) threadIdx.x < n_peers)
+    {
+        const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(&local_cnt[threadIdx.x]);
+        *reinterpret_cast<unsigned long long*>(dst.p[threadIdx.x]) = cnt < C ? cnt : C;
+        local_cnt[threadIdx.x] = 0ull;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        *done = 0u;
+        for (int d = 0; d < n_peers; ++d) *reinterpret_cast<volatile unsigned long long*>(flags.p[d]) = seq;
+    }
+}
+
+// one block waits until every peer has raised its flag for this window (2^33 cycles ~ 4 s, then the window fails)
+__global__ void k_p2p_wait(const unsigned long long* my_flags, int n_peers, unsigned long long seq, Counters* ctr)
+{
+    if ((int) threadIdx.x >= n_peers) return;
+    const volatile unsigned long long* f = my_flags + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < seq)
+    {
+        if (clock64() - t0 > (1ll << 33)) { atomicOr(&ctr->overflow, 64u); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 }  // namespace
 }  // namespace heros
 
@@ -386,6 +510,134 @@ int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, i
         h->cand_p.p, (uint32_t) h->cand_person.n, h->d_ctr.p);
     CU(h, cudaGetLastError());
     return HEROS_OK;
+}
+
+// ---- peer-to-peer exchange over NVLink (CUDA IPC) ----------------------------------------------------------------------
+static size_t region_bytes(int n, size_t gc, size_t cc) { return REGION_HEADER + (size_t) n * (guest_block_bytes(gc) + candidate_block_bytes(cc)); }
+
+int32_t heros_exchange_create(heros_handle h, int32_t rank, int32_t n_peers, int64_t guest_capacity, int64_t candidate_capacity,
+                              void* ipc_handle_out, void** region_out)
+{
+    if (!h || !ipc_handle_out) return HEROS_ERR_INVALID;
+    if (n_peers < 1 || n_peers > MAX_PEERS || rank < 0 || rank >= n_peers) return fail(h, HEROS_ERR_INVALID, "bad rank / number of peers");
+    if (guest_capacity < 4 || (guest_capacity & 3) || candidate_capacity < 4 || (candidate_capacity & 3))
+        return fail(h, HEROS_ERR_INVALID, "block capacities must be multiples of 4");
+    if (h->xc.region) return fail(h, HEROS_ERR_INVALID, "the exchange region exists already");
+    cudaSetDevice(h->cfg.device);
+    h->xc.rank = rank; h->xc.n = n_peers; h->xc.gc = (size_t) guest_capacity; h->xc.cc = (size_t) candidate_capacity;
+    h->xc.bytes = region_bytes(n_peers, h->xc.gc, h->xc.cc);
+    CU(h, cudaMalloc(&h->xc.region, h->xc.bytes));
+    CU(h, cudaMemset(h->xc.region, 0, h->xc.bytes));
+    cudaIpcMemHandle_t ipc;
+    CU(h, cudaIpcGetMemHandle(&ipc, h->xc.region));
+    static_assert(sizeof(ipc) == 64, "CUDA IPC handle size");
+    memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+    if (region_out) *region_out = h->xc.region;
+    return HEROS_OK;
+}
+
+int32_t heros_exchange_connect(heros_handle h, const void* ipc_handles, void* const* local_regions)
+{
+    if (!h || (!ipc_handles && !local_regions)) return HEROS_ERR_INVALID;
+    if (!h->xc.region) return fail(h, HEROS_ERR_INVALID, "heros_exchange_create has not been called");
+    cudaSetDevice(h->cfg.device);
+    for (int d = 0; d < h->xc.n; ++d)
+    {
+        if (d == h->xc.rank) { h->xc.peer[d] = h->xc.region; continue; }
+        if (local_regions && local_regions[d]) { h->xc.peer[d] = (unsigned char*) local_regions[d]; continue; }
+        if (!ipc_handles) return fail(h, HEROS_ERR_INVALID, "no handle for a peer");
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const unsigned char*) ipc_handles + (size_t) d * sizeof(ipc), sizeof(ipc));
+        void* ptr = nullptr;
+        CU(h, cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->xc.peer[d] = (unsigned char*) ptr;
+        h->xc.opened[d] = true;
+    }
+    h->xc.connected = true;
+    return HEROS_OK;
+}
+
+static void peer_targets(heros_handle h, bool candidates, PeerPtrs& dst, PeerFlags& flags)
+{
+    const size_t gb = guest_block_bytes(h->xc.gc), cb = candidate_block_bytes(h->xc.cc);
+    for (int d = 0; d < h->xc.n; ++d)
+    {
+        unsigned char* base = h->xc.peer[d];
+        dst.p[d] = candidates ? base + REGION_HEADER + (size_t) h->xc.n * gb + (size_t) h->xc.rank * cb
+                              : base + REGION_HEADER + (size_t) h->xc.rank * gb;
+        flags.p[d] = reinterpret_cast<unsigned long long*>(base) + (candidates ? 64 : 0) + h->xc.rank;
+    }
+}
+
+int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, const int32_t* person, const int32_t* location,
+                                 const int16_t* sublocation, const double* t_in, const double* t_out)
+{
+    if (!h || !row_offsets) return HEROS_ERR_INVALID;
+    if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are sent between heros_window_begin and heros_window_transmit");
+    const int n = h->xc.n;
+    PeerOffsets off{};
+    for (int d = 0; d <= n; ++d) off.v[d] = row_offsets[d];
+    for (int d = 0; d < n; ++d)
+    {
+        if (off.v[d + 1] < off.v[d] || off.v[0] != 0) return fail(h, HEROS_ERR_INVALID, "row offsets must ascend from 0");
+        if ((size_t) (off.v[d + 1] - off.v[d]) > h->xc.gc) return fail(h, HEROS_ERR_CAPACITY, "more rows for a peer than the block capacity");
+    }
+    const int64_t rows = off.v[n];
+    if (rows > 0 && (!person || !location || !sublocation || !t_in || !t_out)) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    PeerPtrs dst{};
+    PeerFlags flags{};
+    peer_targets(h, false, dst, flags);
+    ++h->xc.seq;
+    unsigned int* done = reinterpret_cast<unsigned int*>(h->xc.region + 1536);
+    k_p2p_pack_guests<<<blocks_for((size_t) std::max<int64_t>(rows, n)), TPB, 0, h->stream>>>(
+        (uint32_t) rows, off, n, person, location, sublocation, t_in, t_out, h->person_base, h->n_agents, h->d_view.p,
+        h->d_ill_end.p, (uint32_t) h->xc.gc, dst, flags, h->xc.seq, done);
+    CU(h, cudaGetLastError());
+    return HEROS_OK;
+}
+
+int32_t heros_window_recv_guests(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
+    if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are received between heros_window_begin and heros_window_transmit");
+    cudaSetDevice(h->cfg.device);
+    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region), h->xc.n, h->xc.seq, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    return heros_submit_guest_blocks_device(h, h->xc.n, (int64_t) h->xc.gc, h->xc.region + REGION_HEADER);
+}
+
+int32_t heros_window_send_candidates(heros_handle h, const int32_t* person_bases)
+{
+    if (!h || !person_bases) return HEROS_ERR_INVALID;
+    if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are sent between heros_window_transmit and heros_window_finish");
+    cudaSetDevice(h->cfg.device);
+    PeerBases bases{};
+    for (int d = 0; d <= h->xc.n; ++d) bases.v[d] = person_bases[d];
+    PeerPtrs dst{};
+    PeerFlags flags{};
+    peer_targets(h, true, dst, flags);
+    const CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    k_p2p_export_candidates<<<h->n_sm * 2, TPB, 0, h->stream>>>(
+        C, h->d_ctr.p, bases, h->xc.n, h->person_base, h->n_agents, (uint32_t) h->xc.cc, dst, flags, h->xc.seq,
+        reinterpret_cast<unsigned long long*>(h->xc.region + 1024), reinterpret_cast<unsigned int*>(h->xc.region + 1536));
+    CU(h, cudaGetLastError());
+    return HEROS_OK;
+}
+
+int32_t heros_window_recv_candidates(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are received between heros_window_transmit and heros_window_finish");
+    cudaSetDevice(h->cfg.device);
+    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region) + 64, h->xc.n, h->xc.seq, h->d_ctr.p);
+    CU(h, cudaGetLastError());
+    return heros_import_candidate_blocks_device(h, h->xc.n, (int64_t) h->xc.cc,
+                                                h->xc.region + REGION_HEADER + (size_t) h->xc.n * guest_block_bytes(h->xc.gc));
 }
 
 }  // extern "C"

@@ -221,6 +221,36 @@ class HerosEngine:
         self._check(self._lib.heros_import_candidate_blocks_device(self._h, int(n_blocks), int(capacity),
                                                                    C.c_void_p(blocks)))
 
+    # ---- peer-to-peer exchange over NVLink (CUDA IPC): no collective call ----
+    def exchange_create(self, rank: int, n_peers: int, guest_capacity: int, candidate_capacity: int):
+        """Returns (64-byte IPC handle as a numpy uint8 array, device pointer of the region)."""
+        handle = np.zeros(64, np.uint8)
+        region = C.c_void_p()
+        self._check(self._lib.heros_exchange_create(self._h, int(rank), int(n_peers), int(guest_capacity),
+                                                    int(candidate_capacity), _p(handle), C.byref(region)))
+        return handle, int(region.value or 0)
+
+    def exchange_connect(self, handles: Optional[np.ndarray], local_regions=None):
+        hs = None if handles is None else np.ascontiguousarray(handles, np.uint8)
+        loc = None
+        if local_regions is not None:
+            loc = (C.c_void_p * len(local_regions))(*[C.c_void_p(int(x)) if x else None for x in local_regions])
+        self._check(self._lib.heros_exchange_connect(self._h, _p(hs), loc))
+
+    def window_send_guests(self, row_offsets, person: int, loc: int, sub: int, t_in: int, t_out: int):
+        off = _arr(row_offsets, np.int64)
+        self._check(self._lib.heros_window_send_guests(self._h, _p(off), *(C.c_void_p(x) for x in (person, loc, sub, t_in, t_out))))
+
+    def window_recv_guests(self):
+        self._check(self._lib.heros_window_recv_guests(self._h))
+
+    def window_send_candidates(self, person_bases):
+        b = _arr(person_bases, np.int32)
+        self._check(self._lib.heros_window_send_candidates(self._h, _p(b)))
+
+    def window_recv_candidates(self):
+        self._check(self._lib.heros_window_recv_candidates(self._h))
+
     def window_finish(self) -> Dict[str, float]:
         st = _lib.StepStats()
         self._check(self._lib.heros_window_finish(self._h, C.byref(st)))

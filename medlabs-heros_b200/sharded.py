@@ -298,3 +298,80 @@ def step_window_blocks_in_process(exchanges: List[BlockExchange], t_until: float
     run(lambda x: x.guests_in_and_transmit())
     transpose(lambda x: x.c_send, lambda x: x.c_recv, exchanges[0].c_bytes)
     return run(lambda x: x.candidates_in_and_finish())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the block exchange with no collective at all: the kernels write into the peers' memory over NVLink (CUDA IPC)
+# ---------------------------------------------------------------------------------------------------------------------
+class PeerExchange:
+    """Window driver of the peer-to-peer exchange (heros_exchange_create / heros_window_send_guests and friends): the
+    shards of one node map each other's receive regions once (the 64-byte IPC handles are gathered with
+    torch.distributed); afterwards a window needs no collective call and no host synchronisation before its end.
+    ``local_peers``: the PeerExchange objects of shards living in THIS process (tests), connected by device pointer."""
+
+    VISIT_COLUMNS = BlockExchange.VISIT_COLUMNS
+
+    def __init__(self, shard: ShardedEngine, guest_capacity: int, candidate_capacity: int = 4096):
+        self.shard = shard
+        self.gc = max(4, (int(guest_capacity) + 3) // 4 * 4)
+        self.cc = max(4, (int(candidate_capacity) + 3) // 4 * 4)
+        self.handle, self.region = shard.engine.exchange_create(shard.rank, shard.world, self.gc, self.cc)
+        self.person_bases = shard.person_bases.to(torch.int32).numpy()
+        self._keep = None
+
+    def connect(self, group=None, local_peers: Optional[List["PeerExchange"]] = None):
+        import numpy as np
+        if local_peers is not None:
+            self.shard.engine.exchange_connect(None, [0 if p is self else p.region for p in local_peers])
+            return
+        import torch.distributed as dist
+        mine = torch.from_numpy(self.handle.copy()).to(self.shard.device)
+        all_handles = [torch.empty_like(mine) for _ in range(self.shard.world)]
+        dist.all_gather(all_handles, mine, group=group)
+        self.shard.engine.exchange_connect(np.stack([h.cpu().numpy() for h in all_handles]))
+
+    def begin_and_send(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets):
+        sh, eng = self.shard, self.shard.engine
+        eng.window_begin(t_until)
+        if remote is not None and remote["person"].device != sh.device:  # pinned host columns: H2D on the engine stream
+            remote = {k: v.to(sh.device, non_blocking=True) for k, v in remote.items()}
+        self._keep = remote  # read asynchronously by the pack kernel
+        ptrs = [0] * 5 if remote is None or remote["person"].numel() == 0 else [remote[k].data_ptr() for k in self.VISIT_COLUMNS]
+        sh.sent_stays += int(row_offsets[-1])
+        eng.window_send_guests(row_offsets, *ptrs)
+
+    def receive_and_transmit(self):
+        eng = self.shard.engine
+        eng.window_recv_guests()
+        eng.window_transmit()
+        eng.window_send_candidates(self.person_bases)
+
+    def receive_and_finish(self):
+        eng = self.shard.engine
+        eng.window_recv_candidates()
+        return eng.window_finish()
+
+    def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets, group=None):
+        with self.shard.on_stream():
+            self.begin_and_send(t_until, remote, row_offsets)
+            self.receive_and_transmit()
+            return self.receive_and_finish()
+
+
+def step_window_peers_in_process(exchanges: List[PeerExchange], t_until: float, remotes, offsets):
+    """The peer-to-peer window for several shards living in ONE process on one GPU: every phase is issued for all shards
+    before the next one starts, so no kernel ever waits for a flag that has not been raised yet."""
+    dev = exchanges[0].shard.device
+    for x, r, o in zip(exchanges, remotes, offsets):
+        with x.shard.on_stream():
+            x.begin_and_send(t_until, r, o)
+    torch.cuda.synchronize(dev)
+    for x in exchanges:
+        with x.shard.on_stream():
+            x.receive_and_transmit()
+    torch.cuda.synchronize(dev)
+    out = []
+    for x in exchanges:
+        with x.shard.on_stream():
+            out.append(x.receive_and_finish())
+    return out

@@ -28,7 +28,9 @@ def build_engine(scn, props, model, trigger, seed, p0, p1, l0, l1):
 @pytest.mark.parametrize("model,trigger,world,exchange", [("area", _lib.TRIGGER_ENTER_AND_EXIT, 2, "rows"),
                                                           ("distance", _lib.TRIGGER_EXIT_ONLY, 3, "rows"),
                                                           ("area", _lib.TRIGGER_EXIT_ONLY, 3, "blocks"),
-                                                          ("distance", _lib.TRIGGER_ENTER_AND_EXIT, 2, "blocks")])
+                                                          ("distance", _lib.TRIGGER_ENTER_AND_EXIT, 2, "blocks"),
+                                                          ("distance", _lib.TRIGGER_EXIT_ONLY, 3, "peers"),
+                                                          ("area", _lib.TRIGGER_ENTER_AND_EXIT, 2, "peers")])
 def test_sharded_equals_unsharded_and_oracle(model, trigger, world, exchange):
     scn = Scenario(seed=21, n_persons=900, n_households=330, n_workplaces=30, n_shops=4, days=9,
                    shop_visits_per_day=2.0, tie_fraction=0.2, short_gap_fraction=0.2)
@@ -53,7 +55,12 @@ def test_sharded_equals_unsharded_and_oracle(model, trigger, world, exchange):
         sh.engine.submit_visits(scn.person[own], scn.loc[own], scn.sub[own], scn.t_in[own], scn.t_out[own])
     counts = []
     n_remote = 0
-    exchanges = [sharded.BlockExchange(sh, guest_capacity=2048, candidate_capacity=512) for sh in shards]
+    if exchange == "peers":  # kernels write straight into the other shards' regions (same process: device pointers)
+        exchanges = [sharded.PeerExchange(sh, guest_capacity=2048, candidate_capacity=512) for sh in shards]
+        for x in exchanges:
+            x.connect(local_peers=exchanges)
+    else:
+        exchanges = [sharded.BlockExchange(sh, guest_capacity=2048, candidate_capacity=512) for sh in shards]
     for d in range(scn.days):
         t0, t1 = 24.0 * d, 24.0 * (d + 1)
         remotes, offsets = [], []
@@ -61,16 +68,18 @@ def test_sharded_equals_unsharded_and_oracle(model, trigger, world, exchange):
             m = (p_owner == r) & (l_owner != r) & (scn.t_in < t1) & (scn.t_out >= t0)   # active in the window
             n_remote += int(m.sum())
             cols = {"person": scn.person[m], "loc": scn.loc[m], "sub": scn.sub[m], "t_in": scn.t_in[m], "t_out": scn.t_out[m]}
-            if exchange == "blocks":  # the producer of the stays groups them by destination shard
+            if exchange != "rows":  # the producer of the stays groups them by destination shard
                 cols, off = sharded.sort_by_destination(cols, lb, world)
                 offsets.append(off)
             remotes.append({k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cols.items()})
         if exchange == "blocks":
             sharded.step_window_blocks_in_process(exchanges, t1, remotes, offsets)
+        elif exchange == "peers":
+            sharded.step_window_peers_in_process(exchanges, t1, remotes, offsets)
         else:
             sharded.step_window_in_process(shards, t1, remotes)
         counts.append(sum(sh.engine.phase_counts() for sh in shards))
-    assert n_remote > 1000 and (exchange == "blocks" or sum(sh.sent_candidates for sh in shards) > 10)
+    assert n_remote > 1000 and (exchange != "rows" or sum(sh.sent_candidates for sh in shards) > 10)
 
     inf = [sh.engine.infections() for sh in shards]
     tr = [sh.engine.transitions() for sh in shards]
