@@ -220,9 +220,12 @@ __global__ void __launch_bounds__(TPB) k_import_candidate_blocks(int n_blocks, u
 //      last publishes the counts and raises this shard's flag at every peer, and the receiver waits for the flags of
 //      all its peers with a one-block kernel before it parses its region.  No collective call, no host in the loop.
 //      Region of a shard: guest flags u64[64] | candidate flags u64[64] | local counters u64[64] | done counter |
-//      (pad to 4096) | guest blocks [n_peers] | candidate blocks [n_peers]  (block s is written by shard s).
-//      A flag carries the window number, so nothing is ever reset; a shard cannot run ahead by more than one exchange
-//      (it needs every peer's flag of the previous one), so a block is never overwritten before it was parsed. ----
+//      (pad to 4096) | guest blocks [2][n_peers] | candidate blocks [n_peers]  (block s is written by shard s).
+//      A flag carries the window number, so nothing is ever reset.  Guests: every shard waits for the flags of ALL
+//      peers (anybody may send guests), and the blocks alternate between two buffers with the window parity: a peer
+//      can be at most one window ahead (its next-but-one window needs this shard's flag of the next one, raised after
+//      this window was parsed).  Candidates can only come back from the shards this one sent guests to, so only their
+//      flags are awaited -- a shard does not wait for the slowest shard of the node, only for its neighbours. ----
 constexpr size_t REGION_HEADER = 4096;
 struct PeerPtrs { unsigned char* p[MAX_PEERS]; };
 struct PeerFlags { unsigned long long* p[MAX_PEERS]; };
@@ -326,9 +329,10 @@ __global__ void __launch_bounds__(TPB) k_p2p_export_candidates(CandArrays Cd, Co
 }
 
 // one block waits until every peer has raised its flag for this window (2^33 cycles ~ 4 s, then the window fails)
-__global__ void k_p2p_wait(const unsigned long long* my_flags, int n_peers, unsigned long long seq, Counters* ctr)
+__global__ void k_p2p_wait(const unsigned long long* my_flags, int n_peers, unsigned long long mask, unsigned long long seq,
+                           Counters* ctr)
 {
-    if ((int) threadIdx.x >= n_peers) return;
+    if ((int) threadIdx.x >= n_peers || !((mask >> threadIdx.x) & 1ull)) return;
     const volatile unsigned long long* f = my_flags + threadIdx.x;
     const long long t0 = clock64();
     while (*f < seq)
@@ -513,7 +517,9 @@ int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, i
 }
 
 // ---- peer-to-peer exchange over NVLink (CUDA IPC) ----------------------------------------------------------------------
-static size_t region_bytes(int n, size_t gc, size_t cc) { return REGION_HEADER + (size_t) n * (guest_block_bytes(gc) + candidate_block_bytes(cc)); }
+static int32_t heros_import_candidate_blocks_from(heros_handle h, unsigned long long mask);
+
+static size_t region_bytes(int n, size_t gc, size_t cc) { return REGION_HEADER + (size_t) n * (2 * guest_block_bytes(gc) + candidate_block_bytes(cc)); }
 
 int32_t heros_exchange_create(heros_handle h, int32_t rank, int32_t n_peers, int64_t guest_capacity, int64_t candidate_capacity,
                               void* ipc_handle_out, void** region_out)
@@ -560,11 +566,12 @@ int32_t heros_exchange_connect(heros_handle h, const void* ipc_handles, void* co
 static void peer_targets(heros_handle h, bool candidates, PeerPtrs& dst, PeerFlags& flags)
 {
     const size_t gb = guest_block_bytes(h->xc.gc), cb = candidate_block_bytes(h->xc.cc);
+    const size_t parity = (size_t) (h->xc.seq & 1ull);  // guest blocks alternate between two buffers
     for (int d = 0; d < h->xc.n; ++d)
     {
         unsigned char* base = h->xc.peer[d];
-        dst.p[d] = candidates ? base + REGION_HEADER + (size_t) h->xc.n * gb + (size_t) h->xc.rank * cb
-                              : base + REGION_HEADER + (size_t) h->xc.rank * gb;
+        dst.p[d] = candidates ? base + REGION_HEADER + 2 * (size_t) h->xc.n * gb + (size_t) h->xc.rank * cb
+                              : base + REGION_HEADER + (parity * (size_t) h->xc.n + (size_t) h->xc.rank) * gb;
         flags.p[d] = reinterpret_cast<unsigned long long*>(base) + (candidates ? 64 : 0) + h->xc.rank;
     }
 }
@@ -588,8 +595,11 @@ int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, con
     cudaSetDevice(h->cfg.device);
     PeerPtrs dst{};
     PeerFlags flags{};
-    peer_targets(h, false, dst, flags);
     ++h->xc.seq;
+    peer_targets(h, false, dst, flags);
+    h->xc.sent_to = 0;  // candidates can only come back from the shards that get guests from this one
+    for (int d = 0; d < n; ++d)
+        if (off.v[d + 1] > off.v[d] && d != h->xc.rank) h->xc.sent_to |= 1ull << d;
     unsigned int* done = reinterpret_cast<unsigned int*>(h->xc.region + 1536);
     k_p2p_pack_guests<<<blocks_for((size_t) std::max<int64_t>(rows, n)), TPB, 0, h->stream>>>(
         (uint32_t) rows, off, n, person, location, sublocation, t_in, t_out, h->person_base, h->n_agents, h->d_view.p,
@@ -604,9 +614,12 @@ int32_t heros_window_recv_guests(heros_handle h)
     if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
     if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are received between heros_window_begin and heros_window_transmit");
     cudaSetDevice(h->cfg.device);
-    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region), h->xc.n, h->xc.seq, h->d_ctr.p);
+    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region), h->xc.n, ~0ull,
+                                               h->xc.seq, h->d_ctr.p);
     CU(h, cudaGetLastError());
-    return heros_submit_guest_blocks_device(h, h->xc.n, (int64_t) h->xc.gc, h->xc.region + REGION_HEADER);
+    return heros_submit_guest_blocks_device(h, h->xc.n, (int64_t) h->xc.gc,
+                                            h->xc.region + REGION_HEADER +
+                                                (size_t) (h->xc.seq & 1ull) * (size_t) h->xc.n * guest_block_bytes(h->xc.gc));
 }
 
 int32_t heros_window_send_candidates(heros_handle h, const int32_t* person_bases)
@@ -634,10 +647,24 @@ int32_t heros_window_recv_candidates(heros_handle h)
     if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
     if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are received between heros_window_transmit and heros_window_finish");
     cudaSetDevice(h->cfg.device);
-    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region) + 64, h->xc.n, h->xc.seq, h->d_ctr.p);
+    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region) + 64, h->xc.n,
+                                               h->xc.sent_to, h->xc.seq, h->d_ctr.p);
     CU(h, cudaGetLastError());
-    return heros_import_candidate_blocks_device(h, h->xc.n, (int64_t) h->xc.cc,
-                                                h->xc.region + REGION_HEADER + (size_t) h->xc.n * guest_block_bytes(h->xc.gc));
+    return heros_import_candidate_blocks_from(h, h->xc.sent_to);
 }
 
 }  // extern "C"
+
+// candidate blocks of the peers in `mask` only (the others were not awaited: their blocks may still be written)
+static int32_t heros_import_candidate_blocks_from(heros_handle h, unsigned long long mask)
+{
+    const size_t cb = candidate_block_bytes(h->xc.cc);
+    const unsigned char* first = h->xc.region + REGION_HEADER + 2 * (size_t) h->xc.n * guest_block_bytes(h->xc.gc);
+    for (int d = 0; d < h->xc.n; ++d)
+    {
+        if (!((mask >> d) & 1ull)) continue;
+        const int32_t rc = heros_import_candidate_blocks_device(h, 1, (int64_t) h->xc.cc, first + (size_t) d * cb);
+        if (rc != HEROS_OK) return rc;
+    }
+    return HEROS_OK;
+}
