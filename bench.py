@@ -271,6 +271,7 @@ def run_ours(args):
             if args.exchange == "p2p":
                 bx = sharded.PeerExchange(sh, guest_capacity[0], candidate_capacity=4096)
                 bx.connect()
+                bx.set_sources([(rank - 1) % world])  # commuters come from the previous tile only
             else:
                 bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
         eng.seed_infections(N_INFECTED)

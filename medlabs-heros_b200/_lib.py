@@ -104,6 +104,8 @@ SIGNATURES = {
     "heros_import_candidate_blocks_device": (C.c_int32, [_P, C.c_int32, C.c_int64, _P]),
     "heros_exchange_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, C.POINTER(_P)]),
     "heros_exchange_connect": (C.c_int32, [_P, _P, _P]),
+    "heros_exchange_set_sources": (C.c_int32, [_P, C.c_uint64]),
+    "heros_window_run_peers": (C.c_int32, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(StepStats)]),
     "heros_window_send_guests": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P]),
     "heros_window_recv_guests": (C.c_int32, [_P]),
     "heros_window_send_candidates": (C.c_int32, [_P, _P]),

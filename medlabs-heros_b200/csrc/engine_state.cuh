@@ -108,6 +108,7 @@ struct heros_engine
         unsigned char* region = nullptr; size_t bytes = 0; int rank = 0, n = 0; size_t gc = 0, cc = 0;
         unsigned char* peer[64] = {}; bool opened[64] = {}; bool connected = false; unsigned long long seq = 0;
         unsigned long long sent_to = 0;  // peers that got guests from this shard in the window in progress
+        unsigned long long sources = ~0ull;  // peers that may send guests to this shard (heros_exchange_set_sources)
     } xc;
     int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
     double win_T0 = 0.0, win_T1 = 0.0;

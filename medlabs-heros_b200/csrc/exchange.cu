@@ -466,23 +466,31 @@ int32_t heros_pack_guest_blocks_device(heros_handle h, int32_t n_blocks, const i
     return HEROS_OK;
 }
 
-int32_t heros_submit_guest_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
+static int32_t submit_guest_blocks_append(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
 {
     int32_t rc = check_blocks(h, n_blocks, capacity, blocks);
     if (rc != HEROS_OK) return rc;
     if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are submitted between heros_window_begin and heros_window_transmit");
-    if (h->n_guest != 0) return fail(h, HEROS_ERR_INVALID, "guest blocks cannot be combined with other guest submissions of the window");
     cudaSetDevice(h->cfg.device);
-    const size_t tot = (size_t) n_blocks * (size_t) capacity;
-    CU(h, h->g_gid.ensure(tot)); CU(h, h->g_key.ensure(tot)); CU(h, h->g_rank.ensure(tot)); CU(h, h->g_view.ensure(tot));
-    CU(h, h->g_ill_end.ensure(tot)); CU(h, h->g_tin.ensure(tot)); CU(h, h->g_tout.ensure(tot));
-    k_submit_guest_blocks<<<blocks_for(tot), TPB, 0, h->stream>>>(
+    const size_t off = h->n_guest, add = (size_t) n_blocks * (size_t) capacity, tot = off + add;
+    if (tot >= 0x7fffffffull) return fail(h, HEROS_ERR_CAPACITY, "too many guest stays");
+    CU(h, h->g_gid.ensure(tot, true, h->stream)); CU(h, h->g_key.ensure(tot, true, h->stream));
+    CU(h, h->g_rank.ensure(tot, true, h->stream)); CU(h, h->g_view.ensure(tot, true, h->stream));
+    CU(h, h->g_ill_end.ensure(tot, true, h->stream)); CU(h, h->g_tin.ensure(tot, true, h->stream));
+    CU(h, h->g_tout.ensure(tot, true, h->stream));
+    k_submit_guest_blocks<<<blocks_for(add), TPB, 0, h->stream>>>(
         n_blocks, (uint32_t) capacity, (const unsigned char*) blocks, h->win_T1, h->location_base, h->d_loc_base.p,
-        h->d_loc_nsub.p, h->n_loc, h->g_gid.p, h->g_view.p, h->g_ill_end.p, h->g_key.p, h->g_tin.p, h->g_tout.p,
-        h->g_rank.p, h->bk_count.p, h->d_ctr.p);
+        h->d_loc_nsub.p, h->n_loc, h->g_gid.p + off, h->g_view.p + off, h->g_ill_end.p + off, h->g_key.p + off,
+        h->g_tin.p + off, h->g_tout.p + off, h->g_rank.p + off, h->bk_count.p, h->d_ctr.p);
     CU(h, cudaGetLastError());
     h->n_guest = (uint32_t) tot;
     return HEROS_OK;
+}
+
+int32_t heros_submit_guest_blocks_device(heros_handle h, int32_t n_blocks, int64_t capacity, const void* blocks)
+{
+    if (h && h->n_guest != 0) return fail(h, HEROS_ERR_INVALID, "guest blocks cannot be combined with other guest submissions of the window");
+    return submit_guest_blocks_append(h, n_blocks, capacity, blocks);
 }
 
 int32_t heros_export_candidate_blocks_device(heros_handle h, int32_t n_blocks, const int32_t* person_bases, int64_t capacity,
@@ -518,6 +526,7 @@ int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, i
 
 // ---- peer-to-peer exchange over NVLink (CUDA IPC) ----------------------------------------------------------------------
 static int32_t heros_import_candidate_blocks_from(heros_handle h, unsigned long long mask);
+static int32_t submit_guest_blocks_from(heros_handle h, unsigned long long mask);
 
 static size_t region_bytes(int n, size_t gc, size_t cc) { return REGION_HEADER + (size_t) n * (2 * guest_block_bytes(gc) + candidate_block_bytes(cc)); }
 
@@ -576,6 +585,28 @@ static void peer_targets(heros_handle h, bool candidates, PeerPtrs& dst, PeerFla
     }
 }
 
+int32_t heros_exchange_set_sources(heros_handle h, uint64_t source_mask)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (!h->xc.region) return fail(h, HEROS_ERR_INVALID, "heros_exchange_create has not been called");
+    h->xc.sources = source_mask | (1ull << h->xc.rank);
+    return HEROS_OK;
+}
+
+int32_t heros_window_run_peers(heros_handle h, double t_until, const int64_t* row_offsets, const int32_t* person,
+                               const int32_t* location, const int16_t* sublocation, const double* t_in, const double* t_out,
+                               const int32_t* person_bases, heros_step_stats* stats)
+{
+    int32_t rc;
+    if ((rc = heros_window_begin(h, t_until)) != HEROS_OK) return rc;
+    if ((rc = heros_window_send_guests(h, row_offsets, person, location, sublocation, t_in, t_out)) != HEROS_OK) return rc;
+    if ((rc = heros_window_recv_guests(h)) != HEROS_OK) return rc;
+    if ((rc = heros_window_transmit(h)) != HEROS_OK) return rc;
+    if ((rc = heros_window_send_candidates(h, person_bases)) != HEROS_OK) return rc;
+    if ((rc = heros_window_recv_candidates(h)) != HEROS_OK) return rc;
+    return heros_window_finish(h, stats);
+}
+
 int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, const int32_t* person, const int32_t* location,
                                  const int16_t* sublocation, const double* t_in, const double* t_out)
 {
@@ -614,12 +645,10 @@ int32_t heros_window_recv_guests(heros_handle h)
     if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
     if (h->win_state != 1) return fail(h, HEROS_ERR_INVALID, "guest stays are received between heros_window_begin and heros_window_transmit");
     cudaSetDevice(h->cfg.device);
-    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region), h->xc.n, ~0ull,
-                                               h->xc.seq, h->d_ctr.p);
+    k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region), h->xc.n,
+                                               h->xc.sources, h->xc.seq, h->d_ctr.p);
     CU(h, cudaGetLastError());
-    return heros_submit_guest_blocks_device(h, h->xc.n, (int64_t) h->xc.gc,
-                                            h->xc.region + REGION_HEADER +
-                                                (size_t) (h->xc.seq & 1ull) * (size_t) h->xc.n * guest_block_bytes(h->xc.gc));
+    return submit_guest_blocks_from(h, h->xc.sources);
 }
 
 int32_t heros_window_send_candidates(heros_handle h, const int32_t* person_bases)
@@ -667,4 +696,20 @@ static int32_t heros_import_candidate_blocks_from(heros_handle h, unsigned long 
         if (rc != HEROS_OK) return rc;
     }
     return HEROS_OK;
+}
+
+// guest blocks of the peers in `mask` only: the others were declared not to send guests (heros_exchange_set_sources)
+// and were not awaited.  The guest arrays are indexed by block * capacity + row, so every peer keeps its slot.
+static int32_t submit_guest_blocks_from(heros_handle h, unsigned long long mask)
+{
+    const unsigned char* first = h->xc.region + REGION_HEADER +
+                                 (size_t) (h->xc.seq & 1ull) * (size_t) h->xc.n * guest_block_bytes(h->xc.gc);
+    bool all = true;
+    for (int d = 0; d < h->xc.n; ++d) all = all && ((mask >> d) & 1ull);
+    if (all) return heros_submit_guest_blocks_device(h, h->xc.n, (int64_t) h->xc.gc, first);
+    // compact the awaited blocks' indices: parse them one by one into consecutive guest slots
+    int32_t rc = HEROS_OK;
+    for (int d = 0; d < h->xc.n && rc == HEROS_OK; ++d)
+        if ((mask >> d) & 1ull) rc = submit_guest_blocks_append(h, 1, (int64_t) h->xc.gc, first + (size_t) d * guest_block_bytes(h->xc.gc));
+    return rc;
 }

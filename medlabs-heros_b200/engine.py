@@ -237,6 +237,20 @@ class HerosEngine:
             loc = (C.c_void_p * len(local_regions))(*[C.c_void_p(int(x)) if x else None for x in local_regions])
         self._check(self._lib.heros_exchange_connect(self._h, _p(hs), loc))
 
+    def exchange_set_sources(self, ranks):
+        mask = 0
+        for r in ranks:
+            mask |= 1 << int(r)
+        self._check(self._lib.heros_exchange_set_sources(self._h, mask))
+
+    def window_run_peers(self, t_until: float, row_offsets: np.ndarray, person: int, loc: int, sub: int, t_in: int,
+                         t_out: int, person_bases: np.ndarray) -> Dict[str, float]:
+        st = _lib.StepStats()
+        self._check(self._lib.heros_window_run_peers(self._h, float(t_until), _p(row_offsets),
+                                                     *(C.c_void_p(x) for x in (person, loc, sub, t_in, t_out)),
+                                                     _p(person_bases), C.byref(st)))
+        return st.as_dict()
+
     def window_send_guests(self, row_offsets, person: int, loc: int, sub: int, t_in: int, t_out: int):
         off = _arr(row_offsets, np.int64)
         self._check(self._lib.heros_window_send_guests(self._h, _p(off), *(C.c_void_p(x) for x in (person, loc, sub, t_in, t_out))))
