@@ -72,7 +72,9 @@ def load_props(model):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md): sampled in-process through
+    NVML every 10 ms (a spawned nvidia-smi takes tens of milliseconds -- longer than the timed region -- and its driver
+    calls disturb the run it is meant to observe); nvidia-smi is the fallback when NVML cannot be loaded."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -82,9 +84,37 @@ class ClockSampler:
         self._stop = threading.Event()
         self._index = index
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = self._dev = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml, self._dev = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def _sample(self):
         try:
+            if self._nvml is not None:
+                n = self._nvml
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                                  ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                  ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                  ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+                    if r & bit:
+                        self.reasons.add(name)
+                return
             out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                   "-i", str(self._index)], capture_output=True, text=True, timeout=5).stdout
             f = [x.strip() for x in out.strip().split(",")]
@@ -99,7 +129,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.05)
+            self._stop.wait(0.01 if self._nvml is not None else 0.05)
 
     def __enter__(self):
         self._sample()
@@ -113,7 +143,8 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": "NVML, every 10 ms during the timed region" if self._nvml is not None else "nvidia-smi"}
 
 
 def oracle_objects(args, props, city):
