@@ -209,3 +209,26 @@ def test_total_location_branch_in_windows(model, trigger):
         assert in_parks > 20          # the total branch infected people, in several zones
         assert len(np.unique(ora["infections"]["sub"][ora["infections"]["loc"] >= park0])) > 1
     gpu["engine"].close()
+
+
+def test_one_crowded_sublocation_takes_the_global_scratch_class():
+    """A single shop for the whole town: > 4096 stays and > 8192 movement events per day in one sub-location, which is
+    beyond the shared-memory classes of the group kernels (class 4 works in global scratch); and a second run with a
+    10 s threshold, where the bound on the evaluations per window (8642) exceeds what the shared-memory classes keep."""
+    scn = Scenario(seed=15, n_persons=1600, n_households=550, n_workplaces=6, n_shops=1, days=5,
+                   shop_visits_per_day=4.0, tie_fraction=0.3, short_gap_fraction=0.3)
+    for model, trigger, threshold in (("distance", "exit", None), ("area", "both", "10")):
+        props = hot_props(model)
+        if model == "area":
+            props["covidT_area.contagiousness"] = "20.0"
+        if threshold:
+            props["covidT_area.calculation_threshold"] = threshold
+        ora = run_oracle(scn, props, MODELS[model], TRIGGERS[trigger], seed=6)
+        gpu = run_gpu(scn, props, MODELS[model], TRIGGERS[trigger], seed=6)
+        shop = scn.n_loc - 1
+        per_day = ((scn.loc == shop).sum()) / scn.days
+        assert per_day > 4096
+        assert len(ora["infections"]["person"]) > 100
+        assert_same_run(gpu, ora)
+        assert sum(s["evaluations"] for s in gpu["stats"]) == ora["evaluations"]
+        gpu["engine"].close()
