@@ -814,7 +814,7 @@ int32_t window_transmit(heros_handle h)
     const size_t list_cap = (size_t) n_total / 32 + 16;
     const size_t occupied_cap = std::min<size_t>(n_keys, n_total) + 16;
     CU(h, h->sub_seg[0].ensure(occupied_cap));
-    CU(h, h->sub_seg[1].ensure((size_t) n_total / 8 + 16));
+    CU(h, h->sub_seg[1].ensure((size_t) n_total / 9 + 16));  // sub-locations of 9..32 stays
     for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
     // exact bounds: a stay leaves at most one draw item, a sub-location at most one table entry per movement event
@@ -858,7 +858,7 @@ int32_t window_transmit(heros_handle h)
     c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) h->cand_person.n;
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
-    c.sub_cap = (uint32_t) std::min(h->sub_seg[0].n, h->sub_seg[1].n);
+    for (int k = 0; k < 2; ++k) c.sub_cap[k] = (uint32_t) h->sub_seg[k].n;
     for (int k = 0; k < N_CLS; ++k) c.blk_seg[k] = h->blk_seg[k].p;
     c.blk_cap = big.blk_cap;
     c.tab_t = h->tab_t.p; c.tab_p = h->tab_p.p; c.tab_cap = std::min(h->tab_t.n, h->tab_p.n);

@@ -118,7 +118,7 @@ struct WindowCtx
     // candidates
     uint32_t* cand_person; uint64_t* cand_gkey; double* cand_t; double* cand_p; uint32_t cand_cap;
     // work lists filled by k_transmit_thread
-    uint32_t* sub_seg[2]; uint32_t sub_cap;          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
+    uint32_t* sub_seg[2]; uint32_t sub_cap[2];          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
     uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;      // ... and for the group kernels
     // draws queued by the group kernels for k_draw: the evaluations with p > 0 of every sub-location (time, p), and one
     // item per susceptible stay = a run of table entries, numbered by its first (stay, evaluation) pair

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
         // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
         const int which = n > THREAD_SLOW_MAX ? 1 : 0;
         const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
-        if (slot < c.sub_cap) c.sub_seg[which][slot] = key;
+        if (slot < c.sub_cap[which]) c.sub_seg[which][slot] = key;
         else atomicOr(&c.ctr->overflow, 2u);
     }
     occupied = __reduce_add_sync(FULL, occupied);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256, 4) k_transmit_sub(const WindowCtx c)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     constexpr int WHICH = S == 8 ? 0 : 1;
-    const uint32_t n_list = (uint32_t) min((unsigned long long) c.sub_cap, c.ctr->n_sub[WHICH]);
+    const uint32_t n_list = (uint32_t) min((unsigned long long) c.sub_cap[WHICH], c.ctr->n_sub[WHICH]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     StayRec* my = &s_rec[wib][g0];

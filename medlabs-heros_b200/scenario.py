@@ -88,47 +88,65 @@ class City:
     """Static tables of a synthetic city, in the layout heros_set_location_types / _locations / _persons take."""
 
     def __init__(self, n_persons: int, seed: int = 20240807, n_locations: Optional[int] = None,
-                 box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8):
+                 box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8,
+                 location_table: Optional[Dict[str, np.ndarray]] = None):
+        """``location_table``: a real location table (type, nsub, area_per_sub, lat, lon -- e.g. the Helsinki fixture
+        of tests/golden) instead of the synthetic one; the population is synthetic either way."""
         rng = np.random.default_rng(seed)
         self.n_persons = int(n_persons)
-        if n_locations is None:
-            n_locations = int(round(143178 * n_persons / 553667))  # The Hague: 143 178 locations for 553 667 persons
-        scale = n_locations / HELSINKI_LOCATIONS
         self.type_infect_sub = TYPE_INFECT_SUB.copy()
         self.type_correction = TYPE_CORRECTION.copy()
-
         n_households = max(1, int(round(n_persons / 2.15)))
-        types, nsubs, per_sub_area = [], [], []
-        for name, count, nsub, area in CATEGORIES:
-            k = max(1, int(round(count * scale)))
-            if name == "Accommodation":
-                k = max(1, min(k, n_households))
-                sub = np.zeros(k, np.int64)  # filled below from the households
-            elif name == "Workplace":
-                sub = np.minimum(1 + np.floor(rng.exponential(1.75, k)).astype(np.int64), 100)
-            else:
-                sub = np.full(k, nsub, np.int64)
-            types.append(np.full(k, TYPE_ID[name], np.uint8))
-            nsubs.append(sub)
-            per_sub_area.append(np.full(k, area))
-        loc_type = np.concatenate(types)
-        loc_nsub = np.concatenate(nsubs)
-        area_sub = np.concatenate(per_sub_area)
-        n_loc = len(loc_type)
-        x = origin_m[0] + rng.random(n_loc) * box_m[0]
-        y = origin_m[1] + rng.random(n_loc) * box_m[1]
+        if location_table is not None:
+            # columns as the loader reads them (ConstructHerosModel.java:300-395); rows with nb_sublocations = 0 and
+            # area = -1 are kept as they are (SURVEY.md 8a A12)
+            loc_type = np.asarray(location_table["type"], np.uint8).copy()
+            loc_nsub = np.asarray(location_table["nsub"], np.int64).copy()
+            area_sub = np.asarray(location_table["area_per_sub"], np.float64).copy()
+            n_loc = len(loc_type)
+            lat, lon = np.asarray(location_table["lat"], np.float64), np.asarray(location_table["lon"], np.float64)
+            x = (lon - lon.mean()) * 111320.0 * np.cos(np.deg2rad(lat.mean()))  # metres, equirectangular
+            y = (lat - lat.mean()) * 110540.0
+            acc = np.nonzero(loc_type == TYPE_ID["Accommodation"])[0]
+            # households by the number of dwellings of the building; a few live in buildings listed with 0 sub-locations
+            w = np.maximum(loc_nsub[acc], 0).astype(np.float64) + 0.05
+            hh_building = acc[rng.choice(len(acc), n_households, p=w / w.sum())]
+            hh_sub = rng.integers(0, 1 << 30, n_households) % np.maximum(loc_nsub[hh_building], 1)
+        else:
+            if n_locations is None:
+                n_locations = int(round(143178 * n_persons / 553667))  # The Hague: 143 178 locations for 553 667 persons
+            scale = n_locations / HELSINKI_LOCATIONS
+            types, nsubs, per_sub_area = [], [], []
+            for name, count, nsub, area in CATEGORIES:
+                k = max(1, int(round(count * scale)))
+                if name == "Accommodation":
+                    k = max(1, min(k, n_households))
+                    sub = np.zeros(k, np.int64)  # filled below from the households
+                elif name == "Workplace":
+                    sub = np.minimum(1 + np.floor(rng.exponential(1.75, k)).astype(np.int64), 100)
+                else:
+                    sub = np.full(k, nsub, np.int64)
+                types.append(np.full(k, TYPE_ID[name], np.uint8))
+                nsubs.append(sub)
+                per_sub_area.append(np.full(k, area))
+            loc_type = np.concatenate(types)
+            loc_nsub = np.concatenate(nsubs)
+            area_sub = np.concatenate(per_sub_area)
+            n_loc = len(loc_type)
+            x = origin_m[0] + rng.random(n_loc) * box_m[0]
+            y = origin_m[1] + rng.random(n_loc) * box_m[1]
 
-        # households -> Accommodation sub-locations in order of first appearance (ConstructHerosModel.java:531-552)
-        acc = np.nonzero(loc_type == TYPE_ID["Accommodation"])[0]
-        hh_building = acc[rng.integers(0, len(acc), n_households)]
-        order = np.argsort(hh_building, kind="stable")
-        hh_sub = np.zeros(n_households, np.int64)
-        sorted_b = hh_building[order]
-        first = np.r_[True, sorted_b[1:] != sorted_b[:-1]]
-        start = np.maximum.accumulate(np.where(first, np.arange(n_households), 0))
-        hh_sub[order] = np.arange(n_households) - start
-        np.add.at(loc_nsub, hh_building, 1)
-        loc_nsub[acc] = np.maximum(loc_nsub[acc], 1)
+            # households -> Accommodation sub-locations in order of first appearance (ConstructHerosModel.java:531-552)
+            acc = np.nonzero(loc_type == TYPE_ID["Accommodation"])[0]
+            hh_building = acc[rng.integers(0, len(acc), n_households)]
+            order = np.argsort(hh_building, kind="stable")
+            hh_sub = np.zeros(n_households, np.int64)
+            sorted_b = hh_building[order]
+            first = np.r_[True, sorted_b[1:] != sorted_b[:-1]]
+            start = np.maximum.accumulate(np.where(first, np.arange(n_households), 0))
+            hh_sub[order] = np.arange(n_households) - start
+            np.add.at(loc_nsub, hh_building, 1)
+            loc_nsub[acc] = np.maximum(loc_nsub[acc], 1)
 
         # persons: ages, roles, households
         age = self._draw_ages(rng, n_persons)
@@ -149,7 +167,7 @@ class City:
         work_sub = np.zeros(n_persons, np.int64)
         wp = np.nonzero(loc_type == TYPE_ID["Workplace"])[0]
         workers = np.nonzero(np.isin(role, (ROLE_WORKER, ROLE_WEEKEND_WORKER, ROLE_ESSENTIAL_WORKER)))[0]
-        weights = loc_nsub[wp] / loc_nsub[wp].sum()
+        weights = np.maximum(loc_nsub[wp], 1) / np.maximum(loc_nsub[wp], 1).sum()
         work_loc[workers] = wp[rng.choice(len(wp), len(workers), p=weights)]
         from scipy.spatial import cKDTree
         for r, tname in ((ROLE_KINDERGARTEN, "Kindergarten"), (ROLE_PRIMARY, "PrimarySchool"),
@@ -165,7 +183,7 @@ class City:
             if len(who) and len(places):
                 work_loc[who] = places[rng.integers(0, len(places), len(who))]
         has = work_loc >= 0
-        work_sub[has] = rng.integers(0, 1 << 30, has.sum()) % loc_nsub[work_loc[has]]
+        work_sub[has] = rng.integers(0, 1 << 30, has.sum()) % np.maximum(loc_nsub[work_loc[has]], 1)
 
         # nearest / random candidate tables per Accommodation building (locators of the activity schedule)
         self.n_random_candidates = K = n_random_candidates

@@ -154,3 +154,21 @@ def test_mirror_classes_keep_the_reference_error_behaviour(capsys):
     assert "Unrecognized variable name covidT_area.beta" in capsys.readouterr().err
     with pytest.raises(ValueError):
         hb.HerosModel({"generic.diseasePropertiesModel": "sir"})
+
+
+def test_helsinki_location_fixture_is_the_reference_table():
+    """tests/golden/helsinki_locations.npz (tools/make_helsinki_fixture.py) is data/helsinki/locations.csv.gz, the one
+    real location table the reference ships: row count, sub-location total and the quirk rows SURVEY.md 8a A12 lists."""
+    tab = dict(np.load(os.path.join(GOLDEN, "helsinki_locations.npz")))
+    assert len(tab["type"]) == 69508 and int(tab["nsub"].sum()) == 431470 and int(tab["nsub"].max()) == 650
+    acc, wp = tab["type"] == scenario.TYPE_ID["Accommodation"], tab["type"] == scenario.TYPE_ID["Workplace"]
+    assert int(acc.sum()) == 20512 and int(wp.sum()) == 42169
+    assert int(((tab["nsub"] == 0) & acc).sum()) == 76 and int((tab["nsub"] == 0).sum()) == 76
+    assert int(((tab["area_per_sub"] < 0) & wp).sum()) == 3563 and (tab["nsub"][tab["area_per_sub"] < 0] == 1).all()
+    parks = tab["type"] == scenario.TYPE_ID["Park"]
+    assert (tab["nsub"][parks] == 1).all() and (tab["area_per_sub"][parks] == 300000.0).all()
+    assert 60.12 < tab["lat"].min() and tab["lat"].max() < 60.30 and 24.83 < tab["lon"].min() and tab["lon"].max() < 25.25
+    city = scenario.City(4000, seed=5, location_table=tab)
+    assert city.n_locations == 69508 and int(city.loc_nsub.sum()) == 431470
+    assert (city.loc_area[tab["nsub"] == 0] == 0.0).all()          # totalArea = area * 0 (ConstructHerosModel.java:381)
+    assert (city.home_sub < np.maximum(city.loc_nsub[city.home_loc], 1)).all()

@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from common import Scenario, assert_same_run, load_props, run_gpu, run_oracle
+import heros_b200 as hb
 from heros_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -232,3 +233,61 @@ def test_one_crowded_sublocation_takes_the_global_scratch_class():
         assert_same_run(gpu, ora)
         assert sum(s["evaluations"] for s in gpu["stats"]) == ora["evaluations"]
         gpu["engine"].close()
+
+
+@pytest.mark.parametrize("model", ["area", "distance"])
+def test_helsinki_real_location_table(model):
+    """BASELINE configs[1] as a parity case: the real Helsinki location table (69 508 locations, 431 470 sub-locations,
+    among them 76 homes listed with 0 sub-locations and 3 563 workplaces with area = -1) with a
+    synthetic population and the reference's activity schedule; engine vs oracle, event for event.  The degenerate rows
+    must behave as Java's IEEE arithmetic does: NaN / negative probabilities infect nobody."""
+    import os
+    from common import GOLDEN, sort_events
+    from heros_b200 import properties, scenario
+    from oracle import binding as ob
+    from common import oracle_props
+    tab = dict(np.load(os.path.join(GOLDEN, "helsinki_locations.npz")))
+    city = scenario.City(24000, seed=5, location_table=tab)
+    props = load_props(model)
+    props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "8.0" if model == "area" else "2.5"
+    kind = MODELS[model]
+    area, dist, prog = oracle_props(props)
+    sim = ob.Sim(kind, ob.TRIGGER_EXIT_ONLY, 111)
+    sim.set_area(area) if model == "area" else sim.set_dist(dist)
+    sim.set_prog(prog)
+    sim.set_location_types(city.type_infect_sub, city.type_correction)
+    sim.set_locations(city.loc_type, city.loc_nsub, city.loc_area)
+    sim.set_persons(city.age, city.female)
+    eng = hb.HerosEngine(kind, 111, flags=_lib.FLAG_EXACT_STATS)
+    city.install(eng)
+    if model == "area":
+        eng.set_transmission_area(properties.area_params(props))
+    else:
+        eng.set_transmission_distance(properties.dist_params(props))
+    eng.set_progression(properties.prog_params(props))
+    seeds = np.arange(0, city.n_persons, 40, dtype=np.int32)
+    sim.expose(seeds, np.zeros(len(seeds)))
+    eng.expose(seeds, np.zeros(len(seeds)))
+    gen = scenario.ScheduleGenerator(city, 111)
+    in_bad_work = 0
+    evaluations = 0
+    for d in range(9):
+        st = gen.generate_day(eng.agent_state()["phase"])
+        in_bad_work += int((city.loc_area[st["loc"]] < 0).sum())
+        sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        eng.submit_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        sim.run(24.0 * (d + 1))
+        evaluations += eng.step(24.0 * (d + 1))["evaluations"]
+        np.testing.assert_array_equal(eng.phase_counts(), sim.phase_counts())
+    assert in_bad_work > 1000                                   # people did work in the area = -1 workplaces
+    gi, oi = sort_events(eng.infections()), sort_events(sim.infections())
+    assert len(oi["person"]) > 150
+    for k in ("person", "loc", "sub", "time"):
+        np.testing.assert_array_equal(gi[k], oi[k])
+    np.testing.assert_allclose(gi["p"], oi["p"], rtol=1e-12, atol=4.5e-16)
+    assert not (city.loc_area[oi["loc"]] < 0).any()             # nobody was infected in a negative-area workplace
+    assert evaluations == sim.n_evaluations()
+    gt, ot = sort_events(eng.transitions()), sort_events(sim.transitions())
+    for k in ("person", "phase", "time"):
+        np.testing.assert_array_equal(gt[k], ot[k])
+    eng.close()
