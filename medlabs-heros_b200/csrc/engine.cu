@@ -821,9 +821,9 @@ int32_t window_transmit(heros_handle h)
     CU(h, h->item_person.ensure((size_t) n_total + 1)); CU(h, h->item_key.ensure((size_t) n_total + 1));
     CU(h, h->item_tab.ensure((size_t) n_total + 1)); CU(h, h->item_pair.ensure((size_t) n_total + 1));
     CU(h, h->tab_t.ensure(2 * (size_t) n_total + 1)); CU(h, h->tab_p.ensure(2 * (size_t) n_total + 1));
-    // global scratch of the sub-locations too large for shared memory: <= 112 B per stay + 172 KB per sub-location of
-    // > 4096 stays (<= 42 B per stay), and 8 B per stay of a total-branch location
-    CU(h, h->scratch.ensure(std::min<size_t>(168 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
+    // global scratch of the sub-locations too large for shared memory: <= 144 B per stay + 172 KB per sub-location of
+    // > 4096 stays (<= 42 B per stay), and 4 B per stay of a total-branch location
+    CU(h, h->scratch.ensure(std::min<size_t>(192 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
 
     BigLists big{};
     for (int k = 0; k < N_CLS; ++k) big.blk_seg[k] = h->blk_seg[k].p;

@@ -164,7 +164,7 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
     {
         unsigned long long mp = 64;
         while (mp < slots) mp <<= 1;
-        const unsigned long long bytes = (unsigned long long) slots * 56 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
+        const unsigned long long bytes = (unsigned long long) slots * 72 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
         const unsigned long long off = atomicAdd(&ctr->scratch_top, bytes);
         if (off + bytes <= b.scratch_cap) b.huge_off[slot] = off;
         else { b.blk_seg[cls][slot] = KEY_NONE; atomicOr(&ctr->overflow, 2u); }

@@ -176,6 +176,46 @@ HD double java_max(double a, double b)
     return a > b ? a : b;
 }
 
+// ---- order-independent summation: 128-bit fixed point (64 fraction bits below 2^-16, i.e. a resolution of 2^-80).
+// The exposure sum of an evaluation runs over the ill occupants of a sub-location, which the bucketing delivers in
+// ticket order (any order).  Instead of sorting them into a canonical order before every sum, the large sub-locations
+// add the terms as integers: exact, associative and commutative, so the sum does not depend on the order, the thread
+// layout or the sharding.  A term keeps all its 53 bits down to 2^-27 and is off by less than 2^-80 below that -- far
+// inside the 1e-12 relative tolerance of the probabilities.  Terms of 2^40 and more (or non-finite ones: NaN areas)
+// do not fit and are added to a plain double beside it (their result is +-inf / NaN whatever the order).
+struct ExactSum
+{
+    long long hi;           // units of 2^-16
+    unsigned long long lo;  // units of 2^-80
+    double loose;           // terms that do not fit the fixed-point range
+};
+HD ExactSum exact_zero() { return ExactSum{0, 0ull, 0.0}; }
+HD void exact_add(ExactSum& a, double t)
+{
+    if (!(t > -0x1p40 && t < 0x1p40)) { a.loose += t; return; }
+    const double s = t * 65536.0;  // exact
+#ifdef __CUDA_ARCH__
+    const double f = floor(s);
+#else
+    const double f = __builtin_floor(s);
+#endif
+    const unsigned long long lo = (unsigned long long) ((s - f) * 18446744073709551616.0);  // (s - f) in [0, 1), exact
+    const unsigned long long sum = a.lo + lo;
+    a.hi += (long long) f + (sum < lo ? 1 : 0);
+    a.lo = sum;
+}
+HD void exact_merge(ExactSum& a, long long hi, unsigned long long lo, double loose)
+{
+    const unsigned long long sum = a.lo + lo;
+    a.hi += hi + (sum < lo ? 1 : 0);
+    a.lo = sum;
+    a.loose += loose;
+}
+HD double exact_value(const ExactSum& a)
+{
+    return ((double) a.hi * 0x1.0p-16 + (double) a.lo * 0x1.0p-80) + a.loose;
+}
+
 // ---- model parameters (already converted to hours, Covid19TransmissionArea.java:63-68 / Distance:59-68) ----------
 struct AreaParams { double contagiousness, beta, t_e_min, t_e_mode, t_e_max, threshold; };
 struct DistParams { double L, I, C, v_max, v_0, r, psi, alpha, mu, threshold; };

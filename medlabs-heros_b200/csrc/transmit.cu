@@ -503,18 +503,17 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 
 // per class: group size, groups per block, capacity in events and in kept probabilities
 template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512, ILL_CAP = 64; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP3, P_CAP = BLOCK_P_CAP, NB_CAP = 2048, ILL_CAP = 256; using idx_t = uint16_t; };
-template <> struct GroupCfg<4> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536, ILL_CAP = 0; using idx_t = uint32_t; };
+template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512; using idx_t = uint16_t; };
+template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048; using idx_t = uint16_t; };
+template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
+template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP3, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
+template <> struct GroupCfg<4> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536; using idx_t = uint32_t; };
 
-// bytes of scratch of one group: 32 per staged ill stay + 17 per event + 8 per kept probability + 12 per bucket
-// (budgeted 16; + slack)
+// bytes of scratch of one group: 17 per event + 24 per kept evaluation (probability + fixed-point exposure sum) + 12
+// per bucket (budgeted 16; + slack)
 template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
 {
-    return (size_t) GroupCfg<CLS>::ILL_CAP * 32 + (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 8 +
-           (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
+    return (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 24 + (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
 }
 
 }  // namespace
@@ -627,13 +626,15 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         const double scale = (double) NB / (c.T1 - c.T0);
         auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
-        // scratch: ill_rec StayRec[ILL_CAP] | ev_t f64[slots] | pr f64[P_CAP or slots] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
-        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]
+        // scratch: acc_hi u64[P] | acc_lo u64[P] | ev_t f64[slots] | pr f64[P] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
+        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]      (P = P_CAP or slots)
         unsigned char* base = CLS == CLS_HUGE ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
-        StayRec* ill_rec = (StayRec*) base;  // the ill stays, staged next to the SM (classes 0-2)
-        double* ev_t = (double*) (base + (size_t) Cfg::ILL_CAP * sizeof(StayRec));
+        const size_t P = CLS == CLS_HUGE ? (size_t) slots : (size_t) Cfg::P_CAP;
+        unsigned long long* acc_hi = (unsigned long long*) base;  // fixed-point exposure sum of every evaluation (ExactSum)
+        unsigned long long* acc_lo = acc_hi + P;
+        double* ev_t = (double*) (acc_lo + P);
         double* pr = ev_t + slots;
-        uint32_t* bstart = (uint32_t*) (pr + (CLS == CLS_HUGE ? slots : Cfg::P_CAP));
+        uint32_t* bstart = (uint32_t*) (pr + P);
         int32_t* bcur = (int32_t*) (bstart + NB + 1);
         int32_t* bsign = bcur + NB;
         idx_t* ja = (idx_t*) (bsign + NB);
@@ -802,87 +803,146 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         for (int v = tid; v < n; v += G)
             if (phase_is_ill(view_tphase(rec[v].view))) jb[ja[v]] = (idx_t) v;
         gsync<G>();
-        // ... in canonical (person, t_in) order, by rank counting, so that the exposure sums do not depend on the order
-        // in which the stays were scattered into the bucket.  When they fit, the ill stays are staged in shared memory:
-        // every evaluation below scans all of them.
-        const bool staged = n_ill <= Cfg::ILL_CAP;
-        if (staged)
-        {
-            for (int k = tid; k < n_ill; k += G) ill_rec[k] = rec[jb[k]];
-            gsync<G>();
-        }
-        const StayRec* ill_src = staged ? ill_rec : rec;
-        for (int k = tid; k < n_ill; k += G)
-        {
-            const int v = staged ? k : (int) jb[k];
-            const uint32_t pv = ill_src[v].person;
-            const double tv = ill_src[v].tin;
-            int rank = 0;
-            for (int k2 = 0; k2 < n_ill; ++k2)
-            {
-                const int v2 = staged ? k2 : (int) jb[k2];
-                const uint32_t p2 = ill_src[v2].person;
-                const double t2 = ill_src[v2].tin;
-                rank += (stay_before(p2, t2, pv, tv) || (p2 == pv && t2 == tv && k2 < k)) ? 1 : 0;
-            }
-            illl[rank] = (idx_t) v;
-        }
-        gsync<G>();
         PHASE_CLOCK(7);
-        // 7. duration, exposure sum and probability of every evaluation: the fixed part (sqrt, exp, divisions) is a long
-        //    dependent fp64 chain, so evaluations run in as many threads as possible; when the group has more threads
-        //    than evaluations, LPN = 2^k lanes share one evaluation and split the ill stays between them (lane partial
-        //    sums in canonical order, combined by a fixed butterfly).
+        // 7. duration, exposure sum and probability of every evaluation.
+        //    a) the factor of every evaluation (head count, sqrt, exp: a long dependent fp64 chain, one per thread);
+        //    b) the exposure sums, PAIR by pair: every ill stay finds the run of evaluations it was present at, the warp
+        //       deals out the (ill stay, evaluation) pairs evenly and every lane adds its term to the evaluation's
+        //       fixed-point sum (ExactSum) with integer atomics -- exact, so the order in which the terms arrive does
+        //       not matter, and no lane idles while another one works through a term;
+        //    c) the probability of every evaluation.
+        for (int r = tid; r < R; r += G)
         {
-            int lpn = 1;
-            while (lpn < 32 && 2 * lpn * R <= G) lpn <<= 1;
-            const int sub = tid & (lpn - 1), per_pass = G / lpn;
-            for (int r0 = 0; r0 < R; r0 += per_pass)
+            const double now = ev_t[node[r]];
+            double factor;
+            if (MODEL == HEROS_MODEL_AREA)
+                factor = area_factor(c.area, now - (r ? ev_t[node[r - 1]] : L0), lp.denom);
+            else
             {
-                const int r = r0 + tid / lpn;
-                const bool active = r < R;
-                double p = 0.0, factor = 0.0, sum = 0.0, now = 0.0, duration = 0.0;
-                if (active)
+                // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
+                const int bk = bucket_of(now);
+                int head_count = carried + bcur[bk];
+                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
+                    head_count += ev_k[j] ? 1 : -1;
+                double psi, mu;
+                policy_at(c, now, psi, mu);
+                factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
+            }
+            pr[r] = factor;
+            acc_hi[r] = 0ull;
+            acc_lo[r] = 0ull;
+        }
+        if (tid == 0) s_w[32] = 0;  // set when a term does not fit the fixed-point range (non-finite areas)
+        gsync<G>();
+        for (int k0 = tid & ~31; k0 < n_ill; k0 += G)
+        {
+            const int lane = tid & 31;
+            const int k = k0 + lane;
+            StayRec s;
+            s.tin = 0.0; s.tout = 0.0; s.view = 0; s.person = 0; s.pad = 0;
+            int lo = 0, cnt = 0;
+            if (k < n_ill)
+            {
+                s = rec[jb[k]];
+                int l = 0, h = R;  // first evaluation with time > t_in
+                while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
+                lo = l;
+                h = R;             // first evaluation with time > t_out
+                while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
+                cnt = l - lo;
+            }
+            int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            for (int p0 = 0; p0 < total; p0 += 32)
+            {
+                const int pi = p0 + lane;
+                int src = 0;  // first lane whose inclusive prefix exceeds pi
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
                 {
-                    now = ev_t[node[r]];
-                    duration = now - (r ? ev_t[node[r - 1]] : L0);
-                    if (MODEL == HEROS_MODEL_AREA)
-                        factor = area_factor(c.area, duration, lp.denom);
-                    else
+                    const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
+                    if (probe <= pi) src += step;
+                }
+                src = min(src, 31);
+                const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
+                const int s_lo = __shfl_sync(FULL, lo, src);
+                StayRec q;
+                q.tin = 0.0;
+                q.tout = __shfl_sync(FULL, s.tout, src);
+                q.view = __shfl_sync(FULL, s.view, src);
+                q.person = __shfl_sync(FULL, s.person, src);
+                q.pad = __shfl_sync(FULL, s.pad, src);
+                if (pi < total)
+                {
+                    const int r = s_lo + (pi - (s_incl - s_cnt));
+                    const double now = ev_t[node[r]];
+                    const double factor = pr[r];
+                    if (factor != 0.0 && ill_at(c, q, now))  // present by construction: t_in < now <= t_out
                     {
-                        // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
-                        const int bk = bucket_of(now);
-                        int head_count = carried + bcur[bk];
-                        for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
-                            head_count += ev_k[j] ? 1 : -1;
-                        double psi, mu;
-                        policy_at(c, now, psi, mu);
-                        factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
-                    }
-                    if (factor != 0.0)
-                        for (int k = sub; k < n_ill; k += lpn)
+                        const double te = now - (double) view_exposure(q.view);
+                        double term = 0.0;
+                        if (MODEL == HEROS_MODEL_AREA)
+                            term = area_contribution(c.area, te);
+                        else
                         {
-                            const StayRec& s = ill_src[illl[k]];
-                            if (s.tin < now && now <= s.tout && ill_at(c, s, now))
+                            const double v_t = dist_viral_load(c.dist, te);
+                            if (v_t > 0) term = dist_term(c.dist, factor, now - (r ? ev_t[node[r - 1]] : L0), v_t);
+                        }
+                        if (term != 0.0)
+                        {
+                            ExactSum one = exact_zero();
+                            exact_add(one, term);
+                            if (one.loose != 0.0 || one.loose != one.loose) s_w[32] = 1;
+                            else
                             {
-                                const double te = now - (double) view_exposure(s.view);
-                                if (MODEL == HEROS_MODEL_AREA)
-                                    sum += area_contribution(c.area, te);
-                                else
-                                {
-                                    const double v_t = dist_viral_load(c.dist, te);
-                                    if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
-                                }
+                                const unsigned long long old = atomicAdd(&acc_lo[r], one.lo);
+                                atomicAdd(&acc_hi[r], (unsigned long long) one.hi + ((old + one.lo < old) ? 1ull : 0ull));
                             }
                         }
-                }
-                for (int o = lpn >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-                if (active && sub == 0)
-                {
-                    if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
-                    pr[r] = p;
+                    }
                 }
             }
+        }
+        gsync<G>();
+        const bool loose = s_w[32] != 0;
+        for (int r = tid; r < R; r += G)
+        {
+            const double factor = pr[r];
+            double sum;
+            if (!loose)
+                sum = exact_value(ExactSum{(long long) acc_hi[r], acc_lo[r], 0.0});
+            else
+            {
+                // a term outside the fixed-point range (NaN / infinite areas): plain doubles; the result is +-inf or
+                // NaN whatever the order
+                const double now = ev_t[node[r]], duration = now - (r ? ev_t[node[r - 1]] : L0);
+                sum = 0.0;
+                if (factor != 0.0)
+                    for (int k = 0; k < n_ill; ++k)
+                    {
+                        const StayRec& q = rec[jb[k]];
+                        if (q.tin < now && now <= q.tout && ill_at(c, q, now))
+                        {
+                            const double te = now - (double) view_exposure(q.view);
+                            if (MODEL == HEROS_MODEL_AREA)
+                                sum += area_contribution(c.area, te);
+                            else
+                            {
+                                const double v_t = dist_viral_load(c.dist, te);
+                                if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
+                            }
+                        }
+                    }
+            }
+            double p = 0.0;
+            if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
+            pr[r] = p;
         }
         gsync<G>();
         if (dbg && tid == 0)
@@ -981,8 +1041,8 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
 // persons of ALL sub-locations of the location (location.getAllPersonIds()) with the un-divided area, the formulas of
 // that branch (sign and shape quirks included) and, in the distance model, the head count of the sub-location.
 // The stays of a location are contiguous in bucket order (its keys are consecutive).  This is a rarely taken path (no
-// location of the shipped data takes it), written for exactness rather than speed: sums are formed in canonical
-// (person, t_in) order, thread t adds elements t, t + 256, ... and the partial sums are combined in a fixed tree.
+// location of the shipped data takes it), written for exactness rather than speed; the sums are formed in fixed point
+// (ExactSum), so they do not depend on the order of the stays.
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -997,6 +1057,25 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* s_red)
         __syncthreads();
     }
     return s_red[0];
+}
+
+// order-independent sum of the threads' fixed-point partial sums
+__device__ __forceinline__ double block_sum_exact(ExactSum v, long long* s_hi, unsigned long long* s_lo, double* s_loose)
+{
+    __syncthreads();
+    s_hi[threadIdx.x] = v.hi; s_lo[threadIdx.x] = v.lo; s_loose[threadIdx.x] = v.loose;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if ((int) threadIdx.x < o)
+        {
+            ExactSum a{s_hi[threadIdx.x], s_lo[threadIdx.x], s_loose[threadIdx.x]};
+            exact_merge(a, s_hi[threadIdx.x + o], s_lo[threadIdx.x + o], s_loose[threadIdx.x + o]);
+            s_hi[threadIdx.x] = a.hi; s_lo[threadIdx.x] = a.lo; s_loose[threadIdx.x] = a.loose;
+        }
+        __syncthreads();
+    }
+    return exact_value(ExactSum{s_hi[0], s_lo[0], s_loose[0]});
 }
 
 __device__ __forceinline__ double block_min_time(double v, double* s_red)
@@ -1018,6 +1097,8 @@ template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
 {
     __shared__ double s_red[256];
+    __shared__ long long s_hi[256];
+    __shared__ unsigned long long s_lo[256];
     __shared__ unsigned long long s_off;
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
@@ -1030,32 +1111,18 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
         const uint32_t n_all = a1 - a0;
         if (n_all == 0) continue;
         const StayRec* all = c.rec + a0;
-        // canonical order of the location's stays: order[rank] = index (rank counting, in global scratch)
+        // the sub-location key of every stay of the location (global scratch)
         if (tid == 0)
         {
-            const unsigned long long off = atomicAdd(&c.ctr->scratch_top, (unsigned long long) n_all * 8 + 16);
-            s_off = off + (unsigned long long) n_all * 8 + 16 <= c.scratch_cap ? off : ~0ull;
+            const unsigned long long off = atomicAdd(&c.ctr->scratch_top, (unsigned long long) n_all * 4 + 16);
+            s_off = off + (unsigned long long) n_all * 4 + 16 <= c.scratch_cap ? off : ~0ull;
             if (s_off == ~0ull) atomicOr(&c.ctr->overflow, 2u);
         }
         __syncthreads();
         if (s_off == ~0ull) continue;
-        uint32_t* order = reinterpret_cast<uint32_t*>(c.scratch + ((s_off + 15) & ~15ull));
-        uint32_t* skey = order + n_all;  // sub-location key of every stay of the location
+        uint32_t* skey = reinterpret_cast<uint32_t*>(c.scratch + ((s_off + 15) & ~15ull));
         for (uint32_t key = L.first_key; key < L.end_key; ++key)
             for (uint32_t i = c.seg_start[key] - a0 + tid; i < c.seg_start[key + 1] - a0; i += 256) skey[i] = key;
-        for (uint32_t i = tid; i < n_all; i += 256)
-        {
-            const uint32_t pi = all[i].person;
-            const double ti = all[i].tin;
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n_all; ++j)
-            {
-                const uint32_t pj = all[j].person;
-                const double tj = all[j].tin;
-                rank += (stay_before(pj, tj, pi, ti) || (pj == pi && tj == ti && j < i)) ? 1u : 0u;
-            }
-            order[rank] = i;
-        }
         __syncthreads();
         for (uint32_t key = L.first_key; key < L.end_key; ++key)
         {
@@ -1108,23 +1175,23 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
                     factor = dist_factor(c.dist, psi, mu, L.area_total, head_count);  // TDist:196-201
                 }
                 if (factor == 0.0) continue;
-                double part = 0.0;
+                ExactSum part = exact_zero();  // order-independent: the stays are in ticket order
                 for (uint32_t r = tid; r < n_all; r += 256)  // every person of the location (TArea:211 / TDist:207)
                 {
-                    const StayRec q = all[order[r]];
-                    if (present(q, skey[order[r]]) && ill_at(c, q, now))
+                    const StayRec q = all[r];
+                    if (present(q, skey[r]) && ill_at(c, q, now))
                     {
                         const double te = now - (double) view_exposure(q.view);
                         if (MODEL == HEROS_MODEL_AREA)
-                            part += area_contribution_total(c.area, te);  // TArea:216-221
+                            exact_add(part, area_contribution_total(c.area, te));  // TArea:216-221
                         else
                         {
                             const double v_t = dist_viral_load(c.dist, te);
-                            if (v_t > 0) part += dist_term(c.dist, factor, duration, v_t);
+                            if (v_t > 0) exact_add(part, dist_term(c.dist, factor, duration, v_t));
                         }
                     }
                 }
-                const double sum = block_sum_fixed(part, s_red);
+                const double sum = block_sum_exact(part, s_hi, s_lo, s_red);
                 double p;
                 if (!probability<MODEL>(factor, sum, p) || !(p > 0)) continue;  // p = 1 - exp(+factor * sum) in the area model
                 for (uint32_t i = tid; i < n_all; i += 256)
