@@ -310,10 +310,14 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
     uint32_t v[SCAN_ITEMS], local = 0;
     if (base + SCAN_ITEMS <= n)
     {
-        const uint4 lo = *reinterpret_cast<const uint4*>(count + base), hi = *reinterpret_cast<const uint4*>(count + base + 4);
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-        *reinterpret_cast<uint4*>(count + base) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(count + base + 4) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+        {
+            const uint4 w = *reinterpret_cast<const uint4*>(count + base + 4 * q);
+            v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+        }
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) *reinterpret_cast<uint4*>(count + base + 4 * q) = make_uint4(0, 0, 0, 0);
     }
     else
     {

@@ -29,6 +29,7 @@ namespace heros {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int PAIR_MIN_ILL = 48;    // more ill stays than this in a sub-location: exposure sums pair by pair
 constexpr int THREAD_SLOW_MAX = 8;  // largest segment handled by 8 lanes (four per warp) in k_transmit_sub
 
 __device__ __forceinline__ double pos_inf() { return bits_f64(0x7ff0000000000000ull); }
@@ -811,138 +812,196 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         //       fixed-point sum (ExactSum) with integer atomics -- exact, so the order in which the terms arrive does
         //       not matter, and no lane idles while another one works through a term;
         //    c) the probability of every evaluation.
-        for (int r = tid; r < R; r += G)
+        if (n_ill <= PAIR_MIN_ILL)
         {
-            const double now = ev_t[node[r]];
-            double factor;
-            if (MODEL == HEROS_MODEL_AREA)
-                factor = area_factor(c.area, now - (r ? ev_t[node[r - 1]] : L0), lp.denom);
-            else
+            // few ill stays (the usual case while the prevalence is low): one evaluation per thread -- or 2^k lanes per
+            // evaluation when threads outnumber evaluations -- walking the short list of ill stays
+            int lpn = 1;
+            while (lpn < 32 && 2 * lpn * R <= G) lpn <<= 1;
+            const int sub = tid & (lpn - 1), per_pass = G / lpn;
+            for (int r0 = 0; r0 < R; r0 += per_pass)
             {
-                // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
-                const int bk = bucket_of(now);
-                int head_count = carried + bcur[bk];
-                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
-                    head_count += ev_k[j] ? 1 : -1;
-                double psi, mu;
-                policy_at(c, now, psi, mu);
-                factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
-            }
-            pr[r] = factor;
-            acc_hi[r] = 0ull;
-            acc_lo[r] = 0ull;
-        }
-        if (tid == 0) s_w[32] = 0;  // set when a term does not fit the fixed-point range (non-finite areas)
-        gsync<G>();
-        for (int k0 = tid & ~31; k0 < n_ill; k0 += G)
-        {
-            const int lane = tid & 31;
-            const int k = k0 + lane;
-            StayRec s;
-            s.tin = 0.0; s.tout = 0.0; s.view = 0; s.person = 0; s.pad = 0;
-            int lo = 0, cnt = 0;
-            if (k < n_ill)
-            {
-                s = rec[jb[k]];
-                int l = 0, h = R;  // first evaluation with time > t_in
-                while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
-                lo = l;
-                h = R;             // first evaluation with time > t_out
-                while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
-                cnt = l - lo;
-            }
-            int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            for (int p0 = 0; p0 < total; p0 += 32)
-            {
-                const int pi = p0 + lane;
-                int src = 0;  // first lane whose inclusive prefix exceeds pi
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1)
+                const int r = r0 + tid / lpn;
+                const bool active = r < R;
+                double p = 0.0, factor = 0.0, now = 0.0, duration = 0.0;
+                ExactSum acc = exact_zero();
+                if (active)
                 {
-                    const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
-                    if (probe <= pi) src += step;
-                }
-                src = min(src, 31);
-                const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
-                const int s_lo = __shfl_sync(FULL, lo, src);
-                StayRec q;
-                q.tin = 0.0;
-                q.tout = __shfl_sync(FULL, s.tout, src);
-                q.view = __shfl_sync(FULL, s.view, src);
-                q.person = __shfl_sync(FULL, s.person, src);
-                q.pad = __shfl_sync(FULL, s.pad, src);
-                if (pi < total)
-                {
-                    const int r = s_lo + (pi - (s_incl - s_cnt));
-                    const double now = ev_t[node[r]];
-                    const double factor = pr[r];
-                    if (factor != 0.0 && ill_at(c, q, now))  // present by construction: t_in < now <= t_out
+                    now = ev_t[node[r]];
+                    duration = now - (r ? ev_t[node[r - 1]] : L0);
+                    if (MODEL == HEROS_MODEL_AREA)
+                        factor = area_factor(c.area, duration, lp.denom);
+                    else
                     {
-                        const double te = now - (double) view_exposure(q.view);
-                        double term = 0.0;
-                        if (MODEL == HEROS_MODEL_AREA)
-                            term = area_contribution(c.area, te);
-                        else
+                        const int bk = bucket_of(now);
+                        int head_count = carried + bcur[bk];
+                        for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
+                            head_count += ev_k[j] ? 1 : -1;
+                        double psi, mu;
+                        policy_at(c, now, psi, mu);
+                        factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
+                    }
+                    if (factor != 0.0)
+                        for (int k = sub; k < n_ill; k += lpn)
                         {
-                            const double v_t = dist_viral_load(c.dist, te);
-                            if (v_t > 0) term = dist_term(c.dist, factor, now - (r ? ev_t[node[r - 1]] : L0), v_t);
-                        }
-                        if (term != 0.0)
-                        {
-                            ExactSum one = exact_zero();
-                            exact_add(one, term);
-                            if (one.loose != 0.0 || one.loose != one.loose) s_w[32] = 1;
-                            else
+                            const StayRec& s = rec[jb[k]];
+                            if (s.tin < now && now <= s.tout && ill_at(c, s, now))
                             {
-                                const unsigned long long old = atomicAdd(&acc_lo[r], one.lo);
-                                atomicAdd(&acc_hi[r], (unsigned long long) one.hi + ((old + one.lo < old) ? 1ull : 0ull));
+                                const double te = now - (double) view_exposure(s.view);
+                                if (MODEL == HEROS_MODEL_AREA)
+                                    exact_add(acc, area_contribution(c.area, te));
+                                else
+                                {
+                                    const double v_t = dist_viral_load(c.dist, te);
+                                    if (v_t > 0) exact_add(acc, dist_term(c.dist, factor, duration, v_t));
+                                }
                             }
                         }
-                    }
+                }
+                for (int o = lpn >> 1; o > 0; o >>= 1)
+                    exact_merge(acc, __shfl_xor_sync(FULL, acc.hi, o), __shfl_xor_sync(FULL, acc.lo, o), __shfl_xor_sync(FULL, acc.loose, o));
+                if (active && sub == 0)
+                {
+                    if (!(factor != 0.0 && probability<MODEL>(factor, exact_value(acc), p) && p > 0)) p = 0.0;
+                    pr[r] = p;
                 }
             }
         }
-        gsync<G>();
-        const bool loose = s_w[32] != 0;
-        for (int r = tid; r < R; r += G)
+        else
         {
-            const double factor = pr[r];
-            double sum;
-            if (!loose)
-                sum = exact_value(ExactSum{(long long) acc_hi[r], acc_lo[r], 0.0});
-            else
+            for (int r = tid; r < R; r += G)
             {
-                // a term outside the fixed-point range (NaN / infinite areas): plain doubles; the result is +-inf or
-                // NaN whatever the order
-                const double now = ev_t[node[r]], duration = now - (r ? ev_t[node[r - 1]] : L0);
-                sum = 0.0;
-                if (factor != 0.0)
-                    for (int k = 0; k < n_ill; ++k)
+                const double now = ev_t[node[r]];
+                double factor;
+                if (MODEL == HEROS_MODEL_AREA)
+                    factor = area_factor(c.area, now - (r ? ev_t[node[r - 1]] : L0), lp.denom);
+                else
+                {
+                    // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
+                    const int bk = bucket_of(now);
+                    int head_count = carried + bcur[bk];
+                    for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
+                        head_count += ev_k[j] ? 1 : -1;
+                    double psi, mu;
+                    policy_at(c, now, psi, mu);
+                    factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
+                }
+                pr[r] = factor;
+                acc_hi[r] = 0ull;
+                acc_lo[r] = 0ull;
+            }
+            if (tid == 0) s_w[32] = 0;  // set when a term does not fit the fixed-point range (non-finite areas)
+            gsync<G>();
+            for (int k0 = tid & ~31; k0 < n_ill; k0 += G)
+            {
+                const int lane = tid & 31;
+                const int k = k0 + lane;
+                StayRec s;
+                s.tin = 0.0; s.tout = 0.0; s.view = 0; s.person = 0; s.pad = 0;
+                int lo = 0, cnt = 0;
+                if (k < n_ill)
+                {
+                    s = rec[jb[k]];
+                    int l = 0, h = R;  // first evaluation with time > t_in
+                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
+                    lo = l;
+                    h = R;             // first evaluation with time > t_out
+                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
+                    cnt = l - lo;
+                }
+                int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                for (int p0 = 0; p0 < total; p0 += 32)
+                {
+                    const int pi = p0 + lane;
+                    int src = 0;  // first lane whose inclusive prefix exceeds pi
+    #pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
                     {
-                        const StayRec& q = rec[jb[k]];
-                        if (q.tin < now && now <= q.tout && ill_at(c, q, now))
+                        const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
+                        if (probe <= pi) src += step;
+                    }
+                    src = min(src, 31);
+                    const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
+                    const int s_lo = __shfl_sync(FULL, lo, src);
+                    StayRec q;
+                    q.tin = 0.0;
+                    q.tout = __shfl_sync(FULL, s.tout, src);
+                    q.view = __shfl_sync(FULL, s.view, src);
+                    q.person = __shfl_sync(FULL, s.person, src);
+                    q.pad = __shfl_sync(FULL, s.pad, src);
+                    if (pi < total)
+                    {
+                        const int r = s_lo + (pi - (s_incl - s_cnt));
+                        const double now = ev_t[node[r]];
+                        const double factor = pr[r];
+                        if (factor != 0.0 && ill_at(c, q, now))  // present by construction: t_in < now <= t_out
                         {
                             const double te = now - (double) view_exposure(q.view);
+                            double term = 0.0;
                             if (MODEL == HEROS_MODEL_AREA)
-                                sum += area_contribution(c.area, te);
+                                term = area_contribution(c.area, te);
                             else
                             {
                                 const double v_t = dist_viral_load(c.dist, te);
-                                if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
+                                if (v_t > 0) term = dist_term(c.dist, factor, now - (r ? ev_t[node[r - 1]] : L0), v_t);
+                            }
+                            if (term != 0.0)
+                            {
+                                ExactSum one = exact_zero();
+                                exact_add(one, term);
+                                if (one.loose != 0.0 || one.loose != one.loose) s_w[32] = 1;
+                                else
+                                {
+                                    const unsigned long long old = atomicAdd(&acc_lo[r], one.lo);
+                                    atomicAdd(&acc_hi[r], (unsigned long long) one.hi + ((old + one.lo < old) ? 1ull : 0ull));
+                                }
                             }
                         }
                     }
+                }
             }
-            double p = 0.0;
-            if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
-            pr[r] = p;
+            gsync<G>();
+            const bool loose = s_w[32] != 0;
+            for (int r = tid; r < R; r += G)
+            {
+                const double factor = pr[r];
+                double sum;
+                if (!loose)
+                    sum = exact_value(ExactSum{(long long) acc_hi[r], acc_lo[r], 0.0});
+                else
+                {
+                    // a term outside the fixed-point range (NaN / infinite areas): plain doubles; the result is +-inf or
+                    // NaN whatever the order
+                    const double now = ev_t[node[r]], duration = now - (r ? ev_t[node[r - 1]] : L0);
+                    sum = 0.0;
+                    if (factor != 0.0)
+                        for (int k = 0; k < n_ill; ++k)
+                        {
+                            const StayRec& q = rec[jb[k]];
+                            if (q.tin < now && now <= q.tout && ill_at(c, q, now))
+                            {
+                                const double te = now - (double) view_exposure(q.view);
+                                if (MODEL == HEROS_MODEL_AREA)
+                                    sum += area_contribution(c.area, te);
+                                else
+                                {
+                                    const double v_t = dist_viral_load(c.dist, te);
+                                    if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
+                                }
+                            }
+                        }
+                }
+                double p = 0.0;
+                if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
+                pr[r] = p;
+            }
         }
         gsync<G>();
         if (dbg && tid == 0)
