@@ -266,7 +266,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
+        # keep NCCL's banner / debug lines out of stdout (one JSON line only), whatever NCCL_DEBUG the launcher set
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/heros_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     props = load_props(args.model)
