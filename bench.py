@@ -215,7 +215,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "infections": int(sim.phase_counts()[1:].sum()),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, city, world, n_commuters):
@@ -561,16 +561,33 @@ def run_ours(args):
                                 "sample": f"first {cpu_days} simulated days of the same city and stays, "
                                           f"oracle/heros_oracle.c single-threaded ({t_cpu:.1f} s)",
                                 "infection_lists_identical": parity}
-    print(json.dumps(line), flush=True)
+    emit(line)
     shutdown()
 
 
 def main():
     args = parse_args()
+    # stdout carries ONE JSON line: while the bench runs, file descriptor 1 points to stderr, so that whatever a library
+    # prints from native code (NCCL's version banner, for one) cannot end up next to it; print() below restores it
+    sys.stdout.flush()
+    global _STDOUT_FD
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+_STDOUT_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the real stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
