@@ -1,16 +1,18 @@
-// engine.cu -- libheros_gpu.so: engine state, the window pipeline and the C ABI of include/heros_gpu.h.
+// engine.cu -- libheros_gpu.so: the engine object, the window pipeline and most of the C ABI of include/heros_gpu.h
+// (multi-GPU exchange: exchange.cu; device-side activity schedule: schedule.cu; transmission kernels: transmit.cu).
 //
-// One window [T0, T1) of simulated time is processed as
-//   1. k_progress        disease-phase state machine of every agent up to T1 (Covid19Progression.java:182-346),
-//                        remembering the phase transmission must see (the phase at T0) and when illness ends
-//   2. k_bucket_count    window list = pool of submitted stays + the open stay of every agent; every active stay takes a
-//                        ticket at its sub-location (replaces the per-location TIntSets the medlabs engine maintains on
-//                        every addPerson / removePerson)
-//   3. k_scan_*          bucket offsets = prefix sum over the dense sub-location keys
-//   4. k_bucket_scatter  stays + packed agent words into bucket order
-//   5. k_transmit_*      transmit.cu: every infectPeople evaluation of the window, Philox draws -> candidates
-//   6. k_resolve*        earliest successful draw per person wins; expose() the winners
-//   7. retire            stays that ended before T1 leave the pool
+// Stays arrive through k_submit (or k_advance_day), which takes every stay's ticket at its sub-location on arrival.
+// One window [T0, T1) of simulated time is then processed as
+//   1. k_window_open     disease-phase state machine of every agent up to T1 (Covid19Progression.java:182-346),
+//                        remembering the phase transmission must see (the phase at T0) and when illness ends; tickets
+//                        of the open stay of every agent and of the stays carried over from earlier windows (replaces
+//                        the per-location TIntSets the medlabs engine maintains on every addPerson / removePerson)
+//   2. k_scan_lookback   bucket offsets = prefix sum over the dense sub-location keys, single pass; files the
+//                        sub-locations of > 32 stays into the work lists of the group kernels
+//   3. k_bucket_scatter  stays + packed agent words into bucket order; stays that outlive the window move to the other
+//                        pool buffer (retire)
+//   4. k_transmit_*      transmit.cu: every infectPeople evaluation of the window, Philox draws -> candidates
+//   5. k_resolve         earliest successful draw per person wins; expose() the winners
 #include "engine_state.cuh"
 
 #include <algorithm>
@@ -747,8 +749,6 @@ int32_t sync_counters(heros_handle h)
 int32_t current_counters(heros_handle h) { return h->ctr_current ? HEROS_OK : sync_counters(h); }
 
 
-int bit_length(uint32_t x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
-
 int32_t check_ready(heros_handle h)
 {
     if (!h) return HEROS_ERR_INVALID;
@@ -763,9 +763,10 @@ int32_t check_ready(heros_handle h)
 }
 
 // A window [T0, T1) runs in three phases so that a multi-GPU host can exchange stays and candidate infections between
-// them: begin (disease-phase state machine + tickets of the shard's own stays + retire; agent words final for the
-// window) -> [guests in] -> transmit (prefix sum, scatter, every evaluation; candidates out / in) -> finish (resolve).
-// heros_step runs the three back to back: 11 launches per window.
+// them: begin (disease-phase state machine + tickets of the open and carried-over stays; agent words final for the
+// window) -> [guests in] -> transmit (prefix sum, scatter + retire, every evaluation; candidates out / in) -> finish
+// (resolve).
+// heros_step runs the three back to back: 13 launches per window.
 int32_t window_begin(heros_handle h, double T1)
 {
     cudaStream_t s = h->stream;
@@ -782,7 +783,7 @@ int32_t window_begin(heros_handle h, double T1)
     { const int32_t rc_ = ensure_pool(h, oth, std::max<size_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
     CU(h, cudaEventRecord(h->ev[2], s));
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_cand, 0, sizeof(Counters) - offsetof(Counters, n_cand), s));
-    // 1. disease-phase state machine, tickets, retire
+    // 1. disease-phase state machine, tickets of open / carried-over stays
     const int pool_blocks = item_blocks(h->n_carried);
     k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur), h->n_carried,
                                                                (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p,

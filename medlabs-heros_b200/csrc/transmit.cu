@@ -17,10 +17,13 @@
 //                       evaluations together (REDUX), then every lane computes ONE evaluation of the chain -- the long
 //                       dependent fp64 chains (sqrt, exp) of up to 32 evaluations run side by side -- then lane = stay
 //                       for the draws
-//   k_transmit_group  : one warp or block per segment of > 32 stays: its events bucketed by time in shared memory, the
-//                       chain of calculated evaluations by successor search + pointer doubling, exposure sums per
-//                       evaluation, then per stay the (stay, evaluation) pairs with p > 0 go to the draw list
-//   k_draw            : the Philox draws of the draw list, spread evenly over the whole GPU
+//   k_transmit_group  : one block per segment of > 32 stays, five classes by its number of events (queued by the
+//                       prefix-sum kernel): events bucketed by time in shared memory, the chain of calculated
+//                       evaluations by successor search + pointer doubling, exposure sums in 128-bit fixed point
+//                       (order-independent; pair by pair with integer atomics when many occupants are ill), then one
+//                       draw item per susceptible stay = a run of the segment's table of evaluations with p > 0
+//   k_transmit_total  : one block per location of the total-location branch (TArea:198-246 / TDist:189-246)
+//   k_draw            : expands the draw items into Philox draws, spread evenly over the whole GPU
 // Output: candidate infections (person, key, time, p); engine.cu keeps the earliest per person.
 #include "engine.cuh"
 
@@ -628,7 +631,7 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
         // scratch: acc_hi u64[P] | acc_lo u64[P] | ev_t f64[slots] | pr f64[P] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
-        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | illl idx[n] | ev_k u8[slots]      (P = P_CAP or slots)
+        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | ev_k u8[slots]                    (P = P_CAP or slots)
         unsigned char* base = CLS == CLS_HUGE ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
         const size_t P = CLS == CLS_HUGE ? (size_t) slots : (size_t) Cfg::P_CAP;
         unsigned long long* acc_hi = (unsigned long long*) base;  // fixed-point exposure sum of every evaluation (ExactSum)
@@ -641,8 +644,7 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         idx_t* ja = (idx_t*) (bsign + NB);
         idx_t* jb = ja + (slots + 1);
         idx_t* node = jb + (slots + 1);
-        idx_t* illl = node + slots;
-        uint8_t* ev_k = (uint8_t*) (illl + n);
+        uint8_t* ev_k = (uint8_t*) (node + slots);
 
         // 1. histogram of the window's movement events over NB time buckets
         for (int i = tid; i <= NB; i += G) bstart[i] = 0;
