@@ -40,12 +40,21 @@ __device__ __forceinline__ double activity_duration(const Activity& a, double u)
     return a.mode;
 }
 
-// The day of one person.  EMIT = false only counts the stays that end; EMIT = true writes them to the pool from slot
-// `first` on (each with its ticket) and updates the open stay of the person.  Both passes make the same draws.
-template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
-                                             double* open_tin, const PoolArrays& P, uint32_t first, uint32_t pool_end,
-                                             uint32_t* count, Counters* ctr, int day, int day_type)
+// The stays that end today are collected per block in shared memory (the stays of 256 persons: about 1 100, at most
+// 256 x 16) and written to the pool together: one atomic per block reserves the slots, the writes are coalesced.
+constexpr int STAGE_CAP = 2560;
+struct StagedStays
+{
+    uint32_t person[STAGE_CAP], key[STAGE_CAP];
+    double tin[STAGE_CAP], tout[STAGE_CAP];
+    uint32_t n;         // staged so far (may exceed STAGE_CAP: the excess went straight to the pool)
+    uint32_t spilled;   // ... that many
+};
+
+// The day of one person: every stay that ends goes to the staging area, the open stay of the person is updated.
+__device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
+                                         double* open_tin, StagedStays& stage, const PoolArrays& P, uint32_t pool_base,
+                                         uint32_t pool_cap, uint32_t* count, Counters* ctr, int day, int day_type)
 {
     const uint64_t v = view[a];
     const uint32_t ph = view_phase(v), role = view_role(v);
@@ -55,25 +64,27 @@ __device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a
     if (cur_tin != cur_tin) cur_key = KEY_NONE;  // nobody in the slot
     const uint32_t key0 = cur_key;
     const double tin0 = cur_tin;
-    uint32_t n_e = 0;
     auto leave = [&](double t_leave) {  // the current stay ends
         if (cur_key != KEY_NONE && t_leave > cur_tin)
         {
-            if (EMIT)
+            const uint32_t j = atomicAdd(&stage.n, 1u);
+            if (j < (uint32_t) STAGE_CAP)
             {
-                const uint32_t slot = first + n_e;
-                if (slot < pool_end)
+                stage.person[j] = a; stage.key[j] = cur_key; stage.tin[j] = cur_tin; stage.tout[j] = t_leave;
+            }
+            else  // the staging area is full (cannot happen with <= 10 stays per person and day): straight to the pool
+            {
+                atomicAdd(&stage.spilled, 1u);
+                const uint32_t slot = (uint32_t) atomicAdd(&ctr->n_sched, 1ull);
+                if (slot < pool_cap)
                 {
-                    P.person[slot] = a;
-                    P.key[slot] = cur_key;
-                    P.tin[slot] = cur_tin;
-                    P.tout[slot] = t_leave;
-                    P.rank[slot] = atomicAdd(&count[cur_key], 1u);  // its ticket for the next window
+                    P.person[pool_base + slot] = a; P.key[pool_base + slot] = cur_key;
+                    P.tin[pool_base + slot] = cur_tin; P.tout[pool_base + slot] = t_leave;
+                    P.rank[pool_base + slot] = atomicAdd(&count[cur_key], 1u);
                 }
                 else
                     atomicOr(&ctr->overflow, 32u);
             }
-            ++n_e;
         }
     };
     int n_act = 0, start = 0;
@@ -162,12 +173,11 @@ __device__ __forceinline__ uint32_t walk_day(const ScheduleTables& S, uint32_t a
             if (!(t < t1)) break;
         }
     }
-    if (EMIT && (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0))))
+    if (cur_key != key0 || (cur_key != KEY_NONE && f64_bits(cur_tin) != f64_bits(tin0)))
     {
         open_key[a] = cur_key;
         open_tin[a] = cur_key != KEY_NONE ? cur_tin : bits_f64(OPEN_CLOSED);
     }
-    return n_e;
 }
 
 __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint32_t* order,
@@ -175,36 +185,31 @@ __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uin
                                                      PoolArrays P, uint32_t pool_base, uint32_t pool_cap, uint32_t* count,
                                                      Counters* ctr, int day, int day_type)
 {
-    __shared__ uint32_t s_w[TPB / 32];
+    extern __shared__ __align__(16) unsigned char smem[];
+    StagedStays& stage = *reinterpret_cast<StagedStays*>(smem);
     __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) { stage.n = 0; stage.spilled = 0; }
+    __syncthreads();
     // persons are visited grouped by social role: the threads of a warp then walk the same day pattern (the phase that
     // also selects it is Susceptible for most) instead of 32 different ones
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t a = slot < n_agents ? order[slot] : n_agents;
-    // pass 1: how many stays end today
-    const uint32_t n_e = a < n_agents ? walk_day<false>(S, a, view, open_key, open_tin, P, 0u, 0u, count, ctr, day, day_type) : 0u;
-    // room in the pool for the stays of the block: one atomic per block
-    uint32_t incl = n_e;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= (unsigned) o) incl += u;
-    }
-    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    if (slot < n_agents)
+        walk_day(S, order[slot], view, open_key, open_tin, stage, P, pool_base, pool_cap, count, ctr, day, day_type);
     __syncthreads();
-    uint32_t off = 0, total = 0;
-    for (int w = 0; w < TPB / 32; ++w)
-    {
-        if (w < (int) (threadIdx.x >> 5)) off += s_w[w];
-        total += s_w[w];
-    }
-    if (threadIdx.x == 0) s_base = total ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) total) : 0u;
+    const uint32_t n = min(stage.n, (uint32_t) STAGE_CAP);
+    if (threadIdx.x == 0) s_base = n ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) n) : 0u;
     __syncthreads();
-    // pass 2: the same day again, now writing the stays
-    if (a < n_agents)
-        walk_day<true>(S, a, view, open_key, open_tin, P, pool_base + s_base + off + incl - n_e, pool_base + pool_cap, count,
-                       ctr, day, day_type);
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x)
+    {
+        const uint32_t at = s_base + j;
+        if (at >= pool_cap) { atomicOr(&ctr->overflow, 32u); continue; }
+        const uint32_t key = stage.key[j];
+        P.person[pool_base + at] = stage.person[j];
+        P.key[pool_base + at] = key;
+        P.tin[pool_base + at] = stage.tin[j];
+        P.tout[pool_base + at] = stage.tout[j];
+        P.rank[pool_base + at] = atomicAdd(&count[key], 1u);  // its ticket for the next window
+    }
 }
 
 }  // namespace
@@ -301,7 +306,13 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
     S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
     static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));
-    k_advance_day<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
+    static bool configured[64] = {};
+    if (h->cfg.device >= 0 && h->cfg.device < 64 && !configured[h->cfg.device])
+    {
+        CU(h, cudaFuncSetAttribute(k_advance_day, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StagedStays)));
+        configured[h->cfg.device] = true;
+    }
+    k_advance_day<<<blocks_for(h->n_agents), TPB, sizeof(StagedStays), h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
                                                                   h->d_open_tin.p, pool_arrays(h, h->pool_cur), h->n_pool,
                                                                   (uint32_t) room, h->bk_count.p, h->d_ctr.p, day,
                                                                   DAY_TYPE[day % 7]);
