@@ -482,8 +482,7 @@ struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub;
 // opening of the next one (t_in differs) ends with the new stay in the slot.
 __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArrays P, uint32_t pool_base,
                                                 uint32_t* open_key, double* open_tin,
-                                                const uint32_t* __restrict__ loc_base,
-                                                const int16_t* __restrict__ loc_nsub, uint32_t n_loc, uint32_t n_agents,
+                                                const uint2* __restrict__ loc_key, uint32_t n_loc, uint32_t n_agents,
                                                 uint32_t person_base, int32_t loc_origin, double t_now, uint32_t* count,
                                                 Counters* ctr)
 {
@@ -512,8 +511,9 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
     {
         ok[k] = person[k] >= 0 && (uint32_t) person[k] < n_agents && loc[k] >= 0 && (uint32_t) loc[k] < n_loc &&
                 sub[k] >= 0 && tin[k] >= 0.0 && tin[k] < inf && tout[k] == tout[k];
-        nsub[k] = ok[k] ? (int) loc_nsub[loc[k]] : 0;
-        key[k] = ok[k] ? loc_base[loc[k]] : 0u;
+        const uint2 lk = ok[k] ? loc_key[loc[k]] : make_uint2(0u, 0u);  // first key and number of sub-locations: one load
+        nsub[k] = (int) lk.y;
+        key[k] = lk.x;
         cur_tin[k] = ok[k] ? open_tin[person[k]] : 0.0;  // the open stay this one may close
     }
     unsigned late = 0, invalid = 0;
@@ -1040,7 +1040,7 @@ int32_t heros_destroy(heros_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_policy.release(); h->d_prog.release(); h->d_loc_base.release(); h->d_key_loc.release();
     h->d_loc_nsub.release(); h->d_loc_param.release(); h->d_last_calc.release(); h->d_view.release();
-    h->d_key_total.release(); h->d_total_loc.release();
+    h->d_key_total.release(); h->d_total_loc.release(); h->d_loc_key.release();
     h->d_next_time.release(); h->d_ill_end.release(); h->d_open_tin.release(); h->d_best_t.release();
     h->d_best_key.release(); h->d_claim.release(); h->d_open_key.release();
     for (int i = 0; i < 2; ++i)
@@ -1136,6 +1136,13 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
     CU(h, cudaMemcpyAsync(h->d_loc_base.p, base.data(), ((size_t) n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_key_loc.p, key_loc.data(), (size_t) h->n_keys * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->d_loc_nsub.p, n_sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
+    {
+        std::vector<uint2> lk(n);
+        for (int i = 0; i < n; ++i) lk[i] = make_uint2(base[i], (uint32_t) (int32_t) n_sub[i]);
+        CU(h, h->d_loc_key.ensure(n));
+        CU(h, cudaMemcpyAsync(h->d_loc_key.p, lk.data(), (size_t) n * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
     CU(h, cudaMemcpyAsync(h->d_loc_param.p, lp.data(), (size_t) n * sizeof(LocParam), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->d_last_calc.p, 0, (size_t) h->n_keys * 8, h->stream));
     h->n_total_loc = (uint32_t) total.size();
@@ -1327,7 +1334,7 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     const PoolArrays P = pool_arrays(h, h->pool_cur);
     h->ctr_current = false;
     k_submit<<<item_blocks(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
-                                                   h->d_loc_base.p, h->d_loc_nsub.p, h->n_loc, h->n_agents,
+                                                   h->d_loc_key.p, h->n_loc, h->n_agents,
                                                    h->person_base, h->location_base, h->t_now, h->bk_count.p, h->d_ctr.p);
     CU(h, cudaGetLastError());
     h->n_pool += (uint32_t) n;

@@ -83,6 +83,7 @@ struct heros_engine
     std::vector<float> h_loc_area;
     DevBuf<uint32_t> d_loc_base, d_key_loc;
     DevBuf<int16_t> d_loc_nsub;
+    DevBuf<uint2> d_loc_key;  // {first key, number of sub-locations} of every location, for k_submit
     DevBuf<LocParam> d_loc_param;
     DevBuf<double> d_last_calc;
     DevBuf<uint8_t> d_key_total;     // total-branch locations (usually none)
