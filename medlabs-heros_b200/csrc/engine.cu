@@ -1588,28 +1588,27 @@ int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, i
     int32_t rc = current_counters(h);
     if (rc != HEROS_OK) return rc;
     const unsigned long long n = std::min<unsigned long long>(h->h_ctr->n_tr_log, h->tr_person.n);
+    if (n < h->o_tr_n || h->o_tr_n == ~0ull) { h->o_tr.clear(); h->o_tr_n = 0; }  // the log was reset
     if (n != h->o_tr_n)
     {
-        std::vector<uint32_t> per(n);
-        std::vector<uint8_t> ph(n);
-        std::vector<double> t(n);
-        if (n)
-        {
-            CU(h, cudaMemcpyAsync(per.data(), h->tr_person.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(ph.data(), h->tr_phase.p, n, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaMemcpyAsync(t.data(), h->tr_time.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
-            CU(h, cudaStreamSynchronize(h->stream));
-        }
-        std::vector<uint32_t> order(n);
-        std::iota(order.begin(), order.end(), 0u);
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return t[a] < t[b] || (t[a] == t[b] && per[a] < per[b]);
-        });
-        h->o_tr_person.resize(n); h->o_tr_phase.resize(n); h->o_tr_time.resize(n);
-        for (size_t i = 0; i < n; ++i)
-        {
-            h->o_tr_person[i] = per[order[i]]; h->o_tr_phase[i] = ph[order[i]]; h->o_tr_time[i] = t[order[i]];
-        }
+        // only what was logged since the last call is fetched, sorted and merged behind the older entries (the
+        // transitions of a later window are later, so the merge normally has nothing to move)
+        const size_t old = (size_t) h->o_tr_n, add = (size_t) (n - h->o_tr_n);
+        std::vector<uint32_t> per(add);
+        std::vector<uint8_t> ph(add);
+        std::vector<double> t(add);
+        CU(h, cudaMemcpyAsync(per.data(), h->tr_person.p + old, add * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(ph.data(), h->tr_phase.p + old, add, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(t.data(), h->tr_time.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->o_tr.resize(old + add);
+        for (size_t i = 0; i < add; ++i) h->o_tr[old + i] = heros_engine::TrEvent{t[i], per[i], ph[i]};
+        auto before = [](const heros_engine::TrEvent& x, const heros_engine::TrEvent& y) {
+            return x.t < y.t || (x.t == y.t && x.person < y.person);
+        };
+        std::sort(h->o_tr.begin() + old, h->o_tr.end(), before);
+        if (old && add && before(h->o_tr[old], h->o_tr[old - 1]))
+            std::inplace_merge(h->o_tr.begin(), h->o_tr.begin() + old, h->o_tr.end(), before);
         h->o_tr_n = n;
     }
     const int64_t avail = std::max<int64_t>(0, (int64_t) n - first);
@@ -1617,9 +1616,9 @@ int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, i
     for (int64_t i = 0; i < m; ++i)
     {
         const size_t k = (size_t) (first + i);
-        if (person) person[i] = (int32_t) h->o_tr_person[k];
-        if (phase) phase[i] = h->o_tr_phase[k];
-        if (time) time[i] = h->o_tr_time[k];
+        if (person) person[i] = (int32_t) h->o_tr[k].person;
+        if (phase) phase[i] = h->o_tr[k].phase;
+        if (time) time[i] = h->o_tr[k].t;
     }
     *n_out = avail;
     return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;

@@ -173,9 +173,8 @@ struct heros_engine
     // sorted output caches
     struct InfEvent { double t, p; uint64_t gkey; uint32_t person; };
     std::vector<InfEvent> o_inf;
-    std::vector<uint32_t> o_tr_person;
-    std::vector<double> o_tr_time;
-    std::vector<uint8_t> o_tr_phase;
+    struct TrEvent { double t; uint32_t person; uint8_t phase; };
+    std::vector<TrEvent> o_tr;
     unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;
 };
 

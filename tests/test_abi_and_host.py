@@ -172,3 +172,26 @@ def test_helsinki_location_fixture_is_the_reference_table():
     assert city.n_locations == 69508 and int(city.loc_nsub.sum()) == 431470
     assert (city.loc_area[tab["nsub"] == 0] == 0.0).all()          # totalArea = area * 0 (ConstructHerosModel.java:381)
     assert (city.home_sub < np.maximum(city.loc_nsub[city.home_loc], 1)).all()
+
+
+def test_compiled_schedule_tables_are_consistent():
+    """scenario.compile_schedule (what heros_set_schedule takes) against the activity rows it was compiled from."""
+    city = scenario.City(1500, seed=2)
+    pat = scenario.load_patterns()
+    t = scenario.compile_schedule(city, pat)
+    assert t["activities"].dtype.itemsize == C.sizeof(_lib.Activity) == 48
+    start, count = t["pattern_start"].reshape(8, 16, 4), t["pattern_count"].reshape(8, 16, 4)
+    assert count.max() <= 32 and (start + count <= len(t["activities"])).all()
+    rows = pat["patterns"]["Susceptible|worker|Monday"]
+    ph, role = pat["phases"].index("Susceptible"), pat["roles"].index("worker") + 1
+    got = t["activities"][start[ph, role, 0]:start[ph, role, 0] + count[ph, role, 0]]
+    assert [int(a["kind"]) for a in got] == [r["kind"] for r in rows]
+    assert [float(a["max"]) for a in got] == [r["max"] for r in rows]
+    assert (count[pat["phases"].index("Dead")] == 0).all()                      # no pattern: a dead person leaves the model
+    hospital = t["activities"][start[4, role, 0]:start[4, role, 0] + count[4, role, 0]]
+    assert len(hospital) >= 1                                                    # Hospitalized: to the nearest hospital
+    cs = t["choice_start"]
+    assert (np.diff(cs) > 0).all() and cs[-1] == len(t["choice_type"]) == len(t["choice_cum"])
+    for c in range(len(cs) - 1):
+        assert (np.diff(t["choice_cum"][cs[c]:cs[c + 1]]) >= 0).all()
+    assert t["nearest"].shape == (city.n_locations, len(scenario.TYPE_NAMES)) and t["cand"].shape[2] == t["n_candidates"]

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from common import Scenario, assert_same_run, load_props, run_gpu, run_oracle
+from common import Scenario, assert_same_run, load_props, make_engine, run_gpu, run_oracle
 import heros_b200 as hb
 from heros_b200 import _lib
 
@@ -290,4 +290,29 @@ def test_helsinki_real_location_table(model):
     gt, ot = sort_events(eng.transitions()), sort_events(sim.transitions())
     for k in ("person", "phase", "time"):
         np.testing.assert_array_equal(gt[k], ot[k])
+    eng.close()
+
+
+def test_logs_can_be_read_window_by_window():
+    """heros_get_infections / heros_get_transitions with a cursor (what a host does after every window): the pieces read
+    day by day are the complete, ordered logs."""
+    scn = Scenario(seed=8, n_persons=600, n_households=220, n_workplaces=20, n_shops=4, days=10)
+    props = hot_props("area")
+    eng = make_engine(scn, props, _lib.MODEL_AREA, _lib.TRIGGER_EXIT_ONLY, 4)
+    eng.expose(scn.seeds, np.zeros(len(scn.seeds)))
+    eng.submit_visits(scn.person, scn.loc, scn.sub, scn.t_in, scn.t_out)
+    inf_parts, tr_parts, n_inf, n_tr = [], [], 0, 0
+    for d in range(scn.days):
+        eng.step(24.0 * (d + 1))
+        a, b = eng.infections(first=n_inf), eng.transitions(first=n_tr)
+        n_inf += len(a["person"]); n_tr += len(b["person"])
+        inf_parts.append(a); tr_parts.append(b)
+        assert (a["time"] >= 24.0 * d).all() and (a["time"] < 24.0 * (d + 1)).all()
+    whole_inf, whole_tr = eng.infections(), eng.transitions()
+    assert len(whole_inf["person"]) > 50 and len(whole_tr["person"]) > len(whole_inf["person"])
+    for k in whole_inf:
+        np.testing.assert_array_equal(np.concatenate([p[k] for p in inf_parts]), whole_inf[k])
+    for k in whole_tr:
+        np.testing.assert_array_equal(np.concatenate([p[k] for p in tr_parts]), whole_tr[k])
+    assert (np.diff(whole_tr["time"]) >= 0).all()
     eng.close()

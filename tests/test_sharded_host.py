@@ -80,3 +80,16 @@ def test_all_to_all_rows_gloo_world_size_2():
             p.join(120)
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
         assert dict(out) == {0: 1, 1: 1}
+
+
+def test_sort_by_destination_groups_rows_by_owner():
+    import numpy as np
+    bases = [0, 10, 25, 40]
+    cols = {"person": np.arange(7, dtype=np.int32), "loc": np.array([30, 3, 12, 39, 0, 24, 10], np.int32),
+            "sub": np.zeros(7, np.int16), "t_in": np.arange(7.0), "t_out": np.arange(7.0) + 1}
+    out, off = sharded.sort_by_destination(cols, bases, 3)
+    assert off.tolist() == [0, 2, 5, 7]
+    assert out["loc"].tolist() == [3, 0, 12, 24, 10, 30, 39]          # stable inside a destination
+    assert out["person"].tolist() == [1, 4, 2, 5, 6, 0, 3]
+    empty, off = sharded.sort_by_destination({k: v[:0] for k, v in cols.items()}, bases, 3)
+    assert off.tolist() == [0, 0, 0, 0] and len(empty["loc"]) == 0
