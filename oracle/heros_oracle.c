@@ -15,6 +15,14 @@
  * (SURVEY.md 8c): the U(0,1) stream (-> counter-based Philox4x32-10 keyed by seed, person and event time, as the
  * north star prescribes), DistTriangular/DistUniform inverse CDFs, DurationDistribution (days*24 = hours),
  * ConditionalProbability (tabulated by gender and age), the movement driver (contract rows C1-C8).
+ *
+ * PARITY STATUS: EXACT PARITY UNPINNED BY THE REFERENCE.  The reference has no tests, golden vectors or fixtures for
+ * this path and cannot run here (no JVM; medlabs / DSOL jars not vendored), so the exact outputs of this oracle
+ * (event lists, probabilities) are checked against nothing the reference produced.  What pins it (tests/test_oracle.py):
+ * Random123 Philox known answers, libm within 1 ulp, the Javadoc worked example TArea:112-121, hand-derived boundary
+ * cases of the formulas, the parameter files of the reference (tests/golden/params_*.json), and the reference-produced
+ * epidemic curves of "seed comparison.xlsx" (tests/golden/seed_comparison.json) for three observable consequences of the
+ * driver contract: latent period, incubation band, exposures only at movement events.
  */
 #include "heros_oracle.h"
 
