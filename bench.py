@@ -218,7 +218,7 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, city, world, n_commuters):
+def workload_config(args, city, world, n_commuters, exchange="p2p"):
     cfg = {"workload": f"thehague-synthetic N={city.n_persons} locations={city.n_locations} "
                        f"sublocations={int(city.loc_nsub.sum())} model={args.model} trigger={args.trigger} seed={SEED} "
                        f"infected0={N_INFECTED}" + (f" per GPU, {world} tiles" if world > 1 else ""),
@@ -229,7 +229,7 @@ def workload_config(args, city, world, n_commuters):
         cfg["cross_tile"] = (f"{args.commute:.3f} of each tile's workers ({n_commuters} on rank 0) work in the next tile: "
                              "guest-stay blocks out, candidate blocks back every window, " +
                              ("written by the pack / export kernels straight into the peers' memory over NVLink (CUDA IPC), "
-                              "flags instead of collectives" if args.exchange == "p2p" else
+                              "flags instead of collectives" if exchange == "p2p" else
                               "2 equal-split NCCL all-to-alls on the engine stream") +
                              ", no host synchronisation inside a window")
     return cfg
@@ -293,6 +293,7 @@ def run_ours(args):
     first_timed = args.preroll + args.warmup
 
     guest_capacity = [4096]
+    exchange = [args.exchange]
     engines = []  # at N > 1 the engines (and their streams, which NCCL has seen) live until the process group is gone
 
     def new_engine():
@@ -300,11 +301,23 @@ def run_ours(args):
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
-            if args.exchange == "p2p":
-                bx = sharded.PeerExchange(sh, guest_capacity[0], candidate_capacity=4096)
-                bx.connect()
-                bx.set_sources([(rank - 1) % world])  # commuters come from the previous tile only
-            else:
+            bx = None
+            if exchange[0] == "p2p":
+                # the shards map each other's receive regions (CUDA IPC); if that is not possible on this machine, every
+                # rank falls back to the NCCL block exchange
+                try:
+                    bx = sharded.PeerExchange(sh, guest_capacity[0], candidate_capacity=4096)
+                    bx.connect()
+                    bx.set_sources([(rank - 1) % world])  # commuters come from the previous tile only
+                    ok = 1
+                except Exception as e:  # noqa: BLE001
+                    print(f"[bench] rank {rank}: peer-to-peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+                    bx, ok = None, 0
+                flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    exchange[0], bx = "nccl", None
+            if bx is None:
                 bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
         eng.seed_infections(N_INFECTED)
         engines.append(eng)
@@ -523,7 +536,7 @@ def run_ours(args):
         "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city, world, n_commuters),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city, world, n_commuters, exchange[0]),
         "clocks": clocks.summary(),
         "timing": "CUDA events on the engine stream around the K steps, max over ranks; wall clock of the same region: "
                   f"{1e3 * wall_seconds / args.steps:.4f} ms/step",
