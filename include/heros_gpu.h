@@ -119,7 +119,8 @@ typedef struct heros_step_stats {
     double retire_ms;         /* 0 (retire is part of k_bucket_scatter) */
     int64_t big_sublocations; /* sub-locations handled by the group kernels */
     int64_t big_stays;        /* ... and their stays */
-    double bucket_count_ms, bucket_scan_ms, bucket_scatter_ms; /* the three parts of bucket_ms */
+    double bucket_count_ms;   /* 0 (tickets are taken by k_submit / k_window_open) */
+    double bucket_scan_ms, bucket_scatter_ms; /* the two parts of bucket_ms */
     /* the group kernels run on auxiliary streams, side by side with k_transmit_thread and the sub-warp kernels: time
      * from the fork (after the scatter) until each of them finished -- classes 0, 1, 2, 3 + 4 -- and until the 32-lane
      * sub-warp kernel finished (it starts after k_transmit_thread) */
