@@ -766,7 +766,7 @@ int32_t check_ready(heros_handle h)
 // them: begin (disease-phase state machine + tickets of the open and carried-over stays; agent words final for the
 // window) -> [guests in] -> transmit (prefix sum, scatter + retire, every evaluation; candidates out / in) -> finish
 // (resolve).
-// heros_step runs the three back to back: 13 launches per window.
+// heros_step runs the three back to back: 14 launches per window.
 int32_t window_begin(heros_handle h, double T1)
 {
     cudaStream_t s = h->stream;
@@ -821,6 +821,7 @@ int32_t window_transmit(heros_handle h)
     CU(h, h->sub_seg[0].ensure(occupied_cap));
     CU(h, h->sub_seg[1].ensure((size_t) n_total / 9 + 16));  // sub-locations of 9..32 stays
     for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
+    for (auto& b : h->run_seg) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
     // exact bounds: a stay leaves at most one draw item, a sub-location at most one table entry per movement event
     CU(h, h->item_person.ensure((size_t) n_total + 1)); CU(h, h->item_key.ensure((size_t) n_total + 1));
@@ -866,7 +867,7 @@ int32_t window_transmit(heros_handle h)
     c.cand_cap = (uint32_t) h->cand_person.n;
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
     for (int k = 0; k < 2; ++k) c.sub_cap[k] = (uint32_t) h->sub_seg[k].n;
-    for (int k = 0; k < N_CLS; ++k) c.blk_seg[k] = h->blk_seg[k].p;
+    for (int k = 0; k < N_CLS; ++k) { c.blk_seg[k] = h->blk_seg[k].p; c.run_seg[k] = h->run_seg[k].p; }
     c.blk_cap = big.blk_cap;
     c.tab_t = h->tab_t.p; c.tab_p = h->tab_p.p; c.tab_cap = std::min(h->tab_t.n, h->tab_p.n);
     c.item_person = h->item_person.p; c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_pair = h->item_pair.p;
@@ -1021,6 +1022,7 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaEventCreate(&h->ts.fork)) != cudaSuccess) return bail("event", e);
     if ((e = cudaEventCreate(&h->ts.mid)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaEventCreateWithFlags(&h->ts.filtered, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     for (auto& j : h->ts.join)
         if ((e = cudaEventCreate(&j)) != cudaSuccess) return bail("event", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -1058,6 +1060,7 @@ int32_t heros_destroy(heros_handle h)
     h->item_person.release(); h->item_key.release(); h->item_tab.release(); h->item_pair.release();
     h->tab_t.release(); h->tab_p.release();
     for (auto& b : h->blk_seg) b.release();
+    for (auto& b : h->run_seg) b.release();
     h->huge_off.release(); h->scratch.release();
     h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
     h->s_choice_type.release(); h->s_nearest.release(); h->s_ncand.release(); h->s_cand.release(); h->d_home_loc.release();
@@ -1073,6 +1076,7 @@ int32_t heros_destroy(heros_handle h)
     for (auto& a : h->ts.aux) if (a) cudaStreamDestroy(a);
     if (h->ts.fork) cudaEventDestroy(h->ts.fork);
     if (h->ts.mid) cudaEventDestroy(h->ts.mid);
+    if (h->ts.filtered) cudaEventDestroy(h->ts.filtered);
     for (auto& j : h->ts.join) if (j) cudaEventDestroy(j);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

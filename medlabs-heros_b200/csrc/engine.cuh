@@ -65,6 +65,7 @@ struct Counters
     unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
     unsigned long long n_blk[N_CLS]; // segments handed to the group kernels (<= 256 / 1024 / 4096 / 8192 events in shared
                                      // memory, larger ones in global scratch)
+    unsigned long long n_run[N_CLS]; // ... of which the filter kernel passed on to the group kernels
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
@@ -125,7 +126,9 @@ struct WindowCtx
     double* tab_t; double* tab_p; unsigned long long tab_cap;
     uint32_t* item_person; uint32_t* item_key; unsigned long long* item_tab; unsigned long long* item_pair;
     unsigned long long item_cap;
-    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[3]
+    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[CLS_HUGE]
+    uint32_t* run_seg[N_CLS];      // the queued sub-locations of classes 0 and 1 that need more than lastCalculation
+                                   // advanced (k_group_filter)
     unsigned char* scratch; unsigned long long scratch_cap;
     uint32_t flags;
     Counters* ctr;
@@ -175,7 +178,7 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
 
 // the engine stream, four auxiliary streams for the kernels that run side by side, and the fork / join events
 constexpr int N_AUX = 5;
-struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid; cudaEvent_t join[N_AUX]; };
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid, filtered; cudaEvent_t join[N_AUX]; };
 constexpr int DRAW_ITEM_SHIFT = 40;
 constexpr unsigned long long DRAW_PAIR_MASK = (1ull << DRAW_ITEM_SHIFT) - 1ull;
 

@@ -140,7 +140,7 @@ struct heros_engine
     DevBuf<uint8_t> tr_phase;
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], item_person, item_key;
+    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], run_seg[N_CLS], item_person, item_key;
     DevBuf<unsigned long long> item_tab, item_pair;
     DevBuf<double> tab_t, tab_p;
     DevBuf<unsigned long long> huge_off;

@@ -17,6 +17,8 @@
 //                       evaluations together (REDUX), then every lane computes ONE evaluation of the chain -- the long
 //                       dependent fp64 chains (sqrt, exp) of up to 32 evaluations run side by side -- then lane = stay
 //                       for the draws
+//   k_group_filter    : one warp per queued segment of 33..512 stays: the same early-out, so that the group kernels of
+//                       the two small classes only get the segments with work for a whole thread block
 //   k_transmit_group  : one block per segment of > 32 stays, five classes by its number of events (queued by the
 //                       prefix-sum kernel): events bucketed by time in shared memory, the chain of calculated
 //                       evaluations by successor search + pointer doubling, exposure sums in 128-bit fixed point
@@ -522,6 +524,67 @@ template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
 
 }  // namespace
 
+constexpr int FILTERED_CLASSES = 2;
+
+// One warp per queued sub-location of classes 0 and 1 (33 .. 512 stays): who is here and the two latest events.  Where nobody can
+// be infected only lastCalculation has to advance (usually most of them); the others are passed on to the group kernel
+// of their class, which then runs whole thread blocks only where there is work for them.
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_group_filter(const WindowCtx c)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
+    const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
+    const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
+    uint32_t first[N_CLS + 1];
+    first[0] = 0;
+    for (int k = 0; k < N_CLS; ++k) first[k + 1] = first[k] + (uint32_t) min((unsigned long long) c.blk_cap, c.ctr->n_blk[k]);
+    for (uint32_t i = warp; i < first[FILTERED_CLASSES]; i += n_warps)
+    {
+        int cls = 0;
+        while (i >= first[cls + 1]) ++cls;
+        const uint32_t w = i - first[cls];
+        const uint32_t key = c.blk_seg[cls][w];
+        if (key == KEY_NONE) continue;
+        const uint32_t a = c.seg_start[key], n = c.seg_start[key + 1] - a;
+        const StayRec* rec = c.rec + a;
+        int ill = 0, sus = 0;
+        Top2 top;
+        top.init();
+        for (uint32_t v = lane; v < n; v += 32)
+        {
+            const StayRec r = rec[v];
+            const uint32_t tph = view_tphase(r.view);
+            ill |= phase_is_ill(tph);
+            sus |= phase_is_susceptible(tph);
+            if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
+            if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
+            top.merge(o1, o2);
+        }
+        const bool need_eval = __any_sync(FULL, ill) && __any_sync(FULL, sus);
+        if (!(top.m1 > neg_inf())) continue;  // no movement in this window
+        if (!need_eval && !exact)
+        {
+            double L;
+            if (advance_only(top, c.last_calc[key], thr, L))
+            {
+                if (lane == 0) c.last_calc[key] = L;
+                continue;
+            }
+        }
+        if (lane == 0)
+        {
+            const unsigned long long slot = atomicAdd(&c.ctr->n_run[cls], 1ull);  // <= n_blk[cls] <= blk_cap
+            c.run_seg[cls][slot] = key;
+        }
+    }
+}
+
 // The chain of calculated evaluations needs, from an evaluation at time e, the earliest later candidate event t with
 // !(t - e < threshold).  Events are put in time order by a counting sort into time buckets (no wider than the threshold
 // where affordable) followed by a rank sort inside every bucket; the successor of an event is then a binary search over
@@ -540,7 +603,10 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
     __shared__ unsigned long long s_tab;
     const int tid = grank<G>();
     const int group_in_block = G == 32 ? (int) (threadIdx.x >> 5) : 0;
-    const uint32_t n_list = (uint32_t) min((unsigned long long) c.blk_cap, c.ctr->n_blk[CLS]);
+    // classes 0 and 1 (thousands of sub-locations, most of which only need lastCalculation advanced) come through
+    // k_group_filter; the few large ones of classes 2-4 start at once and sort that out themselves (step 0)
+    constexpr bool FILTERED = CLS < FILTERED_CLASSES;
+    const uint32_t n_list = (uint32_t) min((unsigned long long) c.blk_cap, FILTERED ? c.ctr->n_run[CLS] : c.ctr->n_blk[CLS]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
@@ -552,7 +618,7 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
 
     for (uint32_t w = blockIdx.x * Cfg::PER_BLOCK + group_in_block; w < n_list; w += gridDim.x * Cfg::PER_BLOCK)
     {
-        const uint32_t key = c.blk_seg[CLS][w];
+        const uint32_t key = FILTERED ? c.run_seg[CLS][w] : c.blk_seg[CLS][w];
         if (key == KEY_NONE) continue;
         const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
         const int n = (int) (b - a);
@@ -560,7 +626,8 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
         const double L0 = c.last_calc[key];
 
         if (dbg) clk = clock64();
-        // 0. who is here and the two latest events; most segments only need lastCalculation advanced
+        // 0. who is here and the two latest events (k_group_filter has already dealt with the sub-locations that only
+        //    need lastCalculation advanced)
         bool need_eval;
         {
             int ill = 0, sus = 0;
@@ -1297,8 +1364,11 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     k_transmit_group<MODEL, 2><<<n_sm * 2, GroupCfg<2>::G, smem2, ts.aux[0]>>>(c);
     k_transmit_group<MODEL, 3><<<n_sm, GroupCfg<3>::G, smem3, ts.aux[4]>>>(c);
     k_transmit_group<MODEL, 4><<<n_sm, 1024, 0, ts.aux[4]>>>(c);
-    k_transmit_group<MODEL, 1><<<n_sm * 8, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
-    k_transmit_group<MODEL, 0><<<n_sm * 8, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
+    k_group_filter<MODEL><<<n_sm * 2, 256, 0, ts.aux[1]>>>(c);
+    cudaEventRecord(ts.filtered, ts.aux[1]);
+    cudaStreamWaitEvent(ts.aux[2], ts.filtered, 0);
+    k_transmit_group<MODEL, 1><<<n_sm * 4, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
+    k_transmit_group<MODEL, 0><<<n_sm * 4, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
     k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
     cudaEventRecord(ts.mid, s);
     cudaStreamWaitEvent(ts.aux[3], ts.mid, 0);
@@ -1315,7 +1385,7 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
         ++launches;
     }
     k_draw<<<n_sm * 4, 256, 0, s>>>(c);
-    launches += 9;
+    launches += 10;
 }
 
 void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
