@@ -5,6 +5,8 @@ transmission + progression -- and the outputs a user of the reference looks at: 
 (0.5 h samples, golden-spreadsheet column layout) as CSV and the infection event list.
 
 usage: python examples/run_thehague.py [--days 60] [--seed 111] [--model distance|area] [--persons 553667] [--out DIR]
+                                       [--location-policy FILE.csv] [--disease-policy FILE.csv]
+(policy files as in data/thehague/policies/: e.g. tests/golden/policies/HardLockdown_Realistic_10-40.csv)
 """
 from __future__ import annotations
 
@@ -27,6 +29,8 @@ def main():
     ap.add_argument("--persons", type=int, default=553667)
     ap.add_argument("--infected", type=int, default=100)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "thehague"))
+    ap.add_argument("--location-policy", default="", help="policies.LocationPolicyFile (ConstructHerosModel.java:1145)")
+    ap.add_argument("--disease-policy", default="", help="policies.DiseasePolicyFile (ConstructHerosModel.java:1179)")
     args = ap.parse_args()
 
     import heros_b200 as hb
@@ -43,11 +47,16 @@ def main():
     monitor = hb.DiseaseMonitor(model, progression, 0.5)                # ConstructHerosModel.java:145
     model.engine.seed_infections(args.infected)                          # ConstructHerosModel.java:1109-1128
     model.engine.set_schedule(scenario.compile_schedule(city), args.seed)
+    if args.location_policy:
+        hb.schedule_location_policies(model, args.location_policy)
+    if args.disease_policy:
+        hb.schedule_disease_policies(model, args.disease_policy)
     print(f"city of {city.n_persons} persons, {city.n_locations} locations built in {time.time() - t:.1f} s")
 
     t = time.time()
     gpu_ms = 0.0
     for day in range(args.days):
+        hb.apply_location_policies(model, 24.0 * day)
         model.engine.advance_schedule(day)
         stats = model.engine.step(24.0 * (day + 1))
         gpu_ms += stats["gpu_ms"]

@@ -202,6 +202,18 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
                            int32_t n_types, int32_t accommodation_type, int32_t n_candidates, const int32_t* nearest,
                            const int32_t* n_cand, const int32_t* cand, const int16_t* work_sublocation, uint64_t seed);
 int32_t heros_advance_schedule(heros_handle h, int32_t day);
+/* = LocationType.setClosurePolicy(fractionOpen, fractionActivities, alternativeLocationType, reportAsLocationName) as
+ * policy/LocationPolicy.java:39-46 calls it at the policy's event time (rows of data/<city>/policies/\*.csv; the report
+ * name only labels output and is not needed here).  The rule itself is inside the un-vendored medlabs jar; the
+ * convention of this engine (and of scenario.ScheduleGenerator, bit for bit): a location of the type is open iff its
+ * uniform keyed by (seed, location) is < fraction_open -- the same locations stay open from day to day and a smaller
+ * fraction keeps a subset; an activity (Work / School, Nearest, Random locators) whose location is open takes place
+ * iff its uniform keyed by (seed, person, day, activity) is < fraction_activities; otherwise the person goes home.
+ * alternative_type must be the Accommodation type (the person's home; every shipped policy row) or location_type
+ * itself (= reopened, fractions taken as 1); anything else: HEROS_ERR_UNSUPPORTED.  Applies to the days advanced
+ * after the call; call it between heros_step(24 d) and heros_advance_schedule(d) for a policy at day d. */
+int32_t heros_set_closure_policy(heros_handle h, int32_t location_type, double fraction_open, double fraction_activities,
+                                 int32_t alternative_type);
 /* debugging / tests: every stay the engine currently holds (pending closed stays, then the open stay of every person
  * with t_out = +inf), in no particular order */
 int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,

@@ -13,7 +13,8 @@ from .disease import (Covid19Progression, Covid19TransmissionArea, Covid19Transm
                       DiseaseTransmission, HerosModel, InfectionRecord, construct_disease_model)
 from .engine import HerosEngine  # noqa: F401
 from .monitor import DiseaseMonitor, compartment_series  # noqa: F401
-from .policy import DiseasePolicy  # noqa: F401
+from .policy import (DiseasePolicy, LocationPolicy, apply_location_policies, schedule_disease_policies,  # noqa: F401
+                     schedule_location_policies)
 from . import sharded  # noqa: F401
 
 __version__ = "0.1.0"

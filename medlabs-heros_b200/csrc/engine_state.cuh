@@ -148,6 +148,7 @@ struct heros_engine
 
     // activity schedule (heros_set_schedule)
     bool have_schedule = false;
+    DevBuf<double2> s_closure; DevBuf<uint8_t> s_loc_type; std::vector<double> h_closure; bool closure_active = false;
     int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
     uint64_t sched_seed = 0;
     DevBuf<Activity> s_acts;

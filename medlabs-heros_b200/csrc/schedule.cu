@@ -25,7 +25,23 @@ struct ScheduleTables
     const int32_t* home_loc; const int16_t* home_sub; const int32_t* work_loc; const int16_t* work_sub;
     const uint32_t* loc_base; const int16_t* loc_nsub; uint32_t n_loc;
     uint64_t seed;
+    // closure policy (policy/LocationPolicy.java:39-46): per location type {fraction of locations open, fraction of
+    // activities that still take place}; nullptr while every type is fully open
+    const double2* closure; const uint8_t* loc_type;
 };
+
+// Does the activity (person a, day * 64 + i) at location dl fall to the closure policy of the location's type?  The
+// location is open iff its keyed uniform (seed, location) < fractionOpen; an activity in an open location takes place
+// iff its keyed uniform (seed, person, day, activity) < fractionActivities (same rule as scenario.ScheduleGenerator).
+__device__ __forceinline__ bool closed_by_policy(const ScheduleTables& S, uint32_t a, uint32_t day_act, int32_t dl, int ty)
+{
+    const double2 f = S.closure[ty];
+    if (!(f.x < 1.0) && !(f.y < 1.0)) return false;
+    const uint32_t k0 = (uint32_t) S.seed, k1 = (uint32_t) (S.seed >> 32);
+    const double u_loc = (double) philox4x32_10((uint32_t) dl, 0u, 2u, TAG_SCHEDULE, k0, k1).x * 0x1.0p-32;
+    const double u_act = (double) philox4x32_10(a, day_act, 1u, TAG_SCHEDULE, k0, k1).x * 0x1.0p-32;
+    return !(u_loc < f.x && u_act < f.y);
+}
 
 __device__ __forceinline__ double activity_duration(const Activity& a, double u)
 {
@@ -116,7 +132,11 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
         else if (act.locator == 1)
         {
             const int32_t wl = S.work_loc[a];
-            if (wl >= 0) dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
+            if (wl >= 0)
+            {
+                dest = S.loc_base[wl] + (uint32_t) S.work_sub[a];
+                if (S.closure && closed_by_policy(S, a, (uint32_t) (day * 64 + i), wl, S.loc_type[wl])) dest = home_key;
+            }
         }
         else if (act.locator >= 3 && act.choice >= 0)
         {
@@ -140,6 +160,8 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
                 dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
             }
             if (ty == S.accommodation_type || dl < 0)
+                dest = home_key;
+            else if (S.closure && closed_by_policy(S, a, (uint32_t) (day * 64 + i), dl, ty))
                 dest = home_key;
             else
             {
@@ -283,6 +305,39 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
     return HEROS_OK;
 }
 
+int32_t heros_set_closure_policy(heros_handle h, int32_t location_type, double fraction_open, double fraction_activities,
+                                 int32_t alternative_type)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (!h->have_schedule) return fail(h, HEROS_ERR_INVALID, "heros_set_schedule has not been called");
+    if (location_type < 0 || location_type >= h->n_types || alternative_type < 0 || alternative_type >= h->n_types)
+        return fail(h, HEROS_ERR_INVALID, "location type id out of range");
+    if (alternative_type == location_type)
+        fraction_open = fraction_activities = 1.0;  // "Workplace -> Workplace": the type is open again
+    else if (alternative_type != h->sched_accommodation)
+        return fail(h, HEROS_ERR_UNSUPPORTED, "the alternative of a closed location type must be Accommodation (the person's home) or the type itself");
+    if (!(fraction_open >= 0.0 && fraction_open <= 1.0) || !(fraction_activities >= 0.0 && fraction_activities <= 1.0))
+        return fail(h, HEROS_ERR_INVALID, "fractions must lie in [0, 1]");
+    cudaSetDevice(h->cfg.device);
+    if (h->h_closure.size() != (size_t) h->n_types * 2) h->h_closure.assign((size_t) h->n_types * 2, 1.0);
+    h->h_closure[(size_t) location_type * 2] = fraction_open;
+    h->h_closure[(size_t) location_type * 2 + 1] = fraction_activities;
+    bool active = false;
+    for (double f : h->h_closure) active = active || f < 1.0;
+    cudaStream_t s = h->stream;
+    if (!h->s_loc_type.p)
+    {
+        CU(h, h->s_loc_type.ensure(h->n_loc));
+        CU(h, cudaMemcpyAsync(h->s_loc_type.p, h->h_loc_type.data(), h->n_loc, cudaMemcpyHostToDevice, s));
+    }
+    CU(h, h->s_closure.ensure(h->n_types));
+    // the table is read by the k_advance_day launches that follow on this stream
+    CU(h, cudaMemcpyAsync(h->s_closure.p, h->h_closure.data(), (size_t) h->n_types * 16, cudaMemcpyHostToDevice, s));
+    CU(h, cudaStreamSynchronize(s));
+    h->closure_active = active;
+    return HEROS_OK;
+}
+
 int32_t heros_advance_schedule(heros_handle h, int32_t day)
 {
     int32_t rc = check_ready(h);
@@ -304,6 +359,7 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
     S.nearest = h->s_nearest.p; S.n_cand = h->s_ncand.p; S.cand = h->s_cand.p;
     S.home_loc = h->d_home_loc.p; S.home_sub = h->d_home_sub.p; S.work_loc = h->d_work_loc.p; S.work_sub = h->d_work_sub.p;
     S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
+    S.closure = h->closure_active ? h->s_closure.p : nullptr; S.loc_type = h->s_loc_type.p;
     static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));
     static bool configured[64] = {};

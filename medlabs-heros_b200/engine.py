@@ -149,6 +149,12 @@ class HerosEngine:
     def advance_schedule(self, day: int):
         self._check(self._lib.heros_advance_schedule(self._h, int(day)))
 
+    def set_closure_policy(self, location_type: int, fraction_open: float, fraction_activities: float,
+                           alternative_type: int):
+        """LocationType.setClosurePolicy of the reference (LocationPolicy.java:45) for the device-side schedule."""
+        self._check(self._lib.heros_set_closure_policy(self._h, int(location_type), float(fraction_open),
+                                                       float(fraction_activities), int(alternative_type)))
+
     def debug_stays(self) -> Dict[str, np.ndarray]:
         n = C.c_int64(0)
         self._check(self._lib.heros_debug_get_stays(self._h, 0, None, None, None, None, None, C.byref(n)))

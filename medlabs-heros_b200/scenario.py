@@ -335,6 +335,44 @@ class ScheduleGenerator:
         self.day = 0
         self._choice_tables = [self._compile_choice(c) for c in self.pat["choices"]]
         self._day_names = ["Monday"] * 4 + ["Friday", "Saturday", "Sunday"]
+        # closure policy per location type: fraction of its locations that stay open, fraction of the activities that
+        # still take place in an open one (LocationPolicy.java:39-46)
+        self.frac_open = np.ones(len(TYPE_NAMES), np.float64)
+        self.frac_act = np.ones(len(TYPE_NAMES), np.float64)
+
+    def set_closure_policy(self, location_type: int, fraction_open: float, fraction_activities: float,
+                           alternative_type: int) -> None:
+        """``LocationType.setClosurePolicy(fractionOpen, fractionActivities, alternativeLocationType, reportAs)`` as the
+        reference's policy files use it (LocationPolicy.java:45; data/*/policies/*.csv: the alternative is always
+        Accommodation = the person's home, or the type itself = reopened).  medlabs' own rule is not in the reference
+        tree; the convention shared with the device-side schedule is: a location of the type is open iff its keyed
+        uniform (seed, location) is < fractionOpen (the same locations stay open while the fraction does not change, and
+        a smaller fraction keeps a subset); an activity that would take place in an open location takes place iff its
+        keyed uniform (seed, person, day, activity) is < fractionActivities; otherwise the person goes home.  A change
+        applies to the days generated after it."""
+        ty = int(location_type)
+        if not 0 <= ty < len(TYPE_NAMES):
+            raise ValueError("unknown location type")
+        if int(alternative_type) == ty:
+            fraction_open = fraction_activities = 1.0  # "Workplace -> Workplace": reopened
+        elif int(alternative_type) != TYPE_ID["Accommodation"]:
+            raise ValueError("the alternative of a closed location type is the person's home (Accommodation)")
+        if not (0.0 <= fraction_open <= 1.0 and 0.0 <= fraction_activities <= 1.0):
+            raise ValueError("fractions must lie in [0, 1]")
+        self.frac_open[ty], self.frac_act[ty] = float(fraction_open), float(fraction_activities)
+
+    def _closed(self, idx, day_act, dl, ty):
+        """True where the activity of persons ``idx`` at location ``dl`` (type ``ty``, arrays) falls to the closure
+        policy of the type."""
+        ty = np.asarray(ty, np.int64)
+        fo, fa = self.frac_open[ty], self.frac_act[ty]
+        if not ((fo < 1.0) | (fa < 1.0)).any():
+            return np.zeros(len(idx), bool)
+        x_loc = philox4x32_10(np.maximum(dl, 0), 0, 2, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
+        x_act = philox4x32_10(idx, day_act, 1, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
+        u_loc = x_loc.astype(np.float64) * 2.0 ** -32
+        u_act = x_act.astype(np.float64) * 2.0 ** -32
+        return (dl >= 0) & ~((u_loc < fo) & (u_act < fa))
 
     @staticmethod
     def _compile_choice(items):
@@ -392,7 +430,7 @@ class ScheduleGenerator:
                 u_type = z.astype(np.float64) * 2.0 ** -32
                 u_cand = (w >> np.uint64(16)).astype(np.float64) * 2.0 ** -16
                 u_sub = (w & np.uint64(0xFFFF)).astype(np.float64) * 2.0 ** -16
-                dest_l, dest_s = self._locate(act, idx, u_type, u_cand, u_sub)
+                dest_l, dest_s = self._locate(act, idx, u_type, u_cand, u_sub, d * 64 + a_i)
                 move = alive & ((dest_l != self.cur_loc[idx]) | (dest_s != self.cur_sub[idx]))
                 dur = self._duration(act, u_dur)
                 if act["kind"] == 1:  # travel: leave now, arrive after the travel time
@@ -441,7 +479,7 @@ class ScheduleGenerator:
             return act["min"] + (act["max"] - act["min"]) * u
         return np.full(len(u), act["mode"])
 
-    def _locate(self, act, idx, u_type, u_cand, u_sub):
+    def _locate(self, act, idx, u_type, u_cand, u_sub, day_act=0):
         c = self.city
         loc = act["locator"]
         home_l, home_s = c.home_loc[idx].astype(np.int64), c.home_sub[idx].astype(np.int64)
@@ -450,7 +488,10 @@ class ScheduleGenerator:
         if loc == 1:  # Work / School; persons without one stay where they are
             wl = c.work_loc[idx].astype(np.int64)
             has = wl >= 0
-            return np.where(has, wl, self.cur_loc[idx]), np.where(has, c.work_sub[idx].astype(np.int64), self.cur_sub[idx])
+            shut = has & self._closed(idx, day_act, wl, c.loc_type[np.maximum(wl, 0)])
+            dl = np.where(has, wl, self.cur_loc[idx])
+            ds = np.where(has, c.work_sub[idx].astype(np.int64), self.cur_sub[idx])
+            return np.where(shut, home_l, dl), np.where(shut, home_s, ds)
         if loc == 2 or act["choice"] < 0:
             return self.cur_loc[idx].copy(), self.cur_sub[idx].copy()
         types, cum = self._choice_tables[act["choice"]]
@@ -463,6 +504,7 @@ class ScheduleGenerator:
             j = np.minimum((u_cand * n).astype(np.int64), np.maximum(n - 1, 0))
             dl = np.where(n > 0, c.cand[home_l, ty, j], NONE).astype(np.int64)
         go_home = (ty == TYPE_ID["Accommodation"]) | (dl < 0)
+        go_home |= self._closed(idx, day_act, dl, ty)
         nsub = np.maximum(c.loc_nsub[np.maximum(dl, 0)].astype(np.int64), 1)
         ds = np.minimum((u_sub * nsub).astype(np.int64), nsub - 1)
         return np.where(go_home, home_l, dl), np.where(go_home, home_s, ds)

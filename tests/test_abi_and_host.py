@@ -195,3 +195,81 @@ def test_compiled_schedule_tables_are_consistent():
     for c in range(len(cs) - 1):
         assert (np.diff(t["choice_cum"][cs[c]:cs[c + 1]]) >= 0).all()
     assert t["nearest"].shape == (city.n_locations, len(scenario.TYPE_NAMES)) and t["cand"].shape[2] == t["n_candidates"]
+
+
+class _QueueModel:
+    """what LocationPolicy needs of the model on a box without a GPU: somewhere to queue"""
+
+
+def test_location_policy_files_close_and_reopen_location_types(capsys):
+    """data/thehague/policies/HardLockdown_Realistic_10-40.csv (tests/golden/policies/, tools/make_policy_fixtures.py)
+    through the LocationPolicy mirror into the host-side schedule: closed types are not visited from day 10 on, the
+    partially open ones keep a subset of their locations and of their activities, everything is back on day 40."""
+    city = scenario.City(4000, seed=5)
+    T = scenario.TYPE_ID
+    model = _QueueModel()
+    pol = hb.schedule_location_policies(model, os.path.join(GOLDEN, "policies", "HardLockdown_Realistic_10-40.csv"))
+    assert len(pol) == 26 and all(p.scheduled for p in pol)
+    assert pol[0].time == 240.0 and pol[0].locationType == T["Workplace"] and pol[0].fractionOpen == 0.2
+    assert pol[0].alternativeLocationType == T["Accommodation"] and pol[0].reportAsLocationName == "WorkToHome"
+    hb.LocationPolicy(model, 0.0, "Casino", 0.0, 0.0, "Accommodation", "StayHome")        # LocationPolicy.java:24-28
+    hb.LocationPolicy(model, 0.0, "Retail", 0.0, 0.0, "Moon", "StayHome")                  # :30-34
+    err = capsys.readouterr().err
+    assert "Did not recognize locationType Casino" in err and "Did not recognize alternativeLocationType Moon" in err
+    assert len(model.locationPolicies) == 26
+
+    gen, free = scenario.ScheduleGenerator(city, 111), scenario.ScheduleGenerator(city, 111)
+    phase = np.zeros(city.n_persons, np.uint8)
+    per_day, per_day_free = [], []
+    for d in range(42):
+        fired = hb.apply_location_policies(model, 24.0 * d, gen)
+        assert fired == (13 if d in (10, 40) else 0)
+        st, sf = gen.generate_day(phase), free.generate_day(phase)
+        per_day.append(st)
+        per_day_free.append(sf)
+        if d < 10:   # before the lockdown: the same stays
+            for k in st:
+                np.testing.assert_array_equal(st[k], sf[k])
+
+    def count(st, name):
+        return int((city.loc_type[st["loc"]] == T[name]).sum())
+
+    for d in range(11, 40):   # day 10 still closes the stays opened on day 9
+        for name in ("Mall", "BarRestaurant", "PrimarySchool", "University", "Recreation", "Park"):
+            assert count(per_day[d], name) == 0, (d, name)
+    work_lock = sum(count(per_day[d], "Workplace") for d in range(14, 19))      # Mon-Fri
+    work_free = sum(count(per_day_free[d], "Workplace") for d in range(14, 19))
+    assert 0.03 * work_free < work_lock < 0.25 * work_free                       # 0.2 x 0.5 of the work stays, roughly
+    # the workplaces still visited are a fixed subset (keyed by the location), not a fresh draw every day
+    open_places = [np.unique(per_day[d]["loc"][city.loc_type[per_day[d]["loc"]] == T["Workplace"]]) for d in (14, 15, 16)]
+    all_places = np.unique(np.concatenate(open_places))
+    free_places = np.unique(per_day_free[14]["loc"][city.loc_type[per_day_free[14]["loc"]] == T["Workplace"]])
+    assert len(all_places) < 0.35 * len(free_places)
+    for d in (40, 41):
+        assert count(per_day[d], "PrimarySchool") > 0 or d % 7 >= 5
+    # day 41: the stays that begin that day are the ones of a run without any policy
+    tables = []
+    for st in (per_day[41], per_day_free[41]):
+        m = st["t_in"] >= 24.0 * 41
+        o = np.lexsort((st["t_in"][m], st["person"][m]))
+        tables.append(np.stack([st[k][m][o].astype(np.float64) for k in ("person", "loc", "sub", "t_in", "t_out")]))
+    np.testing.assert_array_equal(tables[0], tables[1])
+    with pytest.raises(ValueError):
+        gen.set_closure_policy(T["Retail"], 0.5, 0.5, T["Park"])       # only home or the type itself
+    with pytest.raises(ValueError):
+        gen.set_closure_policy(T["Retail"], 1.5, 0.5, T["Accommodation"])
+
+
+def test_disease_policy_file_reader():
+    calls = []
+
+    class Transmission:
+        def setParameter(self, name, value, at_time=None):
+            calls.append((name, value, at_time))
+
+    class Model:
+        def getDiseaseTransmission(self):
+            return Transmission()
+
+    hb.schedule_disease_policies(Model(), os.path.join(GOLDEN, "policies", "MaskingDistance_10-40.csv"))
+    assert calls == [("psi", 2.0, 240.0), ("mu", 0.6, 240.0), ("psi", 1.0, 960.0), ("mu", 0.0, 960.0)]

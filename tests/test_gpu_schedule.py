@@ -64,12 +64,71 @@ def test_device_schedule_equals_host_generator(model):
     dev.close()
 
 
+def test_device_schedule_with_closure_policies_equals_host_generator():
+    """LocationPolicy rows (partial closure 0.2 / 0.5 of workplaces, 0.1 / 0.1 of retail, full closure of the schools,
+    reopening) through heros_set_closure_policy and through the host-side generator: the same stays bit for bit, the
+    same epidemic."""
+    import os
+    from common import GOLDEN
+    city = scenario.City(6000, seed=11)
+    props = load_props("distance")
+    props["covidT_dist.alpha"] = "2.5"
+    T = scenario.TYPE_ID
+    host, dev = make(city, props, hb.MODEL_DISTANCE), make(city, props, hb.MODEL_DISTANCE)
+    gen = scenario.ScheduleGenerator(city, 111)
+    dev.set_schedule(scenario.compile_schedule(city), 111)
+
+    class Model:          # the queue the LocationPolicy mirror needs; the engine receives the device-side calls
+        engine = dev
+    rows = [(2.0, "Workplace", 0.2, 0.5, "Accommodation"), (2.0, "Retail", 0.1, 0.1, "Accommodation"),
+            (2.0, "PrimarySchool", 0.0, 0.0, "Accommodation"), (2.0, "SecondarySchool", 0.0, 0.0, "Accommodation"),
+            (2.0, "BarRestaurant", 0.0, 1.0, "Accommodation"), (2.0, "Park", 1.0, 0.3, "Accommodation"),
+            (9.0, "Workplace", 1.0, 1.0, "Workplace"), (9.0, "PrimarySchool", 1.0, 1.0, "PrimarySchool"),
+            (9.0, "Park", 0.5, 1.0, "Accommodation")]
+    for day, name, fo, fa, alt in rows:
+        hb.LocationPolicy(Model, 24.0 * day, name, fo, fa, alt, "report")
+    work_stays = []
+    for d in range(12):
+        due = [p for p in Model.locationPolicies if p.time <= 24.0 * d]
+        for p in due:
+            p.openCloseLocationType(gen)       # host-side schedule
+        assert hb.apply_location_policies(Model, 24.0 * d) == len(due)   # device-side schedule
+        st = gen.generate_day(host.agent_state()["phase"])
+        work_stays.append(int((city.loc_type[st["loc"]] == T["Workplace"]).sum()))
+        host.submit_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        dev.advance_schedule(d)
+        a, b = stay_table(host.debug_stays()), stay_table(dev.debug_stays())
+        assert a.shape == b.shape, (d, a.shape, b.shape)
+        np.testing.assert_array_equal(a, b)
+        if 3 <= d < 9:
+            assert (city.loc_type[st["loc"]] == T["PrimarySchool"]).sum() == 0
+            assert (city.loc_type[st["loc"]] == T["BarRestaurant"]).sum() == 0
+        host.step(24.0 * (d + 1))
+        dev.step(24.0 * (d + 1))
+        np.testing.assert_array_equal(host.phase_counts(), dev.phase_counts())
+    assert work_stays[3] < 0.3 * work_stays[1] and work_stays[10] > 0.8 * work_stays[1]
+    hi, di = sort_events(host.infections()), sort_events(dev.infections())
+    assert len(hi["person"]) > 50
+    for k in ("person", "loc", "sub", "time", "p"):
+        np.testing.assert_array_equal(hi[k], di[k])
+    with pytest.raises(hb.HerosError):
+        dev.set_closure_policy(T["Retail"], 0.5, 0.5, T["Park"])      # neither home nor the type itself
+    with pytest.raises(hb.HerosError):
+        dev.set_closure_policy(T["Retail"], 1.5, 0.5, T["Accommodation"])
+    with pytest.raises(hb.HerosError):
+        dev.set_closure_policy(99, 0.5, 0.5, T["Accommodation"])
+    host.close()
+    dev.close()
+
+
 def test_schedule_errors():
     city = scenario.City(800, seed=3)
     props = load_props("distance")
     eng = make(city, props, hb.MODEL_DISTANCE)
     with pytest.raises(hb.HerosError):
         eng.advance_schedule(0)               # heros_set_schedule has not been called
+    with pytest.raises(hb.HerosError):
+        eng.set_closure_policy(1, 0.0, 0.0, 0)   # needs the schedule tables
     tables = scenario.compile_schedule(city)
     bad = dict(tables)
     bad["pattern_count"] = tables["pattern_count"].copy()
