@@ -214,6 +214,16 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day);
  * after the call; call it between heros_step(24 d) and heros_advance_schedule(d) for a policy at day d. */
 int32_t heros_set_closure_policy(heros_handle h, int32_t location_type, double fraction_open, double fraction_activities,
                                  int32_t alternative_type);
+/* = what HerosModel.locationDump (model/HerosModel.java:266-299) writes every simulated hour: the number of persons in
+ * every location (Location.getAllPersonIds().size(), :280) and in every sub-location
+ * (DiseaseTransmission.getNrPersonsInSublocation(location, index), :284), sampled at times[0..n_times) (ascending,
+ * hours) from the stays the engine holds for the coming window -- call it after heros_submit_visits /
+ * heros_advance_schedule and before heros_step of that window.  A stay counts at t iff t_in <= t < t_out (the
+ * movements of time t have taken place).  persons_per_location: [n_times][n_locations]; persons_per_sublocation:
+ * [n_times][n_sublocations] with the sub-locations in location-major order, location l owning max(n_sub[l], 1)
+ * consecutive entries; either may be NULL.  The sizes are checked against the tables of heros_set_locations. */
+int32_t heros_sample_occupancy(heros_handle h, int32_t n_times, const double* times, int64_t n_locations,
+                               int32_t* persons_per_location, int64_t n_sublocations, int32_t* persons_per_sublocation);
 /* debugging / tests: every stay the engine currently holds (pending closed stays, then the open stay of every person
  * with t_out = +inf), in no particular order */
 int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,

@@ -12,7 +12,7 @@ from .build import build  # noqa: F401
 from .disease import (Covid19Progression, Covid19TransmissionArea, Covid19TransmissionDistance,  # noqa: F401
                       DiseaseTransmission, HerosModel, InfectionRecord, construct_disease_model)
 from .engine import HerosEngine  # noqa: F401
-from .monitor import DiseaseMonitor, compartment_series  # noqa: F401
+from .monitor import DiseaseMonitor, LocationDump, compartment_series  # noqa: F401
 from .policy import (DiseasePolicy, LocationPolicy, apply_location_policies, schedule_disease_policies,  # noqa: F401
                      schedule_location_policies)
 from . import sharded  # noqa: F401

@@ -1062,7 +1062,7 @@ int32_t heros_destroy(heros_handle h)
     for (auto& b : h->blk_seg) b.release();
     for (auto& b : h->run_seg) b.release();
     h->huge_off.release(); h->scratch.release();
-    h->s_closure.release(); h->s_loc_type.release();
+    h->s_closure.release(); h->s_loc_type.release(); h->m_times.release(); h->m_sub.release(); h->m_loc.release();
     h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
     h->s_choice_type.release(); h->s_nearest.release(); h->s_ncand.release(); h->s_cand.release(); h->d_home_loc.release();
     h->d_work_loc.release(); h->s_choice_cum.release(); h->d_home_sub.release(); h->d_work_sub.release();

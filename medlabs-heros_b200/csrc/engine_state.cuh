@@ -1,6 +1,6 @@
 // engine_state.cuh -- the engine object and the small shared definitions of the translation units that implement the
 // C ABI (engine.cu: lifecycle, inputs, the window pipeline, outputs; exchange.cu: multi-GPU exchange; schedule.cu: the
-// device-side activity schedule).  transmit.cu only needs engine.cuh.
+// device-side activity schedule; monitor.cu: occupancy sampling).  transmit.cu only needs engine.cuh.
 #pragma once
 
 #include "engine.cuh"
@@ -148,6 +148,7 @@ struct heros_engine
 
     // activity schedule (heros_set_schedule)
     bool have_schedule = false;
+    DevBuf<double> m_times; DevBuf<int32_t> m_sub, m_loc;  // heros_sample_occupancy
     DevBuf<double2> s_closure; DevBuf<uint8_t> s_loc_type; std::vector<double> h_closure; bool closure_active = false;
     int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
     uint64_t sched_seed = 0;

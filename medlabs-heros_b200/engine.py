@@ -76,6 +76,10 @@ class HerosEngine:
         e = None if lon is None else _arr(lon, np.float32)
         self._check(self._lib.heros_set_locations(self._h, len(a), _p(a), _p(b), _p(c), _p(d), _p(e)))
         self.n_locations = len(a)
+        self.location_n_sub = b.copy()
+        # first entry of every location in the location-major sub-location order (a location without sub-locations
+        # still owns one entry)
+        self.location_first_sub = np.concatenate([[0], np.cumsum(np.maximum(b.astype(np.int64), 1))])
 
     def set_persons(self, age, female, role=None, home_loc=None, home_sub=None, work_loc=None):
         a = _arr(age, np.int8)
@@ -154,6 +158,18 @@ class HerosEngine:
         """LocationType.setClosurePolicy of the reference (LocationPolicy.java:45) for the device-side schedule."""
         self._check(self._lib.heros_set_closure_policy(self._h, int(location_type), float(fraction_open),
                                                        float(fraction_activities), int(alternative_type)))
+
+    def sample_occupancy(self, times, locations: bool = True, sublocations: bool = True):
+        """Persons per location ``[len(times), n_locations]`` and per sub-location ``[len(times), n_sublocations]``
+        (location-major, see ``location_first_sub``) at the given times, from the stays held for the coming window
+        (heros_sample_occupancy = the hourly samples of HerosModel.locationDump, HerosModel.java:266-299)."""
+        t = _arr(times, np.float64)
+        n_sub_total = int(self.location_first_sub[-1])
+        per_loc = np.zeros((len(t), self.n_locations), np.int32) if locations else None
+        per_sub = np.zeros((len(t), n_sub_total), np.int32) if sublocations else None
+        self._check(self._lib.heros_sample_occupancy(self._h, len(t), _p(t), self.n_locations, _p(per_loc), n_sub_total,
+                                                     _p(per_sub)))
+        return per_loc, per_sub
 
     def debug_stays(self) -> Dict[str, np.ndarray]:
         n = C.c_int64(0)

@@ -12,6 +12,8 @@ sample (phase-change events fire before the monitor's event of the same time).
 from __future__ import annotations
 
 import csv
+import gzip
+import os
 from typing import Dict, Tuple
 
 import numpy as np
@@ -62,3 +64,50 @@ class DiseaseMonitor:
             w.writerow(HEADER)
             for t, row in zip(times, counts):
                 w.writerow([float(t)] + [int(x) for x in row])
+
+
+class LocationDump:
+    """The two hourly occupancy files of the reference (model/HerosModel.java:236-299, ``generic.WriteOutput``):
+    ``locationNrPersons.csv.gz`` (``"Time(h)","LocationNr","NrPersons"``) and ``sublocationNrPersons.csv.gz``
+    (``"Time(h)","LocationNr","SubLocationNr","NrPersons"``), one block of rows per simulated hour.
+
+    As in the reference, the sub-location file lists the indices 1 .. nSub-1 only (the loop of HerosModel.java:282
+    starts at 1), so locations with a single sub-location do not appear in it.  Rows are ordered by location type and
+    then by location id (the reference follows the iteration order of a Trove hash map per type, which is not
+    reproducible).  Usage: after the stays of a day are in the engine (``submit_visits`` / ``advance_schedule``) and
+    before ``step``, call ``dump_hours(t0, t1)`` -- it samples the hours ``t0 <= t < t1`` on the device
+    (``heros_sample_occupancy``) and appends them."""
+
+    LOCATION_HEADER = '"Time(h)","LocationNr","NrPersons"\n'
+    SUBLOCATION_HEADER = '"Time(h)","LocationNr","SubLocationNr","NrPersons"\n'
+
+    def __init__(self, engine, location_type, output_path: str, interval: float = 1.0):
+        self.engine, self.interval = engine, float(interval)
+        ty = np.asarray(location_type, np.int64)
+        self.order = np.lexsort((np.arange(len(ty)), ty))          # by type, then by id
+        n_sub = engine.location_n_sub.astype(np.int64)
+        first = engine.location_first_sub
+        # (location, sub-location index, position in the per-sub-location counts) of every row of the second file
+        loc = np.repeat(self.order, np.maximum(n_sub[self.order] - 1, 0))
+        start = np.cumsum(np.r_[0, np.maximum(n_sub[self.order] - 1, 0)])[:-1]
+        idx = np.arange(len(loc)) - np.repeat(start, np.maximum(n_sub[self.order] - 1, 0)) + 1
+        self.sub_loc, self.sub_index, self.sub_pos = loc, idx, first[loc] + idx
+        os.makedirs(output_path, exist_ok=True)
+        self.loc_file = gzip.open(os.path.join(output_path, "locationNrPersons.csv.gz"), "wt", encoding="utf-8")
+        self.sub_file = gzip.open(os.path.join(output_path, "sublocationNrPersons.csv.gz"), "wt", encoding="utf-8")
+        self.loc_file.write(self.LOCATION_HEADER)
+        self.sub_file.write(self.SUBLOCATION_HEADER)
+
+    def dump_hours(self, t0: float, t1: float) -> int:
+        times = np.arange(t0, t1 - 1e-9, self.interval)
+        per_loc, per_sub = self.engine.sample_occupancy(times)
+        for j, t in enumerate(times):
+            ts = repr(float(t))                                    # Java's Double.toString for these values
+            self.loc_file.write("".join(f"{ts},{l},{n}\n" for l, n in zip(self.order.tolist(), per_loc[j, self.order].tolist())))
+            self.sub_file.write("".join(f"{ts},{l},{i},{n}\n" for l, i, n in zip(self.sub_loc.tolist(), self.sub_index.tolist(),
+                                                                                per_sub[j, self.sub_pos].tolist())))
+        return len(times)
+
+    def close(self) -> None:
+        self.loc_file.close()
+        self.sub_file.close()

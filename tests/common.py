@@ -259,3 +259,14 @@ def assert_same_run(gpu: dict, ora: dict):
     ill = (ora["state"]["phase"] >= 1) & (ora["state"]["phase"] <= 5)
     np.testing.assert_array_equal(gpu["state"]["next_time"][ill], ora["state"]["next_time"][ill])
     np.testing.assert_array_equal(gpu["state"]["next_phase"][ill], ora["state"]["next_phase"][ill])
+
+
+def occupancy_from_stays(st, first_sub, times):
+    """numpy statement of heros_sample_occupancy: a stay counts at t iff t_in <= t < t_out"""
+    pos = first_sub[st["loc"]] + st["sub"]
+    per_sub = np.zeros((len(times), int(first_sub[-1])), np.int32)
+    for j, t in enumerate(times):
+        m = (st["t_in"] <= t) & (t < st["t_out"])
+        np.add.at(per_sub[j], pos[m], 1)
+    per_loc = np.add.reduceat(per_sub, first_sub[:-1], axis=1).astype(np.int32)
+    return per_loc, per_sub

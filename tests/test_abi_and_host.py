@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import heros_b200 as hb
-from common import GOLDEN, ROOT, load_props
+from common import GOLDEN, ROOT, load_props, occupancy_from_stays
 from heros_b200 import _lib, properties, scenario
 
 
@@ -273,3 +273,44 @@ def test_disease_policy_file_reader():
 
     hb.schedule_disease_policies(Model(), os.path.join(GOLDEN, "policies", "MaskingDistance_10-40.csv"))
     assert calls == [("psi", 2.0, 240.0), ("mu", 0.6, 240.0), ("psi", 1.0, 960.0), ("mu", 0.0, 960.0)]
+
+
+def test_location_dump_files_have_the_reference_layout(tmp_path):
+    """HerosModel.locationDump (HerosModel.java:266-299): header lines, one row per location and hour, sub-location rows
+    for the indices 1 .. nSub-1 only."""
+    import gzip
+    city = scenario.City(1500, seed=9)
+    gen = scenario.ScheduleGenerator(city, 5)
+    st = gen.generate_day(np.zeros(city.n_persons, np.uint8))
+
+    class FakeEngine:
+        location_n_sub = city.loc_nsub
+        location_first_sub = np.concatenate([[0], np.cumsum(np.maximum(city.loc_nsub.astype(np.int64), 1))])
+
+        def sample_occupancy(self, times):
+            return occupancy_from_stays(st, self.location_first_sub, times)
+
+    dump = hb.LocationDump(FakeEngine(), city.loc_type, str(tmp_path))
+    assert dump.dump_hours(0.0, 24.0) == 24
+    dump.close()
+    with gzip.open(tmp_path / "locationNrPersons.csv.gz", "rt") as f:
+        loc_lines = f.read().splitlines()
+    with gzip.open(tmp_path / "sublocationNrPersons.csv.gz", "rt") as f:
+        sub_lines = f.read().splitlines()
+    assert loc_lines[0] == '"Time(h)","LocationNr","NrPersons"'
+    assert sub_lines[0] == '"Time(h)","LocationNr","SubLocationNr","NrPersons"'
+    assert len(loc_lines) == 1 + 24 * city.n_locations
+    assert len(sub_lines) == 1 + 24 * int(np.maximum(city.loc_nsub.astype(np.int64) - 1, 0).sum())
+    rows = np.array([[float(x) for x in line.split(",")] for line in loc_lines[1:]])
+    assert rows[0, 0] == 0.0 and loc_lines[1].startswith("0.0,") and loc_lines[-1].startswith("23.0,")
+    # everybody is somewhere at 03:00 (at home), fewer are inside a location at 08:30-ish travel times
+    at3 = rows[rows[:, 0] == 3.0]
+    assert at3[:, 2].sum() == city.n_persons
+    first = rows[rows[:, 0] == 0.0]
+    assert (np.diff(city.loc_type[first[:, 1].astype(int)].astype(int)) >= 0).all()      # grouped by location type
+    srow = np.array([[float(x) for x in line.split(",")] for line in sub_lines[1:]])
+    assert srow[:, 2].min() == 1 and (srow[:, 2] < city.loc_nsub[srow[:, 1].astype(int)]).all()
+    per_loc, per_sub = occupancy_from_stays(st, FakeEngine.location_first_sub, [12.0])
+    noon = srow[srow[:, 0] == 12.0]
+    pos = FakeEngine.location_first_sub[noon[:, 1].astype(int)] + noon[:, 2].astype(int)
+    np.testing.assert_array_equal(noon[:, 3].astype(np.int32), per_sub[0, pos])
