@@ -517,15 +517,17 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
         cur_tin[k] = ok[k] ? open_tin[person[k]] : 0.0;  // the open stay this one may close
     }
     unsigned late = 0, invalid = 0;
+    uint32_t pk[IPT], ticket[IPT];
+    bool good[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k)
     {
         const uint32_t i = base + k * TPB;
+        pk[k] = KEY_NONE; good[k] = false;
         if (i >= n) continue;
-        const bool good = ok[k] && sub[k] < max(nsub[k], 1);
-        const bool open = good && !(tout[k] < inf);
-        const bool positive = good && tout[k] > tin[k];
-        uint32_t pk = KEY_NONE;
+        good[k] = ok[k] && sub[k] < max(nsub[k], 1);
+        const bool open = good[k] && !(tout[k] < inf);
+        const bool positive = good[k] && tout[k] > tin[k];
         if (open)
         {
             open_key[person[k]] = key[k] + (uint32_t) sub[k];
@@ -534,18 +536,27 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
         }
         else if (positive)
         {
-            pk = key[k] + (uint32_t) sub[k];
+            pk[k] = key[k] + (uint32_t) sub[k];
             if (f64_bits(cur_tin[k]) == f64_bits(tin[k]))
                 atomicCAS((unsigned long long*) &open_tin[person[k]], (unsigned long long) f64_bits(tin[k]), OPEN_CLOSED);
             late += tin[k] < t_now;
         }
-        else if (!good)
+        else if (!good[k])
             ++invalid;
-        P.person[pool_base + i] = good ? (uint32_t) person[k] : 0u;
-        P.key[pool_base + i] = pk;
+    }
+    // the tickets of the thread's stays are taken together: IPT atomics in flight instead of one after the other
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) ticket[k] = pk[k] != KEY_NONE ? atomicAdd(&count[pk[k]], 1u) : KEY_NONE;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+    {
+        const uint32_t i = base + k * TPB;
+        if (i >= n) continue;
+        P.person[pool_base + i] = good[k] ? (uint32_t) person[k] : 0u;
+        P.key[pool_base + i] = pk[k];
         P.tin[pool_base + i] = tin[k];
         P.tout[pool_base + i] = tout[k];
-        P.rank[pool_base + i] = pk != KEY_NONE ? atomicAdd(&count[pk], 1u) : KEY_NONE;  // its ticket for the next window
+        P.rank[pool_base + i] = ticket[k];  // its ticket for the next window
     }
     late = __reduce_add_sync(0xffffffffu, late);
     invalid = __reduce_add_sync(0xffffffffu, invalid);

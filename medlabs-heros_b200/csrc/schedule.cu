@@ -221,16 +221,31 @@ __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uin
     const uint32_t n = min(stage.n, (uint32_t) STAGE_CAP);
     if (threadIdx.x == 0) s_base = n ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) n) : 0u;
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x)
+    // four staged stays per thread and round: their tickets are taken together (four atomics in flight)
+    for (uint32_t j0 = threadIdx.x; j0 < n; j0 += blockDim.x * 4)
     {
-        const uint32_t at = s_base + j;
-        if (at >= pool_cap) { atomicOr(&ctr->overflow, 32u); continue; }
-        const uint32_t key = stage.key[j];
-        P.person[pool_base + at] = stage.person[j];
-        P.key[pool_base + at] = key;
-        P.tin[pool_base + at] = stage.tin[j];
-        P.tout[pool_base + at] = stage.tout[j];
-        P.rank[pool_base + at] = atomicAdd(&count[key], 1u);  // its ticket for the next window
+        uint32_t key[4], ticket[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const uint32_t j = j0 + q * blockDim.x;
+            key[q] = (j < n && s_base + j < pool_cap) ? stage.key[j] : KEY_NONE;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ticket[q] = key[q] != KEY_NONE ? atomicAdd(&count[key[q]], 1u) : KEY_NONE;  // for the next window
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            const uint32_t j = j0 + q * blockDim.x;
+            if (j >= n) continue;
+            const uint32_t at = s_base + j;
+            if (at >= pool_cap) { atomicOr(&ctr->overflow, 32u); continue; }
+            P.person[pool_base + at] = stage.person[j];
+            P.key[pool_base + at] = key[q];
+            P.tin[pool_base + at] = stage.tin[j];
+            P.tout[pool_base + at] = stage.tout[j];
+            P.rank[pool_base + at] = ticket[q];
+        }
     }
 }
 
