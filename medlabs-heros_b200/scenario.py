@@ -488,7 +488,12 @@ class ScheduleGenerator:
         if loc == 1:  # Work / School; persons without one stay where they are
             wl = c.work_loc[idx].astype(np.int64)
             has = wl >= 0
-            shut = has & self._closed(idx, day_act, wl, c.loc_type[np.maximum(wl, 0)])
+            # a closure policy applies to the work / school locations of this city's own table (commuters into another
+            # tile, add_commuters, carry ids beyond it)
+            own = has & (wl < len(c.loc_type))
+            shut = np.zeros(len(idx), bool)
+            if ((self.frac_open < 1.0) | (self.frac_act < 1.0)).any():
+                shut = own & self._closed(idx, day_act, np.where(own, wl, 0), c.loc_type[np.where(own, wl, 0)])
             dl = np.where(has, wl, self.cur_loc[idx])
             ds = np.where(has, c.work_sub[idx].astype(np.int64), self.cur_sub[idx])
             return np.where(shut, home_l, dl), np.where(shut, home_s, ds)

@@ -314,3 +314,25 @@ def test_location_dump_files_have_the_reference_layout(tmp_path):
     noon = srow[srow[:, 0] == 12.0]
     pos = FakeEngine.location_first_sub[noon[:, 1].astype(int)] + noon[:, 2].astype(int)
     np.testing.assert_array_equal(noon[:, 3].astype(np.int32), per_sub[0, pos])
+
+
+def test_schedule_generator_with_commuters_into_another_tile():
+    """bench.py's multi-GPU setup: some workers of a tile work in the next tile (location codes beyond the own table);
+    the generator -- with and without a closure policy in force -- sends them there / keeps them home."""
+    city = scenario.City(3000, seed=21)
+    other = scenario.City(3000, seed=22, origin_m=(12000.0, 0.0))
+    n = city.add_commuters(other, 0.2, seed=5)
+    assert n > 0 and (city.work_loc >= city.n_locations).sum() == n
+    gen = scenario.ScheduleGenerator(city, 111)
+    phase = np.zeros(city.n_persons, np.uint8)
+    st = gen.generate_day(phase)
+    remote = st["loc"] >= city.n_locations
+    assert remote.sum() > 0.5 * n                                       # Monday: the commuters go to work
+    glob = city.global_location_ids(st["loc"], 1000000, 2000000)
+    assert (glob[remote] >= 2000000).all() and (glob[~remote] < 2000000).all()
+    gen.set_closure_policy(scenario.TYPE_ID["Workplace"], 0.0, 0.0, scenario.TYPE_ID["Accommodation"])
+    st = gen.generate_day(phase)                                        # own workplaces closed; the other tile's are not ours to close
+    ty = city.loc_type[st["loc"][st["loc"] < city.n_locations]]
+    opened_today = st["t_in"][st["loc"] < city.n_locations] >= 24.0
+    assert ((ty == scenario.TYPE_ID["Workplace"]) & opened_today).sum() == 0
+    assert ((st["loc"] >= city.n_locations) & (st["t_in"] >= 24.0)).sum() > 0.5 * n
