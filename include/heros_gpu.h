@@ -165,7 +165,10 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
                               int32_t* selected_out);
 /* Stays of persons in sub-locations: what Location.addPerson / removePerson of the medlabs engine record.  A stay
  * still open at submission time has t_out = +inf and is re-submitted, with the same t_in, once it is closed.  A stay
- * must be submitted before heros_step passes its t_in.  t_out <= t_in stays are ignored. */
+ * must be submitted before heros_step passes its t_in.  t_out <= t_in stays are ignored.  Entries whose person,
+ * location or sub-location id lies outside the tables, or whose times are NaN / negative, are rejected on the device:
+ * the next heros_step / heros_window_finish carries its window out without them and then returns HEROS_ERR_INVALID
+ * with their number in heros_last_error (once; the engine stays usable). */
 int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                             const int16_t* sublocation, const double* t_in, const double* t_out);
 /* same, from device memory of the engine's GPU (multi-GPU exchange buffers, device-side schedule generators).  The

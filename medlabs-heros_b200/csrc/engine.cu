@@ -972,6 +972,15 @@ int32_t window_finish(heros_handle h)
     }
     h->series_t.push_back(T1);
     for (int k = 0; k < 8; ++k) h->series_counts.push_back((int64_t) h->h_ctr->phase_counts[k]);
+    if (h->h_ctr->invalid_visits != h->invalid_reported)
+    {
+        // not silently: stays with ids outside the tables or NaN / negative times were left out of this window
+        char buf[200];
+        snprintf(buf, sizeof buf, "%u submitted stays were rejected (person, location or sub-location id out of range, or a NaN / negative time); the window ran without them",
+                 h->h_ctr->invalid_visits - h->invalid_reported);
+        h->invalid_reported = h->h_ctr->invalid_visits;
+        return fail(h, HEROS_ERR_INVALID, buf);
+    }
     return HEROS_OK;
 }
 

@@ -148,6 +148,7 @@ struct heros_engine
 
     // activity schedule (heros_set_schedule)
     bool have_schedule = false;
+    unsigned int invalid_reported = 0;  // of Counters::invalid_visits, already returned as an error
     DevBuf<double> m_times; DevBuf<int32_t> m_sub, m_loc;  // heros_sample_occupancy
     DevBuf<double2> s_closure; DevBuf<uint8_t> s_loc_type; std::vector<double> h_closure; bool closure_active = false;
     int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
