@@ -152,7 +152,6 @@ def test_generator_driven_city_with_phase_feedback():
 
 
 def test_seeding_is_the_keyed_bottom_k_and_respects_age_bounds():
-    import bench
     from heros_b200 import scenario
     from common import make_engine
     scn = Scenario(seed=2, n_persons=3000, n_households=900, n_workplaces=30, n_shops=5, days=1)

@@ -68,8 +68,6 @@ def test_device_schedule_with_closure_policies_equals_host_generator():
     """LocationPolicy rows (partial closure 0.2 / 0.5 of workplaces, 0.1 / 0.1 of retail, full closure of the schools,
     reopening) through heros_set_closure_policy and through the host-side generator: the same stays bit for bit, the
     same epidemic."""
-    import os
-    from common import GOLDEN
     city = scenario.City(6000, seed=11)
     props = load_props("distance")
     props["covidT_dist.alpha"] = "2.5"

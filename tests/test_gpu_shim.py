@@ -7,7 +7,6 @@ import pytest
 
 import heros_b200 as hb
 from common import load_props
-from heros_b200 import _lib
 from oracle import binding as ob
 from test_oracle import area as area_props_o, dist_props as dist_props_o
 

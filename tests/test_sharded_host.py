@@ -3,7 +3,6 @@ all-to-all over torch.distributed with the gloo backend, world_size 2."""
 import os
 import socket
 
-import pytest
 import torch
 import torch.multiprocessing as mp
 

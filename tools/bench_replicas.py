@@ -16,7 +16,6 @@ import os
 import sys
 import threading
 
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

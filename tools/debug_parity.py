@@ -1,13 +1,13 @@
 """Development aid: generator-driven city on GPU vs oracle, report the first differing infection events."""
-import argparse, json, os, sys, time
+import argparse
+import os
+import sys
+
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import heros_b200 as hb
-from heros_b200 import properties, scenario
-from oracle import binding as ob
-from common import oracle_props
-import bench
+from heros_b200 import scenario  # noqa: E402
+import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--persons", type=int, default=60000)

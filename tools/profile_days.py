@@ -60,9 +60,4 @@ for d in range(args.days):
         pc = eng.phase_clocks()
         print("  phase kcycles (rows = class 0..3):"); print((pc[:, :10] / 1e3).round(1))
         print("  slowest evaluation phase: n, n_ill, R, m_ev, key | sub-locations of the class"); print(pc[:, 10:16])
-if False:
-    np.set_printoptions(linewidth=200)
-    print("phase clocks (kcycles, max over groups) rows = class 0..3, cols = phase 0..9")
-    print((eng.phase_clocks()[:, :10] / 1e3).round(1))
-    print("slowest evaluation phase per class: n, n_ill, R, m_ev, key"); print(eng.phase_clocks()[:, 10:15])
 print("counts", eng.phase_counts())
