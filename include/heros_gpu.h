@@ -198,7 +198,10 @@ typedef struct heros_activity {
 /* pattern_start / pattern_count: [phase 8][role 16][day type 4 = Mon-Thu, Fri, Sat, Sun] -> slice of activities[];
  * choice table c = entries choice_start[c] .. choice_start[c+1]) of (choice_type, choice_cum = cumulative weights);
  * nearest / n_cand: [location][type], cand: [location][type][n_candidates] (-1 = none; only rows of home buildings are
- * read); work_sublocation: [person]. */
+ * read); work_sublocation: [person].  Like HerosModel.checkChangeActivityPattern (model/HerosModel.java:490-501), which
+ * throws when a person type has no name or the week pattern "0_<phase>_<role>" is missing, the call fails with
+ * HEROS_ERR_INVALID if a social role present in the population is outside 1..15 or lacks the pattern of a phase other
+ * than Dead. */
 int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_activity* activities,
                            const int32_t* pattern_start, const int32_t* pattern_count, int32_t n_choices,
                            const int32_t* choice_start, const int32_t* choice_type, const double* choice_cum,

@@ -280,6 +280,29 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
     if (max_acts > MAX_DAY_ACTIVITIES) return fail(h, HEROS_ERR_UNSUPPORTED, "more than 32 activities in a day pattern");
     for (int i = 0; i < n_activities; ++i)
         if (activities[i].choice >= n_choices) return fail(h, HEROS_ERR_INVALID, "choice table index out of range");
+    {
+        // HerosModel.checkChangeActivityPattern (model/HerosModel.java:490-501) throws when a person's type has no name or
+        // the week pattern "0_<phase>_<role>" does not exist: every role present in the population needs the (Monday)
+        // pattern of every phase but Dead
+        bool present[256] = {};
+        for (uint8_t r : h->h_role) present[r] = true;
+        for (int r = 0; r < 256; ++r)
+        {
+            if (!present[r]) continue;
+            char buf[160];
+            if (r < 1 || r > 15)
+            {
+                snprintf(buf, sizeof buf, "Person type name of social role %d not found", r);
+                return fail(h, HEROS_ERR_INVALID, buf);
+            }
+            for (int ph = 0; ph < 8; ++ph)
+                if (ph != (int) PH_D && pattern_count[(ph * 16 + r) * 4] <= 0)
+                {
+                    snprintf(buf, sizeof buf, "Week pattern key 0_<phase %d>_<role %d> not found in week pattern map", ph, r);
+                    return fail(h, HEROS_ERR_INVALID, buf);
+                }
+        }
+    }
     for (int i = 0; i < n_choices; ++i)
         if (choice_start[i + 1] <= choice_start[i]) return fail(h, HEROS_ERR_INVALID, "empty choice table");
     cudaSetDevice(h->cfg.device);

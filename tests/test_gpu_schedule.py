@@ -134,6 +134,13 @@ def test_schedule_errors():
     bad["pattern_count"][5] = 10 ** 6
     with pytest.raises(hb.HerosError):
         eng.set_schedule(bad, 1)
+    missing = dict(tables)
+    missing["pattern_count"] = tables["pattern_count"].copy()
+    role = int(city.role[0])
+    missing["pattern_count"][(3 * 16 + role) * 4: (3 * 16 + role) * 4 + 4] = 0   # no "0_Infected-Symptomatic_<role>"
+    with pytest.raises(hb.HerosError) as err:                                    # HerosModel.java:497-501
+        eng.set_schedule(missing, 1)
+    assert "Week pattern key" in str(err.value) and "not found in week pattern map" in str(err.value)
     eng.set_schedule(tables, 1)
     eng.advance_schedule(0)
     eng.step(24.0)
