@@ -6,7 +6,7 @@ transmission + progression -- and the outputs a user of the reference looks at: 
 
 usage: python examples/run_thehague.py [--days 60] [--seed 111] [--model distance|area] [--persons 553667] [--out DIR]
                                        [--location-policy FILE.csv] [--disease-policy FILE.csv]
-(policy files as in data/thehague/policies/: e.g. tests/golden/policies/HardLockdown_Realistic_10-40.csv)
+(policy files as in data/thehague/policies/ of the reference)
 """
 from __future__ import annotations
 

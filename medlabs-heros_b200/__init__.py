@@ -14,7 +14,7 @@ from .disease import (Covid19Progression, Covid19TransmissionArea, Covid19Transm
 from .engine import HerosEngine  # noqa: F401
 from .monitor import DiseaseMonitor, LocationDump, compartment_series  # noqa: F401
 from .policy import (DiseasePolicy, LocationPolicy, apply_location_policies, schedule_disease_policies,  # noqa: F401
-                     schedule_location_policies)
+                     schedule_location_policies, schedule_location_policy_rows)
 from . import sharded  # noqa: F401
 
 __version__ = "0.1.0"

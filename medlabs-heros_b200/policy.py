@@ -84,18 +84,24 @@ def apply_location_policies(model: HerosModel, time: float, target=None) -> int:
     return len(due)
 
 
-def schedule_location_policies(model: HerosModel, path: str, type_names: Optional[Sequence[str]] = None) -> List[LocationPolicy]:
-    """ConstructHerosModel.scheduleLocationPolicies (java :1145-1174): rows
+def schedule_location_policy_rows(model: HerosModel, rows, type_names: Optional[Sequence[str]] = None) -> List[LocationPolicy]:
+    """The loop of ConstructHerosModel.scheduleLocationPolicies (java :1157-1171) over rows
     ``Time(d),LocationType,FractionOpen,FractionActivities,AlternativeLocation,ReportAsLocation``; days -> hours."""
     out = []
-    with open(path, newline="") as f:
-        rows = list(csv.reader(f))
-    for row in rows[1:]:
+    for row in rows:
         if len(row) < 6:
             continue
         out.append(LocationPolicy(model, 24.0 * float(row[0]), row[1], float(row[2]), float(row[3]), row[4], row[5],
                                   type_names))
     return out
+
+
+def schedule_location_policies(model: HerosModel, path: str, type_names: Optional[Sequence[str]] = None) -> List[LocationPolicy]:
+    """ConstructHerosModel.scheduleLocationPolicies (java :1145-1174): the CSV file named by
+    ``policies.LocationPolicyFile`` (header line skipped)."""
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    return schedule_location_policy_rows(model, rows[1:], type_names)
 
 
 def schedule_disease_policies(model: HerosModel, path: str) -> List[DiseasePolicy]:

@@ -270,3 +270,21 @@ def occupancy_from_stays(st, first_sub, times):
         np.add.at(per_sub[j], pos[m], 1)
     per_loc = np.add.reduceat(per_sub, first_sub[:-1], axis=1).astype(np.int32)
     return per_loc, per_sub
+
+
+def policy_fixture(name: str):
+    """(header, rows) of one of the reference's location policy files (tests/golden/location_policies.json, made by
+    tools/make_policy_fixtures.py from data/thehague/policies/<name>.csv)."""
+    with open(os.path.join(GOLDEN, "location_policies.json")) as f:
+        entry = json.load(f)["files"][name]
+    return entry["header"], entry["rows"]
+
+
+def write_policy_csv(name: str, directory) -> str:
+    """the fixture written back as the CSV file ``policies.LocationPolicyFile`` would name"""
+    import csv
+    header, rows = policy_fixture(name)
+    path = os.path.join(str(directory), name + ".csv")
+    with open(path, "w", newline="") as f:
+        csv.writer(f).writerows([header] + rows)
+    return path

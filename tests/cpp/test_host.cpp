@@ -48,11 +48,11 @@ static bool close_rel(double a, double b, double rtol, double atol = 0.0) { retu
 // ---------------------------------------------------------------------------------------------------------------------
 static void test_parsers(const std::string& golden)
 {
-    const Parameters area = loadProperties(golden + "/alpha-area.properties");
+    const Parameters area = loadProperties(golden + "/params_alpha_area.properties");
     CHECK(area.at("generic.diseasePropertiesModel") == "area");
     CHECK(area.at("covidT_area.t_e_mode") == "3.4" && area.at("covidT_area.calculation_threshold") == "60");
     CHECK(area.count("! the seed of the shipped scenarios") == 0 && area.at("generic.Seed") == "111");
-    const Parameters dist = loadProperties(golden + "/alpha-distance.properties");
+    const Parameters dist = loadProperties(golden + "/params_alpha_distance.properties");
     CHECK(dist.at("covidT_dist.v_max") == "7.23" && dist.at("covidT_dist.psi") == "1.0");
     CHECK(throws<MedlabsException>([&] { loadProperties(golden + "/no-such-file.properties"); }));
 
@@ -82,7 +82,7 @@ static void test_parsers(const std::string& golden)
 
 static void test_errors_without_device(const std::string& golden)
 {
-    Parameters bad = loadProperties(golden + "/alpha-area.properties");
+    Parameters bad = loadProperties(golden + "/params_alpha_area.properties");
     bad["generic.diseasePropertiesModel"] = "sir";
     CHECK(throws<MedlabsException>([&] { HerosModel m(bad); }));  // ConstructHerosModel.java:137-141
 }
@@ -90,7 +90,7 @@ static void test_errors_without_device(const std::string& golden)
 // there is no CPU fallback: without a usable device the model cannot be constructed
 static void test_engine_refuses_to_start_without_a_gpu(const std::string& golden)
 {
-    const Parameters area = loadProperties(golden + "/alpha-area.properties");
+    const Parameters area = loadProperties(golden + "/params_alpha_area.properties");
     bool refused = false;
     try { HerosModel m(area); }
     catch (const EngineError& e) { refused = e.code == HEROS_ERR_CUDA; }
@@ -124,7 +124,7 @@ static void test_infect_people_known_answers(const std::string& golden)
 {
     // Covid19TransmissionArea.java:112-121: one infectious person at its peak and one susceptible for one hour in 10 m2,
     // p_B = 0.51, beta = sigma_T = 1  ->  p = 1 - exp(-0.051) = 0.0497 ("0.05 (5%)")
-    Parameters area = loadProperties(golden + "/alpha-area.properties");
+    Parameters area = loadProperties(golden + "/params_alpha_area.properties");
     area["covidT_area.contagiousness"] = "0.51";
     const double peak = 3.4 * 24.0;
     {
@@ -173,7 +173,7 @@ static void test_infect_people_known_answers(const std::string& golden)
         CHECK(std::fabs(m->getDiseaseTransmission()->infectPeople(0, {0, 1}, 1.0, nullptr, peak).pInfection - 0.0252) < 5e-4);
     }
     // the distance model against the oracle, before and after a DiseasePolicy (psi, mu)
-    Parameters dist = loadProperties(golden + "/alpha-distance.properties");
+    Parameters dist = loadProperties(golden + "/params_alpha_distance.properties");
     {
         auto m = one_room(dist, 6, 60.0f);
         set_state(*m, {0, 1, 2, 3, 4, 5},
@@ -227,7 +227,7 @@ struct Event { int32_t person, loc; int16_t sub; double time, p; };
 
 static void test_windowed_run_equals_the_oracle(const std::string& golden, const std::string& model_name, int trigger)
 {
-    Parameters props = loadProperties(golden + "/alpha-" + model_name + ".properties");
+    Parameters props = loadProperties(golden + "/params_alpha_" + model_name + ".properties");
     if (model_name == "area") props["covidT_area.contagiousness"] = "30.0";
     else props["covidT_dist.alpha"] = "4.0";
     const int n_home = 40, n_work = 10, n_shop = 3, n_loc = n_home + n_work + n_shop, N = 640, days = 6;

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import heros_b200 as hb
-from common import GOLDEN, ROOT, load_props, occupancy_from_stays
+from common import GOLDEN, ROOT, load_props, occupancy_from_stays, write_policy_csv
 from heros_b200 import _lib, properties, scenario
 
 
@@ -201,14 +201,14 @@ class _QueueModel:
     """what LocationPolicy needs of the model on a box without a GPU: somewhere to queue"""
 
 
-def test_location_policy_files_close_and_reopen_location_types(capsys):
-    """data/thehague/policies/HardLockdown_Realistic_10-40.csv (tests/golden/policies/, tools/make_policy_fixtures.py)
+def test_location_policy_files_close_and_reopen_location_types(capsys, tmp_path):
+    """data/thehague/policies/HardLockdown_Realistic_10-40.csv (tests/golden/location_policies.json, tools/make_policy_fixtures.py)
     through the LocationPolicy mirror into the host-side schedule: closed types are not visited from day 10 on, the
     partially open ones keep a subset of their locations and of their activities, everything is back on day 40."""
     city = scenario.City(4000, seed=5)
     T = scenario.TYPE_ID
     model = _QueueModel()
-    pol = hb.schedule_location_policies(model, os.path.join(GOLDEN, "policies", "HardLockdown_Realistic_10-40.csv"))
+    pol = hb.schedule_location_policies(model, write_policy_csv("HardLockdown_Realistic_10-40", tmp_path))
     assert len(pol) == 26 and all(p.scheduled for p in pol)
     assert pol[0].time == 240.0 and pol[0].locationType == T["Workplace"] and pol[0].fractionOpen == 0.2
     assert pol[0].alternativeLocationType == T["Accommodation"] and pol[0].reportAsLocationName == "WorkToHome"
@@ -260,8 +260,14 @@ def test_location_policy_files_close_and_reopen_location_types(capsys):
         gen.set_closure_policy(T["Retail"], 1.5, 0.5, T["Accommodation"])
 
 
-def test_disease_policy_file_reader():
+def test_disease_policy_file_reader(tmp_path):
+    import csv
     calls = []
+    with open(os.path.join(GOLDEN, "policy_masking_distance_10_40.json")) as f:   # data/thehague/policies/MaskingDistance_10-40.csv
+        fixture = json.load(f)
+    path = str(tmp_path / "MaskingDistance_10-40.csv")
+    with open(path, "w", newline="") as f:
+        csv.writer(f).writerows([fixture["header"]] + fixture["rows"])
 
     class Transmission:
         def setParameter(self, name, value, at_time=None):
@@ -271,7 +277,7 @@ def test_disease_policy_file_reader():
         def getDiseaseTransmission(self):
             return Transmission()
 
-    hb.schedule_disease_policies(Model(), os.path.join(GOLDEN, "policies", "MaskingDistance_10-40.csv"))
+    hb.schedule_disease_policies(Model(), path)
     assert calls == [("psi", 2.0, 240.0), ("mu", 0.6, 240.0), ("psi", 1.0, 960.0), ("mu", 0.0, 960.0)]
 
 

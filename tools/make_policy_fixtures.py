@@ -1,19 +1,21 @@
-"""Copies the rows of the reference's policy files the tests use (data, not code) into tests/golden/policies/ so that
-they travel to the GPU box: data/thehague/policies/{HardLockdown_Realistic_10-40,HardLockdown_10-40,
-HardLockdown_20,MaskingDistance_10-40}.csv.  Run in the container that has /root/reference."""
+"""Collects the rows of the reference's policy files the tests and tools use (data, not code) into
+tests/golden/location_policies.json so that they travel to the GPU box: data/thehague/policies/
+{HardLockdown_Realistic_10-40, HardLockdown_10-40, HardLockdown_20}.csv (location policies; the disease policy
+MaskingDistance_10-40.csv is tests/golden/policy_masking_distance_10_40.json, tools/make_golden_params.py).
+Run in the container that has /root/reference."""
 import csv
+import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/data/thehague/policies"
-DST = os.path.join(ROOT, "tests", "golden", "policies")
 
 if __name__ == "__main__":
-    os.makedirs(DST, exist_ok=True)
-    for name in ("HardLockdown_Realistic_10-40.csv", "HardLockdown_10-40.csv", "HardLockdown_20.csv",
-                 "MaskingDistance_10-40.csv"):
-        with open(os.path.join(SRC, name), newline="") as f:
+    out = {"source": "data/thehague/policies/<name>.csv of the reference", "files": {}}
+    for name in ("HardLockdown_Realistic_10-40", "HardLockdown_10-40", "HardLockdown_20"):
+        with open(os.path.join(SRC, name + ".csv"), newline="") as f:
             rows = [r for r in csv.reader(f) if r]
-        with open(os.path.join(DST, name), "w", newline="") as f:
-            csv.writer(f, lineterminator="\n").writerows(rows)
+        out["files"][name] = {"header": rows[0], "rows": rows[1:]}
         print(name, len(rows) - 1, "policy rows")
+    with open(os.path.join(ROOT, "tests", "golden", "location_policies.json"), "w") as f:
+        json.dump(out, f, indent=1)

@@ -10,7 +10,7 @@ The population is the synthetic Hague of scenario.City (the real people / locati
 tree), so this is a comparison of shapes and orders of magnitude, not a parity test; it is what a calibrated
 population would be judged with (32-seed envelope against the reference's seeds).
 
-usage: python tools/seed_envelope.py [--seeds 32] [--days 120] [--model area|distance] [--policy FILE|none]
+usage: python tools/seed_envelope.py [--seeds 32] [--days 120] [--model area|distance] [--policy FILE.csv|NAME|none]
                                      [--persons 553667] [--out gpurun_out/seed_envelope.json]
 """
 from __future__ import annotations
@@ -40,7 +40,8 @@ def main():
     ap.add_argument("--first-seed", type=int, default=111)
     ap.add_argument("--days", type=int, default=120)
     ap.add_argument("--model", default="area", choices=["area", "distance"])
-    ap.add_argument("--policy", default=os.path.join(ROOT, "tests", "golden", "policies", "HardLockdown_20.csv"))
+    ap.add_argument("--policy", default="HardLockdown_20",
+                    help="a .csv file (policies.LocationPolicyFile), a name in tests/golden/location_policies.json, or none")
     ap.add_argument("--persons", type=int, default=553667)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "seed_envelope.json"))
     args = ap.parse_args()
@@ -53,6 +54,10 @@ def main():
     props["generic.diseasePropertiesModel"] = args.model
     with open(os.path.join(ROOT, "tests", "golden", "seed_comparison.json")) as f:
         golden = json.load(f)["seeds"]
+    policy_rows = []
+    if args.policy and args.policy != "none" and not args.policy.endswith(".csv"):
+        with open(os.path.join(ROOT, "tests", "golden", "location_policies.json")) as f:
+            policy_rows = json.load(f)["files"][args.policy]["rows"]
     t = time.time()
     city = scenario.City(args.persons)
     tables = scenario.compile_schedule(city)
@@ -65,8 +70,10 @@ def main():
         hb.construct_disease_model(model)
         model.engine.seed_infections(100)
         model.engine.set_schedule(tables, seed)
-        if args.policy and args.policy != "none":
+        if args.policy.endswith(".csv"):
             hb.schedule_location_policies(model, args.policy)
+        elif args.policy and args.policy != "none":
+            hb.schedule_location_policy_rows(model, policy_rows)
         daily = [model.engine.phase_counts().tolist()]
         for day in range(args.days):
             hb.apply_location_policies(model, 24.0 * day)
