@@ -5,7 +5,8 @@ transmission + progression -- and the outputs a user of the reference looks at: 
 (0.5 h samples, golden-spreadsheet column layout) as CSV and the infection event list.
 
 usage: python examples/run_thehague.py [--days 60] [--seed 111] [--model distance|area] [--persons 553667] [--out DIR]
-                                       [--location-policy FILE.csv] [--disease-policy FILE.csv]
+                                       [--location-policy FILE.csv|NAME] [--disease-policy FILE.csv] [--helsinki]
+                                       [--summary FILE.json]
 (policy files as in data/thehague/policies/ of the reference)
 """
 from __future__ import annotations
@@ -29,7 +30,13 @@ def main():
     ap.add_argument("--persons", type=int, default=553667)
     ap.add_argument("--infected", type=int, default=100)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "thehague"))
-    ap.add_argument("--location-policy", default="", help="policies.LocationPolicyFile (ConstructHerosModel.java:1145)")
+    ap.add_argument("--location-policy", default="",
+                    help="policies.LocationPolicyFile (ConstructHerosModel.java:1145): a .csv file, or the name of one of the "
+                         "reference's files kept in tests/golden/location_policies.json (e.g. HardLockdown_10-40)")
+    ap.add_argument("--helsinki", action="store_true",
+                    help="BASELINE.json configs[1]: the real Helsinki location table (tests/golden/helsinki_locations.npz = "
+                         "data/helsinki/locations.csv.gz) under a synthetic population instead of the synthetic Hague")
+    ap.add_argument("--summary", default="", help="write a JSON summary (daily compartment counts, timings) here")
     ap.add_argument("--disease-policy", default="", help="policies.DiseasePolicyFile (ConstructHerosModel.java:1179)")
     args = ap.parse_args()
 
@@ -40,26 +47,36 @@ def main():
         props = json.load(f)["properties"]
     props["generic.diseasePropertiesModel"] = args.model
     t = time.time()
-    city = scenario.City(args.persons)
+    if args.helsinki:
+        import numpy as np
+        table = dict(np.load(os.path.join(ROOT, "tests", "golden", "helsinki_locations.npz")))
+        city = scenario.City(args.persons, location_table=table)
+    else:
+        city = scenario.City(args.persons)
     model = hb.HerosModel(props, seed=args.seed)                       # parameter map + engine
     city.install(model.engine)
     progression, transmission = hb.construct_disease_model(model)       # ConstructHerosModel.java:136-144
     monitor = hb.DiseaseMonitor(model, progression, 0.5)                # ConstructHerosModel.java:145
     model.engine.seed_infections(args.infected)                          # ConstructHerosModel.java:1109-1128
     model.engine.set_schedule(scenario.compile_schedule(city), args.seed)
-    if args.location_policy:
+    if args.location_policy.endswith(".csv"):
         hb.schedule_location_policies(model, args.location_policy)
+    elif args.location_policy:
+        with open(os.path.join(ROOT, "tests", "golden", "location_policies.json")) as f:
+            hb.schedule_location_policy_rows(model, json.load(f)["files"][args.location_policy]["rows"])
     if args.disease_policy:
         hb.schedule_disease_policies(model, args.disease_policy)
     print(f"city of {city.n_persons} persons, {city.n_locations} locations built in {time.time() - t:.1f} s")
 
     t = time.time()
     gpu_ms = 0.0
+    daily = [model.engine.phase_counts().tolist()]
     for day in range(args.days):
         hb.apply_location_policies(model, 24.0 * day)
         model.engine.advance_schedule(day)
         stats = model.engine.step(24.0 * (day + 1))
         gpu_ms += stats["gpu_ms"]
+        daily.append(model.engine.phase_counts().tolist())
         if day % 10 == 9 or day == args.days - 1:
             c = model.engine.phase_counts()
             print(f"day {day + 1:3d}: S {c[0]}  E {c[1]}  I(A) {c[2]}  I(S) {c[3]}  H {c[4]}  ICU {c[5]}  D {c[6]}  R {c[7]}")
@@ -67,6 +84,15 @@ def main():
     print(f"{args.days} simulated days in {wall:.2f} s wall ({gpu_ms:.1f} ms of window kernels): "
           f"{city.n_persons * 24.0 * args.days / wall:.3g} person-hours/s")
 
+    if args.summary:
+        os.makedirs(os.path.dirname(os.path.abspath(args.summary)), exist_ok=True)
+        with open(args.summary, "w") as f:
+            json.dump(dict(city="helsinki locations + synthetic persons" if args.helsinki else "synthetic Hague",
+                           persons=city.n_persons, locations=city.n_locations, model=args.model, seed=args.seed,
+                           days=args.days, location_policy=args.location_policy, disease_policy=args.disease_policy,
+                           wall_s=wall, window_kernel_ms=gpu_ms,
+                           person_hours_per_s=city.n_persons * 24.0 * args.days / wall,
+                           header=["S", "E", "Ia", "Is", "H", "ICU", "D", "R"], daily_counts=daily), f)
     os.makedirs(args.out, exist_ok=True)
     monitor.write_csv(os.path.join(args.out, f"compartments_seed{args.seed}.csv"))
     inf = model.engine.infections()
