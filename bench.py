@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--preroll", type=int, default=7, help="untimed simulated days before the warm-up steps")
     ap.add_argument("--model", default="distance", choices=["area", "distance"])
     ap.add_argument("--trigger", default="exit", choices=["exit", "both"])
-    ap.add_argument("--cpu-days", type=int, default=6, help="days of the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-days", type=int, default=14, help="days of the bounded cpu_baseline sample (about 12 s of CPU work)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: kernels write into the peers' memory over NVLink (CUDA IPC), or NCCL all-to-alls")
     ap.add_argument("--commute", type=float, default=0.05,
