@@ -1,11 +1,13 @@
 """The CPU oracle against everything that can pin it without the (non-runnable) JVM reference:
 Random123 known-answer vectors, libm, the worked example of the reference's Javadoc, hand-derived boundary cases."""
+import json
 import math
+import os
 
 import numpy as np
 import pytest
 
-from common import load_props, oracle_props
+from common import GOLDEN, load_props, oracle_props
 from oracle import binding as ob
 
 S, E, IA, IS, H, ICU, D, R = range(8)
@@ -296,11 +298,8 @@ def test_driver_contract_against_the_reference_epidemic_curves():
         histogram of new exposures is empty there), while the bin of midnight itself is not (activities that end at
         24:00).
     The same three properties must hold for the oracle driven by the schedule generator on a synthetic city."""
-    import json
-    import os
     import heros_b200 as hb
     from heros_b200 import scenario
-    from common import GOLDEN
     with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
         gold = json.load(f)
     assert tuple(gold["header"]) == ("Time(h)",) + hb.PHASE_NAMES   # column order = phase registration order
@@ -336,3 +335,63 @@ def test_driver_contract_against_the_reference_epidemic_curves():
     assert len(became_infectious) == len(seeds) and 60.0 <= became_infectious.min() and became_infectious.max() <= 91.2
     hour = inf["time"] % 24.0
     assert not ((hour > 0.0) & (hour <= 6.0)).any()             # nothing happens while everybody sleeps
+
+
+def test_progression_follows_the_reference_transition_table():
+    """Covid19Progression.changeDiseasePhase (java :208-346) with the alpha parameters: only the transitions of the
+    reference's table occur, every sojourn time lies inside the support of its Triangular distribution (days -> hours),
+    and the branch frequencies match covidP.Fraction* of the person's age band (alpha-area.properties:47-108)."""
+    props = load_props("area")
+    _, _, prog = oracle_props(props)
+    n_per_age = 6000
+    ages = np.repeat([10, 35, 65, 75, 85], n_per_age).astype(np.int8)
+    n = len(ages)
+    sim = ob.Sim(ob.MODEL_AREA, ob.TRIGGER_EXIT_ONLY, 2024)
+    sim.set_area(oracle_props(props)[0])
+    sim.set_prog(prog)
+    sim.set_location_types([1], [1.0])
+    sim.set_locations([0], [1], [10.0])
+    sim.set_persons(ages, (np.arange(n) % 2).astype(np.uint8))
+    sim.expose(np.arange(n), np.zeros(n))
+    sim.run(24.0 * 120)
+    tr = sim.transitions()
+    order = np.lexsort((tr["time"], tr["person"]))
+    person, phase, time = tr["person"][order], tr["phase"][order], tr["time"][order]
+    same = person[1:] == person[:-1]
+    frm, to, dt = phase[:-1][same], phase[1:][same], (time[1:] - time[:-1])[same]
+    who = person[1:][same]
+    allowed = {(E, IA): (2.5, 3.8), (E, IS): (2.5, 3.8), (IA, R): (12, 20), (IS, H): (7, 11), (IS, R): (12, 20),
+               (H, ICU): (1, 5), (H, D): (1, 5), (H, R): (11, 15), (ICU, D): (2, 6), (ICU, R): (28, 32)}
+    seen = set(zip(frm.tolist(), to.tolist()))
+    assert seen <= set(allowed), seen - set(allowed)
+    assert (H, D) not in seen                                   # FractionHospitalizedToDead = 0.0
+    for (a, b), (lo, hi) in allowed.items():
+        m = (frm == a) & (to == b)
+        if m.any():
+            assert dt[m].min() >= 24.0 * lo - 1e-9 and dt[m].max() <= 24.0 * hi + 1e-9, (a, b, dt[m].min(), dt[m].max())
+    first = phase[np.r_[True, ~same]]
+    assert (first == E).all() and len(first) == n               # everybody's trajectory starts with Exposed at t = 0
+    # everybody has reached an absorbing phase after 120 days
+    c = sim.phase_counts()
+    assert c[R] + c[D] == n
+
+    def frac(a, b, sel):
+        src = (frm == a) & sel[who]
+        return ((to == b) & src).sum() / max(src.sum(), 1), src.sum()
+
+    everyone = np.ones(n, bool)
+    f, k = frac(E, IA, everyone)
+    assert abs(f - 0.46) < 4 * np.sqrt(0.46 * 0.54 / k)        # FractionAsymptomatic
+    want_s2h = {10: 0.02153, 35: 0.05044, 65: 0.44038, 75: 0.60867, 85: 0.32301}
+    want_h2icu = {10: 0.00152, 35: 0.00921, 65: 0.14674, 75: 0.15508, 85: 0.01647}
+    want_icu2d = {10: 0.0, 35: 0.0, 65: 0.08393, 75: 0.39731, 85: 0.63002}
+    for age in (10, 35, 65, 75, 85):
+        sel = ages == age
+        for (a, b, want) in ((IS, H, want_s2h[age]), (H, ICU, want_h2icu[age]), (ICU, D, want_icu2d[age])):
+            f, k = frac(a, b, sel)
+            if k >= 30:
+                assert abs(f - want) < 4.5 * np.sqrt(max(want * (1 - want), 1e-4) / k) + 1e-9, (age, a, b, f, want, k)
+    # the golden curves show the same split: on day 10 of seed 111 I(A) : I(S) = 239 : 266 (0.473 asymptomatic)
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as fjson:
+        day10 = json.load(fjson)["seeds"]["111"]["daily_counts"][10]
+    assert abs(day10[2] / (day10[2] + day10[3]) - 0.46) < 0.05
