@@ -345,6 +345,18 @@ int32_t heros_get_stream(heros_handle h, void** stream_out);
 /* HEROS_FLAG_PHASE_CLOCKS: clocks[class * 16 + phase], 64 entries, of the last window */
 int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks);
 
+/* ---- checkpoint / resume.  The blob holds the dynamic state of an idle engine (no window in
+ *      progress): agent words, next transitions, open stays, lastCalculation of every sub-location, the pending stays
+ *      with their tickets, both event logs, the counters and compartment series, the parameter-change schedule
+ *      (heros_set_parameter) and the closure table (heros_set_closure_policy), the engine time.  To resume, create an
+ *      engine with the same model and seed, repeat the static inputs (heros_set_location_types / _locations / _persons,
+ *      the transmission and progression parameters, heros_set_schedule if it is used) and call heros_snapshot_load: the
+ *      run then continues bit for bit as the original would have.  Engines connected to a peer exchange are refused
+ *      (HEROS_ERR_UNSUPPORTED); a blob taken with other tables, model or seed is refused (HEROS_ERR_INVALID). ---- */
+int32_t heros_snapshot_size(heros_handle h, int64_t* bytes_out);
+int32_t heros_snapshot_save(heros_handle h, int64_t capacity, void* blob, int64_t* bytes_out);
+int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob);
+
 /* ---- 1:1 shim of DiseaseTransmission.infectPeople(location, personsInSublocation, duration)
  *      (Covid19TransmissionArea.java:133-248 / Covid19TransmissionDistance.java:115-248), evaluated on the GPU against
  *      the engine's current agent state with simulator time `now`.  all_persons = location.getAllPersonIds() (only

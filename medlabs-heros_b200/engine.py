@@ -159,6 +159,19 @@ class HerosEngine:
         self._check(self._lib.heros_set_closure_policy(self._h, int(location_type), float(fraction_open),
                                                        float(fraction_activities), int(alternative_type)))
 
+    def snapshot(self) -> np.ndarray:
+        """The dynamic state of the idle engine as one uint8 array (heros_snapshot_save)."""
+        n = C.c_int64(0)
+        self._check(self._lib.heros_snapshot_size(self._h, C.byref(n)))
+        blob = np.zeros(n.value, np.uint8)
+        self._check(self._lib.heros_snapshot_save(self._h, n.value, _p(blob), C.byref(n)))
+        return blob[:n.value]
+
+    def restore(self, blob) -> None:
+        """heros_snapshot_load into an engine that has been given the same static inputs."""
+        b = np.ascontiguousarray(np.frombuffer(blob, np.uint8) if isinstance(blob, (bytes, bytearray)) else blob, np.uint8)
+        self._check(self._lib.heros_snapshot_load(self._h, len(b), _p(b)))
+
     def sample_occupancy(self, times, locations: bool = True, sublocations: bool = True):
         """Persons per location ``[len(times), n_locations]`` and per sub-location ``[len(times), n_sublocations]``
         (location-major, see ``location_first_sub``) at the given times, from the stays held for the coming window
