@@ -1,0 +1,155 @@
+"""Readers for the input files of a reference scenario (``data/<city>/``), producing the tables the engine takes.
+
+The Java host keeps its own loaders (factory/ConstructHerosModel.java); these are the same rules for a host without a
+JVM, so that the examples and tools can be pointed at a ``data/<city>`` directory:
+
+  * ``locationtypes.csv``          -> ``properties.load_location_types``            (java :230-269)
+  * ``locations.csv[.gz]``         -> ``read_locations``                             (java :300-395)
+  * ``people.csv[.gz]``            -> ``read_people``                                (java :450-758)
+  * both                            -> ``load_city`` = a ``scenario.City`` with real tables (candidate / nearest tables of
+                                      the locators are built as for the synthetic city)
+
+Rows the reference rejects are rejected here with the same message on stderr and skipped, not raised (java prints and
+``continue``s).  Ids: the engine wants dense indices; location and person ids of the files are kept beside them
+(``location_id`` / ``person_id``) for the outputs.
+"""
+from __future__ import annotations
+
+import csv
+import gzip
+import sys
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import scenario
+
+STUDENT_SCHOOL = {2: "kindergarten", 3: "primaryschool", 4: "secondaryschool", 5: "college", 6: "university"}
+ROLE_LABEL = {7: "Worker", 10: "WeekendWorker", 11: "EssentialWorker", 12: "WorkerSatelliteToCity",
+              13: "WorkerCityToSatellite", 14: "WorkerSatelliteToSatellite", 15: "WorkerCountryToCity"}
+
+
+def _open(path: str):
+    return gzip.open(path, "rt", newline="") if path.endswith(".gz") else open(path, newline="")
+
+
+def _columns(header: Sequence[str], wanted: Sequence[str], what: str) -> Dict[str, int]:
+    """case-insensitive header lookup; all columns must be there (java :317-348, :464-493)"""
+    low = [h.strip().lower() for h in header]
+    missing = [w for w in wanted if w not in low]
+    if missing:
+        raise ValueError(f"{what} csv-file header row did not contain all column headers\n{list(header)}")
+    return {w: low.index(w) for w in wanted}
+
+
+def read_locations(path: str, type_names: Optional[Sequence[str]] = None) -> Dict[str, np.ndarray]:
+    """``locations.csv[.gz]``: columns location_id, nb_sublocations, location_category, lat, lon, area (java :329-348);
+    ``area`` is the area of one sub-location, the total surface is ``area * nb_sublocations`` as float (java :381).
+    Rows whose category is not a location type are reported and skipped.  Returns the columns ``scenario.City`` takes
+    (type, nsub, area_per_sub, lat, lon) plus ``location_id``; rows keep the order of the file."""
+    names = list(type_names if type_names is not None else scenario.TYPE_NAMES)
+    type_id = {n: i for i, n in enumerate(names)}
+    with _open(path) as f:
+        rows = list(csv.reader(f))
+    col = _columns(rows[0], ("location_id", "nb_sublocations", "location_category", "lat", "lon", "area"), "Location")
+    ids, types, nsub, area, lat, lon = [], [], [], [], [], []
+    for line, r in enumerate(rows[1:], start=2):
+        if not r:
+            continue
+        cat = r[col["location_category"]]
+        if cat not in type_id:
+            print(f"Location type {cat} not found on line {line}\n{r}", file=sys.stderr)
+            continue
+        ids.append(int(r[col["location_id"]]))
+        types.append(type_id[cat])
+        nsub.append(int(float(r[col["nb_sublocations"]])))
+        area.append(float(r[col["area"]]))
+        lat.append(float(r[col["lat"]]))
+        lon.append(float(r[col["lon"]]))
+    return dict(location_id=np.array(ids, np.int64), type=np.array(types, np.uint8), nsub=np.array(nsub, np.int16),
+                area_per_sub=np.array(area, np.float32), lat=np.array(lat, np.float32), lon=np.array(lon, np.float32))
+
+
+def read_people(path: str, locations: Dict[str, np.ndarray], type_names: Optional[Sequence[str]] = None,
+                seed: int = 111) -> Dict[str, np.ndarray]:
+    """``people.csv[.gz]``: columns person_id, household_id, age, home_id, workplace_id, social_role (java :464-493),
+    all parsed through double as the reference does (java :499-504).
+
+    Rules of the reference loader, in its order: an age outside 0..120 is reported (the person is kept, java :506-510);
+    a home that is not in the location map drops the person (java :514-520); the home sub-location index is the order
+    of first appearance of the household id within its home building, reported when it exceeds the building's number
+    of sub-locations (java :531-552); students (roles 2-6) need a school in the map (java :554-562) and of the matching
+    type for roles 2, 3, 5, 6 (java :572-640; the check of role 4 is the same with "secondaryschool"); roles 7 and 10-15
+    need a work location in the map (java :642-745); unknown roles are reported and dropped.  The gender is drawn
+    ``U01 < 0.5`` per person (java :513) -- here a Philox number keyed by (seed, person index) instead of the model's
+    Mersenne Twister stream."""
+    names = [n.lower() for n in (type_names if type_names is not None else scenario.TYPE_NAMES)]
+    index_of = {int(i): k for k, i in enumerate(locations["location_id"])}
+    loc_type, loc_nsub = locations["type"], locations["nsub"]
+    with _open(path) as f:
+        rows = list(csv.reader(f))
+    col = _columns(rows[0], ("person_id", "household_id", "age", "home_id", "workplace_id", "social_role"), "Person")
+    out = {k: [] for k in ("person_id", "household", "age", "role", "home_loc", "home_sub", "work_loc")}
+    household_sub: Dict[int, Dict[int, int]] = {}
+    for line, r in enumerate(rows[1:], start=2):
+        if not r:
+            continue
+        pid = int(float(r[col["person_id"]]))
+        hh = int(float(r[col["household_id"]]))
+        age = int(float(r[col["age"]]))
+        home = int(float(r[col["home_id"]]))
+        w = r[col["workplace_id"]].strip()
+        work = -1 if w == "" else int(float(w))
+        role = int(float(r[col["social_role"]]))
+        if age < 0 or age > 120:
+            print(f"Person {pid} has age {age} on row {line}\n{r}", file=sys.stderr)
+        if home not in index_of:
+            print(f"homeId {home} not found in the location map on line {line}\n{r}", file=sys.stderr)
+            continue
+        subs = household_sub.setdefault(home, {})
+        if hh in subs:
+            home_sub = subs[hh]
+        else:
+            home_sub = len(subs)
+            if home_sub + 1 > int(loc_nsub[index_of[home]]):
+                print(f"Person {pid}. The homeId {home} with householdId {hh} has more sublocations ({home_sub + 1}) "
+                      f"than defined. Record on row {line}\n{r}", file=sys.stderr)
+            subs[hh] = home_sub
+        if 2 <= role <= 6:
+            if work == -1 or work not in index_of:
+                print(f"No school location [{work}] for Student on line {line}\n{r}", file=sys.stderr)
+                continue
+            if names[int(loc_type[index_of[work]])] != STUDENT_SCHOOL[role]:
+                print(f"workSchoolId {work} not a {STUDENT_SCHOOL[role]} in the location map on line {line}\n{r}",
+                      file=sys.stderr)
+                continue
+        elif role in ROLE_LABEL:
+            if work == -1 or work not in index_of:
+                print(f"No work location [{work}] for {ROLE_LABEL[role]} on line {line}\n{r}", file=sys.stderr)
+                continue
+        elif role not in (1, 8, 9):
+            print(f"social role {role} not recognized on line {line}\n{r}", file=sys.stderr)
+            continue
+        out["person_id"].append(pid); out["household"].append(hh); out["age"].append(min(max(age, -128), 127))
+        out["role"].append(role); out["home_loc"].append(index_of[home]); out["home_sub"].append(home_sub)
+        out["work_loc"].append(index_of[work] if work in index_of else -1)
+    n = len(out["person_id"])
+    x = scenario.philox4x32_10(np.arange(n), 0, 4, scenario.TAG_SCHEDULE, seed & 0xFFFFFFFF, seed >> 32)[0]
+    female = (x.astype(np.float64) * 2.0 ** -32 < 0.5).astype(np.uint8)
+    return dict(person_id=np.array(out["person_id"], np.int64), household=np.array(out["household"], np.int64),
+                age=np.array(out["age"], np.int8), role=np.array(out["role"], np.uint8),
+                home_loc=np.array(out["home_loc"], np.int32), home_sub=np.array(out["home_sub"], np.int16),
+                work_loc=np.array(out["work_loc"], np.int32), female=female)
+
+
+def load_city(locations_path: str, people_path: str, type_names: Optional[Sequence[str]] = None, seed: int = 111,
+              n_random_candidates: int = 8) -> "scenario.City":
+    """A ``scenario.City`` over the real tables of ``data/<city>/locations/locations.csv.gz`` and
+    ``data/<city>/people/people.csv.gz``: ``city.install(engine)`` and ``scenario.compile_schedule(city)`` then work as
+    for the synthetic city; ``city.location_id`` / ``city.person_id`` map engine indices back to the ids of the files."""
+    locations = read_locations(locations_path, type_names)
+    people = read_people(people_path, locations, type_names, seed)
+    city = scenario.City(len(people["age"]), seed=seed, n_random_candidates=n_random_candidates,
+                         location_table=locations, person_table=people)
+    city.location_id, city.person_id = locations["location_id"], people["person_id"]
+    return city

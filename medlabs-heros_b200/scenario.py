@@ -89,10 +89,17 @@ class City:
 
     def __init__(self, n_persons: int, seed: int = 20240807, n_locations: Optional[int] = None,
                  box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8,
-                 location_table: Optional[Dict[str, np.ndarray]] = None):
+                 location_table: Optional[Dict[str, np.ndarray]] = None,
+                 person_table: Optional[Dict[str, np.ndarray]] = None):
         """``location_table``: a real location table (type, nsub, area_per_sub, lat, lon -- e.g. the Helsinki fixture
-        of tests/golden) instead of the synthetic one; the population is synthetic either way."""
+        of tests/golden, or ``loaders.read_locations``) instead of the synthetic one.  ``person_table``: real persons
+        (age, role, home_loc, home_sub, work_loc as location indices, optionally female and work_sub --
+        ``loaders.read_people``) instead of the synthetic population; needs ``location_table``."""
         rng = np.random.default_rng(seed)
+        if person_table is not None:
+            if location_table is None:
+                raise ValueError("a person table refers to the rows of a location table")
+            n_persons = len(person_table["age"])
         self.n_persons = int(n_persons)
         self.type_infect_sub = TYPE_INFECT_SUB.copy()
         self.type_correction = TYPE_CORRECTION.copy()
@@ -148,7 +155,65 @@ class City:
             np.add.at(loc_nsub, hh_building, 1)
             loc_nsub[acc] = np.maximum(loc_nsub[acc], 1)
 
-        # persons: ages, roles, households
+        if person_table is not None:
+            age = np.asarray(person_table["age"], np.int64)
+            role = np.asarray(person_table["role"], np.int64)
+            home_loc = np.asarray(person_table["home_loc"], np.int64)
+            home_sub = np.asarray(person_table["home_sub"], np.int64)
+            work_loc = np.asarray(person_table["work_loc"], np.int64)
+            self.household = np.asarray(person_table.get("household", np.zeros(n_persons)), np.int32)
+            if "work_sub" in person_table:
+                work_sub = np.asarray(person_table["work_sub"], np.int64)
+            else:
+                # where in the work / school building a person sits is medlabs' choice (not visible in the reference):
+                # a keyed hash of the person, fixed for the run
+                hx = philox4x32_10(np.arange(n_persons), 0, 3, TAG_SCHEDULE, seed & 0xFFFFFFFF, seed >> 32)[0]
+                work_sub = np.where(work_loc >= 0, hx.astype(np.int64) % np.maximum(loc_nsub[np.maximum(work_loc, 0)], 1), 0)
+        else:
+            age, role, home_loc, home_sub, work_loc, work_sub = self._synthetic_persons(
+                rng, n_persons, n_households, hh_building, hh_sub, loc_type, loc_nsub, x, y)
+        from scipy.spatial import cKDTree
+        # nearest / random candidate tables per Accommodation building (locators of the activity schedule)
+        self.n_random_candidates = K = n_random_candidates
+        n_types = len(TYPE_NAMES)
+        nearest = np.full((n_loc, n_types), NONE, np.int32)
+        cand = np.full((n_loc, n_types, K), NONE, np.int32)
+        n_cand = np.zeros((n_loc, n_types), np.int32)
+        pts = np.c_[x[acc], y[acc]]
+        for t in range(n_types):
+            places = np.nonzero(loc_type == t)[0]
+            if t in (TYPE_ID["Accommodation"], TYPE_ID["Workplace"]) or len(places) == 0:
+                continue
+            tree = cKDTree(np.c_[x[places], y[places]])
+            _, j = tree.query(pts)
+            nearest[acc, t] = places[j]
+            kk = min(K, len(places))
+            d, j = tree.query(pts, k=kk, distance_upper_bound=2500.0)  # RandomLocator max distance (xlsx column P)
+            d = d.reshape(len(acc), kk)
+            j = j.reshape(len(acc), kk)
+            ok = np.isfinite(d)
+            n_cand[acc, t] = ok.sum(axis=1)
+            jj = np.where(ok, j, 0)
+            cand[acc, t, :kk] = np.where(ok, places[jj], NONE)
+        self.nearest, self.cand, self.n_cand = nearest, cand, n_cand
+
+        self.loc_type = loc_type.astype(np.uint8)
+        self.loc_nsub = loc_nsub.astype(np.int16)
+        self.loc_area = (area_sub * loc_nsub).astype(np.float32)  # totalArea = area * nb_sublocations (java :381)
+        self.loc_x, self.loc_y = x.astype(np.float32), y.astype(np.float32)
+        self.n_locations = n_loc
+        self.age = age.astype(np.int8)
+        self.female = (rng.random(n_persons) < 0.5).astype(np.uint8)  # gender drawn U01 < 0.5 (java :513)
+        if person_table is not None and "female" in person_table:
+            self.female = np.asarray(person_table["female"], np.uint8)
+        self.role = role.astype(np.uint8)
+        self.home_loc = home_loc.astype(np.int32)
+        self.home_sub = home_sub.astype(np.int16)
+        self.work_loc = work_loc.astype(np.int32)
+        self.work_sub = work_sub.astype(np.int16)
+
+    def _synthetic_persons(self, rng, n_persons, n_households, hh_building, hh_sub, loc_type, loc_nsub, x, y):
+        """ages, roles, households, work / school places of the synthetic population"""
         age = self._draw_ages(rng, n_persons)
         role = self._roles(rng, age)
         adults = np.nonzero(age >= 18)[0]
@@ -185,42 +250,7 @@ class City:
         has = work_loc >= 0
         work_sub[has] = rng.integers(0, 1 << 30, has.sum()) % np.maximum(loc_nsub[work_loc[has]], 1)
 
-        # nearest / random candidate tables per Accommodation building (locators of the activity schedule)
-        self.n_random_candidates = K = n_random_candidates
-        n_types = len(TYPE_NAMES)
-        nearest = np.full((n_loc, n_types), NONE, np.int32)
-        cand = np.full((n_loc, n_types, K), NONE, np.int32)
-        n_cand = np.zeros((n_loc, n_types), np.int32)
-        pts = np.c_[x[acc], y[acc]]
-        for t in range(n_types):
-            places = np.nonzero(loc_type == t)[0]
-            if t in (TYPE_ID["Accommodation"], TYPE_ID["Workplace"]) or len(places) == 0:
-                continue
-            tree = cKDTree(np.c_[x[places], y[places]])
-            _, j = tree.query(pts)
-            nearest[acc, t] = places[j]
-            kk = min(K, len(places))
-            d, j = tree.query(pts, k=kk, distance_upper_bound=2500.0)  # RandomLocator max distance (xlsx column P)
-            d = d.reshape(len(acc), kk)
-            j = j.reshape(len(acc), kk)
-            ok = np.isfinite(d)
-            n_cand[acc, t] = ok.sum(axis=1)
-            jj = np.where(ok, j, 0)
-            cand[acc, t, :kk] = np.where(ok, places[jj], NONE)
-        self.nearest, self.cand, self.n_cand = nearest, cand, n_cand
-
-        self.loc_type = loc_type.astype(np.uint8)
-        self.loc_nsub = loc_nsub.astype(np.int16)
-        self.loc_area = (area_sub * loc_nsub).astype(np.float32)  # totalArea = area * nb_sublocations (java :381)
-        self.loc_x, self.loc_y = x.astype(np.float32), y.astype(np.float32)
-        self.n_locations = n_loc
-        self.age = age.astype(np.int8)
-        self.female = (rng.random(n_persons) < 0.5).astype(np.uint8)  # gender drawn U01 < 0.5 (java :513)
-        self.role = role.astype(np.uint8)
-        self.home_loc = home_loc.astype(np.int32)
-        self.home_sub = home_sub.astype(np.int16)
-        self.work_loc = work_loc.astype(np.int32)
-        self.work_sub = work_sub.astype(np.int16)
+        return age, role, home_loc, home_sub, work_loc, work_sub
 
     @staticmethod
     def _draw_ages(rng, n):

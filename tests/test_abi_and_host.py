@@ -342,3 +342,79 @@ def test_schedule_generator_with_commuters_into_another_tile():
     opened_today = st["t_in"][st["loc"] < city.n_locations] >= 24.0
     assert ((ty == scenario.TYPE_ID["Workplace"]) & opened_today).sum() == 0
     assert ((st["loc"] >= city.n_locations) & (st["t_in"] >= 24.0)).sum() > 0.5 * n
+
+
+def test_loaders_read_the_reference_file_formats(tmp_path, capsys):
+    """locations.csv.gz / people.csv.gz in the column layout of data/<city>/ (ConstructHerosModel.java:300-395, :450-758):
+    ids are mapped to dense indices, households get their sub-location in order of first appearance, the rows the
+    reference rejects are reported on stderr with its messages and skipped."""
+    import csv
+    import gzip
+    from heros_b200 import loaders
+    loc_rows = [["location_id", "lon", "lat", "nb_sublocations", "location_category", "area", "extra"],
+                [100, 4.30, 52.07, 3, "Accommodation", 100.0, "x"], [101, 4.31, 52.08, 2, "Accommodation", 80.0, "x"],
+                [205, 4.32, 52.07, 4, "Workplace", 30.0, "x"], [300, 4.30, 52.09, 6, "Kindergarten", 50.0, "x"],
+                [301, 4.33, 52.06, 10, "PrimarySchool", 75.0, "x"], [400, 4.31, 52.07, 1, "Supermarket", 200.0, "x"],
+                [401, 4.32, 52.08, 1, "Casino", 10.0, "x"], [500, 4.30, 52.07, 1, "Park", 300000.0, "x"]]
+    lp = str(tmp_path / "locations.csv.gz")
+    with gzip.open(lp, "wt", newline="") as f:
+        csv.writer(f).writerows(loc_rows)
+    people_rows = [["person_id", "household_id", "age", "home_id", "workplace_id", "social_role"],
+                   [1, 10, 34.0, 100, 205, 7], [2, 10, 36, 100, 205.0, 7], [3, 11, 70, 100, "", 8],
+                   [4, 12, 4, 100, 300, 2], [5, 13, 8, 100, 301, 3],          # household 13: 4th in a home of 3 dwellings
+                   [6, 20, 30, 999, 205, 7],                                   # unknown home
+                   [7, 20, 30, 101, "", 7],                                    # worker without a work location
+                   [8, 20, 5, 101, 301, 2],                                    # kindergarten child registered at a primary school
+                   [9, 21, 130, 101, "", 9],                                   # age out of range: reported, kept
+                   [10, 21, 1, 101, "", 1], [11, 22, 40, 101, 205, 42]]        # unknown role
+    pp = str(tmp_path / "people.csv.gz")
+    with gzip.open(pp, "wt", newline="") as f:
+        csv.writer(f).writerows(people_rows)
+    locs = loaders.read_locations(lp)
+    err = capsys.readouterr().err
+    assert "Location type Casino not found on line 8" in err
+    assert locs["location_id"].tolist() == [100, 101, 205, 300, 301, 400, 500]
+    assert locs["type"].tolist() == [scenario.TYPE_ID[n] for n in ("Accommodation", "Accommodation", "Workplace", "Kindergarten",
+                                                                     "PrimarySchool", "Supermarket", "Park")]
+    assert locs["nsub"].tolist() == [3, 2, 4, 6, 10, 1, 1] and locs["area_per_sub"][2] == 30.0
+    people = loaders.read_people(pp, locs)
+    err = capsys.readouterr().err
+    assert "homeId 999 not found in the location map on line 7" in err
+    assert "No work location [-1] for Worker on line 8" in err
+    assert "workSchoolId 301 not a kindergarten in the location map on line 9" in err
+    assert "Person 9 has age 130 on row 10" in err
+    assert "has more sublocations (4) than defined" in err and "social role 42 not recognized" in err
+    assert people["person_id"].tolist() == [1, 2, 3, 4, 5, 9, 10]
+    assert people["home_loc"].tolist() == [0, 0, 0, 0, 0, 1, 1]
+    assert people["home_sub"].tolist() == [0, 0, 1, 2, 3, 1, 1]      # household 20 took dwelling 0 of home 101 before being dropped
+    assert people["work_loc"].tolist() == [2, 2, -1, 3, 4, -1, -1] and people["role"].tolist() == [7, 7, 8, 2, 3, 9, 1]
+    assert set(people["female"].tolist()) <= {0, 1}
+    with pytest.raises(ValueError):
+        loaders._columns(["person_id", "age"], ("person_id", "household_id"), "Person")
+    city = loaders.load_city(lp, pp)
+    capsys.readouterr()
+    assert city.n_persons == 7 and city.n_locations == 7 and city.person_id.tolist() == [1, 2, 3, 4, 5, 9, 10]
+    assert city.loc_area[2] == np.float32(30.0 * 4)                      # total surface = area * nb_sublocations as float
+    assert (city.work_sub[:2] < 4).all() and city.work_sub[2] == 0
+    # the tables are what the engine and the schedule take
+    tables = scenario.compile_schedule(city)
+    assert tables["nearest"].shape == (7, len(scenario.TYPE_NAMES)) and tables["work_sub"].shape == (7,)
+    assert tables["nearest"][0, scenario.TYPE_ID["Supermarket"]] == 5
+    gen = scenario.ScheduleGenerator(city, 111)
+    st = gen.generate_day(np.zeros(7, np.uint8))
+    assert (st["sub"] < np.maximum(city.loc_nsub[st["loc"]], 1)).all() or (st["sub"][st["loc"] == 0] <= 3).all()
+    assert 2 in st["loc"].tolist()                                        # the workers went to work
+
+
+def test_location_loader_reproduces_the_helsinki_fixture():
+    """data/helsinki/locations.csv.gz through loaders.read_locations == tests/golden/helsinki_locations.npz (only where the
+    reference tree is present: this container, not the GPU box)."""
+    from heros_b200 import loaders
+    path = "/root/reference/data/helsinki/locations.csv.gz"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not on this machine")
+    locs = loaders.read_locations(path)
+    fix = np.load(os.path.join(GOLDEN, "helsinki_locations.npz"))
+    assert len(locs["type"]) == 69508 and locs["location_id"].tolist() == list(range(69508))
+    for k in ("type", "nsub", "area_per_sub", "lat", "lon"):
+        np.testing.assert_array_equal(locs[k], fix[k])
