@@ -6,6 +6,7 @@ JVM, so that the examples and tools can be pointed at a ``data/<city>`` director
   * ``locationtypes.csv``          -> ``properties.load_location_types``            (java :230-269)
   * ``locations.csv[.gz]``         -> ``read_locations``                             (java :300-395)
   * ``people.csv[.gz]``            -> ``read_people``                                (java :450-758)
+  * ``activities/*.xlsx``          -> ``read_activity_schedules``                    (java :763-942)
   * both                            -> ``load_city`` = a ``scenario.City`` with real tables (candidate / nearest tables of
                                       the locators are built as for the synthetic city)
 
@@ -23,6 +24,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import scenario
+from .xlsx import read_xlsx
 
 STUDENT_SCHOOL = {2: "kindergarten", 3: "primaryschool", 4: "secondaryschool", 5: "college", 6: "university"}
 ROLE_LABEL = {7: "Worker", 10: "WeekendWorker", 11: "EssentialWorker", 12: "WorkerSatelliteToCity",
@@ -153,3 +155,83 @@ def load_city(locations_path: str, people_path: str, type_names: Optional[Sequen
                          location_table=locations, person_table=people)
     city.location_id, city.person_id = locations["location_id"], people["person_id"]
     return city
+
+
+# role id 1..15 -> role name of the week-pattern keys (java :565-743, model/HerosModel.java:313-330)
+ROLES = ["infant", "kindergarten student", "primary school student", "secondary school student", "college student",
+         "university student", "worker", "pensioner", "unemployed job-seeker", "weekend worker", "essential worker",
+         "worker satellite to city", "worker city to satellite", "worker satellite to satellite",
+         "worker country to city"]
+PHASES = ["Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic", "Hospitalized", "ICU", "Dead",
+          "Recovered"]
+ACTIVITY_KIND = {"StochasticDurationActivity": 0, "FixedDurationActivity": 0, "TravelActivityDistanceBased": 1,
+                 "TravelActivity": 1, "UntilFixedTimeActivity": 2}
+LOCATOR = {"HomeLocator": 0, "WorkLocator": 1, "SchoolLocator": 1, "CurrentLocator": 2, "NearestLocator": 3,
+           "NearestLocatorCap": 3, "NearestLocatorChoice": 3, "RandomLocator": 4, "RandomLocatorCap": 4,
+           "DistanceBasedTravelLocator": 5}
+
+
+def read_activity_schedules(path: str, sheet: str = "activityschedules", policy: str = "0") -> dict:
+    """The activity-schedule workbook of a scenario (``data/<city>/activities/activityschedules*.xlsx``) as the
+    structure ``scenario.load_patterns`` returns and ``scenario.compile_schedule`` / ``ScheduleGenerator`` interpret.
+
+    Row format: columns A-Q of java :763-904 -- policy, disease phase, day, role, activity name, activity class,
+    until-time, distribution, mode, min, max, (unused), locator, (unused), travel locator, max distance, location-type
+    choice ("LocationType.X:0.6; LocationType.Y:0.4").  Only the rows of ``policy`` are read (policies 1 and 2 of the
+    shipped workbook are never referenced, java :400).  A day pattern ends with its first ``UntilFixedTimeActivity 24``:
+    10 of the 15 roles store the Susceptible block twice back to back, the second copy is dropped.
+    Capacity-constrained locators (``*Cap``) are read as their unconstrained forms."""
+    import json
+    rows = read_xlsx(path)[sheet][1:]
+    choices, choice_index = [], {}
+
+    def number(x, default=0.0):
+        return default if x in (None, "") else float(x)
+
+    def choice_id(text):
+        if not text:
+            return -1
+        items = []
+        for part in text.split(";"):
+            part = part.strip()
+            if not part:
+                continue
+            if ":" in part:
+                name, p = part.split(":")
+                items.append([name.strip().replace("LocationType.", ""), float(p)])
+            else:
+                items.append([part.replace("LocationType.", ""), 1.0])
+        key = json.dumps(items)
+        if key not in choice_index:
+            choice_index[key] = len(choices)
+            choices.append(items)
+        return choice_index[key]
+
+    patterns, closed = {}, set()
+    for r in rows:
+        r = list(r) + [None] * (17 - len(r))
+        if r[0] != policy:
+            continue
+        key = f"{r[1]}|{r[3]}|{r[2]}"
+        if key in closed:
+            continue
+        if r[5] not in ACTIVITY_KIND:
+            raise ValueError(f"unknown activity class {r[5]!r} in {path}")
+        kind = ACTIVITY_KIND[r[5]]
+        dist = {"triangular": 2, "uniform": 1}.get((r[7] or "").strip(), 0)
+        mode, mn, mx = number(r[8]), number(r[9]), number(r[10])
+        locator_name = r[14] if kind == 1 else r[12]
+        if locator_name not in LOCATOR:
+            raise ValueError(f"unknown locator {locator_name!r} in {path}")
+        locator, max_distance, cid = LOCATOR[locator_name], number(r[15]), choice_id(r[16])
+        if kind == 1 and dist == 0:
+            dist = 1  # travel time ~ U(min, max) hours (the reference derives it from the distance)
+        if dist == 0 and kind == 0:
+            mn = mx = mode  # FixedDurationActivity
+        act = {"name": (r[4] or "").strip(), "kind": kind, "locator": locator, "dist": dist, "min": mn, "mode": mode,
+               "max": mx, "until": number(r[6]), "choice": cid, "max_distance": max_distance}
+        patterns.setdefault(key, []).append(act)
+        if kind == 2 and act["until"] >= 24:
+            closed.add(key)
+    return {"source": path, "roles": ROLES, "phases": PHASES, "days": ["Monday", "Friday", "Saturday", "Sunday"],
+            "choices": choices, "patterns": patterns}

@@ -418,3 +418,81 @@ def test_location_loader_reproduces_the_helsinki_fixture():
     assert len(locs["type"]) == 69508 and locs["location_id"].tolist() == list(range(69508))
     for k in ("type", "nsub", "area_per_sub", "lat", "lon"):
         np.testing.assert_array_equal(locs[k], fix[k])
+
+
+def _write_xlsx(path, sheet_name, rows):
+    """a minimal workbook with inline strings and numbers (what heros_b200.xlsx reads)"""
+    import zipfile
+    from xml.sax.saxutils import escape
+
+    def col(i):
+        s = ""
+        i += 1
+        while i:
+            i, r = divmod(i - 1, 26)
+            s = chr(65 + r) + s
+        return s
+    body = []
+    for r, row in enumerate(rows, start=1):
+        cells = []
+        for c, v in enumerate(row):
+            if v is None:
+                continue
+            ref = f"{col(c)}{r}"
+            if isinstance(v, (int, float)):
+                cells.append(f'<c r="{ref}"><v>{v}</v></c>')
+            else:
+                cells.append(f'<c r="{ref}" t="inlineStr"><is><t>{escape(str(v))}</t></is></c>')
+        body.append(f'<row r="{r}">{"".join(cells)}</row>')
+    ns = "http://schemas.openxmlformats.org/spreadsheetml/2006/main"
+    rel = "http://schemas.openxmlformats.org/officeDocument/2006/relationships"
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("xl/workbook.xml", f'<workbook xmlns="{ns}" xmlns:r="{rel}"><sheets><sheet name="{sheet_name}" sheetId="1" r:id="rId1"/></sheets></workbook>')
+        z.writestr("xl/_rels/workbook.xml.rels", '<Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+                   '<Relationship Id="rId1" Type="x" Target="worksheets/sheet1.xml"/></Relationships>')
+        z.writestr("xl/worksheets/sheet1.xml", f'<worksheet xmlns="{ns}"><sheetData>{"".join(body)}</sheetData></worksheet>')
+
+
+def test_activity_schedule_workbook_reader(tmp_path):
+    """rows in the column layout of data/<city>/activities/activityschedules*.xlsx (ConstructHerosModel.java:763-904)"""
+    from heros_b200 import loaders
+    header = ["policy", "phase", "day", "role", "name", "class", "until", "dist", "mode", "min", "max", None, "locator",
+              None, "travel locator", "max distance", "types"]
+    rows = [header,
+            ["0", "Susceptible", "Monday", "worker", "sleep", "UntilFixedTimeActivity", 7, None, None, None, None, None, "HomeLocator"],
+            ["0", "Susceptible", "Monday", "worker", "to work", "TravelActivityDistanceBased", None, None, None, 0.2, 0.5, None, None, None, "WorkLocator"],
+            ["0", "Susceptible", "Monday", "worker", "work", "StochasticDurationActivity", None, "triangular", 8, 7, 9, None, "WorkLocator"],
+            ["0", "Susceptible", "Monday", "worker", "shop", "FixedDurationActivity", None, None, 0.5, None, None, None, "RandomLocatorCap", None, None,
+             2500, "LocationType.Supermarket:0.7; LocationType.Retail:0.3"],
+            ["0", "Susceptible", "Monday", "worker", "home", "UntilFixedTimeActivity", 24, None, None, None, None, None, "HomeLocator"],
+            ["0", "Susceptible", "Monday", "worker", "sleep", "UntilFixedTimeActivity", 7, None, None, None, None, None, "HomeLocator"],   # second copy of the block
+            ["1", "Susceptible", "Monday", "worker", "other policy", "UntilFixedTimeActivity", 24, None, None, None, None, None, "HomeLocator"],
+            ["0", "Infected-Symptomatic", "Monday", "worker", "ill", "UntilFixedTimeActivity", 24, None, None, None, None, None, "HomeLocator"]]
+    path = str(tmp_path / "activityschedules.xlsx")
+    _write_xlsx(path, "activityschedules", rows)
+    pat = loaders.read_activity_schedules(path)
+    day = pat["patterns"]["Susceptible|worker|Monday"]
+    assert [a["name"] for a in day] == ["sleep", "to work", "work", "shop", "home"]           # cut at the first "until 24"
+    assert [a["kind"] for a in day] == [2, 1, 0, 0, 2] and [a["locator"] for a in day] == [0, 1, 1, 4, 0]
+    assert day[1]["dist"] == 1 and (day[1]["min"], day[1]["max"]) == (0.2, 0.5)                # travel time ~ U(min, max)
+    assert day[2]["dist"] == 2 and (day[2]["min"], day[2]["mode"], day[2]["max"]) == (7.0, 8.0, 9.0)
+    assert day[3]["dist"] == 0 and day[3]["min"] == day[3]["max"] == 0.5 and day[3]["max_distance"] == 2500.0
+    assert pat["choices"][day[3]["choice"]] == [["Supermarket", 0.7], ["Retail", 0.3]]
+    assert list(pat["patterns"]) == ["Susceptible|worker|Monday", "Infected-Symptomatic|worker|Monday"]
+    bad = [header, ["0", "Susceptible", "Monday", "worker", "x", "TeleportActivity", 24, None, None, None, None, None, "HomeLocator"]]
+    _write_xlsx(path, "activityschedules", bad)
+    with pytest.raises(ValueError):
+        loaders.read_activity_schedules(path)
+
+
+def test_activity_schedule_reader_reproduces_the_packaged_patterns():
+    """data/thehague/activities/activityschedules_cap.xlsx through loaders.read_activity_schedules == the packaged
+    activity_patterns_thehague.json (only where the reference tree is present)."""
+    from heros_b200 import loaders
+    path = "/root/reference/data/thehague/activities/activityschedules_cap.xlsx"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not on this machine")
+    got = loaders.read_activity_schedules(path)
+    want = scenario.load_patterns()
+    assert got["patterns"] == want["patterns"] and got["choices"] == want["choices"]
+    assert got["roles"] == want["roles"] and got["phases"] == want["phases"]

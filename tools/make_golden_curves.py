@@ -9,10 +9,10 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from xlsx_reader import read_xlsx  # noqa: E402
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from heros_b200.xlsx import read_xlsx  # noqa: E402
+
 book = read_xlsx("/root/reference/seed comparison.xlsx")
 out = {"source": "seed comparison.xlsx, sheets 111-114 (The Hague, N = 553 667, 120 days, 0.5 h samples)",
        "header": book["111"][0][:9], "seeds": {}}
