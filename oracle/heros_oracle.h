@@ -15,7 +15,13 @@
  * cannot be executed in this container (no JVM, medlabs/DSOL jars not
  * vendored).  The oracle is pinned only by (a) the worked example in the
  * reference's Javadoc (TArea:112-121), (b) the Philox4x32-10 known-answer
- * vectors of Random123, (c) libm cross-checks of its exp().
+ * vectors of Random123, (c) libm cross-checks of its exp(), (d) hand-derived
+ * boundary cases of both transmission models and of the total-location
+ * branch, (e) the transition table, sojourn supports and age-band fractions
+ * of Prog:208-346 with the alpha parameters, (f) three observable properties
+ * of the only numbers the reference publishes for this path, the epidemic
+ * curves of "seed comparison.xlsx" (tests/golden/seed_comparison.json) --
+ * see tests/test_oracle.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product (libheros_gpu.so)
