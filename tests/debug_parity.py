@@ -1,4 +1,5 @@
-"""Development aid: generator-driven city on GPU vs oracle, report the first differing infection events."""
+"""Development aid (kept under tests/: it runs the oracle, which only tests may do): generator-driven city on GPU vs
+oracle, report the first differing infection events.  usage: python tests/debug_parity.py [--persons N] [--days D]"""
 import argparse
 import os
 import sys
