@@ -208,6 +208,16 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
                            int32_t n_types, int32_t accommodation_type, int32_t n_candidates, const int32_t* nearest,
                            const int32_t* n_cand, const int32_t* cand, const int16_t* work_sublocation, uint64_t seed);
 int32_t heros_advance_schedule(heros_handle h, int32_t day);
+/* The range checks heros_set_schedule applies to its tables before any kernel indexes with them (host code, no device
+ * needed): homes and work places inside the location table, sub-locations inside their location, nearest / candidate
+ * entries inside the location table (-1 = none), choice tables naming known types.  HEROS_ERR_INVALID with the reason
+ * in message (may be NULL). */
+int32_t heros_validate_schedule_tables(int32_t n_locations, const int16_t* n_sub, int32_t n_persons, const int32_t* home_loc,
+                                       const int16_t* home_sub, const int32_t* work_loc, const int16_t* work_sub,
+                                       int32_t n_types, int32_t n_candidates, const int32_t* nearest, const int32_t* n_cand,
+                                       const int32_t* cand, int32_t n_choices, const int32_t* choice_start,
+                                       const int32_t* choice_type, int32_t accommodation_type, char* message,
+                                       int32_t message_capacity);
 /* = LocationType.setClosurePolicy(fractionOpen, fractionActivities, alternativeLocationType, reportAsLocationName) as
  * policy/LocationPolicy.java:39-46 calls it at the policy's event time (rows of data/<city>/policies/\*.csv; the report
  * name only labels output and is not needed here).  The rule itself is inside the un-vendored medlabs jar; the

@@ -86,6 +86,8 @@ SIGNATURES = {
     "heros_set_schedule": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                        _P, _P, _P, _P, C.c_uint64]),
     "heros_advance_schedule": (C.c_int32, [_P, C.c_int32]),
+    "heros_validate_schedule_tables": (C.c_int32, [C.c_int32, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
+                                                   C.c_int32, _P, _P, C.c_int32, C.c_char_p, C.c_int32]),
     "heros_snapshot_size": (C.c_int32, [_P, C.POINTER(C.c_int64)]),
     "heros_snapshot_save": (C.c_int32, [_P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "heros_snapshot_load": (C.c_int32, [_P, C.c_int64, _P]),

@@ -1200,8 +1200,12 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     h->h_role.assign((size_t) n, 0);
     if (role) h->h_role.assign(role, role + n);
     h->d_home_loc.release(); h->d_home_sub.release(); h->d_work_loc.release();
+    h->h_home_loc.clear(); h->h_home_sub.clear(); h->h_work_loc.clear();
     if (home_loc && home_sub && work_loc)  // only read by the device-side activity schedule
     {
+        // host copies: heros_set_schedule checks them against the location table before a kernel indexes with them
+        h->h_home_loc.assign(home_loc, home_loc + n); h->h_home_sub.assign(home_sub, home_sub + n);
+        h->h_work_loc.assign(work_loc, work_loc + n);
         CU(h, h->d_home_loc.ensure(N)); CU(h, h->d_home_sub.ensure(N)); CU(h, h->d_work_loc.ensure(N));
         CU(h, cudaMemcpyAsync(h->d_home_loc.p, home_loc, N * 4, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaMemcpyAsync(h->d_home_sub.p, home_sub, N * 2, cudaMemcpyHostToDevice, h->stream));

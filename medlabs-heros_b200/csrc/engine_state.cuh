@@ -160,6 +160,8 @@ struct heros_engine
     DevBuf<int16_t> d_home_sub, d_work_sub;
     DevBuf<uint32_t> s_order;      // persons grouped by social role
     std::vector<uint8_t> h_role;   // host copy of the roles (heros_set_persons)
+    std::vector<int32_t> h_home_loc, h_work_loc;  // host copies for the range checks of heros_set_schedule
+    std::vector<int16_t> h_home_sub;
 
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;  // pinned

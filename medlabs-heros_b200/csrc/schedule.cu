@@ -257,6 +257,47 @@ using namespace heros_impl;
 
 extern "C" {
 
+int32_t heros_validate_schedule_tables(int32_t n_locations, const int16_t* n_sub, int32_t n_persons, const int32_t* home_loc,
+                                       const int16_t* home_sub, const int32_t* work_loc, const int16_t* work_sub,
+                                       int32_t n_types, int32_t n_candidates, const int32_t* nearest, const int32_t* n_cand,
+                                       const int32_t* cand, int32_t n_choices, const int32_t* choice_start,
+                                       const int32_t* choice_type, int32_t accommodation_type, char* message,
+                                       int32_t message_capacity)
+{
+    auto bad = [&](const char* why) {
+        if (message && message_capacity > 0) snprintf(message, (size_t) message_capacity, "%s", why);
+        return (int32_t) HEROS_ERR_INVALID;
+    };
+    if (n_locations <= 0 || n_persons < 0 || n_types <= 0 || n_candidates < 0 || n_choices < 0 || !n_sub || !nearest || !n_cand ||
+        (n_candidates > 0 && !cand) || (n_persons > 0 && (!home_loc || !home_sub || !work_loc || !work_sub)) ||
+        (n_choices > 0 && (!choice_start || !choice_type)))
+        return bad("null or empty schedule table");
+    const int64_t n_loc = n_locations;
+    auto subs_of = [&](int64_t loc) { return (int) (n_sub[loc] > 1 ? n_sub[loc] : 1); };
+    for (int64_t a = 0; a < n_persons; ++a)
+    {
+        const int64_t hl = home_loc[a], wl = work_loc[a];
+        if (hl < 0 || hl >= n_loc || home_sub[a] < 0 || home_sub[a] >= subs_of(hl))
+            return bad("a person's home location / sub-location lies outside the location table");
+        if (wl >= n_loc) return bad("a person's work location lies outside the location table");
+        if (wl >= 0 && (work_sub[a] < 0 || work_sub[a] >= subs_of(wl)))
+            return bad("a person's work sub-location lies outside the work location");
+    }
+    const size_t cells = (size_t) n_locations * (size_t) n_types;
+    for (size_t i = 0; i < cells; ++i)
+    {
+        if (nearest[i] >= n_loc) return bad("nearest-location table points outside the location table");
+        if (n_cand[i] < 0 || n_cand[i] > n_candidates) return bad("candidate count outside 0..n_candidates");
+        for (int j = 0; j < n_cand[i]; ++j)
+            if (cand[i * (size_t) n_candidates + (size_t) j] >= n_loc) return bad("candidate table points outside the location table");
+    }
+    const size_t n_entries = n_choices ? (size_t) choice_start[n_choices] : 0;
+    for (size_t i = 0; i < n_entries; ++i)
+        if (choice_type[i] < 0 || choice_type[i] >= n_types) return bad("choice table names an unknown location type");
+    if (accommodation_type < 0 || accommodation_type >= n_types) return bad("unknown accommodation type");
+    return HEROS_OK;
+}
+
 int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_activity* activities,
                            const int32_t* pattern_start, const int32_t* pattern_count, int32_t n_choices,
                            const int32_t* choice_start, const int32_t* choice_type, const double* choice_cum,
@@ -305,6 +346,18 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
     }
     for (int i = 0; i < n_choices; ++i)
         if (choice_start[i + 1] <= choice_start[i]) return fail(h, HEROS_ERR_INVALID, "empty choice table");
+    {
+        // every index the kernel follows is checked here, once, on the host: a table that points outside the location
+        // table is refused instead of being read out of bounds on the device
+        if (h->h_home_loc.size() != h->n_agents || h->h_home_sub.size() != h->n_agents || h->h_work_loc.size() != h->n_agents)
+            return fail(h, HEROS_ERR_INVALID, "heros_set_persons was called without home / work locations");
+        char why[160] = "";
+        if (heros_validate_schedule_tables((int32_t) h->n_loc, h->h_loc_nsub.data(), (int32_t) h->n_agents, h->h_home_loc.data(),
+                                           h->h_home_sub.data(), h->h_work_loc.data(), work_sublocation, n_types, n_candidates,
+                                           nearest, n_cand, cand, n_choices, choice_start, choice_type, accommodation_type,
+                                           why, (int32_t) sizeof why) != HEROS_OK)
+            return fail(h, HEROS_ERR_INVALID, why);
+    }
     cudaSetDevice(h->cfg.device);
     const size_t N = h->n_agents, L = h->n_loc, n_ch = n_choices ? (size_t) choice_start[n_choices] : 0;
     cudaStream_t s = h->stream;

@@ -496,3 +496,57 @@ def test_activity_schedule_reader_reproduces_the_packaged_patterns():
     want = scenario.load_patterns()
     assert got["patterns"] == want["patterns"] and got["choices"] == want["choices"]
     assert got["roles"] == want["roles"] and got["phases"] == want["phases"]
+
+
+def _validate(city, tables, **override):
+    """heros_validate_schedule_tables (host code of the library, no device needed) on the tables of a city"""
+    lib = _lib.load()
+    t = dict(tables)
+    cols = dict(n_sub=city.loc_nsub, home_loc=city.home_loc, home_sub=city.home_sub, work_loc=city.work_loc,
+                work_sub=t["work_sub"], nearest=t["nearest"], n_cand=t["n_cand"], cand=t["cand"],
+                choice_start=t["choice_start"], choice_type=t["choice_type"])
+    acc = int(override.pop("acc", t["accommodation_type"]))
+    cols.update(override)
+    dt = dict(n_sub=np.int16, home_loc=np.int32, home_sub=np.int16, work_loc=np.int32, work_sub=np.int16, nearest=np.int32,
+              n_cand=np.int32, cand=np.int32, choice_start=np.int32, choice_type=np.int32)
+    a = {k: np.ascontiguousarray(v, dt[k]) for k, v in cols.items()}
+    p = lambda k: a[k].ctypes.data_as(C.c_void_p)
+    msg = C.create_string_buffer(200)
+    rc = lib.heros_validate_schedule_tables(city.n_locations, p("n_sub"), city.n_persons, p("home_loc"), p("home_sub"),
+                                            p("work_loc"), p("work_sub"), int(t["n_types"]), int(t["n_candidates"]),
+                                            p("nearest"), p("n_cand"), p("cand"), len(a["choice_start"]) - 1,
+                                            p("choice_start"), p("choice_type"), acc, msg, 200)
+    return rc, msg.value.decode()
+
+
+def test_schedule_tables_are_range_checked_on_the_host():
+    """What heros_set_schedule refuses before a kernel could index out of bounds; the tables of the synthetic cities and
+    of the Helsinki city pass."""
+    tab = dict(np.load(os.path.join(GOLDEN, "helsinki_locations.npz")))
+    for city in (scenario.City(800, seed=3), scenario.City(6000, seed=7), scenario.City(20000, seed=5, location_table=tab)):
+        tables = scenario.compile_schedule(city)
+        assert _validate(city, tables) == (0, "")
+    city = scenario.City(800, seed=3)
+    tables = scenario.compile_schedule(city)
+    n_loc = city.n_locations
+
+    def broken(name, index, value, source=None):
+        arr = np.array(source if source is not None else (tables[name] if name in tables else getattr(city, name))).copy()
+        arr[index] = value
+        return {name: arr}
+
+    worker = int(np.nonzero(city.work_loc >= 0)[0][0])
+    cases = [(broken("home_loc", 5, n_loc), "home location"), (broken("home_loc", 5, -1), "home location"),
+             (broken("home_sub", 5, 300), "home location"), (broken("work_loc", worker, n_loc + 7), "work location lies outside"),
+             (broken("work_sub", worker, 200), "work sub-location"), (broken("nearest", (3, 6), n_loc), "nearest-location table"),
+             (broken("n_cand", (3, 6), 9), "candidate count"), (broken("n_cand", (3, 6), -1), "candidate count"),
+             (broken("choice_type", 0, 22), "unknown location type"), (dict(acc=40), "unknown accommodation type")]
+    home = int(city.home_loc[0])
+    ty = int(np.nonzero(tables["n_cand"][home] > 0)[0][0])
+    cases.append((broken("cand", (home, ty, 0), n_loc + 1), "candidate table"))
+    for override, text in cases:
+        rc, msg = _validate(city, tables, **override)
+        assert rc == _lib.ERR_INVALID and text in msg, (override.keys(), rc, msg)
+    # -1 = "none" stays legal everywhere it means that
+    ok = {**broken("work_loc", worker, -1), **broken("nearest", (3, 6), -1)}
+    assert _validate(city, tables, **ok)[0] == 0
