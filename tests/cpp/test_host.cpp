@@ -381,6 +381,52 @@ static void test_windowed_run_equals_the_oracle(const std::string& golden, const
     orc_sim_destroy(sim);
 }
 
+// the device-side schedule through the C ABI on hand-made tables: accepted when consistent, refused (before any kernel
+// runs) when a table points outside the location table
+static void test_device_schedule_tables(const std::string& golden)
+{
+    HerosModel model(loadProperties(golden + "/params_alpha_area.properties"), 5);
+    constructDiseaseModel(model);
+    const uint8_t infect_sub[3] = {1, 1, 1};
+    const double corr[3] = {1.0, 1.0, 1.0};
+    model.check(heros_set_location_types(model.engine(), 3, infect_sub, corr, nullptr, nullptr, nullptr));
+    const uint8_t type[3] = {0, 1, 2};
+    const int16_t nsub[3] = {2, 1, 1};
+    const float area[3] = {200.0f, 30.0f, 200.0f};
+    model.check(heros_set_locations(model.engine(), 3, type, nsub, area, nullptr, nullptr));
+    const int8_t age[4] = {30, 31, 32, 33};
+    const uint8_t female[4] = {0, 1, 0, 1}, role[4] = {7, 7, 7, 7};
+    const int32_t home_loc[4] = {0, 0, 0, 0}, work_loc[4] = {1, 1, 1, -1};
+    const int16_t home_sub[4] = {0, 0, 1, 1}, work_sub[4] = {0, 0, 0, 0};
+    model.check(heros_set_persons(model.engine(), 4, age, female, role, home_loc, home_sub, work_loc));
+    heros_activity acts[3] = {};
+    acts[0].kind = 2; acts[0].locator = 0; acts[0].choice = -1; acts[0].until = 8.0;                       // at home until 08:00
+    acts[1].kind = 0; acts[1].locator = 1; acts[1].choice = -1; acts[1].min = acts[1].mode = acts[1].max = 8.0;  // 8 h at work
+    acts[2].kind = 2; acts[2].locator = 0; acts[2].choice = -1; acts[2].until = 24.0;                      // home until midnight
+    std::vector<int32_t> pat_start(512, 0), pat_count(512, 0);
+    for (int ph = 0; ph < 8; ++ph)
+        for (int d = 0; d < 4; ++d) pat_count[(ph * 16 + 7) * 4 + d] = 3;
+    const int32_t choice_start[1] = {0}, choice_type[1] = {0};
+    const double choice_cum[1] = {1.0};
+    std::vector<int32_t> nearest(9, -1), n_cand(9, 0), cand(9, -1);
+    auto set = [&](const int32_t* near) {
+        return heros_set_schedule(model.engine(), 3, acts, pat_start.data(), pat_count.data(), 0, choice_start, choice_type, choice_cum,
+                                  3, 0, 1, near, n_cand.data(), cand.data(), work_sub, 5);
+    };
+    std::vector<int32_t> wrong = nearest;
+    wrong[4] = 3;  // a location that does not exist
+    CHECK(set(wrong.data()) == HEROS_ERR_INVALID);
+    CHECK(std::string(heros_last_error(model.engine())).find("nearest-location table") != std::string::npos);
+    model.check(set(nearest.data()));
+    model.check(heros_advance_schedule(model.engine(), 0));
+    heros_step_stats st{};
+    model.check(heros_step(model.engine(), 24.0, &st));
+    CHECK(st.windows == 1 && st.visits >= 7);  // three commuters: home, work, home; one person at home all day
+    model.check(heros_advance_schedule(model.engine(), 1));
+    model.check(heros_step(model.engine(), 48.0, &st));
+    CHECK(model.getSimulatorTime() == 48.0);
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) { std::printf("usage: %s cpu|gpu <golden dir>\n", argv[0]); return 2; }
@@ -389,8 +435,11 @@ int main(int argc, char** argv)
     test_errors_without_device(golden);
     if (mode == "cpu")
         test_engine_refuses_to_start_without_a_gpu(golden);
+    else if (mode == "schedule")
+        test_device_schedule_tables(golden);
     else
     {
+        test_device_schedule_tables(golden);
         test_infect_people_known_answers(golden);
         test_windowed_run_equals_the_oracle(golden, "area", HEROS_TRIGGER_EXIT_ONLY);
         test_windowed_run_equals_the_oracle(golden, "distance", HEROS_TRIGGER_EXIT_ONLY);
