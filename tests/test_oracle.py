@@ -395,3 +395,94 @@ def test_progression_follows_the_reference_transition_table():
     with open(os.path.join(GOLDEN, "seed_comparison.json")) as fjson:
         day10 = json.load(fjson)["seeds"]["111"]["daily_counts"][10]
     assert abs(day10[2] / (day10[2] + day10[3]) - 0.46) < 0.05
+
+
+def test_single_calls_match_an_independent_restatement_of_the_formulas():
+    """A second, independent statement of the two infectPeople formulas (sub-location branch), written here in plain
+    Python from the Java text (Covid19TransmissionArea.java:138-196, Covid19TransmissionDistance.java:119-187), against
+    the C oracle over random occupant sets, areas, durations and times: calculated flag, infectious list, pInfection
+    (python's math.exp is libm, the oracle's exp is fdlibm: <= 1 ulp apart, hence the tolerance) and the infected list
+    given the oracle's own keyed draws."""
+    rng = np.random.default_rng(99)
+    ill = {E, IA, IS, H, ICU}
+    a_props = dict(pB=0.8, beta=0.9, tmin=48.0, tmode=81.6, tmax=230.4, thr=60.0 / 3600.0)
+    d_props = dict(L=48.0, I=81.6, C=148.8, vmax=7.23, v0=4.0, r=2.294, psi=1.0, alpha=0.05, mu=0.1, thr=60.0 / 3600.0)
+
+    def area_ref(phases, exposure, total_area, nsub, corr, duration, now):
+        if duration < a_props["thr"]:
+            return False, [], math.nan
+        a = float(np.float32(total_area)) / nsub
+        factor = -a_props["beta"] * a_props["pB"] * duration / (corr * a)
+        if factor == 0.0:
+            return True, [], math.nan
+        s, infectious = 0.0, []
+        for i, (ph, ex) in enumerate(zip(phases, exposure)):
+            if ph in ill:
+                te = now - float(np.float32(ex))
+                c = 0.0
+                if a_props["tmin"] <= te < a_props["tmode"]:
+                    c = (te - a_props["tmin"]) / (a_props["tmode"] - a_props["tmin"])
+                elif a_props["tmode"] <= te <= a_props["tmax"]:
+                    c = (a_props["tmax"] - te) / (a_props["tmax"] - a_props["tmode"])
+                s += c
+                infectious.append(i)
+        if s == 0.0:
+            return True, infectious, math.nan
+        return True, infectious, 1.0 - math.exp(factor * s)
+
+    def dist_ref(phases, exposure, total_area, nsub, duration, now):
+        if duration < d_props["thr"]:
+            return False, [], math.nan
+        a = float(np.float32(total_area)) / nsub
+        delta = math.sqrt(a / len(phases))
+        sigma = 1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, d_props["psi"]) - 1.5)))
+        factor = sigma * d_props["alpha"] * (1.0 - d_props["mu"]) * (1.0 - d_props["mu"])
+        if factor == 0.0:
+            return True, [], math.nan
+        s, infectious = 0.0, []
+        for i, (ph, ex) in enumerate(zip(phases, exposure)):
+            if ph in ill:
+                t = now - float(np.float32(ex))
+                v = 0.0
+                if d_props["L"] <= t < d_props["I"]:
+                    v = d_props["vmax"] * ((t - d_props["L"]) / (d_props["I"] - d_props["L"]))
+                elif d_props["I"] <= t < d_props["I"] + d_props["C"]:
+                    v = d_props["vmax"] * ((d_props["I"] + d_props["C"] - t) / d_props["C"])
+                if v > 0:
+                    s += factor * duration * (1 / (1 + math.exp(-d_props["r"] * (v - d_props["v0"]))))
+                    infectious.append(i)
+        if s == 0.0:
+            return True, infectious, math.nan
+        return True, infectious, 1.0 - math.exp(-s)
+
+    o_area = ob.AreaProps(0.8, 0.9, 2.0, 3.4, 9.6, 60.0)
+    o_dist = ob.DistProps(2.0, 3.4, 6.2, 7.23, 4.0, 2.294, 1.0, 0.05, 0.1, 60.0)
+    n_p = 0
+    for trial in range(400):
+        n = int(rng.integers(1, 40))
+        phases = rng.choice([S, S, S, E, IA, IS, H, ICU, D, R], n).tolist()
+        now = float(rng.uniform(0.0, 400.0))
+        exposure = np.where(rng.random(n) < 0.2, 0.0, rng.uniform(max(now - 300.0, 0.0), now + 1e-9, n)).astype(np.float32)
+        nsub = int(rng.integers(1, 6))
+        total_area = float(np.float32(rng.uniform(5.0, 400.0) * nsub))
+        corr = float(rng.choice([1.0, 0.8, 1.25]))
+        duration = float(rng.choice([rng.uniform(0.0, 0.03), rng.uniform(0.02, 12.0)]))
+        ids = list(range(n))
+        for model in (ob.MODEL_AREA, ob.MODEL_DIST):
+            if model == ob.MODEL_AREA:
+                got = ob.infect_people(model, o_area, 7, True, corr, total_area, nsub, ids, phases, exposure, now, duration)
+                calc, infectious, p = area_ref(phases, exposure, total_area, nsub, corr, duration, now)
+            else:
+                got = ob.infect_people(model, o_dist, 7, True, 1.0, total_area, nsub, ids, phases, exposure, now, duration)
+                calc, infectious, p = dist_ref(phases, exposure, total_area, nsub, duration, now)
+            assert got["calculated"] == calc, (trial, model)
+            assert got["infectious"].tolist() == infectious, (trial, model)
+            if math.isnan(p):
+                assert math.isnan(got["p"]) and len(got["infected"]) == 0, (trial, model, got["p"])
+                continue
+            n_p += 1
+            assert got["p"] == pytest.approx(p, rel=1e-12, abs=4.5e-16), (trial, model)
+            bits = int(np.float64(now).view(np.uint64))
+            want_infected = [i for i in ids if phases[i] == S and ob.u01(7, i, bits, 0) < got["p"]]
+            assert got["infected"].tolist() == want_infected, (trial, model)
+    assert n_p > 200
