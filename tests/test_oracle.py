@@ -486,3 +486,76 @@ def test_single_calls_match_an_independent_restatement_of_the_formulas():
             want_infected = [i for i in ids if phases[i] == S and ob.u01(7, i, bits, 0) < got["p"]]
             assert got["infected"].tolist() == want_infected, (trial, model)
     assert n_p > 200
+
+
+def test_driver_matches_a_brute_force_statement_of_the_contract():
+    """The oracle's event-by-event driver against a second statement of the driver contract (exit
+    trigger) written here as a plain loop over the exits in time order: per sub-location lastCalculation with the
+    threshold rule, the set S(t-) = {stays: t_in < t <= t_out}, the formula of the area model, keyed draws, a person is
+    infected once.  Four days with the seeds exposed at t = 0: nobody infected later turns contagious inside the run
+    (48 h latent period from an exposure >= 48 h), so the comparison does not involve the progression draws."""
+    from common import Scenario
+    scn = Scenario(seed=21, n_persons=160, n_households=60, n_workplaces=8, n_shops=3, days=4, tie_fraction=0.25,
+                   short_gap_fraction=0.15)
+    props = load_props("area")
+    props["covidT_area.contagiousness"] = "25.0"
+    a, _, prog = oracle_props(props)
+    seed = 4711
+    sim = ob.Sim(ob.MODEL_AREA, ob.TRIGGER_EXIT_ONLY, seed)
+    sim.set_area(a)
+    sim.set_prog(prog)
+    sim.set_location_types(scn.type_infect_sub, scn.type_corr)
+    sim.set_locations(scn.loc_type, scn.loc_nsub, scn.loc_area)
+    sim.set_persons(scn.age, scn.female)
+    sim.expose(scn.seeds, np.zeros(len(scn.seeds)))
+    sim.add_visits(scn.person, scn.loc, scn.sub, scn.t_in, scn.t_out)
+    horizon = 24.0 * scn.days
+    sim.run(horizon)
+    got = sim.infections()
+    order = np.lexsort((got["person"], got["time"]))
+    got = {k: v[order] for k, v in got.items()}
+
+    # ---- the brute-force statement ----
+    pB, beta, tmin, tmode, tmax, thr = 25.0, 1.0, 48.0, 81.6, 230.4, 60.0 / 3600.0
+    susceptible = np.ones(scn.n_persons, bool)
+    susceptible[scn.seeds] = False
+    exposure = np.zeros(scn.n_persons, np.float32)
+    is_ill = ~susceptible                       # the seeds stay ill for the whole run (E -> I(A) / I(S), never out in 4 days)
+    key = scn.loc.astype(np.int64) * 1000 + scn.sub
+    last_calc = {}
+    events = []
+    exits = np.nonzero(np.isfinite(scn.t_out) & (scn.t_out < horizon))[0]
+    for i in sorted(exits.tolist(), key=lambda i: (scn.t_out[i], key[i], scn.person[i])):
+        t, k = float(scn.t_out[i]), int(key[i])
+        duration = t - last_calc.get(k, 0.0)
+        if duration < thr:
+            continue                            # not calculated: the interval keeps accumulating (C6)
+        last_calc[k] = t
+        present = np.nonzero((key == k) & (scn.t_in < t) & (t <= scn.t_out))[0]      # the leaver is still counted, C5
+        persons = scn.person[present]
+        loc = int(scn.loc[i])
+        area = float(np.float32(scn.loc_area[loc])) / int(scn.loc_nsub[loc])
+        factor = -beta * pB * duration / (float(scn.type_corr[scn.loc_type[loc]]) * area)
+        total = 0.0
+        for p in persons[is_ill[persons]]:
+            te = t - float(exposure[p])
+            if tmin <= te < tmode:
+                total += (te - tmin) / (tmode - tmin)
+            elif tmode <= te <= tmax:
+                total += (tmax - te) / (tmax - tmode)
+        if factor == 0.0 or total == 0.0:
+            continue
+        p_inf = 1.0 - math.exp(factor * total)
+        bits = int(np.float64(t).view(np.uint64))
+        for p in sorted(persons[susceptible[persons]].tolist()):
+            if ob.u01(seed, p, bits, 0) < p_inf:
+                susceptible[p] = False
+                is_ill[p] = True
+                exposure[p] = np.float32(t)     # exposure time is a float (C4)
+                events.append((t, p, loc, int(scn.sub[i]), p_inf))
+    events.sort()
+    assert len(events) > 25 and len(events) == len(got["person"])
+    assert [e[1] for e in events] == got["person"].tolist()
+    assert [e[0] for e in events] == got["time"].tolist()
+    assert [e[2] for e in events] == got["loc"].tolist() and [e[3] for e in events] == got["sub"].tolist()
+    np.testing.assert_allclose([e[4] for e in events], got["p"], rtol=1e-12, atol=4.5e-16)
