@@ -488,21 +488,24 @@ def test_single_calls_match_an_independent_restatement_of_the_formulas():
     assert n_p > 200
 
 
-def test_driver_matches_a_brute_force_statement_of_the_contract():
-    """The oracle's event-by-event driver against a second statement of the driver contract (exit
-    trigger) written here as a plain loop over the exits in time order: per sub-location lastCalculation with the
-    threshold rule, the set S(t-) = {stays: t_in < t <= t_out}, the formula of the area model, keyed draws, a person is
-    infected once.  Four days with the seeds exposed at t = 0: nobody infected later turns contagious inside the run
-    (48 h latent period from an exposure >= 48 h), so the comparison does not involve the progression draws."""
+@pytest.mark.parametrize("model,trigger", [("area", "exit"), ("distance", "exit"), ("area", "both"), ("distance", "both")])
+def test_driver_matches_a_brute_force_statement_of_the_contract(model, trigger):
+    """The oracle's event-by-event driver against a second statement of the driver contract
+    written here as a plain loop over the movement events in time order (exits before enters at equal times; enters only
+    with the ENTER_AND_EXIT trigger): per sub-location lastCalculation with the threshold rule, the set S(t-) = {stays:
+    t_in < t <= t_out}, the formula of the model, keyed draws, a person is infected once.  Four days with the seeds
+    exposed at t = 0: nobody infected later turns contagious inside the run (48 h latent period from an exposure
+    >= 48 h), so the comparison does not involve the progression draws."""
     from common import Scenario
     scn = Scenario(seed=21, n_persons=160, n_households=60, n_workplaces=8, n_shops=3, days=4, tie_fraction=0.25,
                    short_gap_fraction=0.15)
-    props = load_props("area")
-    props["covidT_area.contagiousness"] = "25.0"
-    a, _, prog = oracle_props(props)
+    props = load_props(model)
+    props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "25.0" if model == "area" else "3.0"
+    a, d, prog = oracle_props(props)
     seed = 4711
-    sim = ob.Sim(ob.MODEL_AREA, ob.TRIGGER_EXIT_ONLY, seed)
-    sim.set_area(a)
+    kind = ob.MODEL_AREA if model == "area" else ob.MODEL_DIST
+    sim = ob.Sim(kind, ob.TRIGGER_EXIT_ONLY if trigger == "exit" else ob.TRIGGER_ENTER_AND_EXIT, seed)
+    sim.set_area(a) if model == "area" else sim.set_dist(d)
     sim.set_prog(prog)
     sim.set_location_types(scn.type_infect_sub, scn.type_corr)
     sim.set_locations(scn.loc_type, scn.loc_nsub, scn.loc_area)
@@ -517,6 +520,7 @@ def test_driver_matches_a_brute_force_statement_of_the_contract():
 
     # ---- the brute-force statement ----
     pB, beta, tmin, tmode, tmax, thr = 25.0, 1.0, 48.0, 81.6, 230.4, 60.0 / 3600.0
+    L, I, Cc, vmax, v0, r, psi, alpha, mu = 48.0, 81.6, 148.8, 7.23, 4.0, 2.294, 1.0, 3.0, 0.0
     susceptible = np.ones(scn.n_persons, bool)
     susceptible[scn.seeds] = False
     exposure = np.zeros(scn.n_persons, np.float32)
@@ -524,28 +528,50 @@ def test_driver_matches_a_brute_force_statement_of_the_contract():
     key = scn.loc.astype(np.int64) * 1000 + scn.sub
     last_calc = {}
     events = []
-    exits = np.nonzero(np.isfinite(scn.t_out) & (scn.t_out < horizon))[0]
-    for i in sorted(exits.tolist(), key=lambda i: (scn.t_out[i], key[i], scn.person[i])):
-        t, k = float(scn.t_out[i]), int(key[i])
+    moves = [(float(scn.t_out[i]), 0, int(key[i]), int(scn.person[i]), i) for i in range(scn.n_visits)
+             if np.isfinite(scn.t_out[i]) and scn.t_out[i] < horizon]
+    if trigger == "both":
+        moves += [(float(scn.t_in[i]), 1, int(key[i]), int(scn.person[i]), i) for i in range(scn.n_visits) if scn.t_in[i] < horizon]
+    for t, _, k, _, i in sorted(moves):
         duration = t - last_calc.get(k, 0.0)
         if duration < thr:
             continue                            # not calculated: the interval keeps accumulating (C6)
         last_calc[k] = t
-        present = np.nonzero((key == k) & (scn.t_in < t) & (t <= scn.t_out))[0]      # the leaver is still counted, C5
+        present = np.nonzero((key == k) & (scn.t_in < t) & (t <= scn.t_out))[0]      # a leaver is still counted, an enterer not yet (C5)
         persons = scn.person[present]
         loc = int(scn.loc[i])
         area = float(np.float32(scn.loc_area[loc])) / int(scn.loc_nsub[loc])
-        factor = -beta * pB * duration / (float(scn.type_corr[scn.loc_type[loc]]) * area)
-        total = 0.0
-        for p in persons[is_ill[persons]]:
-            te = t - float(exposure[p])
-            if tmin <= te < tmode:
-                total += (te - tmin) / (tmode - tmin)
-            elif tmode <= te <= tmax:
-                total += (tmax - te) / (tmax - tmode)
-        if factor == 0.0 or total == 0.0:
-            continue
-        p_inf = 1.0 - math.exp(factor * total)
+        if model == "area":
+            factor = -beta * pB * duration / (float(scn.type_corr[scn.loc_type[loc]]) * area)
+            total = 0.0
+            for p in persons[is_ill[persons]]:
+                te = t - float(exposure[p])
+                if tmin <= te < tmode:
+                    total += (te - tmin) / (tmode - tmin)
+                elif tmode <= te <= tmax:
+                    total += (tmax - te) / (tmax - tmode)
+            if factor == 0.0 or total == 0.0:
+                continue
+            p_inf = 1.0 - math.exp(factor * total)
+        else:
+            if len(persons) == 0:
+                continue                        # sqrt(area / 0) = inf, nobody there: nothing to sum, nobody to infect
+            delta = math.sqrt(area / len(persons))
+            sigma = 1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, psi) - 1.5)))
+            factor = sigma * alpha * (1.0 - mu) * (1.0 - mu)
+            total = 0.0
+            for p in sorted(persons[is_ill[persons]].tolist()):   # the oracle sums in person order (Trove's order is not reproducible)
+                te = t - float(exposure[p])
+                v = 0.0
+                if L <= te < I:
+                    v = vmax * ((te - L) / (I - L))
+                elif I <= te < I + Cc:
+                    v = vmax * ((I + Cc - te) / Cc)
+                if v > 0:
+                    total += factor * duration * (1 / (1 + math.exp(-r * (v - v0))))
+            if factor == 0.0 or total == 0.0:
+                continue
+            p_inf = 1.0 - math.exp(-total)
         bits = int(np.float64(t).view(np.uint64))
         for p in sorted(persons[susceptible[persons]].tolist()):
             if ob.u01(seed, p, bits, 0) < p_inf:
@@ -554,7 +580,7 @@ def test_driver_matches_a_brute_force_statement_of_the_contract():
                 exposure[p] = np.float32(t)     # exposure time is a float (C4)
                 events.append((t, p, loc, int(scn.sub[i]), p_inf))
     events.sort()
-    assert len(events) > 25 and len(events) == len(got["person"])
+    assert len(events) > 15 and len(events) == len(got["person"])
     assert [e[1] for e in events] == got["person"].tolist()
     assert [e[0] for e in events] == got["time"].tolist()
     assert [e[2] for e in events] == got["loc"].tolist() and [e[3] for e in events] == got["sub"].tolist()
