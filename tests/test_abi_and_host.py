@@ -550,3 +550,41 @@ def test_schedule_tables_are_range_checked_on_the_host():
     # -1 = "none" stays legal everywhere it means that
     ok = {**broken("work_loc", worker, -1), **broken("nearest", (3, 6), -1)}
     assert _validate(city, tables, **ok)[0] == 0
+
+
+def test_java_and_python_bindings_agree_with_the_header():
+    """integration/java/eu/heros/gpu/HerosGpuNative.java (generated by tools/gen_java_binding.py; the Panama FFM handles a
+    maintainer of the reference adds) is up to date with include/heros_gpu.h, and the ctypes table of the Python binding
+    describes the same prototypes: same functions, same arity, pointers where the header has pointers, 32 / 64-bit
+    integers and doubles where it has those."""
+    import importlib.util
+    import subprocess
+    import sys
+    gen = os.path.join(ROOT, "tools", "gen_java_binding.py")
+    assert subprocess.run([sys.executable, gen, "--check"]).returncode == 0
+    spec = importlib.util.spec_from_file_location("gen_java_binding", gen)
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    protos = g.prototypes(open(os.path.join(ROOT, "include", "heros_gpu.h")).read())
+    assert sorted(n for _, n, _ in protos) == header_functions() == sorted(_lib.SIGNATURES)
+    java = open(g.OUT).read()
+    kind = {C.c_int32: "JAVA_INT", C.c_uint32: "JAVA_INT", C.c_int64: "JAVA_LONG", C.c_uint64: "JAVA_LONG",
+            C.c_double: "JAVA_DOUBLE", C.c_int16: "JAVA_SHORT", C.c_float: "JAVA_FLOAT"}
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert len(argtypes) == len(params), name
+        layouts = [g.layout(ret)] + [g.layout(t) for t, _ in params]
+        assert f'fn("{name}",\n            FunctionDescriptor.of({", ".join(layouts)}));' in java, name
+        for ctype, lay in zip([restype] + list(argtypes), layouts):
+            got = kind.get(ctype, "ADDRESS")     # c_void_p, c_char_p, POINTER(...) are addresses
+            assert got == lay, (name, ctype, lay)
+    # the struct layouts: same sizes as the ctypes mirrors (natural alignment, no implicit padding), every field named
+    all_structs = g.structs(open(os.path.join(ROOT, "include", "heros_gpu.h")).read())
+    mirrors = dict(heros_config=_lib.Config, heros_area_params=_lib.AreaParams, heros_dist_params=_lib.DistParams,
+                   heros_duration=_lib.Duration, heros_prog_params=_lib.ProgParams, heros_step_stats=_lib.StepStats,
+                   heros_activity=_lib.Activity)
+    assert set(all_structs) == set(mirrors)
+    for name, mirror in mirrors.items():
+        assert g.struct_size(name, all_structs) == C.sizeof(mirror), name
+        assert f"{name.upper()}_LAYOUT = MemoryLayout.structLayout(" in java
+        assert [f for f, _, _ in all_structs[name]] == [f for f, *_ in mirror._fields_], name
