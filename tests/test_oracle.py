@@ -488,21 +488,11 @@ def test_single_calls_match_an_independent_restatement_of_the_formulas():
     assert n_p > 200
 
 
-@pytest.mark.parametrize("model,trigger", [("area", "exit"), ("distance", "exit"), ("area", "both"), ("distance", "both")])
-def test_driver_matches_a_brute_force_statement_of_the_contract(model, trigger):
-    """The oracle's event-by-event driver against a second statement of the driver contract (SURVEY.md 3.2 C1-C8)
-    written here as a plain loop over the movement events in time order (exits before enters at equal times; enters only
-    with the ENTER_AND_EXIT trigger): per sub-location lastCalculation with the threshold rule, the set S(t-) = {stays:
-    t_in < t <= t_out}, the formula of the model, keyed draws, a person is infected once.  Four days with the seeds
-    exposed at t = 0: nobody infected later turns contagious inside the run (48 h latent period from an exposure
-    >= 48 h), so the comparison does not involve the progression draws."""
-    from common import Scenario
-    scn = Scenario(seed=21, n_persons=160, n_households=60, n_workplaces=8, n_shops=3, days=4, tie_fraction=0.25,
-                   short_gap_fraction=0.15)
+def brute_force_run(model, trigger, scn, seed=4711):
+    """(events of the brute-force statement, infections of the oracle) for one scenario"""
     props = load_props(model)
     props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "25.0" if model == "area" else "3.0"
     a, d, prog = oracle_props(props)
-    seed = 4711
     kind = ob.MODEL_AREA if model == "area" else ob.MODEL_DIST
     sim = ob.Sim(kind, ob.TRIGGER_EXIT_ONLY if trigger == "exit" else ob.TRIGGER_ENTER_AND_EXIT, seed)
     sim.set_area(a) if model == "area" else sim.set_dist(d)
@@ -580,6 +570,21 @@ def test_driver_matches_a_brute_force_statement_of_the_contract(model, trigger):
                 exposure[p] = np.float32(t)     # exposure time is a float (C4)
                 events.append((t, p, loc, int(scn.sub[i]), p_inf))
     events.sort()
+    return events, got
+
+
+@pytest.mark.parametrize("model,trigger", [("area", "exit"), ("distance", "exit"), ("area", "both"), ("distance", "both")])
+def test_driver_matches_a_brute_force_statement_of_the_contract(model, trigger):
+    """The oracle's event-by-event driver against a second statement of the driver contract (SURVEY.md 3.2 C1-C8)
+    written here as a plain loop over the movement events in time order (exits before enters at equal times; enters only
+    with the ENTER_AND_EXIT trigger): per sub-location lastCalculation with the threshold rule, the set S(t-) = {stays:
+    t_in < t <= t_out}, the formula of the model, keyed draws, a person is infected once.  Four days with the seeds
+    exposed at t = 0: nobody infected later turns contagious inside the run (48 h latent period from an exposure
+    >= 48 h), so the comparison does not involve the progression draws."""
+    from common import Scenario
+    scn = Scenario(seed=21, n_persons=160, n_households=60, n_workplaces=8, n_shops=3, days=4, tie_fraction=0.25,
+                   short_gap_fraction=0.15)
+    events, got = brute_force_run(model, trigger, scn)
     assert len(events) > 15 and len(events) == len(got["person"])
     assert [e[1] for e in events] == got["person"].tolist()
     assert [e[0] for e in events] == got["time"].tolist()
