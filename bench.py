@@ -201,16 +201,25 @@ def run_reference(args):
     timed = secs[args.preroll + args.warmup:]
     seconds = float(np.sum(timed))
     value = city.n_persons * 24.0 * args.steps / seconds
+    # the same workload description as the GPU arm's at this N (the sample that was timed is one tile of it)
+    world = max(int(args.gpus), 1)
+    n_commuters = 0
+    if world > 1 and args.commute > 0:
+        tile = scenario.City(args.persons, seed=CITY_SEED)
+        other = scenario.City(args.persons, seed=CITY_SEED + (1 % world), origin_m=(12000.0 * (1 % world), 0.0))
+        n_commuters = tile.add_commuters(other, args.commute, seed=1000)
+        del tile, other
     line = {
         "impl": "reference", "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, city, 1, 0),
+        "config": workload_config(args, city, world, n_commuters),
         "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": 1, "kind": "port",
                          "sample": f"{args.steps} simulated days (days {args.preroll + args.warmup}.."
-                                   f"{total - 1}) of one city tile, oracle/heros_oracle.c single-threaded (a replication "
-                                   f"of the reference is single-threaded by construction)"},
+                                   f"{total - 1}) of one city tile" + (f" of the {world}, without its cross-tile commuters" if world > 1 else "") +
+                                   ", oracle/heros_oracle.c single-threaded (a replication of the reference is "
+                                   "single-threaded by construction; throughput per core does not depend on the number of tiles)"},
         "e2e": {"value": value, "unit": "person-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "infections": int(sim.phase_counts()[1:].sum()),
