@@ -508,7 +508,7 @@ def brute_force_run(model, trigger, scn, seed=4711):
     order = np.lexsort((got["person"], got["time"]))
     got = {k: v[order] for k, v in got.items()}
 
-    # ---- the brute-force statement ----
+    # ---- the brute-force statement: one movement at a time, occupancy kept as plain sets ----
     pB, beta, tmin, tmode, tmax, thr = 25.0, 1.0, 48.0, 81.6, 230.4, 60.0 / 3600.0
     L, I, Cc, vmax, v0, r, psi, alpha, mu = 48.0, 81.6, 148.8, 7.23, 4.0, 2.294, 1.0, 3.0, 0.0
     susceptible = np.ones(scn.n_persons, bool)
@@ -516,42 +516,24 @@ def brute_force_run(model, trigger, scn, seed=4711):
     exposure = np.zeros(scn.n_persons, np.float32)
     is_ill = ~susceptible                       # the seeds stay ill for the whole run (E -> I(A) / I(S), never out in 4 days)
     key = scn.loc.astype(np.int64) * 1000 + scn.sub
-    last_calc = {}
-    events = []
+    occupants, last_calc, events = {}, {}, []
     moves = [(float(scn.t_out[i]), 0, int(key[i]), int(scn.person[i]), i) for i in range(scn.n_visits)
-             if np.isfinite(scn.t_out[i]) and scn.t_out[i] < horizon]
-    if trigger == "both":
-        moves += [(float(scn.t_in[i]), 1, int(key[i]), int(scn.person[i]), i) for i in range(scn.n_visits) if scn.t_in[i] < horizon]
-    for t, _, k, _, i in sorted(moves):
-        duration = t - last_calc.get(k, 0.0)
-        if duration < thr:
-            continue                            # not calculated: the interval keeps accumulating (C6)
-        last_calc[k] = t
-        present = np.nonzero((key == k) & (scn.t_in < t) & (t <= scn.t_out))[0]      # a leaver is still counted, an enterer not yet (C5)
-        persons = scn.person[present]
-        loc = int(scn.loc[i])
-        area = float(np.float32(scn.loc_area[loc])) / int(scn.loc_nsub[loc])
-        if model == "area":
-            factor = -beta * pB * duration / (float(scn.type_corr[scn.loc_type[loc]]) * area)
-            total = 0.0
-            for p in persons[is_ill[persons]]:
-                te = t - float(exposure[p])
-                if tmin <= te < tmode:
-                    total += (te - tmin) / (tmode - tmin)
-                elif tmode <= te <= tmax:
-                    total += (tmax - te) / (tmax - tmode)
-            if factor == 0.0 or total == 0.0:
+             if scn.t_out[i] > scn.t_in[i] and np.isfinite(scn.t_out[i]) and scn.t_out[i] < horizon]
+    moves += [(float(scn.t_in[i]), 1, int(key[i]), int(scn.person[i]), i) for i in range(scn.n_visits)
+              if scn.t_out[i] > scn.t_in[i] and scn.t_in[i] < horizon]
+
+    def contagion(persons, t, duration, factor):
+        total = 0.0
+        for p in sorted(persons):               # the oracle sums in person order (Trove's order is not reproducible)
+            if not is_ill[p]:
                 continue
-            p_inf = 1.0 - math.exp(factor * total)
-        else:
-            if len(persons) == 0:
-                continue                        # sqrt(area / 0) = inf, nobody there: nothing to sum, nobody to infect
-            delta = math.sqrt(area / len(persons))
-            sigma = 1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, psi) - 1.5)))
-            factor = sigma * alpha * (1.0 - mu) * (1.0 - mu)
-            total = 0.0
-            for p in sorted(persons[is_ill[persons]].tolist()):   # the oracle sums in person order (Trove's order is not reproducible)
-                te = t - float(exposure[p])
+            te = t - float(exposure[p])
+            if model == "area":
+                if tmin <= te < tmode:
+                    total += (te - tmin) / (tmode - tmin) if factor < 0 else te / (tmode - tmin)
+                elif tmode <= te <= tmax:
+                    total += (tmax - te) / (tmax - tmode) if factor < 0 else 1.0 - te / (tmax - tmode)
+            else:
                 v = 0.0
                 if L <= te < I:
                     v = vmax * ((te - L) / (I - L))
@@ -559,16 +541,47 @@ def brute_force_run(model, trigger, scn, seed=4711):
                     v = vmax * ((I + Cc - te) / Cc)
                 if v > 0:
                     total += factor * duration * (1 / (1 + math.exp(-r * (v - v0))))
-            if factor == 0.0 or total == 0.0:
-                continue
-            p_inf = 1.0 - math.exp(-total)
-        bits = int(np.float64(t).view(np.uint64))
-        for p in sorted(persons[susceptible[persons]].tolist()):
-            if ob.u01(seed, p, bits, 0) < p_inf:
-                susceptible[p] = False
-                is_ill[p] = True
-                exposure[p] = np.float32(t)     # exposure time is a float (C4)
-                events.append((t, p, loc, int(scn.sub[i]), p_inf))
+        return total
+
+    for t, enter, k, who, i in sorted(moves):   # exits before enters at equal times, then by sub-location, then by person
+        here = occupants.setdefault(k, set())
+        if not enter or trigger == "both":
+            duration = t - last_calc.get(k, 0.0)
+            if duration >= thr:                 # else not calculated: the interval keeps accumulating (C6)
+                last_calc[k] = t
+                loc = int(scn.loc[i])
+                nsub, total_area = int(scn.loc_nsub[loc]), float(np.float32(scn.loc_area[loc]))
+                corr = float(scn.type_corr[scn.loc_type[loc]])
+                whole = not scn.type_infect_sub[scn.loc_type[loc]] and nsub >= 2      # the total-location branch
+                group = set(here)               # a leaver is still counted, an enterer not yet (C5)
+                if whole:
+                    group = set().union(*(occupants.get(loc * 1000 + z, set()) for z in range(nsub)))
+                p_inf = None
+                if model == "area":
+                    factor = (beta * pB * duration / (corr * total_area)) if whole else (-beta * pB * duration / (corr * (total_area / nsub)))
+                    total = contagion(group, t, duration, factor)
+                    if factor != 0.0 and total != 0.0:
+                        p_inf = 1.0 - math.exp(factor * total)
+                elif len(here) > 0:             # sqrt(area / 0) = inf with nobody in the sub-location: factor 0
+                    delta = math.sqrt((total_area if whole else total_area / nsub) / len(here))
+                    factor = (1.0 - 1.0 / (1.0 + math.exp(-3.0 * (max(delta, psi) - 1.5)))) * alpha * (1.0 - mu) * (1.0 - mu)
+                    total = contagion(group, t, duration, factor)
+                    if factor != 0.0 and total != 0.0:
+                        p_inf = 1.0 - math.exp(-total)
+                if p_inf is not None:
+                    bits = int(np.float64(t).view(np.uint64))
+                    for p in sorted(group):
+                        if susceptible[p] and ob.u01(seed, p, bits, 0) < p_inf:
+                            susceptible[p] = False
+                            is_ill[p] = True
+                            exposure[p] = np.float32(t)     # exposure time is a float (C4)
+                            # the event is reported with the sub-location of the evaluation (the InfectionRecord's
+                            # location); in the total-location branch the person may stand in another zone
+                            events.append((t, p, loc, int(scn.sub[i]), p_inf))
+        if enter:
+            here.add(who)
+        else:
+            here.discard(who)
     events.sort()
     return events, got
 
@@ -576,16 +589,18 @@ def brute_force_run(model, trigger, scn, seed=4711):
 @pytest.mark.parametrize("model,trigger", [("area", "exit"), ("distance", "exit"), ("area", "both"), ("distance", "both")])
 def test_driver_matches_a_brute_force_statement_of_the_contract(model, trigger):
     """The oracle's event-by-event driver against a second statement of the driver contract
-    written here as a plain loop over the movement events in time order (exits before enters at equal times; enters only
-    with the ENTER_AND_EXIT trigger): per sub-location lastCalculation with the threshold rule, the set S(t-) = {stays:
-    t_in < t <= t_out}, the formula of the model, keyed draws, a person is infected once.  Four days with the seeds
+    written here as a plain loop over the movements in time order with the occupancy kept as sets (exits before enters
+    at equal times; enters trigger only with ENTER_AND_EXIT): per sub-location lastCalculation with the threshold rule,
+    the leaver still counted and the enterer not yet, the formula of the model -- sub-location and total-location
+    branch, the parks of the scenario have infectInSublocation = false and three zones --, keyed draws, a person is
+    infected once.  Four days with the seeds
     exposed at t = 0: nobody infected later turns contagious inside the run (48 h latent period from an exposure
     >= 48 h), so the comparison does not involve the progression draws."""
     from common import Scenario
     scn = Scenario(seed=21, n_persons=160, n_households=60, n_workplaces=8, n_shops=3, days=4, tie_fraction=0.25,
-                   short_gap_fraction=0.15)
+                   short_gap_fraction=0.15, n_parks=2, park_nsub=3)
     events, got = brute_force_run(model, trigger, scn)
-    assert len(events) > 15 and len(events) == len(got["person"])
+    assert len(events) > 10 and len(events) == len(got["person"])
     assert [e[1] for e in events] == got["person"].tolist()
     assert [e[0] for e in events] == got["time"].tolist()
     assert [e[2] for e in events] == got["loc"].tolist() and [e[3] for e in events] == got["sub"].tolist()
