@@ -12,8 +12,9 @@ engine the Java host keeps); they are recorded once, untimed, and replayed, so t
   value : whole-job person-hours / s with every day's stays already resident in HBM (heros_submit_visits_device)
   e2e   : the same through the C ABI with pinned HOST buffers: H2D of the day's stays, heros_step, D2H of the phase
           counters and the new infection events, all inside the timed region
-  --impl reference : the CPU oracle (sequential event-by-event restatement of the reference, one core) on the same
-          city and days
+  --impl reference : the CPU oracle (sequential event-by-event restatement of the reference) on the same city and
+          days, on all host cores the way the reference's authors fill a server: one single-threaded replication
+          (seed) per core, aggregate throughput; the single-replication figure is reported beside it
 
 N > 1 (launched by torch.distributed.run, one rank per GPU): weak scaling.  Every rank owns one city tile of the
 configured size (persons + locations, tiles side by side); --commute of the workers of a tile work in the next tile,
@@ -56,6 +57,8 @@ def parse_args():
     ap.add_argument("--model", default="distance", choices=["area", "distance"])
     ap.add_argument("--trigger", default="exit", choices=["exit", "both"])
     ap.add_argument("--cpu-days", type=int, default=14, help="days of the bounded cpu_baseline sample (about 12 s of CPU work)")
+    ap.add_argument("--ref-cores", type=int, default=0,
+                    help="--impl reference: replications run side by side (0 = one per available host core, at most 64)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: kernels write into the peers' memory over NVLink (CUDA IPC), or NCCL all-to-alls")
     ap.add_argument("--commute", type=float, default=0.05,
@@ -147,14 +150,14 @@ class ClockSampler:
                 "source": "NVML, every 10 ms during the timed region" if self._nvml is not None else "nvidia-smi"}
 
 
-def oracle_objects(args, props, city):
+def oracle_objects(args, props, city, seed=SEED):
     from oracle import binding as ob
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import oracle_props
     area, dist, prog = oracle_props(props)
     model = ob.MODEL_AREA if args.model == "area" else ob.MODEL_DIST
     trig = ob.TRIGGER_EXIT_ONLY if args.trigger == "exit" else ob.TRIGGER_ENTER_AND_EXIT
-    sim = ob.Sim(model, trig, SEED)
+    sim = ob.Sim(model, trig, seed)
     if model == ob.MODEL_AREA:
         sim.set_area(area)
     else:
@@ -175,32 +178,81 @@ def keyed_seeds(city, seed, n):
     return np.sort(order[:n]).astype(np.int32)
 
 
+def _replication_worker(w, args, props, city, total, barrier, times):
+    """One replication (seed SEED + w) of the oracle in its own process; every day's stays are generated untimed, then
+    all replications run their day side by side between two barriers."""
+    from heros_b200 import scenario
+    seed = SEED + w
+    sim = oracle_objects(args, props, city, seed)
+    seeds = keyed_seeds(city, seed, N_INFECTED)
+    sim.expose(seeds, np.zeros(len(seeds)))
+    gen = scenario.ScheduleGenerator(city, seed)
+    for d in range(total):
+        st = gen.generate_day(sim.agent_state()["phase"])
+        barrier.wait()
+        times[2 * (w * total + d)] = time.perf_counter()          # CLOCK_MONOTONIC: one clock for all processes
+        sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+        sim.run(24.0 * (d + 1))
+        times[2 * (w * total + d) + 1] = time.perf_counter()
+        barrier.wait()
+    times[2 * args.ref_workers_total * total + w] = float(sim.phase_counts()[1:].sum())
+
+
+def host_cores():
+    """Cores this process may use: the affinity mask, cut by the cgroup CPU quota of a container."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the sequential oracle; the JVM reference is
-    not runnable here: no JDK, medlabs / DSOL jars not vendored).  One core: a replication is single-threaded by
-    construction in the reference (server/*.sh start one JVM per seed)."""
+    not runnable here: no JDK, medlabs / DSOL jars not vendored) on all the host threads it can use.  A replication is
+    single-threaded by construction in the reference; its authors fill a server by starting one JVM per seed
+    (src/main/resources/server/*.sh: seeds 111..120 side by side), so that is what this arm does: one oracle process
+    per host core, seeds SEED, SEED+1, ..., the same city and days; the value is the aggregate over the replications
+    (persons x 24 h x days x replications / wall time of the days, every day timed from the first start to the last
+    finish).  cpu_baseline.one_replication holds the single-core figure of replication 0 beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     from heros_b200 import scenario
+    from oracle import binding as ob
+    ob.lib()                                                      # built and loaded before the fork
     props = load_props(args.model)
     city = scenario.City(args.persons, seed=CITY_SEED)
-    sim = oracle_objects(args, props, city)
-    seeds = keyed_seeds(city, SEED, N_INFECTED)
-    sim.expose(seeds, np.zeros(len(seeds)))
-    gen = scenario.ScheduleGenerator(city, SEED)
+    workers = args.ref_cores if args.ref_cores > 0 else min(host_cores(), 64)
     total = args.preroll + args.warmup + args.steps
-    secs = []
-    for d in range(total):
-        phase = sim.agent_state()["phase"]
-        st = gen.generate_day(phase)
-        t = time.perf_counter()
-        sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
-        sim.run(24.0 * (d + 1))
-        secs.append(time.perf_counter() - t)
-    timed = secs[args.preroll + args.warmup:]
-    seconds = float(np.sum(timed))
-    value = city.n_persons * 24.0 * args.steps / seconds
+    args.ref_workers_total = workers
+    ctx = mp.get_context("fork")                                  # the city tables are shared copy-on-write
+    barrier = ctx.Barrier(workers)
+    times = ctx.Array("d", 2 * workers * total + workers, lock=False)
+    procs = [ctx.Process(target=_replication_worker, args=(w, args, props, city, total, barrier, times), daemon=True)
+             for w in range(workers)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join()
+    if any(p.exitcode != 0 for p in procs):
+        raise SystemExit("a replication of the reference arm failed: exit codes " + str([p.exitcode for p in procs]))
+    t = np.asarray(times[:2 * workers * total]).reshape(workers, total, 2)
+    first = args.preroll + args.warmup
+    day_wall = t[:, first:, 1].max(axis=0) - t[:, first:, 0].min(axis=0)      # per timed day: first start .. last finish
+    seconds = float(day_wall.sum())
+    value = workers * city.n_persons * 24.0 * args.steps / seconds
+    own = float((t[0, first:, 1] - t[0, first:, 0]).sum())
+    one_replication = city.n_persons * 24.0 * args.steps / own
+    infections = [int(x) for x in times[2 * workers * total:]]
     # the same workload description as the GPU arm's at this N (the sample that was timed is one tile of it)
     world = max(int(args.gpus), 1)
     n_commuters = 0
@@ -215,14 +267,19 @@ def run_reference(args):
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, city, world, n_commuters),
-        "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.steps} simulated days (days {args.preroll + args.warmup}.."
-                                   f"{total - 1}) of one city tile" + (f" of the {world}, without its cross-tile commuters" if world > 1 else "") +
-                                   ", oracle/heros_oracle.c single-threaded (a replication of the reference is "
-                                   "single-threaded by construction; throughput per core does not depend on the number of tiles)"},
+        "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": workers, "kind": "port",
+                         "host_cores": host_cores(),
+                         "one_replication": {"value": one_replication, "unit": "person-hours/s", "cores": 1,
+                                             "what": "replication 0 alone on its core while the others run beside it"},
+                         "sample": f"{args.steps} simulated days (days {first}..{total - 1}) of one city tile"
+                                   + (f" of the {world}, without its cross-tile commuters" if world > 1 else "") +
+                                   f", {workers} replications (seeds {SEED}..{SEED + workers - 1}) side by side, one "
+                                   "oracle/heros_oracle.c process per core as the reference's server scripts start one "
+                                   "single-threaded JVM per seed; value = aggregate over the replications; "
+                                   "ms_per_step = wall time of one simulated day of all of them"},
         "e2e": {"value": value, "unit": "person-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "infections": int(sim.phase_counts()[1:].sum()),
+        "infections": infections[0], "infections_per_replication": infections,
     }
     emit(line)
 
