@@ -214,6 +214,32 @@ def host_cores():
     return n
 
 
+def host_memory_bytes():
+    """Memory this process may still take: MemAvailable, cut by the cgroup limit of a container."""
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for row in f:
+                if row.startswith("MemAvailable:"):
+                    avail = int(row.split()[1]) * 1024
+    except OSError:
+        pass
+    try:
+        with open("/sys/fs/cgroup/memory.max") as f:
+            limit = f.read().strip()
+        if limit != "max":
+            used = 0
+            try:
+                with open("/sys/fs/cgroup/memory.current") as f:
+                    used = int(f.read())
+            except (OSError, ValueError):
+                pass
+            avail = min(avail, int(limit) - used) if avail is not None else int(limit) - used
+    except (OSError, ValueError):
+        pass
+    return avail
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the sequential oracle; the JVM reference is
     not runnable here: no JDK, medlabs / DSOL jars not vendored) on all the host threads it can use.  A replication is
@@ -232,6 +258,9 @@ def run_reference(args):
     props = load_props(args.model)
     city = scenario.City(args.persons, seed=CITY_SEED)
     workers = args.ref_cores if args.ref_cores > 0 else min(host_cores(), 64)
+    mem = host_memory_bytes()
+    if args.ref_cores <= 0 and mem is not None:                   # a replication holds ~1 KB per person beside the shared city
+        workers = max(1, min(workers, int(0.5 * mem / (2048.0 * args.persons + 2.5e8))))
     total = args.preroll + args.warmup + args.steps
     args.ref_workers_total = workers
     ctx = mp.get_context("fork")                                  # the city tables are shared copy-on-write
