@@ -19,8 +19,9 @@ engine the Java host keeps); they are recorded once, untimed, and replayed, so t
 N > 1 (launched by torch.distributed.run, one rank per GPU): weak scaling.  Every rank owns one city tile of the
 configured size (persons + locations, tiles side by side); --commute of the workers of a tile work in the next tile,
 so every window exchanges the stays of those commuters (with their packed agent words) and sends the candidate
-infections back -- two NCCL all-to-alls per window (heros_b200.sharded).  Timing: CUDA events on the engine stream,
-max over ranks.
+infections back -- written by the pack / export kernels straight into the peers' memory over NVLink (--exchange p2p,
+the default; csrc/exchange.cu) or as two NCCL all-to-alls per window (--exchange nccl; heros_b200.sharded).  Timing:
+CUDA events on the engine stream, max over ranks.
 
 usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
