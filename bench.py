@@ -190,12 +190,12 @@ def _replication_worker(w, args, props, city, total, barrier, times):
     gen = scenario.ScheduleGenerator(city, seed)
     for d in range(total):
         st = gen.generate_day(sim.agent_state()["phase"])
-        barrier.wait()
+        barrier.wait(timeout=900)                                  # a replication that died breaks the barrier for all
         times[2 * (w * total + d)] = time.perf_counter()          # CLOCK_MONOTONIC: one clock for all processes
         sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
         sim.run(24.0 * (d + 1))
         times[2 * (w * total + d) + 1] = time.perf_counter()
-        barrier.wait()
+        barrier.wait(timeout=900)                                  # a replication that died breaks the barrier for all
     times[2 * args.ref_workers_total * total + w] = float(sim.phase_counts()[1:].sum())
 
 
