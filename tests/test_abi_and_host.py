@@ -588,3 +588,47 @@ def test_java_and_python_bindings_agree_with_the_header():
         assert g.struct_size(name, all_structs) == C.sizeof(mirror), name
         assert f"{name.upper()}_LAYOUT = MemoryLayout.structLayout(" in java
         assert [f for f, _, _ in all_structs[name]] == [f for f, *_ in mirror._fields_], name
+
+
+def test_hand_written_java_layer_uses_the_generated_handles_consistently():
+    """integration/java/eu/heros/gpu/{HerosGpu, GpuCovid19Transmission, GpuCovid19Progression, GpuWindow}.java cannot be
+    compiled here (no JDK); what can be checked is checked: every handle and layout they name exists in the generated
+    HerosGpuNative.java, every invokeExact passes as many arguments as the C prototype has parameters, its int result is
+    taken (invokeExact is signature-exact), and the struct fields addressed by name exist in the header's structs."""
+    import importlib.util
+    import re
+    gen = os.path.join(ROOT, "tools", "gen_java_binding.py")
+    spec = importlib.util.spec_from_file_location("gen_java_binding", gen)
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    header = open(os.path.join(ROOT, "include", "heros_gpu.h")).read()
+    arity = {"heros_" + n[len("heros_"):]: len(params) for _, n, params in g.prototypes(header)}
+    java_dir = os.path.dirname(g.OUT)
+    native = open(g.OUT).read()
+    handle_of = dict(re.findall(r"MethodHandle (\w+) = fn\(\"(\w+)\"", native))
+    layouts = set(re.findall(r"StructLayout (\w+) =", native))
+    fields = set(re.findall(r'withName\("(\w+)"\)', native))
+    files = [f for f in sorted(os.listdir(java_dir)) if f.endswith(".java") and f != os.path.basename(g.OUT)]
+    assert {"HerosGpu.java", "GpuCovid19Transmission.java", "GpuCovid19Progression.java", "GpuWindow.java"} <= set(files)
+    calls = 0
+    for name in files:
+        src = open(os.path.join(java_dir, name)).read()
+        for ref in re.findall(r"HerosGpuNative\.(\w+)", src):
+            assert ref in handle_of or ref in layouts, (name, ref)
+        for f in re.findall(r'groupElement\("(\w+)"\)', src) + re.findall(r'offset\("(\w+)"\)', src):
+            assert f in fields, (name, f)
+        for m in re.finditer(r"HerosGpuNative\.(\w+)\.invokeExact\(", src):
+            depth, commas, i = 1, 0, m.end()
+            empty = src[i:].lstrip().startswith(")")
+            while depth:
+                c = src[i]
+                depth += c in "([{"
+                depth -= c in ")]}"
+                commas += c == "," and depth == 1
+                i += 1
+            n_args = 0 if empty else commas + 1
+            assert n_args == arity[handle_of[m.group(1)]], (name, m.group(1), n_args)
+            before = src[max(0, m.start() - 40):m.start()]
+            assert re.search(r"\((int|MemorySegment)\)\s*$", before), (name, m.group(1), "result of invokeExact not taken")
+            calls += 1
+    assert calls >= 15
