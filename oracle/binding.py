@@ -196,7 +196,10 @@ class Sim:
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except TypeError:       # interpreter shutdown: the module globals are already gone
+            pass
 
     def set_area(self, props):
         lib().orc_sim_set_area(self._h, C.byref(props))

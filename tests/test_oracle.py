@@ -267,6 +267,63 @@ def test_driver_progression_matches_golden_timing_band():
     assert sim2.n_evaluations() == 2
 
 
+def test_incubation_period_against_the_reference_curves():
+    """The only reference-produced sample of a sojourn time: in seed comparison.xlsx the 100 persons exposed at t = 0 are
+    the only ones that can be infectious before 54.5 h + 60 h, so I(A) + I(S) over hours 48..96 is 100 x the empirical
+    CDF of the incubation period -- Triangular(2.5, 3.4, 3.8) days drawn by DSOL's DistTriangular and converted by
+    medlabs' DurationDistribution(TimeUnit.DAY), both outside the reference tree.  Checked here:
+    (1) the reference's sample against the closed-form triangular CDF in hours, (2) the oracle's own incubation times
+    (its inverse-CDF statement, keyed Philox uniforms) against the reference's sample, (3) the asymptomatic split of
+    the 4 x 100 initial cases against covidP.FractionAsymptomatic = 0.46 and against the oracle's split.
+    The four sheets carry the SAME infectious-count series (the duration draws of the reference do not depend on
+    generic.Seed; only the split does), so the incubation sample has 100 members, not 400."""
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
+        seeds = json.load(f)["seeds"]
+    series = {k: v["infectious_48_96h"] for k, v in seeds.items()}
+    t = 48.0 + 0.5 * np.arange(len(series["111"]["asymptomatic"]))
+    total = {k: np.array(v["asymptomatic"]) + np.array(v["symptomatic"]) for k, v in series.items()}
+    for k in total:
+        assert (total[k] == total["111"]).all() and total[k][-1] == 100 and total[k][t < 60.0].max() == 0
+    ecdf = total["111"] / 100.0
+    assert (np.diff(ecdf) >= 0).all() and ecdf[t >= 91.5].min() == 1.0     # support [60 h, 91.2 h]
+
+    lo, mode, hi = 2.5 * 24, 3.4 * 24, 3.8 * 24
+
+    def tri_cdf(x):
+        x = np.clip(x, lo, hi)
+        return np.where(x < mode, (x - lo) ** 2 / ((hi - lo) * (mode - lo)), 1 - (hi - x) ** 2 / ((hi - lo) * (hi - mode)))
+
+    ks_crit_100 = 1.36 / math.sqrt(100)                       # 5 % two-sided, n = 100
+    # (1) a count sampled at t holds the transitions of (t - 0.5, t]: the model CDF lies between F(t - 0.5) and F(t)
+    d1 = np.maximum(ecdf - tri_cdf(t), tri_cdf(t - 0.5) - ecdf).max()
+    assert d1 < ks_crit_100, d1
+    # ... and the sample does tell shapes apart: a uniform or a symmetric triangular on the same support is rejected
+    uni = np.clip((t - lo) / (hi - lo), 0, 1)
+    mid = 0.5 * (lo + hi)
+    sym = np.where(t < mid, 2 * (np.clip(t, lo, hi) - lo) ** 2 / (hi - lo) ** 2, 1 - 2 * (hi - np.clip(t, lo, hi)) ** 2 / (hi - lo) ** 2)
+    assert np.abs(ecdf - uni).max() > ks_crit_100 and np.abs(ecdf - sym).max() > ks_crit_100
+
+    # (2) the oracle: 4 000 persons exposed at t = 0, their E -> I transition times
+    n = 4000
+    sim = small_sim(n=n)
+    sim.expose(np.arange(n), np.zeros(n))
+    sim.run(96.0)
+    tr = sim.transitions()
+    onset = tr["time"][(tr["phase"] == IA) | (tr["phase"] == IS)]
+    assert len(onset) == n and onset.min() >= lo and onset.max() <= hi
+    oracle_cdf = np.searchsorted(np.sort(onset), t, side="right") / n
+    d2 = np.abs(oracle_cdf - ecdf).max()
+    assert d2 < 1.36 * math.sqrt((100 + n) / (100.0 * n)), d2
+    assert np.abs(oracle_cdf - tri_cdf(t)).max() < 1.36 / math.sqrt(n)      # and the oracle against the closed form
+
+    # (3) 184 of the 400 initial cases of the four sheets are asymptomatic: 0.46 on the nose
+    asym = sum(v["asymptomatic"][-1] for v in series.values())
+    sigma = math.sqrt(0.46 * 0.54 / 400)
+    assert abs(asym / 400.0 - 0.46) < 2 * sigma
+    oracle_asym = float((tr["phase"] == IA).sum()) / n
+    assert abs(oracle_asym - asym / 400.0) < 2 * math.sqrt(0.46 * 0.54 * (1 / 400 + 1 / n))
+
+
 def test_compartment_series_from_the_transition_log():
     """DiseaseMonitor mirror (ConstructHerosModel.java:145): the 0.5 h compartment series rebuilt from the transition
     log equals the live phase counters at every day boundary, keeps the population constant, and has the column

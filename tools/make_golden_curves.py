@@ -1,7 +1,8 @@
 """Extracts the reference-produced epidemic curve of seed 111 from /root/reference/"seed comparison.xlsx" (the only
 numbers the reference publishes for this path) into tests/golden/seed_comparison_111.json: the daily compartment
 counts, the hour-of-day histogram of new exposures (decrease of Susceptible between two 0.5 h samples, binned by the
-time of day of the later sample) and the first exposure / first infectious times.  Run in the build container
+time of day of the later sample), the first exposure / first infectious times and the half-hourly I(A) / I(S) counts
+of hours 48..96 (the incubation of the 100 initial cases).  Run in the build container
 (the reference tree does not travel to the GPU box); the JSON is committed."""
 import json
 import os
@@ -29,7 +30,12 @@ for sheet in ("111", "112", "113", "114"):
         "new_exposures_by_half_hour_of_day": hist.astype(int).tolist(),
         "first_exposure_h": float(t[1:][new > 0][0]), "first_infectious_h": float(t[infectious > 0][0]),
         "all_seeds_infectious_by_h": float(t[a[:, 2] + 0 * t < 1e9][np.argmax(infectious >= 100)]),
-        "peak_symptomatic": [float(t[np.argmax(a[:, 4])]), int(a[:, 4].max())], "final_recovered": int(a[-1, 8])}
+        "peak_symptomatic": [float(t[np.argmax(a[:, 4])]), int(a[:, 4].max())], "final_recovered": int(a[-1, 8]),
+        # the 100 persons exposed at t = 0 turn infectious between 60 h and 91.2 h; nobody exposed later can before
+        # 54.5 + 60 h, so I(A) + I(S) over 48..96 h is 100 x the empirical CDF of the incubation period
+        "infectious_48_96h": {"t0": 48.0, "dt": 0.5,
+                              "asymptomatic": a[(t >= 48) & (t <= 96), 3].astype(int).tolist(),
+                              "symptomatic": a[(t >= 48) & (t <= 96), 4].astype(int).tolist()}}
 with open(os.path.join(ROOT, "tests", "golden", "seed_comparison.json"), "w") as f:
     json.dump(out, f, indent=1)
 print({k: (v["first_exposure_h"], v["first_infectious_h"], v["peak_symptomatic"], v["final_recovered"])
