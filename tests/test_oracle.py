@@ -394,6 +394,65 @@ def test_driver_contract_against_the_reference_epidemic_curves():
     assert not ((hour > 0.0) & (hour <= 6.0)).any()             # nothing happens while everybody sleeps
 
 
+def test_policy_runs_coincide_until_the_policy_as_in_the_reference():
+    """out-flip-lockdown-no-10-20-comparison.xlsx (tests/golden/policy_comparison.json): seed 111 without policy, with the
+    lockdown from day 10 and from day 20.  The three runs are identical sample for sample until the policy and differ
+    from the 06:30 sample of the policy's day on (246.5 h / 486.5 h): a replication is a pure function of its seed, a
+    policy event of midnight acts on that day's activities, and its first consequence is the first morning exposure.
+    The oracle driven by the schedule generator must show the same: equal infection lists before the policy's day,
+    a different list on it, no difference before the morning."""
+    from heros_b200 import scenario
+    with open(os.path.join(GOLDEN, "policy_comparison.json")) as f:
+        gold = json.load(f)
+    first = gold["first_differing_sample_h"]
+    assert first == {"Day 10 vs Nothing": 246.5, "Day 20 vs Nothing": 486.5, "Day 10 vs Day 20": 246.5}
+    assert gold["nothing_equals_seed_111_of_seed_comparison_until_h"] == 486.5    # that workbook's seed 111 locks down on day 20
+    for day, h in ((10, first["Day 10 vs Nothing"]), (20, first["Day 20 vs Nothing"])):
+        assert 24.0 * day + 6.0 <= h <= 24.0 * day + 7.0
+    sus = gold["susceptible_at_day"]
+    assert sus["Day 10"]["10"] == sus["Day 20"]["10"] == sus["Nothing"]["10"] and sus["Day 20"]["20"] == sus["Nothing"]["20"]
+    assert sus["Day 10"]["120"] > sus["Day 20"]["120"] > sus["Nothing"]["120"]   # the earlier the lockdown, the fewer infected
+
+    city = scenario.City(5000, seed=11)
+    props = load_props("distance")
+    props["covidT_dist.alpha"] = "2.0"
+    _, dist, prog = oracle_props(props)
+    policy_day, days = 5, 8
+
+    def run(lockdown):
+        sim = ob.Sim(ob.MODEL_DIST, ob.TRIGGER_EXIT_ONLY, 111)
+        sim.set_dist(dist)
+        sim.set_prog(prog)
+        sim.set_location_types(city.type_infect_sub, city.type_correction)
+        sim.set_locations(city.loc_type, city.loc_nsub, city.loc_area)
+        sim.set_persons(city.age, city.female)
+        seeds = np.arange(0, 5000, 50, dtype=np.int32)
+        sim.expose(seeds, np.zeros(len(seeds)))
+        gen = scenario.ScheduleGenerator(city, 111)
+        for d in range(days):
+            if lockdown and d == policy_day:          # the policy event of midnight comes before the day's movements
+                for name in ("Workplace", "Retail", "BarRestaurant", "PrimarySchool", "SecondarySchool", "Recreation"):
+                    gen.set_closure_policy(scenario.TYPE_ID[name], 0.1, 0.1, scenario.TYPE_ID["Accommodation"])
+            st = gen.generate_day(sim.agent_state()["phase"])
+            sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+            sim.run(24.0 * (d + 1))
+        inf = sim.infections()
+        return np.stack([inf["time"], inf["person"].astype(np.float64), inf["loc"].astype(np.float64)], axis=1)
+
+    free, locked = run(False), run(True)
+    t0 = 24.0 * policy_day
+    before_free, before_locked = free[free[:, 0] < t0], locked[locked[:, 0] < t0]
+    assert len(before_free) > 50
+    np.testing.assert_array_equal(before_free, before_locked)
+    day_free = free[(free[:, 0] >= t0) & (free[:, 0] < t0 + 24.0)]
+    day_locked = locked[(locked[:, 0] >= t0) & (locked[:, 0] < t0 + 24.0)]
+    assert len(day_free) > 0
+    only_one = set(map(tuple, day_free)) ^ set(map(tuple, day_locked))      # events of the day that only one run has
+    first_diff = min(row[0] for row in only_one)
+    assert t0 + 5.0 < first_diff < t0 + 24.0                   # nothing differs while everybody sleeps
+    assert len(locked) < len(free)                             # and the lockdown slows the epidemic down
+
+
 def test_progression_follows_the_reference_transition_table():
     """Covid19Progression.changeDiseasePhase (java :208-346) with the alpha parameters: only the transitions of the
     reference's table occur, every sojourn time lies inside the support of its Triangular distribution (days -> hours),

@@ -40,3 +40,30 @@ with open(os.path.join(ROOT, "tests", "golden", "seed_comparison.json"), "w") as
     json.dump(out, f, indent=1)
 print({k: (v["first_exposure_h"], v["first_infectious_h"], v["peak_symptomatic"], v["final_recovered"])
        for k, v in out["seeds"].items()})
+
+
+# ---- out-flip-lockdown-no-10-20-comparison.xlsx: the same seed (111) without policy and with the lockdown starting on
+#      day 10 / day 20.  What it pins: runs of one seed coincide sample for sample until the policy takes effect, and
+#      the policy of midnight of day d shows from the first morning movements of day d on. ----
+book = read_xlsx("/root/reference/out-flip-lockdown-no-10-20-comparison.xlsx")
+runs = {k: np.array([[float(x) for x in r[:9]] for r in v[1:] if r and r[0] not in (None, "")]) for k, v in book.items()}
+
+
+def first_difference(a, b):
+    n = min(len(a), len(b))
+    rows = np.nonzero((a[:n, 1:] != b[:n, 1:]).any(axis=1))[0]
+    return float(a[rows[0], 0]) if len(rows) else None
+
+
+pol = {"source": "out-flip-lockdown-no-10-20-comparison.xlsx, sheets Nothing / Day 10 / Day 20 (The Hague, seed 111, 0.5 h samples)",
+       "samples": {k: int(len(v)) for k, v in runs.items()},
+       "first_differing_sample_h": {"Day 10 vs Nothing": first_difference(runs["Day 10"], runs["Nothing"]),
+                                    "Day 20 vs Nothing": first_difference(runs["Day 20"], runs["Nothing"]),
+                                    "Day 10 vs Day 20": first_difference(runs["Day 10"], runs["Day 20"])},
+       "nothing_equals_seed_111_of_seed_comparison_until_h": first_difference(
+           runs["Nothing"], np.array([[float(x) for x in r[:9]] for r in read_xlsx("/root/reference/seed comparison.xlsx")["111"][1:]
+                                      if r and r[0] not in (None, "")])),
+       "susceptible_at_day": {k: {str(d): int(v[d * 48, 1]) for d in (10, 20, 30, 60, 120) if d * 48 < len(v)} for k, v in runs.items()}}
+with open(os.path.join(ROOT, "tests", "golden", "policy_comparison.json"), "w") as f:
+    json.dump(pol, f, indent=1)
+print(pol["first_differing_sample_h"], pol["nothing_equals_seed_111_of_seed_comparison_until_h"])
