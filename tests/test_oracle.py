@@ -394,6 +394,34 @@ def test_driver_contract_against_the_reference_epidemic_curves():
     assert not ((hour > 0.0) & (hour <= 6.0)).any()             # nothing happens while everybody sleeps
 
 
+def test_sojourn_supports_against_the_reference_curves():
+    """First appearance of Hospitalized / ICU / Dead / Recovered in the four reference curves against the lower ends of
+    the sojourn-time supports (alpha parameters, days -> hours): nobody can be in hospital before incubation 2.5 d +
+    PeriodSymptomaticToHospitalized 7 d = 228 h, in the ICU before + 1 d, dead before + 2 d more (deaths only through
+    the ICU: FractionHospitalizedToDead = 0), recovered before 2.5 d + 12 d = 348 h -- and with about a hundred initial
+    cases the first ones come within a few days of those bounds, which a wrong unit (hours for days) or a wrong
+    transition table would not survive.  The oracle's own first times obey the same bounds."""
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
+        seeds = json.load(f)["seeds"]
+    lower = {"Hospitalized": 24 * (2.5 + 7), "ICU": 24 * (2.5 + 7 + 1), "Dead": 24 * (2.5 + 7 + 1 + 2), "Recovered": 24 * (2.5 + 12)}
+    for g in seeds.values():
+        first = g["first_time_positive_h"]
+        for name, bound in lower.items():
+            assert first[name] >= bound, (name, first[name])
+        assert first["Hospitalized"] < lower["Hospitalized"] + 72 and first["Recovered"] < lower["Recovered"] + 48
+        assert first["Hospitalized"] < first["ICU"] < first["Dead"]
+    n = 20000
+    sim = small_sim(n=n)
+    sim.set_persons([70] * n, [0] * n)          # an age band with hospital, ICU and death fractions > 0
+    sim.expose(np.arange(n), np.zeros(n))
+    sim.run(24.0 * 40)
+    tr = sim.transitions()
+    for name, phase in (("Hospitalized", H), ("ICU", ICU), ("Dead", D), ("Recovered", R)):
+        times = tr["time"][tr["phase"] == phase]
+        slack = {"Hospitalized": 48, "ICU": 72, "Dead": 120, "Recovered": 48}[name]   # a minimum of sums of 2..4 triangulars
+        assert len(times) > 0 and lower[name] <= times.min() < lower[name] + slack, (name, times.min())
+
+
 def test_policy_runs_coincide_until_the_policy_as_in_the_reference():
     """out-flip-lockdown-no-10-20-comparison.xlsx (tests/golden/policy_comparison.json): seed 111 without policy, with the
     lockdown from day 10 and from day 20.  The three runs are identical sample for sample until the policy and differ

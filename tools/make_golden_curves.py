@@ -33,6 +33,9 @@ for sheet in ("111", "112", "113", "114"):
         "peak_symptomatic": [float(t[np.argmax(a[:, 4])]), int(a[:, 4].max())], "final_recovered": int(a[-1, 8]),
         # the 100 persons exposed at t = 0 turn infectious between 60 h and 91.2 h; nobody exposed later can before
         # 54.5 + 60 h, so I(A) + I(S) over 48..96 h is 100 x the empirical CDF of the incubation period
+        # first sample with somebody in Hospitalized / ICU / Dead / Recovered: lower ends of the sojourn-time supports
+        "first_time_positive_h": {n: float(t[np.argmax(a[:, c] > 0)]) for n, c in
+                                  (("Hospitalized", 5), ("ICU", 6), ("Dead", 7), ("Recovered", 8))},
         "infectious_48_96h": {"t0": 48.0, "dt": 0.5,
                               "asymptomatic": a[(t >= 48) & (t <= 96), 3].astype(int).tolist(),
                               "symptomatic": a[(t >= 48) & (t <= 96), 4].astype(int).tolist()}}
