@@ -481,24 +481,17 @@ def test_policy_runs_coincide_until_the_policy_as_in_the_reference():
     assert len(locked) < len(free)                             # and the lockdown slows the epidemic down
 
 
-def test_morning_exposures_tell_which_model_made_the_reference_curves():
-    """The reference does not record which transmission model produced seed comparison.xlsx.  Its hour-of-day profile of
-    new exposures does: 7.3 % of them fall into the two half-hours after 06:00, when the first people leave home and the
-    household sub-location is evaluated over the whole night.  With the oracle and the schedule generator on a synthetic
-    city the area model puts a comparable or larger share there (households of 100 m2: p = 1 - exp(-p_B t / A) over
-    ten hours), the distance model next to nothing (the distance factor sigma(sqrt(A / N)) of a home is ~1e-6) -- so
-    the published curves are area-model runs, which is the model the seed-envelope comparison of DESIGN.md uses."""
-    from heros_b200 import scenario
-    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
-        seeds = json.load(f)["seeds"]
-    ref = np.sum([np.array(v["new_exposures_by_half_hour_of_day"]) for v in seeds.values()], axis=0)
-    ref_share = ref[13:15].sum() / ref.sum()            # samples 06:30 and 07:00 = exposures of (06:00, 07:00]
-    assert 0.05 < ref_share < 0.10
-    city = scenario.City(8000, seed=11)
-    share = {}
-    for model, key in (("area", "covidT_area.contagiousness"), ("distance", "covidT_dist.alpha")):
+_CITY_RUNS = {}
+
+
+def synthetic_city_exposure_times(model):
+    """Exposure times of 16 days of the oracle driven by the schedule generator on an 8 000-person synthetic city with 100
+    initial cases (contagiousness / alpha = 1); kept for the tests that compare profiles with the reference curves."""
+    if model not in _CITY_RUNS:
+        from heros_b200 import scenario
+        city = scenario.City(8000, seed=11)
         props = load_props(model)
-        props[key] = "1.0"
+        props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "1.0"
         area, dist, prog = oracle_props(props)
         sim = ob.Sim(ob.MODEL_AREA if model == "area" else ob.MODEL_DIST, ob.TRIGGER_EXIT_ONLY, 111)
         sim.set_area(area) if model == "area" else sim.set_dist(dist)
@@ -513,12 +506,53 @@ def test_morning_exposures_tell_which_model_made_the_reference_curves():
             st = gen.generate_day(sim.agent_state()["phase"])
             sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
             sim.run(24.0 * (d + 1))
-        t = sim.infections()["time"]
+        _CITY_RUNS[model] = sim.infections()["time"].copy()
+    return _CITY_RUNS[model]
+
+
+def test_morning_exposures_tell_which_model_made_the_reference_curves():
+    """The reference does not record which transmission model produced seed comparison.xlsx.  Its hour-of-day profile of
+    new exposures does: 7.3 % of them fall into the two half-hours after 06:00, when the first people leave home and the
+    household sub-location is evaluated over the whole night.  With the oracle and the schedule generator on a synthetic
+    city the area model puts a comparable or larger share there (households of 100 m2: p = 1 - exp(-p_B t / A) over
+    ten hours), the distance model next to nothing (the distance factor sigma(sqrt(A / N)) of a home is ~1e-6) -- so
+    the published curves are area-model runs, which is the model the seed-envelope comparison of DESIGN.md uses."""
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
+        seeds = json.load(f)["seeds"]
+    ref = np.sum([np.array(v["new_exposures_by_half_hour_of_day"]) for v in seeds.values()], axis=0)
+    ref_share = ref[13:15].sum() / ref.sum()            # samples 06:30 and 07:00 = exposures of (06:00, 07:00]
+    assert 0.05 < ref_share < 0.10
+    share = {}
+    for model in ("area", "distance"):
+        t = synthetic_city_exposure_times(model)
         assert len(t) > 1000
         hist = np.bincount(np.ceil((t % 24.0) * 2).astype(int) % 48, minlength=48)   # the sample an exposure shows up in
         share[model] = hist[13:15].sum() / hist.sum()
         assert hist[1:13].sum() == 0
     assert share["area"] > ref_share > 10 * share["distance"], share
+
+
+def test_sundays_show_in_the_exposures_as_in_the_reference():
+    """Day 0 of a run is a Monday and days 6, 13, ... take the Sunday week pattern (ConstructHerosModel.java:931-940:
+    Monday..Thursday share the Monday pattern, Friday / Saturday / Sunday have their own).  In all four reference curves
+    the new exposures of days 6 and 13 fall to about a third of the geometric mean of their neighbouring days, while the
+    epidemic grows tenfold a week; the oracle driven by the schedule generator shows the same dips on the same days."""
+    with open(os.path.join(GOLDEN, "seed_comparison.json")) as f:
+        seeds = json.load(f)["seeds"]
+
+    def dip(new, d):
+        return new[d] / math.sqrt(new[d - 1] * new[d + 1])
+
+    for g in seeds.values():
+        new = -np.diff(np.array(g["daily_counts"])[:, 0]).astype(float)     # exposures of day d = S(d) - S(d + 1)
+        assert new[0] == 0 and new[1] == 0                                   # nobody is contagious in the first 48 h
+        assert dip(new, 6) < 0.5 and dip(new, 13) < 0.5
+        assert sorted(range(3, 19), key=lambda d: dip(new, d))[:2] in ([6, 13], [13, 6])   # the two deepest dips of 16 days
+    t = synthetic_city_exposure_times("area")
+    new = np.bincount((t // 24.0).astype(int), minlength=16).astype(float)
+    assert new[0] == 0 and new[1] == 0
+    assert dip(new, 6) < 0.7 and dip(new, 13) < 0.7
+    assert sorted(range(3, 15), key=lambda d: dip(new, d))[:2] in ([6, 13], [13, 6])
 
 
 def test_progression_follows_the_reference_transition_table():
