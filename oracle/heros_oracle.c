@@ -21,8 +21,14 @@
  * (event lists, probabilities) are checked against nothing the reference produced.  What pins it (tests/test_oracle.py):
  * Random123 Philox known answers, libm within 1 ulp, the Javadoc worked example TArea:112-121, hand-derived boundary
  * cases of the formulas, the parameter files of the reference (tests/golden/params_*.json), and the reference-produced
- * epidemic curves of "seed comparison.xlsx" (tests/golden/seed_comparison.json) for three observable consequences of the
- * driver contract: latent period, incubation band, exposures only at movement events.
+ * epidemic curves of "seed comparison.xlsx" and "out-flip-lockdown-no-10-20-comparison.xlsx"
+ * (tests/golden/seed_comparison.json, policy_comparison.json) for the observable consequences of the driver contract
+ * and of the progression: latent period; the empirical CDF of the incubation period of the 100 initial cases
+ * (Kolmogorov-Smirnov against the triangular inverse CDF in hours and against this oracle's draws); the asymptomatic
+ * split; the lower ends of the sojourn supports (first Hospitalized / ICU / Dead / Recovered); exposures only at
+ * movement events, none at night; the share of exposures in the first hour after 06:00 (which tells the area model
+ * made those curves); the Sunday dips of days 6 and 13; runs of one seed coinciding until the morning of a policy's
+ * day.  These are statistical / structural pins, not bit-exact vectors.
  */
 #include "heros_oracle.h"
 
