@@ -179,7 +179,7 @@ def keyed_seeds(city, seed, n):
     return np.sort(order[:n]).astype(np.int32)
 
 
-def _replication_worker(w, args, props, city, total, barrier, times):
+def _replication_worker(w, args, props, city, total, barrier, times, infections):
     """One replication (seed SEED + w) of the oracle in its own process; every day's stays are generated untimed, then
     all replications run their day side by side between two barriers."""
     from heros_b200 import scenario
@@ -196,7 +196,7 @@ def _replication_worker(w, args, props, city, total, barrier, times):
         sim.run(24.0 * (d + 1))
         times[2 * (w * total + d) + 1] = time.perf_counter()
         barrier.wait(timeout=900)                                  # a replication that died breaks the barrier for all
-    times[2 * args.ref_workers_total * total + w] = float(sim.phase_counts()[1:].sum())
+    infections[w] = int(sim.phase_counts()[1:].sum())
 
 
 def host_cores():
@@ -263,11 +263,11 @@ def run_reference(args):
     if args.ref_cores <= 0 and mem is not None:                   # a replication holds ~1 KB per person beside the shared city
         workers = max(1, min(workers, int(0.5 * mem / (2048.0 * args.persons + 2.5e8))))
     total = args.preroll + args.warmup + args.steps
-    args.ref_workers_total = workers
     ctx = mp.get_context("fork")                                  # the city tables are shared copy-on-write
     barrier = ctx.Barrier(workers)
-    times = ctx.Array("d", 2 * workers * total + workers, lock=False)
-    procs = [ctx.Process(target=_replication_worker, args=(w, args, props, city, total, barrier, times), daemon=True)
+    times = ctx.Array("d", 2 * workers * total, lock=False)       # start / end of every (replication, day)
+    infected = ctx.Array("q", workers, lock=False)
+    procs = [ctx.Process(target=_replication_worker, args=(w, args, props, city, total, barrier, times, infected), daemon=True)
              for w in range(workers)]
     for p in procs:
         p.start()
@@ -275,14 +275,14 @@ def run_reference(args):
         p.join()
     if any(p.exitcode != 0 for p in procs):
         raise SystemExit("a replication of the reference arm failed: exit codes " + str([p.exitcode for p in procs]))
-    t = np.asarray(times[:2 * workers * total]).reshape(workers, total, 2)
+    t = np.asarray(times[:]).reshape(workers, total, 2)
     first = args.preroll + args.warmup
     day_wall = t[:, first:, 1].max(axis=0) - t[:, first:, 0].min(axis=0)      # per timed day: first start .. last finish
     seconds = float(day_wall.sum())
     value = workers * city.n_persons * 24.0 * args.steps / seconds
     own = float((t[0, first:, 1] - t[0, first:, 0]).sum())
     one_replication = city.n_persons * 24.0 * args.steps / own
-    infections = [int(x) for x in times[2 * workers * total:]]
+    infections = [int(x) for x in infected[:]]
     # the same workload description as the GPU arm's at this N (the sample that was timed is one tile of it)
     world = max(int(args.gpus), 1)
     n_commuters = 0
