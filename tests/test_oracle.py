@@ -530,6 +530,10 @@ def test_morning_exposures_tell_which_model_made_the_reference_curves():
         share[model] = hist[13:15].sum() / hist.sum()
         assert hist[1:13].sum() == 0
     assert share["area"] > ref_share > 10 * share["distance"], share
+    # and the first secondary exposure of an area-model run shows in the same sample as in all four reference curves:
+    # 54.5 h = the first departures from home (06:00-06:30) of the first morning after the 48 h latent period
+    assert {g["first_exposure_h"] for g in seeds.values()} == {54.5}
+    assert math.ceil(synthetic_city_exposure_times("area").min() * 2) / 2 == 54.5
 
 
 def test_sundays_show_in_the_exposures_as_in_the_reference():
