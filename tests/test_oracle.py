@@ -484,10 +484,11 @@ def test_policy_runs_coincide_until_the_policy_as_in_the_reference():
 _CITY_RUNS = {}
 
 
-def synthetic_city_exposure_times(model):
+def synthetic_city_exposure_times(model, lockdown_day=None):
     """Exposure times of 16 days of the oracle driven by the schedule generator on an 8 000-person synthetic city with 100
-    initial cases (contagiousness / alpha = 1); kept for the tests that compare profiles with the reference curves."""
-    if model not in _CITY_RUNS:
+    initial cases (contagiousness / alpha = 1), optionally with the day-10 rows of the reference's HardLockdown_10-40.csv
+    applied at midnight of ``lockdown_day``; kept for the tests that compare profiles with the reference curves."""
+    if (model, lockdown_day) not in _CITY_RUNS:
         from heros_b200 import scenario
         city = scenario.City(8000, seed=11)
         props = load_props(model)
@@ -502,12 +503,40 @@ def synthetic_city_exposure_times(model):
         first = np.arange(0, 8000, 80, dtype=np.int32)
         sim.expose(first, np.zeros(len(first)))
         gen = scenario.ScheduleGenerator(city, 111)
+        with open(os.path.join(GOLDEN, "location_policies.json")) as f:
+            lockdown = [r for r in json.load(f)["files"]["HardLockdown_10-40"]["rows"] if float(r[0]) == 10.0]
         for d in range(16):
+            if d == lockdown_day:
+                for _, name, fraction_open, fraction_activities, alternative, _ in lockdown:
+                    if name in scenario.TYPE_ID:
+                        gen.set_closure_policy(scenario.TYPE_ID[name], float(fraction_open), float(fraction_activities),
+                                               scenario.TYPE_ID[alternative])
             st = gen.generate_day(sim.agent_state()["phase"])
             sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
             sim.run(24.0 * (d + 1))
-        _CITY_RUNS[model] = sim.infections()["time"].copy()
-    return _CITY_RUNS[model]
+        _CITY_RUNS[(model, lockdown_day)] = sim.infections()["time"].copy()
+    return _CITY_RUNS[(model, lockdown_day)]
+
+
+def test_lockdown_effect_has_the_size_the_reference_shows():
+    """LocationType.setClosurePolicy is inside medlabs; the convention of DESIGN.md 3.4 stands in for it.  Its effect can
+    be compared with the reference's: with HardLockdown_10-40 the reference counts 20 % of the no-policy exposures over
+    days 10..15 (seed 111; 92 and 24 on days 10 and 11 against 566 and 835); the oracle driven by the schedule generator
+    with the same policy rows applied on day 10 counts 32 % on a synthetic city (62 and 23 on days 10 and 11 against
+    197 and 162), where households -- which a lockdown does not close -- weigh more (see the morning share above).
+    Same direction, same order of magnitude; before day 10 the two runs are one."""
+    with open(os.path.join(GOLDEN, "policy_comparison.json")) as f:
+        daily = json.load(f)["susceptible_daily"]
+    ref_free, ref_locked = -np.diff(daily["Nothing"])[:16], -np.diff(daily["Day 10"])[:16]
+    assert (ref_free[:10] == ref_locked[:10]).all()
+    ref_ratio = ref_locked[10:].sum() / ref_free[10:].sum()
+    assert 0.1 < ref_ratio < 0.3
+    free = np.bincount((synthetic_city_exposure_times("area") // 24.0).astype(int), minlength=16)
+    locked = np.bincount((synthetic_city_exposure_times("area", lockdown_day=10) // 24.0).astype(int), minlength=16)
+    assert (free[:10] == locked[:10]).all() and free[10:].sum() > 500
+    ratio = locked[10:].sum() / free[10:].sum()
+    assert 0.1 < ratio < 0.5, ratio
+    assert locked[11] < 0.3 * free[11] and ref_locked[11] < 0.3 * ref_free[11]      # the second day of the lockdown
 
 
 def test_morning_exposures_tell_which_model_made_the_reference_curves():

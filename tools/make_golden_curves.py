@@ -66,7 +66,8 @@ pol = {"source": "out-flip-lockdown-no-10-20-comparison.xlsx, sheets Nothing / D
        "nothing_equals_seed_111_of_seed_comparison_until_h": first_difference(
            runs["Nothing"], np.array([[float(x) for x in r[:9]] for r in read_xlsx("/root/reference/seed comparison.xlsx")["111"][1:]
                                       if r and r[0] not in (None, "")])),
-       "susceptible_at_day": {k: {str(d): int(v[d * 48, 1]) for d in (10, 20, 30, 60, 120) if d * 48 < len(v)} for k, v in runs.items()}}
+       "susceptible_at_day": {k: {str(d): int(v[d * 48, 1]) for d in (10, 20, 30, 60, 120) if d * 48 < len(v)} for k, v in runs.items()},
+       "susceptible_daily": {k: v[::48, 1].astype(int).tolist() for k, v in runs.items()}}
 with open(os.path.join(ROOT, "tests", "golden", "policy_comparison.json"), "w") as f:
     json.dump(pol, f, indent=1)
 print(pol["first_differing_sample_h"], pol["nothing_equals_seed_111_of_seed_comparison_until_h"])
