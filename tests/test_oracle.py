@@ -485,7 +485,20 @@ _CITY_RUNS = {}
 
 
 def synthetic_city_exposure_times(model, lockdown_day=None):
-    """Exposure times of 16 days of the oracle driven by the schedule generator on an 8 000-person synthetic city with 100
+    return synthetic_city_infections(model, lockdown_day)["time"]
+
+
+SYNTHETIC_CITY = dict(n_persons=8000, city_seed=11, seed=111, days=16, first_cases=np.arange(0, 8000, 80, dtype=np.int32))
+
+
+def synthetic_city_lockdown_rows():
+    """The day-10 rows of the reference's HardLockdown_10-40.csv (tests/golden/location_policies.json)."""
+    with open(os.path.join(GOLDEN, "location_policies.json")) as f:
+        return [r for r in json.load(f)["files"]["HardLockdown_10-40"]["rows"] if float(r[0]) == 10.0]
+
+
+def synthetic_city_infections(model, lockdown_day=None):
+    """Infection events of 16 days of the oracle driven by the schedule generator on an 8 000-person synthetic city with 100
     initial cases (contagiousness / alpha = 1), optionally with the day-10 rows of the reference's HardLockdown_10-40.csv
     applied at midnight of ``lockdown_day``; kept for the tests that compare profiles with the reference curves."""
     if (model, lockdown_day) not in _CITY_RUNS:
@@ -503,8 +516,7 @@ def synthetic_city_exposure_times(model, lockdown_day=None):
         first = np.arange(0, 8000, 80, dtype=np.int32)
         sim.expose(first, np.zeros(len(first)))
         gen = scenario.ScheduleGenerator(city, 111)
-        with open(os.path.join(GOLDEN, "location_policies.json")) as f:
-            lockdown = [r for r in json.load(f)["files"]["HardLockdown_10-40"]["rows"] if float(r[0]) == 10.0]
+        lockdown = synthetic_city_lockdown_rows()
         for d in range(16):
             if d == lockdown_day:
                 for _, name, fraction_open, fraction_activities, alternative, _ in lockdown:
@@ -514,7 +526,7 @@ def synthetic_city_exposure_times(model, lockdown_day=None):
             st = gen.generate_day(sim.agent_state()["phase"])
             sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
             sim.run(24.0 * (d + 1))
-        _CITY_RUNS[(model, lockdown_day)] = sim.infections()["time"].copy()
+        _CITY_RUNS[(model, lockdown_day)] = {k: v.copy() for k, v in sim.infections().items()}
     return _CITY_RUNS[(model, lockdown_day)]
 
 
