@@ -331,12 +331,12 @@ def workload_config(args, city, world, n_commuters, exchange="p2p"):
     return cfg
 
 
-def make_engine(args, props, city, device):
+def make_engine(args, props, city, device, flags=0):
     import heros_b200 as hb
     from heros_b200 import properties
     model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
     trig = hb.TRIGGER_EXIT_ONLY if args.trigger == "exit" else hb.TRIGGER_ENTER_AND_EXIT
-    eng = hb.HerosEngine(model, SEED, trigger=trig, device=device)
+    eng = hb.HerosEngine(model, SEED, trigger=trig, device=device, flags=flags)
     city.install(eng)
     if model == hb.MODEL_AREA:
         eng.set_transmission_area(properties.area_params(props))
@@ -392,8 +392,8 @@ def run_ours(args):
     exchange = [args.exchange]
     engines = []  # at N > 1 the engines (and their streams, which NCCL has seen) live until the process group is gone
 
-    def new_engine():
-        eng = make_engine(args, props, city, local)
+    def new_engine(flags=0):
+        eng = make_engine(args, props, city, local, flags)
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
@@ -423,8 +423,11 @@ def run_ours(args):
         if world == 1:
             eng.close()
 
-    def day_step(eng, bx, d, local_cols, remote_cols, offsets, device):
+    def submit_day(eng, d, local_cols, device):
         eng.submit_visits_ptr(local_cols["person"].numel(), *(local_cols[k].data_ptr() for k, _ in COLS), device=device)
+
+    def day_step(eng, bx, d, local_cols, remote_cols, offsets, device):
+        submit_day(eng, d, local_cols, device)
         if bx is None:
             return eng.step(24.0 * (d + 1))
         # block exchange (peer-to-peer stores over NVLink, or two equal-split NCCL all-to-alls): everything of a window is
@@ -487,16 +490,29 @@ def run_ours(args):
         return float(t.item())
 
     def timed_days(eng, bx, stream, cols_of_day, device, after_step=None):
-        """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream."""
+        """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream.  A single engine is
+        driven the way the asynchronous C ABI is meant to be used: the window of day d is enqueued (heros_step_async), the
+        stays of day d + 1 are handed over while it runs (heros_submit_visits copies on its own stream / takes resident
+        device buffers in on the side stream), then the host waits for day d (heros_wait) and reads its results."""
         stats = []
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         start.record(stream)
-        for d in range(first_timed, total):
-            stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))
-            if after_step:
-                after_step()
+        if bx is None:
+            submit_day(eng, first_timed, cols_of_day(first_timed)[0], device)
+            for d in range(first_timed, total):
+                eng.step_async(24.0 * (d + 1))
+                if d + 1 < total:
+                    submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
+                stats.append(eng.wait())
+                if after_step:
+                    after_step()
+        else:
+            for d in range(first_timed, total):
+                stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))
+                if after_step:
+                    after_step()
         end.record(stream)
         end.synchronize()
         barrier()
@@ -504,9 +520,11 @@ def run_ours(args):
         return max_over_ranks(start.elapsed_time(end) * 1e-3), max_over_ranks(wall), stats
 
     # ---- value: stays resident in HBM ----
-    eng, bx, stream = new_engine()
+    import heros_b200 as hb
+    eng, bx, stream = new_engine(hb._lib.FLAG_RESIDENT_INPUTS)  # the device columns below are complete before they are submitted
     dev_days = [({k: days[d][0][k].to(dev) for k, _ in COLS}, {k: days[d][1][k].to(dev) for k, _ in COLS}, days[d][2])
                 for d in range(total)]
+    torch.cuda.synchronize()
     for d in range(first_timed):
         day_step(eng, bx, d, *dev_days[d], device=True)
     with ClockSampler(local) as clocks:
@@ -583,8 +601,8 @@ def run_ours(args):
     keys = ("progress_ms", "bucket_ms", "bucket_scan_ms", "bucket_scatter_ms", "transmit_small_ms",
             "transmit_big_ms", "resolve_ms", "sub32_done_ms", "gpu_ms")
     stage = {k: float(np.sum([s[k] for s in stats])) for k in keys}
-    for c in range(4):
-        stage[f"group{c if c < 3 else '3+4'}_done_ms"] = float(np.sum([s["group_done_ms"][c] for s in stats]))
+    stage["hot_done_ms"] = float(np.sum([s["group_done_ms"][0] for s in stats]))        # fork -> end of k_hot_eval
+    stage["hot_chain_small_done_ms"] = float(np.sum([s["group_done_ms"][1] for s in stats]))
     visits = float(np.sum([s["visits"] for s in stats]))
     big_stays = float(np.sum([s["big_stays"] for s in stats]))
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -600,17 +618,17 @@ def run_ours(args):
     # streams next to k_transmit_thread and the sub-warp kernels, then k_draw), so the stage is timed as a whole.
     agents = float(city.n_persons * args.steps)
     transmit_ms = stage["transmit_small_ms"] + stage["transmit_big_ms"]
-    kernels = {"transmission (k_transmit_thread | k_transmit_group<0..4> | k_transmit_sub<8,32>, k_draw)": (transmit_ms, 32.0 * visits),
+    kernels = {"transmission (k_transmit_stream | k_hot_filter, k_hot_chain<0..2>, k_hot_eval | k_transmit_sub<8,32>)": (transmit_ms, 32.0 * visits),
                "k_bucket_scatter": (stage["bucket_scatter_ms"], 16.0 * visits),
                "k_window_open": (stage["progress_ms"], 16.0 * agents),
-               "k_transmit_thread (group kernels running beside it)": (stage["transmit_small_ms"], 32.0 * (visits - big_stays))}
+               "k_transmit_stream (the hot path running beside it)": (stage["transmit_small_ms"], 32.0 * (visits - big_stays))}
     dominant = max(kernels, key=lambda k: kernels[k][0])
     achieved = kernels[dominant][1] / (kernels[dominant][0] * 1e-3) / 1e9
     traffic, traffic_source = None, None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_full.json")), reverse=True):
         with open(path) as f:
             rows = json.load(f)
-        names = ("k_transmit", "k_draw") if dominant.startswith("transmission") else (dominant.split(" ")[0],)
+        names = ("k_transmit", "k_hot") if dominant.startswith("transmission") else (dominant.split(" ")[0],)
         per_kernel = {}
         for r in rows:
             if any(n in r["kernel"] for n in names):

@@ -68,8 +68,12 @@ typedef struct heros_config {
 /* count every calculated evaluation in heros_step_stats.evaluations, also in sub-locations where nobody can be
  * infected (there the engine otherwise only advances lastCalculation and skips the walk over the evaluations) */
 #define HEROS_FLAG_EXACT_STATS 1u
-/* development aid: record the longest duration (SM cycles) of every phase of the group kernels */
+/* (formerly a development aid of the group kernels; ignored) */
 #define HEROS_FLAG_PHASE_CLOCKS 2u
+/* the device buffers handed to heros_submit_visits_device are complete when the call is made (nothing that is still
+ * enqueued on the engine stream writes them): the engine may then take them in on its side stream, beside the
+ * transmission stage of a window that is still running (heros_step_async) */
+#define HEROS_FLAG_RESIDENT_INPUTS 4u
 
 /* covidT_area.* exactly as in the .properties file (days / seconds); converted as disease/Covid19TransmissionArea.java:63-68 */
 typedef struct heros_area_params {
@@ -112,18 +116,19 @@ typedef struct heros_step_stats {
     /* device time per stage, summed over the windows of the call (CUDA events on the engine stream) */
     double progress_ms;       /* k_window_open: disease-phase state machine + tickets of open / carried-over stays */
     double bucket_ms;         /* k_scan_lookback + k_bucket_scatter (+ retire) */
-    double transmit_small_ms; /* k_transmit_thread: streams every stay of the window once (group kernels run beside it) */
-    double transmit_big_ms;   /* from the end of k_transmit_thread to the end of k_draw: sub-warp kernels, the rest of
-                                 the group kernels, the draws */
+    double transmit_small_ms; /* k_transmit_stream: streams every stay of the window once (the hot path runs beside it) */
+    double transmit_big_ms;   /* from the end of k_transmit_stream to the end of the stage: sub-warp kernels, the rest of
+                                 the hot path */
     double resolve_ms;        /* earliest-draw-wins + expose */
     double retire_ms;         /* 0 (retire is part of k_bucket_scatter) */
-    int64_t big_sublocations; /* sub-locations handled by the group kernels */
+    int64_t big_sublocations; /* sub-locations of > 32 stays (the hot path) */
     int64_t big_stays;        /* ... and their stays */
     double bucket_count_ms;   /* 0 (tickets are taken by k_submit / k_window_open) */
     double bucket_scan_ms, bucket_scatter_ms; /* the two parts of bucket_ms */
-    /* the group kernels run on auxiliary streams, side by side with k_transmit_thread and the sub-warp kernels: time
-     * from the fork (after the scatter) until each of them finished -- classes 0, 1, 2, 3 + 4 -- and until the 32-lane
-     * sub-warp kernel finished (it starts after k_transmit_thread) */
+    /* the hot path (sub-locations of > 32 stays: k_hot_filter, k_hot_chain, k_hot_eval) runs on auxiliary streams, side by
+     * side with k_transmit_stream and the sub-warp kernels: time from the fork (after the scatter) until [0] the hot path
+     * as a whole and [1] the chain kernel of its small class finished ([2], [3]: 0), and until the 32-lane sub-warp kernel
+     * finished (it starts after k_transmit_stream) */
     double group_done_ms[4], sub32_done_ms;
 } heros_step_stats;
 
@@ -249,6 +254,14 @@ int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person,
  *      sub-location, evaluate infectPeople for every movement event of the window, draw, resolve (earliest successful
  *      draw wins), run the disease-phase state machine.  stats may be NULL. ---- */
 int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats);
+/* The same without waiting for the device: the windows up to t_until are enqueued and the call returns.  The host can
+ * then hand over the stays of the NEXT window (heros_submit_visits copies them on its own stream while the windows run)
+ * or advance its own simulator, and collects the result with heros_wait -- which waits for everything enqueued, fills
+ * the statistics of the windows since the previous heros_wait / heros_step and reports their errors.  Every heros_get_*
+ * also waits.  This is how a host whose activity engine produces day d + 1 while day d is processed keeps PCIe and GPU
+ * busy at the same time. */
+int32_t heros_step_async(heros_handle h, double t_until);
+int32_t heros_wait(heros_handle h, heros_step_stats* stats);
 
 /* ---- multi-GPU: one engine per GPU owns a shard of persons and locations.  Every person / location id that
  *      crosses this ABI is GLOBAL: the engine owns persons [person_base, person_base + n) and locations
@@ -276,6 +289,11 @@ int32_t heros_export_guest_candidates(heros_handle h, int64_t capacity, int32_t*
 int32_t heros_import_candidates_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                                        const int16_t* sublocation, const double* time, const double* p);
 int32_t heros_window_finish(heros_handle h, heros_step_stats* stats);
+/* ... without waiting for the device (the result is collected by heros_wait) */
+int32_t heros_window_finish_async(heros_handle h);
+/* A window that cannot be completed (an exchange call failed between its phases) is carried out with what it has
+ * received so far, so that the engine is idle again instead of refusing every further call.  No-op when idle. */
+int32_t heros_window_abort(heros_handle h);
 
 /* The same exchange as FIXED-CAPACITY BLOCKS, one per peer, so that the host can run both all-to-alls of a window as
  * equal-split collectives on the engine's stream with nothing to negotiate and no host synchronisation before

@@ -16,6 +16,7 @@ MODEL_AREA, MODEL_DISTANCE = 0, 1
 TRIGGER_EXIT_ONLY, TRIGGER_ENTER_AND_EXIT = 0, 1
 FLAG_EXACT_STATS = 1
 FLAG_PHASE_CLOCKS = 2
+FLAG_RESIDENT_INPUTS = 4
 DIST_CONSTANT, DIST_UNIFORM, DIST_TRIANGULAR = 0, 1, 2
 PHASE_NAMES = ("Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomatic", "Hospitalized", "ICU",
                "Dead", "Recovered")  # Covid19Progression.java:130-137
@@ -95,6 +96,10 @@ SIGNATURES = {
     "heros_set_closure_policy": (C.c_int32, [_P, C.c_int32, C.c_double, C.c_double, C.c_int32]),
     "heros_debug_get_stays": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_step": (C.c_int32, [_P, C.c_double, C.POINTER(StepStats)]),
+    "heros_step_async": (C.c_int32, [_P, C.c_double]),
+    "heros_wait": (C.c_int32, [_P, C.POINTER(StepStats)]),
+    "heros_window_finish_async": (C.c_int32, [_P]),
+    "heros_window_abort": (C.c_int32, [_P]),
     "heros_set_id_bases": (C.c_int32, [_P, C.c_int32, C.c_int32]),
     "heros_window_begin": (C.c_int32, [_P, C.c_double]),
     "heros_export_agent_words": (C.c_int32, [_P, C.c_int64, _P, _P, _P]),

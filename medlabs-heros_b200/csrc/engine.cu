@@ -127,24 +127,26 @@ __device__ __forceinline__ void progress_agent(const AgentArrays& A, uint32_t a,
 //                     A submitted stay takes it on arrival (k_submit); k_window_open does it for the open stay of every
 //                     agent and for the stays carried over from earlier windows, and runs the disease-phase state machine.
 // 2. k_scan_lookback  seg_start = exclusive prefix sum of the counts (n_keys + 1 entries), single pass
-// 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank]; the stays
-//                     that outlive the window move to the other pool buffer on the way (retire).  A stay that took a
-//                     ticket on arrival but only begins after the window leaves a dead record in its slot.
+// 3. k_bucket_scatter the stay, with the packed agent word of its person, goes to rec[seg_start[key] + rank] (one 256-bit
+//                     store); the stays that outlive the window move to the other carry pool on the way (retire).  A
+//                     stay that took a ticket on arrival but only begins after the window leaves a dead record in its slot.
 // The order inside a bucket is the ticket order; the transmission kernels put a bucket into canonical
 // (person, t_in) order wherever an exposure sum is computed, so no result depends on it.
+// The fill counts of the pools are read from the device counters: the host never waits for a window to learn them.
 // These kernels are bound by the latency of dependent memory operations (load key -> atomic -> store) and by the
 // number of L2 sectors they touch, not by DRAM bandwidth, so every thread handles IPT items whose loads and atomics
-// are in flight together.  Blocks [0, pool_blocks) take the pool stays, the following ones the agents (then the guests).
+// are in flight together.
 __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32_t n_agents, double T1, PoolArrays P,
-                                                     uint32_t n_carried, uint32_t pool_blocks,
-                                                     const uint32_t* __restrict__ open_key,
+                                                     uint32_t pool_blocks, const uint32_t* __restrict__ open_key,
                                                      const double* __restrict__ open_tin, uint32_t* count,
                                                      uint32_t* __restrict__ agent_rank)
 {
     if (blockIdx.x < pool_blocks)
     {
         // stays carried over from earlier windows (the newer ones took their ticket when they were submitted)
+        const uint32_t n_carried = (uint32_t) A.ctr->n_carry;
         const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
+        if (blockIdx.x * (TPB * IPT) >= n_carried) return;
         uint32_t key[IPT], r[IPT];
         double tin[IPT];
 #pragma unroll
@@ -196,98 +198,128 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
 
 constexpr uint64_t DEAD_VIEW = (uint64_t) PH_R << 4;  // neither ill nor susceptible: the record of a slot nobody is in
 
-__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays P, PoolArrays keep, uint32_t n_pool,
-                                                        uint32_t pool_blocks, const uint32_t* __restrict__ open_key,
+// Virtual blocks of TPB * IPT items over four sources: the carry pool, the fresh pool, the open stay of every agent, the
+// guests.  The first two counts come from the device counters; the grid walks the virtual blocks with a stride.
+__global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays PC, PoolArrays PF, PoolArrays keep, uint32_t keep_cap,
+                                                        const uint32_t* __restrict__ open_key,
                                                         const double* __restrict__ open_tin, uint32_t n_agents,
-                                                        uint32_t agent_blocks, const uint32_t* __restrict__ agent_rank,
-                                                        GuestArrays G, uint32_t person_base, double T1,
+                                                        const uint32_t* __restrict__ agent_rank, GuestArrays G,
+                                                        uint32_t person_base, double T1,
                                                         const uint32_t* __restrict__ seg_start,
                                                         const uint64_t* __restrict__ view, StayRec* __restrict__ rec,
                                                         Counters* ctr)
 {
-    uint32_t r[IPT], key[IPT], person[IPT], pad[IPT], dst[IPT];
-    double tin[IPT], tout[IPT];
-    uint64_t vw[IPT];
-    if (blockIdx.x < pool_blocks)
+    constexpr uint32_t CHUNK = TPB * IPT;
+    const uint32_t n_carry = (uint32_t) ctr->n_carry, n_fresh = (uint32_t) ctr->n_fresh;
+    const uint32_t vb_carry = (n_carry + CHUNK - 1) / CHUNK, vb_fresh = (n_fresh + CHUNK - 1) / CHUNK,
+                   vb_agents = (n_agents + CHUNK - 1) / CHUNK, vb_guests = (G.n + CHUNK - 1) / CHUNK;
+    const uint32_t vb_total = vb_carry + vb_fresh + vb_agents + vb_guests;
+    const double inf = bits_f64(0x7ff0000000000000ull);
+    for (uint32_t vb = blockIdx.x; vb < vb_total; vb += gridDim.x)
     {
-        const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k)
+        uint32_t r[IPT], key[IPT], person[IPT], pad[IPT], dst[IPT];
+        double tin[IPT], tout[IPT];
+        uint64_t vw[IPT];
+        if (vb < vb_carry + vb_fresh)
         {
-            const uint32_t i = base + k * TPB;
-            r[k] = KEY_NONE; key[k] = KEY_NONE; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = 0;
-            if (i < n_pool) { r[k] = P.rank[i]; key[k] = P.key[i]; person[k] = P.person[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; }
-        }
-        // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
+            const bool fresh = vb >= vb_carry;
+            const PoolArrays& P = fresh ? PF : PC;
+            const uint32_t n_pool = fresh ? n_fresh : n_carry;
+            const uint32_t base = (fresh ? vb - vb_carry : vb) * CHUNK + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < IPT; ++k)
-        {
-            const bool kept = key[k] != KEY_NONE && !(tout[k] < T1);
-            const unsigned m = __ballot_sync(0xffffffffu, kept);
-            if (m)
+            for (int k = 0; k < IPT; ++k)
             {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                unsigned long long at = 0;
-                if (lane == leader) at = atomicAdd(&ctr->n_keep, (unsigned long long) __popc(m));
-                at = __shfl_sync(0xffffffffu, at, leader);
-                if (kept)
+                const uint32_t i = base + k * TPB;
+                r[k] = KEY_NONE; key[k] = KEY_NONE; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = 0;
+                if (i < n_pool) { r[k] = P.rank[i]; key[k] = P.key[i]; person[k] = P.person[i]; tin[k] = P.tin[i]; tout[k] = P.tout[i]; }
+            }
+            // retire: the stays that ended before T1 leave the pool; the others move on (one atomic per warp)
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+            {
+                const bool kept = key[k] != KEY_NONE && !(tout[k] < T1);
+                const unsigned m = __ballot_sync(0xffffffffu, kept);
+                if (m)
                 {
-                    const uint32_t j = (uint32_t) at + __popc(m & ((1u << lane) - 1u));
-                    keep.person[j] = person[k]; keep.key[j] = key[k]; keep.tin[j] = tin[k]; keep.tout[j] = tout[k];
+                    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                    unsigned long long at = 0;
+                    if (lane == leader) at = atomicAdd(&ctr->n_keep, (unsigned long long) __popc(m));
+                    at = __shfl_sync(0xffffffffu, at, leader);
+                    if (kept)
+                    {
+                        const unsigned long long j = at + __popc(m & ((1u << lane) - 1u));
+                        if (j < keep_cap)
+                        {
+                            keep.person[j] = person[k]; keep.key[j] = key[k]; keep.tin[j] = tin[k]; keep.tout[j] = tout[k];
+                        }
+                        else
+                            atomicOr(&ctr->overflow, 32u);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+            {
+                vw[k] = 0; dst[k] = 0;
+                if (r[k] != KEY_NONE)
+                {
+                    dst[k] = seg_start[key[k]] + r[k];
+                    if (tin[k] < T1) { vw[k] = view[person[k]]; person[k] += person_base; }
+                    else  // took its ticket on arrival but begins after this window: nobody is in the slot
+                    {
+                        vw[k] = DEAD_VIEW; person[k] = 0xFFFFFFFFu;
+                        tin[k] = inf; tout[k] = bits_f64(0xfff0000000000000ull);
+                    }
                 }
             }
         }
+        else if (vb < vb_carry + vb_fresh + vb_agents)
+        {
+            const uint32_t base = (vb - vb_carry - vb_fresh) * CHUNK + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+            {
+                const uint32_t a = base + k * TPB;
+                r[k] = KEY_NONE; key[k] = 0; person[k] = person_base + a; tin[k] = 0.0; pad[k] = 0; vw[k] = 0;
+                tout[k] = inf;
+                if (a < n_agents) { r[k] = agent_rank[a]; key[k] = open_key[a]; tin[k] = open_tin[a]; vw[k] = view[a]; }
+            }
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
+        }
+        else
+        {
+            const uint32_t base = (vb - vb_carry - vb_fresh - vb_agents) * CHUNK + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+            {
+                const uint32_t j = base + k * TPB;
+                r[k] = KEY_NONE; key[k] = 0; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = REC_GUEST | j; vw[k] = 0;
+                if (j < G.n) { r[k] = G.rank[j]; key[k] = G.key[j]; person[k] = G.gid[j]; tin[k] = G.tin[j]; tout[k] = G.tout[j]; vw[k] = G.view[j]; }
+            }
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
-        {
-            vw[k] = 0; dst[k] = 0;
             if (r[k] != KEY_NONE)
             {
-                dst[k] = seg_start[key[k]] + r[k];
-                if (tin[k] < T1) { vw[k] = view[person[k]]; person[k] += person_base; }
-                else  // took its ticket on arrival but begins after this window: nobody is in the slot
-                {
-                    vw[k] = DEAD_VIEW; person[k] = 0xFFFFFFFFu;
-                    tin[k] = bits_f64(0x7ff0000000000000ull); tout[k] = bits_f64(0xfff0000000000000ull);
-                }
+                StayRec o;
+                o.tin = tin[k]; o.tout = tout[k]; o.view = vw[k]; o.person = person[k]; o.pad = pad[k];
+                st_rec(rec + dst[k], o);
             }
-        }
     }
-    else if (blockIdx.x < pool_blocks + agent_blocks)
+}
+
+// after the scatter the pools have been consumed: what outlived the window is the carry pool of the next one, the fresh
+// pool is empty again (k_submit of the next window may already be waiting for this)
+__global__ void k_window_roll(Counters* ctr)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        const uint32_t base = (blockIdx.x - pool_blocks) * (TPB * IPT) + threadIdx.x;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k)
-        {
-            const uint32_t a = base + k * TPB;
-            r[k] = KEY_NONE; key[k] = 0; person[k] = person_base + a; tin[k] = 0.0; pad[k] = 0; vw[k] = 0;
-            tout[k] = bits_f64(0x7ff0000000000000ull);
-            if (a < n_agents) { r[k] = agent_rank[a]; key[k] = open_key[a]; tin[k] = open_tin[a]; vw[k] = view[a]; }
-        }
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
+        ctr->n_carry = ctr->n_keep;
+        ctr->n_fresh = 0ull;
     }
-    else
-    {
-        const uint32_t base = (blockIdx.x - pool_blocks - agent_blocks) * (TPB * IPT) + threadIdx.x;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k)
-        {
-            const uint32_t j = base + k * TPB;
-            r[k] = KEY_NONE; key[k] = 0; person[k] = 0; tin[k] = 0.0; tout[k] = 0.0; pad[k] = REC_GUEST | j; vw[k] = 0;
-            if (j < G.n) { r[k] = G.rank[j]; key[k] = G.key[j]; person[k] = G.gid[j]; tin[k] = G.tin[j]; tout[k] = G.tout[j]; vw[k] = G.view[j]; }
-        }
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) dst[k] = r[k] != KEY_NONE ? seg_start[key[k]] + r[k] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < IPT; ++k)
-        if (r[k] != KEY_NONE)
-        {
-            StayRec o;
-            o.tin = tin[k]; o.tout = tout[k]; o.view = vw[k]; o.person = person[k]; o.pad = pad[k];
-            rec[dst[k]] = o;
-        }
 }
 
 // Exclusive prefix sum of count[0..n) into out[0..n], out[n] = total, in ONE pass: tiles are handed out in order, every
@@ -389,6 +421,7 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
     {
         out[n] = run;  // the last thread of the last tile has seen everything
         ctr->n_active = run;
+        ctr->visits_total += run;
     }
     // the last block to finish resets the scan state for the next window
     __syncthreads();
@@ -404,16 +437,36 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
 // ---- resolve: earliest successful draw wins (ties: lowest sub-location key) -------------------------------------------
 constexpr uint32_t RESOLVE_SOLO = 8192;  // up to this many candidates one block resolves everything without grid barriers
 
+// the window is complete: its compartment counts go into the series ring, the window counter moves on
+__device__ __forceinline__ void close_window(Counters* ctr, long long* series, unsigned long long n_cand)
+{
+    const unsigned long long w = ctr->windows;
+    long long* row = series + (size_t) (w % SERIES_RING) * 8;
+    for (int k = 0; k < 8; ++k) row[k] = *((volatile long long*) &ctr->phase_counts[k]);
+    ctr->cand_total += n_cand;
+    ctr->windows = w + 1;
+}
+
 // Candidates carry global person ids; the ones of other shards' persons (guests) are skipped here and sent home.
 // Four phases separated by barriers: earliest time per person, lowest sub-location among those, expose() the winner
 // (exposure time := (float) now, contract C4) and run its state machine to the end of the window, reset the scratch.
+// A candidate list that did not fit its buffer is never resolved (the overflow bit is set: the host fails the window).
 // Launched cooperatively (the grid barrier needs every block resident).
 __global__ void __launch_bounds__(1024) k_resolve(CandArrays C, const AgentArrays A, unsigned long long* best_t,
                                                   unsigned long long* best_gkey, uint32_t* claim, InfLog log, double T1,
-                                                  uint32_t n_agents)
+                                                  uint32_t n_agents, long long* series)
 {
-    const uint32_t n = (uint32_t) min((unsigned long long) C.cap, A.ctr->n_cand);
-    if (n == 0) return;
+    const unsigned long long n_all = A.ctr->n_cand;
+    if (n_all == 0 || n_all > (unsigned long long) C.cap)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            if (n_all) atomicOr(&A.ctr->overflow, 1u);
+            close_window(A.ctr, series, 0ull);
+        }
+        return;
+    }
+    const uint32_t n = (uint32_t) n_all;
     const bool solo = n <= RESOLVE_SOLO;
     if (solo && blockIdx.x != 0) return;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
@@ -470,7 +523,17 @@ __global__ void __launch_bounds__(1024) k_resolve(CandArrays C, const AgentArray
         best_gkey[person] = BEST_NONE;
         claim[person] = 0u;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) close_window(A.ctr, series, n_all);
 #undef RESOLVE_BARRIER
+}
+
+// after a candidate buffer overflow the per-agent scratch of k_resolve may hold stale entries
+__global__ void __launch_bounds__(TPB) k_reset_best(unsigned long long* best_t, unsigned long long* best_key, uint32_t* claim,
+                                                    uint32_t n)
+{
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    best_t[a] = BEST_NONE; best_key[a] = BEST_NONE; claim[a] = 0u;
 }
 
 // ---- inputs ------------------------------------------------------------------------------------------------------------
@@ -480,7 +543,7 @@ struct SubmitIn { const int32_t* person; const int32_t* loc; const int16_t* sub;
 // stay (t_out = +inf) becomes the open stay of its person.  One pass: closing is a compare-and-swap of the slot's t_in
 // to NaN ("nobody there"), opening overwrites key and t_in, so any interleaving of the close of the old stay and the
 // opening of the next one (t_in differs) ends with the new stay in the slot.
-__global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArrays P, uint32_t pool_base,
+__global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArrays P, uint32_t pool_cap,
                                                 uint32_t* open_key, double* open_tin,
                                                 const uint2* __restrict__ loc_key, uint32_t n_loc, uint32_t n_agents,
                                                 uint32_t person_base, int32_t loc_origin, double t_now, uint32_t* count,
@@ -488,6 +551,12 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
 {
     const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
     const double inf = bits_f64(0x7ff0000000000000ull);
+    // the block's slots in the fresh pool: its cursor lives on the device (one atomic per block)
+    __shared__ unsigned long long s_slot;
+    if (threadIdx.x == 0)
+        s_slot = atomicAdd(&ctr->n_fresh, (unsigned long long) min((uint32_t) (TPB * IPT), n - blockIdx.x * (TPB * IPT)));
+    __syncthreads();
+    const unsigned long long slot0 = s_slot;
     int32_t person[IPT], loc[IPT], sub[IPT];
     double tin[IPT], tout[IPT];
 #pragma unroll
@@ -552,11 +621,13 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
     {
         const uint32_t i = base + k * TPB;
         if (i >= n) continue;
-        P.person[pool_base + i] = good[k] ? (uint32_t) person[k] : 0u;
-        P.key[pool_base + i] = pk[k];
-        P.tin[pool_base + i] = tin[k];
-        P.tout[pool_base + i] = tout[k];
-        P.rank[pool_base + i] = ticket[k];  // its ticket for the next window
+        const unsigned long long at = slot0 + (unsigned long long) (k * TPB + threadIdx.x);
+        if (at >= pool_cap) { atomicOr(&ctr->overflow, 32u); continue; }
+        P.person[at] = good[k] ? (uint32_t) person[k] : 0u;
+        P.key[at] = pk[k];
+        P.tin[at] = tin[k];
+        P.tout[at] = tout[k];
+        P.rank[at] = ticket[k];  // its ticket for the next window
     }
     late = __reduce_add_sync(0xffffffffu, late);
     invalid = __reduce_add_sync(0xffffffffu, invalid);
@@ -731,27 +802,118 @@ AgentArrays agent_arrays(heros_handle h)
     return A;
 }
 
-PoolArrays pool_arrays(heros_handle h, int which)
+PoolArrays fresh_arrays(heros_handle h)
 {
-    return PoolArrays{h->pool_person[which].p, h->pool_key[which].p, h->pool_tin[which].p, h->pool_tout[which].p,
-                      h->pool_rank[which].p};
+    return PoolArrays{h->fresh_person.p, h->fresh_key.p, h->fresh_tin.p, h->fresh_tout.p, h->fresh_rank.p};
 }
 
-int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep)
+PoolArrays carry_arrays(heros_handle h, int which)
 {
-    CU(h, h->pool_person[which].ensure(n, keep, h->stream));
-    CU(h, h->pool_key[which].ensure(n, keep, h->stream));
-    CU(h, h->pool_tin[which].ensure(n, keep, h->stream));
-    CU(h, h->pool_tout[which].ensure(n, keep, h->stream));
-    CU(h, h->pool_rank[which].ensure(n, keep, h->stream));
+    return PoolArrays{h->carry_person[which].p, h->carry_key[which].p, h->carry_tin[which].p, h->carry_tout[which].p,
+                      h->carry_rank[which].p};
+}
+
+// Growing a pool that is in use: everything enqueued so far (it may read or write the old buffers) is waited for first.
+static int32_t quiesce(heros_handle h)
+{
+    CU(h, cudaStreamSynchronize(h->sub_stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return HEROS_OK;
 }
 
+int32_t ensure_fresh(heros_handle h, size_t n)
+{
+    if (n <= h->fresh_person.n) return HEROS_OK;
+    { const int32_t rc = quiesce(h); if (rc != HEROS_OK) return rc; }
+    CU(h, h->fresh_person.ensure(n, true, h->stream)); CU(h, h->fresh_key.ensure(n, true, h->stream));
+    CU(h, h->fresh_tin.ensure(n, true, h->stream)); CU(h, h->fresh_tout.ensure(n, true, h->stream));
+    CU(h, h->fresh_rank.ensure(n, true, h->stream));
+    return HEROS_OK;
+}
+
+static int32_t ensure_carry(heros_handle h, int which, size_t n)
+{
+    if (n <= h->carry_person[which].n) return HEROS_OK;
+    // the target pool of a window holds nothing that is still needed
+    CU(h, h->carry_person[which].ensure(n)); CU(h, h->carry_key[which].ensure(n)); CU(h, h->carry_tin[which].ensure(n));
+    CU(h, h->carry_tout[which].ensure(n)); CU(h, h->carry_rank[which].ensure(n));
+    return HEROS_OK;
+}
+
+// the engine stream waits for what was submitted on the side stream
+int32_t join_submissions(heros_handle h)
+{
+    if (h->sub_used) CU(h, cudaStreamWaitEvent(h->stream, h->ev_submitted, 0));
+    return HEROS_OK;
+}
+
+int32_t check_idle(heros_handle h, const char* what)
+{
+    if (h->win_state != 0)
+        return fail(h, HEROS_ERR_INVALID, std::string(what) + ": a window opened by heros_window_begin is still in progress");
+    return HEROS_OK;
+}
+
+// stage times of the windows whose events have all been reached
+static int32_t harvest(heros_handle h, WindowEvents& we)
+{
+    if (!we.pending) return HEROS_OK;
+    CU(h, cudaEventSynchronize(we.resolved));
+    cudaEvent_t marks[6] = {we.begin, we.opened, we.scattered, we.mid, we.transmitted, we.resolved};
+    for (int k = 0; k < 5; ++k)
+    {
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
+        h->stage_ms[k] += ms;
+    }
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, we.opened, we.scanned));
+    h->bucket_part_ms[1] += ms;
+    CU(h, cudaEventElapsedTime(&ms, we.scanned, we.scattered));
+    h->bucket_part_ms[2] += ms;
+    for (int k = 0; k < N_AUX; ++k)
+    {
+        CU(h, cudaEventElapsedTime(&ms, we.fork, we.join[k]));
+        h->aux_done_ms[k] += ms;
+    }
+    h->windows_timed++;
+    we.pending = false;
+    return HEROS_OK;
+}
+
+// Everything enqueued has finished; the host copy of the counters is current.  The bounds of the pools become exact,
+// the compartment counts of the finished windows are fetched, the stage times are added up.
 int32_t sync_counters(heros_handle h)
 {
+    { const int32_t rc_ = join_submissions(h); if (rc_ != HEROS_OK) return rc_; }
     CU(h, cudaMemcpyAsync(h->h_ctr, h->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->ctr_current = true;
+    for (auto& we : h->ring) { const int32_t rc = harvest(h, we); if (rc != HEROS_OK) return rc; }
+    if (h->win_state == 0)
+    {
+        h->carry_ub = (size_t) h->h_ctr->n_carry;
+        h->fresh_ub = (size_t) h->h_ctr->n_fresh;
+    }
+    // compartment counts at the end of every window finished since the last fetch (the ring holds SERIES_RING of them)
+    const size_t done = (size_t) h->h_ctr->windows;
+    if (done > h->series_fetched && h->d_series.p)
+    {
+        size_t first = h->series_fetched;
+        if (done - first > (size_t) SERIES_RING) first = done - SERIES_RING;  // older rows were overwritten (never: see window_begin)
+        h->series_counts.resize(done * 8, 0);
+        std::vector<long long> rows((size_t) SERIES_RING * 8);
+        CU(h, cudaMemcpy(rows.data(), h->d_series.p, rows.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t w = first; w < done; ++w)
+            for (int k = 0; k < 8; ++k) h->series_counts[w * 8 + k] = (int64_t) rows[(w % SERIES_RING) * 8 + k];
+        h->series_fetched = done;
+    }
+    if (h->h_ctr->overflow & 1u)
+    {
+        // a truncated candidate list was not resolved: the earliest-draw scratch may hold entries nobody will reset
+        k_reset_best<<<blocks_for(h->n_agents), TPB, 0, h->stream>>>(h->d_best_t.p, h->d_best_key.p, h->d_claim.p, h->n_agents);
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
     return HEROS_OK;
 }
 
@@ -759,6 +921,38 @@ int32_t sync_counters(heros_handle h)
 // round trip when something was enqueued since
 int32_t current_counters(heros_handle h) { return h->ctr_current ? HEROS_OK : sync_counters(h); }
 
+// what a finished window may have to report: a device buffer that overflowed (the results of the call are not to be
+// trusted: HEROS_ERR_CAPACITY) or rejected stays (the windows ran without them: HEROS_ERR_INVALID, once)
+static int32_t report_window_errors(heros_handle h)
+{
+    if (h->h_ctr->overflow)
+    {
+        char buf[200];
+        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch / work lists, 4 transition log, 8 infection log, 16 exchange block, 32 pool, 64 a peer did not answer)",
+                 h->h_ctr->overflow);
+        // the candidate buffer grows for the next attempt; the other buffers are sized from exact bounds
+        if (h->h_ctr->overflow & 1u)
+        {
+            const size_t want = 2 * (size_t) h->cand_person.n;
+            h->cand_person.ensure(want); h->cand_gkey.ensure(want); h->cand_t.ensure(want); h->cand_p.ensure(want);
+        }
+        unsigned int zero = 0;
+        cudaMemcpyAsync(&h->d_ctr.p->overflow, &zero, sizeof zero, cudaMemcpyHostToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+        h->h_ctr->overflow = 0;
+        return fail(h, HEROS_ERR_CAPACITY, buf);
+    }
+    if (h->h_ctr->invalid_visits != h->invalid_reported)
+    {
+        // not silently: stays with ids outside the tables or NaN / negative times were left out of their window
+        char buf[200];
+        snprintf(buf, sizeof buf, "%u submitted stays were rejected (person, location or sub-location id out of range, or a NaN / negative time); the window ran without them",
+                 h->h_ctr->invalid_visits - h->invalid_reported);
+        h->invalid_reported = h->h_ctr->invalid_visits;
+        return fail(h, HEROS_ERR_INVALID, buf);
+    }
+    return HEROS_OK;
+}
 
 int32_t check_ready(heros_handle h)
 {
@@ -776,31 +970,40 @@ int32_t check_ready(heros_handle h)
 // A window [T0, T1) runs in three phases so that a multi-GPU host can exchange stays and candidate infections between
 // them: begin (disease-phase state machine + tickets of the open and carried-over stays; agent words final for the
 // window) -> [guests in] -> transmit (prefix sum, scatter + retire, every evaluation; candidates out / in) -> finish
-// (resolve).
-// heros_step runs the three back to back: 14 launches per window.
+// (resolve).  Nothing in them waits for the device: the fill counts of the pools, the work lists and the candidates
+// stay in HBM, the host only keeps upper bounds (exact again after every synchronising call).
 int32_t window_begin(heros_handle h, double T1)
 {
     cudaStream_t s = h->stream;
-    const uint32_t N = h->n_agents, n_pool = h->n_pool, n_keys = h->n_keys;
-    const int cur = h->pool_cur, oth = cur ^ 1;
+    const uint32_t N = h->n_agents;
     h->win_T0 = h->t_now;
     h->win_T1 = T1;
     h->ctr_current = false;
     h->win_launches = 0;
     h->n_guest = 0;
-    h->win_n_pool = n_pool;
-    (void) n_keys;
+    { const int32_t rc_ = join_submissions(h); if (rc_ != HEROS_OK) return rc_; }
+    // bounds that were never made exact keep growing: refresh them before they get silly (a cheap, rare round trip)
+    if (h->carry_ub > 4 * std::max<size_t>(h->fresh_seen, 1u << 20) || h->series_t.size() - h->series_fetched >= (size_t) SERIES_RING - 1)
+    {
+        const int32_t rc_ = sync_counters(h);
+        if (rc_ != HEROS_OK) return rc_;
+        h->ctr_current = false;
+    }
     CU(h, h->bk_rank.ensure(N));
-    { const int32_t rc_ = ensure_pool(h, oth, std::max<size_t>(n_pool, 1), false); if (rc_ != HEROS_OK) return rc_; }
-    CU(h, cudaEventRecord(h->ev[2], s));
+    { const int32_t rc_ = ensure_carry(h, h->carry_cur ^ 1, std::max<size_t>(h->carry_ub + h->fresh_ub, 1)); if (rc_ != HEROS_OK) return rc_; }
+    h->win_ring = h->ring_next;
+    h->ring_next = (h->ring_next + 1) % WIN_RING;
+    WindowEvents& we = h->ring[h->win_ring];
+    { const int32_t rc_ = harvest(h, we); if (rc_ != HEROS_OK) return rc_; }  // the host is a whole ring ahead: wait for that window
+    CU(h, cudaEventRecord(we.begin, s));
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_cand, 0, sizeof(Counters) - offsetof(Counters, n_cand), s));
     // 1. disease-phase state machine, tickets of open / carried-over stays
-    const int pool_blocks = item_blocks(h->n_carried);
-    k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, pool_arrays(h, cur), h->n_carried,
+    const int pool_blocks = h->carry_ub ? item_blocks(h->carry_ub) : 0;
+    k_window_open<<<pool_blocks + item_blocks(N), TPB, 0, s>>>(agent_arrays(h), N, T1, carry_arrays(h, h->carry_cur),
                                                                (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p,
                                                                h->bk_count.p, h->bk_rank.p);
     h->win_launches += 1;
-    CU(h, cudaEventRecord(h->ev[3], s));
+    CU(h, cudaEventRecord(we.opened, s));
     CU(h, cudaGetLastError());
     h->win_state = 1;
     return HEROS_OK;
@@ -811,8 +1014,10 @@ int32_t window_transmit(heros_handle h)
     cudaStream_t s = h->stream;
     const double T0 = h->win_T0, T1 = h->win_T1;
     const uint32_t N = h->n_agents;
-    const uint32_t n_pool = h->win_n_pool;
-    const uint32_t n_total = n_pool + N + h->n_guest;
+    WindowEvents& we = h->ring[h->win_ring];
+    const size_t pool_ub = h->carry_ub + h->fresh_ub;
+    if (pool_ub + N + h->n_guest >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
+    const uint32_t n_total = (uint32_t) (pool_ub + N + h->n_guest);
     int& launches = h->win_launches;
 
     // 2-3. bucket offsets and the scatter into bucket order
@@ -825,44 +1030,50 @@ int32_t window_transmit(heros_handle h)
         CU(h, cudaMemsetAsync(h->scan_status.p, 0, h->scan_status.n * 8, s));
     }
     CU(h, h->rec.ensure(n_total));
-    const PoolArrays P = pool_arrays(h, h->pool_cur);
     const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->g_rank.p, h->n_guest};
     const size_t list_cap = (size_t) n_total / 32 + 16;
     const size_t occupied_cap = std::min<size_t>(n_keys, n_total) + 16;
     CU(h, h->sub_seg[0].ensure(occupied_cap));
     CU(h, h->sub_seg[1].ensure((size_t) n_total / 9 + 16));  // sub-locations of 9..32 stays
-    for (auto& b : h->blk_seg) CU(h, b.ensure(list_cap));
-    for (auto& b : h->run_seg) CU(h, b.ensure(list_cap));
+    for (auto& b : h->hot_seg) CU(h, b.ensure(list_cap));
+    for (auto& b : h->hot_run) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
-    // exact bounds: a stay leaves at most one draw item, a sub-location at most one table entry per movement event
-    CU(h, h->item_person.ensure((size_t) n_total + 1)); CU(h, h->item_key.ensure((size_t) n_total + 1));
-    CU(h, h->item_tab.ensure((size_t) n_total + 1)); CU(h, h->item_pair.ensure((size_t) n_total + 1));
-    CU(h, h->tab_t.ensure(2 * (size_t) n_total + 1)); CU(h, h->tab_p.ensure(2 * (size_t) n_total + 1));
-    // global scratch of the sub-locations too large for shared memory: <= 144 B per stay + 172 KB per sub-location of
-    // > 4096 stays (<= 42 B per stay), and 4 B per stay of a total-branch location
-    CU(h, h->scratch.ensure(std::min<size_t>(192 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
+    // exact bounds: a sub-location has at most one evaluation per movement event (two per stay), and one work item per
+    // 32 evaluations (rounded up per hot sub-location)
+    const size_t tab_cap = 2 * (size_t) n_total + 64, item_cap = (size_t) n_total / 8 + 1024;
+    CU(h, h->tab_now.ensure(tab_cap)); CU(h, h->tab_dur.ensure(tab_cap)); CU(h, h->tab_head.ensure(tab_cap));
+    CU(h, h->item_key.ensure(item_cap)); CU(h, h->item_tab.ensure(item_cap)); CU(h, h->item_cnt.ensure(item_cap));
+    // global scratch of the sub-locations too large for shared memory (> 8192 movement events): 42 B per stay + 82 KB
+    // per such sub-location (each holds > 4096 stays), and 4 B per stay of a total-branch location
+    CU(h, h->scratch.ensure(std::min<size_t>(72 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
 
     BigLists big{};
-    for (int k = 0; k < N_CLS; ++k) big.blk_seg[k] = h->blk_seg[k].p;
-    big.blk_cap = (uint32_t) h->blk_seg[0].n;
-    for (int k = 1; k < N_CLS; ++k) big.blk_cap = (uint32_t) std::min<size_t>(big.blk_cap, h->blk_seg[k].n);
+    for (int k = 0; k < N_HOT; ++k) big.hot_seg[k] = h->hot_seg[k].p;
+    big.hot_cap = (uint32_t) h->hot_seg[0].n;
+    for (int k = 1; k < N_HOT; ++k) big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, h->hot_seg[k].n);
+    for (int k = 0; k < N_HOT; ++k) big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, h->hot_run[k].n);
+    big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, 0x7fffffffu);
     big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
     big.key_total = h->n_total_loc ? h->d_key_total.p : nullptr;
-    big.both = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
-    big.need_enters = big.both || h->cfg.model == HEROS_MODEL_DISTANCE;
-    {
-        const double thr = h->cfg.model == HEROS_MODEL_AREA ? h->area.threshold : h->dist.threshold;
-        big.r_window = thr > 0 ? (T1 - T0) / thr + 2.0 : std::numeric_limits<double>::infinity();
-    }
-    CU(h, cudaEventRecord(h->ev_bk[0], s));
+    big.need_enters = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT || h->cfg.model == HEROS_MODEL_DISTANCE;
     k_scan_lookback<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->seg_start.p, h->scan_status.p, n_tiles, h->d_ctr.p,
                                             big);
-    CU(h, cudaEventRecord(h->ev_bk[1], s));
-    const int pool_blocks = item_blocks(n_pool), agent_blocks = item_blocks(N);
-    k_bucket_scatter<<<pool_blocks + agent_blocks + item_blocks(h->n_guest), TPB, 0, s>>>(
-        P, pool_arrays(h, h->pool_cur ^ 1), n_pool, (uint32_t) pool_blocks, h->d_open_key.p, h->d_open_tin.p, N,
-        (uint32_t) agent_blocks, h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p);
-    launches += 2;
+    CU(h, cudaEventRecord(we.scanned, s));
+    const size_t vb_ub = (size_t) item_blocks(h->carry_ub) + item_blocks(h->fresh_ub) + item_blocks(N) + item_blocks(h->n_guest);
+    const int scatter_grid = (int) std::max<size_t>(1, std::min<size_t>(vb_ub, (size_t) h->n_sm * 32));
+    k_bucket_scatter<<<scatter_grid, TPB, 0, s>>>(
+        carry_arrays(h, h->carry_cur), fresh_arrays(h), carry_arrays(h, h->carry_cur ^ 1),
+        (uint32_t) std::min<size_t>(h->carry_person[h->carry_cur ^ 1].n, 0xFFFFFFFFu), h->d_open_key.p, h->d_open_tin.p, N,
+        h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p);
+    k_window_roll<<<1, 32, 0, s>>>(h->d_ctr.p);
+    CU(h, cudaEventRecord(h->ev_rolled, s));  // k_submit of the next window may run from here on, beside the transmission
+    CU(h, cudaEventRecord(we.scattered, s));
+    launches += 3;
+    // the pools as the host sees them from now on: everything that may have outlived the window is in the other carry pool
+    h->fresh_seen = std::max(h->fresh_seen, h->fresh_ub);
+    h->carry_ub = pool_ub;
+    h->fresh_ub = 0;
+    h->carry_cur ^= 1;
 
     // 4. transmission
     WindowCtx c{};
@@ -875,39 +1086,46 @@ int32_t window_transmit(heros_handle h)
     c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
     c.rec = h->rec.p; c.seg_start = h->seg_start.p;
     c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
-    c.cand_cap = (uint32_t) h->cand_person.n;
+    c.cand_cap = (uint32_t) std::min<size_t>(std::min(std::min(h->cand_person.n, h->cand_gkey.n), std::min(h->cand_t.n, h->cand_p.n)), 0xFFFFFFFFu);
+    c.best_t = h->d_best_t.p;
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
     for (int k = 0; k < 2; ++k) c.sub_cap[k] = (uint32_t) h->sub_seg[k].n;
-    for (int k = 0; k < N_CLS; ++k) { c.blk_seg[k] = h->blk_seg[k].p; c.run_seg[k] = h->run_seg[k].p; }
-    c.blk_cap = big.blk_cap;
-    c.tab_t = h->tab_t.p; c.tab_p = h->tab_p.p; c.tab_cap = std::min(h->tab_t.n, h->tab_p.n);
-    c.item_person = h->item_person.p; c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_pair = h->item_pair.p;
-    c.item_cap = std::min(std::min(h->item_person.n, h->item_key.n), std::min(h->item_tab.n, h->item_pair.n));
+    for (int k = 0; k < N_HOT; ++k) { c.hot_seg[k] = h->hot_seg[k].p; c.hot_run[k] = h->hot_run[k].p; }
+    c.hot_cap = big.hot_cap;
+    c.tab_now = h->tab_now.p; c.tab_dur = h->tab_dur.p; c.tab_head = h->tab_head.p;
+    c.tab_cap = std::min(std::min(h->tab_now.n, h->tab_dur.n), h->tab_head.n);
+    c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_cnt = h->item_cnt.p;
+    c.item_cap = std::min(std::min(h->item_key.n, h->item_tab.n), h->item_cnt.n);
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
-    CU(h, cudaEventRecord(h->ev[4], s));
-    launch_transmit(c, h->n_sm, h->ts, launches);
-    CU(h, cudaEventRecord(h->ev[6], s));
+    TransmitStreams ts{};
+    ts.main = s;
+    for (int k = 0; k < N_AUX; ++k) { ts.aux[k] = h->aux[k]; ts.join[k] = we.join[k]; }
+    ts.fork = we.fork; ts.mid = we.mid; ts.filtered = we.filtered;
+    launch_transmit(c, h->n_sm, ts, launches);
+    CU(h, cudaEventRecord(we.transmitted, s));
     CU(h, cudaGetLastError());
     h->win_state = 2;
     return HEROS_OK;
 }
 
+// 5. resolve: earliest successful draw per person wins.  Nothing is read back: the window is finished on the host as
+// soon as it is enqueued.
 int32_t window_finish(heros_handle h)
 {
     cudaStream_t s = h->stream;
     double T1 = h->win_T1;
     uint32_t N = h->n_agents;
-    int& launches = h->win_launches;
+    WindowEvents& we = h->ring[h->win_ring];
     AgentArrays A = agent_arrays(h);
-
-    // 5. resolve: earliest successful draw per person wins
-    CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p, (uint32_t) h->cand_person.n};
+    CandArrays C{h->cand_person.p, h->cand_gkey.p, h->cand_t.p, h->cand_p.p,
+                 (uint32_t) std::min<size_t>(std::min(std::min(h->cand_person.n, h->cand_gkey.n), std::min(h->cand_t.n, h->cand_p.n)), 0xFFFFFFFFu)};
     InfLog log{h->inf_person.p, h->inf_gkey.p, h->inf_t.p, h->inf_p.p, h->inf_person.n};
     unsigned long long* best_t = h->d_best_t.p;
     unsigned long long* best_key = h->d_best_key.p;
     uint32_t* claim = h->d_claim.p;
+    long long* series = h->d_series.p;
     if (h->resolve_grid == 0)
     {
         int per_sm = 0;
@@ -915,72 +1133,17 @@ int32_t window_finish(heros_handle h)
         if (per_sm < 1) return fail(h, HEROS_ERR_CUDA, "k_resolve does not fit on an SM");
         h->resolve_grid = h->n_sm;
     }
-    void* args[] = {&C, &A, &best_t, &best_key, &claim, &log, &T1, &N};
+    void* args[] = {&C, &A, &best_t, &best_key, &claim, &log, &T1, &N, &series};
     CU(h, cudaLaunchCooperativeKernel((const void*) k_resolve, dim3(h->resolve_grid), dim3(1024), args, 0, s));
-    launches += 1;
-    CU(h, cudaEventRecord(h->ev[7], s));
+    h->win_launches += 1;
+    CU(h, cudaEventRecord(we.resolved, s));
     CU(h, cudaGetLastError());
-    int32_t rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
-    // the stays that outlive the window were moved to the other pool buffer by k_bucket_scatter
-    h->n_pool = h->n_carried = (uint32_t) h->h_ctr->n_keep;
-    h->pool_cur ^= 1;
-    {
-        // ev[2] start, [3] after k_window_open, [4] after bucketing, ts.mid after k_transmit_thread, [6] after the joined
-        // sub-warp / group kernels, [7] after resolve.  (With a multi-GPU host the intervals also contain the time the
-        // engine waited for the exchanges.)
-        cudaEvent_t marks[6] = {h->ev[2], h->ev[3], h->ev[4], h->ts.mid, h->ev[6], h->ev[7]};
-        for (int k = 0; k < 5; ++k)
-        {
-            float ms = 0.f;
-            CU(h, cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
-            h->stage_ms[k] += ms;
-        }
-        for (int k = 0; k < N_AUX; ++k)
-        {
-            float ms = 0.f;
-            CU(h, cudaEventElapsedTime(&ms, h->ts.fork, h->ts.join[k]));
-            h->aux_done_ms[k] += ms;
-        }
-        if (h->cfg.flags & HEROS_FLAG_PHASE_CLOCKS)
-        {
-            // development aid: when did the kernels of the auxiliary streams finish, relative to the fork after the scatter
-            float a[N_AUX] = {0, 0, 0, 0, 0}, mid = 0, end = 0;
-            for (int k = 0; k < N_AUX; ++k) cudaEventElapsedTime(&a[k], h->ts.fork, h->ts.join[k]);
-            cudaEventElapsedTime(&mid, h->ts.fork, h->ts.mid);
-            cudaEventElapsedTime(&end, h->ts.fork, h->ev[6]);
-            fprintf(stderr, "[heros] after fork: group<2> %.1f us, group<3> %.1f, group<1> %.1f, group<0> %.1f, thread %.1f, sub<32> %.1f, all + draw %.1f\n",
-                    a[0] * 1e3, a[4] * 1e3, a[1] * 1e3, a[2] * 1e3, mid * 1e3, a[3] * 1e3, end * 1e3);
-        }
-        cudaEvent_t bk[3] = {h->ev_bk[0], h->ev_bk[1], h->ev[4]};
-        for (int k = 0; k < 2; ++k)
-        {
-            float ms = 0.f;
-            CU(h, cudaEventElapsedTime(&ms, bk[k], bk[k + 1]));
-            h->bucket_part_ms[k + 1] += ms;
-        }
-    }
+    we.pending = true;
+    h->launches_total += h->win_launches;
     h->win_state = 0;
     h->n_guest = 0;
     h->t_now = T1;
-    if (h->h_ctr->overflow)
-    {
-        char buf[160];
-        snprintf(buf, sizeof buf, "device buffer overflow (mask %u: 1 candidates, 2 scratch, 4 transition log, 8 infection log, 16 exchange block, 32 pool, 64 a peer did not answer)",
-                 h->h_ctr->overflow);
-        return fail(h, HEROS_ERR_CAPACITY, buf);
-    }
     h->series_t.push_back(T1);
-    for (int k = 0; k < 8; ++k) h->series_counts.push_back((int64_t) h->h_ctr->phase_counts[k]);
-    if (h->h_ctr->invalid_visits != h->invalid_reported)
-    {
-        // not silently: stays with ids outside the tables or NaN / negative times were left out of this window
-        char buf[200];
-        snprintf(buf, sizeof buf, "%u submitted stays were rejected (person, location or sub-location id out of range, or a NaN / negative time); the window ran without them",
-                 h->h_ctr->invalid_visits - h->invalid_reported);
-        h->invalid_reported = h->h_ctr->invalid_visits;
-        return fail(h, HEROS_ERR_INVALID, buf);
-    }
     return HEROS_OK;
 }
 
@@ -1033,18 +1196,23 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         return (int32_t) HEROS_ERR_CUDA;
     };
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->sub_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (auto& a : h->aux)
+        if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
-    for (auto& ev : h->ev_bk)
-        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
-    h->ts.main = h->stream;
-    for (auto& a : h->ts.aux)
-        if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-    if ((e = cudaEventCreate(&h->ts.fork)) != cudaSuccess) return bail("event", e);
-    if ((e = cudaEventCreate(&h->ts.mid)) != cudaSuccess) return bail("event", e);
-    if ((e = cudaEventCreateWithFlags(&h->ts.filtered, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
-    for (auto& j : h->ts.join)
-        if ((e = cudaEventCreate(&j)) != cudaSuccess) return bail("event", e);
+    for (cudaEvent_t* ev : {&h->ev_rolled, &h->ev_submitted, &h->ev_copied, &h->ev_stage_free[0], &h->ev_stage_free[1]})
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    for (auto& we : h->ring)
+    {
+        for (cudaEvent_t* ev : {&we.begin, &we.opened, &we.scanned, &we.scattered, &we.mid, &we.transmitted, &we.resolved,
+                                &we.fork, &we.join[0], &we.join[1], &we.join[2]})
+            if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("event", e);
+        if ((e = cudaEventCreateWithFlags(&we.filtered, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    }
+    static_assert(N_AUX == 3, "the events of the auxiliary streams are listed by hand");
+    if ((e = h->d_series.ensure((size_t) SERIES_RING * 8)) != cudaSuccess) return bail("series", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
     if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -1059,7 +1227,10 @@ int32_t heros_destroy(heros_handle h)
 {
     if (!h) return HEROS_OK;
     cudaSetDevice(h->cfg.device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->sub_stream) cudaStreamSynchronize(h->sub_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& a : h->aux) if (a) cudaStreamSynchronize(a);
     h->d_policy.release(); h->d_prog.release(); h->d_loc_base.release(); h->d_key_loc.release();
     h->d_loc_nsub.release(); h->d_loc_param.release(); h->d_last_calc.release(); h->d_view.release();
     h->d_key_total.release(); h->d_total_loc.release(); h->d_loc_key.release();
@@ -1067,9 +1238,12 @@ int32_t heros_destroy(heros_handle h)
     h->d_best_key.release(); h->d_claim.release(); h->d_open_key.release();
     for (int i = 0; i < 2; ++i)
     {
-        h->pool_person[i].release(); h->pool_key[i].release(); h->pool_tin[i].release(); h->pool_tout[i].release();
-        h->pool_rank[i].release();
+        h->carry_person[i].release(); h->carry_key[i].release(); h->carry_tin[i].release(); h->carry_tout[i].release();
+        h->carry_rank[i].release();
+        h->st_person[i].release(); h->st_loc[i].release(); h->st_sub[i].release(); h->st_tin[i].release(); h->st_tout[i].release();
     }
+    h->fresh_person.release(); h->fresh_key.release(); h->fresh_tin.release(); h->fresh_tout.release(); h->fresh_rank.release();
+    h->d_series.release();
     h->bk_count.release(); h->bk_rank.release(); h->scan_status.release(); h->rec.release();
     h->seg_start.release(); h->g_rank.release(); h->cand_person.release();
     h->cand_gkey.release(); h->cand_t.release();
@@ -1077,41 +1251,49 @@ int32_t heros_destroy(heros_handle h)
     h->g_gid.release(); h->g_key.release(); h->g_view.release(); h->g_ill_end.release(); h->g_tin.release();
     h->g_tout.release(); h->d_nguest_cand.release();
     h->inf_p.release(); h->tr_time.release(); h->tr_phase.release(); h->sub_seg[0].release(); h->sub_seg[1].release();
-    h->item_person.release(); h->item_key.release(); h->item_tab.release(); h->item_pair.release();
-    h->tab_t.release(); h->tab_p.release();
-    for (auto& b : h->blk_seg) b.release();
-    for (auto& b : h->run_seg) b.release();
+    h->item_key.release(); h->item_tab.release(); h->item_cnt.release();
+    h->tab_now.release(); h->tab_dur.release(); h->tab_head.release();
+    for (auto& b : h->hot_seg) b.release();
+    for (auto& b : h->hot_run) b.release();
     h->huge_off.release(); h->scratch.release();
     h->s_closure.release(); h->s_loc_type.release(); h->m_times.release(); h->m_sub.release(); h->m_loc.release();
     h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
     h->s_choice_type.release(); h->s_nearest.release(); h->s_ncand.release(); h->s_cand.release(); h->d_home_loc.release();
     h->d_work_loc.release(); h->s_choice_cum.release(); h->d_home_sub.release(); h->d_work_sub.release();
-    h->d_ctr.release(); h->st_person.release(); h->st_loc.release(); h->st_sub.release(); h->st_tin.release();
-    h->st_tout.release();
+    h->d_ctr.release(); h->x_person.release(); h->x_time.release();
     for (int d = 0; d < 64; ++d)
         if (h->xc.opened[d]) cudaIpcCloseMemHandle(h->xc.peer[d]);
     if (h->xc.region) cudaFree(h->xc.region);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
-    for (auto& ev : h->ev_bk) if (ev) cudaEventDestroy(ev);
-    for (auto& a : h->ts.aux) if (a) cudaStreamDestroy(a);
-    if (h->ts.fork) cudaEventDestroy(h->ts.fork);
-    if (h->ts.mid) cudaEventDestroy(h->ts.mid);
-    if (h->ts.filtered) cudaEventDestroy(h->ts.filtered);
-    for (auto& j : h->ts.join) if (j) cudaEventDestroy(j);
+    for (cudaEvent_t ev : {h->ev_rolled, h->ev_submitted, h->ev_copied, h->ev_stage_free[0], h->ev_stage_free[1]})
+        if (ev) cudaEventDestroy(ev);
+    for (auto& we : h->ring)
+        for (cudaEvent_t ev : {we.begin, we.opened, we.scanned, we.scattered, we.mid, we.transmitted, we.resolved, we.fork,
+                               we.filtered, we.join[0], we.join[1], we.join[2]})
+            if (ev) cudaEventDestroy(ev);
+    for (auto& a : h->aux) if (a) cudaStreamDestroy(a);
+    if (h->sub_stream) cudaStreamDestroy(h->sub_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return HEROS_OK;
 }
 
 int32_t heros_set_location_types(heros_handle h, int32_t n, const uint8_t* infect_sub, const double* corr,
-                                 const uint8_t*, const double*, const double*)
+                                 const uint8_t* cap_constrained, const double* cap_per_m2, const double*)
 {
     if (!h) return HEROS_ERR_INVALID;
     if (n <= 0 || n > 256 || !infect_sub || !corr) return fail(h, HEROS_ERR_INVALID, "bad location type table");
     h->n_types = n;
     h->type_infect_sub.assign(infect_sub, infect_sub + n);
     h->type_corr.assign(corr, corr + n);
+    // capConstrained / capPersonsPerM2 (locationtypes.csv columns 8-9): read by the capacity-constrained locators of the
+    // device-side activity schedule
+    h->type_cap_constrained.assign((size_t) n, 0);
+    h->type_cap_per_m2.assign((size_t) n, 0.0);
+    if (cap_constrained) h->type_cap_constrained.assign(cap_constrained, cap_constrained + n);
+    if (cap_per_m2) h->type_cap_per_m2.assign(cap_per_m2, cap_per_m2 + n);
     return HEROS_OK;
 }
 
@@ -1194,6 +1376,9 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     if (!h) return HEROS_ERR_INVALID;
     if (n <= 0) return fail(h, HEROS_ERR_INVALID, "bad person table");
     cudaSetDevice(h->cfg.device);
+    CU(h, cudaStreamSynchronize(h->sub_stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->sub_used = false;
     const size_t N = (size_t) n;
     h->n_agents = (uint32_t) n;
     h->have_schedule = false;
@@ -1230,9 +1415,12 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     CU(h, cudaMemcpyAsync(h->d_ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
     { const int32_t rc_ = sync_counters(h); if (rc_ != HEROS_OK) return rc_; }
     d_age.release(); d_female.release(); d_role.release();
-    h->n_pool = h->n_carried = 0; h->t_now = 0.0;
+    h->fresh_ub = h->carry_ub = 0; h->t_now = 0.0; h->win_state = 0;
     if (h->bk_count.p) CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, h->stream));  // tickets of dropped stays
-    h->series_t.clear(); h->series_counts.clear();
+    h->series_t.clear(); h->series_counts.clear(); h->series_fetched = 0;
+    h->o_inf_n = h->o_tr_n = ~0ull;  // the event logs start again: the sorted output caches are stale
+    h->invalid_reported = 0;
+    CU(h, cudaStreamSynchronize(h->stream));
     return HEROS_OK;
 }
 
@@ -1310,10 +1498,10 @@ int32_t heros_expose(heros_handle h, int32_t n, const int32_t* person, const dou
     if (n < 0 || (n > 0 && (!person || !at_time))) return fail(h, HEROS_ERR_INVALID, "null argument");
     if (n == 0) return HEROS_OK;
     cudaSetDevice(h->cfg.device);
-    CU(h, h->st_person.ensure(n)); CU(h, h->st_tin.ensure(n));
-    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->st_tin.p, at_time, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
-    k_expose<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, h->st_tin.p,
+    CU(h, h->x_person.ensure(n)); CU(h, h->x_time.ensure(n));
+    CU(h, cudaMemcpyAsync(h->x_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->x_time.p, at_time, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_expose<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->x_person.p, h->x_time.p,
                                                    h->n_agents);
     CU(h, cudaGetLastError());
     return sync_counters(h);  // also refreshes the host copy of the counters (transitions, phase counts)
@@ -1350,23 +1538,39 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
     return heros_expose(h, n_infected, chosen.data(), t0.data());
 }
 
+// k_submit of a batch of stays: on the side stream, so that it can run beside the transmission stage of a window that
+// is still in progress (it only needs that window's pools to have been consumed: ev_rolled).  ready: an event the
+// input columns depend on (the host -> device copies of heros_submit_visits), or nullptr.
 static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc,
-                                  const int16_t* sub, const double* tin, const double* tout)
+                                  const int16_t* sub, const double* tin, const double* tout, cudaEvent_t ready, int stage)
 {
     if (h->win_state != 0)
         return fail(h, HEROS_ERR_INVALID, "stays cannot be submitted while a window opened by heros_window_begin is in progress");
-    if ((uint64_t) h->n_pool + (uint64_t) n + h->n_agents >= 0xFFFFFFF0ull)
+    if ((uint64_t) h->carry_ub + (uint64_t) h->fresh_ub + (uint64_t) n + h->n_agents >= 0xFFFFFFF0ull)
         return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
-    int32_t rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + n, true);
+    int32_t rc = ensure_fresh(h, h->fresh_ub + (size_t) n);
     if (rc != HEROS_OK) return rc;
+    cudaStream_t ss = h->sub_stream;
+    if (ready) CU(h, cudaStreamWaitEvent(ss, ready, 0));
+    if (!(h->cfg.flags & HEROS_FLAG_RESIDENT_INPUTS) && !ready)
+    {
+        // the caller's device buffers may have been produced on the engine stream: order the kernel behind it
+        CU(h, cudaEventRecord(h->ev_copied, h->stream));
+        CU(h, cudaStreamWaitEvent(ss, h->ev_copied, 0));
+    }
+    else
+        CU(h, cudaStreamWaitEvent(ss, h->ev_rolled, 0));  // the pools of the last window have been consumed
     const SubmitIn in{person, loc, sub, tin, tout};
-    const PoolArrays P = pool_arrays(h, h->pool_cur);
     h->ctr_current = false;
-    k_submit<<<item_blocks(n), TPB, 0, h->stream>>>(in, (uint32_t) n, P, h->n_pool, h->d_open_key.p, h->d_open_tin.p,
-                                                   h->d_loc_key.p, h->n_loc, h->n_agents,
-                                                   h->person_base, h->location_base, h->t_now, h->bk_count.p, h->d_ctr.p);
+    k_submit<<<item_blocks(n), TPB, 0, ss>>>(in, (uint32_t) n, fresh_arrays(h), (uint32_t) std::min<size_t>(h->fresh_person.n, 0xFFFFFFFFu),
+                                             h->d_open_key.p, h->d_open_tin.p, h->d_loc_key.p, h->n_loc, h->n_agents,
+                                             h->person_base, h->location_base, h->t_now, h->bk_count.p, h->d_ctr.p);
     CU(h, cudaGetLastError());
-    h->n_pool += (uint32_t) n;
+    CU(h, cudaEventRecord(h->ev_submitted, ss));
+    if (stage >= 0) CU(h, cudaEventRecord(h->ev_stage_free[stage], ss));
+    h->sub_used = true;
+    h->fresh_ub += (size_t) n;
+    h->launches_total += 1;
     return HEROS_OK;
 }
 
@@ -1377,17 +1581,31 @@ int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, co
     if (rc != HEROS_OK) return rc;
     if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
     if (n == 0) return HEROS_OK;
+    if (h->win_state != 0)
+        return fail(h, HEROS_ERR_INVALID, "stays cannot be submitted while a window opened by heros_window_begin is in progress");
     cudaSetDevice(h->cfg.device);
-    CU(h, h->st_person.ensure(n)); CU(h, h->st_loc.ensure(n)); CU(h, h->st_sub.ensure(n));
-    CU(h, h->st_tin.ensure(n)); CU(h, h->st_tout.ensure(n));
-    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->st_loc.p, loc, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->st_sub.p, sub, (size_t) n * 2, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->st_tin.p, tin, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(h->st_tout.p, tout, (size_t) n * 8, cudaMemcpyHostToDevice, h->stream));
-    rc = submit_from_device(h, n, h->st_person.p, h->st_loc.p, h->st_sub.p, h->st_tin.p, h->st_tout.p);
+    // The columns go to one of two staging sets on the copy stream: the copy runs beside whatever the engine stream is
+    // doing (a window enqueued by heros_step_async), and the call returns as soon as the caller's buffers have been read.
+    const int k = h->st_cur;
+    h->st_cur ^= 1;
+    cudaStream_t cs = h->copy_stream;
+    CU(h, cudaStreamWaitEvent(cs, h->ev_stage_free[k], 0));  // the kernel that read this staging set has finished
+    if ((size_t) n > h->st_person[k].n)
+    {
+        CU(h, cudaStreamSynchronize(h->sub_stream));
+        CU(h, h->st_person[k].ensure(n)); CU(h, h->st_loc[k].ensure(n)); CU(h, h->st_sub[k].ensure(n));
+        CU(h, h->st_tin[k].ensure(n)); CU(h, h->st_tout[k].ensure(n));
+    }
+    CU(h, cudaMemcpyAsync(h->st_person[k].p, person, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
+    CU(h, cudaMemcpyAsync(h->st_loc[k].p, loc, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
+    CU(h, cudaMemcpyAsync(h->st_sub[k].p, sub, (size_t) n * 2, cudaMemcpyHostToDevice, cs));
+    CU(h, cudaMemcpyAsync(h->st_tin[k].p, tin, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
+    CU(h, cudaMemcpyAsync(h->st_tout[k].p, tout, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
+    CU(h, cudaEventRecord(h->ev_copied, cs));
+    rc = submit_from_device(h, n, h->st_person[k].p, h->st_loc[k].p, h->st_sub[k].p, h->st_tin[k].p, h->st_tout[k].p,
+                            h->ev_copied, k);
     if (rc != HEROS_OK) return rc;
-    CU(h, cudaStreamSynchronize(h->stream));  // the caller may reuse its buffers
+    CU(h, cudaStreamSynchronize(cs));  // the caller may reuse its buffers
     return HEROS_OK;
 }
 
@@ -1399,20 +1617,29 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
     if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
     if (n == 0) return HEROS_OK;
     cudaSetDevice(h->cfg.device);
-    return submit_from_device(h, n, person, loc, sub, tin, tout);  // asynchronous on the engine stream
+    return submit_from_device(h, n, person, loc, sub, tin, tout, nullptr, -1);  // asynchronous
 }
 
-static void begin_stats(heros_handle h, Counters& before)
+// Statistics of a call (or of the windows between two heros_wait calls) = differences of the device counters, which
+// count over the whole life of the engine, plus the stage times of the windows harvested in between.
+static void begin_stats(heros_handle h)
 {
-    before = *h->h_ctr;
+    h->win_before = *h->h_ctr;
+    h->launches_before = h->launches_total;
     for (double& m : h->stage_ms) m = 0.0;
     for (double& m : h->bucket_part_ms) m = 0.0;
     for (double& m : h->aux_done_ms) m = 0.0;
 }
 
-static void fill_stats(heros_handle h, const Counters& before, heros_step_stats& st)
+static void fill_stats(heros_handle h, heros_step_stats& st)
 {
     const Counters& now = *h->h_ctr;
+    const Counters& before = h->win_before;
+    st.windows = (int64_t) (now.windows - before.windows);
+    st.visits = (int64_t) (now.visits_total - before.visits_total);
+    st.sublocations = (int64_t) (now.seg_total - before.seg_total);
+    st.big_sublocations = (int64_t) (now.hot_total - before.hot_total);
+    st.gpu_launches = h->launches_total - h->launches_before;
     st.evaluations = (int64_t) (now.evaluations - before.evaluations);
     st.draws = (int64_t) (now.draws - before.draws);
     st.infections = (int64_t) (now.infections - before.infections);
@@ -1425,19 +1652,11 @@ static void fill_stats(heros_handle h, const Counters& before, heros_step_stats&
     st.transmit_ms = h->stage_ms[2] + h->stage_ms[3];
     st.bucket_count_ms = h->bucket_part_ms[0]; st.bucket_scan_ms = h->bucket_part_ms[1];
     st.bucket_scatter_ms = h->bucket_part_ms[2];
-    // aux streams: 0 class 2, 1 class 1, 2 class 0, 3 sub-warp 32, 4 classes 3 + 4
-    st.group_done_ms[0] = h->aux_done_ms[2]; st.group_done_ms[1] = h->aux_done_ms[1];
-    st.group_done_ms[2] = h->aux_done_ms[0]; st.group_done_ms[3] = h->aux_done_ms[4];
-    st.sub32_done_ms = h->aux_done_ms[3];
-}
-
-static void add_window_stats(heros_handle h, heros_step_stats& st)
-{
-    st.windows++;
-    st.visits += (int64_t) h->h_ctr->n_active;
-    st.sublocations += (int64_t) h->h_ctr->n_seg;
-    for (int k = 0; k < N_CLS; ++k) st.big_sublocations += (int64_t) h->h_ctr->n_blk[k];
-    st.gpu_launches += h->win_launches;
+    // auxiliary streams, time from the fork (after the scatter): 0 the hot path (filter, chain, evaluation), 2 the chain
+    // kernel of the small class, 1 the 32-lane sub-warp kernel
+    st.group_done_ms[0] = h->aux_done_ms[0]; st.group_done_ms[1] = h->aux_done_ms[2];
+    st.group_done_ms[2] = 0.0; st.group_done_ms[3] = 0.0;
+    st.sub32_done_ms = h->aux_done_ms[1];
 }
 
 int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,
@@ -1445,17 +1664,23 @@ int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person,
 {
     if (!h || !n_out || capacity < 0) return HEROS_ERR_INVALID;
     cudaSetDevice(h->cfg.device);
-    const size_t np = h->n_pool, N = h->n_agents;
+    int32_t rc = check_idle(h, "heros_debug_get_stays");
+    if (rc != HEROS_OK) return rc;
+    if ((rc = sync_counters(h)) != HEROS_OK) return rc;  // the fill counts of the pools
+    const size_t nf = (size_t) h->h_ctr->n_fresh, nc = (size_t) h->h_ctr->n_carry, np = nf + nc, N = h->n_agents;
     std::vector<uint32_t> pp(np), pk(np), ok(N);
     std::vector<double> pi(np), po(np), oi(N);
-    const PoolArrays P = pool_arrays(h, h->pool_cur);
-    if (np)
-    {
-        CU(h, cudaMemcpyAsync(pp.data(), P.person, np * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(pk.data(), P.key, np * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(pi.data(), P.tin, np * 8, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(po.data(), P.tout, np * 8, cudaMemcpyDeviceToHost, h->stream));
-    }
+    const PoolArrays F = fresh_arrays(h), Cy = carry_arrays(h, h->carry_cur);
+    auto fetch = [&](const PoolArrays& P, size_t n, size_t at) -> cudaError_t {
+        if (!n) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(pp.data() + at, P.person, n * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(pk.data() + at, P.key, n * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(pi.data() + at, P.tin, n * 8, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return e;
+        return cudaMemcpyAsync(po.data() + at, P.tout, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    };
+    CU(h, fetch(Cy, nc, 0));
+    CU(h, fetch(F, nf, nc));
     CU(h, cudaMemcpyAsync(ok.data(), h->d_open_key.p, N * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(oi.data(), h->d_open_tin.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1480,42 +1705,71 @@ int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person,
     return n > capacity && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
 }
 
-int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
+// the windows up to t_until, enqueued without waiting for any of them
+static int32_t enqueue_windows(heros_handle h, double t_until)
 {
     int32_t rc = check_ready(h);
     if (rc != HEROS_OK) return rc;
-    if (h->win_state != 0) return fail(h, HEROS_ERR_INVALID, "a window opened by heros_window_begin is still in progress");
+    if ((rc = check_idle(h, "heros_step")) != HEROS_OK) return rc;
     if (!(t_until >= h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until lies before the engine time");
     const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
     if (!(h->cfg.window_hours <= latent - 1e-3))
         return fail(h, HEROS_ERR_UNSUPPORTED, "window_hours must be below the latent period of the transmission model");
     cudaSetDevice(h->cfg.device);
-    Counters before;
-    begin_stats(h, before);  // the host copy of the counters is current: every call that changes them refreshes it
-    heros_step_stats st{};
-    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    if (!h->async_open)
+    {
+        begin_stats(h);
+        CU(h, cudaEventRecord(h->ev[0], h->stream));
+        h->async_open = true;
+    }
     while (h->t_now < t_until)
     {
         const double T1 = std::min(h->t_now + h->cfg.window_hours, t_until);
         if ((rc = window_begin(h, T1)) != HEROS_OK) return rc;
         if ((rc = window_transmit(h)) != HEROS_OK) return rc;
         if ((rc = window_finish(h)) != HEROS_OK) return rc;
-        add_window_stats(h, st);
     }
-    CU(h, cudaEventRecord(h->ev[1], h->stream));
-    CU(h, cudaEventSynchronize(h->ev[1]));
-    float ms = 0.f;
-    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    fill_stats(h, before, st);
-    st.gpu_ms = ms;
-    if (stats) *stats = st;
     return HEROS_OK;
+}
+
+// waits for everything enqueued, fills the statistics since the last wait and reports what the windows have to report
+static int32_t wait_and_report(heros_handle h, heros_step_stats* stats)
+{
+    cudaSetDevice(h->cfg.device);
+    float ms = 0.f;
+    if (h->async_open) CU(h, cudaEventRecord(h->ev[1], h->stream));
+    int32_t rc = sync_counters(h);
+    if (rc != HEROS_OK) return rc;
+    if (h->async_open) CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    heros_step_stats st{};
+    if (h->async_open) fill_stats(h, st);
+    st.gpu_ms = ms;
+    h->async_open = false;
+    if (stats) *stats = st;
+    return report_window_errors(h);
+}
+
+int32_t heros_step(heros_handle h, double t_until, heros_step_stats* stats)
+{
+    const int32_t rc = enqueue_windows(h, t_until);
+    if (rc != HEROS_OK) return rc;
+    return wait_and_report(h, stats);
+}
+
+int32_t heros_step_async(heros_handle h, double t_until) { return enqueue_windows(h, t_until); }
+
+int32_t heros_wait(heros_handle h, heros_step_stats* stats)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    const int32_t rc = check_idle(h, "heros_wait");
+    if (rc != HEROS_OK) return rc;
+    return wait_and_report(h, stats);
 }
 
 int32_t heros_set_id_bases(heros_handle h, int32_t person_base, int32_t location_base)
 {
     if (!h || person_base < 0 || location_base < 0) return HEROS_ERR_INVALID;
-    if (h->n_pool != 0 || h->t_now != 0.0) return fail(h, HEROS_ERR_INVALID, "id bases must be set before any stay is submitted");
+    if (h->fresh_ub != 0 || h->carry_ub != 0 || h->t_now != 0.0) return fail(h, HEROS_ERR_INVALID, "id bases must be set before any stay is submitted");
     h->person_base = (uint32_t) person_base;
     h->location_base = location_base;
     return HEROS_OK;
@@ -1529,8 +1783,12 @@ int32_t heros_window_begin(heros_handle h, double t_until)
     if (!(t_until > h->t_now)) return fail(h, HEROS_ERR_INVALID, "t_until must lie after the engine time");
     if ((rc = check_window_length(h, t_until)) != HEROS_OK) return rc;
     cudaSetDevice(h->cfg.device);
-    begin_stats(h, h->win_before);
-    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    if (!h->async_open)
+    {
+        begin_stats(h);
+        CU(h, cudaEventRecord(h->ev[0], h->stream));
+        h->async_open = true;
+    }
     return window_begin(h, t_until);
 }
 
@@ -1542,23 +1800,46 @@ int32_t heros_window_transmit(heros_handle h)
     return window_transmit(h);
 }
 
+// A window that cannot be completed (an exchange call failed between its phases) is carried out with what it has: no
+// further guests, no further candidates.  The engine is idle again afterwards; peers that wait for this shard's flags
+// are the caller's to release (heros_window_send_guests / _candidates with no rows raise them).
+int32_t heros_window_abort(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->win_state == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = HEROS_OK;
+    if (h->win_state == 1) rc = window_transmit(h);
+    if (rc == HEROS_OK && h->win_state == 2) rc = window_finish(h);
+    if (rc != HEROS_OK)
+    {
+        // not even that: the pipeline state is reset by hand (the window's stays are lost)
+        h->win_state = 0;
+        h->n_guest = 0;
+        h->t_now = h->win_T1;
+    }
+    h->async_open = false;
+    sync_counters(h);
+    return rc;
+}
+
 int32_t heros_window_finish(heros_handle h, heros_step_stats* stats)
 {
     if (!h) return HEROS_ERR_INVALID;
     if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "heros_window_transmit has not been called");
     cudaSetDevice(h->cfg.device);
-    int32_t rc = window_finish(h);
+    const int32_t rc = window_finish(h);
     if (rc != HEROS_OK) return rc;
-    CU(h, cudaEventRecord(h->ev[1], h->stream));
-    CU(h, cudaEventSynchronize(h->ev[1]));
-    float ms = 0.f;
-    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    heros_step_stats st{};
-    add_window_stats(h, st);
-    fill_stats(h, h->win_before, st);
-    st.gpu_ms = ms;
-    if (stats) *stats = st;
-    return HEROS_OK;
+    return wait_and_report(h, stats);
+}
+
+// the same without waiting: the window is finished on the device some time later (heros_wait)
+int32_t heros_window_finish_async(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "heros_window_transmit has not been called");
+    cudaSetDevice(h->cfg.device);
+    return window_finish(h);
 }
 
 int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
@@ -1666,7 +1947,9 @@ int32_t heros_get_phase_counts(heros_handle h, int64_t counts[8])
 int32_t heros_get_count_series(heros_handle h, int64_t capacity, double* times, int64_t* counts, int64_t* n_out)
 {
     if (!h || !n_out || capacity < 0) return HEROS_ERR_INVALID;
-    const int64_t n = (int64_t) h->series_t.size();
+    cudaSetDevice(h->cfg.device);
+    { const int32_t rc_ = current_counters(h); if (rc_ != HEROS_OK) return rc_; }  // fetches the rows of the finished windows
+    const int64_t n = (int64_t) std::min(h->series_t.size(), h->series_counts.size() / 8);
     const int64_t m = std::min(n, capacity);
     if (times) memcpy(times, h->series_t.data(), (size_t) m * 8);
     if (counts) memcpy(counts, h->series_counts.data(), (size_t) m * 64);
@@ -1701,11 +1984,11 @@ int32_t heros_set_agent_state(heros_handle h, int32_t n, const int32_t* person, 
     if (n == 0) return HEROS_OK;
     cudaSetDevice(h->cfg.device);
     DevBuf<uint8_t> d_phase; DevBuf<float> d_exp;
-    CU(h, h->st_person.ensure(n)); CU(h, d_phase.ensure(n)); CU(h, d_exp.ensure(n));
-    CU(h, cudaMemcpyAsync(h->st_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, h->x_person.ensure(n)); CU(h, d_phase.ensure(n)); CU(h, d_exp.ensure(n));
+    CU(h, cudaMemcpyAsync(h->x_person.p, person, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(d_phase.p, phase, (size_t) n, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(d_exp.p, exposure, (size_t) n * 4, cudaMemcpyHostToDevice, h->stream));
-    k_set_agent_state<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->st_person.p, d_phase.p,
+    k_set_agent_state<<<blocks_for(n), TPB, 0, h->stream>>>(agent_arrays(h), (uint32_t) n, h->x_person.p, d_phase.p,
                                                             d_exp.p, now, h->n_agents);
     CU(h, cudaGetLastError());
     rc = sync_counters(h);
@@ -1728,13 +2011,9 @@ int32_t heros_get_last_calculation(heros_handle h, int32_t location, int16_t sub
 
 int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
 {
+    // development aid of the former group kernels; kept in the ABI, reports nothing
     if (!h || !clocks) return HEROS_ERR_INVALID;
-    cudaSetDevice(h->cfg.device);
-    int32_t rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
-    memcpy(clocks, h->h_ctr->dbg_clk, 64 * sizeof(uint64_t));  // classes 0 - 3
-    for (int k = 0; k < 4; ++k) clocks[k * 16 + 15] = h->h_ctr->n_blk[k];  // sub-locations per class, last window
-    clocks[3 * 16 + 15] += h->h_ctr->n_blk[CLS_HUGE];
+    memset(clocks, 0, 64 * sizeof(uint64_t));
     return HEROS_OK;
 }
 

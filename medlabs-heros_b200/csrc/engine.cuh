@@ -33,7 +33,7 @@ struct TotalLoc
 };
 
 // one stay of the window in bucket order: everything transmission needs from it in one 32-byte sector
-struct alignas(16) StayRec
+struct alignas(32) StayRec
 {
     double tin, tout;
     uint64_t view;    // packed agent word of the person (phase at window start, exposure time, ...)
@@ -42,16 +42,35 @@ struct alignas(16) StayRec
 };
 constexpr uint32_t REC_GUEST = 0x80000000u;
 
+#ifdef __CUDACC__
+// a record is one 32-byte sector: moved with ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256)
+__device__ __forceinline__ StayRec ld_rec(const StayRec* p)
+{
+    uint64_t a, b, v, w;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(w) : "l"(p));
+    StayRec r;
+    r.tin = bits_f64(a); r.tout = bits_f64(b); r.view = v; r.person = (uint32_t) w; r.pad = (uint32_t) (w >> 32);
+    return r;
+}
+__device__ __forceinline__ void st_rec(StayRec* p, const StayRec& r)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(f64_bits(r.tin)), "l"(f64_bits(r.tout)), "l"(r.view),
+                 "l"((uint64_t) r.person | ((uint64_t) r.pad << 32))
+                 : "memory");
+}
+#endif
+
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
-constexpr int N_CLS = 5;     // classes of sub-locations of > 32 stays (the group kernels)
-constexpr int CLS_HUGE = 4;  // ... the last one works in global scratch
-
 // device-side counters of one engine.  The block from `n_cand` on is zeroed at the start of every window.
+constexpr int N_HOT = 3;     // classes of sub-locations of > 32 stays (the hot path): <= 1024 / <= 8192 movement events in
+                             // shared memory, anything larger in global scratch
+constexpr int HOT_HUGE = 2;
+constexpr int SERIES_RING = 4096;  // windows whose compartment counts are kept on the device between two host reads
 struct Counters
 {
     unsigned long long evaluations, draws, near_ties, infections, transitions;
-    unsigned long long big_stays;    // stays of the sub-locations handed to the group kernels
+    unsigned long long big_stays;    // stays of the sub-locations handed to the hot path
     unsigned long long n_inf_log;    // cursor of the infection log
     unsigned long long n_tr_log;     // cursor of the transition log
     unsigned long long n_sched;      // closed stays produced by the last heros_advance_schedule
@@ -60,20 +79,28 @@ struct Counters
     unsigned int late_visits;        // t_in before the engine time
     unsigned int pad;
     long long phase_counts[8];
+    // the pools of stays live on the device: nothing of a window is read back by the host
+    unsigned long long n_fresh;      // stays submitted since the last window (fresh pool)
+    unsigned long long n_carry;      // stays carried over from earlier windows (carry pool in use)
+    unsigned long long windows;      // windows finished
+    unsigned long long visits_total; // stays bucketed, summed over the windows
+    unsigned long long seg_total;    // occupied sub-locations, summed over the windows
+    unsigned long long hot_total;    // sub-locations handed to the hot path, summed over the windows
+    unsigned long long cand_total;   // candidate infections kept, summed over the windows
+    unsigned long long rate_draws;   // draws of the rate-based locations (LocationProbBased)
+    unsigned long long reserved_[4];
     // ---- per window ----
     unsigned long long n_cand;       // candidate infections of the current window (first field of the window block)
     unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
-    unsigned long long n_blk[N_CLS]; // segments handed to the group kernels (<= 256 / 1024 / 4096 / 8192 events in shared
-                                     // memory, larger ones in global scratch)
-    unsigned long long n_run[N_CLS]; // ... of which the filter kernel passed on to the group kernels
+    unsigned long long n_hot[N_HOT]; // sub-locations of > 32 stays, by class (queued by the prefix-sum kernel)
+    unsigned long long n_run[N_HOT]; // ... of which the filter kernel passed on to the chain kernel
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
     unsigned long long n_active;     // active stays of the current window
-    unsigned long long n_draw;       // draw items << 40 | (stay, evaluation) pairs they stand for
-    unsigned long long tab_top;      // entries of the table of evaluations with p > 0
+    unsigned long long n_items;      // work items (sub-location, 32 evaluations) of the hot evaluation kernel
+    unsigned long long tab_top;      // entries of the table of evaluations of the hot sub-locations
     unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
-    unsigned long long dbg_clk[N_CLS][16];  // HEROS_FLAG_PHASE_CLOCKS: max cycles per phase of k_transmit_group, per class
 };
 template <typename T>
 struct DevBuf
@@ -116,70 +143,64 @@ struct WindowCtx
     // the window's stays bucketed by sub-location: stays of key k are rec[seg_start[k] .. seg_start[k + 1])
     StayRec* rec;
     const uint32_t* seg_start;  // n_keys + 1 entries
-    // candidates
+    // candidates; best_t: earliest successful draw so far of every own agent (time bits), which lets later and therefore
+    // hopeless candidates of the same person be dropped where they arise
     uint32_t* cand_person; uint64_t* cand_gkey; double* cand_t; double* cand_p; uint32_t cand_cap;
-    // work lists filled by k_transmit_thread
+    unsigned long long* best_t;
+    // work lists filled by k_transmit_stream
     uint32_t* sub_seg[2]; uint32_t sub_cap[2];          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
-    uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;      // ... and for the group kernels
-    // draws queued by the group kernels for k_draw: the evaluations with p > 0 of every sub-location (time, p), and one
-    // item per susceptible stay = a run of table entries, numbered by its first (stay, evaluation) pair
-    double* tab_t; double* tab_p; unsigned long long tab_cap;
-    uint32_t* item_person; uint32_t* item_key; unsigned long long* item_tab; unsigned long long* item_pair;
-    unsigned long long item_cap;
-    unsigned long long* huge_off;  // byte offset into scratch of every entry of blk_seg[CLS_HUGE]
-    uint32_t* run_seg[N_CLS];      // the queued sub-locations of classes 0 and 1 that need more than lastCalculation
-                                   // advanced (k_group_filter)
+    // hot sub-locations (> 32 stays): queued by the prefix-sum kernel (hot_seg), passed on by the filter (hot_run)
+    uint32_t* hot_seg[N_HOT]; uint32_t* hot_run[N_HOT]; uint32_t hot_cap;
+    unsigned long long* huge_off;  // byte offset into scratch of every entry of hot_seg[HOT_HUGE]
     unsigned char* scratch; unsigned long long scratch_cap;
+    // the chain kernel leaves one row per calculated evaluation of a hot sub-location (time, duration, head count) and
+    // one work item per 32 of them; the evaluation kernel spreads the items over the whole GPU
+    double* tab_now; double* tab_dur; uint32_t* tab_head; unsigned long long tab_cap;
+    uint32_t* item_key; unsigned long long* item_tab; uint32_t* item_cnt; unsigned long long item_cap;
     uint32_t flags;
     Counters* ctr;
 };
 
-// Sub-locations of > 32 stays go to the group kernels, by the number of events of the sub-location and the bound on
-// its evaluations: classes 0 - 3 keep <= 256 / 1024 / 4096 / 8192 events in shared memory (17 / 66 / 126 / 196 KB per
-// group; groups of classes 0 - 2 fit on an SM side by side), class 4 works in global scratch.
-// The lists are filled by the prefix-sum kernel (it sees every bucket size), so the group kernels can start as soon as
-// the stays are in bucket order, side by side with the kernel that streams the small sub-locations.
-constexpr int BLOCK_P_CAP = 2048;  // evaluations per segment the shared-memory group kernels keep probabilities for
-constexpr int BLOCK_S_CAP = 4096;  // events per segment of class 2
-constexpr int BLOCK_S_CAP3 = 8192; // ... and of class 3, the largest shared-memory class
+// Sub-locations of > 32 stays take the hot path.  The prefix-sum kernel (it sees every bucket size) files them by the
+// number of movement events the chain kernel has to order: <= 1024 and <= 8192 events are ordered in shared memory
+// (26 KB / 205 KB per thread block), anything larger in global scratch.
+constexpr int HOT_M_CAP0 = 1024, HOT_M_CAP1 = 8192;
+constexpr int HOT_NB_CAP0 = 512, HOT_NB_CAP = 4096;  // time buckets of the event ordering
+__host__ __device__ inline unsigned long long hot_scratch_bytes(unsigned long long m)
+{
+    // ev_t f64[m] | 5 bucket arrays u32[NB + 2] | 3 index arrays u32[m + 1] | ev_k u8[m]
+    return (8ull * m + 5ull * 4ull * (HOT_NB_CAP + 2) + 3ull * 4ull * (m + 1) + m + 256ull + 15ull) & ~15ull;
+}
 struct BigLists
 {
-    uint32_t* blk_seg[N_CLS]; uint32_t blk_cap;
+    uint32_t* hot_seg[N_HOT]; uint32_t hot_cap;
     unsigned long long* huge_off; unsigned long long scratch_cap;
     const uint8_t* key_total;  // sub-locations of total-branch locations are not queued here
-    int need_enters, both;  // enter events are needed (distance model head counts / ENTER_AND_EXIT trigger)
-    double r_window;        // (T1 - T0) / threshold + 2: no window holds more evaluations of one sub-location
+    int need_enters;           // enter events are needed (distance model head counts / ENTER_AND_EXIT trigger)
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint32_t key, uint32_t n)
 {
-    const uint32_t slots = b.need_enters ? 2 * n : n;
-    double r_bound = b.both ? 2.0 * n : (double) n;
-    if (b.r_window < r_bound) r_bound = b.r_window;
-    const bool r_fits = r_bound <= (double) BLOCK_P_CAP;
-    const int cls = slots <= 256 ? 0 : (slots <= 1024 ? 1 : ((slots <= (uint32_t) BLOCK_S_CAP && r_fits) ? 2 :
-                    ((slots <= (uint32_t) BLOCK_S_CAP3 && r_fits) ? 3 : CLS_HUGE)));
-    const unsigned long long slot = atomicAdd(&ctr->n_blk[cls], 1ull);
-    if (slot >= b.blk_cap) { atomicOr(&ctr->overflow, 2u); return; }
-    b.blk_seg[cls][slot] = key;
-    if (cls == CLS_HUGE)
+    const uint32_t m = b.need_enters ? 2 * n : n;
+    const int cls = m <= (uint32_t) HOT_M_CAP0 ? 0 : (m <= (uint32_t) HOT_M_CAP1 ? 1 : HOT_HUGE);
+    const unsigned long long slot = atomicAdd(&ctr->n_hot[cls], 1ull);
+    if (slot >= b.hot_cap) { atomicOr(&ctr->overflow, 2u); return; }
+    b.hot_seg[cls][slot] = key;
+    if (cls == HOT_HUGE)
     {
-        unsigned long long mp = 64;
-        while (mp < slots) mp <<= 1;
-        const unsigned long long bytes = (unsigned long long) slots * 72 + 8192 + 20ull * (mp < 65536 ? mp : 65536);
+        const unsigned long long bytes = hot_scratch_bytes(m);
         const unsigned long long off = atomicAdd(&ctr->scratch_top, bytes);
         if (off + bytes <= b.scratch_cap) b.huge_off[slot] = off;
-        else { b.blk_seg[cls][slot] = KEY_NONE; atomicOr(&ctr->overflow, 2u); }
+        else { b.hot_seg[cls][slot] = KEY_NONE; atomicOr(&ctr->overflow, 2u); }
     }
     atomicAdd(&ctr->big_stays, (unsigned long long) n);
 }
 #endif
 
-// the engine stream, four auxiliary streams for the kernels that run side by side, and the fork / join events
-constexpr int N_AUX = 5;
+// the engine stream, the auxiliary streams of the kernels that run side by side, and the fork / join events
+constexpr int N_AUX = 3;  // 0: the hot path (filter, chain kernels of the large classes, evaluation), 1: the 32-lane
+                          // sub-warp kernel, 2: the chain kernel of the small class
 struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid, filtered; cudaEvent_t join[N_AUX]; };
-constexpr int DRAW_ITEM_SHIFT = 40;
-constexpr unsigned long long DRAW_PAIR_MASK = (1ull << DRAW_ITEM_SHIFT) - 1ull;
 
 }  // namespace heros

@@ -50,18 +50,36 @@ struct Activity { int32_t kind, locator, choice, dist; double mn, mode, mx, unti
 
 using namespace heros;
 
+// events of one window, for the per-stage device times (a small ring: the host may be several windows ahead of the device)
+constexpr int WIN_RING = 8;
+struct WindowEvents
+{
+    cudaEvent_t begin, opened, scanned, scattered, mid, transmitted, resolved;  // on the engine stream, in this order
+    cudaEvent_t fork, filtered, join[N_AUX];                                     // the auxiliary streams of the stage
+    bool pending = false;  // recorded, not yet added to the stage times
+};
+
 struct heros_engine
 {
     heros_config cfg{};
     std::string err;
-    cudaStream_t stream = nullptr;
-    TransmitStreams ts{};
-    cudaEvent_t ev[10]{};
-    cudaEvent_t ev_bk[2]{};  // before / after the prefix sum
-    double stage_ms[6]{};  // window open (state machine + tickets + retire), prefix sum + scatter, transmit thread
-                           // kernel, other transmit kernels + draws, resolve, (unused)
+    cudaStream_t stream = nullptr;       // the engine stream: every window kernel is ordered on it
+    cudaStream_t sub_stream = nullptr;   // k_submit of the next window runs here, beside the transmission of the current one
+    cudaStream_t copy_stream = nullptr;  // host -> device copies of heros_submit_visits, beside everything else
+    cudaStream_t aux[N_AUX]{};
+    cudaEvent_t ev[2]{};                 // begin / end of a heros_step (or of the windows since the last heros_wait)
+    cudaEvent_t ev_rolled = nullptr;     // the pools of the last window have been consumed (k_submit may write again)
+    cudaEvent_t ev_submitted = nullptr;  // everything submitted so far is in the pool (the next window may begin)
+    cudaEvent_t ev_stage_free[2]{};      // the staging buffers of heros_submit_visits have been read
+    cudaEvent_t ev_copied = nullptr;
+    bool sub_used = false, async_open = false;
+    WindowEvents ring[WIN_RING];
+    int ring_next = 0;
+    double stage_ms[6]{};  // window open (state machine + tickets), prefix sum + scatter, streaming kernel, rest of the
+                           // transmission stage, resolve, (unused)
     double bucket_part_ms[3]{};  // (unused), prefix sum, scatter
     double aux_done_ms[N_AUX]{}; // fork -> end of the work of every auxiliary stream
+    int64_t windows_timed = 0;
     int n_sm = 148;
     double t_now = 0.0;
 
@@ -75,6 +93,8 @@ struct heros_engine
     int n_types = 0;
     std::vector<uint8_t> type_infect_sub;
     std::vector<double> type_corr;
+    std::vector<uint8_t> type_cap_constrained;   // locationtypes.csv capConstrained / capPersonsPerM2 (schedule.cu)
+    std::vector<double> type_cap_per_m2;
 
     uint32_t n_loc = 0, n_keys = 0;
     std::vector<uint32_t> h_loc_base;
@@ -114,15 +134,19 @@ struct heros_engine
     int win_state = 0;          // 0 idle, 1 after heros_window_begin, 2 after heros_window_transmit
     double win_T0 = 0.0, win_T1 = 0.0;
     int win_launches = 0;
-    uint32_t win_n_pool = 0;
+    int64_t launches_total = 0;  // kernels launched since the engine was created
+    int win_ring = 0;            // ring slot of the window in progress
     Counters win_before{};
+    int64_t launches_before = 0;
 
-    // pool of submitted stays (double buffered)
-    DevBuf<uint32_t> pool_person[2], pool_key[2], pool_rank[2];  // rank: the ticket of the stay at its sub-location
-    uint32_t n_carried = 0;  // pool[0 .. n_carried) came over from earlier windows; the rest was submitted since
-    DevBuf<double> pool_tin[2], pool_tout[2];
-    int pool_cur = 0;
-    uint32_t n_pool = 0;
+    // The pools of stays.  fresh: submitted since the last window (k_submit / k_advance_day append, taking every stay's
+    // ticket on the way); carry[2]: stays that outlive a window move from one to the other.  Their fill counts live on
+    // the DEVICE (Counters::n_fresh / n_carry); the host only keeps upper bounds, for allocation and grid sizes.
+    DevBuf<uint32_t> fresh_person, fresh_key, fresh_rank, carry_person[2], carry_key[2], carry_rank[2];
+    DevBuf<double> fresh_tin, fresh_tout, carry_tin[2], carry_tout[2];
+    int carry_cur = 0;
+    size_t fresh_ub = 0, carry_ub = 0;   // upper bounds of n_fresh / n_carry
+    size_t fresh_seen = 0;               // largest fresh_ub of a window so far
 
     // window buffers
     DevBuf<uint32_t> bk_count, bk_rank, seg_start;
@@ -138,11 +162,13 @@ struct heros_engine
     DevBuf<unsigned long long> d_nguest_cand;
     DevBuf<double> inf_t, inf_p, tr_time;
     DevBuf<uint8_t> tr_phase;
+    DevBuf<long long> d_series;   // compartment counts at the end of the last SERIES_RING windows
+    size_t series_fetched = 0;    // windows whose counts have been copied into series_counts
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], blk_seg[N_CLS], run_seg[N_CLS], item_person, item_key;
-    DevBuf<unsigned long long> item_tab, item_pair;
-    DevBuf<double> tab_t, tab_p;
+    DevBuf<uint32_t> sub_seg[2], hot_seg[N_HOT], hot_run[N_HOT], item_key, item_cnt, tab_head;
+    DevBuf<unsigned long long> item_tab;
+    DevBuf<double> tab_now, tab_dur;
     DevBuf<unsigned long long> huge_off;
     DevBuf<unsigned char> scratch;
 
@@ -153,6 +179,7 @@ struct heros_engine
     DevBuf<double2> s_closure; DevBuf<uint8_t> s_loc_type; std::vector<double> h_closure; bool closure_active = false;
     int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
     uint64_t sched_seed = 0;
+    size_t sched_room = 0;  // stays one simulated day can end, at most (heros_set_schedule)
     DevBuf<Activity> s_acts;
     DevBuf<int32_t> s_pat_start, s_pat_count, s_choice_start, s_choice_type, s_nearest, s_ncand, s_cand, d_home_loc,
         d_work_loc;
@@ -167,10 +194,12 @@ struct heros_engine
     Counters* h_ctr = nullptr;  // pinned
     bool ctr_current = false;   // nothing that changes the counters was enqueued since h_ctr was refreshed
 
-    // staging for host submissions
-    DevBuf<int32_t> st_person, st_loc;
-    DevBuf<int16_t> st_sub;
-    DevBuf<double> st_tin, st_tout;
+    // staging for host submissions (double buffered: the copy of the next batch runs beside the kernel that reads this one)
+    DevBuf<int32_t> st_person[2], st_loc[2];
+    DevBuf<int16_t> st_sub[2];
+    DevBuf<double> st_tin[2], st_tout[2];
+    int st_cur = 0;
+    DevBuf<int32_t> x_person; DevBuf<double> x_time;  // heros_expose / heros_set_agent_state
 
     std::vector<double> series_t;
     std::vector<int64_t> series_counts;
@@ -197,10 +226,13 @@ using namespace heros;
 
 int32_t fail(heros_handle h, int32_t code, const std::string& msg);
 heros::AgentArrays agent_arrays(heros_handle h);
-heros::PoolArrays pool_arrays(heros_handle h, int which);
-int32_t ensure_pool(heros_handle h, int which, size_t n, bool keep);
-int32_t sync_counters(heros_handle h);     // D2H of the counters + stream synchronisation
+heros::PoolArrays fresh_arrays(heros_handle h);
+heros::PoolArrays carry_arrays(heros_handle h, int which);
+int32_t ensure_fresh(heros_handle h, size_t n);  // room for n stays in the fresh pool (contents kept)
+int32_t sync_counters(heros_handle h);     // D2H of the counters + synchronisation of every stream of the engine
 int32_t current_counters(heros_handle h);  // ... only if something was enqueued since the last one
 int32_t check_ready(heros_handle h);
+int32_t join_submissions(heros_handle h);  // the engine stream waits for what was submitted on the side stream
+int32_t check_idle(heros_handle h, const char* what);  // no window in progress
 
 }  // namespace heros_impl

@@ -21,11 +21,12 @@ __device__ __forceinline__ void sample_stay(uint32_t key, double tin, double tou
     for (int j = lo; j < n_times && times[j] < tout; ++j) atomicAdd(&per_sub[(size_t) j * n_keys + key], 1);
 }
 
-__global__ void __launch_bounds__(TPB) k_sample_pool(uint32_t n, const uint32_t* key, const double* tin, const double* tout,
-                                                     int n_times, const double* times, uint32_t n_keys, int32_t* per_sub)
+__global__ void __launch_bounds__(TPB) k_sample_pool(const unsigned long long* n_dev, const uint32_t* key, const double* tin,
+                                                     const double* tout, int n_times, const double* times, uint32_t n_keys,
+                                                     int32_t* per_sub)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (uint32_t) *n_dev) return;  // the fill count of the pool lives on the device
     const uint32_t k = key[i];
     if (k == KEY_NONE || k >= n_keys) return;  // retired slot / a stay in another shard's location
     sample_stay(k, tin[i], tout[i], n_times, times, n_keys, per_sub);
@@ -88,9 +89,12 @@ int32_t heros_sample_occupancy(heros_handle h, int32_t n_times, const double* ti
     CU(h, d_times.ensure(n_times)); CU(h, d_sub.ensure(n_sub_counts));
     CU(h, cudaMemcpyAsync(d_times.p, times, (size_t) n_times * 8, cudaMemcpyHostToDevice, s));
     CU(h, cudaMemsetAsync(d_sub.p, 0, n_sub_counts * 4, s));
-    const PoolArrays P = pool_arrays(h, h->pool_cur);
-    if (h->n_pool)
-        k_sample_pool<<<blocks_for(h->n_pool), TPB, 0, s>>>(h->n_pool, P.key, P.tin, P.tout, n_times, d_times.p, h->n_keys, d_sub.p);
+    { const int32_t rc_ = join_submissions(h); if (rc_ != HEROS_OK) return rc_; }  // what k_submit is still writing
+    const PoolArrays F = fresh_arrays(h), Cy = carry_arrays(h, h->carry_cur);
+    if (h->fresh_ub)
+        k_sample_pool<<<blocks_for(h->fresh_ub), TPB, 0, s>>>(&h->d_ctr.p->n_fresh, F.key, F.tin, F.tout, n_times, d_times.p, h->n_keys, d_sub.p);
+    if (h->carry_ub)
+        k_sample_pool<<<blocks_for(h->carry_ub), TPB, 0, s>>>(&h->d_ctr.p->n_carry, Cy.key, Cy.tin, Cy.tout, n_times, d_times.p, h->n_keys, d_sub.p);
     k_sample_open<<<blocks_for(h->n_agents), TPB, 0, s>>>(h->n_agents, h->d_open_key.p, h->d_open_tin.p, n_times, d_times.p,
                                                          h->n_keys, d_sub.p);
     CU(h, cudaGetLastError());

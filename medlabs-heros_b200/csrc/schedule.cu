@@ -69,7 +69,7 @@ struct StagedStays
 
 // The day of one person: every stay that ends goes to the staging area, the open stay of the person is updated.
 __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, const uint64_t* view, uint32_t* open_key,
-                                         double* open_tin, StagedStays& stage, const PoolArrays& P, uint32_t pool_base,
+                                         double* open_tin, StagedStays& stage, const PoolArrays& P,
                                          uint32_t pool_cap, uint32_t* count, Counters* ctr, int day, int day_type)
 {
     const uint64_t v = view[a];
@@ -91,12 +91,13 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
             else  // the staging area is full (cannot happen with <= 10 stays per person and day): straight to the pool
             {
                 atomicAdd(&stage.spilled, 1u);
-                const uint32_t slot = (uint32_t) atomicAdd(&ctr->n_sched, 1ull);
+                atomicAdd(&ctr->n_sched, 1ull);
+                const unsigned long long slot = atomicAdd(&ctr->n_fresh, 1ull);
                 if (slot < pool_cap)
                 {
-                    P.person[pool_base + slot] = a; P.key[pool_base + slot] = cur_key;
-                    P.tin[pool_base + slot] = cur_tin; P.tout[pool_base + slot] = t_leave;
-                    P.rank[pool_base + slot] = atomicAdd(&count[cur_key], 1u);
+                    P.person[slot] = a; P.key[slot] = cur_key;
+                    P.tin[slot] = cur_tin; P.tout[slot] = t_leave;
+                    P.rank[slot] = atomicAdd(&count[cur_key], 1u);
                 }
                 else
                     atomicOr(&ctr->overflow, 32u);
@@ -204,22 +205,27 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
 
 __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uint32_t n_agents, const uint32_t* order,
                                                      const uint64_t* view, uint32_t* open_key, double* open_tin,
-                                                     PoolArrays P, uint32_t pool_base, uint32_t pool_cap, uint32_t* count,
+                                                     PoolArrays P, uint32_t pool_cap, uint32_t* count,
                                                      Counters* ctr, int day, int day_type)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     StagedStays& stage = *reinterpret_cast<StagedStays*>(smem);
-    __shared__ uint32_t s_base;
+    __shared__ unsigned long long s_base;
     if (threadIdx.x == 0) { stage.n = 0; stage.spilled = 0; }
     __syncthreads();
     // persons are visited grouped by social role: the threads of a warp then walk the same day pattern (the phase that
     // also selects it is Susceptible for most) instead of 32 different ones
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < n_agents)
-        walk_day(S, order[slot], view, open_key, open_tin, stage, P, pool_base, pool_cap, count, ctr, day, day_type);
+        walk_day(S, order[slot], view, open_key, open_tin, stage, P, pool_cap, count, ctr, day, day_type);
     __syncthreads();
     const uint32_t n = min(stage.n, (uint32_t) STAGE_CAP);
-    if (threadIdx.x == 0) s_base = n ? (uint32_t) atomicAdd(&ctr->n_sched, (unsigned long long) n) : 0u;
+    // the block's slots in the fresh pool, whose cursor lives on the device
+    if (threadIdx.x == 0)
+    {
+        s_base = n ? atomicAdd(&ctr->n_fresh, (unsigned long long) n) : 0ull;
+        if (n) atomicAdd(&ctr->n_sched, (unsigned long long) n);
+    }
     __syncthreads();
     // four staged stays per thread and round: their tickets are taken together (four atomics in flight)
     for (uint32_t j0 = threadIdx.x; j0 < n; j0 += blockDim.x * 4)
@@ -238,13 +244,13 @@ __global__ void __launch_bounds__(TPB) k_advance_day(const ScheduleTables S, uin
         {
             const uint32_t j = j0 + q * blockDim.x;
             if (j >= n) continue;
-            const uint32_t at = s_base + j;
+            const unsigned long long at = s_base + j;
             if (at >= pool_cap) { atomicOr(&ctr->overflow, 32u); continue; }
-            P.person[pool_base + at] = stage.person[j];
-            P.key[pool_base + at] = key[q];
-            P.tin[pool_base + at] = stage.tin[j];
-            P.tout[pool_base + at] = stage.tout[j];
-            P.rank[pool_base + at] = ticket[q];
+            P.person[at] = stage.person[j];
+            P.key[at] = key[q];
+            P.tin[at] = stage.tin[j];
+            P.tout[at] = stage.tout[j];
+            P.rank[at] = ticket[q];
         }
     }
 }
@@ -390,6 +396,23 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
         CU(h, cudaStreamSynchronize(s));
     }
     CU(h, cudaStreamSynchronize(s));
+    {
+        // room the fresh pool needs for one day: a stay can only end at an activity whose locator may name another place
+        // (everything but the Current locator), plus one for a person who dies; per person the longest such pattern
+        size_t per_role[16] = {};
+        for (int r = 1; r < 16; ++r)
+            for (int ph = 0; ph < 8; ++ph)
+                for (int d = 0; d < 4; ++d)
+                {
+                    const int idx = (ph * 16 + r) * 4 + d;
+                    size_t moves = 1;
+                    for (int i = 0; i < pattern_count[idx]; ++i) moves += activities[pattern_start[idx] + i].locator != 2 ? 1 : 0;
+                    per_role[r] = std::max(per_role[r], moves);
+                }
+        size_t room = 0;
+        for (uint8_t r : h->h_role) room += r < 16 ? per_role[r] : 1;
+        h->sched_room = room;
+    }
     h->sched_max_acts = max_acts; h->sched_n_types = n_types; h->sched_n_cand = n_candidates;
     h->sched_accommodation = accommodation_type; h->sched_seed = seed;
     h->have_schedule = true;
@@ -439,10 +462,12 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
     if (h->person_base != 0 || h->location_base != 0)
         return fail(h, HEROS_ERR_UNSUPPORTED, "the device-side schedule runs on an unsharded engine");
     cudaSetDevice(h->cfg.device);
-    const size_t room = (size_t) h->n_agents * (size_t) std::max(h->sched_max_acts, 1);
-    if ((uint64_t) h->n_pool + room + h->n_agents >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
-    rc = ensure_pool(h, h->pool_cur, (size_t) h->n_pool + room, true);
+    // every activity of a day can end a stay: the fresh pool gets room for all of them (its fill count lives on the device)
+    const size_t room = h->sched_room;
+    if ((uint64_t) h->carry_ub + h->fresh_ub + room + h->n_agents >= 0xFFFFFFF0ull) return fail(h, HEROS_ERR_CAPACITY, "more than 2^32 stays in one window");
+    rc = ensure_fresh(h, h->fresh_ub + room);
     if (rc != HEROS_OK) return rc;
+    if ((rc = join_submissions(h)) != HEROS_OK) return rc;  // stays submitted by the host come first
     ScheduleTables S{};
     S.acts = h->s_acts.p; S.pat_start = h->s_pat_start.p; S.pat_count = h->s_pat_count.p;
     S.choice_start = h->s_choice_start.p; S.choice_type = h->s_choice_type.p; S.choice_cum = h->s_choice_cum.p;
@@ -459,15 +484,15 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
         CU(h, cudaFuncSetAttribute(k_advance_day, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(StagedStays)));
         configured[h->cfg.device] = true;
     }
-    k_advance_day<<<blocks_for(h->n_agents), TPB, sizeof(StagedStays), h->stream>>>(S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p,
-                                                                  h->d_open_tin.p, pool_arrays(h, h->pool_cur), h->n_pool,
-                                                                  (uint32_t) room, h->bk_count.p, h->d_ctr.p, day,
-                                                                  DAY_TYPE[day % 7]);
+    k_advance_day<<<blocks_for(h->n_agents), TPB, sizeof(StagedStays), h->stream>>>(
+        S, h->n_agents, h->s_order.p, h->d_view.p, h->d_open_key.p, h->d_open_tin.p, fresh_arrays(h),
+        (uint32_t) std::min<size_t>(h->fresh_person.n, 0xFFFFFFFFu), h->bk_count.p, h->d_ctr.p, day, DAY_TYPE[day % 7]);
     CU(h, cudaGetLastError());
-    rc = sync_counters(h);
-    if (rc != HEROS_OK) return rc;
-    if (h->h_ctr->overflow) return fail(h, HEROS_ERR_CAPACITY, "pool overflow in heros_advance_schedule");
-    h->n_pool += (uint32_t) h->h_ctr->n_sched;
+    // nothing is read back: the window kernels take the fill count from the device.  An average day ends about four
+    // stays per person; the bound used for the grids of the next window is the room reserved above.
+    h->fresh_ub += room;
+    h->ctr_current = false;
+    h->launches_total += 1;
     return HEROS_OK;
 }
 

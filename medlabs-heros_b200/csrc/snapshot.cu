@@ -13,7 +13,7 @@ struct SnapshotHeader
     uint64_t magic;
     uint32_t version, model;
     uint64_t seed;
-    uint32_t n_agents, n_keys, n_pool, n_carried;
+    uint32_t n_agents, n_keys, n_fresh, n_carry;
     uint32_t n_policy, n_series, n_closure, closure_active;
     uint32_t invalid_reported, pad;
     uint64_t n_inf, n_tr;
@@ -26,14 +26,16 @@ struct Piece { void* dev; void* host; size_t bytes; };  // one of dev / host is 
 // the dynamic state of an idle engine, in the order it is laid out behind the header
 std::vector<Piece> pieces(heros_handle h, const SnapshotHeader& s)
 {
-    const size_t N = s.n_agents, K = s.n_keys, P = s.n_pool;
-    const int c = h->pool_cur;
+    const size_t N = s.n_agents, K = s.n_keys, F = s.n_fresh, C = s.n_carry;
+    const int c = h->carry_cur;
     return {
         {h->d_view.p, nullptr, N * 8}, {h->d_next_time.p, nullptr, N * 8}, {h->d_ill_end.p, nullptr, N * 8},
         {h->d_open_key.p, nullptr, N * 4}, {h->d_open_tin.p, nullptr, N * 8},
         {h->d_last_calc.p, nullptr, K * 8}, {h->bk_count.p, nullptr, (K + 1) * 4},
-        {h->pool_person[c].p, nullptr, P * 4}, {h->pool_key[c].p, nullptr, P * 4}, {h->pool_rank[c].p, nullptr, P * 4},
-        {h->pool_tin[c].p, nullptr, P * 8}, {h->pool_tout[c].p, nullptr, P * 8},
+        {h->fresh_person.p, nullptr, F * 4}, {h->fresh_key.p, nullptr, F * 4}, {h->fresh_rank.p, nullptr, F * 4},
+        {h->fresh_tin.p, nullptr, F * 8}, {h->fresh_tout.p, nullptr, F * 8},
+        {h->carry_person[c].p, nullptr, C * 4}, {h->carry_key[c].p, nullptr, C * 4}, {h->carry_rank[c].p, nullptr, C * 4},
+        {h->carry_tin[c].p, nullptr, C * 8}, {h->carry_tout[c].p, nullptr, C * 8},
         {h->inf_person.p, nullptr, (size_t) s.n_inf * 4}, {h->inf_gkey.p, nullptr, (size_t) s.n_inf * 8},
         {h->inf_t.p, nullptr, (size_t) s.n_inf * 8}, {h->inf_p.p, nullptr, (size_t) s.n_inf * 8},
         {h->tr_person.p, nullptr, (size_t) s.n_tr * 4}, {h->tr_phase.p, nullptr, (size_t) s.n_tr},
@@ -57,8 +59,8 @@ int32_t describe(heros_handle h, SnapshotHeader& s)
     cudaSetDevice(h->cfg.device);
     if ((rc = sync_counters(h)) != HEROS_OK) return rc;
     memset(&s, 0, sizeof s);
-    s.magic = SNAPSHOT_MAGIC; s.version = 1; s.model = (uint32_t) h->cfg.model; s.seed = h->cfg.seed;
-    s.n_agents = h->n_agents; s.n_keys = h->n_keys; s.n_pool = h->n_pool; s.n_carried = h->n_carried;
+    s.magic = SNAPSHOT_MAGIC; s.version = 2; s.model = (uint32_t) h->cfg.model; s.seed = h->cfg.seed;
+    s.n_agents = h->n_agents; s.n_keys = h->n_keys; s.n_fresh = (uint32_t) h->h_ctr->n_fresh; s.n_carry = (uint32_t) h->h_ctr->n_carry;
     s.n_policy = (uint32_t) h->policy.size(); s.n_series = (uint32_t) h->series_t.size();
     s.n_closure = (uint32_t) h->h_closure.size(); s.closure_active = h->closure_active ? 1u : 0u;
     s.invalid_reported = h->invalid_reported;
@@ -125,7 +127,7 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
     if ((size_t) bytes < sizeof(SnapshotHeader)) return fail(h, HEROS_ERR_INVALID, "not a snapshot");
     SnapshotHeader s;
     memcpy(&s, blob, sizeof s);
-    if (s.magic != SNAPSHOT_MAGIC || s.version != 1) return fail(h, HEROS_ERR_INVALID, "not a snapshot of this engine version");
+    if (s.magic != SNAPSHOT_MAGIC || s.version != 2) return fail(h, HEROS_ERR_INVALID, "not a snapshot of this engine version");
     // the static inputs (heros_set_*) are the host's to repeat; they must describe the same model
     if (s.n_agents != h->n_agents || s.n_keys != h->n_keys || s.model != (uint32_t) h->cfg.model || s.seed != h->cfg.seed)
         return fail(h, HEROS_ERR_INVALID, "the snapshot was taken with other persons, locations, model or seed");
@@ -139,7 +141,14 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
         for (const Piece& p : pieces(h, s)) total += padded(p.bytes);
         if ((size_t) bytes < total) return fail(h, HEROS_ERR_INVALID, "truncated snapshot");
     }
-    if ((rc = ensure_pool(h, h->pool_cur, std::max<size_t>(s.n_pool, 1), false)) != HEROS_OK) return rc;
+    if ((rc = sync_counters(h)) != HEROS_OK) return rc;  // nothing of the engine is in flight while its state is replaced
+    if ((rc = ensure_fresh(h, std::max<size_t>(s.n_fresh, 1))) != HEROS_OK) return rc;
+    {
+        const int c = h->carry_cur;
+        const size_t n = std::max<size_t>(s.n_carry, 1);
+        CU(h, h->carry_person[c].ensure(n)); CU(h, h->carry_key[c].ensure(n)); CU(h, h->carry_rank[c].ensure(n));
+        CU(h, h->carry_tin[c].ensure(n)); CU(h, h->carry_tout[c].ensure(n));
+    }
     h->policy.assign(s.n_policy, PolicyChange{});
     h->series_t.assign(s.n_series, 0.0);
     h->series_counts.assign((size_t) s.n_series * 8, 0);
@@ -174,7 +183,8 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
     }
     CU(h, cudaStreamSynchronize(h->stream));
     h->closure_active = s.closure_active != 0;
-    h->n_pool = s.n_pool; h->n_carried = s.n_carried; h->t_now = s.t_now; h->invalid_reported = s.invalid_reported;
+    h->fresh_ub = s.n_fresh; h->carry_ub = s.n_carry; h->t_now = s.t_now; h->invalid_reported = s.invalid_reported;
+    h->series_fetched = s.n_series;
     h->n_guest = 0;
     h->o_inf_n = h->o_tr_n = ~0ull;  // the sorted output caches are stale
     h->ctr_current = false;

@@ -9,23 +9,29 @@
 // calculated evaluation is >= the threshold, over the occupants S(t-) = { stays : t_in < t <= t_out }.
 //
 // Input: the window's stays sorted by sub-location key (one contiguous segment per occupied sub-location).
-//   k_transmit_thread : one THREAD per segment of <= 32 stays streams its records once.  Where nobody can be infected
-//                       (no ill or no susceptible occupant -- the vast majority) only lastCalculation has to advance,
-//                       which needs just the two latest event times; the other segments are queued for the sub-warp
-//                       kernels, segments of > 32 stays for the group kernels.
+//   k_transmit_stream : a WARP per 32 consecutive sub-location keys streams their (contiguous) records once with
+//                       coalesced 128-bit loads and reduces, per sub-location, who is there and the two latest event
+//                       times (match / redux over the lanes that hold records of the same sub-location).  Where nobody
+//                       can be infected (no ill or no susceptible occupant -- the vast majority) only lastCalculation
+//                       has to advance; the other sub-locations of <= 32 stays are queued for the sub-warp kernels.
 //   k_transmit_sub    : 8 or 32 lanes per queued segment (<= 8 / 9..32 stays): the lanes walk the chain of calculated
 //                       evaluations together (REDUX), then every lane computes ONE evaluation of the chain -- the long
 //                       dependent fp64 chains (sqrt, exp) of up to 32 evaluations run side by side -- then lane = stay
 //                       for the draws
-//   k_group_filter    : one warp per queued segment of 33..512 stays: the same early-out, so that the group kernels of
-//                       the two small classes only get the segments with work for a whole thread block
-//   k_transmit_group  : one block per segment of > 32 stays, five classes by its number of events (queued by the
-//                       prefix-sum kernel): events bucketed by time in shared memory, the chain of calculated
-//                       evaluations by successor search + pointer doubling, exposure sums in 128-bit fixed point
-//                       (order-independent; pair by pair with integer atomics when many occupants are ill), then one
-//                       draw item per susceptible stay = a run of the segment's table of evaluations with p > 0
+// The hot path, sub-locations of > 32 stays (supermarkets, parks, lecture halls ...), in three steps so that the
+// latency of the largest sub-location is not the latency of the stage:
+//   k_hot_filter      : one warp per hot sub-location: the same early-out
+//   k_hot_chain       : one thread block per remaining sub-location orders its movement events in shared memory
+//                       (counting sort into time buckets), finds the successor of every event (the earliest later
+//                       event not closer than the threshold: three buckets to look at), materialises the chain of
+//                       calculated evaluations by pointer doubling and leaves one row per evaluation (time, duration,
+//                       head count) plus one work item per 32 evaluations
+//   k_hot_eval        : one thread block per work item, spread over the whole GPU: the records of the sub-location are
+//                       streamed through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, two tiles in
+//                       flight); lane = evaluation; every ill stay overlapping the item is broadcast and each lane adds
+//                       its term to a 128-bit fixed-point sum in registers (order-independent, no atomics); then every
+//                       susceptible stay is broadcast for the Philox draws
 //   k_transmit_total  : one block per location of the total-location branch (TArea:198-246 / TDist:189-246)
-//   k_draw            : expands the draw items into Philox draws, spread evenly over the whole GPU
 // Output: candidate infections (person, key, time, p); engine.cu keeps the earliest per person.
 #include "engine.cuh"
 
@@ -34,7 +40,6 @@ namespace heros {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PAIR_MIN_ILL = 48;    // more ill stays than this in a sub-location: exposure sums pair by pair
 constexpr int THREAD_SLOW_MAX = 8;  // largest segment handled by 8 lanes (four per warp) in k_transmit_sub
 
 __device__ __forceinline__ double pos_inf() { return bits_f64(0x7ff0000000000000ull); }
@@ -59,8 +64,16 @@ __device__ __forceinline__ void policy_at(const WindowCtx& c, double t, double& 
     }
 }
 
+// A successful draw.  Only the earliest one of a person counts (engine.cu: k_resolve), so a candidate that is later
+// than one already seen for the same (own) person is dropped here; equal times are kept (the lowest sub-location wins).
 __device__ __forceinline__ void push_candidate(const WindowCtx& c, uint32_t person, uint32_t key, double t, double p)
 {
+    const uint32_t local = person - c.person_base;
+    if (local < c.n_agents)
+    {
+        const unsigned long long tb = (unsigned long long) f64_bits(t);  // times are >= 0: their bit patterns order as integers
+        if (atomicMin(&c.best_t[local], tb) < tb) return;
+    }
     const unsigned long long slot = atomicAdd(&c.ctr->n_cand, 1ull);
     if (slot < c.cand_cap)
     {
@@ -161,58 +174,140 @@ __device__ __forceinline__ bool stay_before(uint32_t pa, double ta, uint32_t pb,
 
 }  // namespace
 
-template <int MODEL>
-__global__ void __launch_bounds__(256) k_transmit_thread(const WindowCtx c)
+
+// ------------------------------------------------------------------------------------------------------------------
+// one warp per 32 consecutive sub-location keys
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// max of the 64-bit patterns v over the lanes of `peers` (all of which call with the same mask)
+__device__ __forceinline__ unsigned long long peers_max64(unsigned peers, unsigned long long v)
 {
+    const uint32_t hi = (uint32_t) (v >> 32), lo = (uint32_t) v;
+    const uint32_t mhi = __reduce_max_sync(peers, hi);
+    const uint32_t mlo = __reduce_max_sync(peers, hi == mhi ? lo : 0u);
+    return ((unsigned long long) mhi << 32) | mlo;
+}
+
+}  // namespace
+
+// The records of 32 consecutive keys are contiguous in bucket order, so the warp reads them with coalesced 256-bit
+// loads (a record is one 32-byte sector; LDG.E.256: 1 KB per warp and load, all of it used).  The lane that holds a
+// record finds the key it belongs to by a binary search over the 32 segment ends (shuffles); the lanes holding records
+// of the same key form a group (match.any) and reduce who is there (redux.or) and the two latest distinct event times
+// (redux.max over the time bit patterns: times are non-negative doubles, so their bits order as integers; 0 = none).
+// Segments of > 32 stays (the hot path) and of total-branch locations are skipped without being read.
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
+{
+    __shared__ unsigned long long s_m1[8][32], s_m2[8][32];
+    __shared__ uint32_t s_fl[8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
+    const uint32_t n_groups = (c.n_keys + 31u) >> 5;
     unsigned occupied = 0;
 
-    for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
+    for (uint32_t g = warp; g < n_groups; g += n_warps)
     {
-        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
-        const uint32_t n = b - a;
-        if (n == 0) continue;
-        ++occupied;
-        if (n > 32) continue;  // queued for the group kernels by the prefix-sum kernel
-        if (c.key_total && c.key_total[key]) continue;  // evaluated per location by k_transmit_total
-        const StayRec* rec = c.rec + a;
-        // who is here, and the two latest events
-        bool any_ill = false, any_sus = false;
-        Top2 top;
-        top.init();
-#pragma unroll 4
-        for (uint32_t j = 0; j < n; ++j)
+        const uint32_t key = (g << 5) + (uint32_t) lane;
+        const bool in_table = key < c.n_keys;
+        const uint32_t a = c.seg_start[in_table ? key : c.n_keys];
+        const uint32_t e = c.seg_start[in_table ? key + 1 : c.n_keys];  // segment ends: non-decreasing over the lanes
+        const uint32_t n = e - a;
+        const bool skip = n > 32 || (n > 0 && c.key_total && c.key_total[key]);
+        occupied += n > 0 ? 1u : 0u;
+        s_m1[wib][lane] = 0ull; s_m2[wib][lane] = 0ull; s_fl[wib][lane] = 0u;
+        __syncwarp();
+        const unsigned skip_mask = __ballot_sync(FULL, skip);
+        // runs of lanes between skipped segments: their records are one contiguous range
+        int first = 0;
+        while (first < 32)
         {
-            const StayRec r = rec[j];
-            const uint32_t tph = view_tphase(r.view);
-            any_ill |= phase_is_ill(tph);
-            any_sus |= phase_is_susceptible(tph);
-            if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
-            if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
-        }
-        if (!(top.m1 > neg_inf())) continue;  // no movement in this window
-        const bool need_eval = any_ill && any_sus;
-        if (!need_eval && !exact)
-        {
-            double L;
-            if (advance_only(top, c.last_calc[key], thr, L))
+            const unsigned after = first < 32 ? (skip_mask & ~((1u << first) - 1u)) : 0u;
+            const int last = after ? __ffs(after) - 1 : 32;  // lanes [first, last) form the run
+            if (last > first)
             {
-                c.last_calc[key] = L;
-                continue;
+                const uint32_t lo = __shfl_sync(FULL, a, first), hi = __shfl_sync(FULL, e, last - 1);
+                for (uint32_t b0 = lo; b0 < hi; b0 += 32)
+                {
+                    const uint32_t i = b0 + (uint32_t) lane;
+                    const bool valid = i < hi;
+                    unsigned long long x = 0ull, y = 0ull;
+                    uint32_t fl = 0u;
+                    if (valid)
+                    {
+                        const StayRec r = ld_rec(c.rec + i);
+                        const double tin = r.tin, tout = r.tout;
+                        const uint32_t tph = view_tphase(r.view);
+                        fl = (phase_is_ill(tph) ? 1u : 0u) | (phase_is_susceptible(tph) ? 2u : 0u);
+                        if (tout >= c.T0 && tout < c.T1) x = f64_bits(tout);
+                        if (both && tin >= c.T0 && tin < c.T1) y = f64_bits(tin);  // t_in < t_out: y < x whenever both are set
+                        if (y > x) { const unsigned long long t = x; x = y; y = t; }
+                    }
+                    // owner = number of segment ends <= i (a binary search over the lanes)
+                    int owner = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
+                    {
+                        const uint32_t v = __shfl_sync(FULL, e, owner + step - 1);
+                        if (v <= i) owner += step;
+                    }
+                    const unsigned peers = __match_any_sync(FULL, valid ? owner : 64 + lane);
+                    const unsigned long long m1 = peers_max64(peers, x);
+                    const unsigned long long m2 = peers_max64(peers, x < m1 ? x : (y < m1 ? y : 0ull));
+                    const uint32_t f = __reduce_or_sync(peers, fl);
+                    if (valid && lane == __ffs(peers) - 1)
+                    {
+                        // merge into the two latest distinct times of the key (a segment may span two batches)
+                        unsigned long long a1 = s_m1[wib][owner], a2 = s_m2[wib][owner];
+                        if (m1 > a1) { a2 = a1 > m2 ? a1 : m2; a1 = m1; }
+                        else if (m1 == a1) { a2 = a2 > m2 ? a2 : m2; }
+                        else { a2 = a2 > m1 ? a2 : m1; }
+                        s_m1[wib][owner] = a1; s_m2[wib][owner] = a2; s_fl[wib][owner] |= f;
+                    }
+                    __syncwarp();
+                }
+            }
+            first = last + 1;
+        }
+        __syncwarp();
+        if (n > 0 && !skip)
+        {
+            const unsigned long long b1 = s_m1[wib][lane], b2 = s_m2[wib][lane];
+            if (b1 != 0ull)  // a movement in this window
+            {
+                const bool need_eval = s_fl[wib][lane] == 3u;
+                bool done = false;
+                if (!need_eval && !exact)
+                {
+                    Top2 top;
+                    top.m1 = bits_f64(b1);
+                    top.m2 = b2 ? bits_f64(b2) : neg_inf();
+                    double L;
+                    if (advance_only(top, c.last_calc[key], thr, L)) { c.last_calc[key] = L; done = true; }
+                }
+                if (!done)
+                {
+                    // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
+                    const int which = n > THREAD_SLOW_MAX ? 1 : 0;
+                    const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
+                    if (slot < c.sub_cap[which]) c.sub_seg[which][slot] = key;
+                    else atomicOr(&c.ctr->overflow, 2u);
+                }
             }
         }
-        // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
-        const int which = n > THREAD_SLOW_MAX ? 1 : 0;
-        const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
-        if (slot < c.sub_cap[which]) c.sub_seg[which][slot] = key;
-        else atomicOr(&c.ctr->overflow, 2u);
+        __syncwarp();
     }
     occupied = __reduce_add_sync(FULL, occupied);
-    if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
+    if (lane == 0 && occupied)
+    {
+        atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
+        atomicAdd(&c.ctr->seg_total, (unsigned long long) occupied);
+    }
 }
-
 // ------------------------------------------------------------------------------------------------------------------
 // S = 8 or 32 lanes per queued sub-location (<= 8 / 9..32 stays); lane i of the group holds stay i (canonical order)
 // ------------------------------------------------------------------------------------------------------------------
@@ -371,30 +466,8 @@ __global__ void __launch_bounds__(256, 4) k_transmit_sub(const WindowCtx c)
     flush_stats(c, st, lane);
 }
 
-// The Philox draws of the group kernels' items: pair q belongs to the last item whose first pair number is <= q (the
-// items were reserved in ascending pair order) and is the (q - first pair)-th table entry from the item's first one.
-__global__ void __launch_bounds__(256) k_draw(const WindowCtx c)
-{
-    const unsigned long long packed = c.ctr->n_draw;
-    const unsigned long long n_items = min(packed >> DRAW_ITEM_SHIFT, c.item_cap), n_pairs = packed & DRAW_PAIR_MASK;
-    Local st;
-    if (n_items)
-        for (unsigned long long q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += (unsigned long long) gridDim.x * blockDim.x)
-        {
-            unsigned long long lo = 0, hi = n_items - 1;  // item_pair[0] == 0 <= q
-            while (lo < hi)
-            {
-                const unsigned long long mid = (lo + hi + 1) >> 1;
-                if (c.item_pair[mid] <= q) lo = mid; else hi = mid - 1;
-            }
-            const unsigned long long e = c.item_tab[lo] + (q - c.item_pair[lo]);
-            draw_and_push(c, st, c.item_person[lo], c.item_key[lo], c.tab_t[e], c.tab_p[e]);
-        }
-    flush_stats(c, st, threadIdx.x & 31);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// one thread group (a warp or a block) per sub-location of > 32 stays
+// block-wide building blocks of the hot path
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -507,59 +580,46 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
     gsync<G>();
 }
 
-// per class: group size, groups per block, capacity in events and in kept probabilities
-template <int CLS> struct GroupCfg;
-template <> struct GroupCfg<0> { static constexpr int G = 128, PER_BLOCK = 1, S_CAP = 256, P_CAP = 256, NB_CAP = 512; using idx_t = uint16_t; };
-template <> struct GroupCfg<1> { static constexpr int G = 256, PER_BLOCK = 1, S_CAP = 1024, P_CAP = 1024, NB_CAP = 2048; using idx_t = uint16_t; };
-template <> struct GroupCfg<2> { static constexpr int G = 512, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
-template <> struct GroupCfg<3> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = BLOCK_S_CAP3, P_CAP = BLOCK_P_CAP, NB_CAP = 2048; using idx_t = uint16_t; };
-template <> struct GroupCfg<4> { static constexpr int G = 1024, PER_BLOCK = 1, S_CAP = 0, P_CAP = 0, NB_CAP = 65536; using idx_t = uint32_t; };
-
-// bytes of scratch of one group: 17 per event + 24 per kept evaluation (probability + fixed-point exposure sum) + 12
-// per bucket (budgeted 16; + slack)
-template <int CLS> __host__ __device__ constexpr size_t group_smem_bytes()
-{
-    return (size_t) GroupCfg<CLS>::S_CAP * 17 + (size_t) GroupCfg<CLS>::P_CAP * 24 + (size_t) GroupCfg<CLS>::NB_CAP * 16 + 256;
-}
-
 }  // namespace
 
-constexpr int FILTERED_CLASSES = 2;
+// ------------------------------------------------------------------------------------------------------------------
+// the hot path: sub-locations of > 32 stays
+// ------------------------------------------------------------------------------------------------------------------
 
-// One warp per queued sub-location of classes 0 and 1 (33 .. 512 stays): who is here and the two latest events.  Where nobody can
-// be infected only lastCalculation has to advance (usually most of them); the others are passed on to the group kernel
-// of their class, which then runs whole thread blocks only where there is work for them.
+// One warp per hot sub-location: who is here and the two latest events.  Where nobody can be infected only
+// lastCalculation has to advance (usually most of them); the others are passed on to the chain kernel of their class.
 template <int MODEL>
-__global__ void __launch_bounds__(256) k_group_filter(const WindowCtx c)
+__global__ void __launch_bounds__(256) k_hot_filter(const WindowCtx c)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    uint32_t first[N_CLS + 1];
+    uint32_t first[N_HOT + 1];
     first[0] = 0;
-    for (int k = 0; k < N_CLS; ++k) first[k + 1] = first[k] + (uint32_t) min((unsigned long long) c.blk_cap, c.ctr->n_blk[k]);
-    for (uint32_t i = warp; i < first[FILTERED_CLASSES]; i += n_warps)
+    for (int k = 0; k < N_HOT; ++k) first[k + 1] = first[k] + (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_hot[k]);
+    if (warp == 0 && lane == 0) atomicAdd(&c.ctr->hot_total, (unsigned long long) first[N_HOT]);
+    for (uint32_t i = warp; i < first[N_HOT]; i += n_warps)
     {
         int cls = 0;
         while (i >= first[cls + 1]) ++cls;
         const uint32_t w = i - first[cls];
-        const uint32_t key = c.blk_seg[cls][w];
+        const uint32_t key = c.hot_seg[cls][w];
         if (key == KEY_NONE) continue;
         const uint32_t a = c.seg_start[key], n = c.seg_start[key + 1] - a;
-        const StayRec* rec = c.rec + a;
         int ill = 0, sus = 0;
         Top2 top;
         top.init();
         for (uint32_t v = lane; v < n; v += 32)
         {
-            const StayRec r = rec[v];
+            const StayRec r = ld_rec(c.rec + a + v);
+            const double tin = r.tin, tout = r.tout;
             const uint32_t tph = view_tphase(r.view);
             ill |= phase_is_ill(tph);
             sus |= phase_is_susceptible(tph);
-            if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
-            if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
+            if (tout >= c.T0 && tout < c.T1) top.add(tout);
+            if (both && tin >= c.T0 && tin < c.T1) top.add(tin);
         }
         for (int o = 16; o > 0; o >>= 1)
         {
@@ -579,259 +639,175 @@ __global__ void __launch_bounds__(256) k_group_filter(const WindowCtx c)
         }
         if (lane == 0)
         {
-            const unsigned long long slot = atomicAdd(&c.ctr->n_run[cls], 1ull);  // <= n_blk[cls] <= blk_cap
-            c.run_seg[cls][slot] = key;
+            const unsigned long long slot = atomicAdd(&c.ctr->n_run[cls], 1ull);  // <= n_hot[cls] <= hot_cap
+            // bit 31 of the entry index is free (lists hold < 2^31 entries): the run list keeps the index into hot_seg
+            // (the huge class needs it for its scratch offset) -- the key is looked up again by the chain kernel
+            c.hot_run[cls][slot] = w | (need_eval ? 0x80000000u : 0u);
         }
     }
 }
 
-// The chain of calculated evaluations needs, from an evaluation at time e, the earliest later candidate event t with
-// !(t - e < threshold).  Events are put in time order by a counting sort into time buckets (no wider than the threshold
-// where affordable) followed by a rank sort inside every bucket; the successor of an event is then a binary search over
-// the <= 3 buckets around e + threshold; the chain start, next[start], next[next[start]] ... is materialised in
-// O(log n) rounds of pointer doubling.  Classes 0-2 keep everything in shared memory, class 3 (anything larger) in global scratch.
-template <int MODEL, int CLS>
-__global__ void __launch_bounds__(GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK, 1024 / (GroupCfg<CLS>::G * GroupCfg<CLS>::PER_BLOCK))
-k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register file, not the work, limits how many groups run side by side
+namespace {
+
+template <int CLS> struct HotCfg;
+template <> struct HotCfg<0> { static constexpr int T = 256, M_CAP = HOT_M_CAP0, NB_CAP = HOT_NB_CAP0; using idx_t = uint16_t; };
+template <> struct HotCfg<1> { static constexpr int T = 512, M_CAP = HOT_M_CAP1, NB_CAP = HOT_NB_CAP; using idx_t = uint16_t; };
+template <> struct HotCfg<2> { static constexpr int T = 512, M_CAP = 0, NB_CAP = HOT_NB_CAP; using idx_t = uint32_t; };
+
+template <int CLS> __host__ __device__ constexpr size_t hot_smem_bytes()
 {
-    using Cfg = GroupCfg<CLS>;
+    using Cfg = HotCfg<CLS>;
+    return CLS == HOT_HUGE ? 0
+                           : (size_t) Cfg::M_CAP * 8 + 5 * 4 * (size_t) (Cfg::NB_CAP + 2) +
+                                 3 * sizeof(typename Cfg::idx_t) * (size_t) (Cfg::M_CAP + 1) + (size_t) Cfg::M_CAP + 64;
+}
+
+}  // namespace
+
+// The chain of calculated evaluations of one hot sub-location.  From an evaluation at time e the next one is the
+// earliest later candidate event t with !(t - e < threshold) (candidates: exits, and enters when the trigger is
+// ENTER_AND_EXIT).  The movement events of the window are put into NB time buckets (counting sort; the order inside a
+// bucket is never needed).  With x = e + threshold falling into bucket b, every event of a bucket >= b + 2 qualifies and
+// no event of a bucket <= b - 2 does (a bucket is many orders of magnitude wider than the rounding of t - e), so the
+// successor is the earliest qualifying event of the buckets b - 1 .. b + 1, tested with the reference's own
+// comparison, or else the earliest candidate of the next bucket that holds one.  The chain start, succ[start], ... is
+// materialised in O(log R) rounds of pointer doubling.  Head counts of the distance model (TDist:137: the size of the
+// set S(t-)) = stays carried in + enters - exits before t: a bucket prefix plus the earlier events of t's own bucket.
+template <int MODEL, int CLS>
+__global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
+{
+    using Cfg = HotCfg<CLS>;
     using idx_t = typename Cfg::idx_t;
-    constexpr int G = Cfg::G;
+    constexpr int G = Cfg::T;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_w[33];
-    __shared__ double s_red[2 * 32];
-    __shared__ unsigned long long s_tab;
-    const int tid = grank<G>();
-    const int group_in_block = G == 32 ? (int) (threadIdx.x >> 5) : 0;
-    // classes 0 and 1 (thousands of sub-locations, most of which only need lastCalculation advanced) come through
-    // k_group_filter; the few large ones of classes 2-4 start at once and sort that out themselves (step 0)
-    constexpr bool FILTERED = CLS < FILTERED_CLASSES;
-    const uint32_t n_list = (uint32_t) min((unsigned long long) c.blk_cap, FILTERED ? c.ctr->n_run[CLS] : c.ctr->n_blk[CLS]);
+    __shared__ unsigned long long s_base[2];
+    const int tid = threadIdx.x;
+    const uint32_t n_list = (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_run[CLS]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
-    const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    const bool dbg = (c.flags & HEROS_FLAG_PHASE_CLOCKS) != 0;
     Local st;
-    long long clk = 0;
-#define PHASE_CLOCK(k) do { if (dbg && tid == 0) { const long long t_ = clock64(); atomicMax(&c.ctr->dbg_clk[CLS][k], (unsigned long long) (t_ - clk)); clk = t_; } } while (0)
 
-    for (uint32_t w = blockIdx.x * Cfg::PER_BLOCK + group_in_block; w < n_list; w += gridDim.x * Cfg::PER_BLOCK)
+    for (uint32_t wi = blockIdx.x; wi < n_list; wi += gridDim.x)
     {
-        const uint32_t key = FILTERED ? c.run_seg[CLS][w] : c.blk_seg[CLS][w];
-        if (key == KEY_NONE) continue;
-        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
-        const int n = (int) (b - a);
+        const uint32_t entry = c.hot_run[CLS][wi];
+        const bool need_eval = (entry & 0x80000000u) != 0;
+        const uint32_t w = entry & 0x7fffffffu;
+        const uint32_t key = c.hot_seg[CLS][w];
+        const uint32_t a = c.seg_start[key];
+        const int n = (int) (c.seg_start[key + 1] - a);
         const StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
-
-        if (dbg) clk = clock64();
-        // 0. who is here and the two latest events (k_group_filter has already dealt with the sub-locations that only
-        //    need lastCalculation advanced)
-        bool need_eval;
-        {
-            int ill = 0, sus = 0;
-            Top2 top;
-            top.init();
-            for (int v = tid; v < n; v += G)
-            {
-                const StayRec r = rec[v];
-                const uint32_t tph = view_tphase(r.view);
-                ill |= phase_is_ill(tph);
-                sus |= phase_is_susceptible(tph);
-                if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
-                if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
-            }
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
-                top.merge(o1, o2);
-            }
-            int flags = (__any_sync(FULL, ill) ? 1 : 0) | (__any_sync(FULL, sus) ? 2 : 0);
-            if (G > 32)
-            {
-                __syncthreads();  // the previous segment is finished with the shared arrays
-                if ((tid & 31) == 0)
-                {
-                    s_red[2 * (tid >> 5)] = top.m1;
-                    s_red[2 * (tid >> 5) + 1] = top.m2;
-                    s_w[tid >> 5] = flags;
-                }
-                __syncthreads();
-                const bool in = (tid & 31) < (G >> 5);
-                top.m1 = in ? s_red[2 * (tid & 31)] : neg_inf();
-                top.m2 = in ? s_red[2 * (tid & 31) + 1] : neg_inf();
-                flags = in ? s_w[tid & 31] : 0;
-                for (int o = 16; o > 0; o >>= 1)
-                {
-                    const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
-                    top.merge(o1, o2);
-                    flags |= __shfl_xor_sync(FULL, flags, o);
-                }
-                __syncthreads();
-            }
-            need_eval = flags == 3;
-            if (!(top.m1 > neg_inf())) continue;  // no movement in this window
-            if (!need_eval && !exact)
-            {
-                double L;
-                if (advance_only(top, L0, thr, L))
-                {
-                    if (tid == 0) c.last_calc[key] = L;
-                    continue;
-                }
-            }
-        }
-        gsync<G>();
-        PHASE_CLOCK(0);
-        const LocParam lp = c.loc_param[c.key_loc[key]];
-
         const int slots = need_enters ? 2 * n : n;
-        // buckets: about four events per bucket, and where affordable no wider than the threshold, so that the
-        // successor search below looks at a handful of events even when they come in bursts
         int NB = 32;
-        {
-            const double want = thr > 0 ? (c.T1 - c.T0) / thr : 0.0;
-            while ((NB * 4 < slots || (double) NB < want) && NB < Cfg::NB_CAP) NB <<= 1;
-        }
+        while (NB * 2 < slots && NB < Cfg::NB_CAP) NB <<= 1;
         const double scale = (double) NB / (c.T1 - c.T0);
-        auto bucket_raw = [&](double t) { return (int) floor((t - c.T0) * scale); };
+        auto bucket_raw = [&](double t) -> int {
+            const double f = floor((t - c.T0) * scale);
+            return f < -4.0 ? -4 : (f > (double) (NB + 4) ? NB + 4 : (int) f);
+        };
         auto bucket_of = [&](double t) { return min(max(bucket_raw(t), 0), NB - 1); };
-        // scratch: acc_hi u64[P] | acc_lo u64[P] | ev_t f64[slots] | pr f64[P] | bstart u32[NB+1] | bcur i32[NB] | bsign i32[NB] |
-        //          ja idx[slots+1] | jb idx[slots+1] | node idx[slots] | ev_k u8[slots]                    (P = P_CAP or slots)
-        unsigned char* base = CLS == CLS_HUGE ? c.scratch + c.huge_off[w] : smem + (size_t) group_in_block * group_smem_bytes<CLS>();
-        const size_t P = CLS == CLS_HUGE ? (size_t) slots : (size_t) Cfg::P_CAP;
-        unsigned long long* acc_hi = (unsigned long long*) base;  // fixed-point exposure sum of every evaluation (ExactSum)
-        unsigned long long* acc_lo = acc_hi + P;
-        double* ev_t = (double*) (acc_lo + P);
-        double* pr = ev_t + slots;
-        uint32_t* bstart = (uint32_t*) (pr + P);
-        int32_t* bcur = (int32_t*) (bstart + NB + 1);
-        int32_t* bsign = bcur + NB;
-        idx_t* ja = (idx_t*) (bsign + NB);
-        idx_t* jb = ja + (slots + 1);
-        idx_t* node = jb + (slots + 1);
-        uint8_t* ev_k = (uint8_t*) (node + slots);
+        // scratch: ev_t f64[M] | bstart u32[NB + 2] | bcur i32[NB + 2] | bsign i32[NB + 2] | bminc u32[NB + 2] | nextc u32[NB + 2] |
+        //          pa idx[M + 1] | pb idx[M + 1] | node idx[M + 1] | ev_k u8[M]
+        const size_t M = CLS == HOT_HUGE ? (size_t) slots : (size_t) Cfg::M_CAP;
+        unsigned char* base = CLS == HOT_HUGE ? c.scratch + c.huge_off[w] : smem;
+        double* ev_t = (double*) base;
+        uint32_t* bstart = (uint32_t*) (ev_t + M);
+        int32_t* bcur = (int32_t*) (bstart + NB + 2);
+        int32_t* bsign = bcur + NB + 2;
+        uint32_t* bminc = (uint32_t*) (bsign + NB + 2);
+        uint32_t* nextc = bminc + NB + 2;
+        idx_t* pa = (idx_t*) (nextc + NB + 2);
+        idx_t* pb = pa + (M + 1);
+        idx_t* node = pb + (M + 1);
+        uint8_t* ev_k = (uint8_t*) (node + (M + 1));
 
-        // 1. histogram of the window's movement events over NB time buckets
-        for (int i = tid; i <= NB; i += G) bstart[i] = 0;
-        for (int i = tid; i < NB; i += G) bsign[i] = 0;
-        gsync<G>();
-        for (int i = tid; i < slots; i += G)
+        __syncthreads();  // the previous sub-location is finished with the arrays
+        // 1. histogram of the window's movement events over the time buckets
+        for (int i = tid; i < NB + 2; i += G) { bstart[i] = 0; bsign[i] = 0; }
+        __syncthreads();
+        int carried = 0;
+        for (int v = tid; v < n; v += G)
         {
-            const int v = need_enters ? (i >> 1) : i;
-            const int kind = need_enters ? (i & 1) : 0;
-            const double t = kind ? rec[v].tin : rec[v].tout;
-            if (t >= c.T0 && t < c.T1)
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(rec + v));
+            const double tin = bits_f64(((uint64_t) h0.y << 32) | h0.x), tout = bits_f64(((uint64_t) h0.w << 32) | h0.z);
+            carried += tin < c.T0 ? 1 : 0;
+            if (tout >= c.T0 && tout < c.T1)
             {
-                const int bk = bucket_of(t);
+                const int bk = bucket_of(tout);
                 atomicAdd(&bstart[bk], 1u);
-                if (MODEL == HEROS_MODEL_DISTANCE) atomicAdd(&bsign[bk], kind ? 1 : -1);
+                if (MODEL == HEROS_MODEL_DISTANCE) atomicAdd(&bsign[bk], -1);
+            }
+            if (need_enters && tin >= c.T0 && tin < c.T1)
+            {
+                const int bk = bucket_of(tin);
+                atomicAdd(&bstart[bk], 1u);
+                if (MODEL == HEROS_MODEL_DISTANCE) atomicAdd(&bsign[bk], 1);
             }
         }
-        gsync<G>();
-        PHASE_CLOCK(1);
+        if (MODEL == HEROS_MODEL_DISTANCE) carried = group_sum<G>(carried, s_w);
+        __syncthreads();
         // 2. bucket offsets
         const int m_ev = group_exclusive_scan<G>(NB, [&](int i) { return (int) bstart[i]; }, bstart, s_w);
-        if (tid == 0) bstart[NB] = (uint32_t) m_ev;
+        if (tid == 0) { bstart[NB] = (uint32_t) m_ev; bstart[NB + 1] = (uint32_t) m_ev; }
         for (int i = tid; i < NB; i += G) bcur[i] = (int32_t) bstart[i];
-        gsync<G>();
-        PHASE_CLOCK(2);
-        // 3. scatter the events into their buckets (order inside a bucket is irrelevant to every result)
-        for (int i = tid; i < slots; i += G)
+        __syncthreads();
+        // 3. the events into their buckets (the order inside a bucket is irrelevant to every result)
+        for (int v = tid; v < n; v += G)
         {
-            const int v = need_enters ? (i >> 1) : i;
-            const int kind = need_enters ? (i & 1) : 0;
-            const double t = kind ? rec[v].tin : rec[v].tout;
-            if (t >= c.T0 && t < c.T1)
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(rec + v));
+            const double tin = bits_f64(((uint64_t) h0.y << 32) | h0.x), tout = bits_f64(((uint64_t) h0.w << 32) | h0.z);
+            if (tout >= c.T0 && tout < c.T1)
             {
-                const int pos = atomicAdd(&bcur[bucket_of(t)], 1);
-                ev_t[pos] = t;
-                ev_k[pos] = (uint8_t) kind;
+                const int pos = atomicAdd(&bcur[bucket_of(tout)], 1);
+                ev_t[pos] = tout;
+                ev_k[pos] = 0;
+            }
+            if (need_enters && tin >= c.T0 && tin < c.T1)
+            {
+                const int pos = atomicAdd(&bcur[bucket_of(tin)], 1);
+                ev_t[pos] = tin;
+                ev_k[pos] = 1;
             }
         }
-        gsync<G>();
-        PHASE_CLOCK(3);
-        const idx_t END = (idx_t) m_ev;
+        __syncthreads();
+        const uint32_t END = (uint32_t) m_ev;
         auto is_cand = [&](int j) { return both || ev_k[j] == 0; };
-        // 4. sort inside every bucket: each event counts the events of its bucket that precede it and moves to that
-        //    rank.  Buckets hold a handful of events, so this is a few compares per event, all events in parallel.
-        if (CLS == CLS_HUGE)
+        // 4. per bucket: its earliest candidate; occupancy change before the bucket (distance model)
+        for (int b = tid; b < NB; b += G)
         {
-            double* tmp_t = pr;                  // f64[slots]
-            uint8_t* tmp_k = (uint8_t*) node;    // idx[slots] >= slots bytes
-            for (int i = tid; i < m_ev; i += G) { tmp_t[i] = ev_t[i]; tmp_k[i] = ev_k[i]; }
-            gsync<G>();
-            for (int i = tid; i < m_ev; i += G)
-            {
-                const double t = tmp_t[i];
-                const int bk = bucket_of(t);
-                const int lo = (int) bstart[bk], hi = (int) bstart[bk + 1];
-                int rank = 0;
-                for (int q = lo; q < hi; ++q) rank += (tmp_t[q] < t || (tmp_t[q] == t && q < i)) ? 1 : 0;
-                ev_t[lo + rank] = t;
-                ev_k[lo + rank] = tmp_k[i];
-            }
+            uint32_t best = END;
+            double best_t = pos_inf();
+            for (int j = (int) bstart[b]; j < (int) bstart[b + 1]; ++j)
+                if (is_cand(j) && ev_t[j] < best_t) { best_t = ev_t[j]; best = (uint32_t) j; }
+            bminc[b] = best;
         }
-        else
-        {
-            constexpr int MAXE = Cfg::S_CAP / G;  // events per thread
-            double e_t[MAXE > 0 ? MAXE : 1];
-            int e_dst[MAXE > 0 ? MAXE : 1];
-            uint8_t e_k[MAXE > 0 ? MAXE : 1];
-#pragma unroll
-            for (int k = 0; k < MAXE; ++k)
-            {
-                const int i = tid + k * G;
-                e_dst[k] = -1;
-                if (i < m_ev)
-                {
-                    const double t = ev_t[i];
-                    const int bk = bucket_of(t);
-                    const int lo = (int) bstart[bk], hi = (int) bstart[bk + 1];
-                    int rank = 0;
-                    for (int q = lo; q < hi; ++q) rank += (ev_t[q] < t || (ev_t[q] == t && q < i)) ? 1 : 0;
-                    e_t[k] = t;
-                    e_k[k] = ev_k[i];
-                    e_dst[k] = lo + rank;
-                }
-            }
-            gsync<G>();
-#pragma unroll
-            for (int k = 0; k < MAXE; ++k)
-                if (e_dst[k] >= 0) { ev_t[e_dst[k]] = e_t[k]; ev_k[e_dst[k]] = e_k[k]; }
-        }
-        gsync<G>();
-        int carried = 0;
+        __syncthreads();
         if (MODEL == HEROS_MODEL_DISTANCE)
-        {
-            group_exclusive_scan<G>(NB, [&](int i) { return bsign[i]; }, bcur, s_w);  // occupancy change before bucket
-            for (int v = tid; v < n; v += G) carried += (rec[v].tin < c.T0);
-            carried = group_sum<G>(carried, s_w);
-        }
-        gsync<G>();
-        PHASE_CLOCK(4);
-        // next candidate at or after every event (kept in jb until the pointer doubling needs that table)
-        idx_t* nextc = jb;
-        group_suffix_min<G>(m_ev, [&](int i) { return is_cand(i) ? i : m_ev; }, nextc, s_w);
+            group_exclusive_scan<G>(NB, [&](int i) { return bsign[i]; }, bcur, s_w);
+        group_suffix_min<G>(NB, [&](int b) { return bminc[b] != END ? b : NB; }, nextc, s_w);
+        if (tid == 0) { nextc[NB] = (uint32_t) NB; nextc[NB + 1] = (uint32_t) NB; }
+        __syncthreads();
         // successor of an evaluation at time e: the earliest candidate t > e with !(t - e < thr)
-        auto successor = [&](double e) -> int {
-            int b0 = bucket_raw(e + thr) - 1;
-            b0 = min(max(b0, 0), NB);
-            // the events are in time order; the first one that qualifies lies in buckets b0 .. b0 + 2 or, if none of those
-            // does, is the first event after them (everything later is more than a threshold away)
-            int lo = (int) bstart[b0], hi = (int) bstart[min(b0 + 3, NB)];
-            while (lo < hi)
-            {
-                const int mid = (lo + hi) >> 1;
-                const double t = ev_t[mid];
-                if (t > e && !(t - e < thr)) hi = mid; else lo = mid + 1;
-            }
-            return lo < m_ev ? (int) nextc[lo] : m_ev;  // enter events are not candidates in EXIT_ONLY mode
+        auto successor = [&](double e) -> uint32_t {
+            const int b = bucket_raw(e + thr);
+            uint32_t best = END;
+            double best_t = pos_inf();
+            const int b_lo = max(b - 1, 0), b_hi = min(b + 1, NB - 1);
+            if (b_lo <= b_hi)
+                for (int j = (int) bstart[b_lo]; j < (int) bstart[b_hi + 1]; ++j)
+                {
+                    const double t = ev_t[j];
+                    if (is_cand(j) && t > e && !(t - e < thr) && t < best_t) { best_t = t; best = (uint32_t) j; }
+                }
+            if (best != END) return best;
+            const int nb = (int) nextc[min(max(b + 2, 0), NB)];
+            return nb < NB ? bminc[nb] : END;
         };
         // 5. next pointers, chain start, pointer doubling
-        for (int i = tid; i <= m_ev; i += G) ja[i] = (i < m_ev && is_cand(i)) ? (idx_t) successor(ev_t[i]) : END;
-        const int start = successor(L0);
+        for (int i = tid; i <= m_ev; i += G) pa[i] = (idx_t) ((i < m_ev && is_cand(i)) ? successor(ev_t[i]) : END);
+        const uint32_t start = successor(L0);
         int r_cap = m_ev;
         if (thr > 0)
         {
@@ -839,329 +815,252 @@ k_transmit_group(const WindowCtx c)  // <= 64 registers per thread: the register
             if (bound < (double) r_cap) r_cap = (int) bound;
         }
         for (int r = tid; r < r_cap; r += G) node[r] = (idx_t) start;
-        gsync<G>();
-        PHASE_CLOCK(5);
+        __syncthreads();
         {
-            idx_t* pa = ja;
-            idx_t* pb = jb;
+            idx_t* qa = pa;
+            idx_t* qb = pb;
             for (int k = 0; (1 << k) < r_cap; ++k)
             {
                 for (int r = tid; r < r_cap; r += G)
-                    if ((r >> k) & 1) node[r] = pa[node[r]];
-                for (int i = tid; i <= m_ev; i += G) pb[i] = pa[pa[i]];
-                gsync<G>();
-                idx_t* t = pa; pa = pb; pb = t;
+                    if ((r >> k) & 1) node[r] = qa[node[r]];
+                for (int i = tid; i <= m_ev; i += G) qb[i] = qa[qa[i]];
+                __syncthreads();
+                idx_t* t = qa; qa = qb; qb = t;
             }
         }
-        PHASE_CLOCK(6);
         int R;  // chain length: node[r] != END for r < R
         {
             int lo = 0, hi = r_cap;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (node[mid] == END) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t) node[mid] == END) hi = mid; else lo = mid + 1; }
             R = lo;
         }
+        if (R == 0) continue;
         if (tid == 0)
         {
             st.evaluations += (unsigned long long) R;
-            if (R > 0) c.last_calc[key] = ev_t[node[R - 1]];
+            c.last_calc[key] = ev_t[node[R - 1]];
         }
-        if (!need_eval || R == 0) { gsync<G>(); continue; }
-        // 6. list of the stays whose person can be ill (ja as scan output; the doubling tables are dead) ...
-        gsync<G>();
-        const int n_ill = group_exclusive_scan<G>(n, [&](int v) { return phase_is_ill(view_tphase(rec[v].view)) ? 1 : 0; },
-                                                  ja, s_w);
-        for (int v = tid; v < n; v += G)
-            if (phase_is_ill(view_tphase(rec[v].view))) jb[ja[v]] = (idx_t) v;
-        gsync<G>();
-        PHASE_CLOCK(7);
-        // 7. duration, exposure sum and probability of every evaluation.
-        //    a) the factor of every evaluation (head count, sqrt, exp: a long dependent fp64 chain, one per thread);
-        //    b) the exposure sums, PAIR by pair: every ill stay finds the run of evaluations it was present at, the warp
-        //       deals out the (ill stay, evaluation) pairs evenly and every lane adds its term to the evaluation's
-        //       fixed-point sum (ExactSum) with integer atomics -- exact, so the order in which the terms arrive does
-        //       not matter, and no lane idles while another one works through a term;
-        //    c) the probability of every evaluation.
-        if (n_ill <= PAIR_MIN_ILL)
-        {
-            // few ill stays (the usual case while the prevalence is low): one evaluation per thread -- or 2^k lanes per
-            // evaluation when threads outnumber evaluations -- walking the short list of ill stays
-            int lpn = 1;
-            while (lpn < 32 && 2 * lpn * R <= G) lpn <<= 1;
-            const int sub = tid & (lpn - 1), per_pass = G / lpn;
-            for (int r0 = 0; r0 < R; r0 += per_pass)
-            {
-                const int r = r0 + tid / lpn;
-                const bool active = r < R;
-                double p = 0.0, factor = 0.0, now = 0.0, duration = 0.0;
-                ExactSum acc = exact_zero();
-                if (active)
-                {
-                    now = ev_t[node[r]];
-                    duration = now - (r ? ev_t[node[r - 1]] : L0);
-                    if (MODEL == HEROS_MODEL_AREA)
-                        factor = area_factor(c.area, duration, lp.denom);
-                    else
-                    {
-                        const int bk = bucket_of(now);
-                        int head_count = carried + bcur[bk];
-                        for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
-                            head_count += ev_k[j] ? 1 : -1;
-                        double psi, mu;
-                        policy_at(c, now, psi, mu);
-                        factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
-                    }
-                    if (factor != 0.0)
-                        for (int k = sub; k < n_ill; k += lpn)
-                        {
-                            const StayRec& s = rec[jb[k]];
-                            if (s.tin < now && now <= s.tout && ill_at(c, s, now))
-                            {
-                                const double te = now - (double) view_exposure(s.view);
-                                if (MODEL == HEROS_MODEL_AREA)
-                                    exact_add(acc, area_contribution(c.area, te));
-                                else
-                                {
-                                    const double v_t = dist_viral_load(c.dist, te);
-                                    if (v_t > 0) exact_add(acc, dist_term(c.dist, factor, duration, v_t));
-                                }
-                            }
-                        }
-                }
-                for (int o = lpn >> 1; o > 0; o >>= 1)
-                    exact_merge(acc, __shfl_xor_sync(FULL, acc.hi, o), __shfl_xor_sync(FULL, acc.lo, o), __shfl_xor_sync(FULL, acc.loose, o));
-                if (active && sub == 0)
-                {
-                    if (!(factor != 0.0 && probability<MODEL>(factor, exact_value(acc), p) && p > 0)) p = 0.0;
-                    pr[r] = p;
-                }
-            }
-        }
-        else
-        {
-            for (int r = tid; r < R; r += G)
-            {
-                const double now = ev_t[node[r]];
-                double factor;
-                if (MODEL == HEROS_MODEL_AREA)
-                    factor = area_factor(c.area, now - (r ? ev_t[node[r - 1]] : L0), lp.denom);
-                else
-                {
-                    // head count = occupants before any event of time `now`: bucket prefix + earlier events of the bucket
-                    const int bk = bucket_of(now);
-                    int head_count = carried + bcur[bk];
-                    for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1] && ev_t[j] < now; ++j)
-                        head_count += ev_k[j] ? 1 : -1;
-                    double psi, mu;
-                    policy_at(c, now, psi, mu);
-                    factor = dist_factor(c.dist, psi, mu, lp.area_sub, head_count);
-                }
-                pr[r] = factor;
-                acc_hi[r] = 0ull;
-                acc_lo[r] = 0ull;
-            }
-            if (tid == 0) s_w[32] = 0;  // set when a term does not fit the fixed-point range (non-finite areas)
-            gsync<G>();
-            for (int k0 = tid & ~31; k0 < n_ill; k0 += G)
-            {
-                const int lane = tid & 31;
-                const int k = k0 + lane;
-                StayRec s;
-                s.tin = 0.0; s.tout = 0.0; s.view = 0; s.person = 0; s.pad = 0;
-                int lo = 0, cnt = 0;
-                if (k < n_ill)
-                {
-                    s = rec[jb[k]];
-                    int l = 0, h = R;  // first evaluation with time > t_in
-                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
-                    lo = l;
-                    h = R;             // first evaluation with time > t_out
-                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
-                    cnt = l - lo;
-                }
-                int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
-    #pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const int t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int total = __shfl_sync(FULL, incl, 31);
-                for (int p0 = 0; p0 < total; p0 += 32)
-                {
-                    const int pi = p0 + lane;
-                    int src = 0;  // first lane whose inclusive prefix exceeds pi
-    #pragma unroll
-                    for (int step = 16; step > 0; step >>= 1)
-                    {
-                        const int probe = __shfl_sync(FULL, incl, min(src + step - 1, 31));
-                        if (probe <= pi) src += step;
-                    }
-                    src = min(src, 31);
-                    const int s_incl = __shfl_sync(FULL, incl, src), s_cnt = __shfl_sync(FULL, cnt, src);
-                    const int s_lo = __shfl_sync(FULL, lo, src);
-                    StayRec q;
-                    q.tin = 0.0;
-                    q.tout = __shfl_sync(FULL, s.tout, src);
-                    q.view = __shfl_sync(FULL, s.view, src);
-                    q.person = __shfl_sync(FULL, s.person, src);
-                    q.pad = __shfl_sync(FULL, s.pad, src);
-                    if (pi < total)
-                    {
-                        const int r = s_lo + (pi - (s_incl - s_cnt));
-                        const double now = ev_t[node[r]];
-                        const double factor = pr[r];
-                        if (factor != 0.0 && ill_at(c, q, now))  // present by construction: t_in < now <= t_out
-                        {
-                            const double te = now - (double) view_exposure(q.view);
-                            double term = 0.0;
-                            if (MODEL == HEROS_MODEL_AREA)
-                                term = area_contribution(c.area, te);
-                            else
-                            {
-                                const double v_t = dist_viral_load(c.dist, te);
-                                if (v_t > 0) term = dist_term(c.dist, factor, now - (r ? ev_t[node[r - 1]] : L0), v_t);
-                            }
-                            if (term != 0.0)
-                            {
-                                ExactSum one = exact_zero();
-                                exact_add(one, term);
-                                if (one.loose != 0.0 || one.loose != one.loose) s_w[32] = 1;
-                                else
-                                {
-                                    const unsigned long long old = atomicAdd(&acc_lo[r], one.lo);
-                                    atomicAdd(&acc_hi[r], (unsigned long long) one.hi + ((old + one.lo < old) ? 1ull : 0ull));
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            gsync<G>();
-            const bool loose = s_w[32] != 0;
-            for (int r = tid; r < R; r += G)
-            {
-                const double factor = pr[r];
-                double sum;
-                if (!loose)
-                    sum = exact_value(ExactSum{(long long) acc_hi[r], acc_lo[r], 0.0});
-                else
-                {
-                    // a term outside the fixed-point range (NaN / infinite areas): plain doubles; the result is +-inf or
-                    // NaN whatever the order
-                    const double now = ev_t[node[r]], duration = now - (r ? ev_t[node[r - 1]] : L0);
-                    sum = 0.0;
-                    if (factor != 0.0)
-                        for (int k = 0; k < n_ill; ++k)
-                        {
-                            const StayRec& q = rec[jb[k]];
-                            if (q.tin < now && now <= q.tout && ill_at(c, q, now))
-                            {
-                                const double te = now - (double) view_exposure(q.view);
-                                if (MODEL == HEROS_MODEL_AREA)
-                                    sum += area_contribution(c.area, te);
-                                else
-                                {
-                                    const double v_t = dist_viral_load(c.dist, te);
-                                    if (v_t > 0) sum += dist_term(c.dist, factor, duration, v_t);
-                                }
-                            }
-                        }
-                }
-                double p = 0.0;
-                if (!(factor != 0.0 && probability<MODEL>(factor, sum, p) && p > 0)) p = 0.0;
-                pr[r] = p;
-            }
-        }
-        gsync<G>();
-        if (dbg && tid == 0)
-        {
-            const long long t_ = clock64();
-            const unsigned long long d_ = (unsigned long long) (t_ - clk);
-            if (atomicMax(&c.ctr->dbg_clk[CLS][8], d_) < d_)
-            {
-                c.ctr->dbg_clk[CLS][10] = (unsigned long long) n; c.ctr->dbg_clk[CLS][11] = (unsigned long long) n_ill;
-                c.ctr->dbg_clk[CLS][12] = (unsigned long long) R; c.ctr->dbg_clk[CLS][13] = (unsigned long long) m_ev;
-                c.ctr->dbg_clk[CLS][14] = (unsigned long long) key;
-            }
-            clk = t_;
-        }
-        // 8. draws: every susceptible stay against exactly the evaluations with p > 0 it was present at, (t_in, t_out].
-        //    The (stay, evaluation) pairs can be a hundred times the stays, so they are not expanded here: the
-        //    evaluations with p > 0 go to a table in global memory (ja = how many precede each evaluation; the tables of
-        //    steps 5-6 are dead), every susceptible stay leaves ONE item (person, first table entry, first pair number),
-        //    and k_draw expands the items into draws over the whole GPU.  Nothing is left to do when nobody ill was ever
-        //    present.
-        const int n_pos = group_exclusive_scan<G>(R, [&](int r) { return pr[r] > 0 ? 1 : 0; }, ja, s_w);
-        if (n_pos == 0) { gsync<G>(); continue; }
+        if (!need_eval) continue;
+        // 6. one row per evaluation (time, duration, head count), one work item per 32 rows
+        const int n_chunks = (R + 31) >> 5;
         if (tid == 0)
         {
-            ja[R] = (idx_t) n_pos;
-            s_tab = atomicAdd(&c.ctr->tab_top, (unsigned long long) n_pos);
+            s_base[0] = atomicAdd(&c.ctr->tab_top, (unsigned long long) R);
+            s_base[1] = atomicAdd(&c.ctr->n_items, (unsigned long long) n_chunks);
         }
-        gsync<G>();
-        const unsigned long long tab0 = s_tab;
-        for (int r = tid; r < R; r += G)
-            if (pr[r] > 0)
-            {
-                const unsigned long long e = tab0 + ja[r];
-                if (e < c.tab_cap) { c.tab_t[e] = ev_t[node[r]]; c.tab_p[e] = pr[r]; }
-                else atomicOr(&c.ctr->overflow, 2u);
-            }
-        for (int v0 = tid & ~31; v0 < n; v0 += G)
+        __syncthreads();
+        const unsigned long long tab0 = s_base[0], item0 = s_base[1];
+        if (tab0 + (unsigned long long) R > c.tab_cap || item0 + (unsigned long long) n_chunks > c.item_cap)
         {
-            const int lane = tid & 31;
-            const int v = v0 + lane;
-            int lo = 0, cnt = 0;
-            uint32_t person = 0;
-            if (v < n)
-            {
-                const StayRec s = rec[v];
-                if (phase_is_susceptible(view_tphase(s.view)))
-                {
-                    person = s.person;
-                    int l = 0, h = R;  // first evaluation with time > t_in
-                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tin) h = mid; else l = mid + 1; }
-                    lo = (int) ja[l];
-                    h = R;             // first evaluation with time > t_out
-                    while (l < h) { const int mid = (l + h) >> 1; if (ev_t[node[mid]] > s.tout) h = mid; else l = mid + 1; }
-                    cnt = (int) ja[l] - lo;
-                }
-            }
-            int incl = cnt;  // inclusive prefix sum of the pair counts over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            const unsigned has = __ballot_sync(FULL, cnt > 0);
-            if (total == 0) continue;
-            // one atomic reserves items and pair numbers together, so that both ascend in the same order
-            unsigned long long at = 0;
-            if (lane == 0) at = atomicAdd(&c.ctr->n_draw, ((unsigned long long) __popc(has) << DRAW_ITEM_SHIFT) | (unsigned long long) total);
-            at = __shfl_sync(FULL, at, 0);
-            if (cnt > 0)
-            {
-                const unsigned long long item = (at >> DRAW_ITEM_SHIFT) + __popc(has & ((1u << lane) - 1u));
-                if (item < c.item_cap && tab0 + lo + cnt <= c.tab_cap)
-                {
-                    c.item_person[item] = person;
-                    c.item_key[item] = key;
-                    c.item_tab[item] = tab0 + (unsigned long long) lo;
-                    c.item_pair[item] = (at & DRAW_PAIR_MASK) + (unsigned long long) (incl - cnt);
-                }
-                else
-                    atomicOr(&c.ctr->overflow, 2u);
-            }
+            if (tid == 0) atomicOr(&c.ctr->overflow, 2u);
+            continue;
         }
-        gsync<G>();
-        PHASE_CLOCK(9);
+        for (int r = tid; r < R; r += G)
+        {
+            const double now = ev_t[node[r]];
+            c.tab_now[tab0 + r] = now;
+            c.tab_dur[tab0 + r] = now - (r ? ev_t[node[r - 1]] : L0);
+            int head_count = 0;
+            if (MODEL == HEROS_MODEL_DISTANCE)
+            {
+                // occupants before any event of time `now`: bucket prefix + the earlier events of the bucket
+                const int bk = bucket_of(now);
+                head_count = carried + bcur[bk];
+                for (int j = (int) bstart[bk]; j < (int) bstart[bk + 1]; ++j)
+                    if (ev_t[j] < now) head_count += ev_k[j] ? 1 : -1;
+            }
+            c.tab_head[tab0 + r] = (uint32_t) head_count;
+        }
+        for (int ch = tid; ch < n_chunks; ch += G)
+        {
+            c.item_key[item0 + ch] = key;
+            c.item_tab[item0 + ch] = tab0 + 32ull * (unsigned long long) ch;
+            c.item_cnt[item0 + ch] = (uint32_t) min(32, R - 32 * ch);
+        }
     }
-#undef PHASE_CLOCK
     flush_stats(c, st, threadIdx.x & 31);
 }
 
+namespace {
+
+// ---- bulk asynchronous copies global -> shared (the TMA unit's 1-D form) completing on an mbarrier ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int EVAL_T = 128;      // threads of an evaluation block (4 warps)
+constexpr int EVAL_TILE = 128;   // records per tile (4 KB): every warp takes a quarter of every tile
+constexpr int EVAL_STAGES = 2;   // tiles in flight
+
+}  // namespace
+
+// One thread block per work item = up to 32 consecutive calculated evaluations of one hot sub-location; lane k of every
+// warp stands for evaluation k.  The sub-location's records are streamed twice through shared memory, tile by tile, by
+// the bulk-copy engine: first the ill stays that overlap the item's time span are broadcast lane to lane and every lane
+// adds the term of its evaluation (TArea:167-172 / TDist:155-164) to a 128-bit fixed-point sum in registers -- exact
+// integer additions, so neither the order of the stays nor the split over the four warps can change the result; the
+// four partial sums are merged in shared memory, p follows (TArea:182 / TDist:173); then the susceptible stays are
+// broadcast and every lane draws for the pairs (stay present, p > 0) (TArea:190 / TDist:181).
+template <int MODEL>
+__global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
+{
+    __shared__ __align__(128) StayRec s_tile[EVAL_STAGES][EVAL_TILE];
+    __shared__ __align__(8) uint64_t s_bar[EVAL_STAGES];
+    __shared__ long long s_hi[EVAL_T / 32][32];
+    __shared__ unsigned long long s_lo[EVAL_T / 32][32];
+    __shared__ double s_loose[EVAL_T / 32][32];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const unsigned long long n_items = min(c.ctr->n_items, c.item_cap);
+    uint32_t parity[EVAL_STAGES];
+#pragma unroll
+    for (int s = 0; s < EVAL_STAGES; ++s) parity[s] = 0u;
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < EVAL_STAGES; ++s) mbar_init(&s_bar[s], 1u);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    Local st;
+
+    // streams the records [0, n) of the segment through the tiles; `body(r, v)` is called by every lane with the record
+    // of its slot (v < n) -- all lanes of a warp call together (v may be >= n: then r is undefined and must be ignored)
+    auto for_each_record = [&](const StayRec* rec, int n, auto&& body) {
+        const int n_tiles = (n + EVAL_TILE - 1) / EVAL_TILE;
+        auto issue = [&](int j) {
+            const int s = j % EVAL_STAGES;
+            const uint32_t bytes = (uint32_t) min(EVAL_TILE, n - j * EVAL_TILE) * (uint32_t) sizeof(StayRec);
+            mbar_expect_tx(&s_bar[s], bytes);
+            bulk_g2s(&s_tile[s][0], rec + (size_t) j * EVAL_TILE, bytes, &s_bar[s]);
+        };
+        if (tid == 0)
+            for (int j = 0; j < EVAL_STAGES && j < n_tiles; ++j) issue(j);
+        for (int j = 0; j < n_tiles; ++j)
+        {
+            const int s = j % EVAL_STAGES;
+            mbar_wait(&s_bar[s], parity[s]);
+            parity[s] ^= 1u;
+            const int slot = wib * 32 + lane;
+            const int v = j * EVAL_TILE + slot;
+            StayRec r;
+            {
+                const uint4* q = reinterpret_cast<const uint4*>(&s_tile[s][slot]);
+                const uint4 h0 = q[0], h1 = q[1];
+                r.tin = bits_f64(((uint64_t) h0.y << 32) | h0.x); r.tout = bits_f64(((uint64_t) h0.w << 32) | h0.z);
+                r.view = ((uint64_t) h1.y << 32) | h1.x; r.person = h1.z; r.pad = h1.w;
+            }
+            body(r, v);
+            __syncthreads();  // everybody is done with the tile: its buffer can be filled again
+            if (tid == 0 && j + EVAL_STAGES < n_tiles) issue(j + EVAL_STAGES);
+        }
+    };
+
+    for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
+    {
+        const uint32_t key = c.item_key[it];
+        const unsigned long long tab = c.item_tab[it];
+        const int cnt = (int) c.item_cnt[it];
+        const uint32_t a = c.seg_start[key];
+        const int n = (int) (c.seg_start[key + 1] - a);
+        const StayRec* rec = c.rec + a;
+        const LocParam lp = c.loc_param[c.key_loc[key]];
+        const bool active = lane < cnt;
+        const double now = active ? c.tab_now[tab + lane] : pos_inf();
+        const double duration = active ? c.tab_dur[tab + lane] : 0.0;
+        double factor = 0.0;
+        if (active)
+        {
+            if (MODEL == HEROS_MODEL_AREA)
+                factor = area_factor(c.area, duration, lp.denom);  // TArea:156
+            else
+            {
+                double psi, mu;
+                policy_at(c, now, psi, mu);
+                factor = dist_factor(c.dist, psi, mu, lp.area_sub, (int) c.tab_head[tab + lane]);  // TDist:138-143
+            }
+        }
+        const double t_first = __shfl_sync(FULL, now, 0), t_last = __shfl_sync(FULL, now, cnt - 1);
+
+        // 1. exposure sums
+        ExactSum acc = exact_zero();
+        for_each_record(rec, n, [&](const StayRec& r, int v) {
+            const bool cand = v < n && phase_is_ill(view_tphase(r.view)) && r.tin < t_last && r.tout >= t_first;
+            unsigned m = __ballot_sync(FULL, cand);
+            while (m)
+            {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                StayRec q;
+                q.tin = __shfl_sync(FULL, r.tin, src); q.tout = __shfl_sync(FULL, r.tout, src);
+                q.view = __shfl_sync(FULL, r.view, src); q.person = __shfl_sync(FULL, r.person, src);
+                q.pad = __shfl_sync(FULL, r.pad, src);
+                if (factor != 0.0 && q.tin < now && now <= q.tout && ill_at(c, q, now))  // TArea:157 / TDist:144
+                {
+                    const double te = now - (double) view_exposure(q.view);
+                    if (MODEL == HEROS_MODEL_AREA)
+                        exact_add(acc, area_contribution(c.area, te));  // TArea:167-172
+                    else
+                    {
+                        const double v_t = dist_viral_load(c.dist, te);                       // TDist:155-159
+                        if (v_t > 0) exact_add(acc, dist_term(c.dist, factor, duration, v_t));  // TDist:161-164
+                    }
+                }
+            }
+        });
+        s_hi[wib][lane] = acc.hi; s_lo[wib][lane] = acc.lo; s_loose[wib][lane] = acc.loose;
+        __syncthreads();
+        ExactSum tot = exact_zero();
+#pragma unroll
+        for (int w = 0; w < EVAL_T / 32; ++w) exact_merge(tot, s_hi[w][lane], s_lo[w][lane], s_loose[w][lane]);
+        double p = 0.0;
+        if (!(active && factor != 0.0 && probability<MODEL>(factor, exact_value(tot), p) && p > 0)) p = 0.0;
+        const unsigned pos = __ballot_sync(FULL, p > 0.0);
+        __syncthreads();  // the partial sums are read: the arrays can be written by the next item
+        if (pos == 0u) continue;  // the same in every warp
+
+        // 2. draws
+        for_each_record(rec, n, [&](const StayRec& r, int v) {
+            const bool cand = v < n && phase_is_susceptible(view_tphase(r.view)) && r.tin < t_last && r.tout >= t_first;
+            unsigned m = __ballot_sync(FULL, cand);
+            while (m)
+            {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const double q_tin = __shfl_sync(FULL, r.tin, src), q_tout = __shfl_sync(FULL, r.tout, src);
+                const uint32_t q_person = __shfl_sync(FULL, r.person, src);
+                if (p > 0.0 && q_tin < now && now <= q_tout) draw_and_push(c, st, q_person, key, now, p);  // TArea:190 / TDist:181
+            }
+        });
+    }
+    flush_stats(c, st, lane);
+}
 // ------------------------------------------------------------------------------------------------------------------
 // total-location branch (Covid19TransmissionArea.java:198-246, Covid19TransmissionDistance.java:189-246): one block per
 // location with infectInSublocation = false and >= 2 sub-locations.  The movement events of every sub-location drive
@@ -1336,56 +1235,52 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
     flush_stats(c, st, tid & 31);
 }
 
+
 // host-side launcher ----------------------------------------------------------------------------------------------------
-// k_transmit_thread fills the work lists; the warp kernel and the group kernels then run side by side on the auxiliary
-// streams (they touch disjoint sub-locations), and the main stream joins them.
+// The hot path (its work lists were filled by the prefix-sum kernel) starts at once on the auxiliary streams, side by
+// side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds (they touch disjoint
+// sub-locations); the main stream joins them.
 template <int MODEL>
 static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
 {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem0 = group_smem_bytes<0>() * GroupCfg<0>::PER_BLOCK, smem1 = group_smem_bytes<1>(),
-                 smem2 = group_smem_bytes<2>(), smem3 = group_smem_bytes<3>();
+    const size_t smem0 = hot_smem_bytes<0>(), smem1 = hot_smem_bytes<1>();
     if (dev >= 0 && dev < 64 && !configured[dev])
     {
-        cudaFuncSetAttribute(k_transmit_group<MODEL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem0);
-        cudaFuncSetAttribute(k_transmit_group<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
-        cudaFuncSetAttribute(k_transmit_group<MODEL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem2);
-        cudaFuncSetAttribute(k_transmit_group<MODEL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem3);
+        cudaFuncSetAttribute(k_hot_chain<MODEL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem0);
+        cudaFuncSetAttribute(k_hot_chain<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem1);
         configured[dev] = true;
     }
-    // the group kernels (their work lists were filled by the prefix-sum kernel) start at once on the auxiliary streams,
-    // side by side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds
     cudaStream_t s = ts.main;
     cudaEventRecord(ts.fork, s);
-    for (int k = 0; k < N_AUX; ++k)
-        if (k != 3) cudaStreamWaitEvent(ts.aux[k], ts.fork, 0);
-    k_transmit_group<MODEL, 2><<<n_sm * 2, GroupCfg<2>::G, smem2, ts.aux[0]>>>(c);
-    k_transmit_group<MODEL, 3><<<n_sm, GroupCfg<3>::G, smem3, ts.aux[4]>>>(c);
-    k_transmit_group<MODEL, 4><<<n_sm, 1024, 0, ts.aux[4]>>>(c);
-    k_group_filter<MODEL><<<n_sm * 2, 256, 0, ts.aux[1]>>>(c);
-    cudaEventRecord(ts.filtered, ts.aux[1]);
+    cudaStreamWaitEvent(ts.aux[0], ts.fork, 0);
+    k_hot_filter<MODEL><<<n_sm * 2, 256, 0, ts.aux[0]>>>(c);
+    cudaEventRecord(ts.filtered, ts.aux[0]);
     cudaStreamWaitEvent(ts.aux[2], ts.filtered, 0);
-    k_transmit_group<MODEL, 1><<<n_sm * 4, GroupCfg<1>::G, smem1, ts.aux[1]>>>(c);
-    k_transmit_group<MODEL, 0><<<n_sm * 4, GroupCfg<0>::G * GroupCfg<0>::PER_BLOCK, smem0, ts.aux[2]>>>(c);
-    k_transmit_thread<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
+    k_hot_chain<MODEL, 1><<<n_sm, HotCfg<1>::T, smem1, ts.aux[0]>>>(c);
+    k_hot_chain<MODEL, 2><<<n_sm, HotCfg<2>::T, 0, ts.aux[0]>>>(c);
+    k_hot_chain<MODEL, 0><<<n_sm * 8, HotCfg<0>::T, smem0, ts.aux[2]>>>(c);
+    cudaEventRecord(ts.join[2], ts.aux[2]);
+    cudaStreamWaitEvent(ts.aux[0], ts.join[2], 0);
+    k_hot_eval<MODEL><<<n_sm * 8, EVAL_T, 0, ts.aux[0]>>>(c);
+    cudaEventRecord(ts.join[0], ts.aux[0]);
+
+    k_transmit_stream<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
     cudaEventRecord(ts.mid, s);
-    cudaStreamWaitEvent(ts.aux[3], ts.mid, 0);
-    k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[3]>>>(c);
+    cudaStreamWaitEvent(ts.aux[1], ts.mid, 0);
+    k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[1]>>>(c);
+    cudaEventRecord(ts.join[1], ts.aux[1]);
     k_transmit_sub<MODEL, 8><<<n_sm * 8, 256, 0, s>>>(c);
-    for (int k = 0; k < N_AUX; ++k)
-    {
-        cudaEventRecord(ts.join[k], ts.aux[k]);
-        cudaStreamWaitEvent(s, ts.join[k], 0);
-    }
+    cudaStreamWaitEvent(s, ts.join[0], 0);
+    cudaStreamWaitEvent(s, ts.join[1], 0);
+    launches += 8;
     if (c.n_total_loc)
     {
         k_transmit_total<MODEL><<<(int) min((uint32_t) (n_sm * 4), c.n_total_loc), 256, 0, s>>>(c);
         ++launches;
     }
-    k_draw<<<n_sm * 4, 256, 0, s>>>(c);
-    launches += 10;
 }
 
 void launch_transmit(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)

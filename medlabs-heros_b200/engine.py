@@ -201,6 +201,22 @@ class HerosEngine:
         self._check(self._lib.heros_step(self._h, float(t_until), C.byref(st)))
         return st.as_dict()
 
+    def step_async(self, t_until: float) -> None:
+        """heros_step_async: the windows up to ``t_until`` are enqueued; collect them with ``wait``."""
+        self._check(self._lib.heros_step_async(self._h, float(t_until)))
+
+    def wait(self) -> Dict[str, float]:
+        """heros_wait: everything enqueued has finished; statistics of the windows since the last wait / step."""
+        st = _lib.StepStats()
+        self._check(self._lib.heros_wait(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def window_abort(self) -> None:
+        self._check(self._lib.heros_window_abort(self._h))
+
+    def window_finish_async(self) -> None:
+        self._check(self._lib.heros_window_finish_async(self._h))
+
     # ---- multi-GPU window phases (device pointers, e.g. torch tensors' data_ptr()) ----
     def set_id_bases(self, person_base: int, location_base: int):
         self._check(self._lib.heros_set_id_bases(self._h, int(person_base), int(location_base)))
