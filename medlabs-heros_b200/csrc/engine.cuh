@@ -46,11 +46,20 @@ constexpr uint32_t REC_GUEST = 0x80000000u;
 // a record is one 32-byte sector: moved with ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256)
 __device__ __forceinline__ StayRec ld_rec(const StayRec* p)
 {
+#ifdef HEROS_LD256
     uint64_t a, b, v, w;
-    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(w) : "l"(p));
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(v), "=l"(w) : "l"(p));
     StayRec r;
     r.tin = bits_f64(a); r.tout = bits_f64(b); r.view = v; r.person = (uint32_t) w; r.pad = (uint32_t) (w >> 32);
     return r;
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 h0 = __ldg(q), h1 = __ldg(q + 1);  // {t_in, t_out}, {view, person, pad}
+    StayRec r;
+    r.tin = bits_f64(((uint64_t) h0.y << 32) | h0.x); r.tout = bits_f64(((uint64_t) h0.w << 32) | h0.z);
+    r.view = ((uint64_t) h1.y << 32) | h1.x; r.person = h1.z; r.pad = h1.w;
+    return r;
+#endif
 }
 __device__ __forceinline__ void st_rec(StayRec* p, const StayRec& r)
 {

@@ -178,24 +178,13 @@ __device__ __forceinline__ bool stay_before(uint32_t pa, double ta, uint32_t pb,
 // ------------------------------------------------------------------------------------------------------------------
 // one warp per 32 consecutive sub-location keys
 // ------------------------------------------------------------------------------------------------------------------
-namespace {
-
-// max of the 64-bit patterns v over the lanes of `peers` (all of which call with the same mask)
-__device__ __forceinline__ unsigned long long peers_max64(unsigned peers, unsigned long long v)
-{
-    const uint32_t hi = (uint32_t) (v >> 32), lo = (uint32_t) v;
-    const uint32_t mhi = __reduce_max_sync(peers, hi);
-    const uint32_t mlo = __reduce_max_sync(peers, hi == mhi ? lo : 0u);
-    return ((unsigned long long) mhi << 32) | mlo;
-}
-
-}  // namespace
-
 // The records of 32 consecutive keys are contiguous in bucket order, so the warp reads them with coalesced 256-bit
-// loads (a record is one 32-byte sector; LDG.E.256: 1 KB per warp and load, all of it used).  The lane that holds a
-// record finds the key it belongs to by a binary search over the 32 segment ends (shuffles); the lanes holding records
-// of the same key form a group (match.any) and reduce who is there (redux.or) and the two latest distinct event times
-// (redux.max over the time bit patterns: times are non-negative doubles, so their bits order as integers; 0 = none).
+// loads (a record is one 32-byte sector: 1 KB per warp and load, all of it used).  The lane that holds a record finds
+// the key it belongs to by a binary search over the 32 segment ends (shuffles); the lanes holding records of the same
+// key are neighbours, so who is there and the two latest distinct event times follow from one segmented scan over the
+// lanes (five shuffle steps; times are non-negative doubles, so their bit patterns order as integers; 0 = none) whose
+// result the last lane of every segment adds to the key's entry in shared memory.  (match.any + redux over the groups
+// would look shorter, but redux with masks that differ from lane to lane is executed once per distinct mask.)
 // Segments of > 32 stays (the hot path) and of total-branch locations are skipped without being read.
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
@@ -255,18 +244,33 @@ __global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
                         const uint32_t v = __shfl_sync(FULL, e, owner + step - 1);
                         if (v <= i) owner += step;
                     }
-                    const unsigned peers = __match_any_sync(FULL, valid ? owner : 64 + lane);
-                    const unsigned long long m1 = peers_max64(peers, x);
-                    const unsigned long long m2 = peers_max64(peers, x < m1 ? x : (y < m1 ? y : 0ull));
-                    const uint32_t f = __reduce_or_sync(peers, fl);
-                    if (valid && lane == __ffs(peers) - 1)
+                    // segmented inclusive scan over the lanes (records of a key sit in neighbouring lanes): the two latest
+                    // distinct times (m1 > m2) and the flags of the key's records up to this lane
+                    if (!valid) owner = 64 + lane;
+                    unsigned long long m1 = x, m2 = y;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
                     {
-                        // merge into the two latest distinct times of the key (a segment may span two batches)
+                        const int own_up = __shfl_up_sync(FULL, owner, o);
+                        const unsigned long long u1 = __shfl_up_sync(FULL, m1, o), u2 = __shfl_up_sync(FULL, m2, o);
+                        const uint32_t uf = __shfl_up_sync(FULL, fl, o);
+                        if (lane >= o && own_up == owner)
+                        {
+                            fl |= uf;
+                            if (u1 > m1) { m2 = m1 > u2 ? m1 : u2; m1 = u1; }
+                            else if (u1 == m1) { m2 = m2 > u2 ? m2 : u2; }
+                            else { m2 = m2 > u1 ? m2 : u1; }
+                        }
+                    }
+                    const int own_next = __shfl_down_sync(FULL, owner, 1);
+                    if (valid && (lane == 31 || own_next != owner))
+                    {
+                        // the last lane of the key in this batch: merge into the key's entry (a segment may span two batches)
                         unsigned long long a1 = s_m1[wib][owner], a2 = s_m2[wib][owner];
                         if (m1 > a1) { a2 = a1 > m2 ? a1 : m2; a1 = m1; }
                         else if (m1 == a1) { a2 = a2 > m2 ? a2 : m2; }
                         else { a2 = a2 > m1 ? a2 : m1; }
-                        s_m1[wib][owner] = a1; s_m2[wib][owner] = a2; s_fl[wib][owner] |= f;
+                        s_m1[wib][owner] = a1; s_m2[wib][owner] = a2; s_fl[wib][owner] |= fl;
                     }
                     __syncwarp();
                 }
