@@ -505,9 +505,14 @@ def run_ours(args):
                 eng.step_async(24.0 * (d + 1))
                 if d + 1 < total:
                     submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
-                stats.append(eng.wait())
                 if after_step:
+                    # the host reads the day's results before it hands over the next day (e2e)
+                    stats.append(eng.wait())
                     after_step()
+            if not after_step:
+                # everything is resident in HBM: the whole job is enqueued (no window waits for the host: the fill
+                # counts of the pools, the work lists and the candidates stay on the device), one wait at the end
+                stats.append(eng.wait())
         else:
             for d in range(first_timed, total):
                 stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))

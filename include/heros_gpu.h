@@ -250,6 +250,13 @@ int32_t heros_sample_occupancy(heros_handle h, int32_t n_times, const double* ti
 int32_t heros_debug_get_stays(heros_handle h, int64_t capacity, int32_t* person, int32_t* location, int16_t* sublocation,
                               double* t_in, double* t_out, int64_t* n_out);
 
+/* debugging / profiling: when every kernel of a window actually ran.  enable != 0 starts (or restarts) the collection;
+ * start_us / end_us (32 entries each, may be NULL) receive, per kernel id (HEROS_TL_*), the start of its first thread block
+ * and the end of its last one in microseconds after the start of the window's first kernel, averaged over the windows
+ * since the collection was started (-1: the kernel did not run); n_windows the number of windows.  The kernels of the
+ * transmission stage run side by side on several streams: this is the picture no stream-ordered event can give. */
+int32_t heros_debug_timeline(heros_handle h, int32_t enable, double* start_us, double* end_us, int64_t* n_windows);
+
 /* ---- the hot path: advance simulated time to t_until in windows of cfg.window_hours: bucket stays by
  *      sub-location, evaluate infectPeople for every movement event of the window, draw, resolve (earliest successful
  *      draw wins), run the disease-phase state machine.  stats may be NULL. ---- */

@@ -94,6 +94,7 @@ SIGNATURES = {
     "heros_snapshot_load": (C.c_int32, [_P, C.c_int64, _P]),
     "heros_sample_occupancy": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P]),
     "heros_set_closure_policy": (C.c_int32, [_P, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "heros_debug_timeline": (C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(C.c_int64)]),
     "heros_debug_get_stays": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_step": (C.c_int32, [_P, C.c_double, C.POINTER(StepStats)]),
     "heros_step_async": (C.c_int32, [_P, C.c_double]),

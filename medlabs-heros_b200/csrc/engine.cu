@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
                                                      const double* __restrict__ open_tin, uint32_t* count,
                                                      uint32_t* __restrict__ agent_rank)
 {
+    TlStamp tl_(A.ctr, TL_OPEN);
     if (blockIdx.x < pool_blocks)
     {
         // stays carried over from earlier windows (the newer ones took their ticket when they were submitted)
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays PC, PoolArray
                                                         const uint64_t* __restrict__ view, StayRec* __restrict__ rec,
                                                         Counters* ctr)
 {
+    TlStamp tl_(ctr, TL_SCATTER);
     constexpr uint32_t CHUNK = TPB * IPT;
     const uint32_t n_carry = (uint32_t) ctr->n_carry, n_fresh = (uint32_t) ctr->n_fresh;
     const uint32_t vb_carry = (n_carry + CHUNK - 1) / CHUNK, vb_fresh = (n_fresh + CHUNK - 1) / CHUNK,
@@ -322,6 +324,29 @@ __global__ void k_window_roll(Counters* ctr)
     }
 }
 
+// heros_debug_timeline: the stamps of one window (ns since the start of k_window_open) are added to the running sums
+// tl: stamps u64[TL_N][2] | sums i64[TL_N][2] | windows u64 | runs u64[TL_N]
+__global__ void k_timeline_fold(unsigned long long* tl)
+{
+    const int id = threadIdx.x;
+    const unsigned long long base = tl[2 * TL_OPEN];
+    long long* acc = reinterpret_cast<long long*>(tl + 2 * TL_N);
+    __syncwarp();
+    if (id < TL_N)
+    {
+        const unsigned long long t0 = tl[2 * id], t1 = tl[2 * id + 1];
+        if (t0 != ~0ull && base != ~0ull)
+        {
+            acc[2 * id] += (long long) (t0 - base);
+            acc[2 * id + 1] += (long long) (t1 - base);
+            tl[4 * TL_N + 1 + id] += 1ull;
+        }
+        tl[2 * id] = ~0ull;
+        tl[2 * id + 1] = 0ull;
+    }
+    if (id == 0) tl[4 * TL_N] += 1ull;
+}
+
 // Exclusive prefix sum of count[0..n) into out[0..n], out[n] = total, in ONE pass: tiles are handed out in order, every
 // tile publishes its sum and then its inclusive prefix in a 64-bit status word, and looks back over the statuses of the
 // tiles before it (decoupled look-back).  The counts are zeroed on the way (the next window starts from zero), and the
@@ -335,6 +360,7 @@ __global__ void __launch_bounds__(TPB) k_scan_lookback(uint32_t* count, uint32_t
                                                        unsigned long long* status, uint32_t n_tiles, Counters* ctr,
                                                        const BigLists big)
 {
+    TlStamp tl_(ctr, TL_SCAN);
     __shared__ uint32_t s_w[TPB / 32];
     __shared__ uint32_t s_tile, s_excl;
     if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scan_tile, 1u);
@@ -456,6 +482,7 @@ __global__ void __launch_bounds__(1024) k_resolve(CandArrays C, const AgentArray
                                                   unsigned long long* best_gkey, uint32_t* claim, InfLog log, double T1,
                                                   uint32_t n_agents, long long* series)
 {
+    TlStamp tl_(A.ctr, TL_RESOLVE);
     const unsigned long long n_all = A.ctr->n_cand;
     if (n_all == 0 || n_all > (unsigned long long) C.cap)
     {
@@ -549,6 +576,7 @@ __global__ void __launch_bounds__(TPB) k_submit(SubmitIn in, uint32_t n, PoolArr
                                                 uint32_t person_base, int32_t loc_origin, double t_now, uint32_t* count,
                                                 Counters* ctr)
 {
+    TlStamp tl_(ctr, TL_SUBMIT);
     const uint32_t base = blockIdx.x * (TPB * IPT) + threadIdx.x;
     const double inf = bits_f64(0x7ff0000000000000ull);
     // the block's slots in the fresh pool: its cursor lives on the device (one atomic per block)
@@ -894,6 +922,7 @@ int32_t sync_counters(heros_handle h)
     {
         h->carry_ub = (size_t) h->h_ctr->n_carry;
         h->fresh_ub = (size_t) h->h_ctr->n_fresh;
+        for (bool& p : h->keep_pending) p = false;  // nothing in flight can know better
     }
     // compartment counts at the end of every window finished since the last fetch (the ring holds SERIES_RING of them)
     const size_t done = (size_t) h->h_ctr->windows;
@@ -982,6 +1011,25 @@ int32_t window_begin(heros_handle h, double T1)
     h->win_launches = 0;
     h->n_guest = 0;
     { const int32_t rc_ = join_submissions(h); if (rc_ != HEROS_OK) return rc_; }
+    // the fill of the carry pool after the latest window whose count has reached the host, plus what was submitted since
+    {
+        // a host that runs ahead is held back here until the count of the window before the last has arrived: two
+        // windows of work stay queued on the device, and the bound never lags by more than two windows' submissions
+        for (int k = 0; k < WIN_RING; ++k)
+            if (h->keep_pending[k] && h->keep_seq[k] + 1 == h->win_seq) CU(h, cudaEventSynchronize(h->ev_keep[k]));
+        int best = -1;
+        for (int k = 0; k < WIN_RING; ++k)
+            if (h->keep_pending[k] && (best < 0 || h->keep_seq[k] > h->keep_seq[best]) && cudaEventQuery(h->ev_keep[k]) == cudaSuccess)
+                best = k;
+        if (best >= 0)
+        {
+            const size_t bound = (size_t) h->h_keep[best] + (size_t) (h->fresh_cum - h->keep_cum[best]);
+            if (bound < h->carry_ub) h->carry_ub = bound;
+            for (int k = 0; k < WIN_RING; ++k)
+                if (h->keep_pending[k] && h->keep_seq[k] <= h->keep_seq[best]) h->keep_pending[k] = false;
+        }
+        cudaGetLastError();  // cudaErrorNotReady of the queries is not an error
+    }
     // bounds that were never made exact keep growing: refresh them before they get silly (a cheap, rare round trip)
     if (h->carry_ub > 4 * std::max<size_t>(h->fresh_seen, 1u << 20) || h->series_t.size() - h->series_fetched >= (size_t) SERIES_RING - 1)
     {
@@ -1030,19 +1078,20 @@ int32_t window_transmit(heros_handle h)
         CU(h, cudaMemsetAsync(h->scan_status.p, 0, h->scan_status.n * 8, s));
     }
     CU(h, h->rec.ensure(n_total));
+    CU(h, h->rec_part.ensure(n_total));
     const GuestArrays G{h->g_gid.p, h->g_view.p, h->g_key.p, h->g_tin.p, h->g_tout.p, h->g_rank.p, h->n_guest};
     const size_t list_cap = (size_t) n_total / 32 + 16;
     const size_t occupied_cap = std::min<size_t>(n_keys, n_total) + 16;
     CU(h, h->sub_seg[0].ensure(occupied_cap));
     CU(h, h->sub_seg[1].ensure((size_t) n_total / 9 + 16));  // sub-locations of 9..32 stays
     for (auto& b : h->hot_seg) CU(h, b.ensure(list_cap));
-    for (auto& b : h->hot_run) CU(h, b.ensure(list_cap));
     CU(h, h->huge_off.ensure(list_cap));
     // exact bounds: a sub-location has at most one evaluation per movement event (two per stay), and one work item per
     // 32 evaluations (rounded up per hot sub-location)
     const size_t tab_cap = 2 * (size_t) n_total + 64, item_cap = (size_t) n_total / 8 + 1024;
     CU(h, h->tab_now.ensure(tab_cap)); CU(h, h->tab_dur.ensure(tab_cap)); CU(h, h->tab_head.ensure(tab_cap));
     CU(h, h->item_key.ensure(item_cap)); CU(h, h->item_tab.ensure(item_cap)); CU(h, h->item_cnt.ensure(item_cap));
+    CU(h, h->item_nill.ensure(item_cap)); CU(h, h->item_nsus.ensure(item_cap));
     // global scratch of the sub-locations too large for shared memory (> 8192 movement events): 42 B per stay + 82 KB
     // per such sub-location (each holds > 4096 stays), and 4 B per stay of a total-branch location
     CU(h, h->scratch.ensure(std::min<size_t>(72 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
@@ -1051,7 +1100,6 @@ int32_t window_transmit(heros_handle h)
     for (int k = 0; k < N_HOT; ++k) big.hot_seg[k] = h->hot_seg[k].p;
     big.hot_cap = (uint32_t) h->hot_seg[0].n;
     for (int k = 1; k < N_HOT; ++k) big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, h->hot_seg[k].n);
-    for (int k = 0; k < N_HOT; ++k) big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, h->hot_run[k].n);
     big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, 0x7fffffffu);
     big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
     big.key_total = h->n_total_loc ? h->d_key_total.p : nullptr;
@@ -1067,6 +1115,19 @@ int32_t window_transmit(heros_handle h)
         h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p);
     k_window_roll<<<1, 32, 0, s>>>(h->d_ctr.p);
     CU(h, cudaEventRecord(h->ev_rolled, s));  // k_submit of the next window may run from here on, beside the transmission
+    {
+        // n_carry (= what outlived this window) to the host, beside the transmission stage.  Should the copy be late and
+        // read the count of a later window, the bound computed from it is still an upper bound (it adds the fresh stays
+        // of the windows in between once more).
+        const int k = h->win_ring;
+        h->fresh_cum += (uint64_t) h->fresh_ub;
+        CU(h, cudaStreamWaitEvent(h->meta_stream, h->ev_rolled, 0));
+        CU(h, cudaMemcpyAsync(h->h_keep + k, &h->d_ctr.p->n_carry, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->meta_stream));
+        CU(h, cudaEventRecord(h->ev_keep[k], h->meta_stream));
+        h->keep_pending[k] = true;
+        h->keep_seq[k] = ++h->win_seq;
+        h->keep_cum[k] = h->fresh_cum;
+    }
     CU(h, cudaEventRecord(we.scattered, s));
     launches += 3;
     // the pools as the host sees them from now on: everything that may have outlived the window is in the other carry pool
@@ -1084,25 +1145,26 @@ int32_t window_transmit(heros_handle h)
     c.view = h->d_view.p; c.ill_end = h->d_ill_end.p; c.guest_ill_end = h->g_ill_end.p;
     c.person_base = h->person_base; c.n_agents = N;
     c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
-    c.rec = h->rec.p; c.seg_start = h->seg_start.p;
+    c.rec = h->rec.p; c.rec_part = h->rec_part.p; c.seg_start = h->seg_start.p;
     c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) std::min<size_t>(std::min(std::min(h->cand_person.n, h->cand_gkey.n), std::min(h->cand_t.n, h->cand_p.n)), 0xFFFFFFFFu);
     c.best_t = h->d_best_t.p;
     for (int k = 0; k < 2; ++k) c.sub_seg[k] = h->sub_seg[k].p;
     for (int k = 0; k < 2; ++k) c.sub_cap[k] = (uint32_t) h->sub_seg[k].n;
-    for (int k = 0; k < N_HOT; ++k) { c.hot_seg[k] = h->hot_seg[k].p; c.hot_run[k] = h->hot_run[k].p; }
+    for (int k = 0; k < N_HOT; ++k) c.hot_seg[k] = h->hot_seg[k].p;
     c.hot_cap = big.hot_cap;
     c.tab_now = h->tab_now.p; c.tab_dur = h->tab_dur.p; c.tab_head = h->tab_head.p;
     c.tab_cap = std::min(std::min(h->tab_now.n, h->tab_dur.n), h->tab_head.n);
     c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_cnt = h->item_cnt.p;
-    c.item_cap = std::min(std::min(h->item_key.n, h->item_tab.n), h->item_cnt.n);
+    c.item_nill = h->item_nill.p; c.item_nsus = h->item_nsus.p;
+    c.item_cap = std::min(std::min(std::min(h->item_key.n, h->item_tab.n), h->item_cnt.n), std::min(h->item_nill.n, h->item_nsus.n));
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
     TransmitStreams ts{};
     ts.main = s;
     for (int k = 0; k < N_AUX; ++k) { ts.aux[k] = h->aux[k]; ts.join[k] = we.join[k]; }
-    ts.fork = we.fork; ts.mid = we.mid; ts.filtered = we.filtered;
+    ts.fork = we.fork; ts.mid = we.mid;
     launch_transmit(c, h->n_sm, ts, launches);
     CU(h, cudaEventRecord(we.transmitted, s));
     CU(h, cudaGetLastError());
@@ -1137,6 +1199,7 @@ int32_t window_finish(heros_handle h)
     CU(h, cudaLaunchCooperativeKernel((const void*) k_resolve, dim3(h->resolve_grid), dim3(1024), args, 0, s));
     h->win_launches += 1;
     CU(h, cudaEventRecord(we.resolved, s));
+    if (h->d_timeline.p) k_timeline_fold<<<1, 32, 0, s>>>(h->d_timeline.p);
     CU(h, cudaGetLastError());
     we.pending = true;
     h->launches_total += h->win_launches;
@@ -1198,6 +1261,10 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->sub_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&h->meta_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (auto& ev : h->ev_keep)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    if ((e = cudaMallocHost(&h->h_keep, sizeof(unsigned long long) * WIN_RING)) != cudaSuccess) return bail("pinned counters", e);
     for (auto& a : h->aux)
         if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     for (auto& ev : h->ev)
@@ -1254,7 +1321,7 @@ int32_t heros_destroy(heros_handle h)
     h->item_key.release(); h->item_tab.release(); h->item_cnt.release();
     h->tab_now.release(); h->tab_dur.release(); h->tab_head.release();
     for (auto& b : h->hot_seg) b.release();
-    for (auto& b : h->hot_run) b.release();
+    h->rec_part.release(); h->item_nill.release(); h->item_nsus.release(); h->d_timeline.release();
     h->huge_off.release(); h->scratch.release();
     h->s_closure.release(); h->s_loc_type.release(); h->m_times.release(); h->m_sub.release(); h->m_loc.release();
     h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();
@@ -1265,6 +1332,9 @@ int32_t heros_destroy(heros_handle h)
         if (h->xc.opened[d]) cudaIpcCloseMemHandle(h->xc.peer[d]);
     if (h->xc.region) cudaFree(h->xc.region);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_keep) cudaFreeHost(h->h_keep);
+    for (auto& ev : h->ev_keep) if (ev) cudaEventDestroy(ev);
+    if (h->meta_stream) cudaStreamDestroy(h->meta_stream);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {h->ev_rolled, h->ev_submitted, h->ev_copied, h->ev_stage_free[0], h->ev_stage_free[1]})
         if (ev) cudaEventDestroy(ev);
@@ -1416,6 +1486,8 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     { const int32_t rc_ = sync_counters(h); if (rc_ != HEROS_OK) return rc_; }
     d_age.release(); d_female.release(); d_role.release();
     h->fresh_ub = h->carry_ub = 0; h->t_now = 0.0; h->win_state = 0;
+    cudaStreamSynchronize(h->meta_stream);
+    for (bool& p : h->keep_pending) p = false;
     if (h->bk_count.p) CU(h, cudaMemsetAsync(h->bk_count.p, 0, h->bk_count.n * 4, h->stream));  // tickets of dropped stays
     h->series_t.clear(); h->series_counts.clear(); h->series_fetched = 0;
     h->o_inf_n = h->o_tr_n = ~0ull;  // the event logs start again: the sorted output caches are stale
@@ -2014,6 +2086,44 @@ int32_t heros_get_phase_clocks(heros_handle h, uint64_t* clocks)
     // development aid of the former group kernels; kept in the ABI, reports nothing
     if (!h || !clocks) return HEROS_ERR_INVALID;
     memset(clocks, 0, 64 * sizeof(uint64_t));
+    return HEROS_OK;
+}
+
+int32_t heros_debug_timeline(heros_handle h, int32_t enable, double* start_us, double* end_us, int64_t* n_windows)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = check_idle(h, "heros_debug_timeline");
+    if (rc != HEROS_OK) return rc;
+    if ((rc = sync_counters(h)) != HEROS_OK) return rc;
+    constexpr size_t WORDS = 4 * TL_N + 1 + TL_N;
+    std::vector<unsigned long long> host(WORDS, 0ull);
+    if (h->d_timeline.p && (start_us || end_us || n_windows))
+    {
+        CU(h, cudaMemcpy(host.data(), h->d_timeline.p, WORDS * 8, cudaMemcpyDeviceToHost));
+        const long long* acc = reinterpret_cast<const long long*>(host.data() + 2 * TL_N);
+        for (int k = 0; k < TL_N; ++k)
+        {
+            const double runs = (double) host[4 * TL_N + 1 + k];
+            if (start_us) start_us[k] = runs > 0 ? 1e-3 * (double) acc[2 * k] / runs : -1.0;
+            if (end_us) end_us[k] = runs > 0 ? 1e-3 * (double) acc[2 * k + 1] / runs : -1.0;
+        }
+        if (n_windows) *n_windows = (int64_t) host[4 * TL_N];
+    }
+    else if (n_windows)
+        *n_windows = 0;
+    unsigned long long* dev = nullptr;
+    if (enable)
+    {
+        CU(h, h->d_timeline.ensure(WORDS));
+        for (int k = 0; k < TL_N; ++k) { host[2 * k] = ~0ull; host[2 * k + 1] = 0ull; }
+        for (size_t k = 2 * TL_N; k < WORDS; ++k) host[k] = 0ull;
+        CU(h, cudaMemcpy(h->d_timeline.p, host.data(), WORDS * 8, cudaMemcpyHostToDevice));
+        dev = h->d_timeline.p;
+    }
+    else
+        h->d_timeline.release();
+    CU(h, cudaMemcpy(&h->d_ctr.p->timeline, &dev, sizeof dev, cudaMemcpyHostToDevice));
     return HEROS_OK;
 }
 

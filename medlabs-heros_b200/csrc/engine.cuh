@@ -69,6 +69,20 @@ __device__ __forceinline__ void st_rec(StayRec* p, const StayRec& r)
 }
 #endif
 
+// ---- heros_debug_timeline: when and for how long every kernel of a window actually ran (the kernels of the transmission
+// stage run side by side on several streams; CUDA events only give the end of each stream's work) ----
+enum TlId { TL_OPEN = 0, TL_SCAN, TL_SCATTER, TL_ROLL, TL_STREAM, TL_SUB8, TL_SUB32, TL_CHAIN0, TL_CHAIN1, TL_CHAIN2, TL_EVAL,
+            TL_TOTAL, TL_RESOLVE, TL_SUBMIT, TL_ADVANCE, TL_RATE, TL_N = 32 };
+#ifdef __CUDACC__
+struct Counters;
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
 // device-side counters of one engine.  The block from `n_cand` on is zeroed at the start of every window.
@@ -97,12 +111,13 @@ struct Counters
     unsigned long long hot_total;    // sub-locations handed to the hot path, summed over the windows
     unsigned long long cand_total;   // candidate infections kept, summed over the windows
     unsigned long long rate_draws;   // draws of the rate-based locations (LocationProbBased)
-    unsigned long long reserved_[4];
+    unsigned long long* timeline;    // heros_debug_timeline: per kernel {first block start, last block end} (globaltimer ns), or NULL
+    unsigned long long reserved_[3];
     // ---- per window ----
     unsigned long long n_cand;       // candidate infections of the current window (first field of the window block)
     unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
     unsigned long long n_hot[N_HOT]; // sub-locations of > 32 stays, by class (queued by the prefix-sum kernel)
-    unsigned long long n_run[N_HOT]; // ... of which the filter kernel passed on to the chain kernel
+    unsigned long long reserved_run[N_HOT];
     unsigned long long scratch_top;  // bump allocator for the global scratch of huge segments (bytes)
     unsigned long long n_keep;       // stays kept in the pool after the window
     unsigned long long n_seg;        // occupied sub-locations of the current window
@@ -111,6 +126,23 @@ struct Counters
     unsigned long long tab_top;      // entries of the table of evaluations of the hot sub-locations
     unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
 };
+#ifdef __CUDACC__
+// thread 0 of every block stamps the kernel's entry when it starts and when it leaves the kernel (any return path)
+struct TlStamp
+{
+    unsigned long long* tl;
+    __device__ __forceinline__ TlStamp(const Counters* ctr, int id) : tl(nullptr)
+    {
+        if (threadIdx.x == 0)
+        {
+            unsigned long long* p = ctr->timeline;
+            if (p) { tl = p + 2 * id; atomicMin(tl, global_ns()); }
+        }
+    }
+    __device__ __forceinline__ ~TlStamp() { if (tl) atomicMax(tl + 1, global_ns()); }
+};
+#endif
+
 template <typename T>
 struct DevBuf
 {
@@ -158,14 +190,18 @@ struct WindowCtx
     unsigned long long* best_t;
     // work lists filled by k_transmit_stream
     uint32_t* sub_seg[2]; uint32_t sub_cap[2];          // sub-location keys queued for the sub-warp kernels (8 / 32 lanes)
-    // hot sub-locations (> 32 stays): queued by the prefix-sum kernel (hot_seg), passed on by the filter (hot_run)
-    uint32_t* hot_seg[N_HOT]; uint32_t* hot_run[N_HOT]; uint32_t hot_cap;
+    // hot sub-locations (> 32 stays): queued by the prefix-sum kernel
+    uint32_t* hot_seg[N_HOT]; uint32_t hot_cap;
+    // partitioned copy of the hot segments that need evaluations (same offsets as rec): ill stays from the front of a
+    // segment, susceptible ones from its back -- all the evaluation kernel reads
+    StayRec* rec_part;
     unsigned long long* huge_off;  // byte offset into scratch of every entry of hot_seg[HOT_HUGE]
     unsigned char* scratch; unsigned long long scratch_cap;
     // the chain kernel leaves one row per calculated evaluation of a hot sub-location (time, duration, head count) and
     // one work item per 32 of them; the evaluation kernel spreads the items over the whole GPU
     double* tab_now; double* tab_dur; uint32_t* tab_head; unsigned long long tab_cap;
-    uint32_t* item_key; unsigned long long* item_tab; uint32_t* item_cnt; unsigned long long item_cap;
+    uint32_t* item_key; unsigned long long* item_tab; uint32_t* item_cnt; uint32_t* item_nill; uint32_t* item_nsus;
+    unsigned long long item_cap;
     uint32_t flags;
     Counters* ctr;
 };
@@ -208,8 +244,8 @@ __device__ __forceinline__ void queue_big(const BigLists& b, Counters* ctr, uint
 #endif
 
 // the engine stream, the auxiliary streams of the kernels that run side by side, and the fork / join events
-constexpr int N_AUX = 3;  // 0: the hot path (filter, chain kernels of the large classes, evaluation), 1: the 32-lane
+constexpr int N_AUX = 3;  // 0: the hot path (chain kernels of the large classes, evaluation), 1: the 32-lane
                           // sub-warp kernel, 2: the chain kernel of the small class
-struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid, filtered; cudaEvent_t join[N_AUX]; };
+struct TransmitStreams { cudaStream_t main; cudaStream_t aux[N_AUX]; cudaEvent_t fork, mid; cudaEvent_t join[N_AUX]; };
 
 }  // namespace heros

@@ -147,11 +147,21 @@ struct heros_engine
     int carry_cur = 0;
     size_t fresh_ub = 0, carry_ub = 0;   // upper bounds of n_fresh / n_carry
     size_t fresh_seen = 0;               // largest fresh_ub of a window so far
+    // The exact fill of the carry pool after every window travels to the host on its own stream (8 bytes, pinned);
+    // whatever has arrived by the time the next window is enqueued tightens carry_ub -- without it a host that never
+    // waits (heros_step_async back to back) would see the bound, and every buffer sized from it, grow window by window.
+    cudaStream_t meta_stream = nullptr;
+    unsigned long long* h_keep = nullptr;        // pinned, WIN_RING entries
+    cudaEvent_t ev_keep[WIN_RING]{};
+    bool keep_pending[WIN_RING]{};
+    uint64_t keep_seq[WIN_RING]{}, win_seq = 0;
+    uint64_t keep_cum[WIN_RING]{}, fresh_cum = 0;  // fresh stays consumed by the windows enqueued so far (running sum)
 
     // window buffers
     DevBuf<uint32_t> bk_count, bk_rank, seg_start;
     DevBuf<unsigned long long> scan_status;
-    DevBuf<StayRec> rec;
+    DevBuf<StayRec> rec, rec_part;
+    DevBuf<unsigned long long> d_timeline;  // heros_debug_timeline
     int resolve_grid = 0;  // blocks of the cooperative k_resolve launch
 
     // candidates, logs
@@ -166,7 +176,7 @@ struct heros_engine
     size_t series_fetched = 0;    // windows whose counts have been copied into series_counts
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], hot_seg[N_HOT], hot_run[N_HOT], item_key, item_cnt, tab_head;
+    DevBuf<uint32_t> sub_seg[2], hot_seg[N_HOT], item_key, item_cnt, item_nill, item_nsus, tab_head;
     DevBuf<unsigned long long> item_tab;
     DevBuf<double> tab_now, tab_dur;
     DevBuf<unsigned long long> huge_off;

@@ -165,6 +165,7 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
         }
         at += padded(p.bytes);
     }
+    s.ctr.timeline = h->d_timeline.p;  // a device pointer of the engine that took the snapshot means nothing here
     CU(h, cudaMemcpyAsync(h->d_ctr.p, &s.ctr, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
     if (s.n_policy)
     {
@@ -184,6 +185,8 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
     CU(h, cudaStreamSynchronize(h->stream));
     h->closure_active = s.closure_active != 0;
     h->fresh_ub = s.n_fresh; h->carry_ub = s.n_carry; h->t_now = s.t_now; h->invalid_reported = s.invalid_reported;
+    cudaStreamSynchronize(h->meta_stream);
+    for (bool& p : h->keep_pending) p = false;
     h->series_fetched = s.n_series;
     h->n_guest = 0;
     h->o_inf_n = h->o_tr_n = ~0ull;  // the sorted output caches are stale

@@ -9,30 +9,31 @@
 // calculated evaluation is >= the threshold, over the occupants S(t-) = { stays : t_in < t <= t_out }.
 //
 // Input: the window's stays sorted by sub-location key (one contiguous segment per occupied sub-location).
-//   k_transmit_stream : a WARP per 32 consecutive sub-location keys streams their (contiguous) records once with
-//                       coalesced 128-bit loads and reduces, per sub-location, who is there and the two latest event
-//                       times (match / redux over the lanes that hold records of the same sub-location).  Where nobody
-//                       can be infected (no ill or no susceptible occupant -- the vast majority) only lastCalculation
-//                       has to advance; the other sub-locations of <= 32 stays are queued for the sub-warp kernels.
+//   k_transmit_stream : a thread per sub-location key walks its (contiguous, 32-byte) records once and finds who is
+//                       there and the two latest event times.  Where nobody can be infected (no ill or no susceptible
+//                       occupant -- the vast majority) only lastCalculation has to advance; the other sub-locations of
+//                       <= 32 stays are queued for the sub-warp kernels.
 //   k_transmit_sub    : 8 or 32 lanes per queued segment (<= 8 / 9..32 stays): the lanes walk the chain of calculated
 //                       evaluations together (REDUX), then every lane computes ONE evaluation of the chain -- the long
 //                       dependent fp64 chains (sqrt, exp) of up to 32 evaluations run side by side -- then lane = stay
 //                       for the draws
-// The hot path, sub-locations of > 32 stays (supermarkets, parks, lecture halls ...), in three steps so that the
-// latency of the largest sub-location is not the latency of the stage:
-//   k_hot_filter      : one warp per hot sub-location: the same early-out
-//   k_hot_chain       : one thread block per remaining sub-location orders its movement events in shared memory
-//                       (counting sort into time buckets), finds the successor of every event (the earliest later
-//                       event not closer than the threshold: three buckets to look at), materialises the chain of
-//                       calculated evaluations by pointer doubling and leaves one row per evaluation (time, duration,
-//                       head count) plus one work item per 32 evaluations
-//   k_hot_eval        : one thread block per work item, spread over the whole GPU: the records of the sub-location are
+// The hot path, sub-locations of > 32 stays (supermarkets, parks, lecture halls ...), in two steps so that the latency
+// of the largest sub-location is not the latency of the stage:
+//   k_hot_chain       : one thread block per hot sub-location: the same early-out first; where evaluations are needed
+//                       the ill and the susceptible stays are copied into a partitioned segment, the movement events are
+//                       ordered in shared memory (counting sort into time buckets), the successor of every event is
+//                       found (the earliest later event not closer than the threshold: three buckets to look at), the
+//                       chain of calculated evaluations is materialised by pointer doubling and one row per evaluation
+//                       (time, duration, head count) plus one work item per 32 evaluations is left
+//   k_hot_eval        : one thread block per work item, spread over the whole GPU: the ILL stays of the sub-location are
 //                       streamed through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, two tiles in
 //                       flight); lane = evaluation; every ill stay overlapping the item is broadcast and each lane adds
-//                       its term to a 128-bit fixed-point sum in registers (order-independent, no atomics); then every
-//                       susceptible stay is broadcast for the Philox draws
+//                       its term to a 128-bit fixed-point sum in registers (order-independent, no atomics); then the
+//                       threads take the SUSCEPTIBLE stays, one each, for the Philox draws
 //   k_transmit_total  : one block per location of the total-location branch (TArea:198-246 / TDist:189-246)
 // Output: candidate infections (person, key, time, p); engine.cu keeps the earliest per person.
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace heros {
@@ -176,137 +177,65 @@ __device__ __forceinline__ bool stay_before(uint32_t pa, double ta, uint32_t pb,
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// one warp per 32 consecutive sub-location keys
+// one thread per sub-location key
 // ------------------------------------------------------------------------------------------------------------------
-// The records of 32 consecutive keys are contiguous in bucket order, so the warp reads them with coalesced 256-bit
-// loads (a record is one 32-byte sector: 1 KB per warp and load, all of it used).  The lane that holds a record finds
-// the key it belongs to by a binary search over the 32 segment ends (shuffles); the lanes holding records of the same
-// key are neighbours, so who is there and the two latest distinct event times follow from one segmented scan over the
-// lanes (five shuffle steps; times are non-negative doubles, so their bit patterns order as integers; 0 = none) whose
-// result the last lane of every segment adds to the key's entry in shared memory.  (match.any + redux over the groups
-// would look shorter, but redux with masks that differ from lane to lane is executed once per distinct mask.)
+// A record is one 32-byte sector and the records of consecutive keys are contiguous in bucket order, so the threads of
+// a warp walk neighbouring sectors: every sector that is fetched is used completely, and the independent loads of the
+// (unrolled) walk are in flight together.  Measured against a warp-cooperative form (coalesced 1 KB loads + a segmented
+// scan over the lanes to find who is in which sub-location: 0.105 ms at Hague size) this form takes a third of the time:
+// the stream is bound by instruction issue, not by sectors, and the thread form issues the fewest.
 // Segments of > 32 stays (the hot path) and of total-branch locations are skipped without being read.
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
 {
-    __shared__ unsigned long long s_m1[8][32], s_m2[8][32];
-    __shared__ uint32_t s_fl[8][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    TlStamp tl_(c.ctr, TL_STREAM);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    const uint32_t n_groups = (c.n_keys + 31u) >> 5;
     unsigned occupied = 0;
 
-    for (uint32_t g = warp; g < n_groups; g += n_warps)
+    for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < c.n_keys; key += gridDim.x * blockDim.x)
     {
-        const uint32_t key = (g << 5) + (uint32_t) lane;
-        const bool in_table = key < c.n_keys;
-        const uint32_t a = c.seg_start[in_table ? key : c.n_keys];
-        const uint32_t e = c.seg_start[in_table ? key + 1 : c.n_keys];  // segment ends: non-decreasing over the lanes
-        const uint32_t n = e - a;
-        const bool skip = n > 32 || (n > 0 && c.key_total && c.key_total[key]);
-        occupied += n > 0 ? 1u : 0u;
-        s_m1[wib][lane] = 0ull; s_m2[wib][lane] = 0ull; s_fl[wib][lane] = 0u;
-        __syncwarp();
-        const unsigned skip_mask = __ballot_sync(FULL, skip);
-        // runs of lanes between skipped segments: their records are one contiguous range
-        int first = 0;
-        while (first < 32)
+        const uint32_t a = c.seg_start[key], b = c.seg_start[key + 1];
+        const uint32_t n = b - a;
+        if (n == 0) continue;
+        ++occupied;
+        if (n > 32) continue;  // queued for the hot path by the prefix-sum kernel
+        if (c.key_total && c.key_total[key]) continue;  // evaluated per location by k_transmit_total
+        const StayRec* rec = c.rec + a;
+        // who is here, and the two latest events
+        bool any_ill = false, any_sus = false;
+        Top2 top;
+        top.init();
+#pragma unroll 4
+        for (uint32_t j = 0; j < n; ++j)
         {
-            const unsigned after = first < 32 ? (skip_mask & ~((1u << first) - 1u)) : 0u;
-            const int last = after ? __ffs(after) - 1 : 32;  // lanes [first, last) form the run
-            if (last > first)
-            {
-                const uint32_t lo = __shfl_sync(FULL, a, first), hi = __shfl_sync(FULL, e, last - 1);
-                for (uint32_t b0 = lo; b0 < hi; b0 += 32)
-                {
-                    const uint32_t i = b0 + (uint32_t) lane;
-                    const bool valid = i < hi;
-                    unsigned long long x = 0ull, y = 0ull;
-                    uint32_t fl = 0u;
-                    if (valid)
-                    {
-                        const StayRec r = ld_rec(c.rec + i);
-                        const double tin = r.tin, tout = r.tout;
-                        const uint32_t tph = view_tphase(r.view);
-                        fl = (phase_is_ill(tph) ? 1u : 0u) | (phase_is_susceptible(tph) ? 2u : 0u);
-                        if (tout >= c.T0 && tout < c.T1) x = f64_bits(tout);
-                        if (both && tin >= c.T0 && tin < c.T1) y = f64_bits(tin);  // t_in < t_out: y < x whenever both are set
-                        if (y > x) { const unsigned long long t = x; x = y; y = t; }
-                    }
-                    // owner = number of segment ends <= i (a binary search over the lanes)
-                    int owner = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1)
-                    {
-                        const uint32_t v = __shfl_sync(FULL, e, owner + step - 1);
-                        if (v <= i) owner += step;
-                    }
-                    // segmented inclusive scan over the lanes (records of a key sit in neighbouring lanes): the two latest
-                    // distinct times (m1 > m2) and the flags of the key's records up to this lane
-                    if (!valid) owner = 64 + lane;
-                    unsigned long long m1 = x, m2 = y;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const int own_up = __shfl_up_sync(FULL, owner, o);
-                        const unsigned long long u1 = __shfl_up_sync(FULL, m1, o), u2 = __shfl_up_sync(FULL, m2, o);
-                        const uint32_t uf = __shfl_up_sync(FULL, fl, o);
-                        if (lane >= o && own_up == owner)
-                        {
-                            fl |= uf;
-                            if (u1 > m1) { m2 = m1 > u2 ? m1 : u2; m1 = u1; }
-                            else if (u1 == m1) { m2 = m2 > u2 ? m2 : u2; }
-                            else { m2 = m2 > u1 ? m2 : u1; }
-                        }
-                    }
-                    const int own_next = __shfl_down_sync(FULL, owner, 1);
-                    if (valid && (lane == 31 || own_next != owner))
-                    {
-                        // the last lane of the key in this batch: merge into the key's entry (a segment may span two batches)
-                        unsigned long long a1 = s_m1[wib][owner], a2 = s_m2[wib][owner];
-                        if (m1 > a1) { a2 = a1 > m2 ? a1 : m2; a1 = m1; }
-                        else if (m1 == a1) { a2 = a2 > m2 ? a2 : m2; }
-                        else { a2 = a2 > m1 ? a2 : m1; }
-                        s_m1[wib][owner] = a1; s_m2[wib][owner] = a2; s_fl[wib][owner] |= fl;
-                    }
-                    __syncwarp();
-                }
-            }
-            first = last + 1;
+            const StayRec r = ld_rec(rec + j);
+            const uint32_t tph = view_tphase(r.view);
+            any_ill |= phase_is_ill(tph);
+            any_sus |= phase_is_susceptible(tph);
+            if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
+            if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
         }
-        __syncwarp();
-        if (n > 0 && !skip)
+        if (!(top.m1 > neg_inf())) continue;  // no movement in this window
+        const bool need_eval = any_ill && any_sus;
+        if (!need_eval && !exact)
         {
-            const unsigned long long b1 = s_m1[wib][lane], b2 = s_m2[wib][lane];
-            if (b1 != 0ull)  // a movement in this window
+            double L;
+            if (advance_only(top, c.last_calc[key], thr, L))
             {
-                const bool need_eval = s_fl[wib][lane] == 3u;
-                bool done = false;
-                if (!need_eval && !exact)
-                {
-                    Top2 top;
-                    top.m1 = bits_f64(b1);
-                    top.m2 = b2 ? bits_f64(b2) : neg_inf();
-                    double L;
-                    if (advance_only(top, c.last_calc[key], thr, L)) { c.last_calc[key] = L; done = true; }
-                }
-                if (!done)
-                {
-                    // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
-                    const int which = n > THREAD_SLOW_MAX ? 1 : 0;
-                    const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
-                    if (slot < c.sub_cap[which]) c.sub_seg[which][slot] = key;
-                    else atomicOr(&c.ctr->overflow, 2u);
-                }
+                c.last_calc[key] = L;
+                continue;
             }
         }
-        __syncwarp();
+        // everything else: the sub-warp kernels (8 lanes per sub-location of <= 8 stays, 32 lanes otherwise)
+        const int which = n > THREAD_SLOW_MAX ? 1 : 0;
+        const unsigned long long slot = atomicAdd(&c.ctr->n_sub[which], 1ull);
+        if (slot < c.sub_cap[which]) c.sub_seg[which][slot] = key;
+        else atomicOr(&c.ctr->overflow, 2u);
     }
     occupied = __reduce_add_sync(FULL, occupied);
-    if (lane == 0 && occupied)
+    if ((threadIdx.x & 31) == 0 && occupied)
     {
         atomicAdd(&c.ctr->n_seg, (unsigned long long) occupied);
         atomicAdd(&c.ctr->seg_total, (unsigned long long) occupied);
@@ -318,6 +247,7 @@ __global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
 template <int MODEL, int S>
 __global__ void __launch_bounds__(256, 4) k_transmit_sub(const WindowCtx c)
 {
+    TlStamp tl_(c.ctr, S == 8 ? TL_SUB8 : TL_SUB32);
     constexpr int GPW = 32 / S;  // groups per warp
     __shared__ StayRec s_rec[8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -590,67 +520,6 @@ __device__ void group_suffix_min(int n, F f, T* out, int* s_w)
 // the hot path: sub-locations of > 32 stays
 // ------------------------------------------------------------------------------------------------------------------
 
-// One warp per hot sub-location: who is here and the two latest events.  Where nobody can be infected only
-// lastCalculation has to advance (usually most of them); the others are passed on to the chain kernel of their class.
-template <int MODEL>
-__global__ void __launch_bounds__(256) k_hot_filter(const WindowCtx c)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
-    const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
-    const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
-    uint32_t first[N_HOT + 1];
-    first[0] = 0;
-    for (int k = 0; k < N_HOT; ++k) first[k + 1] = first[k] + (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_hot[k]);
-    if (warp == 0 && lane == 0) atomicAdd(&c.ctr->hot_total, (unsigned long long) first[N_HOT]);
-    for (uint32_t i = warp; i < first[N_HOT]; i += n_warps)
-    {
-        int cls = 0;
-        while (i >= first[cls + 1]) ++cls;
-        const uint32_t w = i - first[cls];
-        const uint32_t key = c.hot_seg[cls][w];
-        if (key == KEY_NONE) continue;
-        const uint32_t a = c.seg_start[key], n = c.seg_start[key + 1] - a;
-        int ill = 0, sus = 0;
-        Top2 top;
-        top.init();
-        for (uint32_t v = lane; v < n; v += 32)
-        {
-            const StayRec r = ld_rec(c.rec + a + v);
-            const double tin = r.tin, tout = r.tout;
-            const uint32_t tph = view_tphase(r.view);
-            ill |= phase_is_ill(tph);
-            sus |= phase_is_susceptible(tph);
-            if (tout >= c.T0 && tout < c.T1) top.add(tout);
-            if (both && tin >= c.T0 && tin < c.T1) top.add(tin);
-        }
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
-            top.merge(o1, o2);
-        }
-        const bool need_eval = __any_sync(FULL, ill) && __any_sync(FULL, sus);
-        if (!(top.m1 > neg_inf())) continue;  // no movement in this window
-        if (!need_eval && !exact)
-        {
-            double L;
-            if (advance_only(top, c.last_calc[key], thr, L))
-            {
-                if (lane == 0) c.last_calc[key] = L;
-                continue;
-            }
-        }
-        if (lane == 0)
-        {
-            const unsigned long long slot = atomicAdd(&c.ctr->n_run[cls], 1ull);  // <= n_hot[cls] <= hot_cap
-            // bit 31 of the entry index is free (lists hold < 2^31 entries): the run list keeps the index into hot_seg
-            // (the huge class needs it for its scratch offset) -- the key is looked up again by the chain kernel
-            c.hot_run[cls][slot] = w | (need_eval ? 0x80000000u : 0u);
-        }
-    }
-}
-
 namespace {
 
 template <int CLS> struct HotCfg;
@@ -680,29 +549,88 @@ template <int CLS> __host__ __device__ constexpr size_t hot_smem_bytes()
 template <int MODEL, int CLS>
 __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
 {
+    TlStamp tl_(c.ctr, TL_CHAIN0 + CLS);
     using Cfg = HotCfg<CLS>;
     using idx_t = typename Cfg::idx_t;
     constexpr int G = Cfg::T;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_w[33];
     __shared__ unsigned long long s_base[2];
+    __shared__ double s_top[2][32];
+    __shared__ int s_cnt[2];
     const int tid = threadIdx.x;
-    const uint32_t n_list = (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_run[CLS]);
+    const uint32_t n_list = (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_hot[CLS]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
     const bool both = c.trigger == HEROS_TRIGGER_ENTER_AND_EXIT;
     const bool need_enters = both || MODEL == HEROS_MODEL_DISTANCE;
+    const bool exact = (c.flags & HEROS_FLAG_EXACT_STATS) != 0;
     Local st;
+    if (blockIdx.x == 0 && tid == 0 && n_list) atomicAdd(&c.ctr->hot_total, (unsigned long long) n_list);
 
-    for (uint32_t wi = blockIdx.x; wi < n_list; wi += gridDim.x)
+    for (uint32_t w = blockIdx.x; w < n_list; w += gridDim.x)
     {
-        const uint32_t entry = c.hot_run[CLS][wi];
-        const bool need_eval = (entry & 0x80000000u) != 0;
-        const uint32_t w = entry & 0x7fffffffu;
         const uint32_t key = c.hot_seg[CLS][w];
+        if (key == KEY_NONE) continue;  // no scratch left for it (the overflow bit is set)
         const uint32_t a = c.seg_start[key];
         const int n = (int) (c.seg_start[key + 1] - a);
         const StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
+        // 0. who is here, and the two latest movement events.  Where nobody can be infected (the majority while the
+        //    prevalence is low) only lastCalculation has to advance; that usually follows from those two times alone.
+        int n_ill = 0, n_sus = 0;
+        {
+            Top2 top;
+            top.init();
+            for (int v = tid; v < n; v += G)
+            {
+                const StayRec r = ld_rec(rec + v);
+                const uint32_t tph = view_tphase(r.view);
+                n_ill += phase_is_ill(tph) ? 1 : 0;
+                n_sus += phase_is_susceptible(tph) ? 1 : 0;
+                if (r.tout >= c.T0 && r.tout < c.T1) top.add(r.tout);
+                if (both && r.tin >= c.T0 && r.tin < c.T1) top.add(r.tin);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double o1 = __shfl_xor_sync(FULL, top.m1, o), o2 = __shfl_xor_sync(FULL, top.m2, o);
+                top.merge(o1, o2);
+            }
+            __syncthreads();  // the previous sub-location is finished with the shared arrays
+            if ((tid & 31) == 0) { s_top[0][tid >> 5] = top.m1; s_top[1][tid >> 5] = top.m2; }
+            n_ill = group_sum<G>(n_ill, s_w);
+            n_sus = group_sum<G>(n_sus, s_w);
+            __syncthreads();
+#pragma unroll 1
+            for (int q = 0; q < (G >> 5); ++q) top.merge(s_top[0][q], s_top[1][q]);
+            if (!(top.m1 > neg_inf())) continue;  // no movement in this window (the same in every thread)
+            if (!(n_ill > 0 && n_sus > 0) && !exact)
+            {
+                double L;
+                if (advance_only(top, L0, thr, L))
+                {
+                    if (tid == 0) c.last_calc[key] = L;
+                    continue;
+                }
+            }
+        }
+        const bool need_eval = n_ill > 0 && n_sus > 0;
+        if (need_eval)
+        {
+            // the evaluation kernel only ever looks at the ill and the susceptible stays: a partitioned copy of the
+            // segment -- the ill ones from the front, the susceptible ones from the back (their order is free: exposure
+            // sums are formed in fixed point, draws are keyed by person and time)
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+            __syncthreads();
+            StayRec* part = c.rec_part + a;
+            for (int v = tid; v < n; v += G)
+            {
+                const StayRec r = ld_rec(rec + v);
+                const uint32_t tph = view_tphase(r.view);
+                if (phase_is_ill(tph)) st_rec(part + atomicAdd(&s_cnt[0], 1), r);
+                else if (phase_is_susceptible(tph)) st_rec(part + (n - 1 - atomicAdd(&s_cnt[1], 1)), r);
+            }
+        }
         const int slots = need_enters ? 2 * n : n;
         int NB = 32;
         while (NB * 2 < slots && NB < Cfg::NB_CAP) NB <<= 1;
@@ -880,6 +808,8 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             c.item_key[item0 + ch] = key;
             c.item_tab[item0 + ch] = tab0 + 32ull * (unsigned long long) ch;
             c.item_cnt[item0 + ch] = (uint32_t) min(32, R - 32 * ch);
+            c.item_nill[item0 + ch] = (uint32_t) n_ill;
+            c.item_nsus[item0 + ch] = (uint32_t) n_sus;
         }
     }
     flush_stats(c, st, threadIdx.x & 31);
@@ -925,21 +855,25 @@ constexpr int EVAL_STAGES = 2;   // tiles in flight
 
 }  // namespace
 
-// One thread block per work item = up to 32 consecutive calculated evaluations of one hot sub-location; lane k of every
-// warp stands for evaluation k.  The sub-location's records are streamed twice through shared memory, tile by tile, by
-// the bulk-copy engine: first the ill stays that overlap the item's time span are broadcast lane to lane and every lane
-// adds the term of its evaluation (TArea:167-172 / TDist:155-164) to a 128-bit fixed-point sum in registers -- exact
-// integer additions, so neither the order of the stays nor the split over the four warps can change the result; the
-// four partial sums are merged in shared memory, p follows (TArea:182 / TDist:173); then the susceptible stays are
-// broadcast and every lane draws for the pairs (stay present, p > 0) (TArea:190 / TDist:181).
+// One thread block per work item = up to 32 consecutive calculated evaluations of one hot sub-location.
+// 1. Exposure sums, evaluation-parallel: lane k of every warp stands for evaluation k.  The ILL stays of the sub-location
+//    (the front of its partitioned copy) are streamed through shared memory, tile by tile, by the bulk-copy engine
+//    (cp.async.bulk + mbarrier, two tiles in flight); those that overlap the item's time span are broadcast lane to lane
+//    and every lane adds the term of its evaluation (TArea:167-172 / TDist:155-164) to a 128-bit fixed-point sum in
+//    registers -- exact integer additions, so neither the order of the stays nor the split over the four warps can change
+//    the result; the four partial sums are merged in shared memory, p follows (TArea:182 / TDist:173).
+// 2. Draws, stay-parallel: every thread takes SUSCEPTIBLE stays (the back of the partitioned copy, coalesced 32-byte
+//    records) and draws against the evaluations with p > 0 it was present at (TArea:190 / TDist:181).
 template <int MODEL>
 __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
 {
+    TlStamp tl_(c.ctr, TL_EVAL);
     __shared__ __align__(128) StayRec s_tile[EVAL_STAGES][EVAL_TILE];
     __shared__ __align__(8) uint64_t s_bar[EVAL_STAGES];
     __shared__ long long s_hi[EVAL_T / 32][32];
     __shared__ unsigned long long s_lo[EVAL_T / 32][32];
     __shared__ double s_loose[EVAL_T / 32][32];
+    __shared__ double s_now[32], s_p[32];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const unsigned long long n_items = min(c.ctr->n_items, c.item_cap);
     uint32_t parity[EVAL_STAGES];
@@ -954,8 +888,8 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
     __syncthreads();
     Local st;
 
-    // streams the records [0, n) of the segment through the tiles; `body(r, v)` is called by every lane with the record
-    // of its slot (v < n) -- all lanes of a warp call together (v may be >= n: then r is undefined and must be ignored)
+    // streams the records [0, n) through the tiles; `body(r, v)` is called by every lane with the record of its slot
+    // (all lanes of a warp call together; v may be >= n: then r is undefined and must be ignored)
     auto for_each_record = [&](const StayRec* rec, int n, auto&& body) {
         const int n_tiles = (n + EVAL_TILE - 1) / EVAL_TILE;
         auto issue = [&](int j) {
@@ -991,9 +925,10 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         const uint32_t key = c.item_key[it];
         const unsigned long long tab = c.item_tab[it];
         const int cnt = (int) c.item_cnt[it];
+        const int n_ill = (int) c.item_nill[it], n_sus = (int) c.item_nsus[it];
         const uint32_t a = c.seg_start[key];
         const int n = (int) (c.seg_start[key + 1] - a);
-        const StayRec* rec = c.rec + a;
+        const StayRec* part = c.rec_part + a;  // ill stays [0, n_ill), susceptible stays [n - n_sus, n)
         const LocParam lp = c.loc_param[c.key_loc[key]];
         const bool active = lane < cnt;
         const double now = active ? c.tab_now[tab + lane] : pos_inf();
@@ -1014,8 +949,8 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
 
         // 1. exposure sums
         ExactSum acc = exact_zero();
-        for_each_record(rec, n, [&](const StayRec& r, int v) {
-            const bool cand = v < n && phase_is_ill(view_tphase(r.view)) && r.tin < t_last && r.tout >= t_first;
+        for_each_record(part, n_ill, [&](const StayRec& r, int v) {
+            const bool cand = v < n_ill && r.tin < t_last && r.tout >= t_first;
             unsigned m = __ballot_sync(FULL, cand);
             while (m)
             {
@@ -1045,23 +980,48 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         for (int w = 0; w < EVAL_T / 32; ++w) exact_merge(tot, s_hi[w][lane], s_lo[w][lane], s_loose[w][lane]);
         double p = 0.0;
         if (!(active && factor != 0.0 && probability<MODEL>(factor, exact_value(tot), p) && p > 0)) p = 0.0;
-        const unsigned pos = __ballot_sync(FULL, p > 0.0);
-        __syncthreads();  // the partial sums are read: the arrays can be written by the next item
-        if (pos == 0u) continue;  // the same in every warp
+        const unsigned pos = __ballot_sync(FULL, p > 0.0);  // the same in every warp
+        if (wib == 0) { s_now[lane] = now; s_p[lane] = p; }
+        __syncthreads();  // the partial sums are read (the arrays can be written by the next item); s_now / s_p are set
 
         // 2. draws
-        for_each_record(rec, n, [&](const StayRec& r, int v) {
-            const bool cand = v < n && phase_is_susceptible(view_tphase(r.view)) && r.tin < t_last && r.tout >= t_first;
-            unsigned m = __ballot_sync(FULL, cand);
-            while (m)
+        if (pos != 0u)
+        {
+            const StayRec* sus = part + (n - n_sus);
+            constexpr int U = 4;  // records in flight per thread
+            for (int v0 = tid; v0 < n_sus; v0 += U * EVAL_T)
             {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const double q_tin = __shfl_sync(FULL, r.tin, src), q_tout = __shfl_sync(FULL, r.tout, src);
-                const uint32_t q_person = __shfl_sync(FULL, r.person, src);
-                if (p > 0.0 && q_tin < now && now <= q_tout) draw_and_push(c, st, q_person, key, now, p);  // TArea:190 / TDist:181
+                double tin[U], tout[U];
+                uint32_t person[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const int v = v0 + u * EVAL_T;
+                    tin[u] = pos_inf(); tout[u] = neg_inf(); person[u] = 0;
+                    if (v < n_sus)
+                    {
+                        const uint4* q = reinterpret_cast<const uint4*>(sus + v);
+                        const uint4 h0 = __ldg(q);
+                        tin[u] = bits_f64(((uint64_t) h0.y << 32) | h0.x); tout[u] = bits_f64(((uint64_t) h0.w << 32) | h0.z);
+                        person[u] = __ldg(reinterpret_cast<const uint32_t*>(q + 1) + 2);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    if (!(tin[u] < t_last && tout[u] >= t_first)) continue;
+                    unsigned m = pos;
+                    while (m)
+                    {
+                        const int k = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double now_k = s_now[k];
+                        if (tin[u] < now_k && now_k <= tout[u]) draw_and_push(c, st, person[u], key, now_k, s_p[k]);
+                    }
+                }
             }
-        });
+        }
+        __syncthreads();  // s_now / s_p are read
     }
     flush_stats(c, st, lane);
 }
@@ -1127,6 +1087,7 @@ __device__ __forceinline__ double block_min_time(double v, double* s_red)
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
 {
+    TlStamp tl_(c.ctr, TL_TOTAL);
     __shared__ double s_red[256];
     __shared__ long long s_hi[256];
     __shared__ unsigned long long s_lo[256];
@@ -1244,9 +1205,18 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
 // The hot path (its work lists were filled by the prefix-sum kernel) starts at once on the auxiliary streams, side by
 // side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds (they touch disjoint
 // sub-locations); the main stream joins them.
+static int tune(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 template <int MODEL>
 static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts, int& launches)
 {
+    // thread blocks per SM of the kernels that run side by side (development knobs; the defaults are the measured best)
+    static const int stream_bpsm = tune("HEROS_TUNE_STREAM_BPSM", 32), chain0_bpsm = tune("HEROS_TUNE_CHAIN0_BPSM", 8),
+                     eval_bpsm = tune("HEROS_TUNE_EVAL_BPSM", 8);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1260,18 +1230,16 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     cudaStream_t s = ts.main;
     cudaEventRecord(ts.fork, s);
     cudaStreamWaitEvent(ts.aux[0], ts.fork, 0);
-    k_hot_filter<MODEL><<<n_sm * 2, 256, 0, ts.aux[0]>>>(c);
-    cudaEventRecord(ts.filtered, ts.aux[0]);
-    cudaStreamWaitEvent(ts.aux[2], ts.filtered, 0);
+    cudaStreamWaitEvent(ts.aux[2], ts.fork, 0);
     k_hot_chain<MODEL, 1><<<n_sm, HotCfg<1>::T, smem1, ts.aux[0]>>>(c);
     k_hot_chain<MODEL, 2><<<n_sm, HotCfg<2>::T, 0, ts.aux[0]>>>(c);
-    k_hot_chain<MODEL, 0><<<n_sm * 8, HotCfg<0>::T, smem0, ts.aux[2]>>>(c);
+    k_hot_chain<MODEL, 0><<<n_sm * chain0_bpsm, HotCfg<0>::T, smem0, ts.aux[2]>>>(c);
     cudaEventRecord(ts.join[2], ts.aux[2]);
     cudaStreamWaitEvent(ts.aux[0], ts.join[2], 0);
-    k_hot_eval<MODEL><<<n_sm * 8, EVAL_T, 0, ts.aux[0]>>>(c);
+    k_hot_eval<MODEL><<<n_sm * eval_bpsm, EVAL_T, 0, ts.aux[0]>>>(c);
     cudaEventRecord(ts.join[0], ts.aux[0]);
 
-    k_transmit_stream<MODEL><<<n_sm * 8, 256, 0, s>>>(c);
+    k_transmit_stream<MODEL><<<(int) min((c.n_keys + 255u) / 256u, (uint32_t) (n_sm * stream_bpsm)), 256, 0, s>>>(c);
     cudaEventRecord(ts.mid, s);
     cudaStreamWaitEvent(ts.aux[1], ts.mid, 0);
     k_transmit_sub<MODEL, 32><<<n_sm * 8, 256, 0, ts.aux[1]>>>(c);
@@ -1279,7 +1247,7 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     k_transmit_sub<MODEL, 8><<<n_sm * 8, 256, 0, s>>>(c);
     cudaStreamWaitEvent(s, ts.join[0], 0);
     cudaStreamWaitEvent(s, ts.join[1], 0);
-    launches += 8;
+    launches += 7;
     if (c.n_total_loc)
     {
         k_transmit_total<MODEL><<<(int) min((uint32_t) (n_sm * 4), c.n_total_loc), 256, 0, s>>>(c);

@@ -211,6 +211,20 @@ class HerosEngine:
         self._check(self._lib.heros_wait(self._h, C.byref(st)))
         return st.as_dict()
 
+    TIMELINE_IDS = ("k_window_open", "k_scan_lookback", "k_bucket_scatter", "k_window_roll", "k_transmit_stream",
+                    "k_transmit_sub<8>", "k_transmit_sub<32>", "k_hot_chain<0>", "k_hot_chain<1>", "k_hot_chain<2>",
+                    "k_hot_eval", "k_transmit_total", "k_resolve", "k_submit", "k_advance_day", "k_rate_locations")
+
+    def timeline(self, enable: bool = True):
+        """heros_debug_timeline: {kernel: (start_us, end_us)} averaged over the windows since the collection was started
+        (relative to the start of the window's first kernel), and the number of windows; (re)starts or stops it."""
+        start = (C.c_double * 32)()
+        end = (C.c_double * 32)()
+        n = C.c_int64(0)
+        self._check(self._lib.heros_debug_timeline(self._h, 1 if enable else 0, start, end, C.byref(n)))
+        rows = {name: (start[k], end[k]) for k, name in enumerate(self.TIMELINE_IDS) if end[k] >= 0 and n.value > 0}
+        return rows, int(n.value)
+
     def window_abort(self) -> None:
         self._check(self._lib.heros_window_abort(self._h))
 
