@@ -489,22 +489,31 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed_days(eng, bx, stream, cols_of_day, device, after_step=None):
+    def timed_days(eng, bx, stream, cols_of_day, device, after_step=None, d0=None, d1=None):
         """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream.  A single engine is
         driven the way the asynchronous C ABI is meant to be used: the window of day d is enqueued (heros_step_async), the
         stays of day d + 1 are handed over while it runs (heros_submit_visits copies on its own stream / takes resident
         device buffers in on the side stream), then the host waits for day d (heros_wait) and reads its results."""
+        d0 = first_timed if d0 is None else d0
+        d1 = total if d1 is None else d1
         stats = []
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         start.record(stream)
         if bx is None:
-            submit_day(eng, first_timed, cols_of_day(first_timed)[0], device)
-            for d in range(first_timed, total):
+            submit_day(eng, d0, cols_of_day(d0)[0], device)
+            for d in range(d0, d1):
+                if d + 1 < d1 and not device:
+                    # host buffers: the copy of day d + 1 starts before the window of day d is enqueued
+                    c = cols_of_day(d + 1)[0]
+                    eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
                 eng.step_async(24.0 * (d + 1))
-                if d + 1 < total:
-                    submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
+                if d + 1 < d1:
+                    if device:
+                        submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
+                    else:
+                        eng.submit_visits_end()
                 if after_step:
                     # the host reads the day's results before it hands over the next day (e2e)
                     stats.append(eng.wait())
@@ -514,7 +523,7 @@ def run_ours(args):
                 # counts of the pools, the work lists and the candidates stay on the device), one wait at the end
                 stats.append(eng.wait())
         else:
-            for d in range(first_timed, total):
+            for d in range(d0, d1):
                 stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))
                 if after_step:
                     after_step()
@@ -530,8 +539,9 @@ def run_ours(args):
     dev_days = [({k: days[d][0][k].to(dev) for k, _ in COLS}, {k: days[d][1][k].to(dev) for k, _ in COLS}, days[d][2])
                 for d in range(total)]
     torch.cuda.synchronize()
-    for d in range(first_timed):
+    for d in range(args.preroll):
         day_step(eng, bx, d, *dev_days[d], device=True)
+    timed_days(eng, bx, stream, lambda d: dev_days[d], True, d0=args.preroll, d1=first_timed)  # warm-up, driven like the timed steps
     with ClockSampler(local) as clocks:
         seconds, wall_seconds, stats = timed_days(eng, bx, stream, lambda d: dev_days[d], True)
     assert (eng.phase_counts() == ref_counts).all(), "replay diverged from the recorded run"
@@ -540,7 +550,7 @@ def run_ours(args):
 
     # ---- e2e: through the C ABI with pinned host buffers, copies inside the timed region ----
     eng, bx, stream = new_engine()
-    for d in range(first_timed):
+    for d in range(args.preroll):
         day_step(eng, bx, d, *days[d], device=False)
     box = {"n_inf": len(eng.infections()["person"]), "d2h": 0, "counts": None}
 
@@ -550,6 +560,8 @@ def run_ours(args):
         box["n_inf"] += len(new["person"])
         box["d2h"] += 64 + len(new["person"]) * 26
 
+    timed_days(eng, bx, stream, lambda d: days[d], False, read_results, d0=args.preroll, d1=first_timed)  # warm-up
+    box["d2h"] = 0
     e2e_seconds, e2e_wall, _ = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
     assert (box["counts"] == ref_counts).all()
     e2e_d2h = int(box["d2h"] / args.steps)

@@ -176,6 +176,14 @@ int32_t heros_seed_infections(heros_handle h, int32_t n_infected, int32_t min_ag
  * with their number in heros_last_error (once; the engine stays usable). */
 int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
                             const int16_t* sublocation, const double* t_in, const double* t_out);
+/* The two halves of heros_submit_visits, for a host that wants the copy to start before it enqueues the window in
+ * front of it:  heros_submit_visits_begin(day d + 1) starts the host -> device copies on the engine's copy stream and
+ * returns at once (the buffers must stay untouched until the matching _end);  heros_step_async(day d) can then be
+ * enqueued while the stays are already crossing PCIe;  heros_submit_visits_end() takes the stays in piece by piece
+ * behind their copies and returns when the caller's buffers have been read.  One submission at a time. */
+int32_t heros_submit_visits_begin(heros_handle h, int64_t n, const int32_t* person, const int32_t* location,
+                                  const int16_t* sublocation, const double* t_in, const double* t_out);
+int32_t heros_submit_visits_end(heros_handle h);
 /* same, from device memory of the engine's GPU (multi-GPU exchange buffers, device-side schedule generators).  The
  * buffers are read asynchronously on the engine's stream (heros_get_stream): they must stay unchanged until the next
  * call that synchronises (heros_step, heros_window_finish, any heros_get_*). */

@@ -83,6 +83,8 @@ SIGNATURES = {
     "heros_expose": (C.c_int32, [_P, C.c_int32, _P, _P]),
     "heros_seed_infections": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "heros_submit_visits": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "heros_submit_visits_begin": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "heros_submit_visits_end": (C.c_int32, [_P]),
     "heros_submit_visits_device": (C.c_int32, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_set_schedule": (C.c_int32, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                        _P, _P, _P, _P, C.c_uint64]),

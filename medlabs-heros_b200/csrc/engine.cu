@@ -16,6 +16,7 @@
 #include "engine_state.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -1013,10 +1014,12 @@ int32_t window_begin(heros_handle h, double T1)
     { const int32_t rc_ = join_submissions(h); if (rc_ != HEROS_OK) return rc_; }
     // the fill of the carry pool after the latest window whose count has reached the host, plus what was submitted since
     {
-        // a host that runs ahead is held back here until the count of the window before the last has arrived: two
-        // windows of work stay queued on the device, and the bound never lags by more than two windows' submissions
+        // A host that runs ahead is held back here until the count of the last window has arrived, i.e. until that window
+        // has been bucketed: its whole transmission stage is still queued on the device while this window is enqueued
+        // (which takes the host less time), so the device does not run dry -- and the bound is exact, so no buffer is
+        // ever sized for stays that are not there.
         for (int k = 0; k < WIN_RING; ++k)
-            if (h->keep_pending[k] && h->keep_seq[k] + 1 == h->win_seq) CU(h, cudaEventSynchronize(h->ev_keep[k]));
+            if (h->keep_pending[k] && h->keep_seq[k] == h->win_seq) CU(h, cudaEventSynchronize(h->ev_keep[k]));
         int best = -1;
         for (int k = 0; k < WIN_RING; ++k)
             if (h->keep_pending[k] && (best < 0 || h->keep_seq[k] > h->keep_seq[best]) && cudaEventQuery(h->ev_keep[k]) == cudaSuccess)
@@ -1258,19 +1261,42 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         heros_destroy(h);
         return (int32_t) HEROS_ERR_CUDA;
     };
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-    if ((e = cudaStreamCreateWithFlags(&h->sub_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    {
+        // k_submit of the NEXT window (side stream) becomes ready in the middle of the current one; thread blocks are handed
+        // out grid by grid in the order the grids became ready, so on equal terms its 2 000 blocks would be placed in front
+        // of the transmission kernels of the window that is running (heros_debug_timeline: + 30 us).  It has a whole
+        // window to finish: lower priority.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const bool flat = getenv("HEROS_TUNE_FLAT_PRIO") != nullptr;
+        if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, flat ? lo : hi)) != cudaSuccess) return bail("stream", e);
+        if ((e = cudaStreamCreateWithPriority(&h->sub_stream, cudaStreamNonBlocking, lo)) != cudaSuccess) return bail("stream", e);
+    }
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->meta_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     for (auto& ev : h->ev_keep)
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     if ((e = cudaMallocHost(&h->h_keep, sizeof(unsigned long long) * WIN_RING)) != cudaSuccess) return bail("pinned counters", e);
-    for (auto& a : h->aux)
-        if ((e = cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    {
+        // The hot path (aux 0, 2) is the longer of the two branches of the transmission stage.  Thread blocks are handed
+        // out grid by grid in the order the grids became ready, so behind the streaming kernel (and k_submit of the next
+        // window) the chain kernels only start when those have no block left to place (heros_debug_timeline shows it);
+        // on streams of higher priority (HEROS_TUNE_AUX_PRIO=1) their blocks go first whenever a slot frees up.
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* knob = getenv("HEROS_TUNE_AUX_PRIO");
+        const bool prio = knob && knob[0] == '1';  // measured at Hague size: both branches then run side by side and each takes
+                                                   // longer (they share the instruction issue slots) -- the stage ends 2 % earlier
+        for (int k = 0; k < N_AUX; ++k)
+            if ((e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, (prio && k != 1) || !getenv("HEROS_TUNE_FLAT_PRIO") ? hi : lo)) != cudaSuccess)
+                return bail("stream", e);
+    }
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
     for (cudaEvent_t* ev : {&h->ev_rolled, &h->ev_submitted, &h->ev_copied, &h->ev_stage_free[0], &h->ev_stage_free[1]})
         if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    for (auto& ev : h->ev_chunk)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     for (auto& we : h->ring)
     {
         for (cudaEvent_t* ev : {&we.begin, &we.opened, &we.scanned, &we.scattered, &we.mid, &we.transmitted, &we.resolved,
@@ -1338,6 +1364,7 @@ int32_t heros_destroy(heros_handle h)
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {h->ev_rolled, h->ev_submitted, h->ev_copied, h->ev_stage_free[0], h->ev_stage_free[1]})
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     for (auto& we : h->ring)
         for (cudaEvent_t ev : {we.begin, we.opened, we.scanned, we.scattered, we.mid, we.transmitted, we.resolved, we.fork,
                                we.filtered, we.join[0], we.join[1], we.join[2]})
@@ -1646,20 +1673,26 @@ static int32_t submit_from_device(heros_handle h, int64_t n, const int32_t* pers
     return HEROS_OK;
 }
 
-int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc, const int16_t* sub,
-                            const double* tin, const double* tout)
+// The two halves of heros_submit_visits.  begin: the columns start travelling to one of two staging sets on the copy
+// stream, in ST_CHUNKS pieces -- beside whatever the engine stream is doing -- and the call returns at once.  end: k_submit
+// of every piece is enqueued behind its copy (and behind the window that consumes the pools, which must have been enqueued
+// by now), so that all but the last piece are taken in while the rest still crosses PCIe; the call returns when the
+// caller's buffers have been read.
+static inline int64_t chunk_begin(int64_t n, int c) { return (n * c / heros_engine::ST_CHUNKS) & ~(int64_t) 63; }
+
+int32_t heros_submit_visits_begin(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc, const int16_t* sub,
+                                  const double* tin, const double* tout)
 {
     int32_t rc = check_ready(h);
     if (rc != HEROS_OK) return rc;
     if (n < 0 || (n > 0 && (!person || !loc || !sub || !tin || !tout))) return fail(h, HEROS_ERR_INVALID, "null argument");
-    if (n == 0) return HEROS_OK;
-    if (h->win_state != 0)
-        return fail(h, HEROS_ERR_INVALID, "stays cannot be submitted while a window opened by heros_window_begin is in progress");
+    if (h->st_pending_n >= 0) return fail(h, HEROS_ERR_INVALID, "heros_submit_visits_begin: the previous submission was not ended");
     cudaSetDevice(h->cfg.device);
-    // The columns go to one of two staging sets on the copy stream: the copy runs beside whatever the engine stream is
-    // doing (a window enqueued by heros_step_async), and the call returns as soon as the caller's buffers have been read.
     const int k = h->st_cur;
     h->st_cur ^= 1;
+    h->st_pending_n = n;
+    h->st_pending_k = k;
+    if (n == 0) return HEROS_OK;
     cudaStream_t cs = h->copy_stream;
     CU(h, cudaStreamWaitEvent(cs, h->ev_stage_free[k], 0));  // the kernel that read this staging set has finished
     if ((size_t) n > h->st_person[k].n)
@@ -1668,17 +1701,62 @@ int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, co
         CU(h, h->st_person[k].ensure(n)); CU(h, h->st_loc[k].ensure(n)); CU(h, h->st_sub[k].ensure(n));
         CU(h, h->st_tin[k].ensure(n)); CU(h, h->st_tout[k].ensure(n));
     }
-    CU(h, cudaMemcpyAsync(h->st_person[k].p, person, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
-    CU(h, cudaMemcpyAsync(h->st_loc[k].p, loc, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
-    CU(h, cudaMemcpyAsync(h->st_sub[k].p, sub, (size_t) n * 2, cudaMemcpyHostToDevice, cs));
-    CU(h, cudaMemcpyAsync(h->st_tin[k].p, tin, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
-    CU(h, cudaMemcpyAsync(h->st_tout[k].p, tout, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
-    CU(h, cudaEventRecord(h->ev_copied, cs));
-    rc = submit_from_device(h, n, h->st_person[k].p, h->st_loc[k].p, h->st_sub[k].p, h->st_tin[k].p, h->st_tout[k].p,
-                            h->ev_copied, k);
-    if (rc != HEROS_OK) return rc;
-    CU(h, cudaStreamSynchronize(cs));  // the caller may reuse its buffers
+    for (int c = 0; c < heros_engine::ST_CHUNKS; ++c)
+    {
+        const int64_t a = c == 0 ? 0 : chunk_begin(n, c), b = c + 1 == heros_engine::ST_CHUNKS ? n : chunk_begin(n, c + 1);
+        if (b > a)
+        {
+            const size_t m = (size_t) (b - a);
+            CU(h, cudaMemcpyAsync(h->st_person[k].p + a, person + a, m * 4, cudaMemcpyHostToDevice, cs));
+            CU(h, cudaMemcpyAsync(h->st_loc[k].p + a, loc + a, m * 4, cudaMemcpyHostToDevice, cs));
+            CU(h, cudaMemcpyAsync(h->st_sub[k].p + a, sub + a, m * 2, cudaMemcpyHostToDevice, cs));
+            CU(h, cudaMemcpyAsync(h->st_tin[k].p + a, tin + a, m * 8, cudaMemcpyHostToDevice, cs));
+            CU(h, cudaMemcpyAsync(h->st_tout[k].p + a, tout + a, m * 8, cudaMemcpyHostToDevice, cs));
+        }
+        CU(h, cudaEventRecord(h->ev_chunk[c], cs));
+    }
     return HEROS_OK;
+}
+
+int32_t heros_submit_visits_end(heros_handle h)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->st_pending_n < 0) return fail(h, HEROS_ERR_INVALID, "heros_submit_visits_end without heros_submit_visits_begin");
+    cudaSetDevice(h->cfg.device);
+    const int64_t n = h->st_pending_n;
+    const int k = h->st_pending_k;
+    h->st_pending_n = -1;
+    if (n == 0) return HEROS_OK;
+    int last = 0;
+    for (int c = 0; c < heros_engine::ST_CHUNKS; ++c)
+        if ((c + 1 == heros_engine::ST_CHUNKS ? n : chunk_begin(n, c + 1)) > (c == 0 ? 0 : chunk_begin(n, c))) last = c;
+    int32_t rc = HEROS_OK;
+    for (int c = 0; c < heros_engine::ST_CHUNKS && rc == HEROS_OK; ++c)
+    {
+        const int64_t a = c == 0 ? 0 : chunk_begin(n, c), b = c + 1 == heros_engine::ST_CHUNKS ? n : chunk_begin(n, c + 1);
+        if (b > a)
+            rc = submit_from_device(h, b - a, h->st_person[k].p + a, h->st_loc[k].p + a, h->st_sub[k].p + a, h->st_tin[k].p + a,
+                                    h->st_tout[k].p + a, h->ev_chunk[c], c == last ? k : -1);
+    }
+    if (rc != HEROS_OK)
+    {
+        // nothing may be left reading the caller's buffers or writing the staging set when the error is reported
+        cudaStreamSynchronize(h->copy_stream);
+        cudaEventRecord(h->ev_stage_free[k], h->sub_stream);
+        return rc;
+    }
+    CU(h, cudaStreamSynchronize(h->copy_stream));  // the caller may reuse its buffers
+    return HEROS_OK;
+}
+
+int32_t heros_submit_visits(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc, const int16_t* sub,
+                            const double* tin, const double* tout)
+{
+    if (h && h->win_state != 0)
+        return fail(h, HEROS_ERR_INVALID, "stays cannot be submitted while a window opened by heros_window_begin is in progress");
+    const int32_t rc = heros_submit_visits_begin(h, n, person, loc, sub, tin, tout);
+    if (rc != HEROS_OK) return rc;
+    return heros_submit_visits_end(h);
 }
 
 int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* person, const int32_t* loc,
@@ -1797,9 +1875,20 @@ static int32_t enqueue_windows(heros_handle h, double t_until)
     while (h->t_now < t_until)
     {
         const double T1 = std::min(h->t_now + h->cfg.window_hours, t_until);
+        static const bool host_times = getenv("HEROS_TUNE_HOSTTIME") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         if ((rc = window_begin(h, T1)) != HEROS_OK) return rc;
+        const auto t1 = std::chrono::steady_clock::now();
         if ((rc = window_transmit(h)) != HEROS_OK) return rc;
+        const auto t2 = std::chrono::steady_clock::now();
         if ((rc = window_finish(h)) != HEROS_OK) return rc;
+        if (host_times)
+        {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            fprintf(stderr, "[heros] window to %.0f h: host us begin %.0f transmit %.0f finish %.0f | carry_ub %zu fresh_seen %zu\n", T1,
+                    us(t0, t1), us(t1, t2), us(t2, t3), h->carry_ub, h->fresh_seen);
+        }
     }
     return HEROS_OK;
 }

@@ -209,6 +209,11 @@ struct heros_engine
     DevBuf<int16_t> st_sub[2];
     DevBuf<double> st_tin[2], st_tout[2];
     int st_cur = 0;
+    // a submission begun by heros_submit_visits_begin: the columns travel in ST_CHUNKS pieces, k_submit follows piece by piece
+    static constexpr int ST_CHUNKS = 4;
+    cudaEvent_t ev_chunk[ST_CHUNKS]{};
+    int64_t st_pending_n = -1;   // -1: nothing begun
+    int st_pending_k = 0;
     DevBuf<int32_t> x_person; DevBuf<double> x_time;  // heros_expose / heros_set_agent_state
 
     std::vector<double> series_t;

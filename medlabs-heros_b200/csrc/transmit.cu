@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
             const int s = j % EVAL_STAGES;
             mbar_wait(&s_bar[s], parity[s]);
             parity[s] ^= 1u;
-            const int slot = wib * 32 + lane;
+            const int slot = lane * (EVAL_T / 32) + wib;  // neighbouring records go to different warps: few ill stays are shared out
             const int v = j * EVAL_TILE + slot;
             StayRec r;
             {

@@ -135,6 +135,16 @@ class HerosEngine:
         self._check(fn(self._h, n, C.c_void_p(person), C.c_void_p(loc), C.c_void_p(sub), C.c_void_p(t_in),
                        C.c_void_p(t_out)))
 
+    def submit_visits_begin_ptr(self, n: int, person: int, loc: int, sub: int, t_in: int, t_out: int):
+        """heros_submit_visits_begin: the host -> device copies start, the call returns at once; the (pinned) buffers
+        must stay untouched until ``submit_visits_end``."""
+        self._check(self._lib.heros_submit_visits_begin(self._h, n, C.c_void_p(person), C.c_void_p(loc), C.c_void_p(sub),
+                                                        C.c_void_p(t_in), C.c_void_p(t_out)))
+
+    def submit_visits_end(self):
+        """heros_submit_visits_end: the stays are taken in behind their copies; returns when the buffers have been read."""
+        self._check(self._lib.heros_submit_visits_end(self._h))
+
     # ---- device-side activity schedule ----
     def set_schedule(self, tables: Dict[str, np.ndarray], seed: int):
         """``tables``: the arrays of ``scenario.compile_schedule`` (heros_set_schedule)."""
