@@ -90,12 +90,18 @@ class City:
     def __init__(self, n_persons: int, seed: int = 20240807, n_locations: Optional[int] = None,
                  box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8,
                  location_table: Optional[Dict[str, np.ndarray]] = None,
-                 person_table: Optional[Dict[str, np.ndarray]] = None):
+                 person_table: Optional[Dict[str, np.ndarray]] = None,
+                 work_anywhere_fraction: float = 1.0, n_work_neighbours: int = 64):
         """``location_table``: a real location table (type, nsub, area_per_sub, lat, lon -- e.g. the Helsinki fixture
         of tests/golden, or ``loaders.read_locations``) instead of the synthetic one.  ``person_table``: real persons
         (age, role, home_loc, home_sub, work_loc as location indices, optionally female and work_sub --
         ``loaders.read_people``) instead of the synthetic population; needs ``location_table``."""
         rng = np.random.default_rng(seed)
+        # share of the workers whose workplace is drawn from the whole city; the others work at one of the
+        # n_work_neighbours workplaces nearest to their home (1.0: the Hague-sized benchmark city, where everybody may work
+        # anywhere; < 1: cities much larger than a commute, BASELINE configs[4])
+        self.work_anywhere_fraction = float(work_anywhere_fraction)
+        self.n_work_neighbours = int(n_work_neighbours)
         if person_table is not None:
             if location_table is None:
                 raise ValueError("a person table refers to the rows of a location table")
@@ -235,6 +241,13 @@ class City:
         weights = np.maximum(loc_nsub[wp], 1) / np.maximum(loc_nsub[wp], 1).sum()
         work_loc[workers] = wp[rng.choice(len(wp), len(workers), p=weights)]
         from scipy.spatial import cKDTree
+        if self.work_anywhere_fraction < 1.0 and len(workers) and len(wp):
+            rng_w = np.random.default_rng(rng.integers(0, 1 << 62))  # its own stream: the draws above stay what they were
+            near = workers[rng_w.random(len(workers)) >= self.work_anywhere_fraction]
+            k = min(self.n_work_neighbours, len(wp))
+            _, j = cKDTree(np.c_[x[wp], y[wp]]).query(np.c_[x[home_loc[near]], y[home_loc[near]]], k=k)
+            j = j.reshape(len(near), k)
+            work_loc[near] = wp[j[np.arange(len(near)), rng_w.integers(0, k, len(near))]]
         for r, tname in ((ROLE_KINDERGARTEN, "Kindergarten"), (ROLE_PRIMARY, "PrimarySchool"),
                          (ROLE_SECONDARY, "SecondarySchool")):
             who = np.nonzero(role == r)[0]
@@ -291,15 +304,22 @@ class City:
         self.n_commuters = len(pick)
         return len(pick)
 
-    def global_location_ids(self, loc: np.ndarray, own_base: int, other_base: int) -> np.ndarray:
-        """Location codes of the schedule generator -> global location ids of a sharded run."""
+    def global_location_ids(self, loc: np.ndarray, own_base: int, other_base: Optional[int] = None) -> np.ndarray:
+        """Location codes of the schedule generator -> global location ids of a sharded run.  Codes beyond the city's own
+        table are foreign locations: entries of ``ext_global`` (a shard of ``partition_city``), or -- ``add_commuters`` --
+        locations of the one neighbouring tile whose first global id is ``other_base``."""
         loc = loc.astype(np.int64)
+        ext = getattr(self, "ext_global", None)
+        if ext is not None:
+            far = loc >= self.n_locations
+            return np.where(far, ext[np.where(far, loc - self.n_locations, 0)], loc + own_base).astype(np.int32)
         return np.where(loc >= self.n_locations, loc - self.n_locations + other_base, loc + own_base).astype(np.int32)
 
     def install(self, engine):
-        """heros_set_location_types / heros_set_locations / heros_set_persons."""
+        """heros_set_location_types / heros_set_locations / heros_set_persons (a shard: its own locations and persons)."""
+        n = self.n_locations
         engine.set_location_types(self.type_infect_sub, self.type_correction)
-        engine.set_locations(self.loc_type, self.loc_nsub, self.loc_area, self.loc_y, self.loc_x)
+        engine.set_locations(self.loc_type[:n], self.loc_nsub[:n], self.loc_area[:n], self.loc_y[:n], self.loc_x[:n])
         engine.set_persons(self.age, self.female, self.role, self.home_loc, self.home_sub, self.work_loc)
 
 
@@ -369,6 +389,13 @@ class ScheduleGenerator:
         # still take place in an open one (LocationPolicy.java:39-46)
         self.frac_open = np.ones(len(TYPE_NAMES), np.float64)
         self.frac_act = np.ones(len(TYPE_NAMES), np.float64)
+        # a shard of partition_city draws with the GLOBAL ids of its persons and locations, so that the stays of a person
+        # do not depend on how the city was cut
+        self.person_key = getattr(city, "person_gid", None)
+        self.loc_key = getattr(city, "loc_gid", None)
+
+    def _pkey(self, idx):
+        return idx if self.person_key is None else self.person_key[idx]
 
     def set_closure_policy(self, location_type: int, fraction_open: float, fraction_activities: float,
                            alternative_type: int) -> None:
@@ -398,8 +425,9 @@ class ScheduleGenerator:
         fo, fa = self.frac_open[ty], self.frac_act[ty]
         if not ((fo < 1.0) | (fa < 1.0)).any():
             return np.zeros(len(idx), bool)
-        x_loc = philox4x32_10(np.maximum(dl, 0), 0, 2, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
-        x_act = philox4x32_10(idx, day_act, 1, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
+        lk = np.maximum(dl, 0) if self.loc_key is None else self.loc_key[np.maximum(dl, 0)]
+        x_loc = philox4x32_10(lk, 0, 2, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
+        x_act = philox4x32_10(self._pkey(idx), day_act, 1, TAG_SCHEDULE, self.seed, self.seed >> 32)[0]
         u_loc = x_loc.astype(np.float64) * 2.0 ** -32
         u_act = x_act.astype(np.float64) * 2.0 ** -32
         return (dl >= 0) & ~((u_loc < fo) & (u_act < fa))
@@ -455,7 +483,7 @@ class ScheduleGenerator:
             for a_i, act in enumerate(acts):
                 if not alive.any():
                     break
-                x, y, z, w = philox4x32_10(idx, d * 64 + a_i, 0, TAG_SCHEDULE, self.seed, self.seed >> 32)
+                x, y, z, w = philox4x32_10(self._pkey(idx), d * 64 + a_i, 0, TAG_SCHEDULE, self.seed, self.seed >> 32)
                 u_dur = u01_from_words(x, y)
                 u_type = z.astype(np.float64) * 2.0 ** -32
                 u_cand = (w >> np.uint64(16)).astype(np.float64) * 2.0 ** -16

@@ -387,3 +387,174 @@ def step_window_peers_in_process(exchanges: List[PeerExchange], t_until: float, 
         with x.shard.on_stream():
             out.append(x.receive_and_finish())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# geographic partition of ONE city: locations in Morton order of (x, y), cut into contiguous ranges of
+# equal expected load; a person belongs to the shard of its home
+# ---------------------------------------------------------------------------------------------------------------------
+def morton_codes(x, y, bits: int = 16):
+    """Z-order key of every point: x and y quantised to ``bits`` bits over their bounding box, bits interleaved."""
+    import numpy as np
+
+    def quantise(v):
+        v = np.asarray(v, np.float64)
+        lo, hi = float(v.min()), float(v.max())
+        q = np.zeros(len(v), np.uint64) if hi <= lo else np.minimum(((v - lo) / (hi - lo) * (1 << bits)).astype(np.uint64),
+                                                                    np.uint64((1 << bits) - 1))
+        return q
+
+    def spread(q):  # abcd -> 0a0b0c0d
+        q = q & np.uint64(0xFFFFFFFF)
+        for shift, mask in ((16, 0x0000FFFF0000FFFF), (8, 0x00FF00FF00FF00FF), (4, 0x0F0F0F0F0F0F0F0F),
+                            (2, 0x3333333333333333), (1, 0x5555555555555555)):
+            q = (q | (q << np.uint64(shift))) & np.uint64(mask)
+        return q
+
+    return spread(quantise(x)) | (spread(quantise(y)) << np.uint64(1))
+
+
+class CityPartition:
+    """Result of ``partition_city``.  The global numbering of a sharded run makes every shard's persons and locations
+    contiguous: ``loc_new[l]`` / ``person_new[p]`` = new global id of location l / person p of the original city,
+    ``loc_bases`` / ``person_bases`` = first new id of every shard followed by the total.  ``shard_city(r)`` is the
+    city of shard r (own persons and locations in local numbering, foreign locations its persons can reach appended
+    behind them with their global ids in ``ext_global``); ``global_city()`` the whole city in the new numbering -- the
+    single-engine / oracle run a sharded run must equal."""
+
+    def __init__(self, city, shard_of_location, n_shards: int):
+        import numpy as np
+        self.city, self.n_shards = city, int(n_shards)
+        self.shard_of_location = np.asarray(shard_of_location, np.int32)
+        self.shard_of_person = self.shard_of_location[city.home_loc]
+        # new ids: stable within a shard (original order kept)
+        l_order = np.argsort(self.shard_of_location, kind="stable")
+        p_order = np.argsort(self.shard_of_person, kind="stable")
+        self.loc_old, self.person_old = l_order, p_order            # new id -> original id
+        self.loc_new = np.empty(len(l_order), np.int64); self.loc_new[l_order] = np.arange(len(l_order))
+        self.person_new = np.empty(len(p_order), np.int64); self.person_new[p_order] = np.arange(len(p_order))
+        self.loc_bases = np.concatenate([[0], np.cumsum(np.bincount(self.shard_of_location, minlength=n_shards))]).astype(np.int64)
+        self.person_bases = np.concatenate([[0], np.cumsum(np.bincount(self.shard_of_person, minlength=n_shards))]).astype(np.int64)
+
+    def _make(self, persons_old, locs_old_own, locs_old_ext, person_gid, loc_gid, ext_global):
+        """A City over the given original persons / locations (own first, then foreign), references renumbered."""
+        import numpy as np
+        from .scenario import City, NONE
+        c = self.city
+        locs = np.concatenate([locs_old_own, locs_old_ext]).astype(np.int64)
+        local_of = np.full(c.n_locations, NONE, np.int64)
+        local_of[locs] = np.arange(len(locs))
+
+        def remap(v):
+            v = np.asarray(v, np.int64)
+            return np.where(v >= 0, local_of[np.maximum(v, 0)], NONE)
+
+        out = object.__new__(City)
+        out.n_persons = len(persons_old)
+        out.n_locations = len(locs_old_own)
+        out.type_infect_sub, out.type_correction = c.type_infect_sub.copy(), c.type_correction.copy()
+        out.n_random_candidates = c.n_random_candidates
+        for name in ("loc_type", "loc_nsub", "loc_area", "loc_x", "loc_y"):
+            setattr(out, name, getattr(c, name)[locs])
+        for name in ("age", "female", "role", "home_sub", "work_sub", "household"):
+            setattr(out, name, getattr(c, name)[persons_old])
+        out.home_loc = remap(c.home_loc[persons_old]).astype(np.int32)
+        out.work_loc = remap(c.work_loc[persons_old]).astype(np.int32)
+        # locator tables: rows of the own locations (homes are own), entries may be foreign
+        own = locs_old_own
+        out.nearest = remap(c.nearest[own]).astype(np.int32)
+        out.cand = remap(c.cand[own]).astype(np.int32)
+        out.n_cand = c.n_cand[own].copy()
+        out.person_gid = np.asarray(person_gid, np.int64)
+        out.loc_gid = np.asarray(loc_gid, np.int64)
+        if ext_global is not None:
+            out.ext_global = np.asarray(ext_global, np.int64)
+        return out
+
+    def global_city(self):
+        import numpy as np
+        n_l, n_p = len(self.loc_old), len(self.person_old)
+        return self._make(self.person_old, self.loc_old, np.empty(0, np.int64), np.arange(n_p), np.arange(n_l), None)
+
+    def shard_city(self, r: int):
+        import numpy as np
+        c = self.city
+        persons = self.person_old[self.person_bases[r]:self.person_bases[r + 1]]
+        own = self.loc_old[self.loc_bases[r]:self.loc_bases[r + 1]]
+        # every location the shard's persons can be sent to: work / school places and the entries of the locator tables
+        refs = [c.work_loc[persons].astype(np.int64).ravel(), c.nearest[own].astype(np.int64).ravel(),
+                c.cand[own].astype(np.int64).ravel()]
+        refs = np.unique(np.concatenate(refs))
+        refs = refs[refs >= 0]
+        ext = refs[self.shard_of_location[refs] != r]
+        return self._make(persons, own, ext, self.person_new[persons], np.concatenate([self.loc_new[own], self.loc_new[ext]]),
+                          self.loc_new[ext])
+
+
+def expected_load(city):
+    """Expected stays per day of every location, the weight the partition balances: residents are at home about three
+    times a day, workers / pupils at their place twice, and every person visits the public places the locator tables of
+    its home point to about once."""
+    import numpy as np
+    n = city.n_locations
+    w = 3.0 * np.bincount(city.home_loc, minlength=n)[:n].astype(np.float64)
+    has = city.work_loc >= 0
+    w += 2.0 * np.bincount(city.work_loc[has], minlength=n)[:n]
+    residents = np.bincount(city.home_loc, minlength=n)[:n].astype(np.float64)
+    near = city.nearest
+    n_types = max(1, (near >= 0).any(axis=0).sum())
+    for t in range(near.shape[1]):
+        col = near[:, t]
+        ok = col >= 0
+        if ok.any():
+            w += np.bincount(col[ok], weights=residents[ok] / n_types, minlength=n)[:n]
+    return w + 1e-3
+
+
+def partition_city(city, n_shards: int, weights=None) -> CityPartition:
+    """Cuts one city into ``n_shards`` geographic shards: the locations are ordered along the Morton (Z-order) curve of
+    their coordinates and the curve is cut into contiguous pieces of equal expected load (``expected_load`` unless
+    ``weights`` is given); a person is owned by the shard of its home (the district columns WK_CODE /
+    BU_CODE of the reference's locations.csv would serve the same purpose, metadata/DataDictionary.xlsx sheet
+    ``locations`` rows 12-13)."""
+    import numpy as np
+    if n_shards < 1:
+        raise ValueError("n_shards must be positive")
+    w = expected_load(city) if weights is None else np.asarray(weights, np.float64)
+    code = morton_codes(city.loc_x, city.loc_y)
+    order = np.argsort(code, kind="stable")
+    cum = np.cumsum(w[order])
+    shard_sorted = np.minimum((cum - 0.5 * w[order]) / cum[-1] * n_shards, n_shards - 1).astype(np.int32)
+    shard = np.empty(city.n_locations, np.int32)
+    shard[order] = shard_sorted
+    return CityPartition(city, shard, n_shards)
+
+
+VISIT_COLUMNS = ("person", "loc", "sub", "t_in", "t_out")
+
+
+def split_stays(city, st, rank: int, person_bases, location_bases, open_remote=None, other_base=None):
+    """The stays a shard's schedule generator produced for one day (local ids) -> what the shard hands to its engine:
+    (own columns with global ids, remote columns grouped by destination shard, the world + 1 row offsets of the groups,
+    the remote stays still open at the end of the day).  A stay in a location of another shard is a *remote* stay: it
+    travels to the owner of the location every window it is active in; while it is open (t_out = +inf) it is kept in
+    ``open_remote`` and sent again the next day, until its closed version arrives.  ``other_base``: see
+    ``City.global_location_ids`` (tiles joined by ``add_commuters``)."""
+    import numpy as np
+    world = len(person_bases) - 1
+    person = (st["person"].astype(np.int64) + int(person_bases[rank])).astype(np.int32)
+    loc = city.global_location_ids(st["loc"], int(location_bases[rank]), other_base)
+    is_remote = st["loc"] >= city.n_locations
+    cols = {"person": person, "loc": loc, "sub": st["sub"], "t_in": st["t_in"], "t_out": st["t_out"]}
+    own = {k: v[~is_remote] for k, v in cols.items()}
+    rem = {k: v[is_remote] for k, v in cols.items()}
+    if open_remote is not None and len(open_remote["person"]):
+        # an open remote stay of an earlier day stays a guest until its closed version arrives
+        key_now = (rem["person"].astype(np.int64) << 32) ^ rem["t_in"].view(np.int64)
+        key_old = (open_remote["person"].astype(np.int64) << 32) ^ open_remote["t_in"].view(np.int64)
+        keep = ~np.isin(key_old, key_now)
+        rem = {k: np.concatenate([open_remote[k][keep], rem[k]]) for k in rem}
+    still_open = np.isinf(rem["t_out"])
+    open_next = {k: v[still_open] for k, v in rem.items()}
+    rem, offsets = sort_by_destination(rem, location_bases, world)
+    return own, rem, offsets, open_next
