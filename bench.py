@@ -63,7 +63,12 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: kernels write into the peers' memory over NVLink (CUDA IPC), or NCCL all-to-alls")
     ap.add_argument("--commute", type=float, default=0.05,
-                    help="N > 1: fraction of a tile's workers whose workplace lies in the next tile")
+                    help="N > 1: fraction of the workers whose workplace is drawn from the whole city (the others work at one "
+                         "of the 64 workplaces nearest to their home); BASELINE configs[4] names 0.01 / 0.05 / 0.20")
+    ap.add_argument("--parity-persons", type=int, default=6000,
+                    help="N > 1: persons per GPU of the small partitioned city that is run on all GPUs first and compared, "
+                         "event for event, with the CPU oracle on the whole city (0 = skip)")
+    ap.add_argument("--parity-days", type=int, default=8)
     return ap.parse_args()
 
 
@@ -285,24 +290,19 @@ def run_reference(args):
     infections = [int(x) for x in infected[:]]
     # the same workload description as the GPU arm's at this N (the sample that was timed is one tile of it)
     world = max(int(args.gpus), 1)
-    n_commuters = 0
-    if world > 1 and args.commute > 0:
-        tile = scenario.City(args.persons, seed=CITY_SEED)
-        other = scenario.City(args.persons, seed=CITY_SEED + (1 % world), origin_m=(12000.0 * (1 % world), 0.0))
-        n_commuters = tile.add_commuters(other, args.commute, seed=1000)
-        del tile, other
     line = {
         "impl": "reference", "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, city, world, n_commuters),
+        "config": workload_config(args, city, world),
         "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": workers, "kind": "port",
                          "host_cores": host_cores(),
                          "one_replication": {"value": one_replication, "unit": "person-hours/s", "cores": 1,
                                              "what": "replication 0 alone on its core while the others run beside it"},
-                         "sample": f"{args.steps} simulated days (days {first}..{total - 1}) of one city tile"
-                                   + (f" of the {world}, without its cross-tile commuters" if world > 1 else "") +
+                         "sample": f"{args.steps} simulated days (days {first}..{total - 1}) of "
+                                   + (f"a city of {args.persons} persons (one GPU's share of the {world} x {args.persons} city)"
+                                      if world > 1 else "the city") +
                                    f", {workers} replications (seeds {SEED}..{SEED + workers - 1}) side by side, one "
                                    "oracle/heros_oracle.c process per core as the reference's server scripts start one "
                                    "single-threaded JVM per seed; value = aggregate over the replications; "
@@ -314,21 +314,27 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, city, world, n_commuters, exchange="p2p"):
-    cfg = {"workload": f"thehague-synthetic N={city.n_persons} locations={city.n_locations} "
-                       f"sublocations={int(city.loc_nsub.sum())} model={args.model} trigger={args.trigger} seed={SEED} "
-                       f"infected0={N_INFECTED}" + (f" per GPU, {world} tiles" if world > 1 else ""),
-           "step": "one simulated day (24 h window)", "first_timed_day": args.preroll + args.warmup,
-           "l2": "inputs larger than L2: every step reads a fresh day of stays (61 MB, written to HBM before the timed "
-                 "region) and streams ~0.4 GB through the pool, ticket and bucket buffers (L2: 126 MB)"}
-    if world > 1:
-        cfg["cross_tile"] = (f"{args.commute:.3f} of each tile's workers ({n_commuters} on rank 0) work in the next tile: "
-                             "guest-stay blocks out, candidate blocks back every window, " +
-                             ("written by the pack / export kernels straight into the peers' memory over NVLink (CUDA IPC), "
-                              "flags instead of collectives" if exchange == "p2p" else
-                              "2 equal-split NCCL all-to-alls on the engine stream") +
-                             ", no host synchronisation inside a window")
-    return cfg
+def workload_config(args, city, world, exchange="p2p"):
+    """The workload both arms are quoted on, from the arguments alone (the two arms must print the same object)."""
+    step = {"step": "one simulated day (24 h window)", "first_timed_day": args.preroll + args.warmup,
+            "l2": "inputs larger than L2: every step reads a fresh day of stays (26 B per stay, 61 MB at Hague size, written "
+                  "to HBM before the timed region) and streams 32-byte records of all of them through the bucket buffers "
+                  "(L2: 126 MB)"}
+    if world == 1:
+        n_own = city.n_locations
+        return {"workload": f"thehague-synthetic N={city.n_persons} locations={n_own} "
+                            f"sublocations={int(city.loc_nsub[:n_own].sum())} model={args.model} trigger={args.trigger} "
+                            f"seed={SEED} infected0={N_INFECTED}", **step}
+    return {"workload": f"one synthetic city of {world} x {args.persons} persons (Hague density and location mix) cut into "
+                        f"{world} geographic shards along the Morton curve of its locations (equal expected load, a person "
+                        f"belongs to the shard of its home), model={args.model} trigger={args.trigger} seed={SEED} "
+                        f"infected0={N_INFECTED} per shard", **step,
+            "cross_shard": f"{args.commute:.3f} of the workers work anywhere in the city, the others at one of the 64 workplaces "
+                           "nearest to their home; every stay in another shard's location travels to its owner and successful "
+                           "draws travel back, every window, between all pairs of shards (no source mask), "
+                           "exchange = " + ("kernels writing into the peers' memory over NVLink (CUDA IPC), flags instead of "
+                                            "collectives" if exchange == "p2p" else "2 equal-split NCCL all-to-alls") +
+                           ", no host synchronisation inside a window"}
 
 
 def make_engine(args, props, city, device, flags=0):
@@ -344,6 +350,103 @@ def make_engine(args, props, city, device, flags=0):
         eng.set_transmission_distance(properties.dist_params(props))
     eng.set_progression(properties.prog_params(props))
     return eng
+
+
+def open_exchange(sh, guest_capacity, candidate_capacity, exchange, rank):
+    """The window exchange of a shard: peer-to-peer stores over NVLink (the shards map each other's receive regions by
+    CUDA IPC), or -- if any rank cannot -- the NCCL block exchange on all of them.  Returns (exchange object, kind)."""
+    import torch
+    import torch.distributed as dist
+    from heros_b200 import sharded
+    bx = None
+    if exchange == "p2p":
+        try:
+            bx = sharded.PeerExchange(sh, guest_capacity, candidate_capacity=candidate_capacity)
+            bx.connect()  # every shard listens to every other shard (no source mask)
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-to-peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+            bx, ok = None, 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=sh.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange, bx = "nccl", None
+    if bx is None:
+        bx = sharded.BlockExchange(sh, guest_capacity, candidate_capacity=candidate_capacity)
+    return bx, exchange
+
+
+def parity_check(args, rank, world, local, dev):
+    """N > 1: a small city cut into `world` geographic shards runs on all GPUs -- one process per GPU, every shard with its
+    own schedule generator, the same exchange as the timed run, all shards exchanging with all shards -- and rank 0
+    compares the gathered infection events, event for event, with the CPU oracle on the whole city."""
+    import torch
+    import torch.distributed as dist
+    import heros_b200 as hb
+    from heros_b200 import properties, scenario, sharded
+    seed, days = SEED, args.parity_days
+    props = load_props(args.model)
+    # more contagious than the scenario, so that a few days of a small city hold a few hundred events
+    props["covidT_area.contagiousness" if args.model == "area" else "covidT_dist.alpha"] = "4.0" if args.model == "area" else "1.5"
+    whole0 = scenario.City(args.parity_persons * world, seed=CITY_SEED + 1, work_anywhere_fraction=max(args.commute, 0.2))
+    part = sharded.partition_city(whole0, world)
+    city = part.shard_city(rank)
+    seeds = keyed_seeds(whole0, seed, 40 * world)
+    seeds = part.person_new[seeds].astype(np.int32)   # ids of the sharded numbering
+    eng = make_engine(args, props, city, local, hb._lib.FLAG_EXACT_STATS)
+    sh = sharded.ShardedEngine(eng, rank, world, part.person_bases, part.loc_bases, device=dev)
+    mine = np.sort(seeds[(seeds >= part.person_bases[rank]) & (seeds < part.person_bases[rank + 1])])
+    eng.expose(mine, np.zeros(len(mine)))
+    gen = scenario.ScheduleGenerator(city, seed)
+    probe = scenario.ScheduleGenerator(city, seed)
+    _, _, off0, _ = sharded.split_stays(city, probe.generate_day(np.zeros(city.n_persons, np.uint8)), rank,
+                                        part.person_bases, part.loc_bases)
+    cap = torch.tensor([int(2 * max(int(np.diff(off0).max()), 1024))], dtype=torch.int64, device=dev)
+    dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+    bx, kind = open_exchange(sh, int(cap.item()), 4096, args.exchange, rank)
+    open_remote, n_remote = None, 0
+    for d in range(days):
+        st = gen.generate_day(eng.agent_state()["phase"])
+        own, rem, off, open_remote = sharded.split_stays(city, st, rank, part.person_bases, part.loc_bases, open_remote)
+        eng.submit_visits(own["person"], own["loc"], own["sub"], own["t_in"], own["t_out"])
+        n_remote += len(rem["person"])
+        remote = {k: torch.from_numpy(np.ascontiguousarray(rem[k])).to(dev) for k, _ in COLS}
+        bx.step_window(24.0 * (d + 1), remote, off)
+    inf = eng.infections()
+    counts = torch.from_numpy(eng.phase_counts().astype(np.int64)).to(dev)
+    dist.all_reduce(counts)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object({k: inf[k] for k in ("person", "loc", "sub", "time", "p")}, gathered, dst=0)
+    remote_total = torch.tensor([n_remote], dtype=torch.int64, device=dev)
+    dist.all_reduce(remote_total)
+    result = None
+    if rank == 0:
+        whole = part.global_city()
+        sim = oracle_objects(args, props, whole, seed)
+        sim.expose(np.sort(seeds), np.zeros(len(seeds)))
+        g = scenario.ScheduleGenerator(whole, seed)
+        for d in range(days):
+            st = g.generate_day(sim.agent_state()["phase"])
+            sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
+            sim.run(24.0 * (d + 1))
+        oi = sim.infections()
+        got = {k: np.concatenate([x[k] for x in gathered]) for k in gathered[0]}
+        o1 = np.lexsort((oi["person"], oi["time"]))
+        o2 = np.lexsort((got["person"], got["time"]))
+        same = len(o1) == len(o2) and all((np.asarray(oi[k])[o1] == np.asarray(got[k])[o2]).all() for k in ("person", "loc", "sub", "time"))
+        p_ok = same and bool(np.allclose(np.asarray(got["p"])[o2], np.asarray(oi["p"])[o1], rtol=1e-12, atol=4.5e-16))
+        result = {"n_gpus": world, "persons": int(whole.n_persons), "days": days, "exchange": kind,
+                  "infection_events": int(len(o2)), "oracle_events": int(len(o1)),
+                  "cross_shard_stays": int(remote_total.item()),
+                  "infection_lists_identical": bool(same), "probabilities_within_1e-12": p_ok,
+                  "phase_counts_identical": bool((counts.cpu().numpy() == sim.phase_counts()).all()),
+                  "what": "one process per GPU, geographic shards of one small city, all shards exchanging with all shards, "
+                          "against oracle/heros_oracle.c on the whole city"}
+        if not (same and p_ok):
+            print(f"[bench] PARITY FAILURE at N = {world}: {result}", file=sys.stderr)
+    torch.cuda.synchronize()
+    dist.barrier()
+    return result
 
 
 COLS = (("person", np.int32), ("loc", np.int32), ("sub", np.int16), ("t_in", np.float64), ("t_out", np.float64))
@@ -367,22 +470,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     props = load_props(args.model)
-    # weak scaling: every rank owns one city tile of the configured size, tiles side by side
-    city = scenario.City(args.persons, seed=CITY_SEED + rank, origin_m=(12000.0 * rank, 0.0))
     n_commuters = 0
-    nxt = (rank + 1) % world
-    if world > 1 and args.commute > 0:
-        other = scenario.City(args.persons, seed=CITY_SEED + nxt, origin_m=(12000.0 * nxt, 0.0))
-        n_commuters = city.add_commuters(other, args.commute, seed=1000 + rank)
-        del other
+    parity = None
     if world > 1:
-        sizes = torch.tensor([city.n_persons, city.n_locations], dtype=torch.int64, device=dev)
-        gathered = [torch.empty_like(sizes) for _ in range(world)]
-        dist.all_gather(gathered, sizes)
-        gathered = torch.stack(gathered).cpu().numpy()
-        person_bases = np.concatenate([[0], np.cumsum(gathered[:, 0])])
-        loc_bases = np.concatenate([[0], np.cumsum(gathered[:, 1])])
+        # Before anything is timed: a small partitioned city on all GPUs through the same exchange, against the CPU oracle
+        # on the whole city (rank 0), event for event.
+        if args.parity_persons > 0:
+            parity = parity_check(args, rank, world, local, dev)
+        # weak scaling: ONE city of world x persons (constant density), cut into world geographic shards; every rank
+        # builds the same city from the same seed and keeps its shard
+        side = float(np.sqrt(world))
+        whole = scenario.City(args.persons * world, seed=CITY_SEED, box_m=(12000.0 * side, 9000.0 * side),
+                              work_anywhere_fraction=args.commute)
+        part = sharded.partition_city(whole, world)
+        city = part.shard_city(rank)
+        person_bases, loc_bases = part.person_bases.copy(), part.loc_bases.copy()
+        n_commuters = int((city.work_loc >= city.n_locations).sum())
+        del whole, part
     else:
+        city = scenario.City(args.persons, seed=CITY_SEED)
         person_bases = np.array([0, city.n_persons])
         loc_bases = np.array([0, city.n_locations])
     total = args.preroll + args.warmup + args.steps
@@ -397,24 +503,7 @@ def run_ours(args):
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
-            bx = None
-            if exchange[0] == "p2p":
-                # the shards map each other's receive regions (CUDA IPC); if that is not possible on this machine, every
-                # rank falls back to the NCCL block exchange
-                try:
-                    bx = sharded.PeerExchange(sh, guest_capacity[0], candidate_capacity=4096)
-                    bx.connect()
-                    bx.set_sources([(rank - 1) % world])  # commuters come from the previous tile only
-                    ok = 1
-                except Exception as e:  # noqa: BLE001
-                    print(f"[bench] rank {rank}: peer-to-peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
-                    bx, ok = None, 0
-                flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if int(flag.item()) == 0:
-                    exchange[0], bx = "nccl", None
-            if bx is None:
-                bx = sharded.BlockExchange(sh, guest_capacity[0], candidate_capacity=4096)
+            bx, exchange[0] = open_exchange(sh, guest_capacity[0], 16384, exchange[0], rank)
         eng.seed_infections(N_INFECTED)
         engines.append(eng)
         return eng, bx, torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -435,33 +524,22 @@ def run_ours(args):
         return bx.step_window(24.0 * (d + 1), remote_cols, offsets)
 
     def split_day(st, open_remote):
-        """global ids; the stays in the next tile's locations are the remote ones (kept while they are open)"""
-        person = (st["person"].astype(np.int64) + person_bases[rank]).astype(np.int32)
-        loc = city.global_location_ids(st["loc"], int(loc_bases[rank]), int(loc_bases[nxt]))
-        is_remote = st["loc"] >= city.n_locations
-        cols = {"person": person, "loc": loc, "sub": st["sub"], "t_in": st["t_in"], "t_out": st["t_out"]}
-        loc_cols = {k: v[~is_remote] for k, v in cols.items()}
-        rem = {k: v[is_remote] for k, v in cols.items()}
-        if open_remote is not None and len(open_remote["person"]):
-            # an open remote stay of an earlier day stays a guest until its closed version arrives
-            closed_now = set(zip(rem["person"].tolist(), rem["t_in"].tolist()))
-            keep = np.array([(p, t) not in closed_now for p, t in zip(open_remote["person"].tolist(),
-                                                                      open_remote["t_in"].tolist())], bool)
-            rem = {k: np.concatenate([open_remote[k][keep], rem[k]]) for k in rem}
-        still_open = np.isinf(rem["t_out"])
-        open_next = {k: v[still_open] for k, v in rem.items()}
-        rem, offsets = sharded.sort_by_destination(rem, loc_bases, world)  # the producer groups by destination shard
-        return loc_cols, rem, offsets, open_next
+        """global ids; the stays in other shards' locations are the remote ones (kept while they are open)"""
+        return sharded.split_stays(city, st, rank, person_bases, loc_bases, open_remote)
 
     def pin(cols):
         return {k: torch.from_numpy(np.ascontiguousarray(cols[k])).pin_memory() for k, _ in COLS}
 
     # ---- record pass (untimed): the medlabs activity engine's job, done once on the host ----
     if world > 1:
-        # block capacity of the guest exchange: the commuters' stays of a day, with head-room, agreed by all ranks
-        cap = torch.tensor([int(2 * max(n_commuters, 1024))], dtype=torch.int64, device=dev)
+        # block capacity of the guest exchange (rows per destination shard and window): twice what a day of a healthy
+        # population sends to its busiest destination, agreed by all ranks
+        probe = scenario.ScheduleGenerator(city, SEED)
+        _, _, off0, _ = split_day(probe.generate_day(np.zeros(city.n_persons, np.uint8)), None)
+        cap = torch.tensor([int(2 * max(int(np.diff(off0).max()), 1024))], dtype=torch.int64, device=dev)
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
         guest_capacity[0] = int(cap.item())
+        del probe
     eng, bx, _ = new_engine()
     gen = scenario.ScheduleGenerator(city, SEED)
     days, open_remote = [], None
@@ -521,6 +599,25 @@ def run_ours(args):
             if not after_step:
                 # everything is resident in HBM: the whole job is enqueued (no window waits for the host: the fill
                 # counts of the pools, the work lists and the candidates stay on the device), one wait at the end
+                stats.append(eng.wait())
+        elif isinstance(bx, sharded.PeerExchange):
+            # the same pattern with the peer-to-peer exchange: the window of day d (guests out, candidates back -- flags in
+            # the peers' memory, no host in the loop) is enqueued, the shard's own stays of day d + 1 follow beside it
+            submit_day(eng, d0, cols_of_day(d0)[0], device)
+            for d in range(d0, d1):
+                if d + 1 < d1 and not device:
+                    c = cols_of_day(d + 1)[0]
+                    eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
+                bx.step_window(24.0 * (d + 1), cols_of_day(d)[1], cols_of_day(d)[2], wait=False)
+                if d + 1 < d1:
+                    if device:
+                        submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
+                    else:
+                        eng.submit_visits_end()
+                if after_step:
+                    stats.append(eng.wait())
+                    after_step()
+            if not after_step:
                 stats.append(eng.wait())
         else:
             for d in range(d0, d1):
@@ -668,7 +765,7 @@ def run_ours(args):
         "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
         "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city, world, n_commuters, exchange[0]),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, city, world, exchange[0]),
         "clocks": clocks.summary(),
         "timing": "CUDA events on the engine stream around the K steps, max over ranks; wall clock of the same region: "
                   f"{1e3 * wall_seconds / args.steps:.4f} ms/step",
@@ -683,7 +780,12 @@ def run_ours(args):
     if dev_sched is not None:
         line["e2e_device_schedule"] = dev_sched
     if world > 1:
-        line["cross_tile_stays_per_step_rank0"] = remote_rows
+        line["cross_shard_stays_per_step_rank0"] = remote_rows
+        line["rank0_shard"] = {"persons": city.n_persons, "locations": city.n_locations,
+                               "persons_working_in_another_shard": n_commuters}
+        line["cross_shard_fraction_rank0"] = remote_rows / max(1.0, visits / args.steps)
+        if parity is not None:
+            line["parity"] = parity
     elif args.cpu_days > 0:
         # ---- cpu_baseline: the oracle on a bounded sample (first cpu_days days), checked against the GPU run ----
         cpu_days = min(args.cpu_days, total)

@@ -349,13 +349,19 @@ int32_t heros_import_candidate_blocks_device(heros_handle h, int32_t n_blocks, i
 int32_t heros_exchange_create(heros_handle h, int32_t rank, int32_t n_peers, int64_t guest_capacity,
                               int64_t candidate_capacity, void* ipc_handle_out, void** region_out);
 int32_t heros_exchange_connect(heros_handle h, const void* ipc_handles, void* const* local_regions);
-/* optional: only the shards in source_mask (bit s = shard s) ever send guests to this shard, so only their flags are
- * awaited (default: all).  With a sparse commuting pattern a shard then synchronises with its neighbours only. */
+/* optional: only the shards in source_mask (bit s = shard s) ever send guests to this shard, so only their guest flags
+ * are awaited (default: all).  With a mask the candidate flags of ALL peers are awaited instead of only those of the
+ * shards this one sent guests to: that wait is then what keeps a shard from running two windows ahead of a peer. */
 int32_t heros_exchange_set_sources(heros_handle h, uint64_t source_mask);
 /* the seven calls of a window in one (begin .. finish), for hosts that do nothing in between */
 int32_t heros_window_run_peers(heros_handle h, double t_until, const int64_t* row_offsets, const int32_t* person,
                                const int32_t* location, const int16_t* sublocation, const double* t_in, const double* t_out,
                                const int32_t* person_bases, heros_step_stats* stats);
+/* the same without waiting for the device (heros_window_finish_async at the end): windows can be enqueued back to back,
+ * heros_wait collects them.  The peers hold each other back through the flags, never by more than one window. */
+int32_t heros_window_run_peers_async(heros_handle h, double t_until, const int64_t* row_offsets, const int32_t* person,
+                                     const int32_t* location, const int16_t* sublocation, const double* t_in,
+                                     const double* t_out, const int32_t* person_bases);
 int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, const int32_t* person, const int32_t* location,
                                  const int16_t* sublocation, const double* t_in, const double* t_out);
 int32_t heros_window_recv_guests(heros_handle h);

@@ -121,6 +121,7 @@ SIGNATURES = {
     "heros_exchange_connect": (C.c_int32, [_P, _P, _P]),
     "heros_exchange_set_sources": (C.c_int32, [_P, C.c_uint64]),
     "heros_window_run_peers": (C.c_int32, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(StepStats)]),
+    "heros_window_run_peers_async": (C.c_int32, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
     "heros_window_send_guests": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P]),
     "heros_window_recv_guests": (C.c_int32, [_P]),
     "heros_window_send_candidates": (C.c_int32, [_P, _P]),

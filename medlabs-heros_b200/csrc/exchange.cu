@@ -607,6 +607,20 @@ int32_t heros_window_run_peers(heros_handle h, double t_until, const int64_t* ro
     return heros_window_finish(h, stats);
 }
 
+int32_t heros_window_run_peers_async(heros_handle h, double t_until, const int64_t* row_offsets, const int32_t* person,
+                                     const int32_t* location, const int16_t* sublocation, const double* t_in, const double* t_out,
+                                     const int32_t* person_bases)
+{
+    int32_t rc;
+    if ((rc = heros_window_begin(h, t_until)) != HEROS_OK) return rc;
+    if ((rc = heros_window_send_guests(h, row_offsets, person, location, sublocation, t_in, t_out)) != HEROS_OK) return rc;
+    if ((rc = heros_window_recv_guests(h)) != HEROS_OK) return rc;
+    if ((rc = heros_window_transmit(h)) != HEROS_OK) return rc;
+    if ((rc = heros_window_send_candidates(h, person_bases)) != HEROS_OK) return rc;
+    if ((rc = heros_window_recv_candidates(h)) != HEROS_OK) return rc;
+    return heros_window_finish_async(h);
+}
+
 int32_t heros_window_send_guests(heros_handle h, const int64_t* row_offsets, const int32_t* person, const int32_t* location,
                                  const int16_t* sublocation, const double* t_in, const double* t_out)
 {
@@ -676,8 +690,17 @@ int32_t heros_window_recv_candidates(heros_handle h)
     if (!h->xc.connected) return fail(h, HEROS_ERR_INVALID, "heros_exchange_connect has not been called");
     if (h->win_state != 2) return fail(h, HEROS_ERR_INVALID, "candidates are received between heros_window_transmit and heros_window_finish");
     cudaSetDevice(h->cfg.device);
+    // Candidates can only come back from the shards this one sent guests to, so only their blocks are parsed.  Which
+    // flags are awaited is a matter of flow control: with every shard listening to every shard for guests, a peer can be
+    // at most one window ahead and waiting for the senders' targets is enough.  With a source mask
+    // (heros_exchange_set_sources) the guest wait no longer couples all shards, and a shard that sends nothing for two
+    // windows could overwrite a guest block that has not been parsed yet: then the candidate flags of ALL peers are
+    // awaited (every shard raises them every window, after it has parsed its guests).
+    const unsigned long long all = h->xc.n >= 64 ? ~0ull : ((1ull << h->xc.n) - 1ull);
+    const unsigned long long others = all & ~(1ull << h->xc.rank);
+    const bool masked = (h->xc.sources & others) != others;
     k_p2p_wait<<<1, MAX_PEERS, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(h->xc.region) + 64, h->xc.n,
-                                               h->xc.sent_to, h->xc.seq, h->d_ctr.p);
+                                               masked ? others : h->xc.sent_to, h->xc.seq, h->d_ctr.p);
     CU(h, cudaGetLastError());
     return heros_import_candidate_blocks_from(h, h->xc.sent_to);
 }

@@ -326,6 +326,13 @@ class HerosEngine:
                                                      _p(person_bases), C.byref(st)))
         return st.as_dict()
 
+    def window_run_peers_async(self, t_until: float, row_offsets: np.ndarray, person: int, loc: int, sub: int, t_in: int,
+                               t_out: int, person_bases: np.ndarray) -> None:
+        """heros_window_run_peers_async: the whole window enqueued, nothing waited for; collect with ``wait``."""
+        self._check(self._lib.heros_window_run_peers_async(self._h, float(t_until), _p(row_offsets),
+                                                           *(C.c_void_p(x) for x in (person, loc, sub, t_in, t_out)),
+                                                           _p(person_bases)))
+
     def window_send_guests(self, row_offsets, person: int, loc: int, sub: int, t_in: int, t_out: int):
         off = _arr(row_offsets, np.int64)
         self._check(self._lib.heros_window_send_guests(self._h, _p(off), *(C.c_void_p(x) for x in (person, loc, sub, t_in, t_out))))

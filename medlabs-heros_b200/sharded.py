@@ -355,19 +355,24 @@ class PeerExchange:
         """Only these shards ever send guests to this one: only their flags are awaited (default: all shards)."""
         self.shard.engine.exchange_set_sources(ranks)
 
-    def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets, group=None):
+    def step_window(self, t_until: float, remote: Optional[Dict[str, torch.Tensor]], row_offsets, group=None, wait: bool = True):
         """One window, one call into the library: begin, send / receive guests, transmit, send / receive candidates,
-        finish -- all enqueued on the engine stream, one host synchronisation at the end."""
+        finish -- all enqueued on the engine stream, one host synchronisation at the end (``wait=False``: none; the
+        windows are then collected with ``engine.wait()``)."""
         import numpy as np
         sh = self.shard
         with sh.on_stream():
             if remote is not None and remote["person"].device != sh.device:  # pinned host columns: H2D on the engine stream
                 remote = {k: v.to(sh.device, non_blocking=True) for k, v in remote.items()}
-            self._keep = remote
+            self._keep_ring = getattr(self, "_keep_ring", [])
+            self._keep_ring.append(remote)  # read asynchronously by the pack kernel: kept for a few windows
+            del self._keep_ring[:-4]
             ptrs = [0] * 5 if remote is None or remote["person"].numel() == 0 else [remote[k].data_ptr() for k in self.VISIT_COLUMNS]
             off = np.ascontiguousarray(row_offsets, np.int64)
             sh.sent_stays += int(off[-1])
-            return sh.engine.window_run_peers(t_until, off, *ptrs, self.person_bases)
+            if wait:
+                return sh.engine.window_run_peers(t_until, off, *ptrs, self.person_bases)
+            return sh.engine.window_run_peers_async(t_until, off, *ptrs, self.person_bases)
 
 
 def step_window_peers_in_process(exchanges: List[PeerExchange], t_until: float, remotes, offsets):

@@ -36,4 +36,4 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_do_nothing():
     assert run_bench(["--gpus", "2", "--ref-cores", "1"], env={"RANK": "1", "WORLD_SIZE": "2"}) == []
     lines = run_bench(["--gpus", "2", "--ref-cores", "1"], env={"RANK": "0", "WORLD_SIZE": "2"})
-    assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and "2 tiles" in lines[0]["config"]["workload"]
+    assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and "2 geographic shards" in lines[0]["config"]["workload"]
