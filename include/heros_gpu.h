@@ -149,6 +149,18 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
 int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const uint8_t* female, const uint8_t* role,
                           const int32_t* home_location, const int16_t* home_sublocation,
                           const int32_t* work_location);
+/* Rate-based locations = the medlabs LocationProbBased objects the reference builds for the rows of
+ * data/<city>/epidemiology/infection_rates.csv (factory/ConstructHerosModel.java:274-295, 382-388: the satellite towns and
+ * countries of the commuter roles), constructor arguments (infectionRateFactor, infectionRate, referenceGroupMap,
+ * Covid19Progression.exposed).  location: ids of heros_set_locations; exactly one of rate_factor[i] / rate[i] is >= 0 (the
+ * file holds -1 in the other column).  No occupancy-based transmission takes place in such a location; a susceptible
+ * person who leaves it at time t after a stay of d hours is exposed iff U(seed; person, t) < 1 - exp(-lambda d / 24) with
+ * lambda = rate (per day), or rate_factor x the share of the reference group (social role 7, Worker:
+ * ConstructHerosModel.java:303-308) that was exposed during the previous simulated day.  The class itself is inside the
+ * un-vendored medlabs jar: this rule is a stated convention, shared with the oracle.  With a factor-driven
+ * location a window must not span a midnight (HEROS_ERR_UNSUPPORTED otherwise).  n = 0 removes the table. */
+int32_t heros_set_rate_locations(heros_handle h, int32_t n, const int32_t* location, const double* rate_factor,
+                                 const double* rate);
 
 /* ---- model parameters ---- */
 int32_t heros_set_transmission_area(heros_handle h, const heros_area_params* p);     /* Covid19TransmissionArea(model) */

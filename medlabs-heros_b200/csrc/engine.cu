@@ -90,6 +90,8 @@ __device__ __forceinline__ void expose_agent(const AgentArrays& A, uint32_t pers
 {
     count_move(A, view_phase(v), PH_E);
     log_transition(A, person, PH_E, t);
+    if (view_role(v) == ROLE_REFERENCE)  // the rate of the rate-based locations follows the reference group, day by day
+        atomicAdd(&A.ctr->ref_exposed[((long long) floor(t / 24.0)) & 3], 1ull);
     v = view_set(v, 0, 0xF, PH_E);
     v = view_set_exposure(v, (float) t);
     uint32_t next_phase;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(TPB) k_window_open(const AgentArrays A, uint32
                                                      uint32_t* __restrict__ agent_rank)
 {
     TlStamp tl_(A.ctr, TL_OPEN);
+    if (blockIdx.x == 0 && threadIdx.x == 0)  // the slot of tomorrow's exposures of the reference group starts from zero
+        A.ctr->ref_exposed[((long long) floor(nextafter(T1, 0.0) / 24.0) + 1) & 3] = 0ull;
     if (blockIdx.x < pool_blocks)
     {
         // stays carried over from earlier windows (the newer ones took their ticket when they were submitted)
@@ -1004,6 +1008,10 @@ int32_t check_ready(heros_handle h)
 // stay in HBM, the host only keeps upper bounds (exact again after every synchronising call).
 int32_t window_begin(heros_handle h, double T1)
 {
+    // a rate-based location that follows the reference group uses the exposures of the PREVIOUS simulated day, which must
+    // be complete when the window starts: such a window lies inside one day
+    if (h->rate_factor_mode && std::floor(h->t_now / 24.0) != std::floor(std::nextafter(T1, 0.0) / 24.0))
+        return fail(h, HEROS_ERR_UNSUPPORTED, "with rate-based locations that follow the reference group a window must not span a midnight");
     cudaStream_t s = h->stream;
     const uint32_t N = h->n_agents;
     h->win_T0 = h->t_now;
@@ -1105,7 +1113,7 @@ int32_t window_transmit(heros_handle h)
     for (int k = 1; k < N_HOT; ++k) big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, h->hot_seg[k].n);
     big.hot_cap = (uint32_t) std::min<size_t>(big.hot_cap, 0x7fffffffu);
     big.huge_off = h->huge_off.p; big.scratch_cap = h->scratch.n;
-    big.key_total = h->n_total_loc ? h->d_key_total.p : nullptr;
+    big.key_total = (h->n_total_loc || h->n_rate_loc) ? h->d_key_total.p : nullptr;
     big.need_enters = h->cfg.trigger == HEROS_TRIGGER_ENTER_AND_EXIT || h->cfg.model == HEROS_MODEL_DISTANCE;
     k_scan_lookback<<<n_tiles, TPB, 0, s>>>(h->bk_count.p, n_keys, h->seg_start.p, h->scan_status.p, n_tiles, h->d_ctr.p,
                                             big);
@@ -1144,7 +1152,8 @@ int32_t window_transmit(heros_handle h)
     c.T0 = T0; c.T1 = T1; c.model = h->cfg.model; c.trigger = h->cfg.trigger; c.seed = h->cfg.seed;
     c.area = h->area; c.dist = h->dist; c.policy = h->d_policy.p; c.n_policy = (int) h->policy.size();
     c.key_loc = h->d_key_loc.p; c.loc_param = h->d_loc_param.p; c.last_calc = h->d_last_calc.p; c.n_keys = h->n_keys;
-    c.key_total = h->n_total_loc ? h->d_key_total.p : nullptr; c.total_loc = h->d_total_loc.p; c.n_total_loc = h->n_total_loc;
+    c.key_total = (h->n_total_loc || h->n_rate_loc) ? h->d_key_total.p : nullptr; c.total_loc = h->d_total_loc.p; c.n_total_loc = h->n_total_loc;
+    c.rate_loc = h->d_rate_loc.p; c.n_rate_loc = h->n_rate_loc;
     c.view = h->d_view.p; c.ill_end = h->d_ill_end.p; c.guest_ill_end = h->g_ill_end.p;
     c.person_base = h->person_base; c.n_agents = N;
     c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
@@ -1220,6 +1229,7 @@ int32_t check_window_length(heros_handle h, double T1)
     const double latent = h->cfg.model == HEROS_MODEL_AREA ? h->area.t_e_min : h->dist.L;
     if (!(h->cfg.window_hours <= latent - 1e-3) || !(T1 - h->t_now <= latent - 1e-3))
         return fail(h, HEROS_ERR_UNSUPPORTED, "the window must be shorter than the latent period of the transmission model");
+
     return HEROS_OK;
 }
 
@@ -1326,7 +1336,7 @@ int32_t heros_destroy(heros_handle h)
     for (auto& a : h->aux) if (a) cudaStreamSynchronize(a);
     h->d_policy.release(); h->d_prog.release(); h->d_loc_base.release(); h->d_key_loc.release();
     h->d_loc_nsub.release(); h->d_loc_param.release(); h->d_last_calc.release(); h->d_view.release();
-    h->d_key_total.release(); h->d_total_loc.release(); h->d_loc_key.release();
+    h->d_key_total.release(); h->d_total_loc.release(); h->d_loc_key.release(); h->d_rate_loc.release();
     h->d_next_time.release(); h->d_ill_end.release(); h->d_open_tin.release(); h->d_best_t.release();
     h->d_best_key.release(); h->d_claim.release(); h->d_open_key.release();
     for (int i = 0; i < 2; ++i)
@@ -1450,12 +1460,14 @@ int32_t heros_set_locations(heros_handle h, int32_t n, const uint8_t* type, cons
     CU(h, cudaMemcpyAsync(h->d_loc_param.p, lp.data(), (size_t) n * sizeof(LocParam), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemsetAsync(h->d_last_calc.p, 0, (size_t) h->n_keys * 8, h->stream));
     h->n_total_loc = (uint32_t) total.size();
-    h->d_key_total.release(); h->d_total_loc.release();
+    h->n_rate_loc = 0; h->rate_factor_mode = false;
+    h->d_key_total.release(); h->d_total_loc.release(); h->d_rate_loc.release();
+    h->h_key_flag.assign(h->n_keys, 0);
     if (!total.empty())
     {
-        std::vector<uint8_t> flag(h->n_keys, 0);
+        std::vector<uint8_t>& flag = h->h_key_flag;
         for (const TotalLoc& t : total)
-            for (uint32_t k = t.first_key; k < t.end_key; ++k) flag[k] = 1;
+            for (uint32_t k = t.first_key; k < t.end_key; ++k) flag[k] = KEYFLAG_TOTAL;
         CU(h, h->d_key_total.ensure(h->n_keys)); CU(h, h->d_total_loc.ensure(total.size()));
         CU(h, cudaMemcpyAsync(h->d_key_total.p, flag.data(), h->n_keys, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaMemcpyAsync(h->d_total_loc.p, total.data(), total.size() * sizeof(TotalLoc), cudaMemcpyHostToDevice, h->stream));
@@ -1509,6 +1521,9 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
                                                         d_female.p, d_role.p, (uint32_t) n);
     Counters zero{};
     zero.phase_counts[PH_S] = n;
+    if (role)
+        for (int32_t i = 0; i < n; ++i) zero.n_ref += role[i] == (uint8_t) ROLE_REFERENCE ? 1ull : 0ull;
+    { Counters live{}; cudaMemcpy(&live, h->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost); zero.timeline = live.timeline; }
     CU(h, cudaMemcpyAsync(h->d_ctr.p, &zero, sizeof(Counters), cudaMemcpyHostToDevice, h->stream));
     { const int32_t rc_ = sync_counters(h); if (rc_ != HEROS_OK) return rc_; }
     d_age.release(); d_female.release(); d_role.release();
@@ -1520,6 +1535,51 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     h->o_inf_n = h->o_tr_n = ~0ull;  // the event logs start again: the sorted output caches are stale
     h->invalid_reported = 0;
     CU(h, cudaStreamSynchronize(h->stream));
+    return HEROS_OK;
+}
+
+int32_t heros_set_rate_locations(heros_handle h, int32_t n, const int32_t* location, const double* rate_factor,
+                                 const double* rate)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (h->n_loc == 0) return fail(h, HEROS_ERR_INVALID, "heros_set_locations must be called first");
+    if (n < 0 || (n > 0 && (!location || !rate_factor || !rate))) return fail(h, HEROS_ERR_INVALID, "null argument");
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = check_idle(h, "heros_set_rate_locations");
+    if (rc != HEROS_OK) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::vector<RateLoc> table;
+    std::vector<uint8_t> flag = h->h_key_flag;
+    for (uint8_t& f : flag) f &= (uint8_t) ~KEYFLAG_RATE;
+    bool factor_mode = false;
+    for (int i = 0; i < n; ++i)
+    {
+        const int64_t l = (int64_t) location[i] - h->location_base;
+        if (l < 0 || l >= (int64_t) h->n_loc) return fail(h, HEROS_ERR_INVALID, "rate-based location outside the location table");
+        if (!(rate[i] >= 0.0) && !(rate_factor[i] >= 0.0))
+            return fail(h, HEROS_ERR_INVALID, "a rate-based location needs an infection rate or an infection-rate factor (>= 0)");
+        RateLoc r{h->h_loc_base[l], h->h_loc_base[l + 1], rate_factor[i], rate[i] >= 0.0 ? rate[i] : -1.0};
+        for (uint32_t k = r.first_key; k < r.end_key; ++k)
+        {
+            if (flag[k] & KEYFLAG_RATE) return fail(h, HEROS_ERR_INVALID, "a rate-based location is listed twice");
+            flag[k] |= KEYFLAG_RATE;
+        }
+        factor_mode = factor_mode || !(rate[i] >= 0.0);
+        table.push_back(r);
+    }
+    h->h_key_flag = flag;
+    h->n_rate_loc = (uint32_t) table.size();
+    h->rate_factor_mode = factor_mode;
+    if (h->n_rate_loc || h->n_total_loc)
+    {
+        CU(h, h->d_key_total.ensure(h->n_keys));
+        CU(h, cudaMemcpy(h->d_key_total.p, flag.data(), h->n_keys, cudaMemcpyHostToDevice));
+    }
+    if (h->n_rate_loc)
+    {
+        CU(h, h->d_rate_loc.ensure(table.size()));
+        CU(h, cudaMemcpy(h->d_rate_loc.p, table.data(), table.size() * sizeof(RateLoc), cudaMemcpyHostToDevice));
+    }
     return HEROS_OK;
 }
 

@@ -83,6 +83,14 @@ __device__ __forceinline__ unsigned long long global_ns()
 }
 #endif
 
+// a rate-based location (medlabs LocationProbBased, factory/ConstructHerosModel.java:382-388): no occupancy-based
+// transmission; a susceptible person leaving it after a stay of d hours is exposed with p = 1 - exp(-lambda d / 24),
+// lambda = rate (per day) if rate >= 0, else factor x the share of the reference group exposed the day before
+struct RateLoc { uint32_t first_key, end_key; double factor, rate; };
+constexpr uint32_t TAG_RATE = 0x500u;     // draw of a rate-based location, keyed by (person, exit time)
+constexpr uint32_t ROLE_REFERENCE = 7u;   // Worker: the reference group of the satellite person types (ConstructHerosModel.java:303-308)
+constexpr uint8_t KEYFLAG_TOTAL = 1, KEYFLAG_RATE = 2;
+
 struct PolicyChange { double t; int32_t which; int32_t pad; double value; };  // which: 0 psi, 1 mu
 
 // device-side counters of one engine.  The block from `n_cand` on is zeroed at the start of every window.
@@ -112,7 +120,11 @@ struct Counters
     unsigned long long cand_total;   // candidate infections kept, summed over the windows
     unsigned long long rate_draws;   // draws of the rate-based locations (LocationProbBased)
     unsigned long long* timeline;    // heros_debug_timeline: per kernel {first block start, last block end} (globaltimer ns), or NULL
-    unsigned long long reserved_[3];
+    // rate-based locations (LocationProbBased): persons of the reference group (role Worker) exposed per simulated day,
+    // a ring over day % 4, and the size of the group
+    unsigned long long ref_exposed[4];
+    unsigned long long n_ref;
+    unsigned long long reserved_[2];
     // ---- per window ----
     unsigned long long n_cand;       // candidate infections of the current window (first field of the window block)
     unsigned long long n_sub[2];     // segments queued for the sub-warp kernels: [0] <= 8 stays, [1] 9..32 stays
@@ -175,7 +187,9 @@ struct WindowCtx
     const PolicyChange* policy; int n_policy;
     // static tables
     const uint32_t* key_loc; const LocParam* loc_param; double* last_calc; uint32_t n_keys;
-    const uint8_t* key_total;  // per key: 1 = its location takes the total-location branch (nullptr: no such location)
+    const uint8_t* key_total;  // per key: KEYFLAG_TOTAL = its location takes the total-location branch, KEYFLAG_RATE = rate-based
+                               // (neither is touched by the occupancy kernels; nullptr: no such location)
+    const RateLoc* rate_loc; uint32_t n_rate_loc;
     const TotalLoc* total_loc; uint32_t n_total_loc;
     // agents (own: indexed by global id - person_base; guests: by the index in StayRec::pad)
     const uint64_t* view; const double* ill_end; const double* guest_ill_end;

@@ -106,7 +106,11 @@ struct heros_engine
     DevBuf<uint2> d_loc_key;  // {first key, number of sub-locations} of every location, for k_submit
     DevBuf<LocParam> d_loc_param;
     DevBuf<double> d_last_calc;
-    DevBuf<uint8_t> d_key_total;     // total-branch locations (usually none)
+    DevBuf<uint8_t> d_key_total;     // per key: KEYFLAG_TOTAL / KEYFLAG_RATE (allocated only if there is such a location)
+    std::vector<uint8_t> h_key_flag;
+    DevBuf<RateLoc> d_rate_loc;      // rate-based locations (heros_set_rate_locations)
+    uint32_t n_rate_loc = 0;
+    bool rate_factor_mode = false;   // some location follows the reference group: windows must not span a midnight
     DevBuf<TotalLoc> d_total_loc;
     uint32_t n_total_loc = 0;
 

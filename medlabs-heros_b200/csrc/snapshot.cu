@@ -59,7 +59,7 @@ int32_t describe(heros_handle h, SnapshotHeader& s)
     cudaSetDevice(h->cfg.device);
     if ((rc = sync_counters(h)) != HEROS_OK) return rc;
     memset(&s, 0, sizeof s);
-    s.magic = SNAPSHOT_MAGIC; s.version = 2; s.model = (uint32_t) h->cfg.model; s.seed = h->cfg.seed;
+    s.magic = SNAPSHOT_MAGIC; s.version = 3; s.model = (uint32_t) h->cfg.model; s.seed = h->cfg.seed;
     s.n_agents = h->n_agents; s.n_keys = h->n_keys; s.n_fresh = (uint32_t) h->h_ctr->n_fresh; s.n_carry = (uint32_t) h->h_ctr->n_carry;
     s.n_policy = (uint32_t) h->policy.size(); s.n_series = (uint32_t) h->series_t.size();
     s.n_closure = (uint32_t) h->h_closure.size(); s.closure_active = h->closure_active ? 1u : 0u;
@@ -127,7 +127,7 @@ int32_t heros_snapshot_load(heros_handle h, int64_t bytes, const void* blob)
     if ((size_t) bytes < sizeof(SnapshotHeader)) return fail(h, HEROS_ERR_INVALID, "not a snapshot");
     SnapshotHeader s;
     memcpy(&s, blob, sizeof s);
-    if (s.magic != SNAPSHOT_MAGIC || s.version != 2) return fail(h, HEROS_ERR_INVALID, "not a snapshot of this engine version");
+    if (s.magic != SNAPSHOT_MAGIC || s.version != 3) return fail(h, HEROS_ERR_INVALID, "not a snapshot of this engine version");
     // the static inputs (heros_set_*) are the host's to repeat; they must describe the same model
     if (s.n_agents != h->n_agents || s.n_keys != h->n_keys || s.model != (uint32_t) h->cfg.model || s.seed != h->cfg.seed)
         return fail(h, HEROS_ERR_INVALID, "the snapshot was taken with other persons, locations, model or seed");

@@ -1099,6 +1099,7 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
     for (uint32_t li = blockIdx.x; li < c.n_total_loc; li += gridDim.x)
     {
         const TotalLoc L = c.total_loc[li];
+        if (c.key_total[L.first_key] & KEYFLAG_RATE) continue;  // a rate-based location: k_rate_locations
         const uint32_t a0 = c.seg_start[L.first_key], a1 = c.seg_start[L.end_key];
         const uint32_t n_all = a1 - a0;
         if (n_all == 0) continue;
@@ -1201,6 +1202,55 @@ __global__ void __launch_bounds__(256) k_transmit_total(const WindowCtx c)
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------
+// rate-based locations (medlabs LocationProbBased, factory/ConstructHerosModel.java:382-388; data/*/epidemiology/
+// infection_rates.csv): the satellite towns and countries of the commuter roles.  The class lives in the un-vendored
+// medlabs jar (INFERRED); the rule implemented here -- and, statement for statement, in the oracle -- is
+// the convention of DESIGN.md 3.5: no occupancy-based evaluation in such a location; a susceptible person who leaves it
+// at time t after a stay of d hours is exposed iff U(seed; person, t, TAG_RATE) < 1 - exp(-lambda d / 24), with
+// lambda = infection_rate (per day) where the file gives one, else infection_rate_factor x the share of the reference
+// group (Worker) that was exposed during the previous simulated day.  One block per location.
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_rate_locations(const WindowCtx c)
+{
+    TlStamp tl_(c.ctr, TL_RATE);
+    Local st;
+    const long long day = (long long) floor(c.T0 / 24.0);
+    double ref_share = 0.0;
+    if (day > 0 && c.ctr->n_ref > 0)
+        ref_share = (double) c.ctr->ref_exposed[(day - 1) & 3] / (double) c.ctr->n_ref;
+    for (uint32_t li = blockIdx.x; li < c.n_rate_loc; li += gridDim.x)
+    {
+        const RateLoc L = c.rate_loc[li];
+        const double lambda = L.rate >= 0.0 ? L.rate : L.factor * ref_share;
+        if (!(lambda > 0.0)) continue;
+        const uint32_t a0 = c.seg_start[L.first_key], a1 = c.seg_start[L.end_key];
+        for (uint32_t i = a0 + threadIdx.x; i < a1; i += blockDim.x)
+        {
+            const StayRec r = ld_rec(c.rec + i);
+            if (!(r.tout >= c.T0 && r.tout < c.T1) || !phase_is_susceptible(view_tphase(r.view))) continue;
+            const double x = lambda * ((r.tout - r.tin) / 24.0);
+            const double p = 1.0 - hexp(-x);
+            const double u = u01(c.seed, r.person, f64_bits(r.tout), TAG_RATE);
+            st.draws++;
+            if (u < p)
+            {
+                // the sub-location key of the record: the segment it lies in
+                uint32_t key = L.first_key;
+                while (key + 1 < L.end_key && c.seg_start[key + 1] <= i) ++key;
+                push_candidate(c, r.person, key, r.tout, p);
+            }
+        }
+    }
+    st.draws = (unsigned long long) warp_sum((double) st.draws);
+    if ((threadIdx.x & 31) == 0 && st.draws)
+    {
+        atomicAdd(&c.ctr->draws, st.draws);
+        atomicAdd(&c.ctr->rate_draws, st.draws);
+    }
+}
+
 // host-side launcher ----------------------------------------------------------------------------------------------------
 // The hot path (its work lists were filled by the prefix-sum kernel) starts at once on the auxiliary streams, side by
 // side with the kernel that streams the small sub-locations and the sub-warp kernels it feeds (they touch disjoint
@@ -1251,6 +1301,11 @@ static void launch_model(const WindowCtx& c, int n_sm, const TransmitStreams& ts
     if (c.n_total_loc)
     {
         k_transmit_total<MODEL><<<(int) min((uint32_t) (n_sm * 4), c.n_total_loc), 256, 0, s>>>(c);
+        ++launches;
+    }
+    if (c.n_rate_loc)
+    {
+        k_rate_locations<MODEL><<<(int) min((uint32_t) (n_sm * 4), c.n_rate_loc), 256, 0, s>>>(c);
         ++launches;
     }
 }

@@ -119,6 +119,14 @@ class HerosEngine:
         self._check(self._lib.heros_seed_infections(self._h, n_infected, min_age, max_age, _p(out)))
         return out
 
+    def set_rate_locations(self, location, rate_factor, rate):
+        """heros_set_rate_locations: the LocationProbBased rows of infection_rates.csv (location id, infection_rate_factor,
+        infection_rate; -1 = not given)."""
+        a, b, c = _arr(location, np.int32), _arr(rate_factor, np.float64), _arr(rate, np.float64)
+        if not (len(a) == len(b) == len(c)):
+            raise ValueError("rate-location columns differ in length")
+        self._check(self._lib.heros_set_rate_locations(self._h, len(a), _p(a), _p(b), _p(c)))
+
     def submit_visits(self, person, loc, sub, t_in, t_out):
         a = _arr(person, np.int32)
         b = _arr(loc, np.int32)

@@ -144,6 +144,21 @@ def read_people(path: str, locations: Dict[str, np.ndarray], type_names: Optiona
                 work_loc=np.array(out["work_loc"], np.int32), female=female)
 
 
+def read_infection_rates(path: str) -> Dict[str, np.ndarray]:
+    """``epidemiology/infection_rates.csv`` (generic.ProbRatioFilePath; ConstructHerosModel.java:274-295): the locations the
+    reference builds as ``LocationProbBased`` -- columns location_id, infection_rate_factor, infection_rate (-1 = not
+    given), the rest is descriptive.  Returns the three columns heros_set_rate_locations takes."""
+    loc, factor, rate = [], [], []
+    with _open(path) as f:
+        rows = csv.reader(f)
+        next(rows, None)  # header (the reference skips it unread)
+        for row in rows:
+            if not row:
+                continue
+            loc.append(int(row[0])); factor.append(float(row[1])); rate.append(float(row[2]))
+    return {"location": np.array(loc, np.int32), "rate_factor": np.array(factor, np.float64), "rate": np.array(rate, np.float64)}
+
+
 def load_city(locations_path: str, people_path: str, type_names: Optional[Sequence[str]] = None, seed: int = 111,
               n_random_candidates: int = 8) -> "scenario.City":
     """A ``scenario.City`` over the real tables of ``data/<city>/locations/locations.csv.gz`` and

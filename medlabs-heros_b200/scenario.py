@@ -313,6 +313,8 @@ class City:
         if ext is not None:
             far = loc >= self.n_locations
             return np.where(far, ext[np.where(far, loc - self.n_locations, 0)], loc + own_base).astype(np.int32)
+        if other_base is None:  # a city on its own: every location is its own
+            return (loc + own_base).astype(np.int32)
         return np.where(loc >= self.n_locations, loc - self.n_locations + other_base, loc + own_base).astype(np.int32)
 
     def install(self, engine):

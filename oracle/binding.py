@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.orc_sim_set_parameter.restype = C.c_int
         L.orc_sim_set_parameter.argtypes = [P, C.c_char_p, C.c_double, C.c_double]
         L.orc_sim_expose.argtypes = [P, C.c_int, P, P]
+        L.orc_sim_set_roles.argtypes = [P, C.c_int, P]
+        L.orc_sim_set_rate_locations.argtypes = [P, C.c_int, P, P, P]
         L.orc_sim_add_visits.argtypes = [P, C.c_int64, P, P, P, P, P]
         L.orc_sim_run.argtypes = [P, C.c_double]
         for name in ("orc_sim_n_infections", "orc_sim_n_transitions", "orc_sim_n_evaluations", "orc_sim_n_draws"):
@@ -226,6 +228,14 @@ class Sim:
         b = _arr(female, np.uint8)
         self.n_person = len(a)
         lib().orc_sim_set_persons(self._h, len(a), _p(a), _p(b))
+
+    def set_roles(self, role):
+        a = _arr(role, np.uint8)
+        lib().orc_sim_set_roles(self._h, len(a), _p(a))
+
+    def set_rate_locations(self, location, rate_factor, rate):
+        a, b, c = _arr(location, np.int32), _arr(rate_factor, np.float64), _arr(rate, np.float64)
+        lib().orc_sim_set_rate_locations(self._h, len(a), _p(a), _p(b), _p(c))
 
     def set_parameter(self, name, value, at_time):
         return lib().orc_sim_set_parameter(self._h, name.encode(), float(value), float(at_time))

@@ -61,6 +61,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* stream tags (word 3 of the counter) */
 #define TAG_TRANSMIT 0u
+#define TAG_RATE 0x500u /* draw of a rate-based location (LocationProbBased), keyed by (person, exit time) */
+#define ROLE_REFERENCE 7 /* Worker: the reference group of the satellite person types (Construct:303-308) */
 #define TAG_PROG(phase, draw) (0x100u | ((uint32_t) (phase) << 4) | (uint32_t) (draw))
 
 /* U(0,1) with 53 random bits, in [0,1): stands in for model.getU01().draw() (TArea:190, TDist:181, Prog:189). */
@@ -433,6 +435,12 @@ struct orc_sim
     int64_t counts[ORC_NPHASE];
     int64_t n_eval, n_draws;
     int32_t* scratch_a; int32_t* scratch_b; int32_t* scratch_all; int64_t cap_scratch;
+
+    /* rate-based locations (medlabs LocationProbBased, Construct:382-388): see rate_exit() */
+    uint8_t* role; int64_t n_ref;
+    int64_t* ref_exposed; int64_t n_ref_days; /* persons of the reference group exposed per simulated day */
+    uint8_t* loc_rate_kind; double* loc_rate_factor; double* loc_rate; /* kind: 0 none, 1 rate-based */
+    double* stay_tin; /* when the person entered the place it is in */
 };
 
 orc_sim* orc_sim_create(int model, int trigger, uint64_t seed)
@@ -453,6 +461,7 @@ void orc_sim_destroy(orc_sim* s)
     free(s->pos_in_set); free(s->open_key); free(s->open_tin);
     free(s->ev); free(s->heap); free(s->pol); free(s->inf); free(s->tr);
     free(s->scratch_a); free(s->scratch_b); free(s->scratch_all);
+    free(s->role); free(s->ref_exposed); free(s->loc_rate_kind); free(s->loc_rate_factor); free(s->loc_rate); free(s->stay_tin);
     free(s);
 }
 
@@ -503,6 +512,7 @@ void orc_sim_set_persons(orc_sim* s, int n, const int8_t* age, const uint8_t* fe
     s->pos_in_set = (int32_t*) malloc(n * 4);
     s->open_key = (uint32_t*) malloc(n * 4);
     s->open_tin = (double*) malloc(n * 8);
+    s->stay_tin = (double*) calloc(n, 8);
     for (int i = 0; i < n; ++i) { s->next_time[i] = INFINITY; s->pos_in_set[i] = -1; s->open_key[i] = 0xFFFFFFFFu; s->open_tin[i] = 0.0; }
     memset(s->counts, 0, sizeof(s->counts));
     s->counts[ORC_S] = n;
@@ -594,6 +604,18 @@ static void record_transition(orc_sim* s, int32_t person, uint8_t phase, double 
 /* Prog:182-201 */
 static void expose(orc_sim* s, int32_t person, double now)
 {
+    if (s->role && s->role[person] == ROLE_REFERENCE)
+    {
+        int64_t day = (int64_t) floor(now / 24.0);
+        if (day >= s->n_ref_days)
+        {
+            int64_t n = 2 * (day + 1) + 16;
+            s->ref_exposed = (int64_t*) realloc(s->ref_exposed, (size_t) n * sizeof(int64_t));
+            for (int64_t k = s->n_ref_days; k < n; ++k) s->ref_exposed[k] = 0;
+            s->n_ref_days = n;
+        }
+        s->ref_exposed[day]++;
+    }
     s->counts[s->phase[person]]--; /* Prog:184 */
     s->phase[person] = ORC_E;      /* Prog:185 */
     s->counts[ORC_E]++;            /* Prog:186 */
@@ -802,6 +824,65 @@ static void evaluate(orc_sim* s, uint32_t key, double now)
     }
 }
 
+void orc_sim_set_roles(orc_sim* s, int n, const uint8_t* role)
+{
+    free(s->role);
+    s->role = (uint8_t*) malloc((size_t) (n > 0 ? n : 1));
+    memcpy(s->role, role, (size_t) n);
+    s->n_ref = 0;
+    for (int i = 0; i < n; ++i) s->n_ref += role[i] == ROLE_REFERENCE;
+}
+
+/* The rows of data/<city>/epidemiology/infection_rates.csv (Construct:274-295): location id, infection_rate_factor,
+ * infection_rate (-1 = not given). */
+void orc_sim_set_rate_locations(orc_sim* s, int n, const int32_t* loc, const double* factor, const double* rate)
+{
+    free(s->loc_rate_kind); free(s->loc_rate_factor); free(s->loc_rate);
+    s->loc_rate_kind = (uint8_t*) calloc((size_t) s->n_loc, 1);
+    s->loc_rate_factor = (double*) calloc((size_t) s->n_loc, sizeof(double));
+    s->loc_rate = (double*) calloc((size_t) s->n_loc, sizeof(double));
+    for (int i = 0; i < n; ++i)
+    {
+        s->loc_rate_kind[loc[i]] = 1;
+        s->loc_rate_factor[loc[i]] = factor[i];
+        s->loc_rate[loc[i]] = rate[i] >= 0.0 ? rate[i] : -1.0;
+    }
+}
+
+/* A person leaves a rate-based location (medlabs LocationProbBased; the class is not in the reference tree, SURVEY.md C16
+ * INFERRED -- this is the convention of DESIGN.md 3.5, stated once here and once in csrc/transmit.cu:k_rate_locations):
+ * no occupancy-based evaluation; a susceptible person who leaves at time t after a stay of d hours is exposed iff
+ * U(seed; person, t, TAG_RATE) < 1 - exp(-lambda d / 24), lambda = infection_rate (per day) where the file gives one, else
+ * infection_rate_factor x the share of the reference group (Worker) exposed during the previous simulated day. */
+static void rate_exit(orc_sim* s, const move_ev* e, int32_t loc)
+{
+    if (!is_susceptible(s->phase[e->person])) return;
+    double lambda = s->loc_rate[loc];
+    if (!(lambda >= 0.0))
+    {
+        int64_t day = (int64_t) floor(e->t / 24.0);
+        double share = 0.0;
+        if (day > 0 && s->n_ref > 0 && day - 1 < s->n_ref_days) share = (double) s->ref_exposed[day - 1] / (double) s->n_ref;
+        lambda = s->loc_rate_factor[loc] * share;
+    }
+    if (!(lambda > 0.0)) return;
+    double x = lambda * ((e->t - s->stay_tin[e->person]) / 24.0);
+    double p = 1.0 - orc_exp(-x);
+    s->n_draws++;
+    if (orc_u01(s->seed, (uint32_t) e->person, dbl_bits(e->t), TAG_RATE) < p)
+    {
+        if (s->n_inf == s->cap_inf)
+        {
+            s->cap_inf = s->cap_inf ? 2 * s->cap_inf : 1024;
+            s->inf = (infection_ev*) realloc(s->inf, s->cap_inf * sizeof(infection_ev));
+        }
+        infection_ev ev = {e->person, loc, (int16_t) (e->key - s->loc_base[loc]), e->t, p};
+        s->inf[s->n_inf++] = ev;
+        s->exposure[e->person] = (float) e->t; /* contract C3/C4 */
+        expose(s, e->person, e->t);
+    }
+}
+
 void orc_sim_run(orc_sim* s, double t_until)
 {
     if (!s->ev_sorted)
@@ -835,15 +916,19 @@ void orc_sim_run(orc_sim* s, double t_until)
             if (!(t_move < t_until)) break;
             move_ev* e = &s->ev[s->ev_head++];
             s->now = e->t;
+            int32_t loc = s->key_loc[e->key];
+            int rate_based = s->loc_rate_kind && s->loc_rate_kind[loc];
             if (e->kind == 0)
             {
-                evaluate(s, e->key, e->t); /* leaving person still in the set */
+                if (rate_based) rate_exit(s, e, loc);
+                else evaluate(s, e->key, e->t); /* leaving person still in the set */
                 set_remove(s, e->key, e->person);
             }
             else
             {
-                if (s->trigger == ORC_TRIGGER_ENTER_AND_EXIT) evaluate(s, e->key, e->t); /* entering one not yet */
+                if (!rate_based && s->trigger == ORC_TRIGGER_ENTER_AND_EXIT) evaluate(s, e->key, e->t); /* entering one not yet */
                 set_add(s, e->key, e->person);
+                if (s->stay_tin) s->stay_tin[e->person] = e->t;
             }
         }
     }

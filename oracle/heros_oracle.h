@@ -107,6 +107,9 @@ void     orc_sim_set_locations(orc_sim*, int n, const uint8_t* type, const int16
 void     orc_sim_set_persons(orc_sim*, int n, const int8_t* age, const uint8_t* female);
 /* DiseasePolicy (DPol:29-43): name is "psi" or "mu"; returns 0 ok, -1 unrecognised */
 int      orc_sim_set_parameter(orc_sim*, const char* name, double value, double at_time);
+/* rate-based locations (medlabs LocationProbBased, Construct:382-388; the convention of DESIGN.md 3.5) */
+void     orc_sim_set_roles(orc_sim*, int n, const uint8_t* role);
+void     orc_sim_set_rate_locations(orc_sim*, int n, const int32_t* loc, const double* factor, const double* rate);
 void     orc_sim_expose(orc_sim*, int n, const int32_t* person, const double* at_time);
 void     orc_sim_add_visits(orc_sim*, int64_t n, const int32_t* person, const int32_t* loc, const int16_t* sub,
                             const double* t_in, const double* t_out);

@@ -169,6 +169,10 @@ def run_oracle(scn: Scenario, props: dict, model: int, trigger: int, seed: int, 
     sim.set_location_types(scn.type_infect_sub, scn.type_corr)
     sim.set_locations(scn.loc_type, scn.loc_nsub, scn.loc_area)
     sim.set_persons(scn.age, scn.female)
+    if getattr(scn, "role", None) is not None:
+        sim.set_roles(scn.role)
+    if getattr(scn, "rate_locations", None) is not None:  # (location ids, infection_rate_factor, infection_rate)
+        sim.set_rate_locations(*scn.rate_locations)
     for (t, name, value) in policies:
         sim.set_parameter(name, value, t)
     sim.expose(scn.seeds, np.zeros(len(scn.seeds)))
@@ -187,7 +191,9 @@ def make_engine(scn: Scenario, props: dict, model: int, trigger: int, seed: int,
     eng = hb.HerosEngine(model, seed, trigger=trigger, window_hours=window_hours, flags=flags)
     eng.set_location_types(scn.type_infect_sub, scn.type_corr)
     eng.set_locations(scn.loc_type, scn.loc_nsub, scn.loc_area)
-    eng.set_persons(scn.age, scn.female)
+    eng.set_persons(scn.age, scn.female, getattr(scn, "role", None))
+    if getattr(scn, "rate_locations", None) is not None:
+        eng.set_rate_locations(*scn.rate_locations)
     if model == _lib.MODEL_AREA:
         eng.set_transmission_area(properties.area_params(props))
     else:
