@@ -211,7 +211,8 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
  *      held at midnight; travel time is spent outside every location.  Draws are Philox numbers keyed by
  *      (seed, person, day, activity), so the stays do not depend on the device or the thread layout.
  *      heros_advance_schedule(day) produces the stays of simulated day `day` for every person directly in HBM (what
- *      heros_submit_visits would have received); heros_step then processes the day.  Capacity-constrained locators and
+ *      heros_submit_visits would have received); heros_step then processes the day.  Capacity-constrained locators: see
+ *      heros_set_capacity_diversion.  (was:) and
  *      LocationPolicy closures are not implemented (they stay with the host-driven path). ---- */
 typedef struct heros_activity {
     int32_t kind;      /* 0 duration activity, 1 travel, 2 until fixed time */
@@ -255,6 +256,14 @@ int32_t heros_validate_schedule_tables(int32_t n_locations, const int16_t* n_sub
  * after the call; call it between heros_step(24 d) and heros_advance_schedule(d) for a policy at day d. */
 int32_t heros_set_closure_policy(heros_handle h, int32_t location_type, double fraction_open, double fraction_activities,
                                  int32_t alternative_type);
+/* Capacity-constrained locators (NearestLocatorCap / RandomLocatorCap and their Choice forms,
+ * factory/ConstructHerosModel.java:998-1020; capConstrained / capPersonsPerM2 / sizeFactor of locationtypes.csv): activities
+ * whose locator carries the flag 0x10 send the share divert[l] of their visits to location l -- decided by a keyed
+ * uniform per (person, day, activity) -- to the next candidate of the same search (the next-nearest place of the type;
+ * the next of the random candidates).  The rule of the medlabs classes is not in the reference tree; this is the
+ * convention of DESIGN.md 3.4, where the shares follow from the peak occupancy of an unconstrained day
+ * (scenario.capacity_diversion).  n_locations = 0 or NULL: no location sheds anything. */
+int32_t heros_set_capacity_diversion(heros_handle h, int32_t n_locations, const double* divert);
 /* = what HerosModel.locationDump (model/HerosModel.java:266-299) writes every simulated hour: the number of persons in
  * every location (Location.getAllPersonIds().size(), :280) and in every sub-location
  * (DiseaseTransmission.getNrPersonsInSublocation(location, index), :284), sampled at times[0..n_times) (ascending,

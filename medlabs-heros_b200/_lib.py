@@ -76,6 +76,7 @@ SIGNATURES = {
     "heros_set_location_types": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "heros_set_locations": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P]),
     "heros_set_persons": (C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "heros_set_capacity_diversion": (C.c_int32, [_P, C.c_int32, _P]),
     "heros_set_rate_locations": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "heros_set_transmission_area": (C.c_int32, [_P, C.POINTER(AreaParams)]),
     "heros_set_transmission_distance": (C.c_int32, [_P, C.POINTER(DistParams)]),

@@ -190,6 +190,7 @@ struct heros_engine
     bool have_schedule = false;
     unsigned int invalid_reported = 0;  // of Counters::invalid_visits, already returned as an error
     DevBuf<double> m_times; DevBuf<int32_t> m_sub, m_loc;  // heros_sample_occupancy
+    DevBuf<double> s_divert;  // heros_set_capacity_diversion (nullptr: no *Cap locator sheds anything)
     DevBuf<double2> s_closure; DevBuf<uint8_t> s_loc_type; std::vector<double> h_closure; bool closure_active = false;
     int sched_max_acts = 0, sched_n_types = 0, sched_n_cand = 0, sched_accommodation = 0;
     uint64_t sched_seed = 0;

@@ -24,6 +24,8 @@ struct ScheduleTables
     const int32_t* nearest; const int32_t* n_cand; const int32_t* cand;  // per location: [type], [type], [type][candidate]
     const int32_t* home_loc; const int16_t* home_sub; const int32_t* work_loc; const int16_t* work_sub;
     const uint32_t* loc_base; const int16_t* loc_nsub; uint32_t n_loc;
+    const uint32_t* key_loc;  // location of every sub-location key (the anchor of Nearest / Random is the CURRENT place)
+    const double* divert;     // per location: share of the visits of a *Cap locator that goes to the next candidate (or nullptr)
     uint64_t seed;
     // closure policy (policy/LocationPolicy.java:39-46): per location type {fraction of locations open, fraction of
     // activities that still take place}; nullptr while every type is fully open
@@ -121,11 +123,13 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
     double t = t0;
     for (int i = 0; i < n_act; ++i)
     {
-        const Activity act = S.acts[start + i];
+        Activity act = S.acts[start + i];
+        const bool capped = (act.locator & 0x10) != 0;  // NearestLocatorCap / RandomLocatorCap and their Choice forms
+        act.locator &= 0xF;
         // destination
         uint32_t dest = cur_key;  // CurrentLocator, and whoever has nowhere else to go
         Philox4 r{0, 0, 0, 0};
-        const bool needs_draw = act.dist != 0 || (act.locator >= 3 && act.choice >= 0);
+        const bool needs_draw = act.dist != 0 || ((act.locator == 3 || act.locator == 4) && act.choice >= 0);
         if (needs_draw)
             r = philox4x32_10(a, (uint32_t) (day * 64 + i), 0u, TAG_SCHEDULE, (uint32_t) S.seed, (uint32_t) (S.seed >> 32));
         if (act.locator == 0)
@@ -139,7 +143,7 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
                 if (S.closure && closed_by_policy(S, a, (uint32_t) (day * 64 + i), wl, S.loc_type[wl])) dest = home_key;
             }
         }
-        else if (act.locator >= 3 && act.choice >= 0)
+        else if ((act.locator == 3 || act.locator == 4) && act.choice >= 0)
         {
             const double u_type = (double) r.z * 0x1.0p-32;
             const double u_cand = (double) (r.w >> 16) * 0x1.0p-16, u_sub = (double) (r.w & 0xFFFFu) * 0x1.0p-16;
@@ -149,16 +153,37 @@ __device__ __forceinline__ void walk_day(const ScheduleTables& S, uint32_t a, co
             while (pick < c1 - c0 && S.choice_cum[c0 + pick] <= x) ++pick;
             if (pick > c1 - c0 - 1) pick = c1 - c0 - 1;
             const int ty = S.choice_type[c0 + pick];
+            // NearestLocator / RandomLocator(new CurrentLocator(), ...) (ConstructHerosModel.java:997, 1012): the search
+            // starts from the place the person is in; somebody on the way (in no location) searches from home
+            const size_t anchor = cur_key != KEY_NONE ? (size_t) S.key_loc[cur_key] : (size_t) home_l;
             int32_t dl;
-            if (act.locator == 3)  // Nearest(type) to the home building
-                dl = S.nearest[(size_t) home_l * S.n_types + ty];
-            else  // Random(type) within the maximum distance of the home building
+            const int n = S.n_cand[anchor * S.n_types + ty];
+            long long j = 0;
+            if (act.locator == 3)  // Nearest(type)
+                dl = S.nearest[anchor * S.n_types + ty];
+            else  // Random(type) within the maximum distance
             {
-                const int n = S.n_cand[(size_t) home_l * S.n_types + ty];
-                long long j = (long long) (u_cand * (double) n);
+                j = (long long) (u_cand * (double) n);
                 if (j > n - 1) j = n - 1;
                 if (j < 0) j = 0;
-                dl = n > 0 ? S.cand[((size_t) home_l * S.n_types + ty) * S.n_candidates + j] : -1;
+                dl = n > 0 ? S.cand[(anchor * S.n_types + ty) * S.n_candidates + j] : -1;
+            }
+            if (capped && S.divert && dl >= 0 && n >= 2)
+            {
+                // capacity-constrained form: a keyed share of the visits to an over-subscribed place goes to the next
+                // candidate of the search (scenario.capacity_diversion: the rule itself is inside medlabs)
+                const double share = S.divert[dl];
+                if (share > 0.0)
+                {
+                    const double u_cap = (double) philox4x32_10(a, (uint32_t) (day * 64 + i), 4u, TAG_SCHEDULE, (uint32_t) S.seed,
+                                                                (uint32_t) (S.seed >> 32)).x * 0x1.0p-32;
+                    if (u_cap < share)
+                    {
+                        const long long j2 = act.locator == 3 ? 1 : (j + 1) % n;
+                        const int32_t alt = S.cand[(anchor * S.n_types + ty) * S.n_candidates + (j2 < S.n_candidates ? j2 : S.n_candidates - 1)];
+                        if (alt >= 0) dl = alt;
+                    }
+                }
             }
             if (ty == S.accommodation_type || dl < 0)
                 dest = home_key;
@@ -406,7 +431,7 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
                 {
                     const int idx = (ph * 16 + r) * 4 + d;
                     size_t moves = 1;
-                    for (int i = 0; i < pattern_count[idx]; ++i) moves += activities[pattern_start[idx] + i].locator != 2 ? 1 : 0;
+                    for (int i = 0; i < pattern_count[idx]; ++i) moves += (activities[pattern_start[idx] + i].locator & 0xF) != 2 ? 1 : 0;
                     per_role[r] = std::max(per_role[r], moves);
                 }
         size_t room = 0;
@@ -416,6 +441,26 @@ int32_t heros_set_schedule(heros_handle h, int32_t n_activities, const heros_act
     h->sched_max_acts = max_acts; h->sched_n_types = n_types; h->sched_n_cand = n_candidates;
     h->sched_accommodation = accommodation_type; h->sched_seed = seed;
     h->have_schedule = true;
+    return HEROS_OK;
+}
+
+int32_t heros_set_capacity_diversion(heros_handle h, int32_t n_locations, const double* divert)
+{
+    if (!h) return HEROS_ERR_INVALID;
+    if (!h->have_schedule) return fail(h, HEROS_ERR_INVALID, "heros_set_schedule has not been called");
+    cudaSetDevice(h->cfg.device);
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (n_locations == 0 || !divert) { h->s_divert.release(); return HEROS_OK; }
+    if ((uint32_t) n_locations != h->n_loc) return fail(h, HEROS_ERR_INVALID, "one share per location of heros_set_locations");
+    bool any = false;
+    for (int32_t i = 0; i < n_locations; ++i)
+    {
+        if (!(divert[i] >= 0.0 && divert[i] <= 1.0)) return fail(h, HEROS_ERR_INVALID, "a share must lie in [0, 1]");
+        any = any || divert[i] > 0.0;
+    }
+    if (!any) { h->s_divert.release(); return HEROS_OK; }
+    CU(h, h->s_divert.ensure((size_t) n_locations));
+    CU(h, cudaMemcpy(h->s_divert.p, divert, (size_t) n_locations * 8, cudaMemcpyHostToDevice));
     return HEROS_OK;
 }
 
@@ -474,7 +519,8 @@ int32_t heros_advance_schedule(heros_handle h, int32_t day)
     S.n_types = h->sched_n_types; S.n_candidates = h->sched_n_cand; S.accommodation_type = h->sched_accommodation;
     S.nearest = h->s_nearest.p; S.n_cand = h->s_ncand.p; S.cand = h->s_cand.p;
     S.home_loc = h->d_home_loc.p; S.home_sub = h->d_home_sub.p; S.work_loc = h->d_work_loc.p; S.work_sub = h->d_work_sub.p;
-    S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.seed = h->sched_seed;
+    S.loc_base = h->d_loc_base.p; S.loc_nsub = h->d_loc_nsub.p; S.n_loc = h->n_loc; S.key_loc = h->d_key_loc.p; S.seed = h->sched_seed;
+    S.divert = h->s_divert.p;
     S.closure = h->closure_active ? h->s_closure.p : nullptr; S.loc_type = h->s_loc_type.p;
     static const int DAY_TYPE[7] = {0, 0, 0, 0, 1, 2, 3};  // Mon-Thu share the Monday pattern (ConstructHerosModel.java:931-940)
     CU(h, cudaMemsetAsync(&h->d_ctr.p->n_sched, 0, sizeof(unsigned long long), h->stream));

@@ -167,6 +167,18 @@ class HerosEngine:
                                                  _p(cc), int(t["n_types"]), int(t["accommodation_type"]),
                                                  int(t["n_candidates"]), _p(near), _p(ncand), _p(cand), _p(wsub),
                                                  int(seed) & (2 ** 64 - 1)))
+        divert = t.get("divert")
+        if divert is not None:
+            self.set_capacity_diversion(np.asarray(divert)[:np.asarray(t["nearest"]).shape[0]])  # a shard: its own locations
+
+    def set_capacity_diversion(self, divert):
+        """heros_set_capacity_diversion: per location, the share of the visits of a *Cap locator that goes to the next
+        candidate (``scenario.capacity_diversion``); None removes the table."""
+        if divert is None:
+            self._check(self._lib.heros_set_capacity_diversion(self._h, 0, None))
+            return
+        d = _arr(divert, np.float64)
+        self._check(self._lib.heros_set_capacity_diversion(self._h, len(d), _p(d)))
 
     def advance_schedule(self, day: int):
         self._check(self._lib.heros_advance_schedule(self._h, int(day)))

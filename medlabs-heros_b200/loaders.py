@@ -181,9 +181,12 @@ PHASES = ["Susceptible", "Exposed", "Infected-Asymptomatic", "Infected-Symptomat
           "Recovered"]
 ACTIVITY_KIND = {"StochasticDurationActivity": 0, "FixedDurationActivity": 0, "TravelActivityDistanceBased": 1,
                  "TravelActivity": 1, "UntilFixedTimeActivity": 2}
+LOCATOR_CAP = 0x10  # flag of the capacity-constrained forms (scenario.capacity_diversion, schedule.cu)
 LOCATOR = {"HomeLocator": 0, "WorkLocator": 1, "SchoolLocator": 1, "CurrentLocator": 2, "NearestLocator": 3,
-           "NearestLocatorCap": 3, "NearestLocatorChoice": 3, "RandomLocator": 4, "RandomLocatorCap": 4,
-           "DistanceBasedTravelLocator": 5}
+           "NearestLocatorChoice": 3, "NearestLocatorCap": 3 | LOCATOR_CAP, "NearestLocatorChoiceCap": 3 | LOCATOR_CAP,
+           "RandomLocator": 4, "RandomLocatorChoice": 4, "RandomLocatorCap": 4 | LOCATOR_CAP,
+           "RandomLocatorChoiceCap": 4 | LOCATOR_CAP, "DistanceBasedTravelLocator": 5, "WalkLocator": 5, "BikeLocator": 5,
+           "CarLocator": 5}
 
 
 def read_activity_schedules(path: str, sheet: str = "activityschedules", policy: str = "0") -> dict:
@@ -195,7 +198,8 @@ def read_activity_schedules(path: str, sheet: str = "activityschedules", policy:
     choice ("LocationType.X:0.6; LocationType.Y:0.4").  Only the rows of ``policy`` are read (policies 1 and 2 of the
     shipped workbook are never referenced, java :400).  A day pattern ends with its first ``UntilFixedTimeActivity 24``:
     10 of the 15 roles store the Susceptible block twice back to back, the second copy is dropped.
-    Capacity-constrained locators (``*Cap``) are read as their unconstrained forms."""
+    Capacity-constrained locators (``*Cap``) keep the flag ``LOCATOR_CAP``: the schedule generators divert a share of the
+    visits to an over-subscribed place to the next candidate (scenario.capacity_diversion)."""
     import json
     rows = read_xlsx(path)[sheet][1:]
     choices, choice_index = [], {}

@@ -34,6 +34,11 @@ TYPE_ID = {n: i for i, n in enumerate(TYPE_NAMES)}
 # locationtypes.csv columns infectSub / contagiousRateFactor (Park .. Satellite* have infectSub = FALSE)
 TYPE_INFECT_SUB = np.array([1] * 19 + [0, 0, 0], np.uint8)
 TYPE_CORRECTION = np.ones(22, np.float64)
+# columns capConstrained / capPersonsPerM2 / sizeFactor of the same file
+TYPE_CAP_CONSTRAINED = np.array([0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 1, 1, 1, 1, 0, 0], np.uint8)
+TYPE_CAP_PER_M2 = np.array([.25, .5, .25, .1, .5, .5, .2, .5, .5, .5, .5, .5, .5, .5, .5, .5, .25, .25, .2, .1, .25, .25])
+TYPE_SIZE_FACTOR = np.array([1, 1, 1, 7.4, 1, 1.3, 9.7, 1, 1, 1, 1, 1, 1, 1, 1, 3.6, 1, 1, 1.9, 1, 1, 1], np.float64)
+LOCATOR_CAP = 0x10  # flag on an activity's locator: the capacity-constrained form (NearestLocatorCap, RandomLocatorCap ...)
 
 # (category, share of locations, sub-locations per location, m2 per sub-location) from data/helsinki/locations.csv.gz
 CATEGORIES = [
@@ -179,28 +184,28 @@ class City:
             age, role, home_loc, home_sub, work_loc, work_sub = self._synthetic_persons(
                 rng, n_persons, n_households, hh_building, hh_sub, loc_type, loc_nsub, x, y)
         from scipy.spatial import cKDTree
-        # nearest / random candidate tables per Accommodation building (locators of the activity schedule)
+        # nearest / random candidate tables of EVERY location: the reference builds NearestLocator / RandomLocator over a
+        # CurrentLocator (ConstructHerosModel.java:997, 1012) -- nearest to, or within the maximum distance of, the place
+        # the person is in when the activity starts (its home, its workplace, the shop it just left ...)
         self.n_random_candidates = K = n_random_candidates
         n_types = len(TYPE_NAMES)
         nearest = np.full((n_loc, n_types), NONE, np.int32)
         cand = np.full((n_loc, n_types, K), NONE, np.int32)
         n_cand = np.zeros((n_loc, n_types), np.int32)
-        pts = np.c_[x[acc], y[acc]]
+        pts = np.c_[x, y]
         for t in range(n_types):
             places = np.nonzero(loc_type == t)[0]
             if t in (TYPE_ID["Accommodation"], TYPE_ID["Workplace"]) or len(places) == 0:
                 continue
             tree = cKDTree(np.c_[x[places], y[places]])
-            _, j = tree.query(pts)
-            nearest[acc, t] = places[j]
             kk = min(K, len(places))
-            d, j = tree.query(pts, k=kk, distance_upper_bound=2500.0)  # RandomLocator max distance (xlsx column P)
-            d = d.reshape(len(acc), kk)
-            j = j.reshape(len(acc), kk)
-            ok = np.isfinite(d)
-            n_cand[acc, t] = ok.sum(axis=1)
-            jj = np.where(ok, j, 0)
-            cand[acc, t, :kk] = np.where(ok, places[jj], NONE)
+            d, j = tree.query(pts, k=kk)
+            d = d.reshape(n_loc, kk)
+            j = j.reshape(n_loc, kk)
+            nearest[:, t] = places[j[:, 0]]
+            ok = d <= 2500.0  # RandomLocator max distance (xlsx column P)
+            n_cand[:, t] = ok.sum(axis=1)
+            cand[:, t, :kk] = np.where(ok, places[j], NONE)
         self.nearest, self.cand, self.n_cand = nearest, cand, n_cand
 
         self.loc_type = loc_type.astype(np.uint8)
@@ -363,7 +368,45 @@ def compile_schedule(city: "City", patterns: Optional[dict] = None) -> Dict[str,
                 choice_start=np.array(c_start, np.int32), choice_type=np.array(c_type, np.int32),
                 choice_cum=np.array(c_cum, np.float64), n_types=len(TYPE_NAMES), accommodation_type=TYPE_ID["Accommodation"],
                 n_candidates=city.n_random_candidates, nearest=city.nearest, n_cand=city.n_cand, cand=city.cand,
-                work_sub=city.work_sub)
+                work_sub=city.work_sub, divert=getattr(city, "divert", None))
+
+
+def location_capacity(city: "City") -> np.ndarray:
+    """Persons a location holds at the same time: capPersonsPerM2 x totalArea x sizeFactor of its type where the type is
+    capConstrained (data/<city>/locations/locationtypes.csv columns 8-10), else unlimited."""
+    ty = city.loc_type.astype(np.int64)
+    cap = TYPE_CAP_PER_M2[ty] * city.loc_area.astype(np.float64) * TYPE_SIZE_FACTOR[ty]
+    return np.where(TYPE_CAP_CONSTRAINED[ty] == 1, np.maximum(cap, 1.0), np.inf)
+
+
+def capacity_diversion(city: "City", seed: int, patterns: Optional[dict] = None) -> np.ndarray:
+    """The capacity-constrained locators (NearestLocatorCap / RandomLocatorCap and their Choice forms,
+    ConstructHerosModel.java:998-1020) act inside medlabs; their rule is not in the reference tree.  Convention here,
+    shared by the host generator and the device-side schedule and free of any dependence on the order in which persons are
+    processed: one ordinary Monday of the healthy population is generated WITHOUT constraint and the largest number of
+    persons present at the same time is taken for every location (peak); a constrained location with peak > capacity
+    sheds the share 1 - capacity / peak of the visits a ``*Cap`` locator sends to it -- which visits is decided by a
+    keyed uniform per (person, day, activity) -- to the next candidate of the same search (next-nearest place of the
+    type; the next of the random candidates).  Returns that share per location; ``city.divert`` is set to it."""
+    city.divert = np.zeros(len(city.loc_type), np.float64)
+    gen = ScheduleGenerator(city, seed, patterns)
+    st = gen.generate_day(np.zeros(city.n_persons, np.uint8))
+    cap = location_capacity(city)
+    sel = np.isfinite(cap[st["loc"]])
+    loc = st["loc"][sel].astype(np.int64)
+    t_in, t_out = st["t_in"][sel], np.where(np.isinf(st["t_out"][sel]), 1e9, st["t_out"][sel])
+    ev_loc = np.concatenate([loc, loc])
+    ev_t = np.concatenate([t_in, t_out])
+    ev_d = np.concatenate([np.ones(len(loc), np.int64), -np.ones(len(loc), np.int64)])
+    order = np.lexsort((ev_d, ev_t, ev_loc))  # by location, time, leaving before entering
+    run = np.cumsum(ev_d[order])              # every location's events sum to zero: the count restarts by itself
+    peak = np.zeros(len(city.loc_type), np.float64)
+    np.maximum.at(peak, ev_loc[order], run.astype(np.float64))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        divert = np.where(peak > cap, 1.0 - cap / np.maximum(peak, 1.0), 0.0)
+    city.divert = divert
+    city.peak_unconstrained = peak
+    return divert
 
 
 class ScheduleGenerator:
@@ -541,7 +584,8 @@ class ScheduleGenerator:
 
     def _locate(self, act, idx, u_type, u_cand, u_sub, day_act=0):
         c = self.city
-        loc = act["locator"]
+        loc = act["locator"] & 0xF
+        capped = bool(act["locator"] & LOCATOR_CAP)
         home_l, home_s = c.home_loc[idx].astype(np.int64), c.home_sub[idx].astype(np.int64)
         if loc == 0:
             return home_l, home_s
@@ -557,17 +601,31 @@ class ScheduleGenerator:
             dl = np.where(has, wl, self.cur_loc[idx])
             ds = np.where(has, c.work_sub[idx].astype(np.int64), self.cur_sub[idx])
             return np.where(shut, home_l, dl), np.where(shut, home_s, ds)
-        if loc == 2 or act["choice"] < 0:
+        if loc == 2 or loc == 5 or act["choice"] < 0:
             return self.cur_loc[idx].copy(), self.cur_sub[idx].copy()
         types, cum = self._choice_tables[act["choice"]]
         pick = np.minimum(np.searchsorted(cum, u_type * cum[-1], side="right"), len(types) - 1)
         ty = types[pick]
-        if loc == 3:  # Nearest(type) to the home building
-            dl = c.nearest[home_l, ty].astype(np.int64)
-        else:  # Random(type) within max distance of the home building
-            n = c.n_cand[home_l, ty]
+        # the anchor of the search: the place the person is in (CurrentLocator); somebody on the way -- in no location --
+        # searches from home
+        here = self.cur_loc[idx]
+        anchor = np.where(here >= 0, here, home_l)
+        n = c.n_cand[anchor, ty]
+        if loc == 3:  # Nearest(type) to the current place
+            dl = c.nearest[anchor, ty].astype(np.int64)
+            j = np.zeros(len(idx), np.int64)
+        else:  # Random(type) within the maximum distance of the current place
             j = np.minimum((u_cand * n).astype(np.int64), np.maximum(n - 1, 0))
-            dl = np.where(n > 0, c.cand[home_l, ty, j], NONE).astype(np.int64)
+            dl = np.where(n > 0, c.cand[anchor, ty, j], NONE).astype(np.int64)
+        divert = getattr(c, "divert", None)
+        if capped and divert is not None and divert.any():
+            # capacity-constrained form: a keyed share of the visits to an over-subscribed place goes to the next
+            # candidate of the search (capacity_diversion)
+            u_cap = philox4x32_10(self._pkey(idx), day_act, 4, TAG_SCHEDULE, self.seed, self.seed >> 32)[0].astype(np.float64) * 2.0 ** -32
+            shed = (dl >= 0) & (u_cap < divert[np.maximum(dl, 0)]) & (n >= 2)
+            j2 = np.where(loc == 3, 1, (j + 1) % np.maximum(n, 1))
+            alt = c.cand[anchor, ty, np.minimum(j2, c.cand.shape[2] - 1)].astype(np.int64)
+            dl = np.where(shed & (alt >= 0), alt, dl)
         go_home = (ty == TYPE_ID["Accommodation"]) | (dl < 0)
         go_home |= self._closed(idx, day_act, dl, ty)
         nsub = np.maximum(c.loc_nsub[np.maximum(dl, 0)].astype(np.int64), 1)

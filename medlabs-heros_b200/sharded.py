@@ -465,11 +465,12 @@ class CityPartition:
             setattr(out, name, getattr(c, name)[persons_old])
         out.home_loc = remap(c.home_loc[persons_old]).astype(np.int32)
         out.work_loc = remap(c.work_loc[persons_old]).astype(np.int32)
-        # locator tables: rows of the own locations (homes are own), entries may be foreign
-        own = locs_old_own
-        out.nearest = remap(c.nearest[own]).astype(np.int32)
-        out.cand = remap(c.cand[own]).astype(np.int32)
-        out.n_cand = c.n_cand[own].copy()
+        # locator tables: a row per location a person of the shard can be in (own and foreign), entries likewise
+        out.nearest = remap(c.nearest[locs]).astype(np.int32)
+        out.cand = remap(c.cand[locs]).astype(np.int32)
+        out.n_cand = c.n_cand[locs].copy()
+        if getattr(c, "divert", None) is not None:
+            out.divert = c.divert[locs]
         out.person_gid = np.asarray(person_gid, np.int64)
         out.loc_gid = np.asarray(loc_gid, np.int64)
         if ext_global is not None:
@@ -486,12 +487,11 @@ class CityPartition:
         c = self.city
         persons = self.person_old[self.person_bases[r]:self.person_bases[r + 1]]
         own = self.loc_old[self.loc_bases[r]:self.loc_bases[r + 1]]
-        # every location the shard's persons can be sent to: work / school places and the entries of the locator tables
-        refs = [c.work_loc[persons].astype(np.int64).ravel(), c.nearest[own].astype(np.int64).ravel(),
-                c.cand[own].astype(np.int64).ravel()]
-        refs = np.unique(np.concatenate(refs))
-        refs = refs[refs >= 0]
-        ext = refs[self.shard_of_location[refs] != r]
+        # Every other location of the city follows as a foreign one: a person searches the nearest / a random place of a
+        # type from wherever it IS (CurrentLocator), e.g. from a workplace in another shard, so the rows of the locator
+        # tables of all places it can get to are needed -- transitively, the whole neighbourhood.  (Tables only: the
+        # shard's engine holds its own locations alone.)
+        ext = self.loc_old[np.r_[0:self.loc_bases[r], self.loc_bases[r + 1]:len(self.loc_old)]]
         return self._make(persons, own, ext, self.person_new[persons], np.concatenate([self.loc_new[own], self.loc_new[ext]]),
                           self.loc_new[ext])
 

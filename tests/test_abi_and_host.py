@@ -473,7 +473,7 @@ def test_activity_schedule_workbook_reader(tmp_path):
     pat = loaders.read_activity_schedules(path)
     day = pat["patterns"]["Susceptible|worker|Monday"]
     assert [a["name"] for a in day] == ["sleep", "to work", "work", "shop", "home"]           # cut at the first "until 24"
-    assert [a["kind"] for a in day] == [2, 1, 0, 0, 2] and [a["locator"] for a in day] == [0, 1, 1, 4, 0]
+    assert [a["kind"] for a in day] == [2, 1, 0, 0, 2] and [a["locator"] for a in day] == [0, 1, 1, 4 | loaders.LOCATOR_CAP, 0]  # the Cap form keeps its flag
     assert day[1]["dist"] == 1 and (day[1]["min"], day[1]["max"]) == (0.2, 0.5)                # travel time ~ U(min, max)
     assert day[2]["dist"] == 2 and (day[2]["min"], day[2]["mode"], day[2]["max"]) == (7.0, 8.0, 9.0)
     assert day[3]["dist"] == 0 and day[3]["min"] == day[3]["max"] == 0.5 and day[3]["max_distance"] == 2500.0

@@ -29,9 +29,15 @@ def stay_table(st):
                      st["sub"][order].astype(np.float64), st["t_in"][order], st["t_out"][order]])
 
 
-@pytest.mark.parametrize("model", ["area", "distance"])
-def test_device_schedule_equals_host_generator(model):
+@pytest.mark.parametrize("model,capacity", [("area", False), ("distance", False), ("distance", True)])
+def test_device_schedule_equals_host_generator(model, capacity):
     city = scenario.City(6000, seed=7)
+    if capacity:
+        # capacity-constrained locators: over-subscribed places shed a keyed share of their visits to the next candidate
+        # (scenario.capacity_diversion -> heros_set_capacity_diversion); floor areas cut down so that many places saturate
+        city.loc_area = (city.loc_area * np.where(scenario.TYPE_CAP_CONSTRAINED[city.loc_type] == 1, 0.05, 1.0)).astype(np.float32)
+        share = scenario.capacity_diversion(city, 111)
+        assert (share > 0.3).sum() > 5 and share.max() < 1.0
     props = load_props(model)
     props["covidT_area.contagiousness" if model == "area" else "covidT_dist.alpha"] = "6.0" if model == "area" else "2.5"
     kind = hb.MODEL_AREA if model == "area" else hb.MODEL_DISTANCE
