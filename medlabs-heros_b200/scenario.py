@@ -96,7 +96,9 @@ class City:
                  box_m=(12000.0, 9000.0), origin_m=(0.0, 0.0), n_random_candidates: int = 8,
                  location_table: Optional[Dict[str, np.ndarray]] = None,
                  person_table: Optional[Dict[str, np.ndarray]] = None,
-                 work_anywhere_fraction: float = 1.0, n_work_neighbours: int = 64):
+                 work_anywhere_fraction: float = 1.0, n_work_neighbours: int = 64,
+                 household_size: float = 2.15, workplace_scale: float = 1.0, workplace_sub_mean: float = 1.75,
+                 type_scale: Optional[Dict[str, float]] = None):
         """``location_table``: a real location table (type, nsub, area_per_sub, lat, lon -- e.g. the Helsinki fixture
         of tests/golden, or ``loaders.read_locations``) instead of the synthetic one.  ``person_table``: real persons
         (age, role, home_loc, home_sub, work_loc as location indices, optionally female and work_sub --
@@ -114,7 +116,11 @@ class City:
         self.n_persons = int(n_persons)
         self.type_infect_sub = TYPE_INFECT_SUB.copy()
         self.type_correction = TYPE_CORRECTION.copy()
-        n_households = max(1, int(round(n_persons / 2.15)))
+        # knobs of the synthetic population that the reference's missing people / location files would fix (persons per
+        # household, number of workplaces and rooms per workplace relative to the Helsinki table, number of places of a type)
+        self.calibration = dict(household_size=household_size, workplace_scale=workplace_scale,
+                                workplace_sub_mean=workplace_sub_mean, type_scale=dict(type_scale or {}))
+        n_households = max(1, int(round(n_persons / household_size)))
         if location_table is not None:
             # columns as the loader reads them (ConstructHerosModel.java:300-395); rows with nb_sublocations = 0 and
             # area = -1 are kept as they are
@@ -136,12 +142,13 @@ class City:
             scale = n_locations / HELSINKI_LOCATIONS
             types, nsubs, per_sub_area = [], [], []
             for name, count, nsub, area in CATEGORIES:
-                k = max(1, int(round(count * scale)))
+                k = max(1, int(round(count * scale * (type_scale or {}).get(name, 1.0))))
                 if name == "Accommodation":
                     k = max(1, min(k, n_households))
                     sub = np.zeros(k, np.int64)  # filled below from the households
                 elif name == "Workplace":
-                    sub = np.minimum(1 + np.floor(rng.exponential(1.75, k)).astype(np.int64), 100)
+                    k = max(1, int(round(k * workplace_scale)))
+                    sub = np.minimum(1 + np.floor(rng.exponential(workplace_sub_mean, k)).astype(np.int64), 100)
                 else:
                     sub = np.full(k, nsub, np.int64)
                 types.append(np.full(k, TYPE_ID[name], np.uint8))
