@@ -51,6 +51,12 @@ CATEGORIES = [
 ]
 HELSINKI_LOCATIONS = 69508
 
+# The free parameters of the synthetic population, fitted (tools/calibrate_city.py, profiles/r02_calibration.json) so that
+# the area-model epidemic of the synthetic Hague with the reference's HardLockdown_20 policy follows the curves the
+# reference publishes for seeds 111-114 (seed comparison.xlsx): persons per household, number of workplaces relative to
+# the Helsinki table (0.23: about 14 workers per workplace instead of 3), mean number of rooms per workplace.
+HAGUE_CALIBRATED = dict(household_size=2.2, workplace_scale=0.23, workplace_sub_mean=1.75)
+
 ROLE_INFANT, ROLE_KINDERGARTEN, ROLE_PRIMARY, ROLE_SECONDARY, ROLE_COLLEGE, ROLE_UNIVERSITY, ROLE_WORKER, \
     ROLE_PENSIONER, ROLE_UNEMPLOYED, ROLE_WEEKEND_WORKER, ROLE_ESSENTIAL_WORKER = range(1, 12)
 

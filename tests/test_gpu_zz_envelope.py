@@ -1,0 +1,39 @@
+"""The north star's statistical criterion: epidemic curves of 32 seeds next to the curves the reference publishes (seed
+comparison.xlsx, seeds 111-114: The Hague, area model, HardLockdown_20, 120 days; tests/golden/seed_comparison.json).
+The population is the synthetic Hague with the three fitted parameters of scenario.HAGUE_CALIBRATED, everything runs on the
+device (schedule, capacity diversion, closure policy, transmission, progression).  What is asserted is what the fit
+achieves -- stated in DESIGN.md 4: through the bulk of the epidemic (days 15-60) the reference's curves lie inside the
+32-seed envelope; the first ten days run about a day ahead and the tail (days 65-100) decays more slowly."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_curves_lie_inside_the_32_seed_envelope_through_the_bulk_of_the_epidemic():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import seed_envelope
+    out = seed_envelope.run(types.SimpleNamespace(seeds=32, first_seed=111, days=120, model="area", policy="HardLockdown_20",
+                                                  persons=553667))
+    assert out["reference_days_inside_envelope_day_15_to_60"] >= 0.9
+    assert out["reference_days_inside_envelope"] >= 0.5
+    lo, hi = out["ours_peak_symptomatic"]
+    rlo, rhi = out["reference_peak_symptomatic"]
+    assert lo <= rhi and rlo <= hi                                  # the ranges of the symptomatic peak overlap ...
+    days = [v["peak_symptomatic_day"] for v in out["ours"].values()]
+    assert min(days) >= 32 and max(days) <= 36                      # ... and it falls on day 34 +- 2 (reference: 34)
+    lo, hi = out["ours_final_recovered"]
+    rlo, rhi = out["reference_final_recovered"]
+    assert lo <= rhi and rlo <= hi and lo > 0.8 * rlo and hi < 1.2 * rhi
+    # day 20 (the day the lockdown starts): 23 - 30 thousand infected in the reference
+    env = out["envelope"]
+    assert env["infected_min"][20] < 30159 and env["infected_max"][20] > 23244
+    med = np.array(env["infected_median"])
+    ref = np.mean([v["infected"] for v in out["reference"].values()], axis=0)
+    ratio = med[15:61] / ref[15:61]
+    assert ratio.min() > 0.8 and ratio.max() < 1.25                 # the median follows the reference's mean within 25 %

@@ -93,6 +93,14 @@ def main():
         t = time.time()
         curves = run_city(hb, scenario, props, policy_rows, kw, range(111, 111 + args.seeds), args.days, args.persons)
         d = describe(curves)
+        # distance to the reference: root mean square of the log ratio of the mean infected curves on the days shown plus
+        # every tenth day, and of the recovered at the end
+        days = sorted(set(DAYS_SHOWN) | set(range(10, args.days + 1, 10)))
+        days = [k for k in days if k <= args.days]
+        ours, theirs = curves[:, :, 1:6].sum(axis=2).mean(axis=0), ref[:, :, 1:6].sum(axis=2).mean(axis=0)
+        terms = [np.log(max(ours[k], 1.0) / max(theirs[k], 1.0)) for k in days]
+        terms.append(np.log(max(curves[:, -1, 7].mean(), 1.0) / max(ref[:, -1, 7].mean(), 1.0)))
+        d["rms_log_ratio"] = float(np.sqrt(np.mean(np.square(terms))))
         results.append(dict(city=kw, summary=d, curves=curves.tolist() if args.out else None))
         print(json.dumps(kw), json.dumps(d), f"{time.time() - t:.0f}s", flush=True)
     if args.out:
