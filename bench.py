@@ -262,7 +262,8 @@ def run_reference(args):
     from oracle import binding as ob
     ob.lib()                                                      # built and loaded before the fork
     props = load_props(args.model)
-    city = scenario.City(args.persons, seed=CITY_SEED)
+    city = scenario.City(args.persons, seed=CITY_SEED, **scenario.HAGUE_CALIBRATED)
+    scenario.capacity_diversion(city, SEED)
     workers = args.ref_cores if args.ref_cores > 0 else min(host_cores(), 64)
     mem = host_memory_bytes()
     if args.ref_cores <= 0 and mem is not None:                   # a replication holds ~1 KB per person beside the shared city
@@ -314,6 +315,11 @@ def run_reference(args):
     emit(line)
 
 
+def scenario_calibration():
+    from heros_b200 import scenario
+    return scenario.HAGUE_CALIBRATED
+
+
 def workload_config(args, city, world, exchange="p2p"):
     """The workload both arms are quoted on, from the arguments alone (the two arms must print the same object)."""
     step = {"step": "one simulated day (24 h window)", "first_timed_day": args.preroll + args.warmup,
@@ -322,10 +328,11 @@ def workload_config(args, city, world, exchange="p2p"):
                   "(L2: 126 MB)"}
     if world == 1:
         n_own = city.n_locations
-        return {"workload": f"thehague-synthetic N={city.n_persons} locations={n_own} "
+        return {"workload": f"thehague-synthetic (calibrated: {json.dumps(scenario_calibration())}) N={city.n_persons} locations={n_own} "
                             f"sublocations={int(city.loc_nsub[:n_own].sum())} model={args.model} trigger={args.trigger} "
                             f"seed={SEED} infected0={N_INFECTED}", **step}
-    return {"workload": f"one synthetic city of {world} x {args.persons} persons (Hague density and location mix) cut into "
+    return {"workload": f"one synthetic city of {world} x {args.persons} persons (Hague density and location mix, calibrated: "
+                        f"{json.dumps(scenario_calibration())}) cut into "
                         f"{world} geographic shards along the Morton curve of its locations (equal expected load, a person "
                         f"belongs to the shard of its home), model={args.model} trigger={args.trigger} seed={SEED} "
                         f"infected0={N_INFECTED} per shard", **step,
@@ -388,7 +395,9 @@ def parity_check(args, rank, world, local, dev):
     props = load_props(args.model)
     # more contagious than the scenario, so that a few days of a small city hold a few hundred events
     props["covidT_area.contagiousness" if args.model == "area" else "covidT_dist.alpha"] = "4.0" if args.model == "area" else "1.5"
-    whole0 = scenario.City(args.parity_persons * world, seed=CITY_SEED + 1, work_anywhere_fraction=max(args.commute, 0.2))
+    whole0 = scenario.City(args.parity_persons * world, seed=CITY_SEED + 1, work_anywhere_fraction=max(args.commute, 0.2),
+                           **scenario.HAGUE_CALIBRATED)
+    scenario.capacity_diversion(whole0, seed)
     part = sharded.partition_city(whole0, world)
     city = part.shard_city(rank)
     seeds = keyed_seeds(whole0, seed, 40 * world)
@@ -481,14 +490,16 @@ def run_ours(args):
         # builds the same city from the same seed and keeps its shard
         side = float(np.sqrt(world))
         whole = scenario.City(args.persons * world, seed=CITY_SEED, box_m=(12000.0 * side, 9000.0 * side),
-                              work_anywhere_fraction=args.commute)
+                              work_anywhere_fraction=args.commute, **scenario.HAGUE_CALIBRATED)
+        scenario.capacity_diversion(whole, SEED)
         part = sharded.partition_city(whole, world)
         city = part.shard_city(rank)
         person_bases, loc_bases = part.person_bases.copy(), part.loc_bases.copy()
         n_commuters = int((city.work_loc >= city.n_locations).sum())
         del whole, part
     else:
-        city = scenario.City(args.persons, seed=CITY_SEED)
+        city = scenario.City(args.persons, seed=CITY_SEED, **scenario.HAGUE_CALIBRATED)
+        scenario.capacity_diversion(city, SEED)
         person_bases = np.array([0, city.n_persons])
         loc_bases = np.array([0, city.n_locations])
     total = args.preroll + args.warmup + args.steps

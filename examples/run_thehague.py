@@ -52,7 +52,8 @@ def main():
         table = dict(np.load(os.path.join(ROOT, "tests", "golden", "helsinki_locations.npz")))
         city = scenario.City(args.persons, location_table=table)
     else:
-        city = scenario.City(args.persons)
+        city = scenario.City(args.persons, **scenario.HAGUE_CALIBRATED)
+        scenario.capacity_diversion(city, 111)
     model = hb.HerosModel(props, seed=args.seed)                       # parameter map + engine
     city.install(model.engine)
     progression, transmission = hb.construct_disease_model(model)       # ConstructHerosModel.java:136-144

@@ -1369,6 +1369,7 @@ int32_t heros_destroy(heros_handle h)
     if (h->xc.region) cudaFree(h->xc.region);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_keep) cudaFreeHost(h->h_keep);
+    if (h->pin_buf) cudaFreeHost(h->pin_buf);
     for (auto& ev : h->ev_keep) if (ev) cudaEventDestroy(ev);
     if (h->meta_stream) cudaStreamDestroy(h->meta_stream);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -2077,13 +2078,24 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         // only the events logged since the last call are fetched; they are sorted and merged behind the older ones
         // (the events of a later window are later, so the merge normally has nothing to move)
         const size_t old = (size_t) h->o_inf_n, add = (size_t) (n - h->o_inf_n);
-        std::vector<uint32_t> per(add);
-        std::vector<uint64_t> key(add);
-        std::vector<double> t(add), pp(add);
-        CU(h, cudaMemcpyAsync(per.data(), h->inf_person.p + old, add * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(key.data(), h->inf_gkey.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(t.data(), h->inf_t.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaMemcpyAsync(pp.data(), h->inf_p.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        // into pinned memory: four asynchronous copies, one wait (pageable targets would be staged one after the other)
+        const size_t need = add * 28 + 64;
+        if (need > h->pin_bytes)
+        {
+            if (h->pin_buf) cudaFreeHost(h->pin_buf);
+            h->pin_buf = nullptr; h->pin_bytes = 0;
+            CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
+            h->pin_bytes = 2 * need;
+        }
+        unsigned char* pb = static_cast<unsigned char*>(h->pin_buf);
+        double* t = reinterpret_cast<double*>(pb);
+        double* pp = t + add;
+        uint64_t* key = reinterpret_cast<uint64_t*>(pp + add);
+        uint32_t* per = reinterpret_cast<uint32_t*>(key + add);
+        CU(h, cudaMemcpyAsync(per, h->inf_person.p + old, add * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(key, h->inf_gkey.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(t, h->inf_t.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaMemcpyAsync(pp, h->inf_p.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         h->o_inf.resize(old + add);
         for (size_t i = 0; i < add; ++i) h->o_inf[old + i] = heros_engine::InfEvent{t[i], pp[i], key[i], per[i]};

@@ -207,6 +207,7 @@ struct heros_engine
 
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;  // pinned
+    void* pin_buf = nullptr; size_t pin_bytes = 0;  // pinned staging of the getters
     bool ctr_current = false;   // nothing that changes the counters was enqueued since h_ctr was refreshed
 
     // staging for host submissions (double buffered: the copy of the next batch runs beside the kernel that reads this one)

@@ -37,7 +37,7 @@ def main():
     name = "params_alpha_area.json" if args.model == "area" else "params_alpha_distance.json"
     with open(os.path.join(ROOT, "tests", "golden", name)) as f:
         props = json.load(f)["properties"]
-    city = scenario.City(args.persons)
+    city = scenario.City(args.persons, **scenario.HAGUE_CALIBRATED)
     tables = scenario.compile_schedule(city)
     model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
     dev = torch.device("cuda", 0)

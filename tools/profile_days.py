@@ -28,7 +28,8 @@ with open(os.path.join(ROOT, "tests", "golden", f"params_alpha_{'area' if args.m
 if args.contagiousness is not None:
     props["covidT_area.contagiousness"] = str(args.contagiousness)
 t = time.time()
-city = scenario.City(args.persons)
+city = scenario.City(args.persons, **scenario.HAGUE_CALIBRATED)
+scenario.capacity_diversion(city, 111)
 print(f"city: {city.n_persons} persons, {city.n_locations} locations, {int(city.loc_nsub.sum())} sub-locations, {time.time()-t:.1f}s")
 model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
 eng = hb.HerosEngine(model, 111, trigger=args.trigger, flags=(2 if args.clocks else 0) | args.flags)

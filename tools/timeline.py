@@ -34,7 +34,8 @@ with open(os.path.join(ROOT, "tests", "golden", f"params_alpha_{'area' if args.m
     props = json.load(f)["properties"]
 if args.alpha is not None:
     props["covidT_area.contagiousness" if args.model == "area" else "covidT_dist.alpha"] = str(args.alpha)
-city = scenario.City(args.persons)
+city = scenario.City(args.persons, **scenario.HAGUE_CALIBRATED)
+scenario.capacity_diversion(city, 111)
 model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
 eng = hb.HerosEngine(model, 111, flags=hb._lib.FLAG_RESIDENT_INPUTS if args.mode == "resident" else 0)
 city.install(eng)
