@@ -578,6 +578,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    step_ms = []  # per-step device times of the last timed_days call (this rank)
+    host_ms = {"submit_begin": 0.0, "enqueue_window": 0.0, "submit_end_copy_done": 0.0, "wait": 0.0, "read_results": 0.0}
+
     def timed_days(eng, bx, stream, cols_of_day, device, after_step=None, d0=None, d1=None):
         """K steps bracketed by barrier + synchronize, timed with CUDA events on the engine stream.  A single engine is
         driven the way the asynchronous C ABI is meant to be used: the window of day d is enqueued (heros_step_async), the
@@ -587,26 +590,46 @@ def run_ours(args):
         d1 = total if d1 is None else d1
         stats = []
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []  # one event per step on the engine stream: the time of every single day
+
+        def mark():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            marks.append(ev)
+
         barrier()
         t0 = time.perf_counter()
         start.record(stream)
         if bx is None:
             submit_day(eng, d0, cols_of_day(d0)[0], device)
+            host = host_ms
+            for k in host:
+                host[k] = 0.0
             for d in range(d0, d1):
+                ta = time.perf_counter()
                 if d + 1 < d1 and not device:
                     # host buffers: the copy of day d + 1 starts before the window of day d is enqueued
                     c = cols_of_day(d + 1)[0]
                     eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
+                tb = time.perf_counter()
                 eng.step_async(24.0 * (d + 1))
+                mark()
+                tc = time.perf_counter()
                 if d + 1 < d1:
                     if device:
                         submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
                     else:
                         eng.submit_visits_end()
+                td = time.perf_counter()
                 if after_step:
                     # the host reads the day's results before it hands over the next day (e2e)
                     stats.append(eng.wait())
+                    te = time.perf_counter()
                     after_step()
+                    tf = time.perf_counter()
+                    host["wait"] += 1e3 * (te - td); host["read_results"] += 1e3 * (tf - te)
+                host["submit_begin"] += 1e3 * (tb - ta); host["enqueue_window"] += 1e3 * (tc - tb)
+                host["submit_end_copy_done"] += 1e3 * (td - tc)
             if not after_step:
                 # everything is resident in HBM: the whole job is enqueued (no window waits for the host: the fill
                 # counts of the pools, the work lists and the candidates stay on the device), one wait at the end
@@ -620,6 +643,7 @@ def run_ours(args):
                     c = cols_of_day(d + 1)[0]
                     eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
                 bx.step_window(24.0 * (d + 1), cols_of_day(d)[1], cols_of_day(d)[2], wait=False)
+                mark()
                 if d + 1 < d1:
                     if device:
                         submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
@@ -639,6 +663,11 @@ def run_ours(args):
         end.synchronize()
         barrier()
         wall = time.perf_counter() - t0
+        step_ms.clear()
+        prev = start
+        for ev in marks:
+            step_ms.append(prev.elapsed_time(ev))
+            prev = ev
         return max_over_ranks(start.elapsed_time(end) * 1e-3), max_over_ranks(wall), stats
 
     # ---- value: stays resident in HBM ----
@@ -650,8 +679,11 @@ def run_ours(args):
     for d in range(args.preroll):
         day_step(eng, bx, d, *dev_days[d], device=True)
     timed_days(eng, bx, stream, lambda d: dev_days[d], True, d0=args.preroll, d1=first_timed)  # warm-up, driven like the timed steps
+    counts_before = eng.phase_counts()
     with ClockSampler(local) as clocks:
         seconds, wall_seconds, stats = timed_days(eng, bx, stream, lambda d: dev_days[d], True)
+    value_step_ms = list(step_ms)
+    counts_after = eng.phase_counts()
     assert (eng.phase_counts() == ref_counts).all(), "replay diverged from the recorded run"
     release(eng)
     del dev_days
@@ -660,17 +692,18 @@ def run_ours(args):
     eng, bx, stream = new_engine()
     for d in range(args.preroll):
         day_step(eng, bx, d, *days[d], device=False)
-    box = {"n_inf": len(eng.infections()["person"]), "d2h": 0, "counts": None}
+    box = {"n_inf": len(eng.infections(ordered=False)["person"]), "d2h": 0, "counts": None}
 
     def read_results():
         box["counts"] = eng.phase_counts()          # D2H: the DiseaseMonitor counters
-        new = eng.infections(first=box["n_inf"])    # D2H: the day's infection events
+        new = eng.infections(first=box["n_inf"], ordered=False)    # D2H: the day's infection events (as logged)
         box["n_inf"] += len(new["person"])
         box["d2h"] += 64 + len(new["person"]) * 26
 
     timed_days(eng, bx, stream, lambda d: days[d], False, read_results, d0=args.preroll, d1=first_timed)  # warm-up
     box["d2h"] = 0
     e2e_seconds, e2e_wall, _ = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
+    e2e_host_ms = {k: v / args.steps for k, v in host_ms.items()}
     assert (box["counts"] == ref_counts).all()
     e2e_d2h = int(box["d2h"] / args.steps)
     release(eng)
@@ -782,9 +815,16 @@ def run_ours(args):
                   f"{1e3 * wall_seconds / args.steps:.4f} ms/step",
         "e2e": {"value": e2e_value, "unit": "person-hours/s",
                 "h2d_bytes_per_step": int(np.mean(h2d_bytes[first_timed:])), "d2h_bytes_per_step": e2e_d2h,
-                "ms_per_step": 1e3 * e2e_seconds / args.steps, "wall_ms_per_step": 1e3 * e2e_wall / args.steps},
+                "ms_per_step": 1e3 * e2e_seconds / args.steps, "wall_ms_per_step": 1e3 * e2e_wall / args.steps,
+                "host_ms_per_step": e2e_host_ms},
         "gpu_launches": int(np.sum([s["gpu_launches"] for s in stats])) + args.steps,
         "roofline": roofline,
+        "ms_per_step_min_median_max": ([float(np.min(value_step_ms)), float(np.median(value_step_ms)), float(np.max(value_step_ms))]
+                                       if value_step_ms else None),
+        "epidemic": {"what": "share of this rank's persons infected (E, I(A), I(S), H, ICU) / ever infected at the start and "
+                             "at the end of the timed days (no policy in force)",
+                     "infected_share": [float(counts_before[1:6].sum() / city.n_persons), float(counts_after[1:6].sum() / city.n_persons)],
+                     "ever_infected_share": [float(counts_before[1:].sum() / city.n_persons), float(counts_after[1:].sum() / city.n_persons)]},
         "infections_total": int(ref_counts[1:].sum()), "visits_per_step": visits / args.steps,
         "device_ms_per_step": stage["gpu_ms"] / args.steps,
     }

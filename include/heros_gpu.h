@@ -394,6 +394,12 @@ int32_t heros_window_recv_candidates(heros_handle h);
  * p = pInfection of the evaluation.  first = index of the first event wanted. */
 int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
                              int16_t* sublocation, double* time, double* p, int64_t* n_out);
+/* The same events in the order the device logged them: all events of a window lie behind those of the windows before it,
+ * inside a window the order is arbitrary (and may differ from run to run; the SET of events does not).  For a host that
+ * applies the day's events and does not care about their order: no ordering pass, the columns are copied as they are.
+ * `first` counts in log order here, in (time, person) order in heros_get_infections -- use one of the two consistently. */
+int32_t heros_get_infections_unordered(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
+                                       int16_t* sublocation, double* time, double* p, int64_t* n_out);
 /* disease-phase trajectory: every phase entered (incl. Exposed), ordered by (time, person) */
 int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, int32_t* person, uint8_t* phase,
                               double* time, int64_t* n_out);

@@ -936,10 +936,14 @@ int32_t sync_counters(heros_handle h)
         size_t first = h->series_fetched;
         if (done - first > (size_t) SERIES_RING) first = done - SERIES_RING;  // older rows were overwritten (never: see window_begin)
         h->series_counts.resize(done * 8, 0);
-        std::vector<long long> rows((size_t) SERIES_RING * 8);
-        CU(h, cudaMemcpy(rows.data(), h->d_series.p, rows.size() * 8, cudaMemcpyDeviceToHost));
-        for (size_t w = first; w < done; ++w)
-            for (int k = 0; k < 8; ++k) h->series_counts[w * 8 + k] = (int64_t) rows[(w % SERIES_RING) * 8 + k];
+        // only the rows of the windows finished since the last fetch (one or two pieces of the ring)
+        for (size_t w = first; w < done;)
+        {
+            const size_t slot = w % SERIES_RING, run = std::min(done - w, (size_t) SERIES_RING - slot);
+            static_assert(sizeof(int64_t) == sizeof(long long), "series rows are copied as they are");
+            CU(h, cudaMemcpy(h->series_counts.data() + w * 8, h->d_series.p + slot * 8, run * 64, cudaMemcpyDeviceToHost));
+            w += run;
+        }
         h->series_fetched = done;
     }
     if (h->h_ctr->overflow & 1u)
@@ -2079,7 +2083,7 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         // (the events of a later window are later, so the merge normally has nothing to move)
         const size_t old = (size_t) h->o_inf_n, add = (size_t) (n - h->o_inf_n);
         // into pinned memory: four asynchronous copies, one wait (pageable targets would be staged one after the other)
-        const size_t need = add * 28 + 64;
+        const size_t need = add * 32 + 64;
         if (need > h->pin_bytes)
         {
             if (h->pin_buf) cudaFreeHost(h->pin_buf);
@@ -2097,12 +2101,50 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         CU(h, cudaMemcpyAsync(t, h->inf_t.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaMemcpyAsync(pp, h->inf_p.p + old, add * 8, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
+        if (h->o_inf.capacity() < old + add) h->o_inf.reserve(std::max<size_t>(2 * (old + add), 1u << 16));
         h->o_inf.resize(old + add);
-        for (size_t i = 0; i < add; ++i) h->o_inf[old + i] = heros_engine::InfEvent{t[i], pp[i], key[i], per[i]};
         auto before = [](const heros_engine::InfEvent& x, const heros_engine::InfEvent& y) {
             return x.t < y.t || (x.t == y.t && x.person < y.person);
         };
-        std::sort(h->o_inf.begin() + old, h->o_inf.end(), before);
+        {
+            // order of the new events by (time, person): times are non-negative, so their bit patterns order as integers.
+            // LSD radix sort of 16-byte keys by the time bits (digits that are the same in every key -- the high ones of a
+            // 24 h window -- are skipped), stable; runs of equal times are then ordered by person; one gather.
+            using Key = heros_engine::SortKey;
+            std::vector<Key>& keys = h->sort_keys;
+            std::vector<Key>& tmp = h->sort_tmp;
+            keys.resize(add);
+            tmp.resize(add);
+            for (size_t i = 0; i < add; ++i)
+            {
+                uint64_t b;
+                memcpy(&b, &t[i], 8);
+                keys[i] = Key{b, per[i], (uint32_t) i};
+            }
+            for (int shift = 0; shift < 64; shift += 11)
+            {
+                uint32_t hist[2049] = {};
+                for (const Key& k : keys) ++hist[((k.t >> shift) & 0x7FF) + 1];
+                bool trivial = false;
+                for (int b = 1; b <= 2048; ++b) trivial = trivial || hist[b] == add;
+                if (trivial) continue;
+                for (int b = 0; b < 2048; ++b) hist[b + 1] += hist[b];
+                for (const Key& k : keys) tmp[hist[(k.t >> shift) & 0x7FF]++] = k;
+                keys.swap(tmp);
+            }
+            for (size_t i = 0; i < add;)
+            {
+                size_t j = i + 1;
+                while (j < add && keys[j].t == keys[i].t) ++j;
+                if (j - i > 1) std::sort(keys.begin() + i, keys.begin() + j, [](const Key& x, const Key& y) { return x.person < y.person; });
+                i = j;
+            }
+            for (size_t i = 0; i < add; ++i)
+            {
+                const uint32_t k = keys[i].idx;
+                h->o_inf[old + i] = heros_engine::InfEvent{t[k], pp[k], key[k], per[k]};
+            }
+        }
         if (old && add && before(h->o_inf[old], h->o_inf[old - 1]))
             std::inplace_merge(h->o_inf.begin(), h->o_inf.begin() + old, h->o_inf.end(), before);
         h->o_inf_n = n;
@@ -2120,6 +2162,48 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         if (p) p[i] = h->o_inf[k].p;
     }
     *n_out = avail;
+    return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+int32_t heros_get_infections_unordered(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
+                                       int16_t* sublocation, double* time, double* p, int64_t* n_out)
+{
+    if (!h || !n_out || first < 0 || capacity < 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    int32_t rc = current_counters(h);
+    if (rc != HEROS_OK) return rc;
+    const int64_t n = (int64_t) std::min<unsigned long long>(h->h_ctr->n_inf_log, h->inf_person.n);
+    const int64_t avail = std::max<int64_t>(0, n - first);
+    const int64_t m = std::min(avail, capacity);
+    *n_out = avail;
+    if (m > 0)
+    {
+        const size_t add = (size_t) m, need = add * 28 + 64;
+        if (need > h->pin_bytes)
+        {
+            if (h->pin_buf) cudaFreeHost(h->pin_buf);
+            h->pin_buf = nullptr; h->pin_bytes = 0;
+            CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
+            h->pin_bytes = 2 * need;
+        }
+        double* t = reinterpret_cast<double*>(h->pin_buf);
+        double* pp = t + add;
+        uint64_t* key = reinterpret_cast<uint64_t*>(pp + add);
+        uint32_t* per = reinterpret_cast<uint32_t*>(key + add);
+        if (person) CU(h, cudaMemcpyAsync(per, h->inf_person.p + first, add * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (location || sublocation) CU(h, cudaMemcpyAsync(key, h->inf_gkey.p + first, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (time) CU(h, cudaMemcpyAsync(t, h->inf_t.p + first, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (p) CU(h, cudaMemcpyAsync(pp, h->inf_p.p + first, add * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (person) memcpy(person, per, add * 4);
+        if (time) memcpy(time, t, add * 8);
+        if (p) memcpy(p, pp, add * 8);
+        for (size_t i = 0; i < add && (location || sublocation); ++i)
+        {
+            if (location) location[i] = (int32_t) (key[i] >> 16);  // (global location id << 16) | sub-location
+            if (sublocation) sublocation[i] = (int16_t) (key[i] & 0xFFFFu);
+        }
+    }
     return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
 }
 

@@ -228,6 +228,8 @@ struct heros_engine
     // sorted output caches
     struct InfEvent { double t, p; uint64_t gkey; uint32_t person; };
     std::vector<InfEvent> o_inf;
+    struct SortKey { uint64_t t; uint32_t person, idx; };
+    std::vector<SortKey> sort_keys, sort_tmp;  // scratch of the (time, person) ordering of newly fetched events
     struct TrEvent { double t; uint32_t person; uint8_t phase; };
     std::vector<TrEvent> o_tr;
     unsigned long long o_inf_n = ~0ull, o_tr_n = ~0ull;

@@ -373,9 +373,12 @@ class HerosEngine:
         return st.as_dict()
 
     # ---- outputs ----
-    def infections(self, first: int = 0) -> Dict[str, np.ndarray]:
+    def infections(self, first: int = 0, ordered: bool = True) -> Dict[str, np.ndarray]:
+        """Infection events from number ``first`` on: ordered by (time, person) (heros_get_infections), or -- cheaper -- in
+        the order the device logged them (heros_get_infections_unordered: windows in order, arbitrary inside a window)."""
+        fn = self._lib.heros_get_infections if ordered else self._lib.heros_get_infections_unordered
         n = C.c_int64(0)
-        self._check(self._lib.heros_get_infections(self._h, first, 0, None, None, None, None, None, C.byref(n)))
+        self._check(fn(self._h, first, 0, None, None, None, None, None, C.byref(n)))
         m = n.value
         person = np.zeros(m, np.int32)
         loc = np.zeros(m, np.int32)
@@ -383,8 +386,7 @@ class HerosEngine:
         t = np.zeros(m, np.float64)
         p = np.zeros(m, np.float64)
         if m:
-            self._check(self._lib.heros_get_infections(self._h, first, m, _p(person), _p(loc), _p(sub), _p(t), _p(p),
-                                                       C.byref(n)))
+            self._check(fn(self._h, first, m, _p(person), _p(loc), _p(sub), _p(t), _p(p), C.byref(n)))
         return dict(person=person, loc=loc, sub=sub, time=t, p=p)
 
     def transitions(self, first: int = 0) -> Dict[str, np.ndarray]:

@@ -48,3 +48,31 @@ def test_factor_driven_location_refuses_a_window_across_midnight():
         eng.step(36.0)
     assert "midnight" in str(e.value)
     eng.close()
+
+
+def test_unordered_getter_returns_the_same_events():
+    """heros_get_infections_unordered: the events as the device logged them (windows in order), fetched day by day with a
+    running count -- the same set as the (time, person)-ordered getter."""
+    from common import make_engine
+    scn, _ = satellite_city(seed=33)
+    props = load_props("distance")
+    props["covidT_dist.alpha"] = "1.0"
+    eng = make_engine(scn, props, _lib.MODEL_DISTANCE, _lib.TRIGGER_EXIT_ONLY, 17)
+    eng.expose(scn.seeds, np.zeros(len(scn.seeds)))
+    eng.submit_visits(scn.person, scn.loc, scn.sub, scn.t_in, scn.t_out)
+    got = {k: [] for k in ("person", "loc", "sub", "time", "p")}
+    n = 0
+    for d in range(scn.days):
+        eng.step(24.0 * (d + 1))
+        new = eng.infections(first=n, ordered=False)
+        assert ((new["time"] >= 24.0 * d) & (new["time"] < 24.0 * (d + 1))).all()   # the events of this window only
+        n += len(new["person"])
+        for k in got:
+            got[k].append(new[k])
+    got = {k: np.concatenate(v) for k, v in got.items()}
+    want = eng.infections()
+    assert len(want["person"]) == n > 100
+    order = np.lexsort((got["person"], got["time"]))
+    for k in got:
+        np.testing.assert_array_equal(got[k][order], want[k])
+    eng.close()
