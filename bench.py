@@ -412,7 +412,7 @@ def parity_check(args, rank, world, local, dev):
                                         part.person_bases, part.loc_bases)
     cap = torch.tensor([int(2 * max(int(np.diff(off0).max()), 1024))], dtype=torch.int64, device=dev)
     dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-    bx, kind = open_exchange(sh, int(cap.item()), 4096, args.exchange, rank)
+    bx, kind = open_exchange(sh, int(cap.item()), 65536, args.exchange, rank)
     open_remote, n_remote = None, 0
     for d in range(days):
         st = gen.generate_day(eng.agent_state()["phase"])
@@ -514,7 +514,7 @@ def run_ours(args):
         bx = None
         if world > 1:
             sh = sharded.ShardedEngine(eng, rank, world, person_bases, loc_bases, device=dev)
-            bx, exchange[0] = open_exchange(sh, guest_capacity[0], 16384, exchange[0], rank)
+            bx, exchange[0] = open_exchange(sh, guest_capacity[0], 65536, exchange[0], rank)
         eng.seed_infections(N_INFECTED)
         engines.append(eng)
         return eng, bx, torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -638,20 +638,45 @@ def run_ours(args):
             # the same pattern with the peer-to-peer exchange: the window of day d (guests out, candidates back -- flags in
             # the peers' memory, no host in the loop) is enqueued, the shard's own stays of day d + 1 follow beside it
             submit_day(eng, d0, cols_of_day(d0)[0], device)
+            host = host_ms
+            for k in host:
+                host[k] = 0.0
             for d in range(d0, d1):
-                if d + 1 < d1 and not device:
+                ta = time.perf_counter()
+                remote = cols_of_day(d)[1]
+                if not device:
+                    # The (few) stays of this window in other shards' locations cross PCIe FIRST, on the engine stream: behind
+                    # the 50 MB of tomorrow's own stays they would wait a millisecond in the copy engine's queue, the window
+                    # with them -- and, through the flags, every peer's window too.
+                    with bx.shard.on_stream():
+                        remote = {k: v.to(dev, non_blocking=True) for k, v in remote.items()}
+                # Measured at N = 2: with tomorrow's copy enqueued BEFORE the window (as in the single-engine loop) the window
+                # only started when the copy had finished (heros_wait 0.58 ms instead of 0.16 ms); enqueued behind the window
+                # it overlaps.  HEROS_BENCH_EARLY_COPY=1 restores the other order.
+                early = os.environ.get("HEROS_BENCH_EARLY_COPY") is not None
+                if d + 1 < d1 and not device and early:
                     c = cols_of_day(d + 1)[0]
                     eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
-                bx.step_window(24.0 * (d + 1), cols_of_day(d)[1], cols_of_day(d)[2], wait=False)
+                tb = time.perf_counter()
+                bx.step_window(24.0 * (d + 1), remote, cols_of_day(d)[2], wait=False)
+                if d + 1 < d1 and not device and not early:
+                    c = cols_of_day(d + 1)[0]
+                    eng.submit_visits_begin_ptr(c["person"].numel(), *(c[k].data_ptr() for k, _ in COLS))
                 mark()
+                tc = time.perf_counter()
+                host["submit_begin"] += 1e3 * (tb - ta); host["enqueue_window"] += 1e3 * (tc - tb)
                 if d + 1 < d1:
                     if device:
                         submit_day(eng, d + 1, cols_of_day(d + 1)[0], device)
                     else:
                         eng.submit_visits_end()
+                td = time.perf_counter()
+                host["submit_end_copy_done"] += 1e3 * (td - tc)
                 if after_step:
                     stats.append(eng.wait())
+                    te = time.perf_counter()
                     after_step()
+                    host["wait"] += 1e3 * (te - td); host["read_results"] += 1e3 * (time.perf_counter() - te)
             if not after_step:
                 stats.append(eng.wait())
         else:
@@ -702,8 +727,11 @@ def run_ours(args):
 
     timed_days(eng, bx, stream, lambda d: days[d], False, read_results, d0=args.preroll, d1=first_timed)  # warm-up
     box["d2h"] = 0
-    e2e_seconds, e2e_wall, _ = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
+    e2e_seconds, e2e_wall, e2e_stats = timed_days(eng, bx, stream, lambda d: days[d], False, read_results)
     e2e_host_ms = {k: v / args.steps for k, v in host_ms.items()}
+    e2e_host_ms["device_stage_ms"] = {k: float(np.sum([s_[k] for s_ in e2e_stats])) / args.steps
+                                      for k in ("progress_ms", "bucket_ms", "bucket_scan_ms", "transmit_small_ms",
+                                                "transmit_big_ms", "resolve_ms", "gpu_ms")}
     assert (box["counts"] == ref_counts).all()
     e2e_d2h = int(box["d2h"] / args.steps)
     release(eng)
