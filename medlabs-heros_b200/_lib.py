@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libheros_gpu.so")
+# HEROS_GPU_LIB: another build of the same library (csrc/Makefile: `make debug` = device-side bounds checks)
+LIB_PATH = os.environ.get("HEROS_GPU_LIB") or os.path.join(PKG_DIR, "libheros_gpu.so")
 
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_UNKNOWN_PARAMETER = 0, -1, -2, -3, -4, -5

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays PC, PoolArray
                                                         uint32_t person_base, double T1,
                                                         const uint32_t* __restrict__ seg_start,
                                                         const uint64_t* __restrict__ view, StayRec* __restrict__ rec,
-                                                        Counters* ctr)
+                                                        Counters* ctr, uint32_t rec_cap, uint32_t n_keys)
 {
     TlStamp tl_(ctr, TL_SCATTER);
     constexpr uint32_t CHUNK = TPB * IPT;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(TPB) k_bucket_scatter(PoolArrays PC, PoolArray
         }
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
-            if (r[k] != KEY_NONE)
+            if (r[k] != KEY_NONE && HEROS_CHECK(ctr, key[k] < n_keys && dst[k] < rec_cap && dst[k] < seg_start[key[k] + 1]))
             {
                 StayRec o;
                 o.tin = tin[k]; o.tout = tout[k]; o.view = vw[k]; o.person = person[k]; o.pad = pad[k];
@@ -1127,7 +1127,8 @@ int32_t window_transmit(heros_handle h)
     k_bucket_scatter<<<scatter_grid, TPB, 0, s>>>(
         carry_arrays(h, h->carry_cur), fresh_arrays(h), carry_arrays(h, h->carry_cur ^ 1),
         (uint32_t) std::min<size_t>(h->carry_person[h->carry_cur ^ 1].n, 0xFFFFFFFFu), h->d_open_key.p, h->d_open_tin.p, N,
-        h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p);
+        h->bk_rank.p, G, h->person_base, T1, h->seg_start.p, h->d_view.p, h->rec.p, h->d_ctr.p,
+        (uint32_t) std::min<size_t>(h->rec.n, 0xFFFFFFFFu), n_keys);
     k_window_roll<<<1, 32, 0, s>>>(h->d_ctr.p);
     CU(h, cudaEventRecord(h->ev_rolled, s));  // k_submit of the next window may run from here on, beside the transmission
     {
@@ -1162,6 +1163,7 @@ int32_t window_transmit(heros_handle h)
     c.person_base = h->person_base; c.n_agents = N;
     c.loc_first_key = h->d_loc_base.p; c.location_base = h->location_base;
     c.rec = h->rec.p; c.rec_part = h->rec_part.p; c.seg_start = h->seg_start.p;
+    c.rec_cap = (uint32_t) std::min<size_t>(std::min(h->rec.n, h->rec_part.n), 0xFFFFFFFFu);
     c.cand_person = h->cand_person.p; c.cand_gkey = h->cand_gkey.p; c.cand_t = h->cand_t.p; c.cand_p = h->cand_p.p;
     c.cand_cap = (uint32_t) std::min<size_t>(std::min(std::min(h->cand_person.n, h->cand_gkey.n), std::min(h->cand_t.n, h->cand_p.n)), 0xFFFFFFFFu);
     c.best_t = h->d_best_t.p;

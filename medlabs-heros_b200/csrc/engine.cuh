@@ -137,7 +137,19 @@ struct Counters
     unsigned long long n_items;      // work items (sub-location, 32 evaluations) of the hot evaluation kernel
     unsigned long long tab_top;      // entries of the table of evaluations of the hot sub-locations
     unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
+    // work of very different size (a corner shop, a supermarket at noon) is handed out block by block, not by a fixed stride
+    unsigned long long eval_next;      // next work item of k_hot_eval
+    unsigned long long chain_next[N_HOT];  // next entry of hot_seg[class] for k_hot_chain
 };
+// Debug build (-DHEROS_DEBUG, csrc/Makefile `make debug`): every index a window kernel computes is checked before it is used;
+// a failed check raises bit 7 of the overflow mask (the window then fails with HEROS_ERR_CAPACITY naming "128") and the
+// access is skipped.  In the normal build the macro is the bare condition-free statement.
+#ifdef HEROS_DEBUG
+#define HEROS_CHECK(ctr, cond) ((cond) ? true : (atomicOr(&(ctr)->overflow, 128u), false))
+#else
+#define HEROS_CHECK(ctr, cond) (true)
+#endif
+
 #ifdef __CUDACC__
 // thread 0 of every block stamps the kernel's entry when it starts and when it leaves the kernel (any return path)
 struct TlStamp
@@ -197,6 +209,7 @@ struct WindowCtx
     const uint32_t* loc_first_key; int32_t location_base;  // for the global sub-location id of a candidate
     // the window's stays bucketed by sub-location: stays of key k are rec[seg_start[k] .. seg_start[k + 1])
     StayRec* rec;
+    uint32_t rec_cap;           // records allocated (debug build: every segment must end inside)
     const uint32_t* seg_start;  // n_keys + 1 entries
     // candidates; best_t: earliest successful draw so far of every own agent (time bits), which lets later and therefore
     // hopeless candidates of the same person be dropped where they arise

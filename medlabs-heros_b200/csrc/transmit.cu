@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) k_transmit_stream(const WindowCtx c)
         ++occupied;
         if (n > 32) continue;  // queued for the hot path by the prefix-sum kernel
         if (c.key_total && c.key_total[key]) continue;  // evaluated per location by k_transmit_total
+        if (!HEROS_CHECK(c.ctr, a <= b && b <= c.rec_cap)) continue;
         const StayRec* rec = c.rec + a;
         // who is here, and the two latest events
         bool any_ill = false, any_sus = false;
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256, 4) k_transmit_sub(const WindowCtx c)
             key = c.sub_seg[WHICH][w];
             a = c.seg_start[key];
             n = c.seg_start[key + 1] - a;
+            if (!HEROS_CHECK(c.ctr, key < c.n_keys && n <= (uint32_t) S && a + n <= c.rec_cap)) n = 0;
         }
         const bool have = (uint32_t) gl < n;
         StayRec r;
@@ -567,12 +569,22 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
     Local st;
     if (blockIdx.x == 0 && tid == 0 && n_list) atomicAdd(&c.ctr->hot_total, (unsigned long long) n_list);
 
-    for (uint32_t w = blockIdx.x; w < n_list; w += gridDim.x)
+    __shared__ uint32_t s_next;
+    for (;;)
     {
+        // the next sub-location of the class: handed out one at a time (their cost differs by orders of magnitude)
+        __syncthreads();
+        if (tid == 0) s_next = (uint32_t) min(atomicAdd(&c.ctr->chain_next[CLS], 1ull), 0xFFFFFFFFull);
+        __syncthreads();
+        const uint32_t w = s_next;
+        if (w >= n_list) break;
         const uint32_t key = c.hot_seg[CLS][w];
         if (key == KEY_NONE) continue;  // no scratch left for it (the overflow bit is set)
         const uint32_t a = c.seg_start[key];
         const int n = (int) (c.seg_start[key + 1] - a);
+        if (!HEROS_CHECK(c.ctr, key < c.n_keys && n > 32 && a + (uint32_t) n <= c.rec_cap &&
+                                    (CLS == HOT_HUGE || (need_enters ? 2 * n : n) <= (int) HotCfg<CLS>::M_CAP)))
+            continue;
         const StayRec* rec = c.rec + a;
         const double L0 = c.last_calc[key];
         // 0. who is here, and the two latest movement events.  Where nobody can be infected (the majority while the
@@ -627,8 +639,16 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             {
                 const StayRec r = ld_rec(rec + v);
                 const uint32_t tph = view_tphase(r.view);
-                if (phase_is_ill(tph)) st_rec(part + atomicAdd(&s_cnt[0], 1), r);
-                else if (phase_is_susceptible(tph)) st_rec(part + (n - 1 - atomicAdd(&s_cnt[1], 1)), r);
+                if (phase_is_ill(tph))
+                {
+                    const int slot = atomicAdd(&s_cnt[0], 1);
+                    if (HEROS_CHECK(c.ctr, slot >= 0 && slot < n_ill)) st_rec(part + slot, r);
+                }
+                else if (phase_is_susceptible(tph))
+                {
+                    const int slot = n - 1 - atomicAdd(&s_cnt[1], 1);
+                    if (HEROS_CHECK(c.ctr, slot >= n - n_sus && slot < n)) st_rec(part + slot, r);
+                }
             }
         }
         const int slots = need_enters ? 2 * n : n;
@@ -693,12 +713,14 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             if (tout >= c.T0 && tout < c.T1)
             {
                 const int pos = atomicAdd(&bcur[bucket_of(tout)], 1);
+                if (!HEROS_CHECK(c.ctr, pos >= 0 && pos < m_ev && (size_t) pos < M)) continue;
                 ev_t[pos] = tout;
                 ev_k[pos] = 0;
             }
             if (need_enters && tin >= c.T0 && tin < c.T1)
             {
                 const int pos = atomicAdd(&bcur[bucket_of(tin)], 1);
+                if (!HEROS_CHECK(c.ctr, pos >= 0 && pos < m_ev && (size_t) pos < M)) continue;
                 ev_t[pos] = tin;
                 ev_k[pos] = 1;
             }
@@ -920,8 +942,15 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         }
     };
 
-    for (unsigned long long it = blockIdx.x; it < n_items; it += gridDim.x)
+    __shared__ unsigned long long s_item;
+    for (;;)
     {
+        // the next work item: handed out one at a time (a corner shop at night, a supermarket at noon)
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&c.ctr->eval_next, 1ull);
+        __syncthreads();
+        const unsigned long long it = s_item;
+        if (it >= n_items) break;
         const uint32_t key = c.item_key[it];
         const unsigned long long tab = c.item_tab[it];
         const int cnt = (int) c.item_cnt[it];
@@ -929,6 +958,9 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         const uint32_t a = c.seg_start[key];
         const int n = (int) (c.seg_start[key + 1] - a);
         const StayRec* part = c.rec_part + a;  // ill stays [0, n_ill), susceptible stays [n - n_sus, n)
+        if (!HEROS_CHECK(c.ctr, n_ill >= 0 && n_sus >= 0 && n_ill + n_sus <= n && a + (uint32_t) n <= c.rec_cap && cnt >= 1 && cnt <= 32 &&
+                                    tab + (unsigned long long) cnt <= c.tab_cap))
+            continue;
         const LocParam lp = c.loc_param[c.key_loc[key]];
         const bool active = lane < cnt;
         const double now = active ? c.tab_now[tab + lane] : pos_inf();
