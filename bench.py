@@ -69,6 +69,11 @@ def parse_args():
                     help="N > 1: persons per GPU of the small partitioned city that is run on all GPUs first and compared, "
                          "event for event, with the CPU oracle on the whole city (0 = skip)")
     ap.add_argument("--parity-days", type=int, default=8)
+    ap.add_argument("--config", default="hague", choices=["hague", "replicas", "europe"],
+                    help="hague: BASELINE configs[0] / [4] (the default the driver runs); replicas: configs[2], seeds side by side "
+                         "on every GPU (--replicas engines per GPU, --persons defaults to 2 x The Hague, --steps 180 for the "
+                         "configuration as written); europe: configs[3], one city of its own size per GPU linked by commuters")
+    ap.add_argument("--replicas", type=int, default=4, help="--config replicas: engines (seeds) per GPU")
     return ap.parse_args()
 
 
@@ -331,6 +336,12 @@ def workload_config(args, city, world, exchange="p2p"):
         return {"workload": f"thehague-synthetic (calibrated: {json.dumps(scenario_calibration())}) N={city.n_persons} locations={n_own} "
                             f"sublocations={int(city.loc_nsub[:n_own].sum())} model={args.model} trigger={args.trigger} "
                             f"seed={SEED} infected0={N_INFECTED}", **step}
+    if args.config == "europe":
+        sizes = [max(20000, int(args.persons * EUROPE_SIZES[r % len(EUROPE_SIZES)])) for r in range(world)]
+        return {"workload": f"europe-synthetic: {world} cities of {sizes} persons (calibrated Hague density), one per GPU, "
+                            f"{args.commute:.3f} of every city's workers work in another city chosen in proportion to its size "
+                            f"(all pairs exchange), model={args.model} trigger={args.trigger} seed={SEED} infected0={N_INFECTED} per city",
+                **step}
     return {"workload": f"one synthetic city of {world} x {args.persons} persons (Hague density and location mix, calibrated: "
                         f"{json.dumps(scenario_calibration())}) cut into "
                         f"{world} geographic shards along the Morton curve of its locations (equal expected load, a person "
@@ -357,6 +368,65 @@ def make_engine(args, props, city, device, flags=0):
         eng.set_transmission_distance(properties.dist_params(props))
     eng.set_progression(properties.prog_params(props))
     return eng
+
+
+EUROPE_SIZES = (1.5, 0.4, 0.9, 0.25, 1.2, 0.6, 1.0, 0.3)  # persons of the cities relative to --persons
+
+
+def europe_city(args, rank, world):
+    """BASELINE configs[3]: the Europe data set -- several cities of their own, one per GPU, linked only by the commuters of
+    role 15 ("worker country to city", data/europe).  Synthetic stand-in: `world` cities of different sizes (EUROPE_SIZES x
+    --persons), every one with its own locations and schedule; the share --commute of the workers of a city works in ANOTHER
+    city, chosen in proportion to its size (all pairs of cities exchange).  A commuter's workplace is a foreign location of
+    its shard's city table (scenario.City.ext_global); after work it goes straight home.  Returns (this rank's city, first
+    global person id of every rank + total, first global location id of every rank + total)."""
+    from heros_b200 import scenario
+    sizes = [max(20000, int(args.persons * EUROPE_SIZES[r % len(EUROPE_SIZES)])) for r in range(world)]
+    cities = [scenario.City(sizes[r], seed=CITY_SEED + 100 + r, origin_m=(40000.0 * r, 0.0), **scenario.HAGUE_CALIBRATED)
+              for r in range(world)]   # every rank builds all of them: it needs the workplace tables of the others
+    person_bases = np.concatenate([[0], np.cumsum([c.n_persons for c in cities])]).astype(np.int64)
+    loc_bases = np.concatenate([[0], np.cumsum([c.n_locations for c in cities])]).astype(np.int64)
+    city = cities[rank]
+    scenario.capacity_diversion(city, SEED)
+    rng = np.random.default_rng(5000 + rank)
+    workers = np.nonzero(city.role == scenario.ROLE_WORKER)[0]
+    pick = workers[rng.random(len(workers)) < args.commute]
+    others = [r for r in range(world) if r != rank]
+    w = np.array([sizes[r] for r in others], np.float64)
+    dest_city = np.array(others)[rng.choice(len(others), len(pick), p=w / w.sum())]
+    ext_gid, ext_nsub, ext_type = [], [], []
+    work_loc, work_sub = city.work_loc.copy(), city.work_sub.copy()
+    for r in others:
+        who = pick[dest_city == r]
+        if not len(who):
+            continue
+        other = cities[r]
+        wp = np.nonzero(other.loc_type == scenario.TYPE_ID["Workplace"])[0]
+        wts = np.maximum(other.loc_nsub[wp], 1).astype(np.float64)
+        dest = wp[rng.choice(len(wp), len(who), p=wts / wts.sum())]
+        uniq, inv = np.unique(dest, return_inverse=True)
+        work_loc[who] = (city.n_locations + len(ext_gid) + inv).astype(np.int32)
+        work_sub[who] = (rng.integers(0, 1 << 30, len(who)) % np.maximum(other.loc_nsub[dest], 1)).astype(np.int16)
+        ext_gid += (loc_bases[r] + uniq).tolist()
+        ext_nsub += other.loc_nsub[uniq].tolist()
+        ext_type += other.loc_type[uniq].tolist()
+    n_ext = len(ext_gid)
+    city.work_loc, city.work_sub = work_loc, work_sub
+    city.ext_global = np.array(ext_gid, np.int64)
+    # the tables of the schedule generator get a row per foreign workplace; nothing is near it: whoever leaves it goes home
+    city.loc_type = np.concatenate([city.loc_type, np.array(ext_type, np.uint8)])
+    city.loc_nsub = np.concatenate([city.loc_nsub, np.array(ext_nsub, np.int16)])
+    city.loc_area = np.concatenate([city.loc_area, np.zeros(n_ext, np.float32)])
+    city.loc_x = np.concatenate([city.loc_x, np.zeros(n_ext, np.float32)])
+    city.loc_y = np.concatenate([city.loc_y, np.zeros(n_ext, np.float32)])
+    city.nearest = np.concatenate([city.nearest, np.full((n_ext,) + city.nearest.shape[1:], scenario.NONE, np.int32)])
+    city.cand = np.concatenate([city.cand, np.full((n_ext,) + city.cand.shape[1:], scenario.NONE, np.int32)])
+    city.n_cand = np.concatenate([city.n_cand, np.zeros((n_ext,) + city.n_cand.shape[1:], np.int32)])
+    if getattr(city, "divert", None) is not None:
+        city.divert = np.concatenate([city.divert, np.zeros(n_ext)])
+    city.person_gid = person_bases[rank] + np.arange(city.n_persons, dtype=np.int64)   # draws keyed by global ids
+    city.loc_gid = np.concatenate([loc_bases[rank] + np.arange(city.n_locations, dtype=np.int64), city.ext_global])
+    return city, person_bases, loc_bases
 
 
 def open_exchange(sh, guest_capacity, candidate_capacity, exchange, rank):
@@ -486,6 +556,10 @@ def run_ours(args):
         # on the whole city (rank 0), event for event.
         if args.parity_persons > 0:
             parity = parity_check(args, rank, world, local, dev)
+        if args.config == "europe":
+            city, person_bases, loc_bases = europe_city(args, rank, world)
+            n_commuters = int((city.work_loc >= city.n_locations).sum())
+    if world > 1 and args.config != "europe":
         # weak scaling: ONE city of world x persons (constant density), cut into world geographic shards; every rank
         # builds the same city from the same seed and keeps its shard
         side = float(np.sqrt(world))
@@ -497,7 +571,7 @@ def run_ours(args):
         person_bases, loc_bases = part.person_bases.copy(), part.loc_bases.copy()
         n_commuters = int((city.work_loc >= city.n_locations).sum())
         del whole, part
-    else:
+    elif world == 1:
         city = scenario.City(args.persons, seed=CITY_SEED, **scenario.HAGUE_CALIBRATED)
         scenario.capacity_diversion(city, SEED)
         person_bases = np.array([0, city.n_persons])
@@ -891,6 +965,119 @@ def run_ours(args):
     shutdown()
 
 
+def run_replicas(args):
+    """BASELINE configs[2]: Haaglanden (about twice The Hague), 32-seed batched replications -- the reference's own practice
+    of one JVM per seed side by side (src/main/resources/server/flip-normal-area-cap.sh) becomes `--replicas` engines per GPU,
+    every engine with its own seed, its own stream and its own host thread (a handle is single-threaded like a DSOL
+    replication; the C ABI releases the GIL), schedule advanced on the device.  The path does not shard: N GPUs = N x
+    replicas independent engines, no data-path collective."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    import heros_b200 as hb
+    from heros_b200 import properties, scenario
+    rank, world, local = (int(os.environ.get(k, "0")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    world = max(world, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/heros_bench_nccl_%h_%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    persons = args.persons if args.persons != HAGUE_PERSONS else 2 * HAGUE_PERSONS
+    props = load_props(args.model)
+    city = scenario.City(persons, seed=CITY_SEED, box_m=(17000.0, 12700.0), **scenario.HAGUE_CALIBRATED)
+    scenario.capacity_diversion(city, SEED)
+    tables = scenario.compile_schedule(city)
+    R = args.replicas
+    total = args.preroll + args.warmup + args.steps
+    first_timed = args.preroll + args.warmup
+
+    engines = []
+    for r in range(R):
+        seed = SEED + rank * R + r
+        model = hb.MODEL_AREA if args.model == "area" else hb.MODEL_DISTANCE
+        eng = hb.HerosEngine(model, seed, device=local)
+        city.install(eng)
+        (eng.set_transmission_area(properties.area_params(props)) if model == hb.MODEL_AREA
+         else eng.set_transmission_distance(properties.dist_params(props)))
+        eng.set_progression(properties.prog_params(props))
+        eng.seed_infections(N_INFECTED)
+        eng.set_schedule(tables, seed)
+        engines.append(eng)
+    streams = [torch.cuda.ExternalStream(e.stream, device=dev) for e in engines]
+    launches = [0] * R
+    go = threading.Barrier(R)
+    start = [torch.cuda.Event(enable_timing=True) for _ in engines]
+    end = [torch.cuda.Event(enable_timing=True) for _ in engines]
+    origin = torch.cuda.Event(enable_timing=True)
+
+    def run(i):
+        e = engines[i]
+        for d in range(first_timed):
+            e.advance_schedule(d)
+            e.step(24.0 * (d + 1))
+        go.wait()
+        if i == 0:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            origin.record()
+        go.wait()
+        start[i].record(streams[i])
+        for d in range(first_timed, total):
+            e.advance_schedule(d)
+            st = e.step(24.0 * (d + 1))          # the replication's host reads the day's counters (DiseaseMonitor)
+            launches[i] += st["gpu_launches"] + 1
+            e.phase_counts()
+        end[i].record(streams[i])
+        end[i].synchronize()
+
+    with ClockSampler(local) as clocks:
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(R)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        torch.cuda.synchronize()
+    seconds = (max(origin.elapsed_time(end[i]) for i in range(R)) - min(origin.elapsed_time(start[i]) for i in range(R))) * 1e-3
+    if world > 1:
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = float(t.item())
+    infected = [int(e.phase_counts()[1:].sum()) for e in engines]
+    value = world * R * city.n_persons * 24.0 * args.steps / seconds
+    line = {
+        "metric": "simulated person-hours/sec", "value": value, "unit": "person-hours/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
+        "sec_per_sim_day": seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"haaglanden-synthetic (calibrated Hague density, {json.dumps(scenario.HAGUE_CALIBRATED)}) N={city.n_persons} "
+                               f"locations={city.n_locations}, {R} replications per GPU (seeds {SEED}..{SEED + world * R - 1}), "
+                               f"model={args.model}, activity schedule on the device, replicas only (no exchange)",
+                   "step": "one simulated day of every replication", "first_timed_day": first_timed,
+                   "l2": "every replication streams its own 4.7 M stays per day (150 MB of records) through HBM; "
+                         f"{R} replications side by side exceed the 126 MB L2"},
+        "clocks": clocks.summary(),
+        "timing": "CUDA events on every engine stream, from the first start to the last end of the timed days, max over ranks",
+        "e2e": {"value": value, "unit": "person-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64 * R,
+                "ms_per_step": 1e3 * seconds / args.steps,
+                "what": "the schedule is advanced on the device: per day and replication the host only reads the counters"},
+        "gpu_launches": int(sum(launches)),
+        "replicas_per_gpu": R, "ms_per_replica_day": 1e3 * seconds / args.steps / R,
+        "infected_per_seed_rank0": infected,
+        "roofline": None, "cpu_baseline": None,
+    }
+    for e in engines:
+        e.close()
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     # stdout carries ONE JSON line: while the bench runs, file descriptor 1 points to stderr, so that whatever a library
@@ -901,6 +1088,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "replicas":
+        run_replicas(args)
     else:
         run_ours(args)
 
