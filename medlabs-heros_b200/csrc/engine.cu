@@ -1106,7 +1106,8 @@ int32_t window_transmit(heros_handle h)
     const size_t tab_cap = 2 * (size_t) n_total + 64, item_cap = (size_t) n_total / 8 + 1024;
     CU(h, h->tab_now.ensure(tab_cap)); CU(h, h->tab_dur.ensure(tab_cap)); CU(h, h->tab_head.ensure(tab_cap));
     CU(h, h->item_key.ensure(item_cap)); CU(h, h->item_tab.ensure(item_cap)); CU(h, h->item_cnt.ensure(item_cap));
-    CU(h, h->item_nill.ensure(item_cap)); CU(h, h->item_nsus.ensure(item_cap));
+    CU(h, h->item_nill.ensure(item_cap)); CU(h, h->item_nsus.ensure(item_cap)); CU(h, h->item_part.ensure(item_cap));
+    CU(h, h->part_table.ensure((size_t) n_total / 33 + 64));  // one per hot sub-location (> 32 stays each)
     // global scratch of the sub-locations too large for shared memory (> 8192 movement events): 42 B per stay + 82 KB
     // per such sub-location (each holds > 4096 stays), and 4 B per stay of a total-branch location
     CU(h, h->scratch.ensure(std::min<size_t>(72 * (size_t) n_total + (4u << 20), (size_t) 8 << 30)));
@@ -1174,8 +1175,9 @@ int32_t window_transmit(heros_handle h)
     c.tab_now = h->tab_now.p; c.tab_dur = h->tab_dur.p; c.tab_head = h->tab_head.p;
     c.tab_cap = std::min(std::min(h->tab_now.n, h->tab_dur.n), h->tab_head.n);
     c.item_key = h->item_key.p; c.item_tab = h->item_tab.p; c.item_cnt = h->item_cnt.p;
-    c.item_nill = h->item_nill.p; c.item_nsus = h->item_nsus.p;
-    c.item_cap = std::min(std::min(std::min(h->item_key.n, h->item_tab.n), h->item_cnt.n), std::min(h->item_nill.n, h->item_nsus.n));
+    c.item_nill = h->item_nill.p; c.item_nsus = h->item_nsus.p; c.item_part = h->item_part.p;
+    c.part_table = h->part_table.p; c.part_cap = h->part_table.n;
+    c.item_cap = std::min(std::min(std::min(h->item_key.n, h->item_tab.n), h->item_cnt.n), std::min(std::min(h->item_nill.n, h->item_nsus.n), h->item_part.n));
     c.huge_off = h->huge_off.p; c.scratch = h->scratch.p; c.scratch_cap = h->scratch.n;
     c.flags = h->cfg.flags;
     c.ctr = h->d_ctr.p;
@@ -1363,7 +1365,8 @@ int32_t heros_destroy(heros_handle h)
     h->item_key.release(); h->item_tab.release(); h->item_cnt.release();
     h->tab_now.release(); h->tab_dur.release(); h->tab_head.release();
     for (auto& b : h->hot_seg) b.release();
-    h->rec_part.release(); h->item_nill.release(); h->item_nsus.release(); h->d_timeline.release();
+    h->rec_part.release(); h->item_nill.release(); h->item_nsus.release(); h->item_part.release(); h->part_table.release();
+    h->d_timeline.release();
     h->huge_off.release(); h->scratch.release();
     h->s_closure.release(); h->s_loc_type.release(); h->m_times.release(); h->m_sub.release(); h->m_loc.release();
     h->s_order.release(); h->s_acts.release(); h->s_pat_start.release(); h->s_pat_count.release(); h->s_choice_start.release();

@@ -139,6 +139,7 @@ struct Counters
     unsigned int scan_tile, scan_done;  // single-pass prefix sum: next tile to hand out, tiles finished
     // work of very different size (a corner shop, a supermarket at noon) is handed out block by block, not by a fixed stride
     unsigned long long eval_next;      // next work item of k_hot_eval
+    unsigned long long n_part;         // PartTables handed out
     unsigned long long chain_next[N_HOT];  // next entry of hot_seg[class] for k_hot_chain
 };
 // Debug build (-DHEROS_DEBUG, csrc/Makefile `make debug`): every index a window kernel computes is checked before it is used;
@@ -187,6 +188,18 @@ struct DevBuf
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// The partitioned copy of a hot segment is ordered by the time slot (PART_SLOTS over the window) in which a stay BEGAN, the
+// ill stays and the susceptible stays each; per slot the table keeps where its stays start and the latest t_out among them.
+// A work item of the evaluation kernel covers a short time span: it reads the stays from the first slot that still holds
+// somebody present at its first evaluation to the slot of its last evaluation -- a few slots instead of the whole day.
+constexpr int PART_SLOTS = 32;
+struct PartTable
+{
+    uint32_t start[2][PART_SLOTS + 1];   // [ill, susceptible]: first stay of every slot (relative to the list's first stay)
+    uint32_t pad_[2];
+    double max_tout[2][PART_SLOTS];      // latest t_out of the stays of the slot (-inf: none)
+};
+
 // everything the window kernels need, passed by value
 struct WindowCtx
 {
@@ -228,7 +241,9 @@ struct WindowCtx
     // one work item per 32 of them; the evaluation kernel spreads the items over the whole GPU
     double* tab_now; double* tab_dur; uint32_t* tab_head; unsigned long long tab_cap;
     uint32_t* item_key; unsigned long long* item_tab; uint32_t* item_cnt; uint32_t* item_nill; uint32_t* item_nsus;
+    uint32_t* item_part;             // index of the sub-location's PartTable
     unsigned long long item_cap;
+    PartTable* part_table; unsigned long long part_cap;
     uint32_t flags;
     Counters* ctr;
 };

@@ -180,7 +180,8 @@ struct heros_engine
     size_t series_fetched = 0;    // windows whose counts have been copied into series_counts
 
     // work lists of the transmission kernels + global scratch of huge segments
-    DevBuf<uint32_t> sub_seg[2], hot_seg[N_HOT], item_key, item_cnt, item_nill, item_nsus, tab_head;
+    DevBuf<uint32_t> sub_seg[2], hot_seg[N_HOT], item_key, item_cnt, item_nill, item_nsus, item_part, tab_head;
+    DevBuf<PartTable> part_table;
     DevBuf<unsigned long long> item_tab;
     DevBuf<double> tab_now, tab_dur;
     DevBuf<unsigned long long> huge_off;

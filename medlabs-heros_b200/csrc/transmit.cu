@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
     __shared__ int s_w[33];
     __shared__ unsigned long long s_base[2];
     __shared__ double s_top[2][32];
-    __shared__ int s_cnt[2];
+    __shared__ uint32_t s_pstart[2][PART_SLOTS + 1], s_pcur[2][PART_SLOTS];
+    __shared__ unsigned long long s_pmax[2][PART_SLOTS];
     const int tid = threadIdx.x;
     const uint32_t n_list = (uint32_t) min((unsigned long long) c.hot_cap, c.ctr->n_hot[CLS]);
     const double thr = MODEL == HEROS_MODEL_AREA ? c.area.threshold : c.dist.threshold;
@@ -627,29 +628,67 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             }
         }
         const bool need_eval = n_ill > 0 && n_sus > 0;
+        uint32_t part_idx = 0xFFFFFFFFu;
         if (need_eval)
         {
-            // the evaluation kernel only ever looks at the ill and the susceptible stays: a partitioned copy of the
-            // segment -- the ill ones from the front, the susceptible ones from the back (their order is free: exposure
-            // sums are formed in fixed point, draws are keyed by person and time)
-            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+            // The evaluation kernel only ever looks at the ill and the susceptible stays: a partitioned copy of the segment
+            // -- the ill ones from the front, the susceptible ones behind the others at the back -- each list ordered by the
+            // time slot in which the stay began (a counting sort over PART_SLOTS slots; the order inside a slot is free:
+            // exposure sums are formed in fixed point, draws are keyed by person and time), with the latest t_out per slot.
+            for (int i = tid; i < 2 * (PART_SLOTS + 1); i += G) s_pstart[i / (PART_SLOTS + 1)][i % (PART_SLOTS + 1)] = 0u;
+            for (int i = tid; i < 2 * PART_SLOTS; i += G) s_pmax[i / PART_SLOTS][i % PART_SLOTS] = 0ull;
+            if (tid == 0) s_base[0] = atomicAdd(&c.ctr->n_part, 1ull);
+            __syncthreads();
+            const double pscale = (double) PART_SLOTS / (c.T1 - c.T0);
+            auto pslot = [&](double tin) -> int {
+                const double f = floor((tin - c.T0) * pscale);
+                return f < 0.0 ? 0 : (f > (double) (PART_SLOTS - 1) ? PART_SLOTS - 1 : (int) f);
+            };
+            for (int v = tid; v < n; v += G)
+            {
+                const StayRec r = ld_rec(rec + v);
+                const uint32_t tph = view_tphase(r.view);
+                const int kind = phase_is_ill(tph) ? 0 : (phase_is_susceptible(tph) ? 1 : -1);
+                if (kind < 0) continue;
+                const int b = pslot(r.tin);
+                atomicAdd(&s_pstart[kind][b + 1], 1u);
+                // t_out >= t_in >= 0 (or +inf): the bit patterns order as integers; 0 = no stay in the slot
+                atomicMax(&s_pmax[kind][b], (unsigned long long) f64_bits(r.tout));
+            }
+            __syncthreads();
+            if (tid < 2)  // 32 slots: one thread per list
+            {
+                uint32_t run = 0;
+                for (int b = 0; b <= PART_SLOTS; ++b) { run += s_pstart[tid][b]; s_pstart[tid][b] = run; }
+            }
+            __syncthreads();
+            for (int i = tid; i < 2 * PART_SLOTS; i += G) s_pcur[i / PART_SLOTS][i % PART_SLOTS] = s_pstart[i / PART_SLOTS][i % PART_SLOTS];
             __syncthreads();
             StayRec* part = c.rec_part + a;
             for (int v = tid; v < n; v += G)
             {
                 const StayRec r = ld_rec(rec + v);
                 const uint32_t tph = view_tphase(r.view);
-                if (phase_is_ill(tph))
+                const int kind = phase_is_ill(tph) ? 0 : (phase_is_susceptible(tph) ? 1 : -1);
+                if (kind < 0) continue;
+                const int slot = (int) atomicAdd(&s_pcur[kind][pslot(r.tin)], 1u);
+                const int at = kind == 0 ? slot : n - n_sus + slot;
+                if (HEROS_CHECK(c.ctr, slot >= 0 && slot < (kind == 0 ? n_ill : n_sus))) st_rec(part + at, r);
+            }
+            const unsigned long long pi = s_base[0];
+            if (pi < c.part_cap)
+            {
+                part_idx = (uint32_t) pi;
+                PartTable& T = c.part_table[pi];
+                for (int i = tid; i < 2 * (PART_SLOTS + 1); i += G) T.start[i / (PART_SLOTS + 1)][i % (PART_SLOTS + 1)] = s_pstart[i / (PART_SLOTS + 1)][i % (PART_SLOTS + 1)];
+                for (int i = tid; i < 2 * PART_SLOTS; i += G)
                 {
-                    const int slot = atomicAdd(&s_cnt[0], 1);
-                    if (HEROS_CHECK(c.ctr, slot >= 0 && slot < n_ill)) st_rec(part + slot, r);
-                }
-                else if (phase_is_susceptible(tph))
-                {
-                    const int slot = n - 1 - atomicAdd(&s_cnt[1], 1);
-                    if (HEROS_CHECK(c.ctr, slot >= n - n_sus && slot < n)) st_rec(part + slot, r);
+                    const unsigned long long m = s_pmax[i / PART_SLOTS][i % PART_SLOTS];
+                    T.max_tout[i / PART_SLOTS][i % PART_SLOTS] = m ? bits_f64(m) : neg_inf();
                 }
             }
+            else if (tid == 0)
+                atomicOr(&c.ctr->overflow, 2u);
         }
         const int slots = need_enters ? 2 * n : n;
         int NB = 32;
@@ -794,7 +833,7 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             st.evaluations += (unsigned long long) R;
             c.last_calc[key] = ev_t[node[R - 1]];
         }
-        if (!need_eval) continue;
+        if (!need_eval || part_idx == 0xFFFFFFFFu) continue;
         // 6. one row per evaluation (time, duration, head count), one work item per 32 rows
         const int n_chunks = (R + 31) >> 5;
         if (tid == 0)
@@ -832,6 +871,7 @@ __global__ void __launch_bounds__(HotCfg<CLS>::T) k_hot_chain(const WindowCtx c)
             c.item_cnt[item0 + ch] = (uint32_t) min(32, R - 32 * ch);
             c.item_nill[item0 + ch] = (uint32_t) n_ill;
             c.item_nsus[item0 + ch] = (uint32_t) n_sus;
+            c.item_part[item0 + ch] = part_idx;
         }
     }
     flush_stats(c, st, threadIdx.x & 31);
@@ -959,7 +999,7 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         const int n = (int) (c.seg_start[key + 1] - a);
         const StayRec* part = c.rec_part + a;  // ill stays [0, n_ill), susceptible stays [n - n_sus, n)
         if (!HEROS_CHECK(c.ctr, n_ill >= 0 && n_sus >= 0 && n_ill + n_sus <= n && a + (uint32_t) n <= c.rec_cap && cnt >= 1 && cnt <= 32 &&
-                                    tab + (unsigned long long) cnt <= c.tab_cap))
+                                    tab + (unsigned long long) cnt <= c.tab_cap && (unsigned long long) c.item_part[it] < c.part_cap))
             continue;
         const LocParam lp = c.loc_param[c.key_loc[key]];
         const bool active = lane < cnt;
@@ -978,11 +1018,31 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
             }
         }
         const double t_first = __shfl_sync(FULL, now, 0), t_last = __shfl_sync(FULL, now, cnt - 1);
+        // the part of the two time-ordered lists this item can meet: from the first slot that still holds somebody present
+        // at t_first to the slot of t_last (every lane looks at one slot)
+        int ill_lo = 0, ill_hi = 0, sus_lo = 0, sus_hi = 0;
+        {
+            const PartTable& T = c.part_table[c.item_part[it]];
+            const double f = floor((t_last - c.T0) * ((double) PART_SLOTS / (c.T1 - c.T0)));
+            const int b_hi = f < 0.0 ? 0 : (f > (double) (PART_SLOTS - 1) ? PART_SLOTS - 1 : (int) f);
+#pragma unroll
+            for (int kind = 0; kind < 2; ++kind)
+            {
+                const unsigned live = __ballot_sync(FULL, lane <= b_hi && T.max_tout[kind][lane] >= t_first);
+                int lo = 0, hi = 0;
+                if (live)
+                {
+                    lo = (int) T.start[kind][__ffs(live) - 1];
+                    hi = (int) T.start[kind][b_hi + 1];
+                }
+                if (kind == 0) { ill_lo = lo; ill_hi = hi; } else { sus_lo = lo; sus_hi = hi; }
+            }
+        }
 
         // 1. exposure sums
         ExactSum acc = exact_zero();
-        for_each_record(part, n_ill, [&](const StayRec& r, int v) {
-            const bool cand = v < n_ill && r.tin < t_last && r.tout >= t_first;
+        for_each_record(part + ill_lo, ill_hi - ill_lo, [&](const StayRec& r, int v) {
+            const bool cand = v < ill_hi - ill_lo && r.tin < t_last && r.tout >= t_first;
             unsigned m = __ballot_sync(FULL, cand);
             while (m)
             {
@@ -1019,9 +1079,10 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
         // 2. draws
         if (pos != 0u)
         {
-            const StayRec* sus = part + (n - n_sus);
+            const StayRec* sus = part + (n - n_sus) + sus_lo;
+            const int n_scan = sus_hi - sus_lo;
             constexpr int U = 4;  // records in flight per thread
-            for (int v0 = tid; v0 < n_sus; v0 += U * EVAL_T)
+            for (int v0 = tid; v0 < n_scan; v0 += U * EVAL_T)
             {
                 double tin[U], tout[U];
                 uint32_t person[U];
@@ -1030,7 +1091,7 @@ __global__ void __launch_bounds__(EVAL_T) k_hot_eval(const WindowCtx c)
                 {
                     const int v = v0 + u * EVAL_T;
                     tin[u] = pos_inf(); tout[u] = neg_inf(); person[u] = 0;
-                    if (v < n_sus)
+                    if (v < n_scan)
                     {
                         const uint4* q = reinterpret_cast<const uint4*>(sus + v);
                         const uint4 h0 = __ldg(q);
