@@ -1285,9 +1285,11 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         // of the transmission kernels of the window that is running (heros_debug_timeline: + 30 us).  It has a whole
         // window to finish: lower priority.
         int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // numerically: hi <= lo
         const bool flat = getenv("HEROS_TUNE_FLAT_PRIO") != nullptr;
-        if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, flat ? lo : hi)) != cudaSuccess) return bail("stream", e);
+        // three levels where the device has them: the hot path (below) above the engine stream above k_submit
+        const int mid = hi < lo - 1 ? hi + 1 : hi;
+        if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, flat ? lo : mid)) != cudaSuccess) return bail("stream", e);
         if ((e = cudaStreamCreateWithPriority(&h->sub_stream, cudaStreamNonBlocking, lo)) != cudaSuccess) return bail("stream", e);
     }
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
@@ -1302,12 +1304,15 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         // on streams of higher priority (HEROS_TUNE_AUX_PRIO=1) their blocks go first whenever a slot frees up.
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // HEROS_TUNE_AUX_PRIO=0: the hot path on the level of the engine stream (both branches then mostly follow each other)
         const char* knob = getenv("HEROS_TUNE_AUX_PRIO");
-        const bool prio = knob && knob[0] == '1';  // measured at Hague size: both branches then run side by side and each takes
-                                                   // longer (they share the instruction issue slots) -- the stage ends 2 % earlier
+        const bool hot_first = !(knob && knob[0] == '0');
+        const int mid = hi < lo - 1 ? hi + 1 : hi;
         for (int k = 0; k < N_AUX; ++k)
-            if ((e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, (prio && k != 1) || !getenv("HEROS_TUNE_FLAT_PRIO") ? hi : lo)) != cudaSuccess)
-                return bail("stream", e);
+        {
+            const int level = getenv("HEROS_TUNE_FLAT_PRIO") ? lo : ((hot_first && k != 1) ? hi : mid);
+            if ((e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, level)) != cudaSuccess) return bail("stream", e);
+        }
     }
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("event", e);
