@@ -400,6 +400,14 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
  * `first` counts in log order here, in (time, person) order in heros_get_infections -- use one of the two consistently. */
 int32_t heros_get_infections_unordered(heros_handle h, int64_t first, int64_t capacity, int32_t* person, int32_t* location,
                                        int16_t* sublocation, double* time, double* p, int64_t* n_out);
+/* For a host that keeps windows enqueued (heros_step_async / heros_window_run_peers_async) and consumes results one window
+ * behind: the compartment counts at the end of window number `window` (0-based since heros_set_persons / a snapshot load)
+ * and the number of infection events the log held then.  Waits for THAT window only -- the windows enqueued behind it keep
+ * running -- and reads on a side stream.  heros_get_infections_range then fetches log rows [first, first + n) of finished
+ * windows, in log order (see heros_get_infections_unordered), without waiting for anything. */
+int32_t heros_window_results(heros_handle h, int64_t window, int64_t counts[8], int64_t* infections_logged);
+int32_t heros_get_infections_range(heros_handle h, int64_t first, int64_t n, int32_t* person, int32_t* location,
+                                   int16_t* sublocation, double* time, double* p);
 /* disease-phase trajectory: every phase entered (incl. Exposed), ordered by (time, person) */
 int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, int32_t* person, uint8_t* phase,
                               double* time, int64_t* n_out);

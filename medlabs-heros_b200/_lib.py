@@ -130,6 +130,8 @@ SIGNATURES = {
     "heros_window_send_candidates": (C.c_int32, [_P, _P]),
     "heros_window_recv_candidates": (C.c_int32, [_P]),
     "heros_get_infections": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
+    "heros_window_results": (C.c_int32, [_P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "heros_get_infections_range": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "heros_get_infections_unordered": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_transitions": (C.c_int32, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64)]),
     "heros_get_phase_counts": (C.c_int32, [_P, _P]),

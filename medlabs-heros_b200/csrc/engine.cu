@@ -474,6 +474,8 @@ __device__ __forceinline__ void close_window(Counters* ctr, long long* series, u
     const unsigned long long w = ctr->windows;
     long long* row = series + (size_t) (w % SERIES_RING) * 8;
     for (int k = 0; k < 8; ++k) row[k] = *((volatile long long*) &ctr->phase_counts[k]);
+    // behind the rows: how many infection events the log holds at the end of every window (heros_window_results)
+    series[(size_t) SERIES_RING * 8 + (size_t) (w % SERIES_RING)] = (long long) *((volatile unsigned long long*) &ctr->n_inf_log);
     ctr->cand_total += n_cand;
     ctr->windows = w + 1;
 }
@@ -1222,6 +1224,7 @@ int32_t window_finish(heros_handle h)
     if (h->d_timeline.p) k_timeline_fold<<<1, 32, 0, s>>>(h->d_timeline.p);
     CU(h, cudaGetLastError());
     we.pending = true;
+    we.window_no = (int64_t) h->series_t.size();  // 0-based number of this window since the persons were set
     h->launches_total += h->win_launches;
     h->win_state = 0;
     h->n_guest = 0;
@@ -1328,7 +1331,7 @@ int32_t heros_create(const heros_config* cfg, heros_handle* out)
         if ((e = cudaEventCreateWithFlags(&we.filtered, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
     }
     static_assert(N_AUX == 3, "the events of the auxiliary streams are listed by hand");
-    if ((e = h->d_series.ensure((size_t) SERIES_RING * 8)) != cudaSuccess) return bail("series", e);
+    if ((e = h->d_series.ensure((size_t) SERIES_RING * 9)) != cudaSuccess) return bail("series", e);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((e = h->d_ctr.ensure(1)) != cudaSuccess) return bail("counters", e);
     if ((e = cudaMemsetAsync(h->d_ctr.p, 0, sizeof(Counters), h->stream)) != cudaSuccess) return bail("memset", e);
@@ -2215,6 +2218,74 @@ int32_t heros_get_infections_unordered(heros_handle h, int64_t first, int64_t ca
         }
     }
     return m < avail && capacity > 0 ? HEROS_ERR_CAPACITY : HEROS_OK;
+}
+
+// Results of ONE finished window without waiting for the windows enqueued behind it: the call waits for that window's
+// last kernel only and reads on a side stream (the compartment counts were left in the series ring by k_resolve, the
+// infection log is append-only and the rows of a finished window never change).
+int32_t heros_window_results(heros_handle h, int64_t window, int64_t counts[8], int64_t* infections_logged)
+{
+    if (!h || window < 0) return HEROS_ERR_INVALID;
+    cudaSetDevice(h->cfg.device);
+    if (window >= (int64_t) h->series_t.size()) return fail(h, HEROS_ERR_INVALID, "heros_window_results: that window has not been enqueued");
+    if ((int64_t) h->series_t.size() - window > SERIES_RING - 1) return fail(h, HEROS_ERR_INVALID, "heros_window_results: that window is too long ago");
+    bool found = false;
+    for (auto& we : h->ring)
+        if (we.window_no == window) { CU(h, cudaEventSynchronize(we.resolved)); found = true; }
+    if (!found) CU(h, cudaStreamSynchronize(h->stream));  // its events have been recycled: it finished long ago, or nothing is behind it
+    if (!h->pin_buf || h->pin_bytes < 128)
+    {
+        if (h->pin_buf) cudaFreeHost(h->pin_buf);
+        h->pin_buf = nullptr; h->pin_bytes = 0;
+        CU(h, cudaMallocHost(&h->pin_buf, 4096));
+        h->pin_bytes = 4096;
+    }
+    long long* pin = static_cast<long long*>(h->pin_buf);
+    const size_t slot = (size_t) (window % SERIES_RING);
+    CU(h, cudaMemcpyAsync(pin, h->d_series.p + slot * 8, 64, cudaMemcpyDeviceToHost, h->meta_stream));
+    CU(h, cudaMemcpyAsync(pin + 8, h->d_series.p + (size_t) SERIES_RING * 8 + slot, 8, cudaMemcpyDeviceToHost, h->meta_stream));
+    CU(h, cudaStreamSynchronize(h->meta_stream));
+    if (counts) for (int k = 0; k < 8; ++k) counts[k] = (int64_t) pin[k];
+    if (infections_logged) *infections_logged = (int64_t) pin[8];
+    return HEROS_OK;
+}
+
+// Rows [first, first + n) of the infection log as the device wrote them, read on a side stream: for rows of windows that
+// have finished (heros_window_results tells how many the log held at the end of a window).  Nothing is waited for.
+int32_t heros_get_infections_range(heros_handle h, int64_t first, int64_t n, int32_t* person, int32_t* location,
+                                   int16_t* sublocation, double* time, double* p)
+{
+    if (!h || first < 0 || n < 0) return HEROS_ERR_INVALID;
+    if (n == 0) return HEROS_OK;
+    cudaSetDevice(h->cfg.device);
+    if ((size_t) (first + n) > h->inf_person.n) return fail(h, HEROS_ERR_INVALID, "heros_get_infections_range: beyond the log");
+    const size_t add = (size_t) n, need = add * 28 + 64;
+    if (need > h->pin_bytes)
+    {
+        if (h->pin_buf) cudaFreeHost(h->pin_buf);
+        h->pin_buf = nullptr; h->pin_bytes = 0;
+        CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
+        h->pin_bytes = 2 * need;
+    }
+    double* t = reinterpret_cast<double*>(h->pin_buf);
+    double* pp = t + add;
+    uint64_t* key = reinterpret_cast<uint64_t*>(pp + add);
+    uint32_t* per = reinterpret_cast<uint32_t*>(key + add);
+    cudaStream_t ms = h->meta_stream;
+    if (person) CU(h, cudaMemcpyAsync(per, h->inf_person.p + first, add * 4, cudaMemcpyDeviceToHost, ms));
+    if (location || sublocation) CU(h, cudaMemcpyAsync(key, h->inf_gkey.p + first, add * 8, cudaMemcpyDeviceToHost, ms));
+    if (time) CU(h, cudaMemcpyAsync(t, h->inf_t.p + first, add * 8, cudaMemcpyDeviceToHost, ms));
+    if (p) CU(h, cudaMemcpyAsync(pp, h->inf_p.p + first, add * 8, cudaMemcpyDeviceToHost, ms));
+    CU(h, cudaStreamSynchronize(ms));
+    if (person) memcpy(person, per, add * 4);
+    if (time) memcpy(time, t, add * 8);
+    if (p) memcpy(p, pp, add * 8);
+    for (size_t i = 0; i < add && (location || sublocation); ++i)
+    {
+        if (location) location[i] = (int32_t) (key[i] >> 16);
+        if (sublocation) sublocation[i] = (int16_t) (key[i] & 0xFFFFu);
+    }
+    return HEROS_OK;
 }
 
 int32_t heros_get_transitions(heros_handle h, int64_t first, int64_t capacity, int32_t* person, uint8_t* phase,

@@ -57,6 +57,7 @@ struct WindowEvents
     cudaEvent_t begin, opened, scanned, scattered, mid, transmitted, resolved;  // on the engine stream, in this order
     cudaEvent_t fork, filtered, join[N_AUX];                                     // the auxiliary streams of the stage
     bool pending = false;  // recorded, not yet added to the stage times
+    int64_t window_no = -1; // which window of the run these events belong to
 };
 
 struct heros_engine

@@ -389,6 +389,21 @@ class HerosEngine:
             self._check(fn(self._h, first, m, _p(person), _p(loc), _p(sub), _p(t), _p(p), C.byref(n)))
         return dict(person=person, loc=loc, sub=sub, time=t, p=p)
 
+    def window_results(self, window: int):
+        """heros_window_results: (compartment counts at the end of window ``window``, infection events logged by then);
+        waits for that window only."""
+        c = np.zeros(8, np.int64)
+        n = C.c_int64(0)
+        self._check(self._lib.heros_window_results(self._h, int(window), _p(c), C.byref(n)))
+        return c, int(n.value)
+
+    def infections_range(self, first: int, n: int) -> Dict[str, np.ndarray]:
+        """heros_get_infections_range: log rows [first, first + n) of finished windows, nothing waited for."""
+        person, loc, sub = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int16)
+        t, p = np.zeros(n, np.float64), np.zeros(n, np.float64)
+        self._check(self._lib.heros_get_infections_range(self._h, int(first), int(n), _p(person), _p(loc), _p(sub), _p(t), _p(p)))
+        return dict(person=person, loc=loc, sub=sub, time=t, p=p)
+
     def transitions(self, first: int = 0) -> Dict[str, np.ndarray]:
         n = C.c_int64(0)
         self._check(self._lib.heros_get_transitions(self._h, first, 0, None, None, None, C.byref(n)))

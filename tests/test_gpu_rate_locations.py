@@ -76,3 +76,42 @@ def test_unordered_getter_returns_the_same_events():
     for k in got:
         np.testing.assert_array_equal(got[k][order], want[k])
     eng.close()
+
+
+def test_window_results_one_window_behind():
+    """heros_window_results / heros_get_infections_range: the counts and the events of every window of a run whose windows
+    were all enqueued at once (heros_step_async), read window by window -- equal to a run that waits after every day."""
+    from common import make_engine
+    scn, _ = satellite_city(seed=35)
+    props = load_props("distance")
+    props["covidT_dist.alpha"] = "1.0"
+    runs = []
+    for lagged in (False, True):
+        eng = make_engine(scn, props, _lib.MODEL_DISTANCE, _lib.TRIGGER_EXIT_ONLY, 17)
+        eng.expose(scn.seeds, np.zeros(len(scn.seeds)))
+        eng.submit_visits(scn.person, scn.loc, scn.sub, scn.t_in, scn.t_out)
+        counts, events, n = [], [], 0
+        if lagged:
+            for d in range(scn.days):
+                eng.step_async(24.0 * (d + 1))
+            for d in range(scn.days):
+                c, logged = eng.window_results(d)
+                counts.append(c)
+                events.append(eng.infections_range(n, logged - n))
+                n = logged
+            eng.wait()
+        else:
+            for d in range(scn.days):
+                eng.step(24.0 * (d + 1))
+                counts.append(eng.phase_counts())
+                new = eng.infections(first=n, ordered=False)
+                events.append(new)
+                n += len(new["person"])
+        runs.append((np.array(counts), events, n))
+        eng.close()
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])
+    assert runs[0][2] == runs[1][2] > 100
+    for a, b in zip(runs[0][1], runs[1][1]):
+        oa, ob = np.lexsort((a["person"], a["time"])), np.lexsort((b["person"], b["time"]))
+        for k in a:
+            np.testing.assert_array_equal(a[k][oa], b[k][ob])
