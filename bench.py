@@ -708,7 +708,7 @@ def run_ours(args):
                 # everything is resident in HBM: the whole job is enqueued (no window waits for the host: the fill
                 # counts of the pools, the work lists and the candidates stay on the device), one wait at the end
                 stats.append(eng.wait())
-        elif isinstance(bx, sharded.PeerExchange):
+        elif isinstance(bx, sharded.PeerExchange) and not (after_step and os.environ.get("HEROS_BENCH_SERIAL")):
             # the same pattern with the peer-to-peer exchange: the window of day d (guests out, candidates back -- flags in
             # the peers' memory, no host in the loop) is enqueued, the shard's own stays of day d + 1 follow beside it
             submit_day(eng, d0, cols_of_day(d0)[0], device)

@@ -92,3 +92,38 @@ def test_open_remote_stays_are_resent_until_closed():
                                                 dict(person=np.array([1], np.int32), loc=np.array([7], np.int32),
                                                      sub=np.zeros(1, np.int16), t_in=np.array([20.0]), t_out=np.array([np.inf])))
     assert rem["person"].tolist() == [1] and np.isinf(rem["t_out"]).all() and open_next2["person"].tolist() == [1]
+
+
+def test_europe_cities_are_linked_by_commuters_with_global_ids():
+    """bench.py --config europe (BASELINE configs[3]): cities of their own size, one per GPU; the commuters' workplaces are
+    foreign locations of the city table, their stays come out of the schedule generator with the other city's global ids."""
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    args = types.SimpleNamespace(persons=20000, commute=0.1)
+    world = 3
+    shards = [bench.europe_city(args, r, world) for r in range(world)]
+    for r, (c, pb, lb) in enumerate(shards):
+        np.testing.assert_array_equal(pb, shards[0][1])
+        np.testing.assert_array_equal(lb, shards[0][2])
+        assert pb[r + 1] - pb[r] == c.n_persons and lb[r + 1] - lb[r] == c.n_locations
+        far = c.work_loc >= c.n_locations
+        assert 0.02 * c.n_persons < far.sum() < 0.1 * c.n_persons            # a tenth of the workers
+        gid = c.ext_global[c.work_loc[far] - c.n_locations]
+        owner = np.searchsorted(lb[1:], gid, side="right")
+        assert (owner != r).all() and set(owner.tolist()) == set(range(world)) - {r}   # every other city is a destination
+        st = scenario.ScheduleGenerator(c, 111).generate_day(np.zeros(c.n_persons, np.uint8))
+        own, rem, off, _ = sharded.split_stays(c, st, r, pb, lb)
+        assert len(rem["person"]) > 0.5 * far.sum() and off[r + 1] == off[r]
+        assert ((rem["person"] >= pb[r]) & (rem["person"] < pb[r + 1])).all()
+        assert (np.searchsorted(lb[1:], rem["loc"], side="right") != r).all()
+        # the sub-location of a remote stay exists in the city that owns the workplace
+        for dest in range(world):
+            rows = slice(off[dest], off[dest + 1])
+            if dest != r and off[dest + 1] > off[dest]:
+                other = shards[dest][0]
+                local = rem["loc"][rows] - lb[dest]
+                assert (rem["sub"][rows] < np.maximum(other.loc_nsub[local], 1)).all()
+                assert (other.loc_type[local] == scenario.TYPE_ID["Workplace"]).all()
