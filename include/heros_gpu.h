@@ -207,16 +207,16 @@ int32_t heros_submit_visits_device(heros_handle h, int64_t n, const int32_t* per
  *      (model/HerosModel.java:484-504; Mon-Thu use the Monday pattern, factory/ConstructHerosModel.java:931-940), activity
  *      rows (:763-942: duration / travel / until-fixed-time activities with Constant / Uniform / Triangular durations),
  *      locators (:944-1072: 0 Home, 1 Work / School, 2 Current, 3 Nearest(type choice), 4 Random(type choice) among the
- *      candidates within the maximum distance of the home building).  The phase that selects a day pattern is the one
+ *      candidates within the maximum distance; both search from the place the person IS in, as the reference's
+ *      NearestLocator / RandomLocator(new CurrentLocator(), ...) do (:997, 1012); + 0x10: the capacity-constrained form).  The phase that selects a day pattern is the one
  *      held at midnight; travel time is spent outside every location.  Draws are Philox numbers keyed by
  *      (seed, person, day, activity), so the stays do not depend on the device or the thread layout.
  *      heros_advance_schedule(day) produces the stays of simulated day `day` for every person directly in HBM (what
  *      heros_submit_visits would have received); heros_step then processes the day.  Capacity-constrained locators: see
- *      heros_set_capacity_diversion.  (was:) and
- *      LocationPolicy closures are not implemented (they stay with the host-driven path). ---- */
+ *      heros_set_capacity_diversion; LocationPolicy closures: heros_set_closure_policy. ---- */
 typedef struct heros_activity {
     int32_t kind;      /* 0 duration activity, 1 travel, 2 until fixed time */
-    int32_t locator;   /* 0 home, 1 work / school, 2 current, 3 nearest, 4 random */
+    int32_t locator;   /* 0 home, 1 work / school, 2 current, 3 nearest, 4 random, 5 travel-mode locator; | 0x10 capacity-constrained */
     int32_t choice;    /* index of the location-type choice table, -1 none */
     int32_t dist;      /* heros_distribution of the duration (hours) */
     double min, mode, max, until;
