@@ -92,3 +92,61 @@ def test_sort_by_destination_groups_rows_by_owner():
     assert out["person"].tolist() == [1, 4, 2, 5, 6, 0, 3]
     empty, off = sharded.sort_by_destination({k: v[:0] for k, v in cols.items()}, bases, 3)
     assert off.tolist() == [0, 0, 0, 0] and len(empty["loc"]) == 0
+
+
+def _partition_worker(rank, world, port, out):
+    """One process per shard of ONE partitioned city: every rank builds the city, keeps its shard, generates its persons'
+    day, splits it (own / remote by destination) and sends the remote stays to their owners over gloo; what a rank holds
+    afterwards must be exactly the stays the WHOLE city's generator puts into the rank's locations."""
+    import numpy as np
+    import torch.distributed as dist
+    from heros_b200 import scenario
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        whole0 = scenario.City(8000, seed=12, work_anywhere_fraction=0.3)
+        part = sharded.partition_city(whole0, world)
+        city = part.shard_city(rank)
+        gen = scenario.ScheduleGenerator(city, 111)
+        ref_gen = scenario.ScheduleGenerator(part.global_city(), 111)
+        open_remote = None
+        for d in range(3):
+            phase_all = np.zeros(whole0.n_persons, np.uint8)
+            if d == 1:
+                phase_all[::11] = 3
+            st = gen.generate_day(phase_all[part.person_bases[rank]:part.person_bases[rank + 1]])
+            own, rem, off, open_remote = sharded.split_stays(city, st, rank, part.person_bases, part.loc_bases, open_remote)
+            cols = {k: torch.from_numpy(np.ascontiguousarray(rem[k])) for k in sharded.VISIT_COLUMNS}
+            counts = torch.from_numpy(np.diff(off).astype(np.int64))
+            got, recv = sharded.all_to_all_rows(cols, counts)
+            assert recv[rank] == 0
+            mine = {k: np.concatenate([own[k], got[k].numpy()]) for k in sharded.VISIT_COLUMNS}
+            ref = ref_gen.generate_day(phase_all)
+            here = (ref["loc"] >= part.loc_bases[rank]) & (ref["loc"] < part.loc_bases[rank + 1])
+            # a guest stay that is still open from an earlier day is sent again every day: leave those copies out
+            fresh = ~((mine["t_in"] < 24.0 * d) & np.isinf(mine["t_out"]) &
+                      ~((mine["person"] >= part.person_bases[rank]) & (mine["person"] < part.person_bases[rank + 1])))
+            a = np.c_[mine["person"], mine["loc"], mine["sub"], mine["t_in"], mine["t_out"]][fresh]
+            b = np.c_[ref["person"], ref["loc"], ref["sub"], ref["t_in"], ref["t_out"]][here]
+            a, b = a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])]
+            assert a.shape == b.shape and (a == b).all(), (rank, d, a.shape, b.shape)
+            assert sum(recv) > 50
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_city_exchange_gloo_world_size_2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as m:
+        out = m.dict()
+        procs = [ctx.Process(target=_partition_worker, args=(r, world, port, out)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(out) == {0: 1, 1: 1}
