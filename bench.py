@@ -715,6 +715,7 @@ def run_ours(args):
             host = host_ms
             for k in host:
                 host[k] = 0.0
+            diag = [] if (os.environ.get("HEROS_BENCH_DIAG") and after_step) else None
             for d in range(d0, d1):
                 ta = time.perf_counter()
                 remote = cols_of_day(d)[1]
@@ -751,8 +752,15 @@ def run_ours(args):
                     te = time.perf_counter()
                     after_step()
                     host["wait"] += 1e3 * (te - td); host["read_results"] += 1e3 * (time.perf_counter() - te)
+                    if diag is not None:  # CLOCK_MONOTONIC: one clock for all processes of the machine
+                        diag.append([d, ta, tb, tc, td, te, time.perf_counter(), stats[-1]["bucket_scan_ms"], stats[-1]["resolve_ms"],
+                                     stats[-1]["gpu_ms"], stats[-1]["progress_ms"]])
             if not after_step:
                 stats.append(eng.wait())
+            if diag:
+                with open(f"{os.environ['HEROS_BENCH_DIAG']}_rank{rank}.json", "w") as f:
+                    json.dump({"columns": ["day", "start", "remote+begin", "window enqueued", "copy done", "wait done", "read done",
+                                           "bucket_scan_ms", "resolve_ms", "gpu_ms", "progress_ms"], "rows": diag}, f)
         else:
             for d in range(d0, d1):
                 stats.append(day_step(eng, bx, d, *cols_of_day(d), device=device))

@@ -882,6 +882,20 @@ int32_t join_submissions(heros_handle h)
     return HEROS_OK;
 }
 
+// Pinned staging of the getters.  Page-locking memory is slow (measured at N = 2: one regrow in the middle of a run held the
+// process -- and, through the exchange flags, its peer -- for 15 ms), so it is sized once for what a day can bring
+// (heros_set_persons) and grows by factors of four.
+int32_t ensure_pinned(heros_handle h, size_t bytes)
+{
+    if (bytes <= h->pin_bytes) return HEROS_OK;
+    size_t want = std::max<size_t>(h->pin_bytes ? 4 * h->pin_bytes : 0, std::max<size_t>(bytes, 1u << 20));
+    if (h->pin_buf) cudaFreeHost(h->pin_buf);
+    h->pin_buf = nullptr; h->pin_bytes = 0;
+    CU(h, cudaMallocHost(&h->pin_buf, want));
+    h->pin_bytes = want;
+    return HEROS_OK;
+}
+
 int32_t check_idle(heros_handle h, const char* what)
 {
     if (h->win_state != 0)
@@ -1552,6 +1566,7 @@ int32_t heros_set_persons(heros_handle h, int32_t n, const int8_t* age, const ui
     h->series_t.clear(); h->series_counts.clear(); h->series_fetched = 0;
     h->o_inf_n = h->o_tr_n = ~0ull;  // the event logs start again: the sorted output caches are stale
     h->invalid_reported = 0;
+    { const int32_t rc_ = ensure_pinned(h, 32 * std::min<size_t>(N, (size_t) 1 << 18) + 4096); if (rc_ != HEROS_OK) return rc_; }
     CU(h, cudaStreamSynchronize(h->stream));
     return HEROS_OK;
 }
@@ -2097,13 +2112,7 @@ int32_t heros_get_infections(heros_handle h, int64_t first, int64_t capacity, in
         const size_t old = (size_t) h->o_inf_n, add = (size_t) (n - h->o_inf_n);
         // into pinned memory: four asynchronous copies, one wait (pageable targets would be staged one after the other)
         const size_t need = add * 32 + 64;
-        if (need > h->pin_bytes)
-        {
-            if (h->pin_buf) cudaFreeHost(h->pin_buf);
-            h->pin_buf = nullptr; h->pin_bytes = 0;
-            CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
-            h->pin_bytes = 2 * need;
-        }
+        { const int32_t rc_ = ensure_pinned(h, need); if (rc_ != HEROS_OK) return rc_; }
         unsigned char* pb = static_cast<unsigned char*>(h->pin_buf);
         double* t = reinterpret_cast<double*>(pb);
         double* pp = t + add;
@@ -2192,13 +2201,7 @@ int32_t heros_get_infections_unordered(heros_handle h, int64_t first, int64_t ca
     if (m > 0)
     {
         const size_t add = (size_t) m, need = add * 28 + 64;
-        if (need > h->pin_bytes)
-        {
-            if (h->pin_buf) cudaFreeHost(h->pin_buf);
-            h->pin_buf = nullptr; h->pin_bytes = 0;
-            CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
-            h->pin_bytes = 2 * need;
-        }
+        { const int32_t rc_ = ensure_pinned(h, need); if (rc_ != HEROS_OK) return rc_; }
         double* t = reinterpret_cast<double*>(h->pin_buf);
         double* pp = t + add;
         uint64_t* key = reinterpret_cast<uint64_t*>(pp + add);
@@ -2233,13 +2236,7 @@ int32_t heros_window_results(heros_handle h, int64_t window, int64_t counts[8], 
     for (auto& we : h->ring)
         if (we.window_no == window) { CU(h, cudaEventSynchronize(we.resolved)); found = true; }
     if (!found) CU(h, cudaStreamSynchronize(h->stream));  // its events have been recycled: it finished long ago, or nothing is behind it
-    if (!h->pin_buf || h->pin_bytes < 128)
-    {
-        if (h->pin_buf) cudaFreeHost(h->pin_buf);
-        h->pin_buf = nullptr; h->pin_bytes = 0;
-        CU(h, cudaMallocHost(&h->pin_buf, 4096));
-        h->pin_bytes = 4096;
-    }
+    { const int32_t rc_ = ensure_pinned(h, 128); if (rc_ != HEROS_OK) return rc_; }
     long long* pin = static_cast<long long*>(h->pin_buf);
     const size_t slot = (size_t) (window % SERIES_RING);
     CU(h, cudaMemcpyAsync(pin, h->d_series.p + slot * 8, 64, cudaMemcpyDeviceToHost, h->meta_stream));
@@ -2260,13 +2257,7 @@ int32_t heros_get_infections_range(heros_handle h, int64_t first, int64_t n, int
     cudaSetDevice(h->cfg.device);
     if ((size_t) (first + n) > h->inf_person.n) return fail(h, HEROS_ERR_INVALID, "heros_get_infections_range: beyond the log");
     const size_t add = (size_t) n, need = add * 28 + 64;
-    if (need > h->pin_bytes)
-    {
-        if (h->pin_buf) cudaFreeHost(h->pin_buf);
-        h->pin_buf = nullptr; h->pin_bytes = 0;
-        CU(h, cudaMallocHost(&h->pin_buf, 2 * need));
-        h->pin_bytes = 2 * need;
-    }
+    { const int32_t rc_ = ensure_pinned(h, need); if (rc_ != HEROS_OK) return rc_; }
     double* t = reinterpret_cast<double*>(h->pin_buf);
     double* pp = t + add;
     uint64_t* key = reinterpret_cast<uint64_t*>(pp + add);
