@@ -14,4 +14,4 @@ echo "smoke rc=$? : $(tail -1 gpurun_out/smoke_$TAG.log)"
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 rc=$?
 echo "bench rc=$rc"
-[ $rc -eq 0 ] && bash tools/gpu_profile.sh $TAG
+[ $rc -eq 0 ] && bash tools/gpu_profile.sh $TAG 18   # days 24-26: about 15 % prevalence
