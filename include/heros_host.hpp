@@ -226,6 +226,17 @@ public:
     }
     const std::map<std::string, int>& getLocationTypeNameMap() const { return typeNames_; }
 
+    // The locations ConstructHerosModel.readLocationTable builds as LocationProbBased (factory/ConstructHerosModel.java:382-388,
+    // rows of epidemiology/infection_rates.csv) collect here and go to the engine in one call, after heros_set_locations.
+    void addProbBasedLocation(int locationId, double infectionRateFactor, double infectionRate)
+    {
+        probLoc_.push_back(locationId); probFactor_.push_back(infectionRateFactor); probRate_.push_back(infectionRate);
+    }
+    void installProbBasedLocations()
+    {
+        check(heros_set_rate_locations(engine_, (int32_t) probLoc_.size(), probLoc_.data(), probFactor_.data(), probRate_.data()));
+    }
+
     heros_handle engine() const { return engine_; }
     int modelKind() const { return modelKind_; }
     void check(int32_t rc) const
@@ -240,6 +251,20 @@ private:
     std::shared_ptr<DiseaseTransmission> transmission_;
     std::shared_ptr<Covid19Progression> progression_;
     std::map<std::string, int> typeNames_;
+    std::vector<int32_t> probLoc_;
+    std::vector<double> probFactor_, probRate_;
+};
+
+// medlabs LocationProbBased(model, locationId, locationType, lat, lon, nbSublocations, area, infectionRateFactor, infectionRate,
+// referenceGroupMap, Covid19Progression.exposed) as the factory constructs it (ConstructHerosModel.java:386-387): of its
+// arguments the engine needs the id and the two rates (the reference group is the Worker role, :303-308).
+class LocationProbBased
+{
+public:
+    LocationProbBased(HerosModel& model, int locationId, double infectionRateFactor, double infectionRate)
+    {
+        model.addProbBasedLocation(locationId, infectionRateFactor, infectionRate);
+    }
 };
 
 // medlabs InfectionRecord(exposurePhase, location) as infectPeople fills it (Covid19TransmissionArea.java:135-193)

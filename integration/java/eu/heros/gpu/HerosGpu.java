@@ -202,6 +202,32 @@ public final class HerosGpu implements AutoCloseable
     }
 
     /**
+     * The locations ConstructHerosModel.readLocationTable builds as LocationProbBased (the rows of
+     * epidemiology/infection_rates.csv, ConstructHerosModel.java:274-295 and 382-388): location id, infection_rate_factor,
+     * infection_rate (-1 = not given).  The engine infects in them by rate, never by occupancy (DESIGN.md 3.5).
+     * @param location int[]; location ids as in locations.csv
+     * @param rateFactor double[]; infectionRateFactor of every location
+     * @param rate double[]; infectionRate of every location
+     */
+    public void setRateLocations(final int[] location, final double[] rateFactor, final double[] rate)
+    {
+        try (Arena a = Arena.ofConfined())
+        {
+            check((int) HerosGpuNative.SET_RATE_LOCATIONS.invokeExact(this.handle, location.length,
+                    a.allocateFrom(JAVA_INT, location), a.allocateFrom(JAVA_DOUBLE, rateFactor),
+                    a.allocateFrom(JAVA_DOUBLE, rate)));
+        }
+        catch (RuntimeException e)
+        {
+            throw e;
+        }
+        catch (Throwable t)
+        {
+            throw new MedlabsRuntimeException(t);
+        }
+    }
+
+    /**
      * heros_step: every window up to tUntil (bucket, transmit, draw, resolve, progress).
      * @param tUntil double; simulator time in hours
      */
