@@ -127,3 +127,35 @@ def test_europe_cities_are_linked_by_commuters_with_global_ids():
                 local = rem["loc"][rows] - lb[dest]
                 assert (rem["sub"][rows] < np.maximum(other.loc_nsub[local], 1)).all()
                 assert (other.loc_type[local] == scenario.TYPE_ID["Workplace"]).all()
+
+
+def test_partition_properties_hold_for_random_point_sets():
+    """Property test (hypothesis): whatever the coordinates and weights, the shards are contiguous pieces of the Morton
+    curve, every location lies in exactly one of them, and no shard carries more than its share plus one location's weight."""
+    from hypothesis import given, settings, strategies as st
+
+    class Points:
+        pass
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 400), st.integers(1, 9), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(n, n_shards, seed, clustered):
+        rng = np.random.default_rng(seed)
+        c = Points()
+        c.n_locations = n
+        c.loc_x = (rng.normal(0, 1, n) if clustered else rng.random(n) * 1000).astype(np.float32)
+        c.loc_y = (rng.normal(0, 1, n) if clustered else np.zeros(n)).astype(np.float32)   # also a degenerate line
+        c.home_loc = rng.integers(0, n, 3 * n)
+        w = rng.random(n) * rng.choice([1.0, 50.0], n) + 1e-3
+        part = sharded.partition_city(c, n_shards, weights=w)
+        s = part.shard_of_location
+        assert s.min() >= 0 and s.max() < n_shards and len(s) == n
+        order = np.argsort(sharded.morton_codes(c.loc_x, c.loc_y), kind="stable")
+        assert (np.diff(s[order]) >= 0).all()
+        per = np.bincount(s, weights=w, minlength=n_shards)
+        assert per.max() <= w.sum() / n_shards + w.max() + 1e-9
+        assert part.loc_bases[-1] == n and part.person_bases[-1] == len(c.home_loc)
+        np.testing.assert_array_equal(np.sort(part.loc_new), np.arange(n))
+        np.testing.assert_array_equal(part.shard_of_person, s[c.home_loc])
+
+    check()
