@@ -189,7 +189,7 @@ def keyed_seeds(city, seed, n):
     return np.sort(order[:n]).astype(np.int32)
 
 
-def _replication_worker(w, args, props, city, total, barrier, times, infections):
+def _replication_worker(w, args, props, city, total, barrier, times, infections, gen_times=None):
     """One replication (seed SEED + w) of the oracle in its own process; every day's stays are generated untimed, then
     all replications run their day side by side between two barriers."""
     from heros_b200 import scenario
@@ -199,7 +199,10 @@ def _replication_worker(w, args, props, city, total, barrier, times, infections)
     sim.expose(seeds, np.zeros(len(seeds)))
     gen = scenario.ScheduleGenerator(city, seed)
     for d in range(total):
+        tg = time.perf_counter()
         st = gen.generate_day(sim.agent_state()["phase"])
+        if gen_times is not None:
+            gen_times[w * total + d] = time.perf_counter() - tg   # the activity engine's share (numpy stand-in for medlabs)
         barrier.wait(timeout=900)                                  # a replication that died breaks the barrier for all
         times[2 * (w * total + d)] = time.perf_counter()          # CLOCK_MONOTONIC: one clock for all processes
         sim.add_visits(st["person"], st["loc"], st["sub"], st["t_in"], st["t_out"])
@@ -278,7 +281,8 @@ def run_reference(args):
     barrier = ctx.Barrier(workers)
     times = ctx.Array("d", 2 * workers * total, lock=False)       # start / end of every (replication, day)
     infected = ctx.Array("q", workers, lock=False)
-    procs = [ctx.Process(target=_replication_worker, args=(w, args, props, city, total, barrier, times, infected), daemon=True)
+    gen_times = ctx.Array("d", workers * total, lock=False)       # schedule generation of every (replication, day)
+    procs = [ctx.Process(target=_replication_worker, args=(w, args, props, city, total, barrier, times, infected, gen_times), daemon=True)
              for w in range(workers)]
     for p in procs:
         p.start()
@@ -294,6 +298,10 @@ def run_reference(args):
     own = float((t[0, first:, 1] - t[0, first:, 0]).sum())
     one_replication = city.n_persons * 24.0 * args.steps / own
     infections = [int(x) for x in infected[:]]
+    # the same days with every replication's schedule generation counted in (the GPU arm's e2e_device_schedule produces
+    # the stays on the device inside its timed region): per day the slowest generation + the day's run
+    g = np.asarray(gen_times[:]).reshape(workers, total)[:, first:]
+    seconds_with_schedule = float((day_wall + g.max(axis=0)).sum())
     # the same workload description as the GPU arm's at this N (the sample that was timed is one tile of it)
     world = max(int(args.gpus), 1)
     line = {
@@ -304,6 +312,10 @@ def run_reference(args):
         "config": workload_config(args, city, world),
         "cpu_baseline": {"value": value, "unit": "person-hours/s", "cores": workers, "kind": "port",
                          "host_cores": host_cores(),
+                         "with_schedule_generation": {
+                             "value": workers * city.n_persons * 24.0 * args.steps / seconds_with_schedule, "unit": "person-hours/s",
+                             "what": "the same days with the generation of every day's stays timed too (scenario.ScheduleGenerator, "
+                                     "numpy, one per replication) -- what the GPU arm's e2e_device_schedule is to be compared with"},
                          "one_replication": {"value": one_replication, "unit": "person-hours/s", "cores": 1,
                                              "what": "replication 0 alone on its core while the others run beside it"},
                          "sample": f"{args.steps} simulated days (days {first}..{total - 1}) of "
